@@ -1,0 +1,210 @@
+"""Problem definitions (initial data + solver settings) for the configurations named in
+BASELINE.json / SURVEY.md section 8(d), restated from the reference examples:
+
+  advection_2d      pyclaw/examples/advection_2d/advection_2d.py:21-80
+  acoustics_2d      pyclaw/examples/acoustics_2d_homogeneous/acoustics_2d.py:31-99
+  quadrants         pyclaw/examples/euler_2d/quadrants.py:73-115
+  radial_dam_break  pyclaw/examples/shallow_2d/radial_dam_break.py:23-72
+  shock_bubble      synthetic 4-equation Euler shock/bubble (state formulas from
+                    pyclaw/examples/euler_2d/shock_bubble_interaction.py:57-59), point-sampled
+  acoustics_3d      pyclaw/examples/acoustics_3d_variable/acoustics_3d_interface.py:76-125
+
+Each builder returns a plain ``dict`` (no PyClaw objects), so the same definition feeds the
+CUDA solver (via ``make_claw``), the oracle in tests, and bench.py.  Cell centres follow
+``Dimension.centers`` (pyclaw/src/pyclaw/geometry.py:546-553): ``lower + (i+0.5)*delta``.
+"""
+import numpy as np
+
+EXTRAP, PERIODIC, WALL = 1, 2, 3
+MINMOD, SUPERBEE, VANLEER, MC = 1, 2, 3, 4
+
+
+def centers(lower, upper, n):
+    delta = (upper - lower) / float(n)
+    return lower + (np.arange(n) + 0.5) * delta
+
+
+def _grid(lower, upper, n):
+    cs = [centers(lo, up, k) for lo, up, k in zip(lower, upper, n)]
+    return np.meshgrid(*cs, indexing='ij')
+
+
+def _base(rp, lower, upper, n, q, **kw):
+    d = dict(rp=rp, lower=list(map(float, lower)), upper=list(map(float, upper)), num_cells=list(map(int, n)),
+             q=np.asfortranarray(q), aux=None, problem_data={}, limiters=MINMOD, order=2,
+             dimensional_split=True, transverse_waves=None, cfl_max=1.0, cfl_desired=0.9,
+             dt_initial=0.1, bc_lower=None, bc_upper=None, aux_bc_lower=None, aux_bc_upper=None,
+             tfinal=1.0, num_output_times=10)
+    d.update(kw)
+    return d
+
+
+def advection_2d(mx=50, my=50, dimensional_split=True, transverse_waves=0):
+    X, Y = _grid((0., 0.), (1., 1.), (mx, my))
+    q = np.empty((1, mx, my), order='F')
+    q[0] = 0.9 * (0.1 < X) * (X < 0.6) * (0.1 < Y) * (Y < 0.6) + 0.1
+    no_trans = (not dimensional_split) and (not transverse_waves)
+    return _base('advection_2D', (0., 0.), (1., 1.), (mx, my), q,
+                 problem_data={'u': 0.5, 'v': 1.0}, limiters=VANLEER,
+                 dimensional_split=bool(dimensional_split), transverse_waves=int(transverse_waves),
+                 cfl_max=0.5 if no_trans else 1.0, cfl_desired=0.45 if no_trans else 0.9,
+                 bc_lower=[PERIODIC, PERIODIC], bc_upper=[PERIODIC, PERIODIC], tfinal=2.0)
+
+
+def acoustics_2d(mx=100, my=100, tfinal=0.12, num_output_times=10):
+    X, Y = _grid((-1., -1.), (1., 1.), (mx, my))
+    r = np.sqrt(X ** 2 + Y ** 2)
+    width = 0.2
+    q = np.zeros((3, mx, my), order='F')
+    q[0] = (np.abs(r - 0.5) <= width) * (1. + np.cos(np.pi * (r - 0.5) / width))
+    rho, bulk = 1.0, 4.0
+    cc = np.sqrt(bulk / rho)
+    zz = rho * cc
+    delta = [2.0 / mx, 2.0 / my]
+    return _base('acoustics_2D', (-1., -1.), (1., 1.), (mx, my), q,
+                 problem_data={'rho': rho, 'bulk': bulk, 'zz': zz, 'cc': cc}, limiters=MC,
+                 dimensional_split=True, cfl_max=0.5, cfl_desired=0.45,
+                 dt_initial=np.min(delta) / cc * 0.45,
+                 bc_lower=[EXTRAP, EXTRAP], bc_upper=[EXTRAP, EXTRAP], tfinal=tfinal,
+                 num_output_times=num_output_times)
+
+
+def quadrants(mx=100, my=100, tfinal=0.8):
+    xx, yy = _grid((0., 0.), (1., 1.), (mx, my))
+    gamma = 1.4
+    l = xx < 0.8
+    r = xx >= 0.8
+    b = yy < 0.8
+    t = yy >= 0.8
+    q = np.empty((4, mx, my), order='F')
+    q[0] = 1.5 * r * t + 0.532258064516129 * l * t + 0.137992831541219 * l * b + 0.532258064516129 * r * b
+    u = 0.0 * r * t + 1.206045378311055 * l * t + 1.206045378311055 * l * b + 0.0 * r * b
+    v = 0.0 * r * t + 0.0 * l * t + 1.206045378311055 * l * b + 1.206045378311055 * r * b
+    p = 1.5 * r * t + 0.3 * l * t + 0.029032258064516 * l * b + 0.3 * r * b
+    q[1] = q[0] * u
+    q[2] = q[0] * v
+    q[3] = 0.5 * q[0] * (u ** 2 + v ** 2) + p / (gamma - 1.0)
+    # quadrants.py sets transverse_waves=2 but leaves dimensional_split at its default True
+    return _base('euler_4wave_2D', (0., 0.), (1., 1.), (mx, my), q, problem_data={'gamma': gamma},
+                 limiters=MINMOD, dimensional_split=True, transverse_waves=2,
+                 bc_lower=[EXTRAP, EXTRAP], bc_upper=[EXTRAP, EXTRAP], tfinal=tfinal)
+
+
+def radial_dam_break(mx=150, my=150, tfinal=2.5):
+    X, Y = _grid((-2.5, -2.5), (2.5, 2.5), (mx, my))
+    r = np.sqrt((X - 0.) ** 2 + (Y - 0.) ** 2)
+    q = np.zeros((3, mx, my), order='F')
+    q[0] = 2. * (r <= 0.5) + 1. * (r > 0.5)
+    return _base('shallow_roe_with_efix_2D', (-2.5, -2.5), (2.5, 2.5), (mx, my), q,
+                 problem_data={'grav': 1.0}, limiters=MC, dimensional_split=True,
+                 bc_lower=[EXTRAP, EXTRAP], bc_upper=[WALL, WALL], tfinal=tfinal)
+
+
+def shock_bubble(mx=8192, my=8192, ly=1.0, y_offset=0.0, ly_total=None, dimensional_split=False,
+                 transverse_waves=2, tfinal=0.02):
+    """BASELINE configs 2/5: 4-equation Euler, planar Mach shock at x=0.2 hitting a low-density
+    bubble; unsplit with transverse corrections, MC limiter, extrapolation BCs, dt_initial=0.1 so
+    the first step is a deliberate reject.  ``ly``/``y_offset``/``ly_total`` describe a y-slab of a
+    taller weak-scaling domain (bubble centred in the full domain)."""
+    gamma = 1.4
+    gamma1 = gamma - 1.
+    if ly_total is None:
+        ly_total = ly
+    x = centers(0., 1., mx)
+    y = centers(y_offset, y_offset + ly, my)
+    X, Y = np.meshgrid(x, y, indexing='ij')
+    pinf = 5.
+    rinf = (gamma1 + pinf * (gamma + 1.)) / ((gamma + 1.) + gamma1 * pinf)
+    vinf = 1. / np.sqrt(gamma) * (pinf - 1.) / np.sqrt(0.5 * ((gamma + 1.) / gamma) * pinf + 0.5 * gamma1 / gamma)
+    einf = 0.5 * rinf * vinf ** 2 + pinf / gamma1
+    rr = np.sqrt((X - 0.5) ** 2 + (Y - 0.5 * ly_total) ** 2)
+    shocked = X < 0.2
+    bubble = rr <= 0.2
+    rho = np.where(shocked, rinf, np.where(bubble, 0.1, 1.0))
+    q = np.empty((4, mx, my), order='F')
+    q[0] = rho
+    q[1] = np.where(shocked, rinf * vinf, 0.0)
+    q[2] = 0.0
+    q[3] = np.where(shocked, einf, 1.0 / gamma1)
+    return _base('euler_4wave_2D', (0., y_offset), (1., y_offset + ly), (mx, my), q,
+                 problem_data={'gamma': gamma}, limiters=MC, dimensional_split=bool(dimensional_split),
+                 transverse_waves=int(transverse_waves), cfl_max=1.0, cfl_desired=0.9, dt_initial=0.1,
+                 bc_lower=[EXTRAP, EXTRAP], bc_upper=[EXTRAP, EXTRAP], tfinal=tfinal)
+
+
+def acoustics_3d(mx=32, my=32, mz=32, heterogeneous=True, dimensional_split=False, transverse_waves=22,
+                 periodic=False, tfinal=0.2, num_output_times=2):
+    """acoustics_3d_interface.py:76-125, problem='heterogeneous' (interface at x=0) or homogeneous."""
+    X, Y, Z = _grid((-1., -1., -1.), (1., 1., 1.), (mx, my, mz))
+    aux = np.empty((2, mx, my, mz), order='F')
+    if heterogeneous:
+        zr, cr, zl, cl = 1.0, 1.0, 2.0, 2.0
+        aux[0] = zl * (X < 0.) + zr * (X >= 0.)
+        aux[1] = cl * (X < 0.) + cr * (X >= 0.)
+        x0, y0, z0 = -0.5, 0.0, 0.0
+        r = np.sqrt((X - x0) ** 2 + (Y - y0) ** 2 + (Z - z0) ** 2)
+        width = 0.1
+        p0 = (np.abs(r - 0.3) <= width) * (1. + np.cos(np.pi * (r - 0.3) / width))
+    else:
+        aux[0] = 1.0
+        aux[1] = 1.0
+        x0 = -0.5
+        p0 = np.exp(-80. * (X - x0) ** 2)
+    q = np.zeros((4, mx, my, mz), order='F')
+    q[0] = p0
+    if periodic:
+        lo = [PERIODIC] * 3
+        up = [PERIODIC] * 3
+    else:
+        lo = [WALL, WALL, WALL] if heterogeneous else [PERIODIC] * 3
+        up = [EXTRAP, EXTRAP, EXTRAP] if heterogeneous else [PERIODIC] * 3
+    return _base('vc_acoustics_3D', (-1., -1., -1.), (1., 1., 1.), (mx, my, mz), q, aux=np.asfortranarray(aux),
+                 limiters=MC, dimensional_split=bool(dimensional_split), transverse_waves=int(transverse_waves),
+                 cfl_max=1.0, cfl_desired=0.9, dt_initial=0.1,
+                 bc_lower=lo, bc_upper=up, aux_bc_lower=lo, aux_bc_upper=up,
+                 tfinal=tfinal, num_output_times=num_output_times)
+
+
+def make_claw(sc, kernel_language='CUDA', pyclaw=None, **solver_kw):
+    """Build a PyClaw-API Controller (solver + solution) from a scenario dict."""
+    if pyclaw is None:
+        from clawpack_b200 import pyclaw
+    from clawpack_b200 import riemann
+    ndim = len(sc['num_cells'])
+    Solver = pyclaw.ClawSolver2D if ndim == 2 else pyclaw.ClawSolver3D
+    solver = Solver(getattr(riemann, sc['rp']))
+    solver.kernel_language = kernel_language
+    solver.limiters = sc['limiters']
+    solver.order = sc['order']
+    solver.dimensional_split = sc['dimensional_split']
+    if sc['transverse_waves'] is not None:
+        solver.transverse_waves = sc['transverse_waves']
+    solver.cfl_max = sc['cfl_max']
+    solver.cfl_desired = sc['cfl_desired']
+    solver.dt_initial = sc['dt_initial']
+    for i in range(ndim):
+        solver.bc_lower[i] = sc['bc_lower'][i]
+        solver.bc_upper[i] = sc['bc_upper'][i]
+        if sc['aux'] is not None:
+            solver.aux_bc_lower[i] = sc['aux_bc_lower'][i]
+            solver.aux_bc_upper[i] = sc['aux_bc_upper'][i]
+    for k, v in solver_kw.items():
+        setattr(solver, k, v)
+    names = ['x', 'y', 'z'][:ndim]
+    dims = [pyclaw.Dimension(lo, up, n, name=nm)
+            for lo, up, n, nm in zip(sc['lower'], sc['upper'], sc['num_cells'], names)]
+    domain = pyclaw.Domain(dims)
+    num_aux = 0 if sc['aux'] is None else sc['aux'].shape[0]
+    state = pyclaw.State(domain, sc['q'].shape[0], num_aux)
+    state.q[...] = sc['q']
+    if num_aux:
+        state.aux[...] = sc['aux']
+    state.problem_data.update(sc['problem_data'])
+    claw = pyclaw.Controller()
+    claw.tfinal = sc['tfinal']
+    claw.num_output_times = sc['num_output_times']
+    claw.solution = pyclaw.Solution(state, domain)
+    claw.solver = solver
+    claw.output_format = None
+    claw.keep_copy = True
+    return claw

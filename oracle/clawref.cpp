@@ -1,0 +1,151 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see clawref2.hpp header).  C entry points for ctypes.
+//
+// build:  make -C oracle        (g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC)
+#include "clawref2.hpp"
+#ifdef CLAWREF_WITH_3D
+#include "clawref3.hpp"
+#endif
+
+#include <cstdint>
+#include <cstring>
+
+namespace clawref {
+
+// ---------------------------------------------------------------------
+// Counting scalar: every arithmetic operator bumps a thread-local tally so that one
+// oracle step yields the exact operation mix of the reference algorithm.
+// ---------------------------------------------------------------------
+struct OpTally { uint64_t add, mul, div, sqrt, cmp, abs; };
+static thread_local OpTally g_tally;
+
+struct Counted {
+  double v;
+  Counted() : v(0.0) {}
+  explicit Counted(double x) : v(x) {}
+};
+inline Counted operator+(Counted a, Counted b) { ++g_tally.add; return Counted(a.v + b.v); }
+inline Counted operator-(Counted a, Counted b) { ++g_tally.add; return Counted(a.v - b.v); }
+inline Counted operator*(Counted a, Counted b) { ++g_tally.mul; return Counted(a.v * b.v); }
+inline Counted operator/(Counted a, Counted b) { ++g_tally.div; return Counted(a.v / b.v); }
+inline Counted operator-(Counted a) { return Counted(-a.v); }
+inline bool operator>(Counted a, Counted b) { ++g_tally.cmp; return a.v > b.v; }
+inline bool operator<(Counted a, Counted b) { ++g_tally.cmp; return a.v < b.v; }
+inline bool operator>=(Counted a, Counted b) { ++g_tally.cmp; return a.v >= b.v; }
+inline bool operator<=(Counted a, Counted b) { ++g_tally.cmp; return a.v <= b.v; }
+inline bool operator==(Counted a, Counted b) { ++g_tally.cmp; return a.v == b.v; }
+inline Counted r_sqrt(Counted x) { ++g_tally.sqrt; return Counted(std::sqrt(x.v)); }
+inline Counted r_abs(Counted x) { ++g_tally.abs; return Counted(std::fabs(x.v)); }
+inline Counted r_max(Counted a, Counted b) { ++g_tally.cmp; return (b.v > a.v) ? b : a; }
+inline Counted r_min(Counted a, Counted b) { ++g_tally.cmp; return (b.v < a.v) ? b : a; }
+inline Counted r_sign1(Counted s) { return Counted(std::copysign(1.0, s.v)); }
+
+}  // namespace clawref
+
+using namespace clawref;
+
+extern "C" {
+
+// qnew,cfl = step2(maxm,num_ghost,mx,my,qold,qnew,aux,dx,dy,dt,method,mthlim,...,use_fwave,rpn2,rpt2)
+// (f2py signature of pyclaw/src/pyclaw/classic/step2.f90:2-5).  The (rpn2,rpt2) C-pointer pair is
+// replaced by rp_id + cparam (the COMMON /cparam/ contents in declaration order).
+int clawref_step2(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int mx, int my,
+                  double* qold, double* qnew, double* aux, double dx, double dy, double dt,
+                  const int* method, const int* mthlim, double* cfl, int use_fwave,
+                  int rp_id, const double* cparam, int nthreads) {
+  return step2<double>(maxm, num_eqn, num_waves, num_aux, num_ghost, mx, my, qold, qnew, aux, dx, dy, dt,
+                       method, mthlim, cfl, use_fwave != 0, rp_id, cparam, nthreads);
+}
+
+int clawref_step2ds(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int mx, int my,
+                    double* qold, double* qnew, double* aux, double dx, double dy, double dt,
+                    const int* method, const int* mthlim, double* cfl, int ids, int use_fwave,
+                    int rp_id, const double* cparam, int nthreads) {
+  return step2ds<double>(maxm, num_eqn, num_waves, num_aux, num_ghost, mx, my, qold, qnew, aux, dx, dy, dt,
+                         method, mthlim, cfl, ids, use_fwave != 0, rp_id, cparam, nthreads);
+}
+
+#ifdef CLAWREF_WITH_3D
+int clawref_step3(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int mx, int my, int mz,
+                  double* qold, double* qnew, double* aux, double dx, double dy, double dz, double dt,
+                  const int* method, const int* mthlim, double* cfl, int use_fwave,
+                  int rp_id, const double* cparam, int nthreads) {
+  return step3<double>(maxm, num_eqn, num_waves, num_aux, num_ghost, mx, my, mz, qold, qnew, aux, dx, dy, dz, dt,
+                       method, mthlim, cfl, use_fwave != 0, rp_id, cparam, nthreads);
+}
+
+int clawref_step3ds(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int mx, int my, int mz,
+                    double* qold, double* qnew, double* aux, double dx, double dy, double dz, double dt,
+                    const int* method, const int* mthlim, double* cfl, int idir, int use_fwave,
+                    int rp_id, const double* cparam, int nthreads) {
+  return step3ds<double>(maxm, num_eqn, num_waves, num_aux, num_ghost, mx, my, mz, qold, qnew, aux, dx, dy, dz, dt,
+                         method, mthlim, cfl, idir, use_fwave != 0, rp_id, cparam, nthreads);
+}
+
+#endif
+
+// Operation counts of ONE hyperbolic step on the given data (serial, counting scalar).
+// split != 0: step2ds(ids=1) then step2ds(ids=2) aliased, as classic/solver.py:527-535.
+// counts[6] = add(+,-), mul, div, sqrt, compare/min/max, abs
+int clawref_count_ops2(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int mx, int my,
+                       const double* qbc, const double* aux, double dx, double dy, double dt,
+                       const int* method, const int* mthlim, int split, int use_fwave,
+                       int rp_id, const double* cparam, uint64_t* counts) {
+  const size_t ncell = (size_t)(mx + 2 * num_ghost) * (my + 2 * num_ghost);
+  std::vector<Counted> qold(ncell * num_eqn), qnew(ncell * num_eqn), ax(ncell * (num_aux > 0 ? num_aux : 1));
+  for (size_t k = 0; k < ncell * num_eqn; ++k) { qold[k] = Counted(qbc[k]); qnew[k] = Counted(qbc[k]); }
+  if (num_aux > 0) for (size_t k = 0; k < ncell * num_aux; ++k) ax[k] = Counted(aux[k]);
+  std::memset(&g_tally, 0, sizeof(g_tally));
+  Counted cfl; int rc;
+  if (split) {
+    rc = step2ds<Counted>(maxm, num_eqn, num_waves, num_aux, num_ghost, mx, my, qold.data(), qnew.data(), ax.data(),
+                          Counted(dx), Counted(dy), Counted(dt), method, mthlim, &cfl, 1, use_fwave != 0, rp_id, cparam, 1);
+    if (rc == 0)
+      rc = step2ds<Counted>(maxm, num_eqn, num_waves, num_aux, num_ghost, mx, my, qnew.data(), qnew.data(), ax.data(),
+                            Counted(dx), Counted(dy), Counted(dt), method, mthlim, &cfl, 2, use_fwave != 0, rp_id, cparam, 1);
+  } else {
+    rc = step2<Counted>(maxm, num_eqn, num_waves, num_aux, num_ghost, mx, my, qold.data(), qnew.data(), ax.data(),
+                        Counted(dx), Counted(dy), Counted(dt), method, mthlim, &cfl, use_fwave != 0, rp_id, cparam, 1);
+  }
+  counts[0] = g_tally.add; counts[1] = g_tally.mul; counts[2] = g_tally.div;
+  counts[3] = g_tally.sqrt; counts[4] = g_tally.cmp; counts[5] = g_tally.abs;
+  return rc;
+}
+
+#ifdef CLAWREF_WITH_3D
+int clawref_count_ops3(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int mx, int my, int mz,
+                       const double* qbc, const double* aux, double dx, double dy, double dz, double dt,
+                       const int* method, const int* mthlim, int split, int use_fwave,
+                       int rp_id, const double* cparam, uint64_t* counts) {
+  const size_t ncell = (size_t)(mx + 2 * num_ghost) * (my + 2 * num_ghost) * (mz + 2 * num_ghost);
+  std::vector<Counted> qold(ncell * num_eqn), qnew(ncell * num_eqn), ax(ncell * (num_aux > 0 ? num_aux : 1));
+  for (size_t k = 0; k < ncell * num_eqn; ++k) { qold[k] = Counted(qbc[k]); qnew[k] = Counted(qbc[k]); }
+  if (num_aux > 0) for (size_t k = 0; k < ncell * num_aux; ++k) ax[k] = Counted(aux[k]);
+  std::memset(&g_tally, 0, sizeof(g_tally));
+  Counted cfl; int rc = 0;
+  if (split) {
+    for (int idir = 1; idir <= 3 && rc == 0; ++idir)
+      rc = step3ds<Counted>(maxm, num_eqn, num_waves, num_aux, num_ghost, mx, my, mz,
+                            idir == 1 ? qold.data() : qnew.data(), qnew.data(), ax.data(),
+                            Counted(dx), Counted(dy), Counted(dz), Counted(dt), method, mthlim, &cfl, idir,
+                            use_fwave != 0, rp_id, cparam, 1);
+  } else {
+    rc = step3<Counted>(maxm, num_eqn, num_waves, num_aux, num_ghost, mx, my, mz, qold.data(), qnew.data(), ax.data(),
+                        Counted(dx), Counted(dy), Counted(dz), Counted(dt), method, mthlim, &cfl, use_fwave != 0,
+                        rp_id, cparam, 1);
+  }
+  counts[0] = g_tally.add; counts[1] = g_tally.mul; counts[2] = g_tally.div;
+  counts[3] = g_tally.sqrt; counts[4] = g_tally.cmp; counts[5] = g_tally.abs;
+  return rc;
+}
+
+#endif
+
+int clawref_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+}  // extern "C"

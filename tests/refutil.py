@@ -1,0 +1,38 @@
+"""Test helpers: build the ORACLE twin (oracle/pyclaw_ref.RefSolver) of a scenario dict."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import pyclaw_ref  # noqa: E402
+
+
+def ref_solver(sc, nthreads=1):
+    ndim = len(sc['num_cells'])
+    num_aux = 0 if sc['aux'] is None else sc['aux'].shape[0]
+    s = pyclaw_ref.RefSolver(sc['rp'], ndim, sc['problem_data'], num_aux=num_aux)
+    s.limiters = sc['limiters']
+    s.order = sc['order']
+    s.dimensional_split = sc['dimensional_split']
+    if sc['transverse_waves'] is not None:
+        s.transverse_waves = sc['transverse_waves']
+    s.cfl_max = sc['cfl_max']
+    s.cfl_desired = sc['cfl_desired']
+    s.dt_initial = sc['dt_initial']
+    s.bc_lower = list(sc['bc_lower'])
+    s.bc_upper = list(sc['bc_upper'])
+    if num_aux:
+        s.aux_bc_lower = list(sc['aux_bc_lower'])
+        s.aux_bc_upper = list(sc['aux_bc_upper'])
+    s.nthreads = nthreads
+    delta = [(u - l) / float(n) for l, u, n in zip(sc['lower'], sc['upper'], sc['num_cells'])]
+    s.setup(sc['q'], sc['aux'], delta)
+    return s
+
+
+def goldens():
+    return np.load(os.path.join(ROOT, 'tests', 'golden', 'reference_goldens.npz'))
