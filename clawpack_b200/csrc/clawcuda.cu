@@ -1,0 +1,763 @@
+// libclawcuda.so -- C ABI (include/clawcuda.h) over the fused sm_100a sweep kernels.
+//
+// Device data layout (2-D): structure-of-arrays planes, q[m][J][I] with I fastest, row pitch
+// padded to a multiple of 16 doubles, ghost cells included (array coords I in [0, mx+4)).
+// Two q buffers are ping-ponged: a step reads `cur`, writes the interior of `alt`; accept
+// swaps them, reject keeps `cur` (this replaces PyClaw's q_backup copy, solver.py:611,645, and
+// the qold = qbc.copy of classic/solver.py:514).
+#include "../../include/clawcuda.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "launch.h"
+
+using namespace clawcuda;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct Dev2 {  // geometry of the device arrays
+  int ndim = 2;
+  int n[3] = {1, 1, 1};      // interior cells
+  int ng = 2;
+  int nt[3] = {1, 1, 1};     // with ghosts
+  int pitch = 0;             // row pitch (doubles)
+  long long plane = 0;       // doubles per component plane
+};
+
+}  // namespace
+
+struct claw_solver {
+  Dev2 g;
+  int rp_id = 0, meqn = 0, mwaves = 0, maux = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  double* q[2] = {nullptr, nullptr};
+  double* aux = nullptr;
+  double* work = nullptr;    // [0..8): CFL slot + scratch; [8..): AoS staging
+  bool owns_buffers = false;
+  int cur = 0;
+  size_t q_elems = 0, aux_elems = 0, work_elems = 0;
+  double cparam[4] = {0, 0, 0, 0};
+  int method[7] = {1, 2, -1, 0, 0, 0, 0};
+  int mthlim[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int use_fwave = 0;
+  int bc_lower[3] = {1, 1, 1}, bc_upper[3] = {1, 1, 1};
+  int aux_bc_lower[3] = {1, 1, 1}, aux_bc_upper[3] = {1, 1, 1};
+  int reflect_index[3] = {1, 2, 3};
+  int on_lower[3] = {1, 1, 1}, on_upper[3] = {1, 1, 1};
+  int mode = CLAW_MODE_STRICT;
+  int seg_rows = 0;
+  double* h_cfl = nullptr;   // pinned
+  cudaEvent_t ev_cfl = nullptr;
+  uint64_t launches = 0;
+  LaunchInfo last_launch{};
+  std::string err;
+};
+
+namespace {
+
+int fail(claw_solver* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  if (h) h->err = buf;
+  return code;
+}
+
+#define CK(h, call)                                                                          \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return fail(h, 100 + (int)e__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                  __FILE__, __LINE__);                                                       \
+  } while (0)
+
+constexpr int WORK_HDR = 8;  // doubles reserved at the start of `work` (CFL slot)
+
+// ---------------------------------------------------------------------------------------
+// layout conversion: host/staging AoS (m fastest, Fortran order) <-> device SoA planes
+// region [i0,i1) x [j0,j1) of the ghosted array; staging holds exactly that region.
+// ---------------------------------------------------------------------------------------
+__global__ void aos_to_soa2(const double* __restrict__ aos, double* __restrict__ soa, int ncomp, int i0, int i1,
+                            int j0, int j1, int pitch, long long plane) {
+  const int w = i1 - i0;
+  const long long ncell = (long long)w * (j1 - j0);
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncell;
+       c += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(c % w), j = (int)(c / w);
+    const double* src = aos + c * ncomp;
+    double* dst = soa + (long long)(j0 + j) * pitch + (i0 + i);
+    for (int m = 0; m < ncomp; ++m) dst[m * plane] = src[m];
+  }
+}
+
+__global__ void soa_to_aos2(const double* __restrict__ soa, double* __restrict__ aos, int ncomp, int i0, int i1,
+                            int j0, int j1, int pitch, long long plane) {
+  const int w = i1 - i0;
+  const long long ncell = (long long)w * (j1 - j0);
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncell;
+       c += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(c % w), j = (int)(c / w);
+    const double* src = soa + (long long)(j0 + j) * pitch + (i0 + i);
+    double* dst = aos + c * ncomp;
+    for (int m = 0; m < ncomp; ++m) dst[m] = src[m * plane];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// ghost fill -- Solver._bc_lower/_bc_upper (pyclaw/src/pyclaw/solver.py:439-519), 2-D.
+// x strips first (all rows, ghost rows included), then y strips (all columns, x-ghosts
+// included), so corners are the composition x-then-y exactly as the numpy slicing does.
+// reflect < 0: no negation (aux arrays / non-wall).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void bc_fill_pair(double* base, long long stride, int n, int lo_type, int up_type,
+                                             bool lo_on, bool up_on, bool negate) {
+  // base[k*stride], k in [0, n+4): cells along the BC dimension
+  if (lo_on) {
+    if (lo_type == CLAW_BC_EXTRAP) {
+      const double v = base[2 * stride];
+      base[0] = v; base[stride] = v;
+    } else if (lo_type == CLAW_BC_PERIODIC) {
+      if (up_on) { base[0] = base[(long long)n * stride]; base[stride] = base[(long long)(n + 1) * stride]; }
+    } else if (lo_type == CLAW_BC_WALL) {
+      const double v3 = base[3 * stride], v2 = base[2 * stride];
+      base[0] = negate ? -v3 : v3; base[stride] = negate ? -v2 : v2;
+    }
+  }
+  if (up_on) {
+    if (up_type == CLAW_BC_EXTRAP) {
+      const double v = base[(long long)(n + 1) * stride];
+      base[(long long)(n + 2) * stride] = v; base[(long long)(n + 3) * stride] = v;
+    } else if (up_type == CLAW_BC_PERIODIC) {
+      if (lo_on) { base[(long long)(n + 2) * stride] = base[2 * stride]; base[(long long)(n + 3) * stride] = base[3 * stride]; }
+    } else if (up_type == CLAW_BC_WALL) {
+      const double vn1 = base[(long long)(n + 1) * stride], vn = base[(long long)n * stride];
+      base[(long long)(n + 2) * stride] = negate ? -vn1 : vn1; base[(long long)(n + 3) * stride] = negate ? -vn : vn;
+    }
+  }
+}
+
+__global__ void bc_x2(double* q, int ncomp, int mx, int ny, int pitch, long long plane, int lo_type, int up_type,
+                      int lo_on, int up_on, int reflect) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ny * ncomp) return;
+  const int j = idx % ny, m = idx / ny;
+  bc_fill_pair(q + m * plane + (long long)j * pitch, 1, mx, lo_type, up_type, lo_on != 0, up_on != 0, m == reflect);
+}
+
+__global__ void bc_y2(double* q, int ncomp, int nx, int my, int pitch, long long plane, int lo_type, int up_type,
+                      int lo_on, int up_on, int reflect) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nx * ncomp) return;
+  const int i = idx % nx, m = idx / nx;
+  bc_fill_pair(q + m * plane + i, pitch, my, lo_type, up_type, lo_on != 0, up_on != 0, m == reflect);
+}
+
+// halo rows [j0, j0+2) x all columns x all components <-> contiguous buffer
+__global__ void halo_pack2(const double* q, double* buf, int ncomp, int nx, int j0, int pitch, long long plane) {
+  const long long n = (long long)ncomp * 2 * nx;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(k % nx);
+    const int r = (int)((k / nx) % 2);
+    const int m = (int)(k / (2LL * nx));
+    buf[k] = q[m * plane + (long long)(j0 + r) * pitch + i];
+  }
+}
+__global__ void halo_unpack2(double* q, const double* buf, int ncomp, int nx, int j0, int pitch, long long plane) {
+  const long long n = (long long)ncomp * 2 * nx;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(k % nx);
+    const int r = (int)((k / nx) % 2);
+    const int m = (int)(k / (2LL * nx));
+    q[m * plane + (long long)(j0 + r) * pitch + i] = buf[k];
+  }
+}
+
+// FP64 issue-rate probe: 8 independent DFMA chains per thread
+__global__ void dfma_probe(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int check_handle(const claw_solver* h) {
+  if (!h) { g_last_error = "null solver handle"; return 1; }
+  return 0;
+}
+
+int ensure_buffers(claw_solver* h) {
+  if (h->q[0]) return 0;
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaMalloc(&h->q[0], h->q_elems * sizeof(double)));
+  CK(h, cudaMalloc(&h->q[1], h->q_elems * sizeof(double)));
+  if (h->aux_elems) CK(h, cudaMalloc(&h->aux, h->aux_elems * sizeof(double)));
+  CK(h, cudaMalloc(&h->work, h->work_elems * sizeof(double)));
+  CK(h, cudaMemsetAsync(h->q[0], 0, h->q_elems * sizeof(double), h->stream));
+  CK(h, cudaMemsetAsync(h->q[1], 0, h->q_elems * sizeof(double), h->stream));
+  h->owns_buffers = true;
+  return 0;
+}
+
+int grid_for(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  if (g > 148LL * 32) g = 148LL * 32;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// copy a region of the ghosted host array (AoS) to / from the device SoA array
+int put_region(claw_solver* h, double* dsoa, int ncomp, const double* host, bool host_has_ghosts) {
+  const Dev2& g = h->g;
+  if (g.ndim != 2) return fail(h, 20, "3-D transfers are not available in this build");
+  if (int rc = ensure_buffers(h)) return rc;
+  double* stage = h->work + WORK_HDR;
+  const int i0 = host_has_ghosts ? 0 : g.ng, i1 = host_has_ghosts ? g.nt[0] : g.ng + g.n[0];
+  const int j0 = host_has_ghosts ? 0 : g.ng, j1 = host_has_ghosts ? g.nt[1] : g.ng + g.n[1];
+  const size_t bytes = (size_t)ncomp * (i1 - i0) * (j1 - j0) * sizeof(double);
+  CK(h, cudaMemcpyAsync(stage, host, bytes, cudaMemcpyHostToDevice, h->stream));
+  const long long ncell = (long long)(i1 - i0) * (j1 - j0);
+  aos_to_soa2<<<grid_for(ncell, 256), 256, 0, h->stream>>>(stage, dsoa, ncomp, i0, i1, j0, j1, g.pitch, g.plane);
+  ++h->launches;
+  CK(h, cudaGetLastError());
+  return 0;
+}
+
+int get_region(claw_solver* h, const double* dsoa, int ncomp, double* host, int i0, int i1, int j0, int j1,
+               size_t host_row_pitch_bytes, size_t host_offset_bytes) {
+  const Dev2& g = h->g;
+  if (g.ndim != 2) return fail(h, 20, "3-D transfers are not available in this build");
+  double* stage = h->work + WORK_HDR;
+  const long long ncell = (long long)(i1 - i0) * (j1 - j0);
+  soa_to_aos2<<<grid_for(ncell, 256), 256, 0, h->stream>>>(dsoa, stage, ncomp, i0, i1, j0, j1, g.pitch, g.plane);
+  ++h->launches;
+  CK(h, cudaGetLastError());
+  const size_t row_bytes = (size_t)ncomp * (i1 - i0) * sizeof(double);
+  CK(h, cudaMemcpy2DAsync((char*)host + host_offset_bytes, host_row_pitch_bytes, stage, row_bytes, row_bytes,
+                          (size_t)(j1 - j0), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int fill_ghosts_array(claw_solver* h, double* arr, int ncomp, const int* lo, const int* up, bool is_q) {
+  const Dev2& g = h->g;
+  if (g.ndim != 2) return fail(h, 20, "3-D ghost fill is not available in this build");
+  for (int d = 0; d < 2; ++d) {
+    if ((h->on_lower[d] && (lo[d] < 1 || lo[d] > 3)) || (h->on_upper[d] && (up[d] < 1 || up[d] > 3)))
+      return fail(h, 21, "boundary condition %d/%d in dimension %d cannot run on the device "
+                         "(BC.custom needs a host round trip)", lo[d], up[d], d);
+  }
+  {
+    // the negation flag is only consulted by the BC.wall branches (solver.py:464-473)
+    const int refl = is_q ? h->reflect_index[0] : -1;
+    const int n = g.nt[1] * ncomp;
+    bc_x2<<<(n + 127) / 128, 128, 0, h->stream>>>(arr, ncomp, g.n[0], g.nt[1], g.pitch, g.plane, lo[0], up[0],
+                                                  h->on_lower[0], h->on_upper[0], refl);
+    ++h->launches;
+  }
+  {
+    const int refl = is_q ? h->reflect_index[1] : -1;
+    const int n = g.nt[0] * ncomp;
+    bc_y2<<<(n + 127) / 128, 128, 0, h->stream>>>(arr, ncomp, g.nt[0], g.n[1], g.pitch, g.plane, lo[1], up[1],
+                                                  h->on_lower[1], h->on_upper[1], refl);
+    ++h->launches;
+  }
+  CK(h, cudaGetLastError());
+  return 0;
+}
+
+int launch_step2(claw_solver* h, double dx, double dy, double dt, int kind, int do_x, int do_y,
+                 const double* src, double* dst) {
+  Sweep2Params P{};
+  P.qin = src;
+  P.qout = dst;
+  P.cfl_bits = reinterpret_cast<unsigned long long*>(h->work);
+  P.mx = h->g.n[0]; P.my = h->g.n[1];
+  P.pitch = h->g.pitch; P.plane = h->g.plane;
+  P.dtdx = dt / dx;                                   // step2.f90:77-78
+  P.dtdy = dt / dy;
+  P.order = h->method[1];
+  P.mtrans = h->method[2];
+  P.limit = 0;
+  for (int mw = 0; mw < h->mwaves; ++mw) { P.mthlim[mw] = h->mthlim[mw]; if (h->mthlim[mw] > 0) P.limit = 1; }
+  P.do_x = do_x; P.do_y = do_y;
+  for (int k = 0; k < 4; ++k) P.rp.p[k] = h->cparam[k];
+  cudaError_t e = (h->mode == CLAW_MODE_FAST)
+                      ? fast::launch_sweep2(h->rp_id, kind, P, h->seg_rows, h->num_sms, h->stream, &h->last_launch)
+                      : strict::launch_sweep2(h->rp_id, kind, P, h->seg_rows, h->num_sms, h->stream, &h->last_launch);
+  ++h->launches;
+  if (e != cudaSuccess) return fail(h, 100 + (int)e, "sweep kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int validate_config(claw_solver* h) {
+  if (h->g.ndim == 2) {
+    if (h->rp_id < 1 || h->rp_id > 4) return fail(h, 30, "rp_id %d is not a 2-D Riemann solver of this build", h->rp_id);
+    if (h->maux != 0 || h->method[5] != 0)
+      return fail(h, 31, "aux arrays / capacity functions are not supported by the 2-D CUDA kernels yet "
+                         "(num_aux=%d, index_capa=%d)", h->maux, h->method[5] - 1);
+    if (h->use_fwave) return fail(h, 32, "f-wave solvers are not supported by the CUDA kernels yet");
+    if (h->method[1] != 1 && h->method[1] != 2) return fail(h, 33, "order must be 1 or 2 (got %d)", h->method[1]);
+    if (h->method[2] < -1 || h->method[2] > 2) return fail(h, 34, "transverse_waves must be 0, 1 or 2 in 2-D (got %d)", h->method[2]);
+    for (int mw = 0; mw < h->mwaves; ++mw)
+      if (h->mthlim[mw] < 0 || h->mthlim[mw] > 5)
+        return fail(h, 35, "limiter id %d of wave family %d is not defined by philim.f90 (0..5)", h->mthlim[mw], mw);
+    return 0;
+  }
+  return fail(h, 20, "3-D stepping is not available in this build");
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+const char* claw_version(void) { return "clawcuda 0.1 (sm_100a)"; }
+
+const char* claw_last_error(const claw_solver* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int claw_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int claw_create(claw_solver** out, int ndim, int rp_id, int meqn, int mwaves, int maux, const int* n, int num_ghost,
+                int device, void* stream) {
+  if (!out) return fail(nullptr, 1, "claw_create: out is NULL");
+  *out = nullptr;
+  if (ndim != 2 && ndim != 3) return fail(nullptr, 2, "claw_create: ndim must be 2 or 3 (got %d)", ndim);
+  if (num_ghost != 2) return fail(nullptr, 3, "claw_create: num_ghost must be 2 (classic solvers), got %d", num_ghost);
+  if (meqn < 1 || meqn > 8 || mwaves < 1 || mwaves > 8 || maux < 0)
+    return fail(nullptr, 4, "claw_create: bad sizes meqn=%d mwaves=%d maux=%d", meqn, mwaves, maux);
+  static const int k_meqn[] = {0, 1, 3, 4, 3, 4}, k_mwaves[] = {0, 1, 2, 4, 3, 2}, k_ndim[] = {0, 2, 2, 2, 2, 3};
+  if (rp_id < 1 || rp_id > 5) return fail(nullptr, 5, "claw_create: unknown rp_id %d", rp_id);
+  if (k_meqn[rp_id] != meqn || k_mwaves[rp_id] != mwaves || k_ndim[rp_id] != ndim)
+    return fail(nullptr, 6, "claw_create: rp_id %d expects ndim=%d meqn=%d mwaves=%d (got %d, %d, %d)", rp_id,
+                k_ndim[rp_id], k_meqn[rp_id], k_mwaves[rp_id], ndim, meqn, mwaves);
+  for (int d = 0; d < ndim; ++d)
+    if (n[d] < 1) return fail(nullptr, 7, "claw_create: n[%d] = %d", d, n[d]);
+  int ndev = claw_device_count();
+  if (ndev == 0) return fail(nullptr, 8, "claw_create: no CUDA device available (the CUDA path has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(nullptr, 9, "claw_create: device %d out of range (%d devices)", device, ndev);
+  claw_solver* h = new claw_solver();
+  h->g.ndim = ndim;
+  for (int d = 0; d < ndim; ++d) { h->g.n[d] = n[d]; h->g.nt[d] = n[d] + 2 * num_ghost; }
+  h->g.ng = num_ghost;
+  h->g.pitch = (h->g.nt[0] + 15) / 16 * 16;
+  long long rows = 1;
+  for (int d = 1; d < ndim; ++d) rows *= h->g.nt[d];
+  h->g.plane = (long long)h->g.pitch * rows;
+  h->rp_id = rp_id; h->meqn = meqn; h->mwaves = mwaves; h->maux = maux;
+  h->device = device;
+  h->stream = (cudaStream_t)stream;
+  h->q_elems = (size_t)h->g.plane * meqn;
+  h->aux_elems = (size_t)h->g.plane * maux;
+  long long cells = 1;
+  for (int d = 0; d < ndim; ++d) cells *= h->g.nt[d];
+  h->work_elems = WORK_HDR + (size_t)cells * (meqn > maux ? meqn : maux);
+  cudaError_t e = cudaSetDevice(device);
+  cudaDeviceProp prop;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+  if (e == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+  if (e == cudaSuccess) e = cudaHostAlloc(&h->h_cfl, 64, cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_cfl, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    int rc = fail(nullptr, 100 + (int)e, "claw_create: %s", cudaGetErrorString(e));
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+int claw_destroy(claw_solver* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  if (h->owns_buffers) {
+    cudaFree(h->q[0]); cudaFree(h->q[1]); cudaFree(h->aux); cudaFree(h->work);
+  }
+  if (h->h_cfl) cudaFreeHost(h->h_cfl);
+  if (h->ev_cfl) cudaEventDestroy(h->ev_cfl);
+  delete h;
+  return 0;
+}
+
+int claw_buffer_sizes(const claw_solver* h, size_t* q_elems, size_t* aux_elems, size_t* work_elems) {
+  if (check_handle(h)) return 1;
+  if (q_elems) *q_elems = h->q_elems;
+  if (aux_elems) *aux_elems = h->aux_elems;
+  if (work_elems) *work_elems = h->work_elems;
+  return 0;
+}
+
+int claw_bind(claw_solver* h, double* d_q0, double* d_q1, double* d_aux, double* d_work) {
+  if (check_handle(h)) return 1;
+  if (h->owns_buffers) return fail(h, 10, "claw_bind: buffers were already allocated internally");
+  if (!d_q0 || !d_q1 || !d_work || (h->maux > 0 && !d_aux)) return fail(h, 11, "claw_bind: NULL buffer");
+  h->q[0] = d_q0; h->q[1] = d_q1; h->aux = d_aux; h->work = d_work;
+  h->cur = 0;
+  return 0;
+}
+
+int claw_set_cparam(claw_solver* h, const double* cparam, int n) {
+  if (check_handle(h)) return 1;
+  if (n < 0 || n > 4) return fail(h, 12, "claw_set_cparam: n=%d (max 4)", n);
+  for (int k = 0; k < n; ++k) h->cparam[k] = cparam[k];
+  return 0;
+}
+
+int claw_set_method(claw_solver* h, const int* method7, const int* mthlim, int use_fwave) {
+  if (check_handle(h)) return 1;
+  for (int k = 0; k < 7; ++k) h->method[k] = method7[k];
+  for (int k = 0; k < h->mwaves; ++k) h->mthlim[k] = mthlim[k];
+  h->use_fwave = use_fwave;
+  return validate_config(h);
+}
+
+int claw_set_bc(claw_solver* h, const int* lower, const int* upper, const int* aux_lower, const int* aux_upper,
+                const int* reflect_index) {
+  if (check_handle(h)) return 1;
+  for (int d = 0; d < h->g.ndim; ++d) {
+    h->bc_lower[d] = lower[d]; h->bc_upper[d] = upper[d];
+    if (aux_lower) h->aux_bc_lower[d] = aux_lower[d];
+    if (aux_upper) h->aux_bc_upper[d] = aux_upper[d];
+    if (reflect_index) h->reflect_index[d] = reflect_index[d];
+  }
+  return 0;
+}
+
+int claw_set_boundary_ownership(claw_solver* h, const int* on_lower, const int* on_upper) {
+  if (check_handle(h)) return 1;
+  for (int d = 0; d < h->g.ndim; ++d) { h->on_lower[d] = on_lower[d]; h->on_upper[d] = on_upper[d]; }
+  return 0;
+}
+
+int claw_set_mode(claw_solver* h, int mode) {
+  if (check_handle(h)) return 1;
+  if (mode != CLAW_MODE_STRICT && mode != CLAW_MODE_FAST) return fail(h, 13, "claw_set_mode: unknown mode %d", mode);
+  h->mode = mode;
+  return 0;
+}
+
+int claw_set_tuning(claw_solver* h, int seg_rows) {
+  if (check_handle(h)) return 1;
+  h->seg_rows = seg_rows < 0 ? 0 : seg_rows;
+  return 0;
+}
+
+int claw_put_q(claw_solver* h, const double* host_q) {
+  if (check_handle(h)) return 1;
+  if (int rc = ensure_buffers(h)) return rc;
+  CK(h, cudaSetDevice(h->device));
+  if (int rc = put_region(h, h->q[h->cur], h->meqn, host_q, false)) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int claw_get_q(claw_solver* h, double* host_q) {
+  if (check_handle(h)) return 1;
+  if (int rc = ensure_buffers(h)) return rc;
+  CK(h, cudaSetDevice(h->device));
+  const Dev2& g = h->g;
+  return get_region(h, h->q[h->cur], h->meqn, host_q, g.ng, g.ng + g.n[0], g.ng, g.ng + g.n[1],
+                    (size_t)h->meqn * g.n[0] * sizeof(double), 0);
+}
+
+int claw_put_aux(claw_solver* h, const double* host_aux) {
+  if (check_handle(h)) return 1;
+  if (h->maux == 0) return 0;
+  if (int rc = ensure_buffers(h)) return rc;
+  CK(h, cudaSetDevice(h->device));
+  if (int rc = put_region(h, h->aux, h->maux, host_aux, false)) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int claw_put_qbc(claw_solver* h, const double* host_qbc) {
+  if (check_handle(h)) return 1;
+  if (int rc = ensure_buffers(h)) return rc;
+  CK(h, cudaSetDevice(h->device));
+  if (int rc = put_region(h, h->q[h->cur], h->meqn, host_qbc, true)) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int claw_get_qbc(claw_solver* h, double* host_qbc) {
+  if (check_handle(h)) return 1;
+  if (int rc = ensure_buffers(h)) return rc;
+  CK(h, cudaSetDevice(h->device));
+  const Dev2& g = h->g;
+  return get_region(h, h->q[h->cur], h->meqn, host_qbc, 0, g.nt[0], 0, g.nt[1],
+                    (size_t)h->meqn * g.nt[0] * sizeof(double), 0);
+}
+
+int claw_put_auxbc(claw_solver* h, const double* host_auxbc) {
+  if (check_handle(h)) return 1;
+  if (h->maux == 0) return 0;
+  if (int rc = ensure_buffers(h)) return rc;
+  CK(h, cudaSetDevice(h->device));
+  if (int rc = put_region(h, h->aux, h->maux, host_auxbc, true)) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int claw_apply_bcs(claw_solver* h) {
+  if (check_handle(h)) return 1;
+  if (int rc = ensure_buffers(h)) return rc;
+  CK(h, cudaSetDevice(h->device));
+  if (h->maux > 0)
+    if (int rc = fill_ghosts_array(h, h->aux, h->maux, h->aux_bc_lower, h->aux_bc_upper, false)) return rc;
+  return fill_ghosts_array(h, h->q[h->cur], h->meqn, h->bc_lower, h->bc_upper, true);
+}
+
+int claw_step_launch(claw_solver* h, const double* delta, double dt, int fill_ghosts) {
+  if (check_handle(h)) return 1;
+  if (int rc = validate_config(h)) return rc;
+  if (int rc = ensure_buffers(h)) return rc;
+  CK(h, cudaSetDevice(h->device));
+  if (fill_ghosts)
+    if (int rc = claw_apply_bcs(h)) return rc;
+  CK(h, cudaMemsetAsync(h->work, 0, sizeof(double), h->stream));
+  const int kind = (h->method[2] < 0) ? 1 : 0;         // method(3) = -1: dimensional splitting (classic/solver.py:186)
+  if (int rc = launch_step2(h, delta[0], delta[1], dt, kind, 1, 1, h->q[h->cur], h->q[h->cur ^ 1])) return rc;
+  CK(h, cudaMemcpyAsync(h->h_cfl, h->work, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaEventRecord(h->ev_cfl, h->stream));
+  return 0;
+}
+
+int claw_cfl_device_ptr(claw_solver* h, void** d_cfl) {
+  if (check_handle(h)) return 1;
+  if (int rc = ensure_buffers(h)) return rc;
+  *d_cfl = h->work;
+  return 0;
+}
+
+int claw_cfl_wait(claw_solver* h, double* cfl) {
+  if (check_handle(h)) return 1;
+  CK(h, cudaEventSynchronize(h->ev_cfl));
+  if (cfl) *cfl = *h->h_cfl;
+  return 0;
+}
+
+int claw_step(claw_solver* h, const double* delta, double dt, int fill_ghosts, double* cfl) {
+  if (int rc = claw_step_launch(h, delta, dt, fill_ghosts)) return rc;
+  return claw_cfl_wait(h, cfl);
+}
+
+int claw_accept(claw_solver* h) {
+  if (check_handle(h)) return 1;
+  h->cur ^= 1;
+  return 0;
+}
+
+int claw_reject(claw_solver* h) {
+  if (check_handle(h)) return 1;
+  return 0;  // `cur` still holds the pre-step state (its ghost cells were refilled, its interior is untouched)
+}
+
+int claw_sync(claw_solver* h) {
+  if (check_handle(h)) return 1;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int claw_halo_elems(const claw_solver* h, size_t* elems) {
+  if (check_handle(h)) return 1;
+  if (h->g.ndim != 2) { g_last_error = "3-D halo exchange is not available in this build"; return 20; }
+  *elems = (size_t)h->meqn * 2 * h->g.nt[0];
+  return 0;
+}
+
+int claw_halo_pack(claw_solver* h, int side, double* d_buf) {
+  if (check_handle(h)) return 1;
+  if (h->g.ndim != 2) return fail(h, 20, "3-D halo exchange is not available in this build");
+  if (int rc = ensure_buffers(h)) return rc;
+  CK(h, cudaSetDevice(h->device));
+  const Dev2& g = h->g;
+  const int j0 = side == 0 ? g.ng : g.n[1];            // interior rows [2,4) or [my, my+2)
+  const long long n = (long long)h->meqn * 2 * g.nt[0];
+  halo_pack2<<<grid_for(n, 256), 256, 0, h->stream>>>(h->q[h->cur], d_buf, h->meqn, g.nt[0], j0, g.pitch, g.plane);
+  ++h->launches;
+  CK(h, cudaGetLastError());
+  return 0;
+}
+
+int claw_halo_unpack(claw_solver* h, int side, const double* d_buf) {
+  if (check_handle(h)) return 1;
+  if (h->g.ndim != 2) return fail(h, 20, "3-D halo exchange is not available in this build");
+  if (int rc = ensure_buffers(h)) return rc;
+  CK(h, cudaSetDevice(h->device));
+  const Dev2& g = h->g;
+  const int j0 = side == 0 ? 0 : g.n[1] + g.ng;        // ghost rows [0,2) or [my+2, my+4)
+  const long long n = (long long)h->meqn * 2 * g.nt[0];
+  halo_unpack2<<<grid_for(n, 256), 256, 0, h->stream>>>(h->q[h->cur], d_buf, h->meqn, g.nt[0], j0, g.pitch, g.plane);
+  ++h->launches;
+  CK(h, cudaGetLastError());
+  return 0;
+}
+
+int claw_launch_count(const claw_solver* h, uint64_t* count) {
+  if (check_handle(h)) return 1;
+  *count = h->launches;
+  return 0;
+}
+
+// ---- f2py-shaped host entry points ---------------------------------------------------------
+namespace {
+std::mutex g_host_mutex;
+claw_solver* g_host = nullptr;
+
+int host_handle(int ndim, int rp_id, int meqn, int mwaves, int maux, const int* n, claw_solver** out) {
+  if (g_host && (g_host->g.ndim != ndim || g_host->rp_id != rp_id || g_host->meqn != meqn || g_host->maux != maux ||
+                 g_host->g.n[0] != n[0] || g_host->g.n[1] != n[1] || (ndim == 3 && g_host->g.n[2] != n[2]))) {
+    claw_destroy(g_host);
+    g_host = nullptr;
+  }
+  if (!g_host) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (int rc = claw_create(&g_host, ndim, rp_id, meqn, mwaves, maux, n, 2, dev, nullptr)) return rc;
+  }
+  *out = g_host;
+  return 0;
+}
+
+int host_fail(claw_solver* h, int rc) {
+  if (h) g_last_error = h->err;
+  return rc;
+}
+}  // namespace
+
+int claw_step2_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, int mx, int my, const double* qold,
+                    double* qnew, const double* aux, double dx, double dy, double dt, const int* method7,
+                    const int* mthlim, int use_fwave, int rp_id, const double* cparam, int ncparam, int mode,
+                    double* cfl) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  if (num_ghost != 2) return fail(nullptr, 3, "claw_step2_host: num_ghost must be 2");
+  if (maxm < mx || maxm < my) return fail(nullptr, 40, "claw_step2_host: maxm=%d < max(mx,my)", maxm);
+  const int n[2] = {mx, my};
+  claw_solver* h = nullptr;
+  if (int rc = host_handle(2, rp_id, meqn, mwaves, maux, n, &h)) return rc;
+  int rc;
+  if ((rc = claw_set_mode(h, mode))) return host_fail(h, rc);
+  if ((rc = claw_set_cparam(h, cparam, ncparam))) return host_fail(h, rc);
+  if ((rc = claw_set_method(h, method7, mthlim, use_fwave))) return host_fail(h, rc);
+  if (h->method[2] < 0) return host_fail(h, fail(h, 41, "claw_step2_host: method(3) = -1 (dimensional splitting) belongs to step2ds"));
+  if ((rc = claw_put_qbc(h, qold))) return host_fail(h, rc);
+  if (maux > 0 && (rc = claw_put_auxbc(h, aux))) return host_fail(h, rc);
+  const double delta[2] = {dx, dy};
+  if ((rc = claw_step(h, delta, dt, 0, cfl))) return host_fail(h, rc);
+  const Dev2& g = h->g;
+  rc = get_region(h, h->q[h->cur ^ 1], meqn, qnew, g.ng, g.ng + mx, g.ng, g.ng + my,
+                  (size_t)meqn * g.nt[0] * sizeof(double),
+                  ((size_t)g.ng * g.nt[0] + g.ng) * meqn * sizeof(double));
+  return rc ? host_fail(h, rc) : 0;
+}
+
+int claw_step2ds_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, int mx, int my, const double* qold,
+                      double* qnew, const double* aux, double dx, double dy, double dt, const int* method7,
+                      const int* mthlim, int ids, int use_fwave, int rp_id, const double* cparam, int ncparam,
+                      int mode, double* cfl) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  if (num_ghost != 2) return fail(nullptr, 3, "claw_step2ds_host: num_ghost must be 2");
+  if (maxm < mx || maxm < my) return fail(nullptr, 40, "claw_step2ds_host: maxm=%d < max(mx,my)", maxm);
+  if (ids != 1 && ids != 2) return fail(nullptr, 42, "claw_step2ds_host: ids must be 1 or 2 (got %d)", ids);
+  const int n[2] = {mx, my};
+  claw_solver* h = nullptr;
+  if (int rc = host_handle(2, rp_id, meqn, mwaves, maux, n, &h)) return rc;
+  int rc;
+  if ((rc = claw_set_mode(h, mode))) return host_fail(h, rc);
+  if ((rc = claw_set_cparam(h, cparam, ncparam))) return host_fail(h, rc);
+  if ((rc = claw_set_method(h, method7, mthlim, use_fwave))) return host_fail(h, rc);
+  if ((rc = claw_put_qbc(h, qold))) return host_fail(h, rc);
+  if (maux > 0 && (rc = claw_put_auxbc(h, aux))) return host_fail(h, rc);
+  if (cudaMemsetAsync(h->work, 0, sizeof(double), h->stream) != cudaSuccess) return fail(nullptr, 43, "memset failed");
+  if ((rc = launch_step2(h, dx, dy, dt, 1, ids == 1, ids == 2, h->q[h->cur], h->q[h->cur ^ 1]))) return host_fail(h, rc);
+  if (cudaMemcpyAsync(h->h_cfl, h->work, sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
+    return fail(nullptr, 43, "cfl copy failed");
+  const Dev2& g = h->g;
+  if (ids == 1)   // rows: all; columns: interior   (step2ds.f90:96,149)
+    rc = get_region(h, h->q[h->cur ^ 1], meqn, qnew, g.ng, g.ng + mx, 0, g.nt[1],
+                    (size_t)meqn * g.nt[0] * sizeof(double), (size_t)g.ng * meqn * sizeof(double));
+  else            // columns: all; rows: interior   (step2ds.f90:180,237)
+    rc = get_region(h, h->q[h->cur ^ 1], meqn, qnew, 0, g.nt[0], g.ng, g.ng + my,
+                    (size_t)meqn * g.nt[0] * sizeof(double), (size_t)g.ng * g.nt[0] * meqn * sizeof(double));
+  if (rc) return host_fail(h, rc);
+  if (cfl) *cfl = *h->h_cfl;    // get_region synchronised the stream
+  return 0;
+}
+
+int claw_step3_host(int, int, int, int, int, int, int, int, const double*, double*, const double*, double, double,
+                    double, double, const int*, const int*, int, int, const double*, int, int, double*) {
+  return fail(nullptr, 20, "claw_step3_host: 3-D stepping is not available in this build");
+}
+
+int claw_step3ds_host(int, int, int, int, int, int, int, int, const double*, double*, const double*, double, double,
+                      double, double, const int*, const int*, int, int, int, const double*, int, int, double*) {
+  return fail(nullptr, 20, "claw_step3ds_host: 3-D stepping is not available in this build");
+}
+
+int claw_host_release(void) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  if (g_host) { claw_destroy(g_host); g_host = nullptr; }
+  return 0;
+}
+
+int claw_host_alloc(void** p, size_t bytes) {
+  cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(nullptr, 100 + (int)e, "claw_host_alloc: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int claw_host_free(void* p) {
+  cudaError_t e = cudaFreeHost(p);
+  if (e != cudaSuccess) return fail(nullptr, 100 + (int)e, "claw_host_free: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int claw_measure_fp64_peak(int device, double* gdfma_per_s) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, 100 + (int)e, "claw_measure_fp64_peak: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  double* d = nullptr;
+  if ((e = cudaMalloc(&d, (size_t)blocks * threads * sizeof(double))) != cudaSuccess)
+    return fail(nullptr, 100 + (int)e, "claw_measure_fp64_peak: %s", cudaGetErrorString(e));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a);
+    dfma_probe<<<blocks, threads>>>(d, iters);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    const double rate = (double)blocks * threads * iters * 8 / (ms * 1e-3) / 1e9;
+    if (rep > 0 && rate > best) best = rate;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  cudaFree(d);
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail(nullptr, 100 + (int)e, "dfma probe: %s", cudaGetErrorString(e));
+  *gdfma_per_s = best;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,581 @@
+// Fused 2-D classic wave-propagation sweep for sm_100a (fp64, no tensor cores: this is a
+// stencil bound by the FP64 pipe).
+//
+// One kernel performs what the reference does in step2.f90 + flux2.f90 + limiter.f90 +
+// philim.f90 + rpn2/rpt2 (unsplit), or in two step2ds.f90 calls (dimension-split):
+// normal Riemann solve, CFL max, wave limiting, second-order correction, transverse
+// propagation and the conservative update, reading q once and writing q once.
+//
+// Decomposition ("strip marching"): a CTA owns a strip of NT-4 interior columns plus a 2-cell
+// halo on either side (one thread per column) and marches through a segment of rows.  At
+// march step J each thread
+//   * loads q(I, J+2) (coalesced, SoA planes),
+//   * solves the y-interface J+2 and finishes y-interface J+1 (its limiter needs the waves of
+//     interfaces J, J+1, J+2: the same thread produced them on consecutive steps, they stay
+//     in registers / thread-private shared-memory slots),
+//   * runs the x-pipeline of row J+1 (neighbouring interfaces live in neighbouring threads:
+//     exchanged through shared memory),
+//   * gathers the six contributions of cell (I, J) in the reference's accumulation order
+//     (step2.f90:139-147 rows j-1, j, j+1; then :221-229 columns i-1, i, i+1) and stores it.
+// The scatter of the reference (each pencil adds into three rows of qnew) becomes a gather,
+// so no atomics and no second pass over q are needed; redundant work is limited to the
+// 4 halo columns per strip and 3-4 warm-up rows per segment.
+//
+// Index convention: array coordinates (I, J) = Fortran (i + 1, j + 1) with num_ghost = 2;
+// interior cells are I in [2, mx+1]; interface I separates cells I-1 and I.
+#pragma once
+#include "rp2.cuh"
+
+namespace clawcuda {
+
+#ifndef CLAWCUDA_SWEEP2_PARAMS
+#define CLAWCUDA_SWEEP2_PARAMS
+struct Sweep2Params {
+  const double* qin;        // SoA: plane m at qin + m*plane, row J at + J*pitch
+  double* qout;
+  unsigned long long* cfl_bits;   // running max of the CFL number (bit pattern of a double >= 0)
+  int mx, my;               // interior cells
+  int pitch;                // row pitch in doubles
+  long long plane;          // plane stride in doubles
+  double dtdx, dtdy;
+  int order;                // method(2)
+  int mtrans;               // method(3): 0, 1, 2 (unsplit kernel)
+  int limit;                // any(mthlim > 0)
+  int mthlim[8];
+  int seg_rows;             // rows per march segment
+  int do_x, do_y;           // split kernel: which sweeps to perform (fused step: both)
+  RpParams rp;
+};
+#endif
+
+namespace CLAW_NS {
+
+__device__ __forceinline__ double philim(double a, double b, int meth) {
+  // philim.f90:14-35
+  const double r = b / a;
+  switch (meth) {
+    case 1: return fmax2(0.0, fmin2(1.0, r));
+    case 2: return fmax2(fmax2(0.0, fmin2(1.0, 2.0 * r)), fmin2(2.0, r));
+    case 3: return (r + fabs(r)) / (1.0 + fabs(r));
+    case 4: { const double c = (1.0 + r) / 2.0; return fmax2(0.0, fmin2(fmin2(c, 2.0), 2.0 * r)); }
+    case 5: return r;
+  }
+  return 0.0;
+}
+
+// natural <-> rotated component index (swap of the two momenta for a y-pencil)
+template <int M> __host__ __device__ constexpr int rot(int m) {
+  return (M >= 3 && m == 1) ? 2 : ((M >= 3 && m == 2) ? 1 : m);
+}
+
+// limiter.f90:33-38: wnorm2 and the dot product with the right/upper neighbour.  The sums run
+// over the components in the reference's NATURAL order (m = 1..meqn) -- for a y-pencil the waves
+// are held in the rotated frame, so the index is mapped back (floating-point sums do not commute
+// across three terms).
+template <class RP, bool ROTATED>
+__device__ __forceinline__ void wave_dots(const double (*wave)[RP::MEQN], const double (*waveR)[RP::MEQN],
+                                          double* wnorm2, double* dotr) {
+#pragma unroll
+  for (int mw = 0; mw < RP::MWAVES; ++mw) {
+    double wn = 0.0, dr = 0.0;
+#pragma unroll
+    for (int mn = 0; mn < RP::MEQN; ++mn) {
+      const int m = ROTATED ? rot<RP::MEQN>(mn) : mn;
+      wn = (mn == 0) ? from0(wave[mw][m] * wave[mw][m]) : wn + wave[mw][m] * wave[mw][m];
+      dr = (mn == 0) ? from0(wave[mw][m] * waveR[mw][m]) : dr + wave[mw][m] * waveR[mw][m];
+    }
+    wnorm2[mw] = wn; dotr[mw] = dr;
+  }
+}
+
+// limiter.f90:39-50 for one interface, given the dot products with both neighbours
+template <class RP>
+__device__ __forceinline__ void limit_waves(const Sweep2Params& P, double (*wave)[RP::MEQN], const double* s,
+                                            const double* wnorm2, const double* dotl, const double* dotr) {
+#pragma unroll
+  for (int mw = 0; mw < RP::MWAVES; ++mw) {
+    const int meth = P.mthlim[mw];
+    if (meth == 0) continue;
+    if (wnorm2[mw] == 0.0) continue;
+    const double wl = philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
+#pragma unroll
+    for (int m = 0; m < RP::MEQN; ++m) wave[mw][m] = wl * wave[mw][m];
+  }
+}
+
+// flux2.f90:134-146 (use_fwave = .false.): cqxx of one interface
+template <class RP>
+__device__ __forceinline__ void second_order(double dtd, const double (*wave)[RP::MEQN], const double* s,
+                                             double* cqxx) {
+  const double dtdxave = 0.5 * (dtd + dtd);
+#pragma unroll
+  for (int m = 0; m < RP::MEQN; ++m) {
+    double c = 0.0;
+#pragma unroll
+    for (int mw = 0; mw < RP::MWAVES; ++mw) {
+      const double t = fabs(s[mw]) * (1.0 - fabs(s[mw]) * dtdxave) * wave[mw][m];
+      c = (mw == 0) ? from0(t) : c + t;
+    }
+    cqxx[m] = c;
+  }
+}
+
+__device__ __forceinline__ void atomic_max_cfl(unsigned long long* addr, double v) {
+  // v >= 0: the IEEE bit patterns of non-negative doubles are ordered like unsigned integers
+  atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+}
+
+template <int NT> __device__ __forceinline__ void block_max_cfl(double cfl, unsigned long long* addr, double* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cfl = fmax(cfl, __shfl_xor_sync(0xffffffffu, cfl, o));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) s_red[warp] = cfl;
+  __syncthreads();
+  if (warp == 0) {
+    double c = (lane < NT / 32) ? s_red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c = fmax(c, __shfl_xor_sync(0xffffffffu, c, o));
+    if (lane == 0 && c > 0.0) atomic_max_cfl(addr, c);
+  }
+}
+
+template <class RP, int NT> struct Smem2 {
+  static constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE;
+  static constexpr int XW = (W * M > 4 * M) ? W * M : 4 * M;
+  // doubles per thread column
+  static constexpr int OFF_Q = 0;               // [M]     q of the x-row (neighbour access)
+  static constexpr int OFF_XW = OFF_Q + M;      // [XW]    x waves, then x outputs (aliased)
+  static constexpr int OFF_DOT = OFF_XW + XW;   // [W]     dotr exchange
+  static constexpr int OFF_GY = OFF_DOT + W;    // [2][2M] y gadd exchange, double-buffered by step parity
+  static constexpr int OFF_YW = OFF_GY + 4 * M; // [W*M]   private: waves of the pending y-interface
+  static constexpr int OFF_YA = OFF_YW + W * M; // [2M+NR+W] private: amdq, apdq, roe, dotl
+  static constexpr int PER_THREAD = OFF_YA + 2 * M + NR + W;
+  static constexpr size_t BYTES = (size_t)PER_THREAD * NT * sizeof(double) + 64 * sizeof(double);
+};
+
+// ---- x-pipeline pieces shared by the unsplit and split kernels ------------------------
+
+// normal solve + (limiter via neighbour exchange) + second-order correction at my left face.
+// On return: wave limited, s, amdq/apdq ORIGINAL fluctuations, cqxx, fadd (= 0.5 cqxx or 0).
+// Contains __syncthreads(): must be called by all threads of the CTA.
+template <class RP, int NT>
+__device__ __forceinline__ void x_face(const Sweep2Params& P, const double* q, int t, int tl, int tr,
+                                       bool second, bool limit, double* sq, double* sxw, double* sdot,
+                                       double (*wave)[RP::MEQN], double* s, double* amdq, double* apdq,
+                                       double* roe, double* cqxx, double* fadd) {
+  constexpr int M = RP::MEQN, W = RP::MWAVES;
+#pragma unroll
+  for (int m = 0; m < M; ++m) sq[m * NT] = q[m];
+  __syncthreads();                                                        // (A)
+  double ql[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) ql[m] = sq[m * NT + tl];
+  RP::normal(P.rp, 0, ql, q, wave, s, amdq, apdq, roe);                  // flux2.f90:101
+#pragma unroll
+  for (int m = 0; m < M; ++m) { cqxx[m] = 0.0; fadd[m] = 0.0; }
+  if (second) {
+    if (limit) {                                                          // flux2.f90:127
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw)
+#pragma unroll
+        for (int m = 0; m < M; ++m) sxw[(mw * M + m) * NT] = wave[mw][m];
+      __syncthreads();                                                    // (B)
+      double wnorm2[W], dotr[W], dotl[W];
+      {
+        double waveR[W][M];
+#pragma unroll
+        for (int mw = 0; mw < W; ++mw)
+#pragma unroll
+          for (int m = 0; m < M; ++m) waveR[mw][m] = sxw[(mw * M + m) * NT + tr];
+        wave_dots<RP, false>(wave, waveR, wnorm2, dotr);
+      }
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw) sdot[mw * NT] = dotr[mw];
+      __syncthreads();                                                    // (C)
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw) dotl[mw] = sdot[mw * NT + tl];
+      limit_waves<RP>(P, wave, s, wnorm2, dotl, dotr);
+    }
+    second_order<RP>(P.dtdx, wave, s, cqxx);                              // flux2.f90:134-146
+#pragma unroll
+    for (int m = 0; m < M; ++m) fadd[m] = 0.0 + 0.5 * cqxx[m];
+  }
+}
+
+// =====================================================================================
+// Unsplit step (step2.f90 semantics), method(3) in {0,1,2}
+// =====================================================================================
+template <class RP, int NT>
+__global__ void __launch_bounds__(NT) sweep2_unsplit(const __grid_constant__ Sweep2Params P) {
+  constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE;
+  using S = Smem2<RP, NT>;
+  constexpr int TX = NT - 4;
+  extern __shared__ double smem[];
+  const int t = threadIdx.x;
+  double* const sq = smem + S::OFF_Q * NT + t;
+  double* const sxw = smem + S::OFF_XW * NT + t;
+  double* const sdot = smem + S::OFF_DOT * NT + t;
+  double* const sgy0 = smem + S::OFF_GY * NT + t;
+  double* const syw = smem + S::OFF_YW * NT + t;
+  double* const sya = smem + S::OFF_YA * NT + t;
+  double* const sred = smem + S::PER_THREAD * NT;
+
+  const int nx = P.mx + 4;
+  const int I = blockIdx.x * TX + t;                       // my column (array coords): 2 + bx*TX - 2 + t
+  const int Ic = I < nx ? I : nx - 1;                      // clamped for loads
+  const int Jb = 2 + blockIdx.y * P.seg_rows;              // first output row
+  const int Je = min(Jb + P.seg_rows, P.my + 2);           // one past the last output row
+  const int tl = t > 0 ? -1 : 0;                           // neighbour offsets (clamped at the strip edge)
+  const int tr = t < NT - 1 ? 1 : 0;
+
+  const double dtdx = P.dtdx, dtdy = P.dtdy;
+  const double hdx = 0.5 * dtdx, hdy = 0.5 * dtdy;
+  const bool second = (P.order != 1);
+  const bool limit = second && (P.limit != 0);
+  const int mt = P.mtrans;
+
+  const double* qcol = P.qin + Ic;
+  double q1[M], qn0[M], qn1[M];
+  double yI_apdq[M], yI_fadd[M], yI_bm[M], yI_bp[M];      // finished y-interface J (rotated frame)
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    q1[m] = qcol[m * P.plane + (long long)(Jb - 2) * P.pitch];
+    qn0[m] = 0.0; qn1[m] = 0.0; yI_apdq[m] = 0.0; yI_fadd[m] = 0.0; yI_bm[m] = 0.0; yI_bp[m] = 0.0;
+  }
+  double cfl = 0.0;
+  const bool x_cfl_col = (t >= 1) && (I >= 2) && (I <= P.mx + 2);
+  const bool y_cfl_col = (I >= 1) && (I <= P.mx + 2);
+  const bool store_col = (t >= 2) && (t <= NT - 3) && (I <= P.mx + 1);
+
+  for (int J = Jb - 3; J < Je; ++J) {
+    double* const sgy = sgy0 + (J & 1) * (2 * M * NT);
+    // ---- load row J+2 ---------------------------------------------------------------
+    double qN[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) qN[m] = qcol[m * P.plane + (long long)(J + 2) * P.pitch];
+
+    // =========================== y-pipeline ==========================================
+    double ycomb[M];                                       // (qadd - dtdy*df) - dtdx*(g2 - g1), natural frame
+#pragma unroll
+    for (int m = 0; m < M; ++m) ycomb[m] = 0.0;
+    {
+      double waveN[W][M], sN[W], amdqN[M], apdqN[M], roeN[NR];
+      {
+        double ql[M], qr[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) { ql[m] = q1[rot<M>(m)]; qr[m] = qN[rot<M>(m)]; }
+        RP::normal(P.rp, 1, ql, qr, waveN, sN, amdqN, apdqN, roeN);
+      }
+      if (y_cfl_col && (J + 2 >= 2) && (J + 2 <= P.my + 2)) {             // flux2.f90:111-119
+#pragma unroll
+        for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtdy * sN[mw]), -dtdy * sN[mw]);
+      }
+      double dotn[W];
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw) dotn[mw] = 0.0;
+      if (J >= Jb - 2) {
+        double waveC[W][M], wnorm2[W];
+#pragma unroll
+        for (int mw = 0; mw < W; ++mw) {
+          wnorm2[mw] = 0.0;
+#pragma unroll
+          for (int m = 0; m < M; ++m) waveC[mw][m] = syw[(mw * M + m) * NT];
+        }
+        if (limit) wave_dots<RP, true>(waveC, waveN, wnorm2, dotn);
+        if (J >= Jb - 1) {
+          double sC[W], amdqC[M], apdqC[M], roeC[NR], dotl[W];
+#pragma unroll
+          for (int m = 0; m < M; ++m) { amdqC[m] = sya[m * NT]; apdqC[m] = sya[(M + m) * NT]; }
+#pragma unroll
+          for (int k = 0; k < NR; ++k) roeC[k] = sya[(2 * M + k) * NT];
+#pragma unroll
+          for (int mw = 0; mw < W; ++mw) dotl[mw] = sya[(2 * M + NR + mw) * NT];
+          RP::speeds(P.rp, 1, roeC, sC);
+          // first-order increment of cell J uses the ORIGINAL fluctuations (flux2.f90:105-108)
+          double qadd[M];
+#pragma unroll
+          for (int m = 0; m < M; ++m) {
+            qadd[m] = (0.0 - dtdy * yI_apdq[m]) - dtdy * amdqC[m];
+            yI_apdq[m] = apdqC[m];                                         // carry: original apdq of interface J+1
+          }
+          double fadd[M];
+#pragma unroll
+          for (int m = 0; m < M; ++m) fadd[m] = 0.0;
+          if (second) {
+            if (limit) limit_waves<RP>(P, waveC, sC, wnorm2, dotl, dotn);
+            double cqxx[M];
+            second_order<RP>(dtdy, waveC, sC, cqxx);
+#pragma unroll
+            for (int m = 0; m < M; ++m) fadd[m] = 0.0 + 0.5 * cqxx[m];
+            if (mt == 2) {                                                 // flux2.f90:167-173
+#pragma unroll
+              for (int m = 0; m < M; ++m) { amdqC[m] = amdqC[m] + cqxx[m]; apdqC[m] = apdqC[m] - cqxx[m]; }
+            }
+          }
+          double bmA[M], bpA[M], bmP[M], bpP[M];
+#pragma unroll
+          for (int m = 0; m < M; ++m) { bmA[m] = 0.0; bpA[m] = 0.0; bmP[m] = 0.0; bpP[m] = 0.0; }
+          if (mt > 0) {
+            RP::transverse(P.rp, 1, roeC, amdqC, bmA, bpA);               // flux2.f90:181
+            RP::transverse(P.rp, 1, roeC, apdqC, bmP, bpP);               // flux2.f90:194
+          }
+          // cell J of this y-pencil: interface J (carried) and interface J+1 (just finished)
+#pragma unroll
+          for (int m = 0; m < M; ++m) {
+            const double g1 = (0.0 - hdy * bmA[m]) - hdy * yI_bm[m];      // flux2.f90:185-203
+            const double g2 = (0.0 - hdy * bpA[m]) - hdy * yI_bp[m];
+            // step2.f90:223-225: qadd - dtdy*(fadd(j+1)-fadd(j)) - dtdx*(gadd(2)-gadd(1))
+            ycomb[rot<M>(m)] = (qadd[m] - dtdy * (fadd[m] - yI_fadd[m])) - dtdx * (g2 - g1);
+            sgy[rot<M>(m) * NT] = g1;
+            sgy[(M + rot<M>(m)) * NT] = g2;
+            yI_fadd[m] = fadd[m]; yI_bm[m] = bmP[m]; yI_bp[m] = bpP[m];
+          }
+        }
+      }
+      // the new interface becomes the pending one
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw)
+#pragma unroll
+        for (int m = 0; m < M; ++m) syw[(mw * M + m) * NT] = waveN[mw][m];
+#pragma unroll
+      for (int m = 0; m < M; ++m) { sya[m * NT] = amdqN[m]; sya[(M + m) * NT] = apdqN[m]; }
+#pragma unroll
+      for (int k = 0; k < NR; ++k) sya[(2 * M + k) * NT] = roeN[k];
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw) sya[(2 * M + NR + mw) * NT] = dotn[mw];
+    }
+
+    // =========================== x-pipeline on row J+1 ===============================
+    double qn2[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) qn2[m] = qN[m];
+    if (J >= Jb - 2) {
+      double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
+      x_face<RP, NT>(P, q1, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
+      if (x_cfl_col && (J + 1 >= 1) && (J + 1 <= P.my + 2)) {             // flux2.f90:111-119
+#pragma unroll
+        for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtdx * s[mw]), -dtdx * s[mw]);
+      }
+      double bmA[M], bpA[M], bmP[M], bpP[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) { bmA[m] = 0.0; bpA[m] = 0.0; bmP[m] = 0.0; bpP[m] = 0.0; }
+      if (mt > 0) {
+        double tm[M], tp[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) { tm[m] = amdq[m]; tp[m] = apdq[m]; }
+        if (second && mt == 2) {                                           // flux2.f90:167-173
+#pragma unroll
+          for (int m = 0; m < M; ++m) { tm[m] = tm[m] + cqxx[m]; tp[m] = tp[m] - cqxx[m]; }
+        }
+        RP::transverse(P.rp, 0, roe, tm, bmA, bpA);                        // flux2.f90:181
+        RP::transverse(P.rp, 0, roe, tp, bmP, bpP);                        // flux2.f90:194
+      }
+      // hand my left-face results to the cell on my left (sxw is free again after barrier C / A)
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        sxw[m * NT] = amdq[m]; sxw[(M + m) * NT] = fadd[m];
+        sxw[(2 * M + m) * NT] = bmA[m]; sxw[(3 * M + m) * NT] = bpA[m];
+      }
+      __syncthreads();                                                     // (D) also publishes sgy
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const double amdqR = sxw[m * NT + tr], faddR = sxw[(M + m) * NT + tr];
+        const double bmAR = sxw[(2 * M + m) * NT + tr], bpAR = sxw[(3 * M + m) * NT + tr];
+        const double qadd = (0.0 - dtdx * apdq[m]) - dtdx * amdqR;         // flux2.f90:105-108
+        const double g1 = (0.0 - hdx * bmAR) - hdx * bmP[m];              // flux2.f90:185-203
+        const double g2 = (0.0 - hdx * bpAR) - hdx * bpP[m];
+        // step2.f90:139-147, pencil J+1: rows J, J+1, J+2
+        qn0[m] = qn0[m] - dtdy * g1;
+        qn1[m] = ((qn1[m] + qadd) - dtdx * (faddR - fadd[m])) - dtdy * (g2 - g1);
+        qn2[m] = qN[m] + dtdy * g2;
+      }
+    }
+
+    // =========================== cell (I, J) is complete =============================
+    if (J >= Jb) {
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        // step2.f90:221-229, columns I-1, I, I+1
+        double r = qn0[m] + dtdx * sgy[(M + m) * NT + tl];
+        r = r + ycomb[m];
+        r = r - dtdx * sgy[m * NT + tr];
+        if (store_col) P.qout[m * P.plane + (long long)J * P.pitch + I] = r;
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) { qn0[m] = qn1[m]; qn1[m] = qn2[m]; q1[m] = qN[m]; }
+  }
+  block_max_cfl<NT>(cfl, P.cfl_bits, sred);
+}
+
+// =====================================================================================
+// Dimension-split step: x-sweeps (step2ds ids=1) then y-sweeps (ids=2) of the x-updated data,
+// fused.  do_x / do_y select a single sweep (the f2py-shaped plugin entry points).
+//   x-sweep: all rows J in [0, my+3], cells I in [2, mx+1]          (step2ds.f90:96, 149-152)
+//   y-sweep: all columns I in [0, mx+3], cells J in [2, my+1]       (step2ds.f90:180, 237-240)
+// Segments: blockIdx.y covers output rows [Jb, Je) of [2, my+2) (fused / y-only) or of
+// [0, my+4) (x-only).
+// =====================================================================================
+template <class RP, int NT>
+__global__ void __launch_bounds__(NT) sweep2_split(const __grid_constant__ Sweep2Params P) {
+  constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE;
+  using S = Smem2<RP, NT>;
+  constexpr int TX = NT - 4;
+  extern __shared__ double smem[];
+  const int t = threadIdx.x;
+  double* const sq = smem + S::OFF_Q * NT + t;
+  double* const sxw = smem + S::OFF_XW * NT + t;
+  double* const sdot = smem + S::OFF_DOT * NT + t;
+  double* const syw = smem + S::OFF_YW * NT + t;
+  double* const sya = smem + S::OFF_YA * NT + t;
+  double* const sred = smem + S::PER_THREAD * NT;
+
+  const int nx = P.mx + 4;
+  const int I = blockIdx.x * TX + t;
+  const int Ic = I < nx ? I : nx - 1;
+  const int tl = t > 0 ? -1 : 0;
+  const int tr = t < NT - 1 ? 1 : 0;
+  const double dtdx = P.dtdx, dtdy = P.dtdy;
+  const bool second = (P.order != 1);
+  const bool limit = second && (P.limit != 0);
+  const bool do_x = P.do_x != 0, do_y = P.do_y != 0;
+  const double* qcol = P.qin + Ic;
+  double cfl = 0.0;
+  const bool x_cfl_col = (t >= 1) && (I >= 2) && (I <= P.mx + 2);
+  const bool interior_col = (I >= 2) && (I <= P.mx + 1);
+  const bool x_ok = (t >= 2) && (t <= NT - 3);            // my x-updated value is complete
+  // column whose x-updated data are valid in this strip: x-updated interior, or untouched ghost
+  const bool col_ok = (I <= P.mx + 3) && (!do_x || !interior_col || x_ok);
+
+  if (!do_y) {
+    // ---- x-sweep only: rows [Jb, Je) of the whole array -------------------------------
+    const int Jb = blockIdx.y * P.seg_rows;
+    const int Je = min(Jb + P.seg_rows, P.my + 4);
+    for (int J = Jb; J < Je; ++J) {
+      double q[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) q[m] = qcol[m * P.plane + (long long)J * P.pitch];
+      double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
+      x_face<RP, NT>(P, q, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
+      if (x_cfl_col) {
+#pragma unroll
+        for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtdx * s[mw]), -dtdx * s[mw]);
+      }
+#pragma unroll
+      for (int m = 0; m < M; ++m) { sxw[m * NT] = amdq[m]; sxw[(M + m) * NT] = fadd[m]; }
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const double qadd = (0.0 - dtdx * apdq[m]) - dtdx * sxw[m * NT + tr];
+        const double r = (q[m] + qadd) - dtdx * (sxw[(M + m) * NT + tr] - fadd[m]);   // step2ds.f90:149-152
+        if (interior_col && x_ok) P.qout[m * P.plane + (long long)J * P.pitch + I] = r;
+      }
+    }
+    block_max_cfl<NT>(cfl, P.cfl_bits, sred);
+    return;
+  }
+
+  const int Jb = 2 + blockIdx.y * P.seg_rows;
+  const int Je = min(Jb + P.seg_rows, P.my + 2);
+  double qx0[M], qx1[M];                                   // x-updated rows J, J+1 (natural frame)
+  double yI_apdq[M], yI_fadd[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) { qx0[m] = 0.0; qx1[m] = 0.0; yI_apdq[m] = 0.0; yI_fadd[m] = 0.0; }
+
+  for (int J = Jb - 4; J < Je; ++J) {
+    // ---- x-sweep of row J+2 ----------------------------------------------------------
+    double qx2[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) qx2[m] = qcol[m * P.plane + (long long)(J + 2) * P.pitch];
+    if (do_x) {
+      double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
+      x_face<RP, NT>(P, qx2, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
+      if (x_cfl_col) {
+#pragma unroll
+        for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtdx * s[mw]), -dtdx * s[mw]);
+      }
+#pragma unroll
+      for (int m = 0; m < M; ++m) { sxw[m * NT] = amdq[m]; sxw[(M + m) * NT] = fadd[m]; }
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const double qadd = (0.0 - dtdx * apdq[m]) - dtdx * sxw[m * NT + tr];
+        const double r = (qx2[m] + qadd) - dtdx * (sxw[(M + m) * NT + tr] - fadd[m]);
+        if (interior_col) qx2[m] = r;                      // ghost columns are not updated by the x-sweep
+      }
+    }
+    // ---- y-pipeline --------------------------------------------------------------------
+    if (J >= Jb - 3) {
+      double waveN[W][M], sN[W], amdqN[M], apdqN[M], roeN[NR];
+      {
+        double ql[M], qr[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) { ql[m] = qx1[rot<M>(m)]; qr[m] = qx2[rot<M>(m)]; }
+        RP::normal(P.rp, 1, ql, qr, waveN, sN, amdqN, apdqN, roeN);
+      }
+      if (col_ok && (J + 2 >= 2) && (J + 2 <= P.my + 2)) {
+#pragma unroll
+        for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtdy * sN[mw]), -dtdy * sN[mw]);
+      }
+      double dotn[W];
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw) dotn[mw] = 0.0;
+      if (J >= Jb - 2) {
+        double waveC[W][M], wnorm2[W];
+#pragma unroll
+        for (int mw = 0; mw < W; ++mw) {
+          wnorm2[mw] = 0.0;
+#pragma unroll
+          for (int m = 0; m < M; ++m) waveC[mw][m] = syw[(mw * M + m) * NT];
+        }
+        if (limit) wave_dots<RP, true>(waveC, waveN, wnorm2, dotn);
+        if (J >= Jb - 1) {
+          double sC[W], amdqC[M], apdqC[M], roeC[NR], dotl[W];
+#pragma unroll
+          for (int m = 0; m < M; ++m) { amdqC[m] = sya[m * NT]; apdqC[m] = sya[(M + m) * NT]; }
+#pragma unroll
+          for (int k = 0; k < NR; ++k) roeC[k] = sya[(2 * M + k) * NT];
+#pragma unroll
+          for (int mw = 0; mw < W; ++mw) dotl[mw] = sya[(2 * M + NR + mw) * NT];
+          RP::speeds(P.rp, 1, roeC, sC);
+          double fadd[M];
+#pragma unroll
+          for (int m = 0; m < M; ++m) fadd[m] = 0.0;
+          if (second) {
+            if (limit) limit_waves<RP>(P, waveC, sC, wnorm2, dotl, dotn);
+            double cqxx[M];
+            second_order<RP>(dtdy, waveC, sC, cqxx);
+#pragma unroll
+            for (int m = 0; m < M; ++m) fadd[m] = 0.0 + 0.5 * cqxx[m];
+          }
+#pragma unroll
+          for (int m = 0; m < M; ++m) {
+            const double qadd = (0.0 - dtdy * yI_apdq[m]) - dtdy * amdqC[m];
+            // step2ds.f90:237-240
+            const double r = (qx0[rot<M>(m)] + qadd) - dtdy * (fadd[m] - yI_fadd[m]);
+            if (J >= Jb && col_ok && (do_x ? interior_col : true))
+              P.qout[rot<M>(m) * P.plane + (long long)J * P.pitch + I] = r;
+            yI_apdq[m] = apdqC[m]; yI_fadd[m] = fadd[m];
+          }
+        }
+      }
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw)
+#pragma unroll
+        for (int m = 0; m < M; ++m) syw[(mw * M + m) * NT] = waveN[mw][m];
+#pragma unroll
+      for (int m = 0; m < M; ++m) { sya[m * NT] = amdqN[m]; sya[(M + m) * NT] = apdqN[m]; }
+#pragma unroll
+      for (int k = 0; k < NR; ++k) sya[(2 * M + k) * NT] = roeN[k];
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw) sya[(2 * M + NR + mw) * NT] = dotn[mw];
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) { qx0[m] = qx1[m]; qx1[m] = qx2[m]; }
+  }
+  block_max_cfl<NT>(cfl, P.cfl_bits, sred);
+}
+
+}  // namespace CLAW_NS
+}  // namespace clawcuda

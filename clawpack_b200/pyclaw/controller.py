@@ -1,0 +1,97 @@
+"""Controller: the output-time loop around ``solver.evolve_to_time`` (pyclaw/src/pyclaw/controller.py:275-397).
+
+Kept thin: output styles 1-3, ``keep_copy`` frames, ``tfinal``, ``num_output_times``.  Frame file
+output (``output_format``) is outside this build's scope; the default here is ``None`` (no files),
+and any other value raises in ``Solution.write``."""
+import copy
+import logging
+
+import numpy as np
+
+
+class Controller(object):
+    def __init__(self):
+        self.solution = None
+        self.solver = None
+        self.keep_copy = False
+        self.frames = []
+        self.write_aux_init = False
+        self.write_aux_always = False
+        self.output_format = None
+        self.output_file_prefix = None
+        self.output_options = {}
+        self.outdir = './_output'
+        self.overwrite = True
+        self.logger = logging.getLogger('pyclaw.controller')
+        self.tfinal = 1.0
+        self.output_style = 1
+        self.verbosity = 3
+        self.num_output_times = 10
+        self.out_times = np.linspace(0.0, self.tfinal, self.num_output_times)
+        self.nstepout = 1
+        self.start_frame = 0
+        self.setplot = None
+        self.compute_p = None
+        self.compute_F = None
+
+    @property
+    def verbosity(self):
+        return self._verbosity
+
+    @verbosity.setter
+    def verbosity(self, value):
+        self._verbosity = value
+
+    def check_validity(self):
+        if not self.solution.is_valid():
+            raise Exception('The solution is not valid.')
+        valid, reason = self.solver.is_valid()
+        if not valid:
+            raise Exception('The solver failed to initialize properly because: ' + reason)
+
+    def run(self):
+        """Evolve to ``tfinal`` stopping at the output times; returns the solver status dict."""
+        if self.solver is None or self.solution is None:
+            raise Exception('To run, a Controller must have a Solver and a Solution.')
+        self.start_frame = self.solution.start_frame
+        if not self.solver._is_set_up:
+            self.solver.setup(self.solution)
+            self.solver.dt = self.solver.dt_initial
+        self.check_validity()
+
+        if self.output_style == 1:
+            output_times = np.linspace(self.solution.t, self.tfinal, self.num_output_times + 1)
+        elif self.output_style == 2:
+            output_times = self.out_times
+        elif self.output_style == 3:
+            output_times = np.ones((self.num_output_times + 1 - self.start_frame))
+        else:
+            raise Exception('Invalid output style %s' % self.output_style)
+        if len(output_times) == 0:
+            print('No valid output times; halting.')
+            return None
+
+        frame = self.start_frame
+        if self.keep_copy:
+            self.frames.append(copy.deepcopy(self.solution))
+        if self.output_format is not None:
+            self.solution.write(frame, self.outdir, self.output_format, self.output_file_prefix,
+                                self.write_aux_always or self.write_aux_init, self.output_options)
+        self.logger.info('Solution %s computed for time t=%f' % (frame, self.solution.t))
+
+        status = None
+        for t in output_times[1:]:
+            if self.output_style < 3:
+                status = self.solver.evolve_to_time(self.solution, t)
+            else:
+                for n in range(self.nstepout):
+                    status = self.solver.evolve_to_time(self.solution)
+            frame += 1
+            if self.keep_copy:
+                self.frames.append(copy.deepcopy(self.solution))
+            if self.output_format is not None:
+                self.solution.write(frame, self.outdir, self.output_format, self.output_file_prefix,
+                                    self.write_aux_always, self.output_options)
+            self.logger.info('Solution %s computed for time t=%f' % (frame, self.solution.t))
+        self.solution._start_frame = len(self.frames)
+        return status

@@ -1,0 +1,224 @@
+"""CUDA back end of the classic solvers: the bridge between the PyClaw-shaped host classes and
+libclawcuda.so (include/clawcuda.h), via ctypes.  PyTorch only provides the device buffers.
+
+* ``DeviceStepper``  -- device-resident state for ClawSolver2D/3D(kernel_language='CUDA').
+* ``fmod(num_dim)``  -- object with the f2py signatures of the reference's ``classic2`` /
+  ``classic3`` extension modules (step2, step2ds, step3, step3ds; step2.f90:2-5 etc.), running
+  the same kernels on host arrays.  Assign it to ``solver.fmod`` wherever the reference would
+  use its Fortran module.
+"""
+import ctypes
+
+import numpy as np
+
+from .. import _lib
+
+_MODES = {'strict': 0, 'fast': 1}
+
+
+def _iarr(values, n=None):
+    a = np.zeros(n if n is not None else len(values), dtype=np.intc)
+    for k, v in enumerate(values):
+        a[k] = -1 if v is None else int(v)
+    return a
+
+
+def _cparam_of(rp):
+    cp = getattr(rp, 'cparam', None)
+    vals = cp.values() if cp is not None else []
+    return np.array(list(vals) + [0.0], dtype=np.float64), len(vals)
+
+
+class DeviceStepper(object):
+    """Owns the libclawcuda handle and the torch device buffers of one State."""
+
+    def __init__(self, solver, state):
+        import torch
+        L = _lib.lib()
+        if L.claw_device_count() == 0 or not torch.cuda.is_available():
+            raise _lib.ClawCudaError("kernel_language='CUDA' needs a CUDA device; none is visible "
+                                     "(there is no CPU fallback in this package)")
+        self.L = L
+        self.torch = torch
+        dev = solver.cuda_device if solver.cuda_device is not None else torch.cuda.current_device()
+        self.device = torch.device('cuda', int(dev))
+        self.num_dim = solver.num_dim
+        n = _iarr(state.grid.num_cells)
+        self.handle = ctypes.c_void_p()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(L.claw_create(ctypes.byref(self.handle), solver.num_dim, int(solver.rp.rp_id), state.num_eqn,
+                                 solver.num_waves, state.num_aux, _lib.ip(n), solver.num_ghost, int(dev),
+                                 ctypes.c_void_p(stream)))
+        h = self.handle
+        nq, na, nw = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(L.claw_buffer_sizes(h, ctypes.byref(nq), ctypes.byref(na), ctypes.byref(nw)), h)
+        f64 = torch.float64
+        self.q0 = torch.zeros(nq.value, dtype=f64, device=self.device)
+        self.q1 = torch.zeros(nq.value, dtype=f64, device=self.device)
+        self.aux = torch.zeros(max(na.value, 1), dtype=f64, device=self.device)
+        self.work = torch.zeros(nw.value, dtype=f64, device=self.device)
+        _lib.check(L.claw_bind(h, ctypes.c_void_p(self.q0.data_ptr()), ctypes.c_void_p(self.q1.data_ptr()),
+                               ctypes.c_void_p(self.aux.data_ptr() if na.value else 0),
+                               ctypes.c_void_p(self.work.data_ptr())), h)
+        self.cfl_tensor = self.work[0:1]          # the 8-byte CFL slot (for the multi-GPU max all-reduce)
+        cp, ncp = _cparam_of(solver.rp)
+        _lib.check(L.claw_set_cparam(h, _lib.dp(cp), ncp), h)
+        mth = _iarr(solver._mthlim)
+        _lib.check(L.claw_set_method(h, _lib.ip(np.ascontiguousarray(solver._method, dtype=np.intc)), _lib.ip(mth),
+                                     int(bool(solver.fwave))), h)
+        nd = solver.num_dim
+        _lib.check(L.claw_set_bc(h, _lib.ip(_iarr(solver.bc_lower, 3)), _lib.ip(_iarr(solver.bc_upper, 3)),
+                                 _lib.ip(_iarr(solver.aux_bc_lower, 3)), _lib.ip(_iarr(solver.aux_bc_upper, 3)),
+                                 _lib.ip(_iarr(solver.reflect_index, 3))), h)
+        grid = state.grid
+        lo = [1 if b in (True, None) else 0 for b in grid.on_lower_boundary] + [1] * (3 - nd)
+        up = [1 if b in (True, None) else 0 for b in grid.on_upper_boundary] + [1] * (3 - nd)
+        _lib.check(L.claw_set_boundary_ownership(h, _lib.ip(_iarr(lo)), _lib.ip(_iarr(up))), h)
+        if solver.cuda_precision not in _MODES:
+            raise ValueError("cuda_precision must be 'strict' or 'fast'")
+        _lib.check(L.claw_set_mode(h, _MODES[solver.cuda_precision]), h)
+        _lib.check(L.claw_set_tuning(h, int(solver.cuda_seg_rows)), h)
+        self.delta = np.array(list(grid.delta) + [1.0] * (3 - nd), dtype=np.float64)
+        # host <-> device coherence of state.q
+        self.host_valid = True      # state._q equals the device's current buffer
+        self.host_dirty = True      # state._q may have been changed on the host since the last upload
+        self.pre_step_hook = None   # e.g. the multi-GPU ghost exchange (petclaw)
+        self.post_step_hook = None  # e.g. the CFL all-reduce
+        if state.num_aux > 0:
+            aux = np.asfortranarray(state.aux)
+            _lib.check(L.claw_put_aux(h, aux.ctypes.data_as(ctypes.c_void_p)), h)
+        state._device = self
+
+    # ---- coherence protocol used by State.q --------------------------------------------------
+    def sync_host(self, state):
+        if not self.host_valid:
+            q = state._q
+            if not (q.flags['F_CONTIGUOUS'] and q.flags['WRITEABLE'] and q.flags['OWNDATA']):
+                q = np.empty(q.shape, order='F')
+                state._q = q
+            _lib.check(self.L.claw_get_q(self.handle, q.ctypes.data_as(ctypes.c_void_p)), self.handle)
+            self.host_valid = True
+        self.host_dirty = True          # the caller may write through the returned array
+
+    def host_modified(self):
+        self.host_valid = True
+        self.host_dirty = True
+
+    def _upload_if_needed(self, state):
+        if self.host_dirty:
+            q = np.asfortranarray(state._q, dtype=np.float64)
+            _lib.check(self.L.claw_put_q(self.handle, q.ctypes.data_as(ctypes.c_void_p)), self.handle)
+            self.host_dirty = False
+
+    # ---- stepping ------------------------------------------------------------------------------
+    def step(self, state, dt):
+        """ghost fill + fused sweep on the device; returns the (local) CFL number."""
+        self._upload_if_needed(state)
+        if self.pre_step_hook is not None:
+            self.pre_step_hook(self)
+        cfl = ctypes.c_double(0.0)
+        if self.post_step_hook is None:
+            _lib.check(self.L.claw_step(self.handle, _lib.dp(self.delta), float(dt), 1, ctypes.byref(cfl)),
+                       self.handle)
+            return cfl.value
+        _lib.check(self.L.claw_step_launch(self.handle, _lib.dp(self.delta), float(dt), 1), self.handle)
+        return self.post_step_hook(self)
+
+    def accept(self):
+        _lib.check(self.L.claw_accept(self.handle), self.handle)
+        self.host_valid = False
+
+    def reject(self):
+        _lib.check(self.L.claw_reject(self.handle), self.handle)
+
+    def launch_count(self):
+        c = ctypes.c_uint64()
+        _lib.check(self.L.claw_launch_count(self.handle, ctypes.byref(c)), self.handle)
+        return int(c.value)
+
+    def synchronize(self):
+        _lib.check(self.L.claw_sync(self.handle), self.handle)
+
+    def close(self):
+        if self.handle:
+            self.L.claw_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _CudaFmod(object):
+    """f2py-shaped plug-in object.  Same positional arguments as the reference modules; the
+    work/aux1..3 scratch arguments are accepted and ignored; ``rpn*`` must be a
+    clawpack_b200.riemann solver object (it carries rp_id and cparam)."""
+
+    def __init__(self, num_dim, precision='strict'):
+        self.num_dim = num_dim
+        self.mode = _MODES[precision]
+        self.L = _lib.lib()
+        if self.L.claw_device_count() == 0:
+            raise _lib.ClawCudaError('the CUDA plug-in needs a CUDA device; none is visible (no CPU fallback)')
+
+    @staticmethod
+    def _prep(qold, qnew, aux, method, mthlim):
+        qold = np.asfortranarray(qold, dtype=np.float64)
+        if not (isinstance(qnew, np.ndarray) and qnew.flags['F_CONTIGUOUS'] and qnew.dtype == np.float64):
+            qnew = np.asfortranarray(qnew, dtype=np.float64)
+        aux = None if aux is None or aux.size == 0 else np.asfortranarray(aux, dtype=np.float64)
+        return qold, qnew, aux, np.ascontiguousarray(method, dtype=np.intc), _iarr(mthlim)
+
+    @staticmethod
+    def _vp(a):
+        return ctypes.c_void_p(0) if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+    def step2(self, maxm, num_ghost, mx, my, qold, qnew, aux, dx, dy, dt, method, mthlim, aux1, aux2, aux3, work,
+              use_fwave, rpn2, rpt2):
+        qold, qnew, aux, method, mth = self._prep(qold, qnew, aux, method, mthlim)
+        cp, ncp = _cparam_of(rpn2)
+        cfl = ctypes.c_double(0.0)
+        _lib.check(self.L.claw_step2_host(maxm, qold.shape[0], len(mth), int(method[6]), num_ghost, mx, my,
+                                          self._vp(qold), self._vp(qnew), self._vp(aux), dx, dy, dt, _lib.ip(method),
+                                          _lib.ip(mth), int(bool(use_fwave)), int(rpn2.rp_id), _lib.dp(cp), ncp,
+                                          self.mode, ctypes.byref(cfl)))
+        return qnew, cfl.value
+
+    def step2ds(self, maxm, num_ghost, mx, my, qold, qnew, aux, dx, dy, dt, method, mthlim, aux1, aux2, aux3, work,
+                ids, use_fwave, rpn2, rpt2):
+        qold, qnew, aux, method, mth = self._prep(qold, qnew, aux, method, mthlim)
+        cp, ncp = _cparam_of(rpn2)
+        cfl = ctypes.c_double(0.0)
+        _lib.check(self.L.claw_step2ds_host(maxm, qold.shape[0], len(mth), int(method[6]), num_ghost, mx, my,
+                                            self._vp(qold), self._vp(qnew), self._vp(aux), dx, dy, dt,
+                                            _lib.ip(method), _lib.ip(mth), int(ids), int(bool(use_fwave)),
+                                            int(rpn2.rp_id), _lib.dp(cp), ncp, self.mode, ctypes.byref(cfl)))
+        return qnew, cfl.value
+
+    def step3(self, maxm, num_ghost, mx, my, mz, qold, qnew, aux, dx, dy, dz, dt, method, mthlim, aux1, aux2, aux3,
+              work, use_fwave, rpn3, rpt3, rptt3):
+        qold, qnew, aux, method, mth = self._prep(qold, qnew, aux, method, mthlim)
+        cp, ncp = _cparam_of(rpn3)
+        cfl = ctypes.c_double(0.0)
+        _lib.check(self.L.claw_step3_host(maxm, qold.shape[0], len(mth), int(method[6]), num_ghost, mx, my, mz,
+                                          self._vp(qold), self._vp(qnew), self._vp(aux), dx, dy, dz, dt,
+                                          _lib.ip(method), _lib.ip(mth), int(bool(use_fwave)), int(rpn3.rp_id),
+                                          _lib.dp(cp), ncp, self.mode, ctypes.byref(cfl)))
+        return qnew, cfl.value
+
+    def step3ds(self, maxm, num_ghost, mx, my, mz, qold, qnew, aux, dx, dy, dz, dt, method, mthlim, aux1, aux2,
+                aux3, work, idir, use_fwave, rpn3, rpt3, rptt3):
+        qold, qnew, aux, method, mth = self._prep(qold, qnew, aux, method, mthlim)
+        cp, ncp = _cparam_of(rpn3)
+        cfl = ctypes.c_double(0.0)
+        _lib.check(self.L.claw_step3ds_host(maxm, qold.shape[0], len(mth), int(method[6]), num_ghost, mx, my, mz,
+                                            self._vp(qold), self._vp(qnew), self._vp(aux), dx, dy, dz, dt,
+                                            _lib.ip(method), _lib.ip(mth), int(idir), int(bool(use_fwave)),
+                                            int(rpn3.rp_id), _lib.dp(cp), ncp, self.mode, ctypes.byref(cfl)))
+        return qnew, cfl.value
+
+
+def fmod(num_dim, precision='strict'):
+    return _CudaFmod(num_dim, precision)

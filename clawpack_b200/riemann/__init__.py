@@ -1,0 +1,23 @@
+"""clawpack.riemann-compatible namespace: solver objects by the reference's module names
+(riemann/riemann/__init__.py:56-111) plus ``static`` and the ``*_constants`` field indices."""
+import sys as _sys
+
+from . import static
+from ._make import make as _make
+
+# name -> (rp_id (include/clawcuda.h), COMMON /cparam/ members in declaration order, num_dim)
+_SOLVERS = {
+    'advection_2D': (1, ('u', 'v'), 2),                       # riemann/src/rpn2_advection.f90
+    'acoustics_2D': (2, ('rho', 'bulk', 'cc', 'zz'), 2),      # rpn2_acoustics.f90:52
+    'euler_4wave_2D': (3, ('gamma',), 2),                     # rpn2_euler_4wave.f90:71
+    'shallow_roe_with_efix_2D': (4, ('grav',), 2),            # rpn2_shallow_roe_with_efix.f90:59
+    'vc_acoustics_3D': (5, (), 3),                            # rpn3_vc_acoustics.f90 (no common block)
+}
+
+for _name, (_id, _cp, _nd) in _SOLVERS.items():
+    _m = _make(_name, _id, _cp, _nd)
+    globals()[_name] = _m
+    _sys.modules[__name__ + '.' + _name] = _m
+
+from . import acoustics_2D_constants, advection_2D_constants, euler_4wave_2D_constants  # noqa: E402,F401
+from . import shallow_roe_with_efix_2D_constants, vc_acoustics_3D_constants             # noqa: E402,F401

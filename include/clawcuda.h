@@ -1,0 +1,164 @@
+/* clawcuda.h -- C ABI of libclawcuda.so: the B200 (sm_100a) classic wave-propagation step.
+ *
+ * This is the drop-in boundary for PyClaw's kernel plug-in point `solver.fmod`
+ * (reference: pyclaw/src/pyclaw/classic/solver.py:208-211, 498-549, 648-706).  Everything is
+ * `extern "C"`, plain pointers and sizes; no torch / CUDA types appear in a signature
+ * (a CUDA stream is passed as an opaque `void*`, NULL = default stream).
+ *
+ * Two families of entry points:
+ *
+ *  (1) f2py-shaped, HOST buffers -- bind these where the reference binds the f2py module
+ *      `clawpack.pyclaw.classic.classic2` / `classic3`:
+ *        claw_step2_host    <->  step2    (pyclaw/src/pyclaw/classic/step2.f90:2-5)
+ *        claw_step2ds_host  <->  step2ds  (pyclaw/src/pyclaw/classic/step2ds.f90:2-5)
+ *        claw_step3_host    <->  step3    (pyclaw/src/pyclaw/classic/step3.f90:2-5)
+ *        claw_step3ds_host  <->  step3ds  (pyclaw/src/pyclaw/classic/step3ds.f90:2-5)
+ *      Arrays are float64, Fortran-contiguous, WITH ghost cells, exactly as PyClaw passes
+ *      them (qbc / auxbc).  The (rpn, rpt[, rptt]) C-function-pointer arguments of the
+ *      reference (classic/solver.py:516-521) become `rp_id` + `cparam` (the COMMON /cparam/
+ *      contents, reference pyclaw/src/pyclaw/state.py:192-217).  Host<->device copies happen
+ *      inside the call.
+ *
+ *  (2) device-resident solver handle -- what ClawSolver2D/3D(kernel_language='CUDA') drives:
+ *      q lives in HBM across steps; per step one ghost fill + one fused sweep kernel + an
+ *      8-byte CFL read-back; accept/reject is a pointer swap (replaces the q_backup copy of
+ *      pyclaw/src/pyclaw/solver.py:611,645).
+ *
+ * All functions return 0 on success, non-zero on error (never abort; the reference's Fortran
+ * `stop` paths, step2.f90:66-71, become error codes).  claw_last_error() gives the message.
+ * A handle is not thread-safe; distinct handles are independent.
+ */
+#ifndef CLAWCUDA_H
+#define CLAWCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Riemann solver ids (clawpack.riemann module names, riemann/riemann/static.py) */
+enum {
+  CLAW_RP_ADVECTION_2D = 1,            /* riemann/src/rpn2_advection.f90, rpt2_advection.f90 */
+  CLAW_RP_ACOUSTICS_2D = 2,            /* rpn2_acoustics.f90, rpt2_acoustics.f90 */
+  CLAW_RP_EULER_4WAVE_2D = 3,          /* rpn2_euler_4wave.f90, rpt2_euler.f90 */
+  CLAW_RP_SHALLOW_ROE_EFIX_2D = 4,     /* rpn2_shallow_roe_with_efix.f90, rpt2_shallow_roe_with_efix.f90 */
+  CLAW_RP_VC_ACOUSTICS_3D = 5          /* rpn3_vc_acoustics.f90, rpt3_vc_acoustics.f90, rptt3_vc_acoustics.f90 */
+};
+
+/* Boundary-condition ids = pyclaw.BC (pyclaw/src/pyclaw/solver.py:13-19) */
+enum { CLAW_BC_CUSTOM = 0, CLAW_BC_EXTRAP = 1, CLAW_BC_PERIODIC = 2, CLAW_BC_WALL = 3 };
+
+/* arithmetic mode: STRICT = no FMA contraction, op-for-op the reference (bit-exact vs the oracle);
+   FAST = FMA contraction allowed (within the 1e-12/step tolerance) */
+enum { CLAW_MODE_STRICT = 0, CLAW_MODE_FAST = 1 };
+
+typedef struct claw_solver claw_solver;
+
+const char* claw_version(void);
+/* message of the last error on this handle (h may be NULL: last error of a failed create / host call) */
+const char* claw_last_error(const claw_solver* h);
+/* number of CUDA devices visible (0 when there is none; never fails) */
+int claw_device_count(void);
+
+/* ---- (2) device-resident solver ------------------------------------------------------ */
+
+/* ndim 2|3; n[ndim] interior cells; num_ghost must be 2 (classic/solver.py:78); stream: cudaStream_t or NULL */
+int claw_create(claw_solver** out, int ndim, int rp_id, int meqn, int mwaves, int maux,
+                const int* n, int num_ghost, int device, void* stream);
+int claw_destroy(claw_solver* h);
+
+/* element counts (doubles) of the device buffers the caller must provide via claw_bind */
+int claw_buffer_sizes(const claw_solver* h, size_t* q_elems, size_t* aux_elems, size_t* work_elems);
+/* borrow caller-owned device buffers (e.g. torch tensors): two q buffers (ping-pong), aux, staging */
+int claw_bind(claw_solver* h, double* d_q0, double* d_q1, double* d_aux, double* d_work);
+
+/* COMMON /cparam/ values in the solver's declaration order (state.set_cparam, state.py:192-217) */
+int claw_set_cparam(claw_solver* h, const double* cparam, int n);
+/* method(7), mthlim(mwaves), use_fwave as packed by ClawSolver._set_method (classic/solver.py:173-193) */
+int claw_set_method(claw_solver* h, const int* method7, const int* mthlim, int use_fwave);
+/* BC ids per dimension; reflect_index = component negated by BC.wall (classic/solver.py:445,608) */
+int claw_set_bc(claw_solver* h, const int* lower, const int* upper, const int* aux_lower,
+                const int* aux_upper, const int* reflect_index);
+/* which faces of this patch are physical boundaries (petclaw/geometry.py:21-41); default all */
+int claw_set_boundary_ownership(claw_solver* h, const int* on_lower, const int* on_upper);
+int claw_set_mode(claw_solver* h, int mode);
+/* tuning knobs: rows per march segment (0 = auto) */
+int claw_set_tuning(claw_solver* h, int seg_rows);
+
+/* host <-> device state transfer; host arrays are Fortran-ordered (meqn, mx, my[, mz]) WITHOUT ghosts
+   (state.q / state.aux, pyclaw/src/pyclaw/state.py:316-321) */
+int claw_put_q(claw_solver* h, const double* host_q);
+int claw_get_q(claw_solver* h, double* host_q);
+int claw_put_aux(claw_solver* h, const double* host_aux);
+/* same WITH ghost cells (qbc / auxbc, solver.py:341-347) */
+int claw_put_qbc(claw_solver* h, const double* host_qbc);
+int claw_get_qbc(claw_solver* h, double* host_qbc);
+int claw_put_auxbc(claw_solver* h, const double* host_auxbc);
+
+/* ghost fill of the current q (and aux) -- Solver._apply_bcs (solver.py:351-437) */
+int claw_apply_bcs(claw_solver* h);
+
+/* one hyperbolic step attempt: [ghost fill] + fused sweep + CFL max.  The new state goes to the
+   alternate buffer; call claw_accept to make it current or claw_reject to drop it
+   (ClawSolver2D/3D.step_hyperbolic + evolve_to_time accept/reject, solver.py:605-657).
+   delta[ndim] = cell sizes.  fill_ghosts != 0 runs claw_apply_bcs first. */
+int claw_step_launch(claw_solver* h, const double* delta, double dt, int fill_ghosts);
+/* device address of the 8-byte CFL result of the last launch (a double; for an NCCL all-reduce) */
+int claw_cfl_device_ptr(claw_solver* h, void** d_cfl);
+/* wait for the launch and return its CFL number */
+int claw_cfl_wait(claw_solver* h, double* cfl);
+/* claw_step_launch + claw_cfl_wait */
+int claw_step(claw_solver* h, const double* delta, double dt, int fill_ghosts, double* cfl);
+int claw_accept(claw_solver* h);
+int claw_reject(claw_solver* h);
+int claw_sync(claw_solver* h);
+
+/* slab-decomposition ghost exchange along the slowest dimension (replaces DMDA.globalToLocal,
+   petclaw/state.py:223-231): pack the 2 interior rows/planes next to face `side` (0 lower, 1 upper)
+   of the current q into a contiguous device buffer / unpack a received buffer into that face's ghosts */
+int claw_halo_elems(const claw_solver* h, size_t* elems);
+int claw_halo_pack(claw_solver* h, int side, double* d_buf);
+int claw_halo_unpack(claw_solver* h, int side, const double* d_buf);
+
+/* kernels launched by this handle so far (bench.py `gpu_launches`) */
+int claw_launch_count(const claw_solver* h, uint64_t* count);
+
+/* ---- (1) f2py-shaped plug-in calls on HOST buffers ------------------------------------ */
+
+/* requires qnew == qold on the interior on entry (as PyClaw always calls it, classic/solver.py:514);
+   on return the interior of qnew holds the updated cells; ghost cells of qnew are left as passed
+   (the reference leaves partial sums there which PyClaw never reads). */
+int claw_step2_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, int mx, int my,
+                    const double* qold, double* qnew, const double* aux, double dx, double dy, double dt,
+                    const int* method7, const int* mthlim, int use_fwave,
+                    int rp_id, const double* cparam, int ncparam, int mode, double* cfl);
+/* ids = 1: x-sweeps of all rows; ids = 2: y-sweeps of all columns (qold may alias qnew) */
+int claw_step2ds_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, int mx, int my,
+                      const double* qold, double* qnew, const double* aux, double dx, double dy, double dt,
+                      const int* method7, const int* mthlim, int ids, int use_fwave,
+                      int rp_id, const double* cparam, int ncparam, int mode, double* cfl);
+int claw_step3_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, int mx, int my, int mz,
+                    const double* qold, double* qnew, const double* aux, double dx, double dy, double dz, double dt,
+                    const int* method7, const int* mthlim, int use_fwave,
+                    int rp_id, const double* cparam, int ncparam, int mode, double* cfl);
+int claw_step3ds_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, int mx, int my, int mz,
+                      const double* qold, double* qnew, const double* aux, double dx, double dy, double dz, double dt,
+                      const int* method7, const int* mthlim, int idir, int use_fwave,
+                      int rp_id, const double* cparam, int ncparam, int mode, double* cfl);
+/* drop the cached device state of the host entry points */
+int claw_host_release(void);
+
+/* pinned host memory for fast transfers of the (1)-family buffers */
+int claw_host_alloc(void** p, size_t bytes);
+int claw_host_free(void* p);
+
+/* FP64 issue-rate micro-benchmark (DFMA chain on all SMs): returns measured G DFMA/s; used by
+   bench.py as the roofline denominator of the FP64-bound kernels */
+int claw_measure_fp64_peak(int device, double* gdfma_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLAWCUDA_H */

@@ -1,0 +1,168 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on identical data.
+
+Bars (BASELINE.json north_star): relative L-inf <= 1e-12 after one step, <= 1e-10 after 100 steps,
+identical accept/reject sequences.  In 'strict' arithmetic (no FMA contraction) the kernels are
+op-for-op the reference, so we additionally demand BIT-EXACT equality with the oracle."""
+import numpy as np
+import pytest
+
+from clawpack_b200 import scenarios as S
+from refutil import goldens, ref_solver
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda_available():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+CASES = {
+    'advection_split': lambda: S.advection_2d(mx=50, my=50, dimensional_split=True),
+    'advection_unsplit_notrans': lambda: S.advection_2d(dimensional_split=False, transverse_waves=0),
+    'advection_unsplit_inc': lambda: S.advection_2d(dimensional_split=False, transverse_waves=1),
+    'advection_unsplit_cor': lambda: S.advection_2d(dimensional_split=False, transverse_waves=2),
+    'acoustics_split': lambda: S.acoustics_2d(mx=100, my=100),
+    'acoustics_unsplit_cor': lambda: dict(S.acoustics_2d(mx=60, my=44), dimensional_split=False, transverse_waves=2,
+                                          cfl_max=1.0, cfl_desired=0.9),
+    'euler_split': lambda: S.quadrants(mx=100, my=100),
+    'euler_unsplit_cor': lambda: dict(S.quadrants(mx=70, my=90), dimensional_split=False, transverse_waves=2,
+                                      limiters=S.MC),
+    'euler_unsplit_inc_superbee': lambda: dict(S.quadrants(mx=130, my=37), dimensional_split=False,
+                                               transverse_waves=1, limiters=[S.SUPERBEE, S.MINMOD, S.VANLEER, S.MC]),
+    'euler_shockbubble': lambda: S.shock_bubble(mx=160, my=120),
+    'shallow_split': lambda: S.radial_dam_break(mx=150, my=150),
+    'shallow_unsplit_cor': lambda: dict(S.radial_dam_break(mx=64, my=50), dimensional_split=False, transverse_waves=2),
+    'euler_first_order': lambda: dict(S.quadrants(mx=48, my=48), order=1, dimensional_split=False, transverse_waves=1),
+    'euler_tiny': lambda: dict(S.quadrants(mx=3, my=2), dimensional_split=False, transverse_waves=2),
+    'euler_wide_strip_edge': lambda: dict(S.quadrants(mx=249, my=9), dimensional_split=False, transverse_waves=2),
+}
+
+
+def _run_cuda(sc, nsteps, precision):
+    claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision=precision)
+    sol, solver = claw.solution, claw.solver
+    solver.setup(sol)
+    solver.dt = solver.dt_initial
+    for _ in range(nsteps):
+        solver.evolve_to_time(sol)
+    return np.array(sol.state.q, copy=True), list(solver.step_log), solver
+
+
+def _run_ref(sc, nsteps):
+    r = ref_solver(sc)
+    for _ in range(nsteps):
+        r.evolve_to_time()
+    return np.array(r.q, copy=True), list(r.step_log)
+
+
+def _rel_linf(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_strict_bit_exact_vs_oracle(name):
+    sc = CASES[name]()
+    q, log, _ = _run_cuda(sc, 6, 'strict')
+    qr, logr = _run_ref(sc, 6)
+    assert [s[2] for s in log] == [s[2] for s in logr], 'accept/reject sequence differs'
+    assert log == logr, 'dt / CFL sequence differs: %r vs %r' % (log[:3], logr[:3])
+    assert np.array_equal(q, qr), 'max abs diff %g' % np.max(np.abs(q - qr))
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_fast_within_tolerance(name):
+    sc = CASES[name]()
+    q, log, _ = _run_cuda(sc, 2, 'fast')       # dt_initial is a reject for most cases: 1 reject + 1 accept
+    qr, logr = _run_ref(sc, 2)
+    assert [s[2] for s in log] == [s[2] for s in logr]
+    assert _rel_linf(q, qr) <= 1e-12           # north_star: 1e-12 relative L-inf per step
+
+
+@pytest.mark.parametrize('name', ['euler_unsplit_cor', 'shallow_split', 'acoustics_split', 'euler_shockbubble'])
+def test_100_steps(name):
+    sc = CASES[name]()
+    qr, logr = _run_ref(sc, 101)
+    for precision, tol in (('strict', 0.0), ('fast', 1e-10)):
+        q, log, _ = _run_cuda(sc, 101, precision)
+        assert [s[2] for s in log] == [s[2] for s in logr], 'accept/reject sequence differs (%s)' % precision
+        assert _rel_linf(q, qr) <= tol, (precision, _rel_linf(q, qr))
+
+
+GOLDEN_RUNS = [
+    ('advection_2d__classic_dim_split', lambda: S.advection_2d(dimensional_split=True), 1e-6),
+    ('advection_2d__classic_unsplit_no_trans', lambda: S.advection_2d(dimensional_split=False, transverse_waves=0), 1e-6),
+    ('advection_2d__classic_unsplit_trans_inc', lambda: S.advection_2d(dimensional_split=False, transverse_waves=1), 1e-6),
+    ('advection_2d__classic_unsplit_trans_cor', lambda: S.advection_2d(dimensional_split=False, transverse_waves=2), 1e-6),
+    ('euler_2d__quadrants_roe', lambda: S.quadrants(), 1e-6),
+    ('shallow_2d__radialdambreak_classic_roe', lambda: S.radial_dam_break(), 1e-5),
+]
+
+
+@pytest.mark.parametrize('key,make,tol', GOLDEN_RUNS)
+@pytest.mark.parametrize('precision', ['strict', 'fast'])
+def test_full_run_vs_reference_golden(key, make, tol, precision):
+    """Whole Controller.run() on the GPU against the vector the reference's own Fortran path stored
+    (same L1 metric and tolerance as the reference tests, e.g. examples/euler_2d/test_euler2d.py:10-26)."""
+    sc = make()
+    claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision=precision)
+    claw.run()
+    q0 = claw.frames[claw.num_output_times].state.get_q_global()[0].reshape(-1)
+    dx, dy = claw.solution.domain.grid.delta
+    expected = goldens()[key].reshape(-1)
+    assert dx * dy * np.sum(np.abs(q0 - expected)) < tol
+    # and far tighter than the reference tolerance: we sit on the oracle, which sits on the golden
+    assert np.max(np.abs(q0 - expected)) < 1e-11
+
+
+def test_acoustics_golden():
+    sc = S.acoustics_2d()
+    claw = S.make_claw(sc, kernel_language='CUDA')
+    claw.run()
+    p = claw.frames[-1].q[0]
+    expected = goldens()['acoustics_2d__verify_classic']
+    # reference tolerance: relative L2 < 1e-3 (examples/acoustics_2d_homogeneous/test_2d_acoustics.py:14)
+    assert np.linalg.norm(p - expected) / np.linalg.norm(expected) < 1e-3
+
+
+def test_plugin_fmod_matches_oracle_fmod():
+    """The f2py-shaped plug-in (host buffers) against the oracle, unsplit + both split sweeps."""
+    from clawpack_b200 import riemann
+    from clawpack_b200.pyclaw import cuda_classic
+    from oracle_fmod import OracleFmod
+    sc = S.quadrants(mx=90, my=70)
+    r = ref_solver(sc)
+    r.apply_bcs()
+    rp = riemann.euler_4wave_2D
+    rp.cparam.gamma = 1.4
+    dx, dy = r.delta
+    dt = 0.002
+    mthlim = [4, 4, 4, 4]
+    cu, orc = cuda_classic.fmod(2), OracleFmod()
+    for method2 in (2, -1):
+        method = np.array([1, 2, method2, 0, 0, 0, 0], dtype=np.intc)
+        if method2 >= 0:
+            qa, qb = r.qbc.copy('F'), r.qbc.copy('F')
+            qa, ca = cu.step2(90, 2, 90, 70, r.qbc.copy('F'), qa, None, dx, dy, dt, method, mthlim, 0, 0, 0, 0, False, rp, rp)
+            qb, cb = orc.step2(90, 2, 90, 70, r.qbc.copy('F'), qb, None, dx, dy, dt, method, mthlim, 0, 0, 0, 0, False, rp, rp)
+            assert ca == cb
+            assert np.array_equal(qa[:, 2:-2, 2:-2], qb[:, 2:-2, 2:-2])
+        else:
+            for ids in (1, 2):
+                qa, qb = r.qbc.copy('F'), r.qbc.copy('F')
+                qa, ca = cu.step2ds(90, 2, 90, 70, r.qbc.copy('F'), qa, None, dx, dy, dt, method, mthlim, 0, 0, 0, 0, ids, False, rp, rp)
+                qb, cb = orc.step2ds(90, 2, 90, 70, r.qbc.copy('F'), qb, None, dx, dy, dt, method, mthlim, 0, 0, 0, 0, ids, False, rp, rp)
+                assert ca == cb, ids
+                assert np.array_equal(qa, qb), ids     # whole array incl. the updated ghost rows / columns
+
+
+def test_no_cpu_fallback_symbols_loaded():
+    """The CUDA path must run in libclawcuda.so, not in the oracle."""
+    import ctypes
+    from clawpack_b200 import _lib
+    L = _lib.lib()
+    assert L.claw_device_count() >= 1
+    assert b'clawcuda' in L.claw_version()
