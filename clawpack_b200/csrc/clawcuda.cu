@@ -612,6 +612,30 @@ int claw_halo_unpack(claw_solver* h, int side, const double* d_buf) {
   return 0;
 }
 
+int claw_time_sweep(claw_solver* h, const double* delta, double dt, int reps, double* avg_ms) {
+  if (check_handle(h)) return 1;
+  if (int rc = validate_config(h)) return rc;
+  if (int rc = ensure_buffers(h)) return rc;
+  if (reps < 1) return fail(h, 14, "claw_time_sweep: reps must be >= 1");
+  CK(h, cudaSetDevice(h->device));
+  cudaEvent_t a, b;
+  CK(h, cudaEventCreate(&a));
+  CK(h, cudaEventCreate(&b));
+  const int kind = (h->method[2] < 0) ? 1 : 0;
+  CK(h, cudaMemsetAsync(h->work, 0, sizeof(double), h->stream));
+  CK(h, cudaEventRecord(a, h->stream));
+  for (int r = 0; r < reps; ++r)
+    if (int rc = launch_step2(h, delta[0], delta[1], dt, kind, 1, 1, h->q[h->cur], h->q[h->cur ^ 1])) return rc;
+  CK(h, cudaEventRecord(b, h->stream));
+  CK(h, cudaEventSynchronize(b));
+  float ms = 0.f;
+  CK(h, cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *avg_ms = (double)ms / reps;
+  return 0;
+}
+
 int claw_launch_count(const claw_solver* h, uint64_t* count) {
   if (check_handle(h)) return 1;
   *count = h->launches;

@@ -52,11 +52,11 @@ namespace CLAW_NS {
 
 __device__ __forceinline__ double philim(double a, double b, int meth) {
   // philim.f90:14-35
-  const double r = b / a;
+  const double r = ddiv(b, a);
   switch (meth) {
     case 1: return fmax2(0.0, fmin2(1.0, r));
     case 2: return fmax2(fmax2(0.0, fmin2(1.0, 2.0 * r)), fmin2(2.0, r));
-    case 3: return (r + fabs(r)) / (1.0 + fabs(r));
+    case 3: return ddiv(r + fabs(r), 1.0 + fabs(r));
     case 4: { const double c = (1.0 + r) / 2.0; return fmax2(0.0, fmin2(fmin2(c, 2.0), 2.0 * r)); }
     case 5: return r;
   }

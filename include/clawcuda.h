@@ -122,6 +122,10 @@ int claw_halo_elems(const claw_solver* h, size_t* elems);
 int claw_halo_pack(claw_solver* h, int side, double* d_buf);
 int claw_halo_unpack(claw_solver* h, int side, const double* d_buf);
 
+/* time `reps` back-to-back launches of the sweep kernel alone (no ghost fill, no swap) with CUDA
+   events on the handle's stream; returns the average duration in milliseconds (bench.py roofline) */
+int claw_time_sweep(claw_solver* h, const double* delta, double dt, int reps, double* avg_ms);
+
 /* kernels launched by this handle so far (bench.py `gpu_launches`) */
 int claw_launch_count(const claw_solver* h, uint64_t* count);
 
