@@ -1,0 +1,72 @@
+"""Rank helpers and the scenario -> distributed Controller factory."""
+import numpy as np
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+def rank():
+    d = _dist()
+    return d.get_rank() if d else 0
+
+
+def world_size():
+    d = _dist()
+    return d.get_world_size() if d else 1
+
+
+def slab_range(n, nranks, r):
+    """Cells [start, stop) of the slowest dimension owned by rank r (balanced block partition, the
+    same rule as PETSc's default DMDA split: the first n % nranks ranks get one extra cell)."""
+    base, extra = divmod(n, nranks)
+    start = r * base + min(r, extra)
+    return start, start + base + (1 if r < extra else 0)
+
+
+def make_claw_distributed(sc, kernel_language='CUDA', **solver_kw):
+    """Build the Controller for a GLOBAL scenario dict; every rank keeps only its slab.  Initial data
+    come from the global arrays, so 1-rank and N-rank runs start from identical bits
+    (SURVEY.md appendix B)."""
+    from .. import petclaw as pyclaw
+    from .. import riemann
+    ndim = len(sc['num_cells'])
+    Solver = pyclaw.ClawSolver2D if ndim == 2 else pyclaw.ClawSolver3D
+    solver = Solver(getattr(riemann, sc['rp']))
+    solver.kernel_language = kernel_language
+    solver.limiters = sc['limiters']
+    solver.order = sc['order']
+    solver.dimensional_split = sc['dimensional_split']
+    if sc['transverse_waves'] is not None:
+        solver.transverse_waves = sc['transverse_waves']
+    solver.cfl_max = sc['cfl_max']
+    solver.cfl_desired = sc['cfl_desired']
+    solver.dt_initial = sc['dt_initial']
+    for i in range(ndim):
+        solver.bc_lower[i] = sc['bc_lower'][i]
+        solver.bc_upper[i] = sc['bc_upper'][i]
+        if sc['aux'] is not None:
+            solver.aux_bc_lower[i] = sc['aux_bc_lower'][i]
+            solver.aux_bc_upper[i] = sc['aux_bc_upper'][i]
+    for k, v in solver_kw.items():
+        setattr(solver, k, v)
+    names = ['x', 'y', 'z'][:ndim]
+    dims = [pyclaw.Dimension(lo, up, n, name=nm)
+            for lo, up, n, nm in zip(sc['lower'], sc['upper'], sc['num_cells'], names)]
+    domain = pyclaw.Domain(dims)
+    num_aux = 0 if sc['aux'] is None else sc['aux'].shape[0]
+    state = pyclaw.State(domain, sc['q'].shape[0], num_aux)
+    s0, s1 = state.patch.slab
+    state.q[...] = np.asarray(sc['q'])[..., s0:s1]
+    if num_aux:
+        state.aux[...] = np.asarray(sc['aux'])[..., s0:s1]
+    state.problem_data.update(sc['problem_data'])
+    claw = pyclaw.Controller()
+    claw.tfinal = sc['tfinal']
+    claw.num_output_times = sc['num_output_times']
+    claw.solution = pyclaw.Solution(state, domain)
+    claw.solver = solver
+    claw.output_format = None
+    claw.keep_copy = False
+    return claw

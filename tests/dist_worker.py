@@ -1,0 +1,53 @@
+"""Worker of the world_size>1 CPU tests (gloo): runs a scenario with the slab-decomposed host logic
+(clawpack_b200.petclaw) driving the TEST-ONLY oracle plug-in, gathers the result and compares it on
+rank 0 with the serial oracle run.  Usage: python dist_worker.py <case> <port>  (RANK/WORLD_SIZE in env)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import numpy as np
+import torch.distributed as dist
+
+from clawpack_b200 import petclaw, scenarios as S
+from oracle_fmod import OracleFmod
+from refutil import ref_solver
+
+CASES = {
+    'advection_unsplit_periodic': lambda: dict(S.advection_2d(mx=40, my=36, dimensional_split=False, transverse_waves=2),
+                                               tfinal=0.3, num_output_times=2),
+    'euler_unsplit_extrap': lambda: dict(S.quadrants(mx=30, my=41, tfinal=0.1), dimensional_split=False,
+                                         transverse_waves=2, limiters=S.MC, num_output_times=2),
+    'shallow_split_wall': lambda: dict(S.radial_dam_break(mx=36, my=30, tfinal=0.4), num_output_times=2),
+}
+
+
+def main():
+    case, port = sys.argv[1], sys.argv[2]
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = port
+    dist.init_process_group('gloo')
+    rank, world = dist.get_rank(), dist.get_world_size()
+    sc = CASES[case]()
+    claw = petclaw.make_claw_distributed(sc, kernel_language='Fortran', fmod=OracleFmod())
+    claw.run()
+    q = claw.solution.state.get_q_global()
+    log = claw.solver.step_log
+    ok = True
+    if rank == 0:
+        r = ref_solver(sc)
+        r.run(sc['tfinal'], sc['num_output_times'])
+        same_q = np.array_equal(q, r.q)
+        same_log = (log == r.step_log)
+        print('case %s world %d: q bit-identical to serial: %s, step log identical: %s (%d steps, %d rejected)'
+              % (case, world, same_q, same_log, len(log), sum(1 for s in log if not s[2])))
+        ok = same_q and same_log
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,42 @@
+"""world_size-2 and -3 runs of the slab-decomposed host logic on CPU (gloo backend): partition, ghost
+exchange, boundary ownership, periodic wrap-around and the CFL max all-reduce must reproduce the
+serial run bit for bit (the unsplit and 2-D split algorithms are decomposition-invariant,
+SURVEY.md appendix A.15)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _launch(case, world, port):
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), OMP_NUM_THREADS='1')
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, 'dist_worker.py'), case, str(port)],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=240)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(out)
+    return [p.returncode for p in procs], outs
+
+
+@pytest.mark.parametrize('case,world,port', [
+    ('advection_unsplit_periodic', 2, 29611),
+    ('euler_unsplit_extrap', 2, 29612),
+    ('shallow_split_wall', 2, 29613),
+    ('euler_unsplit_extrap', 3, 29614),
+    ('advection_unsplit_periodic', 3, 29615),
+])
+def test_slab_decomposition_matches_serial(case, world, port, oracle_lib):
+    codes, outs = _launch(case, world, port)
+    assert codes == [0] * world, '\n'.join(outs)
+    assert 'q bit-identical to serial: True, step log identical: True' in outs[0], outs[0]
