@@ -16,7 +16,8 @@ namespace clawref {
 // oracle step yields the exact operation mix of the reference algorithm.
 // ---------------------------------------------------------------------
 struct OpTally { uint64_t add, mul, div, sqrt, cmp, abs; };
-static thread_local OpTally g_tally;
+static thread_local OpTally g_tally_alg, g_tally_rec;
+#define g_tally (*(g_recompute_scope ? &g_tally_rec : &g_tally_alg))
 
 struct Counted {
   double v;
@@ -85,7 +86,8 @@ int clawref_step3ds(int maxm, int num_eqn, int num_waves, int num_aux, int num_g
 
 // Operation counts of ONE hyperbolic step on the given data (serial, counting scalar).
 // split != 0: step2ds(ids=1) then step2ds(ids=2) aliased, as classic/solver.py:527-535.
-// counts[6] = add(+,-), mul, div, sqrt, compare/min/max, abs
+// counts[12] = add(+,-), mul, div, sqrt, compare/min/max, abs of the algorithm, then the same six for the
+// work the reference merely repeats (Roe averages rebuilt inside rpt2)
 int clawref_count_ops2(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int mx, int my,
                        const double* qbc, const double* aux, double dx, double dy, double dt,
                        const int* method, const int* mthlim, int split, int use_fwave,
@@ -94,7 +96,7 @@ int clawref_count_ops2(int maxm, int num_eqn, int num_waves, int num_aux, int nu
   std::vector<Counted> qold(ncell * num_eqn), qnew(ncell * num_eqn), ax(ncell * (num_aux > 0 ? num_aux : 1));
   for (size_t k = 0; k < ncell * num_eqn; ++k) { qold[k] = Counted(qbc[k]); qnew[k] = Counted(qbc[k]); }
   if (num_aux > 0) for (size_t k = 0; k < ncell * num_aux; ++k) ax[k] = Counted(aux[k]);
-  std::memset(&g_tally, 0, sizeof(g_tally));
+  std::memset(&g_tally_alg, 0, sizeof(OpTally)); std::memset(&g_tally_rec, 0, sizeof(OpTally));
   Counted cfl; int rc;
   if (split) {
     rc = step2ds<Counted>(maxm, num_eqn, num_waves, num_aux, num_ghost, mx, my, qold.data(), qnew.data(), ax.data(),
@@ -106,8 +108,10 @@ int clawref_count_ops2(int maxm, int num_eqn, int num_waves, int num_aux, int nu
     rc = step2<Counted>(maxm, num_eqn, num_waves, num_aux, num_ghost, mx, my, qold.data(), qnew.data(), ax.data(),
                         Counted(dx), Counted(dy), Counted(dt), method, mthlim, &cfl, use_fwave != 0, rp_id, cparam, 1);
   }
-  counts[0] = g_tally.add; counts[1] = g_tally.mul; counts[2] = g_tally.div;
-  counts[3] = g_tally.sqrt; counts[4] = g_tally.cmp; counts[5] = g_tally.abs;
+  counts[0] = g_tally_alg.add; counts[1] = g_tally_alg.mul; counts[2] = g_tally_alg.div;
+  counts[3] = g_tally_alg.sqrt; counts[4] = g_tally_alg.cmp; counts[5] = g_tally_alg.abs;
+  counts[6] = g_tally_rec.add; counts[7] = g_tally_rec.mul; counts[8] = g_tally_rec.div;
+  counts[9] = g_tally_rec.sqrt; counts[10] = g_tally_rec.cmp; counts[11] = g_tally_rec.abs;
   return rc;
 }
 
@@ -120,7 +124,7 @@ int clawref_count_ops3(int maxm, int num_eqn, int num_waves, int num_aux, int nu
   std::vector<Counted> qold(ncell * num_eqn), qnew(ncell * num_eqn), ax(ncell * (num_aux > 0 ? num_aux : 1));
   for (size_t k = 0; k < ncell * num_eqn; ++k) { qold[k] = Counted(qbc[k]); qnew[k] = Counted(qbc[k]); }
   if (num_aux > 0) for (size_t k = 0; k < ncell * num_aux; ++k) ax[k] = Counted(aux[k]);
-  std::memset(&g_tally, 0, sizeof(g_tally));
+  std::memset(&g_tally_alg, 0, sizeof(OpTally)); std::memset(&g_tally_rec, 0, sizeof(OpTally));
   Counted cfl; int rc = 0;
   if (split) {
     for (int idir = 1; idir <= 3 && rc == 0; ++idir)
@@ -133,8 +137,10 @@ int clawref_count_ops3(int maxm, int num_eqn, int num_waves, int num_aux, int nu
                         Counted(dx), Counted(dy), Counted(dz), Counted(dt), method, mthlim, &cfl, use_fwave != 0,
                         rp_id, cparam, 1);
   }
-  counts[0] = g_tally.add; counts[1] = g_tally.mul; counts[2] = g_tally.div;
-  counts[3] = g_tally.sqrt; counts[4] = g_tally.cmp; counts[5] = g_tally.abs;
+  counts[0] = g_tally_alg.add; counts[1] = g_tally_alg.mul; counts[2] = g_tally_alg.div;
+  counts[3] = g_tally_alg.sqrt; counts[4] = g_tally_alg.cmp; counts[5] = g_tally_alg.abs;
+  counts[6] = g_tally_rec.add; counts[7] = g_tally_rec.mul; counts[8] = g_tally_rec.div;
+  counts[9] = g_tally_rec.sqrt; counts[10] = g_tally_rec.cmp; counts[11] = g_tally_rec.abs;
   return rc;
 }
 

@@ -27,6 +27,12 @@
 
 namespace clawref {
 
+// Counting hook: when the scalar is the counting type, operations inside a "recompute" scope are
+// work the reference repeats verbatim (rpt2 rebuilding the Roe averages rpn2 already produced,
+// rpt2_euler.f90:53-70) and are tallied separately from the algorithmic count.
+inline thread_local int g_recompute_scope = 0;
+struct RecomputeScope { RecomputeScope() { ++g_recompute_scope; } ~RecomputeScope() { --g_recompute_scope; } };
+
 // ---- scalar helpers (overloaded for the counting scalar in clawref.cpp) ----
 inline double r_sqrt(double x) { return std::sqrt(x); }
 inline double r_abs(double x) { return std::fabs(x); }
@@ -341,7 +347,7 @@ void rpt2_euler(int ixy, int, int maxm, int meqn, int, int, int mbc, int mx, V2<
   int mu, mv;
   if (ixy == 1) { mu = 2; mv = 3; } else { mu = 3; mv = 2; }
   EulerRoe<R> w(maxm, mbc);
-  euler_roe_averages(mu, mv, mbc, mx, ql, qr, gamma1, w);        // rpt2_euler.f90:53-70
+  { RecomputeScope scope; euler_roe_averages(mu, mv, mbc, mx, ql, qr, gamma1, w); }   // rpt2_euler.f90:53-70
   R waveb[5][4]; R sb[4];                                         // waveb(4,3), sb(3): 1-based
   for (int i = 2 - mbc; i <= mx + mbc; ++i) {                    // loop 20, :72-111
     R a3 = w.g1a2(i) * (w.euv(i) * asdq(1, i) + w.u(i) * asdq(mu, i) + w.v(i) * asdq(mv, i) - asdq(4, i));
@@ -470,6 +476,8 @@ void rpt2_shallow_roe_efix(int ixy, int, int maxm, int meqn, int mwaves, int, in
   const int n = maxm + 2 * mbc + 2, lo = 1 - mbc;
   std::vector<R> buf((size_t)4 * n);
   V1<R> u{buf.data(), lo}, v{buf.data() + n, lo}, a{buf.data() + 2 * n, lo}, h{buf.data() + 3 * n, lo};
+  {
+  RecomputeScope scope;
   for (int i = 2 - mbc; i <= mx + mbc; ++i) {          // loop 10, rpt2_shallow...:42-50
     h(i) = (qr(1, i - 1) + ql(1, i)) * R(0.50);
     R hsqrtl = r_sqrt(qr(1, i - 1));
@@ -478,6 +486,7 @@ void rpt2_shallow_roe_efix(int ixy, int, int maxm, int meqn, int mwaves, int, in
     u(i) = (qr(mu, i - 1) / hsqrtl + ql(mu, i) / hsqrtr) / hsq2;
     v(i) = (qr(mv, i - 1) / hsqrtl + ql(mv, i) / hsqrtr) / hsq2;
     a(i) = r_sqrt(grav * h(i));
+  }
   }
   R waveb[4][4]; R sb[4];
   for (int i = 2 - mbc; i <= mx + mbc; ++i) {          // loop 20, :52-84
