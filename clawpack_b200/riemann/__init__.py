@@ -12,6 +12,7 @@ _SOLVERS = {
     'euler_4wave_2D': (3, ('gamma',), 2),                     # rpn2_euler_4wave.f90:71
     'shallow_roe_with_efix_2D': (4, ('grav',), 2),            # rpn2_shallow_roe_with_efix.f90:59
     'vc_acoustics_3D': (5, (), 3),                            # rpn3_vc_acoustics.f90 (no common block)
+    'euler_3D': (6, ('gamma',), 3),                           # rpn3_euler.f90 / rpt3_euler.f90 / rptt3_euler.f90
 }
 
 for _name, (_id, _cp, _nd) in _SOLVERS.items():
@@ -21,3 +22,4 @@ for _name, (_id, _cp, _nd) in _SOLVERS.items():
 
 from . import acoustics_2D_constants, advection_2D_constants, euler_4wave_2D_constants  # noqa: E402,F401
 from . import shallow_roe_with_efix_2D_constants, vc_acoustics_3D_constants             # noqa: E402,F401
+from . import euler_3D_constants                                                        # noqa: E402,F401

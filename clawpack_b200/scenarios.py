@@ -7,7 +7,8 @@ BASELINE.json / SURVEY.md section 8(d), restated from the reference examples:
   radial_dam_break  pyclaw/examples/shallow_2d/radial_dam_break.py:23-72
   shock_bubble      synthetic 4-equation Euler shock/bubble (state formulas from
                     pyclaw/examples/euler_2d/shock_bubble_interaction.py:57-59), point-sampled
-  acoustics_3d      pyclaw/examples/acoustics_3d_variable/acoustics_3d_interface.py:76-125
+  acoustics_3d      pyclaw/examples/acoustics_3d_variable/acoustics_3d_interface.py:25-135
+  euler_3d_*        pyclaw/examples/euler_3d/shocktube.py, shock_bubble.py
 
 Each builder returns a plain ``dict`` (no PyClaw objects), so the same definition feeds the
 CUDA solver (via ``make_claw``), the oracle in tests, and bench.py.  Cell centres follow
@@ -132,36 +133,72 @@ def shock_bubble(mx=8192, my=8192, ly=1.0, y_offset=0.0, ly_total=None, dimensio
                  bc_lower=[EXTRAP, EXTRAP], bc_upper=[EXTRAP, EXTRAP], tfinal=tfinal)
 
 
-def acoustics_3d(mx=32, my=32, mz=32, heterogeneous=True, dimensional_split=False, transverse_waves=22,
-                 periodic=False, tfinal=0.2, num_output_times=2):
-    """acoustics_3d_interface.py:76-125, problem='heterogeneous' (interface at x=0) or homogeneous."""
+def acoustics_3d(mx=30, my=30, mz=30, heterogeneous=True, dimensional_split=None, transverse_waves=22,
+                 periodic=False, tfinal=2.0, num_output_times=10):
+    """pyclaw/examples/acoustics_3d_variable/acoustics_3d_interface.py:25-135: problem='heterogeneous'
+    (impedance/sound speed 1 for x<0, 2 for x>=0; unsplit, lower wall / upper periodic) or
+    'homogeneous' (dimension-split, all periodic).  ``periodic=True`` makes every face periodic
+    (sharded runs).  mx=my=mz=15 with the defaults reproduces the stored vector
+    verify_classic_heterogeneous.txt."""
     X, Y, Z = _grid((-1., -1., -1.), (1., 1., 1.), (mx, my, mz))
+    zl, cl = 1.0, 1.0
+    zr, cr = (2.0, 2.0) if heterogeneous else (1.0, 1.0)
     aux = np.empty((2, mx, my, mz), order='F')
+    aux[0] = zl * (X < 0.) + zr * (X >= 0.)
+    aux[1] = cl * (X < 0.) + cr * (X >= 0.)
+    x0, y0, z0 = -0.5, 0., 0.
+    q = np.zeros((4, mx, my, mz), order='F')
     if heterogeneous:
-        zr, cr, zl, cl = 1.0, 1.0, 2.0, 2.0
-        aux[0] = zl * (X < 0.) + zr * (X >= 0.)
-        aux[1] = cl * (X < 0.) + cr * (X >= 0.)
-        x0, y0, z0 = -0.5, 0.0, 0.0
         r = np.sqrt((X - x0) ** 2 + (Y - y0) ** 2 + (Z - z0) ** 2)
         width = 0.1
-        p0 = (np.abs(r - 0.3) <= width) * (1. + np.cos(np.pi * (r - 0.3) / width))
+        q[0] = (np.abs(r - 0.3) <= width) * (1. + np.cos(np.pi * (r - 0.3) / width))
     else:
-        aux[0] = 1.0
-        aux[1] = 1.0
-        x0 = -0.5
-        p0 = np.exp(-80. * (X - x0) ** 2)
-    q = np.zeros((4, mx, my, mz), order='F')
-    q[0] = p0
-    if periodic:
-        lo = [PERIODIC] * 3
-        up = [PERIODIC] * 3
-    else:
-        lo = [WALL, WALL, WALL] if heterogeneous else [PERIODIC] * 3
-        up = [EXTRAP, EXTRAP, EXTRAP] if heterogeneous else [PERIODIC] * 3
+        r = np.sqrt((X - x0) ** 2)
+        width = 0.2
+        q[0] = (np.abs(r) <= width) * (1. + np.cos(np.pi * (r) / width))
+    if dimensional_split is None:
+        dimensional_split = not heterogeneous
+    lo = [WALL] * 3 if (heterogeneous and not periodic) else [PERIODIC] * 3
+    up = [PERIODIC] * 3
     return _base('vc_acoustics_3D', (-1., -1., -1.), (1., 1., 1.), (mx, my, mz), q, aux=np.asfortranarray(aux),
                  limiters=MC, dimensional_split=bool(dimensional_split), transverse_waves=int(transverse_waves),
                  cfl_max=1.0, cfl_desired=0.9, dt_initial=0.1,
                  bc_lower=lo, bc_upper=up, aux_bc_lower=lo, aux_bc_upper=up,
+                 tfinal=tfinal, num_output_times=num_output_times)
+
+
+def euler_3d_shocktube(mx=10, my=10, mz=128, tfinal=0.2, num_output_times=10):
+    """pyclaw/examples/euler_3d/shocktube.py:17-66 as run by test_euler3d.py:27 (dimension-split, MC)."""
+    gamma = 1.4
+    X, Y, Z = _grid((-1., -1., -1.), (1., 1., 1.), (mx, my, mz))
+    q = np.zeros((5, mx, my, mz), order='F')
+    pressure = 3. * (Z <= 0) + 1. * (Z > 0)
+    q[0] = 3. * (Z <= 0) + 1. * (Z > 0)
+    q[4] = pressure / (gamma - 1.)
+    return _base('euler_3D', (-1., -1., -1.), (1., 1., 1.), (mx, my, mz), q, problem_data={'gamma': gamma},
+                 limiters=MC, dimensional_split=True, transverse_waves=22, cfl_max=1.0, cfl_desired=0.8,
+                 bc_lower=[EXTRAP] * 3, bc_upper=[EXTRAP] * 3, tfinal=tfinal, num_output_times=num_output_times)
+
+
+def euler_3d_shock_bubble(q0, consts, tfinal=0.1, num_output_times=10, dimensional_split=False):
+    """pyclaw/examples/euler_3d/shock_bubble.py:75-156 as run by test_euler3d.py:31 (64x16x16, unsplit,
+    transverse_waves=22, default minmod limiter, custom inflow BC at x-lower, walls at y/z-lower).
+    ``q0`` is the initial state (scipy sub-cell quadrature; stored fixture, tests/golden/make_golden.py)
+    and ``consts`` = (gamma, rho_shock, v_shock, e_shock)."""
+    gamma, rho_shock, v_shock, e_shock = [float(c) for c in consts]
+    n = q0.shape[1:]
+
+    def incoming_shock(qbc, num_ghost):                 # shock_bubble.py:63-72
+        for i in range(num_ghost):
+            qbc[0, i, ...] = rho_shock
+            qbc[1, i, ...] = rho_shock * v_shock
+            qbc[2, i, ...] = 0.
+            qbc[3, i, ...] = 0.
+            qbc[4, i, ...] = e_shock
+
+    return _base('euler_3D', (0., 0., 0.), (2., 0.5, 0.5), n, np.array(q0, order='F'), problem_data={'gamma': gamma},
+                 limiters=MINMOD, dimensional_split=bool(dimensional_split), transverse_waves=22,
+                 bc_lower=[0, WALL, WALL], bc_upper=[EXTRAP] * 3, custom_bc_lower=incoming_shock,
                  tfinal=tfinal, num_output_times=num_output_times)
 
 
@@ -188,6 +225,9 @@ def make_claw(sc, kernel_language='CUDA', pyclaw=None, **solver_kw):
         if sc['aux'] is not None:
             solver.aux_bc_lower[i] = sc['aux_bc_lower'][i]
             solver.aux_bc_upper[i] = sc['aux_bc_upper'][i]
+    if sc.get('custom_bc_lower') is not None:           # BC.custom (solver.py:393-398): q fill of one face
+        f = sc['custom_bc_lower']
+        solver.user_bc_lower = lambda state, dim, t, qbc, auxbc, num_ghost: f(qbc, num_ghost)
     for k, v in solver_kw.items():
         setattr(solver, k, v)
     names = ['x', 'y', 'z'][:ndim]

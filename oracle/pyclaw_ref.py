@@ -24,6 +24,7 @@ RP_IDS = {
     'euler_4wave_2D': 3,
     'shallow_roe_with_efix_2D': 4,
     'vc_acoustics_3D': 5,
+    'euler_3D': 6,
 }
 # COMMON /cparam/ member order of each solver (rpn2_advection.f90, rpn2_acoustics.f90:52,
 # rpn2_euler_4wave.f90:71, rpn2_shallow_roe_with_efix.f90:59; vc_acoustics_3D has none)
@@ -33,11 +34,12 @@ CPARAM_NAMES = {
     'euler_4wave_2D': ('gamma',),
     'shallow_roe_with_efix_2D': ('grav',),
     'vc_acoustics_3D': (),
+    'euler_3D': ('gamma',),           # rpn3_euler.f90: COMMON /cparam/ gamma
 }
 NUM_EQN = {'advection_2D': 1, 'acoustics_2D': 3, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
-           'vc_acoustics_3D': 4}
+           'vc_acoustics_3D': 4, 'euler_3D': 5}
 NUM_WAVES = {'advection_2D': 1, 'acoustics_2D': 2, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
-             'vc_acoustics_3D': 2}
+             'vc_acoustics_3D': 2, 'euler_3D': 3}
 
 BC_CUSTOM, BC_EXTRAP, BC_PERIODIC, BC_WALL = 0, 1, 2, 3
 
@@ -89,7 +91,7 @@ def max_threads():
 #  Ghost-cell fill -- solver.py:351-519
 # ----------------------------------------------------------------------------------------
 def fill_ghosts(arr, bc_lower, bc_upper, num_ghost, reflect_index=None, is_q=True,
-                on_lower=None, on_upper=None):
+                on_lower=None, on_upper=None, custom_lower=None, custom_upper=None):
     """arr: (n, mx+2g, my+2g[, mz+2g]) F-ordered with the interior already copied in.
     For each dimension ascending: lower then upper (solver.py:377-437); strips span the full
     extent of the other dimensions including their ghost cells."""
@@ -113,6 +115,8 @@ def fill_ghosts(arr, bc_lower, bc_upper, num_ghost, reflect_index=None, is_q=Tru
                     if is_q:
                         r = reflect_index[idim]
                         a[r, i, ...] = -a[r, 2 * g - 1 - i, ...]
+            elif t == BC_CUSTOM and custom_lower is not None:   # :393-398 (un-rolled array handed over)
+                custom_lower(idim, arr, g)
             else:
                 raise NotImplementedError('oracle: lower BC %r' % (t,))
         if up_on:
@@ -129,6 +133,8 @@ def fill_ghosts(arr, bc_lower, bc_upper, num_ghost, reflect_index=None, is_q=Tru
                     if is_q:
                         r = reflect_index[idim]
                         a[r, -i - 1, ...] = -a[r, -2 * g + i, ...]
+            elif t == BC_CUSTOM and custom_upper is not None:
+                custom_upper(idim, arr, g)
             else:
                 raise NotImplementedError('oracle: upper BC %r' % (t,))
     return arr
@@ -163,6 +169,8 @@ class RefSolver(object):
         self.aux_bc_lower = [None] * num_dim
         self.aux_bc_upper = [None] * num_dim
         self.reflect_index = list(range(1, num_dim + 1))
+        self.user_bc_lower = None           # f(idim, qbc, num_ghost): BC.custom fill of q (solver.py:393-398)
+        self.user_bc_upper = None
         self.nthreads = 1
         self.cparam = np.array([float(problem_data[k]) for k in CPARAM_NAMES[rp_name]] + [0.0], dtype=np.float64)
         self.dt = self.dt_initial
@@ -216,7 +224,8 @@ class RefSolver(object):
         if self.num_aux > 0:
             self._interior(self.auxbc)[...] = self.aux
             fill_ghosts(self.auxbc, self.aux_bc_lower, self.aux_bc_upper, g, is_q=False)
-        fill_ghosts(self.qbc, self.bc_lower, self.bc_upper, g, self.reflect_index, is_q=True)
+        fill_ghosts(self.qbc, self.bc_lower, self.bc_upper, g, self.reflect_index, is_q=True,
+                    custom_lower=self.user_bc_lower, custom_upper=self.user_bc_upper)
 
     # -- step_hyperbolic: classic/solver.py:498-549 / 648-706 --------------------------------
     def step_hyperbolic(self):

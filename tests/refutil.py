@@ -28,6 +28,9 @@ def ref_solver(sc, nthreads=1):
     if num_aux:
         s.aux_bc_lower = list(sc['aux_bc_lower'])
         s.aux_bc_upper = list(sc['aux_bc_upper'])
+    if sc.get('custom_bc_lower') is not None:
+        f = sc['custom_bc_lower']
+        s.user_bc_lower = lambda idim, qbc, g: f(qbc, g)
     s.nthreads = nthreads
     delta = [(u - l) / float(n) for l, u, n in zip(sc['lower'], sc['upper'], sc['num_cells'])]
     s.setup(sc['q'], sc['aux'], delta)
