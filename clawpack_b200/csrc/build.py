@@ -14,7 +14,8 @@ ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 HOSTCXX = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
 COMMON = ['nvcc', '-ccbin', HOSTCXX] + ARCH + ['-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '--threads', '4']
 
-SOURCES = ['clawcuda.cu', 'sweep_inst.cu', 'sweep2.cuh', 'rp2.cuh', 'launch.h', '../../include/clawcuda.h']
+SOURCES = ['clawcuda.cu', 'sweep_inst.cu', 'sweep3_inst.cu', 'sweep2.cuh', 'sweep3.cuh', 'rp2.cuh', 'rp3.cuh', 'launch.h',
+           '../../include/clawcuda.h']
 KERNEL_UNITS = ['sweep_inst.cu', 'sweep3_inst.cu']
 
 

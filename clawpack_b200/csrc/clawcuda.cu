@@ -16,6 +16,7 @@
 #include <string>
 
 #include "launch.h"
+#include "sweep3.cuh"
 
 using namespace clawcuda;
 
@@ -29,6 +30,7 @@ struct Dev2 {  // geometry of the device arrays
   int ng = 2;
   int nt[3] = {1, 1, 1};     // with ghosts
   int pitch = 0;             // row pitch (doubles)
+  long long kstride = 0;     // 3-D: doubles per K plane (pitch * nt[1]); 0 in 2-D
   long long plane = 0;       // doubles per component plane
 };
 
@@ -90,27 +92,27 @@ constexpr int WORK_HDR = 8;  // doubles reserved at the start of `work` (CFL slo
 // layout conversion: host/staging AoS (m fastest, Fortran order) <-> device SoA planes
 // region [i0,i1) x [j0,j1) of the ghosted array; staging holds exactly that region.
 // ---------------------------------------------------------------------------------------
-__global__ void aos_to_soa2(const double* __restrict__ aos, double* __restrict__ soa, int ncomp, int i0, int i1,
-                            int j0, int j1, int pitch, long long plane) {
-  const int w = i1 - i0;
-  const long long ncell = (long long)w * (j1 - j0);
+__global__ void aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, int ncomp, int i0, int i1,
+                           int j0, int j1, int k0, int k1, int pitch, long long kstride, long long plane) {
+  const int w = i1 - i0, hgt = j1 - j0;
+  const long long ncell = (long long)w * hgt * (k1 - k0);
   for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncell;
        c += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(c % w), j = (int)(c / w);
+    const int i = (int)(c % w), j = (int)((c / w) % hgt), k = (int)(c / ((long long)w * hgt));
     const double* src = aos + c * ncomp;
-    double* dst = soa + (long long)(j0 + j) * pitch + (i0 + i);
+    double* dst = soa + (long long)(k0 + k) * kstride + (long long)(j0 + j) * pitch + (i0 + i);
     for (int m = 0; m < ncomp; ++m) dst[m * plane] = src[m];
   }
 }
 
-__global__ void soa_to_aos2(const double* __restrict__ soa, double* __restrict__ aos, int ncomp, int i0, int i1,
-                            int j0, int j1, int pitch, long long plane) {
-  const int w = i1 - i0;
-  const long long ncell = (long long)w * (j1 - j0);
+__global__ void soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, int ncomp, int i0, int i1,
+                           int j0, int j1, int k0, int k1, int pitch, long long kstride, long long plane) {
+  const int w = i1 - i0, hgt = j1 - j0;
+  const long long ncell = (long long)w * hgt * (k1 - k0);
   for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncell;
        c += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(c % w), j = (int)(c / w);
-    const double* src = soa + (long long)(j0 + j) * pitch + (i0 + i);
+    const int i = (int)(c % w), j = (int)((c / w) % hgt), k = (int)(c / ((long long)w * hgt));
+    const double* src = soa + (long long)(k0 + k) * kstride + (long long)(j0 + j) * pitch + (i0 + i);
     double* dst = aos + c * ncomp;
     for (int m = 0; m < ncomp; ++m) dst[m] = src[m * plane];
   }
@@ -185,6 +187,32 @@ __global__ void halo_unpack2(double* q, const double* buf, int ncomp, int nx, in
   }
 }
 
+// 3-D ghost fill of one dimension: one thread per (component, a, b) where a, b run over the FULL
+// extent (ghosts included) of the other two dimensions, so edges/corners are the composition
+// x-then-y-then-z of the numpy slicing (solver.py:377-437).
+__global__ void bc_dim3(double* q, int ncomp, int n_d, long long stride_d, int ext_a, long long stride_a, int ext_b,
+                        long long stride_b, long long plane, int lo_type, int up_type, int lo_on, int up_on,
+                        int reflect) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long per = (long long)ext_a * ext_b;
+  if (idx >= per * ncomp) return;
+  const int a = (int)(idx % ext_a), b = (int)((idx / ext_a) % ext_b), m = (int)(idx / per);
+  bc_fill_pair(q + m * plane + a * stride_a + b * stride_b, stride_d, n_d, lo_type, up_type, lo_on != 0, up_on != 0,
+               m == reflect);
+}
+
+// ncomp runs of `len` contiguous doubles <-> one contiguous buffer (3-D halo planes)
+__global__ void gather_runs(const double* src, long long src_stride, double* dst, long long len, int ncomp) {
+  const long long n = len * ncomp;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+    dst[k] = src[(k / len) * src_stride + (k % len)];
+}
+__global__ void scatter_runs(double* dst, long long dst_stride, const double* src, long long len, int ncomp) {
+  const long long n = len * ncomp;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+    dst[(k / len) * dst_stride + (k % len)] = src[k];
+}
+
 // FP64 issue-rate probe: 8 independent DFMA chains per thread
 __global__ void dfma_probe(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -224,43 +252,91 @@ int grid_for(long long n, int block) {
 // copy a region of the ghosted host array (AoS) to / from the device SoA array
 int put_region(claw_solver* h, double* dsoa, int ncomp, const double* host, bool host_has_ghosts) {
   const Dev2& g = h->g;
-  if (g.ndim != 2) return fail(h, 20, "3-D transfers are not available in this build");
   if (int rc = ensure_buffers(h)) return rc;
   double* stage = h->work + WORK_HDR;
-  const int i0 = host_has_ghosts ? 0 : g.ng, i1 = host_has_ghosts ? g.nt[0] : g.ng + g.n[0];
-  const int j0 = host_has_ghosts ? 0 : g.ng, j1 = host_has_ghosts ? g.nt[1] : g.ng + g.n[1];
-  const size_t bytes = (size_t)ncomp * (i1 - i0) * (j1 - j0) * sizeof(double);
-  CK(h, cudaMemcpyAsync(stage, host, bytes, cudaMemcpyHostToDevice, h->stream));
-  const long long ncell = (long long)(i1 - i0) * (j1 - j0);
-  aos_to_soa2<<<grid_for(ncell, 256), 256, 0, h->stream>>>(stage, dsoa, ncomp, i0, i1, j0, j1, g.pitch, g.plane);
+  int lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+  for (int d = 0; d < g.ndim; ++d) {
+    lo[d] = host_has_ghosts ? 0 : g.ng;
+    hi[d] = host_has_ghosts ? g.nt[d] : g.ng + g.n[d];
+  }
+  const long long ncell = (long long)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+  CK(h, cudaMemcpyAsync(stage, host, (size_t)ncomp * ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  aos_to_soa<<<grid_for(ncell, 256), 256, 0, h->stream>>>(stage, dsoa, ncomp, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2],
+                                                          g.pitch, g.kstride, g.plane);
   ++h->launches;
   CK(h, cudaGetLastError());
   return 0;
 }
 
-int get_region(claw_solver* h, const double* dsoa, int ncomp, double* host, int i0, int i1, int j0, int j1,
-               size_t host_row_pitch_bytes, size_t host_offset_bytes) {
+// region [lo, hi) of the device array -> the same cells of a host array whose ghosted/unghosted extents are
+// host_n[] and whose first stored cell is host_lo[] (array coordinates)
+int get_region(claw_solver* h, const double* dsoa, int ncomp, double* host, const int* lo, const int* hi,
+               const int* host_lo, const int* host_n) {
   const Dev2& g = h->g;
-  if (g.ndim != 2) return fail(h, 20, "3-D transfers are not available in this build");
   double* stage = h->work + WORK_HDR;
-  const long long ncell = (long long)(i1 - i0) * (j1 - j0);
-  soa_to_aos2<<<grid_for(ncell, 256), 256, 0, h->stream>>>(dsoa, stage, ncomp, i0, i1, j0, j1, g.pitch, g.plane);
+  const int w = hi[0] - lo[0], hgt = hi[1] - lo[1], dep = hi[2] - lo[2];
+  const long long ncell = (long long)w * hgt * dep;
+  soa_to_aos<<<grid_for(ncell, 256), 256, 0, h->stream>>>(dsoa, stage, ncomp, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2],
+                                                          g.pitch, g.kstride, g.plane);
   ++h->launches;
   CK(h, cudaGetLastError());
-  const size_t row_bytes = (size_t)ncomp * (i1 - i0) * sizeof(double);
-  CK(h, cudaMemcpy2DAsync((char*)host + host_offset_bytes, host_row_pitch_bytes, stage, row_bytes, row_bytes,
-                          (size_t)(j1 - j0), cudaMemcpyDeviceToHost, h->stream));
+  const size_t row_bytes = (size_t)ncomp * w * sizeof(double);
+  const size_t host_row = (size_t)ncomp * host_n[0] * sizeof(double);
+  char* dst = (char*)host + (((size_t)(lo[2] - host_lo[2]) * host_n[1] + (lo[1] - host_lo[1])) * host_n[0] +
+                             (lo[0] - host_lo[0])) * ncomp * sizeof(double);
+  if (dep == 1) {
+    CK(h, cudaMemcpy2DAsync(dst, host_row, stage, row_bytes, row_bytes, (size_t)hgt, cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof p);
+    p.srcPtr = make_cudaPitchedPtr(stage, row_bytes, row_bytes, (size_t)hgt);
+    p.dstPtr = make_cudaPitchedPtr(dst, host_row, host_row, (size_t)host_n[1]);
+    p.extent = make_cudaExtent(row_bytes, (size_t)hgt, (size_t)dep);
+    p.kind = cudaMemcpyDeviceToHost;
+    CK(h, cudaMemcpy3DAsync(&p, h->stream));
+  }
   CK(h, cudaStreamSynchronize(h->stream));
   return 0;
 }
 
+// interior / whole-array downloads
+int get_interior(claw_solver* h, const double* dsoa, int ncomp, double* host, bool host_has_ghosts) {
+  const Dev2& g = h->g;
+  int lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1}, hlo[3] = {0, 0, 0}, hn[3] = {1, 1, 1};
+  for (int d = 0; d < g.ndim; ++d) {
+    lo[d] = g.ng; hi[d] = g.ng + g.n[d];
+    hlo[d] = host_has_ghosts ? 0 : g.ng;
+    hn[d] = host_has_ghosts ? g.nt[d] : g.n[d];
+  }
+  return get_region(h, dsoa, ncomp, host, lo, hi, hlo, hn);
+}
+int get_all(claw_solver* h, const double* dsoa, int ncomp, double* host) {
+  const Dev2& g = h->g;
+  int lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1}, hn[3] = {1, 1, 1};
+  for (int d = 0; d < g.ndim; ++d) { hi[d] = g.nt[d]; hn[d] = g.nt[d]; }
+  return get_region(h, dsoa, ncomp, host, lo, hi, lo, hn);
+}
+
 int fill_ghosts_array(claw_solver* h, double* arr, int ncomp, const int* lo, const int* up, bool is_q) {
   const Dev2& g = h->g;
-  if (g.ndim != 2) return fail(h, 20, "3-D ghost fill is not available in this build");
-  for (int d = 0; d < 2; ++d) {
+  for (int d = 0; d < g.ndim; ++d) {
     if ((h->on_lower[d] && (lo[d] < 1 || lo[d] > 3)) || (h->on_upper[d] && (up[d] < 1 || up[d] > 3)))
       return fail(h, 21, "boundary condition %d/%d in dimension %d cannot run on the device "
                          "(BC.custom needs a host round trip)", lo[d], up[d], d);
+  }
+  if (g.ndim == 3) {
+    const long long st[3] = {1, (long long)g.pitch, g.kstride};
+    for (int d = 0; d < 3; ++d) {
+      const int a = (d + 1) % 3, b = (d + 2) % 3;
+      const int refl = is_q ? h->reflect_index[d] : -1;
+      const long long n = (long long)g.nt[a] * g.nt[b] * ncomp;
+      bc_dim3<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(arr, ncomp, g.n[d], st[d], g.nt[a], st[a], g.nt[b],
+                                                                  st[b], g.plane, lo[d], up[d], h->on_lower[d],
+                                                                  h->on_upper[d], refl);
+      ++h->launches;
+    }
+    CK(h, cudaGetLastError());
+    return 0;
   }
   {
     // the negation flag is only consulted by the BC.wall branches (solver.py:464-473)
@@ -305,6 +381,51 @@ int launch_step2(claw_solver* h, double dx, double dy, double dt, int kind, int 
   return 0;
 }
 
+// one directional pass of the 3-D step (dir 0/1/2 = x/y/z)
+int launch_pass3(claw_solver* h, const double* delta, double dt, int dir, int first_pass, const double* src,
+                 double* dst) {
+  Sweep3Params P{};
+  P.qin = src;
+  P.qout = dst;
+  P.aux = h->aux;
+  P.cfl_bits = reinterpret_cast<unsigned long long*>(h->work);
+  for (int d = 0; d < 3; ++d) { P.n[d] = h->g.n[d]; P.dtd[d] = dt / delta[d]; }      // step3.f90:106-108
+  P.pitch = h->g.pitch; P.kstride = h->g.kstride; P.plane = h->g.plane;
+  P.order = h->method[1];
+  if (h->method[2] < 0) { P.m3 = -1; P.m4 = 0; }                                     // flux3.f90:186-194
+  else { P.m3 = h->method[2] / 10; P.m4 = h->method[2] - 10 * P.m3; }
+  P.limit = 0;
+  for (int mw = 0; mw < h->mwaves; ++mw) { P.mthlim[mw] = h->mthlim[mw]; if (h->mthlim[mw] > 0) P.limit = 1; }
+  P.first_pass = first_pass;
+  for (int k = 0; k < 4; ++k) P.rp.p[k] = h->cparam[k];
+  cudaError_t e = (h->mode == CLAW_MODE_FAST)
+                      ? fast::launch_sweep3(h->rp_id, dir, P, h->num_sms, h->stream, &h->last_launch)
+                      : strict::launch_sweep3(h->rp_id, dir, P, h->num_sms, h->stream, &h->last_launch);
+  ++h->launches;
+  if (e != cudaSuccess) return fail(h, 100 + (int)e, "3-D sweep kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// whole 3-D step: src (ghosts filled) -> dst.  Unsplit (step3.f90): x-sweep writes dst = src + terms, the y- and
+// z-sweeps add into dst.  Split (3 x step3ds.f90, classic/solver.py:680-690): src -> dst -> tmp -> dst.
+int launch_step3(claw_solver* h, const double* delta, double dt, const double* src, double* dst) {
+  if (h->method[2] < 0) {
+    double* tmp = h->work + WORK_HDR;
+    if (int rc = launch_pass3(h, delta, dt, 0, 1, src, dst)) return rc;
+    if (int rc = launch_pass3(h, delta, dt, 1, 1, dst, tmp)) return rc;
+    return launch_pass3(h, delta, dt, 2, 1, tmp, dst);
+  }
+  if (int rc = launch_pass3(h, delta, dt, 0, 1, src, dst)) return rc;
+  if (int rc = launch_pass3(h, delta, dt, 1, 0, src, dst)) return rc;
+  return launch_pass3(h, delta, dt, 2, 0, src, dst);
+}
+
+int launch_step(claw_solver* h, const double* delta, double dt, const double* src, double* dst) {
+  if (h->g.ndim == 3) return launch_step3(h, delta, dt, src, dst);
+  const int kind = (h->method[2] < 0) ? 1 : 0;         // method(3) = -1: dimensional splitting (classic/solver.py:186)
+  return launch_step2(h, delta[0], delta[1], dt, kind, 1, 1, src, dst);
+}
+
 int validate_config(claw_solver* h) {
   if (h->g.ndim == 2) {
     if (h->rp_id < 1 || h->rp_id > 4) return fail(h, 30, "rp_id %d is not a 2-D Riemann solver of this build", h->rp_id);
@@ -319,7 +440,20 @@ int validate_config(claw_solver* h) {
         return fail(h, 35, "limiter id %d of wave family %d is not defined by philim.f90 (0..5)", h->mthlim[mw], mw);
     return 0;
   }
-  return fail(h, 20, "3-D stepping is not available in this build");
+  if (h->rp_id < 5 || h->rp_id > 6) return fail(h, 30, "rp_id %d is not a 3-D Riemann solver of this build", h->rp_id);
+  if (h->method[5] != 0) return fail(h, 31, "capacity functions are not supported by the 3-D CUDA kernels yet (index_capa=%d)", h->method[5] - 1);
+  if (h->use_fwave) return fail(h, 32, "f-wave solvers are not supported by the CUDA kernels yet");
+  if (h->method[1] != 1 && h->method[1] != 2) return fail(h, 33, "order must be 1 or 2 (got %d)", h->method[1]);
+  {
+    const int mt = h->method[2];
+    if (!(mt == -1 || mt == 0 || mt == 10 || mt == 11 || mt == 20 || mt == 21 || mt == 22))
+      return fail(h, 34, "transverse_waves must be one of 0, 10, 11, 20, 21, 22 in 3-D (got %d)", mt);
+    if (mt >= 20 && h->method[1] != 2) return fail(h, 34, "transverse_waves=%d needs order=2 (flux3.f90:66-74)", mt);
+  }
+  for (int mw = 0; mw < h->mwaves; ++mw)
+    if (h->mthlim[mw] < 0 || h->mthlim[mw] > 5)
+      return fail(h, 35, "limiter id %d of wave family %d is not defined by philim.f90 (0..5)", h->mthlim[mw], mw);
+  return 0;
 }
 
 }  // namespace
@@ -345,8 +479,8 @@ int claw_create(claw_solver** out, int ndim, int rp_id, int meqn, int mwaves, in
   if (num_ghost != 2) return fail(nullptr, 3, "claw_create: num_ghost must be 2 (classic solvers), got %d", num_ghost);
   if (meqn < 1 || meqn > 8 || mwaves < 1 || mwaves > 8 || maux < 0)
     return fail(nullptr, 4, "claw_create: bad sizes meqn=%d mwaves=%d maux=%d", meqn, mwaves, maux);
-  static const int k_meqn[] = {0, 1, 3, 4, 3, 4}, k_mwaves[] = {0, 1, 2, 4, 3, 2}, k_ndim[] = {0, 2, 2, 2, 2, 3};
-  if (rp_id < 1 || rp_id > 5) return fail(nullptr, 5, "claw_create: unknown rp_id %d", rp_id);
+  static const int k_meqn[] = {0, 1, 3, 4, 3, 4, 5}, k_mwaves[] = {0, 1, 2, 4, 3, 2, 3}, k_ndim[] = {0, 2, 2, 2, 2, 3, 3};
+  if (rp_id < 1 || rp_id > 6) return fail(nullptr, 5, "claw_create: unknown rp_id %d", rp_id);
   if (k_meqn[rp_id] != meqn || k_mwaves[rp_id] != mwaves || k_ndim[rp_id] != ndim)
     return fail(nullptr, 6, "claw_create: rp_id %d expects ndim=%d meqn=%d mwaves=%d (got %d, %d, %d)", rp_id,
                 k_ndim[rp_id], k_meqn[rp_id], k_mwaves[rp_id], ndim, meqn, mwaves);
@@ -363,6 +497,7 @@ int claw_create(claw_solver** out, int ndim, int rp_id, int meqn, int mwaves, in
   long long rows = 1;
   for (int d = 1; d < ndim; ++d) rows *= h->g.nt[d];
   h->g.plane = (long long)h->g.pitch * rows;
+  h->g.kstride = (ndim == 3) ? (long long)h->g.pitch * h->g.nt[1] : 0;
   h->rp_id = rp_id; h->meqn = meqn; h->mwaves = mwaves; h->maux = maux;
   h->device = device;
   h->stream = (cudaStream_t)stream;
@@ -371,6 +506,8 @@ int claw_create(claw_solver** out, int ndim, int rp_id, int meqn, int mwaves, in
   long long cells = 1;
   for (int d = 0; d < ndim; ++d) cells *= h->g.nt[d];
   h->work_elems = WORK_HDR + (size_t)cells * (meqn > maux ? meqn : maux);
+  // 3-D dimension-split steps use the staging area as a third q buffer (x: cur->alt, y: alt->tmp, z: tmp->alt)
+  if (ndim == 3 && h->work_elems < WORK_HDR + h->q_elems) h->work_elems = WORK_HDR + h->q_elems;
   cudaError_t e = cudaSetDevice(device);
   cudaDeviceProp prop;
   if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
@@ -474,9 +611,7 @@ int claw_get_q(claw_solver* h, double* host_q) {
   if (check_handle(h)) return 1;
   if (int rc = ensure_buffers(h)) return rc;
   CK(h, cudaSetDevice(h->device));
-  const Dev2& g = h->g;
-  return get_region(h, h->q[h->cur], h->meqn, host_q, g.ng, g.ng + g.n[0], g.ng, g.ng + g.n[1],
-                    (size_t)h->meqn * g.n[0] * sizeof(double), 0);
+  return get_interior(h, h->q[h->cur], h->meqn, host_q, false);
 }
 
 int claw_put_aux(claw_solver* h, const double* host_aux) {
@@ -502,9 +637,7 @@ int claw_get_qbc(claw_solver* h, double* host_qbc) {
   if (check_handle(h)) return 1;
   if (int rc = ensure_buffers(h)) return rc;
   CK(h, cudaSetDevice(h->device));
-  const Dev2& g = h->g;
-  return get_region(h, h->q[h->cur], h->meqn, host_qbc, 0, g.nt[0], 0, g.nt[1],
-                    (size_t)h->meqn * g.nt[0] * sizeof(double), 0);
+  return get_all(h, h->q[h->cur], h->meqn, host_qbc);
 }
 
 int claw_put_auxbc(claw_solver* h, const double* host_auxbc) {
@@ -534,8 +667,7 @@ int claw_step_launch(claw_solver* h, const double* delta, double dt, int fill_gh
   if (fill_ghosts)
     if (int rc = claw_apply_bcs(h)) return rc;
   CK(h, cudaMemsetAsync(h->work, 0, sizeof(double), h->stream));
-  const int kind = (h->method[2] < 0) ? 1 : 0;         // method(3) = -1: dimensional splitting (classic/solver.py:186)
-  if (int rc = launch_step2(h, delta[0], delta[1], dt, kind, 1, 1, h->q[h->cur], h->q[h->cur ^ 1])) return rc;
+  if (int rc = launch_step(h, delta, dt, h->q[h->cur], h->q[h->cur ^ 1])) return rc;
   CK(h, cudaMemcpyAsync(h->h_cfl, h->work, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaEventRecord(h->ev_cfl, h->stream));
   return 0;
@@ -579,20 +711,25 @@ int claw_sync(claw_solver* h) {
 
 int claw_halo_elems(const claw_solver* h, size_t* elems) {
   if (check_handle(h)) return 1;
-  if (h->g.ndim != 2) { g_last_error = "3-D halo exchange is not available in this build"; return 20; }
-  *elems = (size_t)h->meqn * 2 * h->g.nt[0];
+  *elems = (h->g.ndim == 2) ? (size_t)h->meqn * 2 * h->g.nt[0] : (size_t)h->meqn * 2 * h->g.kstride;
   return 0;
 }
 
 int claw_halo_pack(claw_solver* h, int side, double* d_buf) {
   if (check_handle(h)) return 1;
-  if (h->g.ndim != 2) return fail(h, 20, "3-D halo exchange is not available in this build");
   if (int rc = ensure_buffers(h)) return rc;
   CK(h, cudaSetDevice(h->device));
   const Dev2& g = h->g;
-  const int j0 = side == 0 ? g.ng : g.n[1];            // interior rows [2,4) or [my, my+2)
-  const long long n = (long long)h->meqn * 2 * g.nt[0];
-  halo_pack2<<<grid_for(n, 256), 256, 0, h->stream>>>(h->q[h->cur], d_buf, h->meqn, g.nt[0], j0, g.pitch, g.plane);
+  const int last = g.ndim - 1;
+  const int s0 = side == 0 ? g.ng : g.n[last];         // interior rows/planes [2,4) or [m, m+2)
+  if (g.ndim == 2) {
+    const long long n = (long long)h->meqn * 2 * g.nt[0];
+    halo_pack2<<<grid_for(n, 256), 256, 0, h->stream>>>(h->q[h->cur], d_buf, h->meqn, g.nt[0], s0, g.pitch, g.plane);
+  } else {
+    const long long len = 2 * g.kstride;
+    gather_runs<<<grid_for(len * h->meqn, 256), 256, 0, h->stream>>>(h->q[h->cur] + (long long)s0 * g.kstride, g.plane,
+                                                                     d_buf, len, h->meqn);
+  }
   ++h->launches;
   CK(h, cudaGetLastError());
   return 0;
@@ -600,13 +737,19 @@ int claw_halo_pack(claw_solver* h, int side, double* d_buf) {
 
 int claw_halo_unpack(claw_solver* h, int side, const double* d_buf) {
   if (check_handle(h)) return 1;
-  if (h->g.ndim != 2) return fail(h, 20, "3-D halo exchange is not available in this build");
   if (int rc = ensure_buffers(h)) return rc;
   CK(h, cudaSetDevice(h->device));
   const Dev2& g = h->g;
-  const int j0 = side == 0 ? 0 : g.n[1] + g.ng;        // ghost rows [0,2) or [my+2, my+4)
-  const long long n = (long long)h->meqn * 2 * g.nt[0];
-  halo_unpack2<<<grid_for(n, 256), 256, 0, h->stream>>>(h->q[h->cur], d_buf, h->meqn, g.nt[0], j0, g.pitch, g.plane);
+  const int last = g.ndim - 1;
+  const int s0 = side == 0 ? 0 : g.n[last] + g.ng;     // ghost rows/planes [0,2) or [m+2, m+4)
+  if (g.ndim == 2) {
+    const long long n = (long long)h->meqn * 2 * g.nt[0];
+    halo_unpack2<<<grid_for(n, 256), 256, 0, h->stream>>>(h->q[h->cur], d_buf, h->meqn, g.nt[0], s0, g.pitch, g.plane);
+  } else {
+    const long long len = 2 * g.kstride;
+    scatter_runs<<<grid_for(len * h->meqn, 256), 256, 0, h->stream>>>(h->q[h->cur] + (long long)s0 * g.kstride, g.plane,
+                                                                      d_buf, len, h->meqn);
+  }
   ++h->launches;
   CK(h, cudaGetLastError());
   return 0;
@@ -621,11 +764,10 @@ int claw_time_sweep(claw_solver* h, const double* delta, double dt, int reps, do
   cudaEvent_t a, b;
   CK(h, cudaEventCreate(&a));
   CK(h, cudaEventCreate(&b));
-  const int kind = (h->method[2] < 0) ? 1 : 0;
   CK(h, cudaMemsetAsync(h->work, 0, sizeof(double), h->stream));
   CK(h, cudaEventRecord(a, h->stream));
   for (int r = 0; r < reps; ++r)
-    if (int rc = launch_step2(h, delta[0], delta[1], dt, kind, 1, 1, h->q[h->cur], h->q[h->cur ^ 1])) return rc;
+    if (int rc = launch_step(h, delta, dt, h->q[h->cur], h->q[h->cur ^ 1])) return rc;
   CK(h, cudaEventRecord(b, h->stream));
   CK(h, cudaEventSynchronize(b));
   float ms = 0.f;
@@ -687,10 +829,7 @@ int claw_step2_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, int
   if (maux > 0 && (rc = claw_put_auxbc(h, aux))) return host_fail(h, rc);
   const double delta[2] = {dx, dy};
   if ((rc = claw_step(h, delta, dt, 0, cfl))) return host_fail(h, rc);
-  const Dev2& g = h->g;
-  rc = get_region(h, h->q[h->cur ^ 1], meqn, qnew, g.ng, g.ng + mx, g.ng, g.ng + my,
-                  (size_t)meqn * g.nt[0] * sizeof(double),
-                  ((size_t)g.ng * g.nt[0] + g.ng) * meqn * sizeof(double));
+  rc = get_interior(h, h->q[h->cur ^ 1], meqn, qnew, true);
   return rc ? host_fail(h, rc) : 0;
 }
 
@@ -716,25 +855,71 @@ int claw_step2ds_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, i
   if (cudaMemcpyAsync(h->h_cfl, h->work, sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
     return fail(nullptr, 43, "cfl copy failed");
   const Dev2& g = h->g;
-  if (ids == 1)   // rows: all; columns: interior   (step2ds.f90:96,149)
-    rc = get_region(h, h->q[h->cur ^ 1], meqn, qnew, g.ng, g.ng + mx, 0, g.nt[1],
-                    (size_t)meqn * g.nt[0] * sizeof(double), (size_t)g.ng * meqn * sizeof(double));
-  else            // columns: all; rows: interior   (step2ds.f90:180,237)
-    rc = get_region(h, h->q[h->cur ^ 1], meqn, qnew, 0, g.nt[0], g.ng, g.ng + my,
-                    (size_t)meqn * g.nt[0] * sizeof(double), (size_t)g.ng * g.nt[0] * meqn * sizeof(double));
+  {
+    const int zero[3] = {0, 0, 0}, hn[3] = {g.nt[0], g.nt[1], 1};
+    if (ids == 1) {   // rows: all; columns: interior   (step2ds.f90:96,149)
+      const int lo[3] = {g.ng, 0, 0}, hi[3] = {g.ng + mx, g.nt[1], 1};
+      rc = get_region(h, h->q[h->cur ^ 1], meqn, qnew, lo, hi, zero, hn);
+    } else {          // columns: all; rows: interior   (step2ds.f90:180,237)
+      const int lo[3] = {0, g.ng, 0}, hi[3] = {g.nt[0], g.ng + my, 1};
+      rc = get_region(h, h->q[h->cur ^ 1], meqn, qnew, lo, hi, zero, hn);
+    }
+  }
   if (rc) return host_fail(h, rc);
   if (cfl) *cfl = *h->h_cfl;    // get_region synchronised the stream
   return 0;
 }
 
-int claw_step3_host(int, int, int, int, int, int, int, int, const double*, double*, const double*, double, double,
-                    double, double, const int*, const int*, int, int, const double*, int, int, double*) {
-  return fail(nullptr, 20, "claw_step3_host: 3-D stepping is not available in this build");
+int claw_step3_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, int mx, int my, int mz,
+                    const double* qold, double* qnew, const double* aux, double dx, double dy, double dz, double dt,
+                    const int* method7, const int* mthlim, int use_fwave, int rp_id, const double* cparam,
+                    int ncparam, int mode, double* cfl) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  if (num_ghost != 2) return fail(nullptr, 3, "claw_step3_host: num_ghost must be 2");
+  if (maxm < mx || maxm < my || maxm < mz) return fail(nullptr, 40, "claw_step3_host: maxm=%d < max(mx,my,mz)", maxm);
+  const int n[3] = {mx, my, mz};
+  claw_solver* h = nullptr;
+  if (int rc = host_handle(3, rp_id, meqn, mwaves, maux, n, &h)) return rc;
+  int rc;
+  if ((rc = claw_set_mode(h, mode))) return host_fail(h, rc);
+  if ((rc = claw_set_cparam(h, cparam, ncparam))) return host_fail(h, rc);
+  if ((rc = claw_set_method(h, method7, mthlim, use_fwave))) return host_fail(h, rc);
+  if (h->method[2] < 0) return host_fail(h, fail(h, 41, "claw_step3_host: method(3) = -1 (dimensional splitting) belongs to step3ds"));
+  if ((rc = claw_put_qbc(h, qold))) return host_fail(h, rc);
+  if (maux > 0 && (rc = claw_put_auxbc(h, aux))) return host_fail(h, rc);
+  const double delta[3] = {dx, dy, dz};
+  if ((rc = claw_step(h, delta, dt, 0, cfl))) return host_fail(h, rc);
+  rc = get_interior(h, h->q[h->cur ^ 1], meqn, qnew, true);
+  return rc ? host_fail(h, rc) : 0;
 }
 
-int claw_step3ds_host(int, int, int, int, int, int, int, int, const double*, double*, const double*, double, double,
-                      double, double, const int*, const int*, int, int, int, const double*, int, int, double*) {
-  return fail(nullptr, 20, "claw_step3ds_host: 3-D stepping is not available in this build");
+int claw_step3ds_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, int mx, int my, int mz,
+                      const double* qold, double* qnew, const double* aux, double dx, double dy, double dz, double dt,
+                      const int* method7, const int* mthlim, int idir, int use_fwave, int rp_id,
+                      const double* cparam, int ncparam, int mode, double* cfl) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  if (num_ghost != 2) return fail(nullptr, 3, "claw_step3ds_host: num_ghost must be 2");
+  if (maxm < mx || maxm < my || maxm < mz) return fail(nullptr, 40, "claw_step3ds_host: maxm=%d < max(mx,my,mz)", maxm);
+  if (idir < 1 || idir > 3) return fail(nullptr, 42, "claw_step3ds_host: idir must be 1, 2 or 3 (got %d)", idir);
+  const int n[3] = {mx, my, mz};
+  claw_solver* h = nullptr;
+  if (int rc = host_handle(3, rp_id, meqn, mwaves, maux, n, &h)) return rc;
+  int rc;
+  if ((rc = claw_set_mode(h, mode))) return host_fail(h, rc);
+  if ((rc = claw_set_cparam(h, cparam, ncparam))) return host_fail(h, rc);
+  if ((rc = claw_set_method(h, method7, mthlim, use_fwave))) return host_fail(h, rc);
+  if (h->method[2] >= 0) return host_fail(h, fail(h, 41, "claw_step3ds_host: needs method(3) = -1 (dimensional splitting)"));
+  if ((rc = claw_put_qbc(h, qold))) return host_fail(h, rc);
+  if (maux > 0 && (rc = claw_put_auxbc(h, aux))) return host_fail(h, rc);
+  if (cudaMemsetAsync(h->work, 0, sizeof(double), h->stream) != cudaSuccess) return fail(nullptr, 43, "memset failed");
+  const double delta[3] = {dx, dy, dz};
+  if ((rc = launch_pass3(h, delta, dt, idir - 1, 1, h->q[h->cur], h->q[h->cur ^ 1]))) return host_fail(h, rc);
+  if (cudaMemcpyAsync(h->h_cfl, h->work, sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
+    return fail(nullptr, 43, "cfl copy failed");
+  // the pass wrote every cell (cells outside step3ds's range are copied through from qold)
+  if ((rc = get_all(h, h->q[h->cur ^ 1], meqn, qnew))) return host_fail(h, rc);
+  if (cfl) *cfl = *h->h_cfl;    // get_region synchronised the stream
+  return 0;
 }
 
 int claw_host_release(void) {

@@ -1,0 +1,642 @@
+// Fused 3-D classic wave-propagation sweeps for sm_100a (fp64 stencil, FP64-pipe bound; no
+// tensor cores).  One kernel per sweep direction does what the reference does in
+// step3.f90 / step3ds.f90 + flux3.f90 + limiter.f90 + philim.f90 + rpn3/rpt3/rptt3 for that
+// direction: normal solve, CFL max, wave limiter, second-order correction, the 4+4 transverse
+// and 8 double-transverse solves, and the update of the 3x3 neighbourhood of pencils.
+//
+// Design ("2.5-D blocking"): a CTA owns a 2-D tile of columns (thread-x <-> i, thread-y <-> j
+// or k) and marches along the third direction.
+//   * The transverse solves are organised per CELL, not per interface: cell c owns the
+//     "p-side" of interface c (apdq, imp = 2) and the "m-side" of interface c+1 (amdq,
+//     imp = 1) -- exactly the solves that read the aux column of cell c (i1 = i-2+imp,
+//     rpt3_vc_acoustics.f90:100) and that add into gadd/hadd(.,.,.,c) (flux3.f90:390-469,
+//     513-594).  A cell therefore builds its own 12 gadd/hadd vectors with the reference's
+//     statement order and nothing but amdq/cqxx of the next interface crosses threads.
+//   * The reference's scatter (each pencil adds into 9 pencils of qnew, step3.f90:193-226)
+//     becomes a gather: the 12 vectors go to shared memory once, and each cell adds the nine
+//     contributions it receives in the reference's pencil order, each as the same two
+//     sequential addends (g term, then h term).  No atomics, bit-reproducible.
+//   * x-sweep (sweep3_x): tile (i, j), lanes along i (neighbouring interfaces by warp shuffle),
+//     march in k with three running accumulators (planes k-1, k, k+1).
+//   * y-/z-sweep (sweep3_march): tile (i, k) / (i, j), march ALONG the pencil: consecutive
+//     interfaces are produced by the same thread on consecutive steps (limiter pipeline in
+//     registers); the nine contributions of a cell meet in the same march step.
+// Unsplit: the x-sweep writes qout = qin + (its 9 terms), the y- and z-sweeps read-modify-
+// write qout, so every cell receives its 27 addends in the reference order.
+// Dimension-split (method(3) < 0): same kernels without the exchange; each pass writes the
+// whole array (cells outside step3ds's range are copied through), ping-ponging two buffers.
+//
+// Array coordinates (I,J,K) = Fortran (i+1, j+1, k+1); interior cells [2, n+2); interface I
+// separates cells I-1 and I.
+#pragma once
+#include "rp3.cuh"
+#include "sweep2.cuh"
+
+namespace clawcuda {
+
+#ifndef CLAWCUDA_SWEEP3_PARAMS
+#define CLAWCUDA_SWEEP3_PARAMS
+struct Sweep3Params {
+  const double* qin;        // SoA planes: component m at + m*plane, (I,J,K) at K*kstride + J*pitch + I
+  double* qout;
+  const double* aux;
+  unsigned long long* cfl_bits;
+  int n[3];                 // interior cells
+  int pitch;
+  long long kstride;        // pitch * (my+4)
+  long long plane;          // kstride * (mz+4)
+  double dtd[3];            // dt/dx, dt/dy, dt/dz
+  int order;                // method(2)
+  int m3, m4;               // flux3.f90:186-194 (m3 = -1: dimensional splitting)
+  int limit;
+  int mthlim[8];
+  int first_pass;           // unsplit: 1 -> qout = qin + terms (x-sweep), 0 -> qout += terms
+  int seg;                  // cells per march segment (blockIdx.z)
+  RpParams rp;
+};
+#endif
+
+namespace CLAW_NS {
+
+template <int M, int W>
+__device__ __forceinline__ void wave_dots3(const double (*wave)[M], const double (*waveR)[M], double* wnorm2,
+                                           double* dotr) {
+  // limiter.f90:33-38
+#pragma unroll
+  for (int mw = 0; mw < W; ++mw) {
+    double wn = 0.0, dr = 0.0;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      wn = (m == 0) ? from0(wave[mw][m] * wave[mw][m]) : wn + wave[mw][m] * wave[mw][m];
+      dr = (m == 0) ? from0(wave[mw][m] * waveR[mw][m]) : dr + wave[mw][m] * waveR[mw][m];
+    }
+    wnorm2[mw] = wn; dotr[mw] = dr;
+  }
+}
+
+template <int M, int W>
+__device__ __forceinline__ void limit_waves3(const int* mthlim, double (*wave)[M], const double* s,
+                                             const double* wnorm2, const double* dotl, const double* dotr) {
+  // limiter.f90:39-50
+#pragma unroll
+  for (int mw = 0; mw < W; ++mw) {
+    const int meth = mthlim[mw];
+    if (meth == 0) continue;
+    if (wnorm2[mw] == 0.0) continue;
+    const double wl = philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
+#pragma unroll
+    for (int m = 0; m < M; ++m) wave[mw][m] = wl * wave[mw][m];
+  }
+}
+
+// flux3.f90:231-259 (use_fwave = .false.): cqxx (= the fadd increment) of one interface
+template <int M, int W>
+__device__ __forceinline__ void second_order3(double dtd, const double (*wave)[M], const double* s, double* cqxx) {
+  const double dtdxave = 0.5 * (dtd + dtd);
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    double c = 0.0;
+#pragma unroll
+    for (int mw = 0; mw < W; ++mw) {
+      const double t = 0.5 * fabs(s[mw]) * (1.0 - fabs(s[mw]) * dtdxave) * wave[mw][m];
+      c = (mw == 0) ? from0(t) : c + t;
+    }
+    cqxx[m] = c;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// One side of cell c's transverse work: SIDE 0 = the p-side of interface c (asdq = apdq, imp = 2),
+// SIDE 1 = the m-side of interface c+1 (asdq = amdq, imp = 1).  Accumulates into
+// g[e][m], h[e][m] with e = (slice+1)*2 + (side-1)  <->  gadd/hadd(m, side, slice, c).
+// A[dy][dz][ma] = aux of the cell column at offsets (dy, dz) in the (y-like, z-like) directions
+// = aux{1,2,3}(ma, i1, 1..3) of flux3 (step3.f90:144-150).
+// Statement order follows flux3.f90:272-291 (rpt3), 296-344 (cqxx splits), 353-384 (c*2, rptt3),
+// 390-469 (gadd), 479-507 (b*, rptt3), 513-594 (hadd).
+// -------------------------------------------------------------------------------------------
+template <class RP, int IXYZ, int SIDE>
+__device__ __forceinline__ void flux3_side(const RpParams& P, int m3, int m4, double dtdx, double dty, double dtz,
+                                           const double* asdq, const double* cqxx, const double* ctx,
+                                           const double (*A)[3][RP::MAUX > 0 ? RP::MAUX : 1],
+                                           double (*g)[RP::MEQN], double (*h)[RP::MEQN]) {
+  constexpr int M = RP::MEQN;
+  constexpr double SGN = (SIDE == 0) ? -1.0 : 1.0;        // cqxx enters the p-side with -, the m-side with +
+  const double hd = 0.5 * dtdx;
+  const double sixth = 1.0 / 6.0;
+  const double sdz = sixth * dtdx * dtz;                   // (1/6)*dtdx1d*dtdz   (flux3.f90:412)
+  const double sdy = sixth * dtdx * dty;                   // (1/6)*dtdx1d*dtdy   (flux3.f90:537)
+  // ---- z-like splits (rpt3 icoor = 3) ---------------------------------------------------
+  double cm[M], cp[M], cmq[M], cpq[M];
+  RP::template transverse<IXYZ, 3>(P, ctx, A[1][0], A[1][1], A[1][2], asdq, cm, cp);
+#pragma unroll
+  for (int m = 0; m < M; ++m) { cmq[m] = 0.0; cpq[m] = 0.0; }
+  if (m3 == 2) RP::template transverse<IXYZ, 3>(P, ctx, A[1][0], A[1][1], A[1][2], cqxx, cmq, cpq);
+  // ---- y-like splits (rpt3 icoor = 2) ---------------------------------------------------
+  double bm[M], bp[M], bmq[M], bpq[M];
+  RP::template transverse<IXYZ, 2>(P, ctx, A[0][1], A[1][1], A[2][1], asdq, bm, bp);
+#pragma unroll
+  for (int m = 0; m < M; ++m) { bmq[m] = 0.0; bpq[m] = 0.0; }
+  if (m3 == 2) RP::template transverse<IXYZ, 2>(P, ctx, A[0][1], A[1][1], A[2][1], cqxx, bmq, bpq);
+  // ---- G: y-like fluxes ---------------------------------------------------------------------
+  {
+    double bmcp[M], bpcp[M], bmcm[M], bpcm[M];
+    if (m4 > 0) {
+      double cp2[M], cm2[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        if (m4 == 2) { cp2[m] = cp[m] + SGN * (3.0 * cpq[m]); cm2[m] = cm[m] + SGN * (3.0 * cmq[m]); }
+        else { cp2[m] = cp[m]; cm2[m] = cm[m]; }
+      }
+      RP::template transverse<IXYZ, 2>(P, ctx, A[0][2], A[1][2], A[2][2], cp2, bmcp, bpcp);   // impt = 2
+      RP::template transverse<IXYZ, 2>(P, ctx, A[0][0], A[1][0], A[2][0], cm2, bmcm, bpcm);   // impt = 1
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      g[2][m] = g[2][m] - hd * bm[m];                                  // gadd(m,1,0,.)
+      g[3][m] = g[3][m] - hd * bp[m];                                  // gadd(m,2,0,.)
+      if (m4 > 0) {
+        g[3][m] = g[3][m] + sdz * (bpcp[m] - bpcm[m]);
+        g[2][m] = g[2][m] + sdz * (bmcp[m] - bmcm[m]);
+        g[5][m] = g[5][m] - sdz * bpcp[m];                             // gadd(m,2,1,.)
+        g[4][m] = g[4][m] - sdz * bmcp[m];                             // gadd(m,1,1,.)
+        g[1][m] = g[1][m] + sdz * bpcm[m];                             // gadd(m,2,-1,.)
+        g[0][m] = g[0][m] + sdz * bmcm[m];                             // gadd(m,1,-1,.)
+      }
+      if (m3 >= 2) {
+        if (SIDE == 0) { g[3][m] = g[3][m] + dtdx * bpq[m]; g[2][m] = g[2][m] + dtdx * bmq[m]; }
+        else           { g[3][m] = g[3][m] - dtdx * bpq[m]; g[2][m] = g[2][m] - dtdx * bmq[m]; }
+      }
+    }
+  }
+  // ---- H: z-like fluxes ---------------------------------------------------------------------
+  {
+    double bmcp[M], bpcp[M], bmcm[M], bpcm[M];
+    if (m4 > 0) {
+      double bp2[M], bm2[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        if (m4 == 2) { bp2[m] = bp[m] + SGN * (3.0 * bpq[m]); bm2[m] = bm[m] + SGN * (3.0 * bmq[m]); }
+        else { bp2[m] = bp[m]; bm2[m] = bm[m]; }
+      }
+      RP::template transverse<IXYZ, 3>(P, ctx, A[2][0], A[2][1], A[2][2], bp2, bmcp, bpcp);   // impt = 2
+      RP::template transverse<IXYZ, 3>(P, ctx, A[0][0], A[0][1], A[0][2], bm2, bmcm, bpcm);   // impt = 1
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      h[2][m] = h[2][m] - hd * cm[m];
+      h[3][m] = h[3][m] - hd * cp[m];
+      if (m4 > 0) {
+        h[3][m] = h[3][m] + sdy * (bpcp[m] - bpcm[m]);
+        h[2][m] = h[2][m] + sdy * (bmcp[m] - bmcm[m]);
+        h[5][m] = h[5][m] - sdy * bpcp[m];
+        h[4][m] = h[4][m] - sdy * bmcp[m];
+        h[1][m] = h[1][m] + sdy * bpcm[m];
+        h[0][m] = h[0][m] + sdy * bmcm[m];
+      }
+      if (m3 >= 2) {
+        if (SIDE == 0) { h[3][m] = h[3][m] + dtdx * cpq[m]; h[2][m] = h[2][m] + dtdx * cmq[m]; }
+        else           { h[3][m] = h[3][m] - dtdx * cpq[m]; h[2][m] = h[2][m] - dtdx * cmq[m]; }
+      }
+    }
+  }
+}
+
+// Both sides of cell c, results to shared memory: sm[(e*M + m)*NT] (g) and sm[((6+e)*M + m)*NT] (h)
+template <class RP, int IXYZ, int NT>
+__device__ __forceinline__ void flux3_cell(const Sweep3Params& P, double dtdx, double dty, double dtz,
+                                           const double* apdqC, const double* cqxxC, const double* ctxC,
+                                           const double* amdqR, const double* cqxxR, const double* ctxR,
+                                           const double (*A)[3][RP::MAUX > 0 ? RP::MAUX : 1], double* sm) {
+  constexpr int M = RP::MEQN;
+  double g[6][M], h[6][M];
+#pragma unroll
+  for (int e = 0; e < 6; ++e)
+#pragma unroll
+    for (int m = 0; m < M; ++m) { g[e][m] = 0.0; h[e][m] = 0.0; }
+  flux3_side<RP, IXYZ, 0>(P.rp, P.m3, P.m4, dtdx, dty, dtz, apdqC, cqxxC, ctxC, A, g, h);   // iteration i = c
+  flux3_side<RP, IXYZ, 1>(P.rp, P.m3, P.m4, dtdx, dty, dtz, amdqR, cqxxR, ctxR, A, g, h);   // iteration i = c+1
+#pragma unroll
+  for (int e = 0; e < 6; ++e)
+#pragma unroll
+    for (int m = 0; m < M; ++m) { sm[(e * M + m) * NT] = g[e][m]; sm[((6 + e) * M + m) * NT] = h[e][m]; }
+}
+
+// The (a, b) target term of a source pencil (step3.f90:198-225): a / b = offset of the target
+// pencil in the y-like / z-like direction.  sm = shared-memory slot of the SOURCE thread.
+template <int A, int B, int M, int NT>
+__device__ __forceinline__ void apply_target(double* acc, const double* sm, double dty, double dtz) {
+#define G_(side, slice) sm[((((slice) + 1) * 2 + (side)-1) * M + m) * NT]
+#define H_(side, slice) sm[((6 + ((slice) + 1) * 2 + (side)-1) * M + m) * NT]
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    double r = acc[m];
+    if (A == -1 && B == 0) { r = r - dty * G_(1, 0); r = r - dtz * (H_(2, -1) - H_(1, -1)); }
+    if (A == -1 && B == -1) { r = r - dty * G_(1, -1); r = r - dtz * H_(1, -1); }
+    if (A == 0 && B == -1) { r = r - dty * (G_(2, -1) - G_(1, -1)); r = r - dtz * H_(1, 0); }
+    if (A == 1 && B == -1) { r = r + dty * G_(2, -1); r = r - dtz * H_(1, 1); }
+    if (A == 1 && B == 0) { r = r + dty * G_(2, 0); r = r - dtz * (H_(2, 1) - H_(1, 1)); }
+    if (A == 1 && B == 1) { r = r + dty * G_(2, 1); r = r + dtz * H_(2, 1); }
+    if (A == 0 && B == 1) { r = r - dty * (G_(2, 1) - G_(1, 1)); r = r + dtz * H_(2, 0); }
+    if (A == -1 && B == 1) { r = r - dty * G_(1, 1); r = r + dtz * H_(2, -1); }
+    acc[m] = r;
+  }
+}
+// the pencil's own cell (step3.f90:194-197)
+template <int M, int NT>
+__device__ __forceinline__ void apply_center(double* acc, const double* sm, const double* qadd, const double* fdiff,
+                                             double dtdn, double dty, double dtz, bool transverse) {
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    double r = (acc[m] + qadd[m]) - dtdn * fdiff[m];
+    if (transverse) { r = r - dty * (G_(2, 0) - G_(1, 0)); r = r - dtz * (H_(2, 0) - H_(1, 0)); }
+    acc[m] = r;
+  }
+}
+#undef G_
+#undef H_
+
+template <int NT> __device__ __forceinline__ void block_max_cfl3(double cfl, unsigned long long* addr, double* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cfl = fmax(cfl, __shfl_xor_sync(0xffffffffu, cfl, o));
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  __syncthreads();
+  if (lane == 0) s_red[warp] = cfl;
+  __syncthreads();
+  if (warp == 0) {
+    double c = (lane < NT / 32) ? s_red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c = fmax(c, __shfl_xor_sync(0xffffffffu, c, o));
+    if (lane == 0 && c > 0.0) atomic_max_cfl(addr, c);
+  }
+}
+
+__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+template <class RP, int NT> struct Smem3 {
+  static constexpr size_t BYTES = (size_t)12 * RP::MEQN * NT * sizeof(double) + 64 * sizeof(double);
+};
+
+// =====================================================================================
+// x-sweep: block (32, BY); lanes <-> I (28 owner lanes + 2 halo lanes per side), thread-y <-> J,
+// march in K.   step3.f90:124-276 (unsplit) / step3ds.f90 idir = 1.
+// =====================================================================================
+template <class RP, int BY>
+__global__ void __launch_bounds__(32 * BY) sweep3_x(const __grid_constant__ Sweep3Params P) {
+  constexpr int M = RP::MEQN, W = RP::MWAVES, MA = RP::MAUX > 0 ? RP::MAUX : 1, NC = RP::NCTX > 0 ? RP::NCTX : 1;
+  constexpr int NT = 32 * BY;
+  constexpr int TX = 28;
+  extern __shared__ double smem[];
+  const int t = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * 32 + t;
+  double* const sm = smem + tid;
+  double* const sred = smem + 12 * M * NT;
+
+  const bool split = P.m3 < 0;
+  const int nx = P.n[0] + 4, ny = P.n[1] + 4, nz = P.n[2] + 4;
+  const int I = blockIdx.x * TX + t;
+  const int Ic = I < nx ? I : nx - 1;
+  const int HT = split ? 0 : 1;                              // transverse halo of the tile
+  const int J = (split ? 0 : 1) + blockIdx.y * (BY - 2 * HT) + ty;
+  const int Jc = J < ny ? J : ny - 1;
+  const int Jm = Jc > 0 ? Jc - 1 : 0, Jp = Jc < ny - 1 ? Jc + 1 : ny - 1;
+  // output planes [kb, ke)
+  const int k_lo = split ? 0 : 2, k_hi = split ? nz : P.n[2] + 2;
+  const int kb = k_lo + blockIdx.z * P.seg;
+  const int ke = min(kb + P.seg, k_hi);
+  const int k0 = split ? kb : kb - 1, k1 = split ? ke - 1 : ke;     // pencil planes k0..k1
+
+  const double dtdx = P.dtd[0], dtdy = P.dtd[1], dtdz = P.dtd[2];
+  const bool second = (P.order != 1);
+  const bool limit = second && (P.limit != 0);
+  const bool transverse = P.m3 > 0;
+
+  const bool owner_lane = (t >= 2 && t <= 29 && I < nx) || (blockIdx.x == 0 && t < 2);
+  const bool interior_i = (I >= 2 && I <= P.n[0] + 1);
+  const bool row_pencil = (J >= 1 && J <= P.n[1] + 2);       // Fortran j in 0..my+1
+  const bool row_out = split ? (J < ny) : (ty >= 1 && ty <= BY - 2 && J >= 2 && J <= P.n[1] + 1);
+  const bool cfl_lane = (t >= 1) && (I >= 2) && (I <= P.n[0] + 2) && row_pencil;
+
+  const double* qbase = P.qin + (long long)Jc * P.pitch + Ic;
+  const double* abase = P.aux + Ic;
+  double q[M], qnext[M];
+  double acc0[M], acc1[M], acc2[M];
+  double A[3][3][MA];
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    qnext[m] = qbase[m * P.plane + (long long)k0 * P.kstride];
+    acc0[m] = 0.0; acc1[m] = qnext[m]; acc2[m] = 0.0;
+  }
+  if (RP::MAUX > 0) {
+    // planes k0-1 (dz slot 1 after the first rotation -> slot 0) and k0 (-> slot 1)
+    const int kz[2] = {k0 > 0 ? k0 - 1 : 0, k0};
+    const int jr[3] = {Jm, Jc, Jp};
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int ma = 0; ma < MA; ++ma) {
+        A[dy][0][ma] = 0.0;
+        A[dy][1][ma] = abase[ma * P.plane + (long long)kz[0] * P.kstride + (long long)jr[dy] * P.pitch];
+        A[dy][2][ma] = abase[ma * P.plane + (long long)kz[1] * P.kstride + (long long)jr[dy] * P.pitch];
+      }
+  }
+  double cfl = 0.0;
+
+  for (int k = k0; k <= k1; ++k) {
+    // ---- rotate: pencil plane k; prefetch plane k+1 -------------------------------------
+    const int kn = k + 1 < nz ? k + 1 : nz - 1;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      q[m] = qnext[m];
+      qnext[m] = qbase[m * P.plane + (long long)kn * P.kstride];
+      acc2[m] = qnext[m];
+    }
+    if (RP::MAUX > 0) {
+      const int jr[3] = {Jm, Jc, Jp};
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int ma = 0; ma < MA; ++ma) {
+          A[dy][0][ma] = A[dy][1][ma];
+          A[dy][1][ma] = A[dy][2][ma];
+          A[dy][2][ma] = abase[ma * P.plane + (long long)kn * P.kstride + (long long)jr[dy] * P.pitch];
+        }
+    }
+    const bool plane_pencil = (k >= 1 && k <= P.n[2] + 2);   // Fortran k in 0..mz+1
+    // ---- interface I (my left face) ------------------------------------------------------
+    double ql[M], auxl[MA];
+#pragma unroll
+    for (int m = 0; m < M; ++m) ql[m] = shfl_up1(q[m]);
+#pragma unroll
+    for (int ma = 0; ma < MA; ++ma) auxl[ma] = (RP::MAUX > 0) ? shfl_up1(A[1][1][ma]) : 0.0;
+    double wave[W][M], s[W], amdq[M], apdq[M], ctx[NC], cqxx[M];
+    RP::template normal<0>(P.rp, ql, q, auxl, A[1][1], wave, s, amdq, apdq, ctx);      // flux3.f90:201
+    if (cfl_lane && plane_pencil) {                                                     // flux3.f90:211-218
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtdx * s[mw]), -dtdx * s[mw]);
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) cqxx[m] = 0.0;
+    if (second) {
+      if (limit) {                                                                      // flux3.f90:228
+        double wnorm2[W], dotr[W], dotl[W];
+        {
+          double waveR[W][M];
+#pragma unroll
+          for (int mw = 0; mw < W; ++mw)
+#pragma unroll
+            for (int m = 0; m < M; ++m) waveR[mw][m] = shfl_dn1(wave[mw][m]);
+          wave_dots3<M, W>(wave, waveR, wnorm2, dotr);
+        }
+#pragma unroll
+        for (int mw = 0; mw < W; ++mw) dotl[mw] = shfl_up1(dotr[mw]);
+        limit_waves3<M, W>(P.mthlim, wave, s, wnorm2, dotl, dotr);
+      }
+      second_order3<M, W>(dtdx, wave, s, cqxx);                                         // flux3.f90:231-259
+    }
+    // ---- the next interface's left-going pieces (cell I owns the m-side of interface I+1) --
+    double amdqR[M], cqxxR[M], ctxR[NC];
+#pragma unroll
+    for (int m = 0; m < M; ++m) { amdqR[m] = shfl_dn1(amdq[m]); cqxxR[m] = shfl_dn1(cqxx[m]); }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) ctxR[c] = (RP::NCTX > 0) ? shfl_dn1(ctx[c]) : 0.0;
+    double qadd[M], fdiff[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      qadd[m] = (0.0 - dtdx * apdq[m]) - dtdx * amdqR[m];                              // flux3.f90:205-208
+      fdiff[m] = (0.0 + cqxxR[m]) - (0.0 + cqxx[m]);                                    // fadd(i+1) - fadd(i)
+    }
+    if (split) {
+      // step3ds.f90:195-198: only the pencil itself is updated; everything else is copied through
+      const bool upd = interior_i && row_pencil && plane_pencil;
+      if (owner_lane && row_out && k >= kb && k < ke) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          const double r = (q[m] + qadd[m]) - dtdx * fdiff[m];
+          P.qout[m * P.plane + (long long)k * P.kstride + (long long)J * P.pitch + I] = upd ? r : q[m];
+        }
+      }
+      continue;
+    }
+    if (transverse) flux3_cell<RP, 0, NT>(P, dtdx, dtdy, dtdz, apdq, cqxx, ctx, amdqR, cqxxR, ctxR, A, sm);
+    __syncthreads();
+    if (row_out) {
+      if (transverse) {
+        // pencils (J-1, k), (J, k), (J+1, k) in this order (step3.f90:124-125: k outer, j inner);
+        // a = J_target - J_source, b = plane_target - k
+        apply_target<1, -1, M, NT>(acc0, sm - 32, dtdy, dtdz);
+        apply_target<0, -1, M, NT>(acc0, sm, dtdy, dtdz);
+        apply_target<-1, -1, M, NT>(acc0, sm + 32, dtdy, dtdz);
+        apply_target<1, 0, M, NT>(acc1, sm - 32, dtdy, dtdz);
+        apply_center<M, NT>(acc1, sm, qadd, fdiff, dtdx, dtdy, dtdz, true);
+        apply_target<-1, 0, M, NT>(acc1, sm + 32, dtdy, dtdz);
+        apply_target<1, 1, M, NT>(acc2, sm - 32, dtdy, dtdz);
+        apply_target<0, 1, M, NT>(acc2, sm, dtdy, dtdz);
+        apply_target<-1, 1, M, NT>(acc2, sm + 32, dtdy, dtdz);
+      } else {
+        apply_center<M, NT>(acc1, sm, qadd, fdiff, dtdx, dtdy, dtdz, false);
+      }
+      if (owner_lane && interior_i && k - 1 >= kb && k - 1 < ke) {
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+          P.qout[m * P.plane + (long long)(k - 1) * P.kstride + (long long)J * P.pitch + I] = acc0[m];
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) { acc0[m] = acc1[m]; acc1[m] = acc2[m]; }
+    __syncthreads();
+  }
+  block_max_cfl3<NT>(cfl, P.cfl_bits, sred);
+}
+
+// =====================================================================================
+// y-sweep (IXYZ = 1: march J, thread-y <-> K) and z-sweep (IXYZ = 2: march K, thread-y <-> J);
+// thread-x <-> I.   step3.f90:283-431 / 439-593, step3ds.f90 idir = 2 / 3.
+// =====================================================================================
+template <class RP, int IXYZ, int BX, int BY>
+__global__ void __launch_bounds__(BX * BY) sweep3_march(const __grid_constant__ Sweep3Params P) {
+  constexpr int M = RP::MEQN, W = RP::MWAVES, MA = RP::MAUX > 0 ? RP::MAUX : 1, NC = RP::NCTX > 0 ? RP::NCTX : 1;
+  constexpr int NT = BX * BY;
+  constexpr int TD = (IXYZ == 1) ? 2 : 1;                    // array dimension carried by thread-y
+  extern __shared__ double smem[];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * BX + tx;
+  double* const sm = smem + tid;
+  double* const sred = smem + 12 * M * NT;
+
+  const bool split = P.m3 < 0;
+  const int nx = P.n[0] + 4, nT = P.n[TD] + 4, nlen = P.n[IXYZ] + 4, mlen = P.n[IXYZ];
+  const int HT = split ? 0 : 1;
+  const int I = (split ? 0 : 1) + blockIdx.x * (BX - 2 * HT) + tx;
+  const int T = (split ? 0 : 1) + blockIdx.y * (BY - 2 * HT) + ty;
+  const int Ic = I < nx ? I : nx - 1, Tc = T < nT ? T : nT - 1;
+  const int Im = Ic > 0 ? Ic - 1 : 0, Ip = Ic < nx - 1 ? Ic + 1 : nx - 1;
+  const int Tm = Tc > 0 ? Tc - 1 : 0, Tp = Tc < nT - 1 ? Tc + 1 : nT - 1;
+  const long long strideT = (IXYZ == 1) ? P.kstride : (long long)P.pitch;     // thread-y stride
+  const long long strideN = (IXYZ == 1) ? (long long)P.pitch : P.kstride;     // march stride
+  // y-sweep: y-like = z (thread-y), z-like = x (thread-x).  z-sweep: y-like = x, z-like = y.
+  const double dtdn = P.dtd[IXYZ];
+  const double dty = (IXYZ == 1) ? P.dtd[2] : P.dtd[0];
+  const double dtz = (IXYZ == 1) ? P.dtd[0] : P.dtd[1];
+
+  const int c_lo = split ? 0 : 2, c_hi = split ? nlen : mlen + 2;
+  const int cb = c_lo + blockIdx.z * P.seg;
+  const int ce = min(cb + P.seg, c_hi);
+
+  const bool second = (P.order != 1);
+  const bool limit = second && (P.limit != 0);
+  const bool transverse = P.m3 > 0;
+  const bool pencil = (I >= 1 && I <= P.n[0] + 2 && T >= 1 && T <= P.n[TD] + 2);
+  const bool out_thread = split ? (I < nx && T < nT)
+                                : (tx >= 1 && tx <= BX - 2 && ty >= 1 && ty <= BY - 2 && I >= 2 && I <= P.n[0] + 1 &&
+                                   T >= 2 && T <= P.n[TD] + 1);
+
+  const long long col = (long long)Tc * strideT + Ic;
+  const double* qcol = P.qin + col;
+  double* ocol = P.qout + (long long)T * strideT + I;
+  double q1[M], q2[M];                                       // q(n-1), q(n-2)
+  double auxP[MA];                                           // aux(n-1)
+  double waveP[W][M], sP[W], amdqP[M], apdqP[M], ctxP[NC], dotlP[W];   // interface n-1 (pending, unlimited)
+  double apdqC[M], cqxxC[M], ctxC[NC];                       // interface n-2 (finished): the p-side of cell n-2
+#pragma unroll
+  for (int m = 0; m < M; ++m) { q1[m] = 0.0; q2[m] = 0.0; amdqP[m] = 0.0; apdqP[m] = 0.0; apdqC[m] = 0.0; cqxxC[m] = 0.0; }
+#pragma unroll
+  for (int mw = 0; mw < W; ++mw) {
+    sP[mw] = 0.0; dotlP[mw] = 0.0;
+#pragma unroll
+    for (int m = 0; m < M; ++m) waveP[mw][m] = 0.0;
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) { ctxP[c] = 0.0; ctxC[c] = 0.0; }
+#pragma unroll
+  for (int ma = 0; ma < MA; ++ma) auxP[ma] = 1.0;
+  double cfl = 0.0;
+
+  for (int n = cb - 2; n <= ce + 1; ++n) {
+    const int nc = n < 0 ? 0 : (n < nlen ? n : nlen - 1);
+    double qN[M], auxN[MA];
+#pragma unroll
+    for (int m = 0; m < M; ++m) qN[m] = qcol[m * P.plane + (long long)nc * strideN];
+#pragma unroll
+    for (int ma = 0; ma < MA; ++ma) auxN[ma] = (RP::MAUX > 0) ? P.aux[ma * P.plane + col + (long long)nc * strideN] : 0.0;
+    // ---- interface n (raw) ---------------------------------------------------------------
+    double waveN[W][M], sN[W], amdqN[M], apdqN[M], ctxN[NC];
+    RP::template normal<IXYZ>(P.rp, q1, qN, auxP, auxN, waveN, sN, amdqN, apdqN, ctxN);
+    if (pencil && n >= 2 && n <= mlen + 2 && n > cb - 2) {                              // flux3.f90:211-218
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtdn * sN[mw]), -dtdn * sN[mw]);
+    }
+    // ---- finish interface n-1: limiter (needs waves n-2 via dotl, n-1, n) + cqxx -----------
+    double cqxxP[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) cqxxP[m] = 0.0;
+    double dotn[W];
+#pragma unroll
+    for (int mw = 0; mw < W; ++mw) dotn[mw] = 0.0;
+    if (second) {
+      if (limit) {
+        double wnorm2[W];
+        wave_dots3<M, W>(waveP, waveN, wnorm2, dotn);
+        limit_waves3<M, W>(P.mthlim, waveP, sP, wnorm2, dotlP, dotn);
+      }
+      second_order3<M, W>(dtdn, waveP, sP, cqxxP);
+    }
+    // ---- cell c = n-2: p-side = interface n-2 (carried), m-side = interface n-1 ---------------
+    const int c = n - 2;
+    const bool c_out = (c >= cb && c < ce);
+    double qadd[M], fdiff[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      qadd[m] = (0.0 - dtdn * apdqC[m]) - dtdn * amdqP[m];
+      fdiff[m] = (0.0 + cqxxP[m]) - (0.0 + cqxxC[m]);
+    }
+    if (split) {
+      const bool upd = pencil && c >= 2 && c <= mlen + 1;
+      if (out_thread && c_out) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          const double r = (q2[m] + qadd[m]) - dtdn * fdiff[m];
+          ocol[m * P.plane + (long long)c * strideN] = upd ? r : q2[m];
+        }
+      }
+    } else if (c >= cb - 0 && c < ce) {                      // uniform across the CTA
+      if (transverse) {
+        double A[3][3][MA];
+        if (RP::MAUX > 0) {
+          // A[dy][dz]: y-sweep: dy <-> thread-y (K), dz <-> thread-x (I); z-sweep: dy <-> I, dz <-> J
+          const int ti[3] = {Im, Ic, Ip};
+          const int tt[3] = {Tm, Tc, Tp};
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dz = 0; dz < 3; ++dz) {
+              const int ii = (IXYZ == 1) ? ti[dz] : ti[dy];
+              const int tj = (IXYZ == 1) ? tt[dy] : tt[dz];
+#pragma unroll
+              for (int ma = 0; ma < MA; ++ma)
+                A[dy][dz][ma] = P.aux[ma * P.plane + (long long)tj * strideT + ii + (long long)c * strideN];
+            }
+        }
+        flux3_cell<RP, IXYZ, NT>(P, dtdn, dty, dtz, apdqC, cqxxC, ctxC, amdqP, cqxxP, ctxP, A, sm);
+      }
+      __syncthreads();
+      if (out_thread) {
+        double acc[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) acc[m] = P.first_pass ? q2[m] : ocol[m * P.plane + (long long)c * strideN];
+        if (transverse) {
+          // source pencils in the reference's loop order: thread-y outer, thread-x inner
+          // (step3.f90:283-284 "do k / do i", :439-440 "do j / do i")
+          if (IXYZ == 1) {   // a <-> thread-y, b <-> thread-x;   (a, b) = -(source offset)
+            apply_target<1, 1, M, NT>(acc, sm - BX - 1, dty, dtz);
+            apply_target<1, 0, M, NT>(acc, sm - BX, dty, dtz);
+            apply_target<1, -1, M, NT>(acc, sm - BX + 1, dty, dtz);
+            apply_target<0, 1, M, NT>(acc, sm - 1, dty, dtz);
+            apply_center<M, NT>(acc, sm, qadd, fdiff, dtdn, dty, dtz, true);
+            apply_target<0, -1, M, NT>(acc, sm + 1, dty, dtz);
+            apply_target<-1, 1, M, NT>(acc, sm + BX - 1, dty, dtz);
+            apply_target<-1, 0, M, NT>(acc, sm + BX, dty, dtz);
+            apply_target<-1, -1, M, NT>(acc, sm + BX + 1, dty, dtz);
+          } else {           // a <-> thread-x, b <-> thread-y
+            apply_target<1, 1, M, NT>(acc, sm - BX - 1, dty, dtz);
+            apply_target<0, 1, M, NT>(acc, sm - BX, dty, dtz);
+            apply_target<-1, 1, M, NT>(acc, sm - BX + 1, dty, dtz);
+            apply_target<1, 0, M, NT>(acc, sm - 1, dty, dtz);
+            apply_center<M, NT>(acc, sm, qadd, fdiff, dtdn, dty, dtz, true);
+            apply_target<-1, 0, M, NT>(acc, sm + 1, dty, dtz);
+            apply_target<1, -1, M, NT>(acc, sm + BX - 1, dty, dtz);
+            apply_target<0, -1, M, NT>(acc, sm + BX, dty, dtz);
+            apply_target<-1, -1, M, NT>(acc, sm + BX + 1, dty, dtz);
+          }
+        } else {
+          apply_center<M, NT>(acc, sm, qadd, fdiff, dtdn, dty, dtz, false);
+        }
+#pragma unroll
+        for (int m = 0; m < M; ++m) ocol[m * P.plane + (long long)c * strideN] = acc[m];
+      }
+      __syncthreads();
+    }
+    // ---- carry ------------------------------------------------------------------------------------
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      q2[m] = q1[m]; q1[m] = qN[m];
+      apdqC[m] = apdqP[m]; cqxxC[m] = cqxxP[m];
+      amdqP[m] = amdqN[m]; apdqP[m] = apdqN[m];
+    }
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc) { ctxC[cc] = ctxP[cc]; ctxP[cc] = ctxN[cc]; }
+#pragma unroll
+    for (int ma = 0; ma < MA; ++ma) auxP[ma] = auxN[ma];
+#pragma unroll
+    for (int mw = 0; mw < W; ++mw) {
+      sP[mw] = sN[mw]; dotlP[mw] = dotn[mw];
+#pragma unroll
+      for (int m = 0; m < M; ++m) waveP[mw][m] = waveN[mw][m];
+    }
+  }
+  block_max_cfl3<NT>(cfl, P.cfl_bits, sred);
+}
+
+}  // namespace CLAW_NS
+}  // namespace clawcuda

@@ -1,0 +1,78 @@
+// 3-D kernel instantiations + launch heuristics.  Compiled twice (see csrc/build.py), like
+// sweep_inst.cu:  -DCLAW_NS=strict -fmad=false  /  -DCLAW_NS=fast -fmad=true.
+#include "launch.h"
+#include "sweep3.cuh"
+
+namespace clawcuda {
+namespace CLAW_NS {
+
+static int pick_seg(int len, long long tiles, int num_sms) {
+  // enough CTAs for ~2 waves, segments not shorter than 16 cells (each pays 2-4 warm-up steps)
+  long long nseg = (2LL * num_sms + tiles - 1) / tiles;
+  if (nseg < 1) nseg = 1;
+  int seg = (int)((len + nseg - 1) / nseg);
+  if (seg < 16) seg = 16;
+  if (seg > len) seg = len;
+  return seg < 1 ? 1 : seg;
+}
+
+template <class RP, int BY>
+static cudaError_t launch_x(Sweep3Params& P, int num_sms, cudaStream_t st, LaunchInfo* info) {
+  constexpr int NT = 32 * BY;
+  auto kern = sweep3_x<RP, BY>;
+  const int smem = (int)Smem3<RP, NT>::BYTES;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  const bool split = P.m3 < 0;
+  const int nx = P.n[0] + 4, ny = P.n[1] + 4, nz = P.n[2] + 4;
+  const int gx = (nx - 2 + 27) / 28;
+  const int gy = split ? (ny + BY - 1) / BY : (P.n[1] + BY - 3) / (BY - 2);
+  const int len = split ? nz : P.n[2];
+  P.seg = pick_seg(len, (long long)gx * gy, num_sms);
+  dim3 grid(gx, gy, (len + P.seg - 1) / P.seg), block(32, BY);
+  kern<<<grid, block, smem, st>>>(P);
+  if (info) { info->grid_x = grid.x; info->grid_y = grid.y * grid.z; info->block = NT; info->smem_bytes = smem; info->ctas_per_sm = 1; }
+  return cudaGetLastError();
+}
+
+template <class RP, int IXYZ, int BX, int BY>
+static cudaError_t launch_march(Sweep3Params& P, int num_sms, cudaStream_t st, LaunchInfo* info) {
+  constexpr int NT = BX * BY;
+  auto kern = sweep3_march<RP, IXYZ, BX, BY>;
+  const int smem = (int)Smem3<RP, NT>::BYTES;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  const bool split = P.m3 < 0;
+  const int TD = (IXYZ == 1) ? 2 : 1;
+  const int nx = P.n[0] + 4, nT = P.n[TD] + 4, nlen = P.n[IXYZ] + 4;
+  const int gx = split ? (nx + BX - 1) / BX : (P.n[0] + BX - 3) / (BX - 2);
+  const int gy = split ? (nT + BY - 1) / BY : (P.n[TD] + BY - 3) / (BY - 2);
+  const int len = split ? nlen : P.n[IXYZ];
+  P.seg = pick_seg(len, (long long)gx * gy, num_sms);
+  dim3 grid(gx, gy, (len + P.seg - 1) / P.seg), block(BX, BY);
+  kern<<<grid, block, smem, st>>>(P);
+  if (info) { info->grid_x = grid.x; info->grid_y = grid.y * grid.z; info->block = NT; info->smem_bytes = smem; info->ctas_per_sm = 1; }
+  return cudaGetLastError();
+}
+
+template <class RP>
+static cudaError_t launch_dir(int dir, Sweep3Params& P, int num_sms, cudaStream_t st, LaunchInfo* info) {
+  switch (dir) {
+    case 0: return launch_x<RP, 8>(P, num_sms, st, info);
+    case 1: return launch_march<RP, 1, 32, 8>(P, num_sms, st, info);
+    case 2: return launch_march<RP, 2, 32, 8>(P, num_sms, st, info);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// dir: 0 = x-sweep, 1 = y-sweep, 2 = z-sweep
+cudaError_t launch_sweep3(int rp_id, int dir, Sweep3Params& P, int num_sms, cudaStream_t st, LaunchInfo* info) {
+  switch (rp_id) {
+    case 5: return launch_dir<RpVcAcoustics3D>(dir, P, num_sms, st, info);
+    case 6: return launch_dir<RpEuler3D>(dir, P, num_sms, st, info);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace CLAW_NS
+}  // namespace clawcuda

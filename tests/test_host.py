@@ -36,6 +36,32 @@ def test_host_loop_reference_golden(oracle_lib):
     assert dx * dy * np.sum(np.abs(rho - goldens()['euler_2d__quadrants_roe'])) < 1e-6
 
 
+def test_host_loop_3d_with_plugin_matches_oracle_loop(oracle_lib):
+    """ClawSolver3D (classic/solver.py:648-706) with the oracle plug-in: unsplit (step3) with aux arrays and
+    wall/periodic BCs, dimension-split (3 aliased step3ds calls), and BC.custom + wall on euler_3D."""
+    G = goldens()
+    cases = [S.acoustics_3d(mx=12, my=10, mz=9, tfinal=0.3, num_output_times=2),
+             S.acoustics_3d(mx=16, my=4, mz=4, heterogeneous=False, tfinal=0.3, num_output_times=2),
+             S.euler_3d_shocktube(mx=4, my=5, mz=24, tfinal=0.05, num_output_times=1),
+             S.euler_3d_shock_bubble(G['euler_3d__shock_bubble_q0'][:, :20, :6, :6].copy(order='F'),
+                                     G['euler_3d__shock_bubble_consts'], tfinal=0.02, num_output_times=1)]
+    for sc in cases:
+        claw = S.make_claw(sc, kernel_language='Fortran', fmod=OracleFmod())
+        claw.run()
+        r = ref_solver(sc)
+        r.run(sc['tfinal'], sc['num_output_times'])
+        assert np.array_equal(claw.frames[-1].q, r.q)
+        assert claw.solver.step_log == r.step_log
+
+
+def test_host_loop_3d_reference_golden(oracle_lib):
+    sc = S.acoustics_3d(mx=15, my=15, mz=15)
+    claw = S.make_claw(sc, kernel_language='Fortran', fmod=OracleFmod())
+    claw.run()
+    p = claw.frames[-1].q[0].reshape(-1)
+    assert np.max(np.abs(p - goldens()['acoustics_3d__verify_classic_heterogeneous'])) < 1e-13
+
+
 def test_api_surface():
     solver = pyclaw.ClawSolver2D(riemann.euler_4wave_2D)
     assert (solver.num_eqn, solver.num_waves, solver.num_ghost) == (4, 4, 2)
