@@ -397,6 +397,11 @@ int launch_pass3(claw_solver* h, const double* delta, double dt, int dir, int fi
   P.limit = 0;
   for (int mw = 0; mw < h->mwaves; ++mw) { P.mthlim[mw] = h->mthlim[mw]; if (h->mthlim[mw] > 0) P.limit = 1; }
   P.first_pass = first_pass;
+  // dimension-split sweeps cover one ghost layer (step3ds.f90:134-135); at a rank-to-rank face of the slab
+  // dimension both received ghost planes are swept so that the sharded run equals the SERIAL reference
+  // (a PetClaw run differs there)
+  P.zlo = (h->method[2] < 0 && !h->on_lower[2]) ? 0 : 1;
+  P.zhi = h->g.n[2] + ((h->method[2] < 0 && !h->on_upper[2]) ? 3 : 2);
   for (int k = 0; k < 4; ++k) P.rp.p[k] = h->cparam[k];
   cudaError_t e = (h->mode == CLAW_MODE_FAST)
                       ? fast::launch_sweep3(h->rp_id, dir, P, h->num_sms, h->stream, &h->last_launch)
@@ -709,50 +714,61 @@ int claw_sync(claw_solver* h) {
   return 0;
 }
 
+namespace {
+size_t halo_elems_of(const claw_solver* h, int ncomp) {
+  return (h->g.ndim == 2) ? (size_t)ncomp * 2 * h->g.nt[0] : (size_t)ncomp * 2 * h->g.kstride;
+}
+// pack (interior rows/planes next to `side`) or unpack (ghost rows/planes of `side`) of one array
+int halo_move(claw_solver* h, double* arr, int ncomp, int side, double* d_buf, bool pack) {
+  if (int rc = ensure_buffers(h)) return rc;
+  CK(h, cudaSetDevice(h->device));
+  const Dev2& g = h->g;
+  const int last = g.ndim - 1;
+  const int s0 = pack ? (side == 0 ? g.ng : g.n[last])            // interior [2,4) or [m, m+2)
+                      : (side == 0 ? 0 : g.n[last] + g.ng);        // ghost [0,2) or [m+2, m+4)
+  if (g.ndim == 2) {
+    const long long n = (long long)ncomp * 2 * g.nt[0];
+    if (pack) halo_pack2<<<grid_for(n, 256), 256, 0, h->stream>>>(arr, d_buf, ncomp, g.nt[0], s0, g.pitch, g.plane);
+    else halo_unpack2<<<grid_for(n, 256), 256, 0, h->stream>>>(arr, d_buf, ncomp, g.nt[0], s0, g.pitch, g.plane);
+  } else {
+    const long long len = 2 * g.kstride;
+    double* base = arr + (long long)s0 * g.kstride;
+    if (pack) gather_runs<<<grid_for(len * ncomp, 256), 256, 0, h->stream>>>(base, g.plane, d_buf, len, ncomp);
+    else scatter_runs<<<grid_for(len * ncomp, 256), 256, 0, h->stream>>>(base, g.plane, d_buf, len, ncomp);
+  }
+  ++h->launches;
+  CK(h, cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
 int claw_halo_elems(const claw_solver* h, size_t* elems) {
   if (check_handle(h)) return 1;
-  *elems = (h->g.ndim == 2) ? (size_t)h->meqn * 2 * h->g.nt[0] : (size_t)h->meqn * 2 * h->g.kstride;
+  *elems = halo_elems_of(h, h->meqn);
   return 0;
 }
-
 int claw_halo_pack(claw_solver* h, int side, double* d_buf) {
   if (check_handle(h)) return 1;
-  if (int rc = ensure_buffers(h)) return rc;
-  CK(h, cudaSetDevice(h->device));
-  const Dev2& g = h->g;
-  const int last = g.ndim - 1;
-  const int s0 = side == 0 ? g.ng : g.n[last];         // interior rows/planes [2,4) or [m, m+2)
-  if (g.ndim == 2) {
-    const long long n = (long long)h->meqn * 2 * g.nt[0];
-    halo_pack2<<<grid_for(n, 256), 256, 0, h->stream>>>(h->q[h->cur], d_buf, h->meqn, g.nt[0], s0, g.pitch, g.plane);
-  } else {
-    const long long len = 2 * g.kstride;
-    gather_runs<<<grid_for(len * h->meqn, 256), 256, 0, h->stream>>>(h->q[h->cur] + (long long)s0 * g.kstride, g.plane,
-                                                                     d_buf, len, h->meqn);
-  }
-  ++h->launches;
-  CK(h, cudaGetLastError());
-  return 0;
+  return halo_move(h, h->q[h->cur], h->meqn, side, d_buf, true);
 }
-
 int claw_halo_unpack(claw_solver* h, int side, const double* d_buf) {
   if (check_handle(h)) return 1;
-  if (int rc = ensure_buffers(h)) return rc;
-  CK(h, cudaSetDevice(h->device));
-  const Dev2& g = h->g;
-  const int last = g.ndim - 1;
-  const int s0 = side == 0 ? 0 : g.n[last] + g.ng;     // ghost rows/planes [0,2) or [m+2, m+4)
-  if (g.ndim == 2) {
-    const long long n = (long long)h->meqn * 2 * g.nt[0];
-    halo_unpack2<<<grid_for(n, 256), 256, 0, h->stream>>>(h->q[h->cur], d_buf, h->meqn, g.nt[0], s0, g.pitch, g.plane);
-  } else {
-    const long long len = 2 * g.kstride;
-    scatter_runs<<<grid_for(len * h->meqn, 256), 256, 0, h->stream>>>(h->q[h->cur] + (long long)s0 * g.kstride, g.plane,
-                                                                      d_buf, len, h->meqn);
-  }
-  ++h->launches;
-  CK(h, cudaGetLastError());
+  return halo_move(h, h->q[h->cur], h->meqn, side, const_cast<double*>(d_buf), false);
+}
+int claw_halo_elems_aux(const claw_solver* h, size_t* elems) {
+  if (check_handle(h)) return 1;
+  *elems = halo_elems_of(h, h->maux);
   return 0;
+}
+int claw_halo_pack_aux(claw_solver* h, int side, double* d_buf) {
+  if (check_handle(h)) return 1;
+  if (h->maux == 0) return 0;
+  return halo_move(h, h->aux, h->maux, side, d_buf, true);
+}
+int claw_halo_unpack_aux(claw_solver* h, int side, const double* d_buf) {
+  if (check_handle(h)) return 1;
+  if (h->maux == 0) return 0;
+  return halo_move(h, h->aux, h->maux, side, const_cast<double*>(d_buf), false);
 }
 
 int claw_time_sweep(claw_solver* h, const double* delta, double dt, int reps, double* avg_ms) {

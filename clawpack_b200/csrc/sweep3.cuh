@@ -52,6 +52,8 @@ struct Sweep3Params {
   int mthlim[8];
   int first_pass;           // unsplit: 1 -> qout = qin + terms (x-sweep), 0 -> qout += terms
   int seg;                  // cells per march segment (blockIdx.z)
+  int zlo, zhi;             // pencil planes K swept by the x- and y-sweeps: [1, mz+2], widened by one at
+                            // rank-to-rank faces of a slab decomposition when dimension-split
   RpParams rp;
 };
 #endif
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(32 * BY) sweep3_x(const __grid_constant__ Swee
           A[dy][2][ma] = abase[ma * P.plane + (long long)kn * P.kstride + (long long)jr[dy] * P.pitch];
         }
     }
-    const bool plane_pencil = (k >= 1 && k <= P.n[2] + 2);   // Fortran k in 0..mz+1
+    const bool plane_pencil = (k >= P.zlo && k <= P.zhi);    // Fortran k in 0..mz+1
     // ---- interface I (my left face) ------------------------------------------------------
     double ql[M], auxl[MA];
 #pragma unroll
@@ -487,7 +489,8 @@ __global__ void __launch_bounds__(BX * BY) sweep3_march(const __grid_constant__ 
   const bool second = (P.order != 1);
   const bool limit = second && (P.limit != 0);
   const bool transverse = P.m3 > 0;
-  const bool pencil = (I >= 1 && I <= P.n[0] + 2 && T >= 1 && T <= P.n[TD] + 2);
+  const bool pencil = (I >= 1 && I <= P.n[0] + 2) &&
+                      (IXYZ == 1 ? (T >= P.zlo && T <= P.zhi) : (T >= 1 && T <= P.n[TD] + 2));
   const bool out_thread = split ? (I < nx && T < nT)
                                 : (tx >= 1 && tx <= BX - 2 && ty >= 1 && ty <= BY - 2 && I >= 2 && I <= P.n[0] + 1 &&
                                    T >= 2 && T <= P.n[TD] + 1);

@@ -10,18 +10,19 @@ class _DistributedMixin(object):
     def setup(self, solution):
         state = solution.state
         last = self.num_dim - 1
-        periodic = (self.bc_lower[last] == BC.periodic and self.bc_upper[last] == BC.periodic)
-        if (self.bc_lower[last] == BC.periodic) != (self.bc_upper[last] == BC.periodic):
-            raise Exception('periodic boundary conditions must be set on both faces of a dimension')
+        # each face of the slab dimension wraps around independently (the reference's 3-D acoustics example
+        # has a wall below and a periodic face above); the ghost fill skips a periodic face on a rank that
+        # does not own both ends (solver.py:400-402, 430-432), the exchange provides the wrapped values
+        periodic = (self.bc_lower[last] == BC.periodic, self.bc_upper[last] == BC.periodic)
         state._periodic_last = periodic
-        if periodic and state.patch.num_ranks > 1:
-            # the wrap-around is an ordinary ghost exchange: no rank owns a physical face in that dimension
-            state.grid.dimensions[last].on_lower_boundary = False
-            state.grid.dimensions[last].on_upper_boundary = False
+        periodic_aux = (self.aux_bc_lower[last] == BC.periodic, self.aux_bc_upper[last] == BC.periodic)
+        state._periodic_last_aux = periodic_aux
         super(_DistributedMixin, self).setup(solution)
         if self._dev is not None and state.patch.num_ranks > 1:
             from ..device_halo import DeviceHalo
             halo = DeviceHalo(self._dev, state.patch, periodic)
+            if state.num_aux > 0:
+                DeviceHalo(self._dev, state.patch, periodic_aux).exchange_aux(self._dev)
             self._dev.pre_step_hook = halo.exchange
             self._dev.post_step_hook = halo.reduce_cfl
 

@@ -16,9 +16,8 @@ class DeviceHalo(object):
         self.dev = dev
         self.dist = util._dist()
         nranks, r = patch.num_ranks, patch.rank
-        self.lower_nb = r - 1 if r > 0 else (nranks - 1 if periodic else None)
-        self.upper_nb = r + 1 if r < nranks - 1 else (0 if periodic else None)
-        self.same_nb = (nranks == 2 and periodic)
+        per_lo, per_up = periodic if isinstance(periodic, tuple) else (periodic, periodic)
+        self.nb = util.slab_neighbours(nranks, r, per_lo, per_up)
         n = ctypes.c_size_t()
         _lib.check(dev.L.claw_halo_elems(dev.handle, ctypes.byref(n)), dev.handle)
         mk = lambda: torch.empty(n.value, dtype=torch.float64, device=dev.device)   # noqa: E731
@@ -27,27 +26,42 @@ class DeviceHalo(object):
     def _vp(self, t):
         return ctypes.c_void_p(t.data_ptr())
 
+    def exchange_aux(self, dev):
+        """One-off exchange of the static aux ghost rows/planes (petclaw/state.py:233-241)."""
+        n = ctypes.c_size_t()
+        _lib.check(dev.L.claw_halo_elems_aux(dev.handle, ctypes.byref(n)), dev.handle)
+        if n.value == 0:
+            return
+        torch = self.torch
+        bufs = [torch.empty(n.value, dtype=torch.float64, device=dev.device) for _ in range(4)]
+        self._exchange(dev, dev.L.claw_halo_pack_aux, dev.L.claw_halo_unpack_aux, *bufs)
+
     def exchange(self, dev):
-        L, h, d = dev.L, dev.handle, self.dist
+        self._exchange(dev, dev.L.claw_halo_pack, dev.L.claw_halo_unpack, self.send_lo, self.send_up,
+                       self.recv_lo, self.recv_up)
+
+    def _exchange(self, dev, pack, unpack, send_lo, send_up, recv_lo, recv_up):
+        L, h, d, nb = dev.L, dev.handle, self.dist, self.nb
+        if nb['send_up_to'] is not None:
+            _lib.check(pack(h, 1, self._vp(send_up)), h)
+        if nb['send_lo_to'] is not None:
+            _lib.check(pack(h, 0, self._vp(send_lo)), h)
         ops = []
-        if self.upper_nb is not None:
-            _lib.check(L.claw_halo_pack(h, 1, self._vp(self.send_up)), h)
-        if self.lower_nb is not None:
-            _lib.check(L.claw_halo_pack(h, 0, self._vp(self.send_lo)), h)
-        if self.same_nb:
-            ops = [d.P2POp(d.isend, self.send_up, self.upper_nb), d.P2POp(d.irecv, self.recv_lo, self.lower_nb),
-                   d.P2POp(d.isend, self.send_lo, self.lower_nb), d.P2POp(d.irecv, self.recv_up, self.upper_nb)]
-        else:
-            if self.upper_nb is not None:
-                ops += [d.P2POp(d.isend, self.send_up, self.upper_nb), d.P2POp(d.irecv, self.recv_up, self.upper_nb)]
-            if self.lower_nb is not None:
-                ops += [d.P2POp(d.isend, self.send_lo, self.lower_nb), d.P2POp(d.irecv, self.recv_lo, self.lower_nb)]
-        for req in d.batch_isend_irecv(ops):
-            req.wait()
-        if self.lower_nb is not None:
-            _lib.check(L.claw_halo_unpack(h, 0, self._vp(self.recv_lo)), h)
-        if self.upper_nb is not None:
-            _lib.check(L.claw_halo_unpack(h, 1, self._vp(self.recv_up)), h)
+        if nb['send_up_to'] is not None:
+            ops.append(d.P2POp(d.isend, send_up, nb['send_up_to']))
+        if nb['recv_lo_from'] is not None:
+            ops.append(d.P2POp(d.irecv, recv_lo, nb['recv_lo_from']))
+        if nb['send_lo_to'] is not None:
+            ops.append(d.P2POp(d.isend, send_lo, nb['send_lo_to']))
+        if nb['recv_up_from'] is not None:
+            ops.append(d.P2POp(d.irecv, recv_up, nb['recv_up_from']))
+        if ops:
+            for req in d.batch_isend_irecv(ops):
+                req.wait()
+        if nb['recv_lo_from'] is not None:
+            _lib.check(unpack(h, 0, self._vp(recv_lo)), h)
+        if nb['recv_up_from'] is not None:
+            _lib.check(unpack(h, 1, self._vp(recv_up)), h)
 
     def reduce_cfl(self, dev):
         """max over ranks of the CFL slot written by the sweep kernel, on the device, then one read."""

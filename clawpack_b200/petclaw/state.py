@@ -8,34 +8,35 @@ from . import util
 
 def exchange_ghost_rows_host(arr, num_ghost, patch, periodic):
     """Fill the ghost rows of the slowest dimension of ``arr`` (components, ..., n_last + 2g), host
-    numpy, from the neighbouring ranks' interior rows (full extent of the other dimensions).  The
-    blocking exchange is ordered by rank parity so that it cannot deadlock."""
+    numpy, from the neighbouring ranks' interior rows (full extent of the other dimensions).
+    ``periodic`` = (lower face periodic, upper face periodic)."""
     d = util._dist()
     nranks, r = patch.num_ranks, patch.rank
     if d is None or nranks == 1:
         return
     import torch
     g = num_ghost
-    lower_nb = r - 1 if r > 0 else (nranks - 1 if periodic else None)
-    upper_nb = r + 1 if r < nranks - 1 else (0 if periodic else None)
+    per_lo, per_up = periodic if isinstance(periodic, tuple) else (periodic, periodic)
+    nb = util.slab_neighbours(nranks, r, per_lo, per_up)
     send_lo = torch.from_numpy(np.ascontiguousarray(arr[..., g:2 * g]))
     send_up = torch.from_numpy(np.ascontiguousarray(arr[..., -2 * g:-g]))
     recv_lo = torch.empty_like(send_lo)
     recv_up = torch.empty_like(send_up)
     ops = []
-    if upper_nb is not None:
-        ops += [d.P2POp(d.isend, send_up, upper_nb), d.P2POp(d.irecv, recv_up, upper_nb)]
-    if lower_nb is not None:
-        ops += [d.P2POp(d.isend, send_lo, lower_nb), d.P2POp(d.irecv, recv_lo, lower_nb)]
-    if nranks == 2 and periodic:
-        # both neighbours are the same rank: tag the two messages by direction
-        ops = [d.P2POp(d.isend, send_up, upper_nb, tag=1), d.P2POp(d.irecv, recv_up, upper_nb, tag=2),
-               d.P2POp(d.isend, send_lo, lower_nb, tag=2), d.P2POp(d.irecv, recv_lo, lower_nb, tag=1)]
-    for req in d.batch_isend_irecv(ops):
-        req.wait()
-    if lower_nb is not None:
+    if nb['send_up_to'] is not None:
+        ops.append(d.P2POp(d.isend, send_up, nb['send_up_to'], tag=1))
+    if nb['recv_lo_from'] is not None:
+        ops.append(d.P2POp(d.irecv, recv_lo, nb['recv_lo_from'], tag=1))
+    if nb['send_lo_to'] is not None:
+        ops.append(d.P2POp(d.isend, send_lo, nb['send_lo_to'], tag=2))
+    if nb['recv_up_from'] is not None:
+        ops.append(d.P2POp(d.irecv, recv_up, nb['recv_up_from'], tag=2))
+    if ops:
+        for req in d.batch_isend_irecv(ops):
+            req.wait()
+    if nb['recv_lo_from'] is not None:
         arr[..., :g] = recv_lo.numpy()
-    if upper_nb is not None:
+    if nb['recv_up_from'] is not None:
         arr[..., -g:] = recv_up.numpy()
 
 
@@ -44,12 +45,12 @@ class State(base.State):
 
     def get_qbc_from_q(self, num_ghost, qbc):
         qbc = super(State, self).get_qbc_from_q(num_ghost, qbc)
-        exchange_ghost_rows_host(qbc, num_ghost, self.patch, getattr(self, '_periodic_last', False))
+        exchange_ghost_rows_host(qbc, num_ghost, self.patch, getattr(self, '_periodic_last', (False, False)))
         return qbc
 
     def get_auxbc_from_aux(self, num_ghost, auxbc):
         auxbc = super(State, self).get_auxbc_from_aux(num_ghost, auxbc)
-        exchange_ghost_rows_host(auxbc, num_ghost, self.patch, getattr(self, '_periodic_last', False))
+        exchange_ghost_rows_host(auxbc, num_ghost, self.patch, getattr(self, '_periodic_last_aux', (False, False)))
         return auxbc
 
     def _gather(self, local):

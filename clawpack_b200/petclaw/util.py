@@ -25,6 +25,22 @@ def slab_range(n, nranks, r):
     return start, start + base + (1 if r < extra else 0)
 
 
+def slab_neighbours(nranks, r, per_lo, per_up):
+    """Who fills my ghost rows and who needs my interior rows (slowest dimension).  ``per_lo`` / ``per_up``:
+    the lower / upper physical face is periodic (the reference allows them to differ, e.g.
+    examples/acoustics_3d_variable: lower wall, upper periodic -- the DMDA is always periodic and a
+    non-periodic BC simply overwrites the wrapped ghost values, petclaw/state.py:192-195).
+    Channel A = upper interior -> the upper neighbour's lower ghosts; channel B = lower interior ->
+    the lower neighbour's upper ghosts.  Every rank posts (send A, recv A, send B, recv B) in that
+    order, so two messages between the same pair are matched in order."""
+    nb = {}
+    nb['send_up_to'] = r + 1 if r < nranks - 1 else (0 if per_lo else None)            # A
+    nb['recv_lo_from'] = r - 1 if r > 0 else (nranks - 1 if per_lo else None)          # A
+    nb['send_lo_to'] = r - 1 if r > 0 else (nranks - 1 if per_up else None)            # B
+    nb['recv_up_from'] = r + 1 if r < nranks - 1 else (0 if per_up else None)          # B
+    return nb
+
+
 def make_claw_distributed(sc, kernel_language='CUDA', **solver_kw):
     """Build the Controller for a GLOBAL scenario dict; every rank keeps only its slab.  Initial data
     come from the global arrays, so 1-rank and N-rank runs start from identical bits

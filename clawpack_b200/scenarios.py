@@ -167,6 +167,25 @@ def acoustics_3d(mx=30, my=30, mz=30, heterogeneous=True, dimensional_split=None
                  tfinal=tfinal, num_output_times=num_output_times)
 
 
+def acoustics_3d_general(mx=18, my=15, mz=13, **kw):
+    """vc_acoustics_3D stress variant: impedance / sound speed varying smoothly in all three directions and a
+    state with non-zero pressure and velocities everywhere (every aux cell of the 3x3 neighbourhood and every
+    limiter branch matters); all faces periodic."""
+    sc = acoustics_3d(mx=mx, my=my, mz=mz, periodic=True)
+    X, Y, Z = _grid((-1., -1., -1.), (1., 1., 1.), (mx, my, mz))
+    aux = np.empty((2, mx, my, mz), order='F')
+    aux[0] = 1.5 + 0.5 * np.sin(3 * X + 1) * np.cos(2 * Y) + 0.3 * np.sin(4 * Z + X * Y)
+    aux[1] = 1.2 + 0.4 * np.cos(2 * X - Y + 0.5 * Z) + 0.2 * np.sin(5 * Y * Z)
+    q = np.empty((4, mx, my, mz), order='F')
+    q[0] = np.exp(-3 * ((X + 0.2) ** 2 + Y ** 2 + (Z - 0.1) ** 2)) + 0.1 * np.sin(7 * X * Y * Z)
+    q[1] = 0.3 * np.sin(2 * X + Y)
+    q[2] = -0.2 * np.cos(3 * Y - Z)
+    q[3] = 0.25 * np.sin(Z + 2 * X)
+    sc = dict(sc, q=q, aux=aux)
+    sc.update(kw)
+    return sc
+
+
 def euler_3d_shocktube(mx=10, my=10, mz=128, tfinal=0.2, num_output_times=10):
     """pyclaw/examples/euler_3d/shocktube.py:17-66 as run by test_euler3d.py:27 (dimension-split, MC)."""
     gamma = 1.4

@@ -44,7 +44,8 @@ enum {
   CLAW_RP_ACOUSTICS_2D = 2,            /* rpn2_acoustics.f90, rpt2_acoustics.f90 */
   CLAW_RP_EULER_4WAVE_2D = 3,          /* rpn2_euler_4wave.f90, rpt2_euler.f90 */
   CLAW_RP_SHALLOW_ROE_EFIX_2D = 4,     /* rpn2_shallow_roe_with_efix.f90, rpt2_shallow_roe_with_efix.f90 */
-  CLAW_RP_VC_ACOUSTICS_3D = 5          /* rpn3_vc_acoustics.f90, rpt3_vc_acoustics.f90, rptt3_vc_acoustics.f90 */
+  CLAW_RP_VC_ACOUSTICS_3D = 5,         /* rpn3_vc_acoustics.f90, rpt3_vc_acoustics.f90, rptt3_vc_acoustics.f90 */
+  CLAW_RP_EULER_3D = 6                 /* rpn3_euler.f90, rpt3_euler.f90, rptt3_euler.f90 */
 };
 
 /* Boundary-condition ids = pyclaw.BC (pyclaw/src/pyclaw/solver.py:13-19) */
@@ -121,6 +122,10 @@ int claw_sync(claw_solver* h);
 int claw_halo_elems(const claw_solver* h, size_t* elems);
 int claw_halo_pack(claw_solver* h, int side, double* d_buf);
 int claw_halo_unpack(claw_solver* h, int side, const double* d_buf);
+/* the same for the (static) aux array: exchanged once at setup (petclaw/state.py:233-241) */
+int claw_halo_elems_aux(const claw_solver* h, size_t* elems);
+int claw_halo_pack_aux(claw_solver* h, int side, double* d_buf);
+int claw_halo_unpack_aux(claw_solver* h, int side, const double* d_buf);
 
 /* time `reps` back-to-back launches of the sweep kernel alone (no ghost fill, no swap) with CUDA
    events on the handle's stream; returns the average duration in milliseconds (bench.py roofline) */

@@ -19,6 +19,12 @@ CASES = {
     'advection_unsplit_periodic': lambda: dict(S.advection_2d(mx=64, my=96, dimensional_split=False, transverse_waves=2),
                                                tfinal=0.2, num_output_times=2),
     'shallow_split_wall': lambda: dict(S.radial_dam_break(mx=150, my=120, tfinal=0.3), num_output_times=2),
+    # 3-D z-slabs: unsplit (2,22) with aux (aux ghost planes exchanged once), wall below / periodic above;
+    # dimension-split (both received ghost planes are swept at rank-to-rank faces => equals the SERIAL run)
+    'acoustics3d_wall_periodic': lambda: S.acoustics_3d(mx=40, my=36, mz=32, tfinal=0.3, num_output_times=2),
+    'acoustics3d_split_periodic': lambda: S.acoustics_3d(mx=30, my=20, mz=24, periodic=True, dimensional_split=True,
+                                                        tfinal=0.3, num_output_times=2),
+    'euler3d_split_extrap': lambda: S.euler_3d_shocktube(mx=10, my=10, mz=64, tfinal=0.1, num_output_times=2),
 }
 
 

@@ -21,6 +21,12 @@ CASES = {
     'euler_unsplit_extrap': lambda: dict(S.quadrants(mx=30, my=41, tfinal=0.1), dimensional_split=False,
                                          transverse_waves=2, limiters=S.MC, num_output_times=2),
     'shallow_split_wall': lambda: dict(S.radial_dam_break(mx=36, my=30, tfinal=0.4), num_output_times=2),
+    # 3-D, unsplit (2,22) with aux arrays: the reference example's lower wall / upper periodic faces (z-slabs),
+    # and the all-periodic variant
+    'acoustics3d_wall_periodic': lambda: S.acoustics_3d(mx=10, my=9, mz=13, tfinal=0.4, num_output_times=2),
+    'acoustics3d_periodic': lambda: S.acoustics_3d(mx=8, my=7, mz=12, periodic=True, tfinal=0.4, num_output_times=2),
+    'euler3d_unsplit_extrap': lambda: dict(S.euler_3d_shocktube(mx=5, my=6, mz=20, tfinal=0.05, num_output_times=1),
+                                           dimensional_split=False),
 }
 
 

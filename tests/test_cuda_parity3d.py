@@ -18,23 +18,7 @@ def _ac(**kw):
     return S.acoustics_3d(**base)
 
 
-def _ac_general(mx=18, my=15, mz=13, **kw):
-    """vc_acoustics_3D with impedance / sound speed varying in all three directions and a state with
-    non-zero pressure and velocities everywhere: every aux cell of the 3x3 neighbourhood matters."""
-    sc = S.acoustics_3d(mx=mx, my=my, mz=mz, periodic=True)
-    cs = [S.centers(-1., 1., k) for k in (mx, my, mz)]
-    X, Y, Z = np.meshgrid(*cs, indexing='ij')
-    aux = np.empty((2, mx, my, mz), order='F')
-    aux[0] = 1.5 + 0.5 * np.sin(3 * X + 1) * np.cos(2 * Y) + 0.3 * np.sin(4 * Z + X * Y)
-    aux[1] = 1.2 + 0.4 * np.cos(2 * X - Y + 0.5 * Z) + 0.2 * np.sin(5 * Y * Z)
-    q = np.empty((4, mx, my, mz), order='F')
-    q[0] = np.exp(-3 * ((X + 0.2) ** 2 + Y ** 2 + (Z - 0.1) ** 2)) + 0.1 * np.sin(7 * X * Y * Z)
-    q[1] = 0.3 * np.sin(2 * X + Y)
-    q[2] = -0.2 * np.cos(3 * Y - Z)
-    q[3] = 0.25 * np.sin(Z + 2 * X)
-    sc = dict(sc, q=q, aux=aux)
-    sc.update(kw)
-    return sc
+_ac_general = S.acoustics_3d_general
 
 
 def _euler_blob(mx=20, my=14, mz=12, **kw):

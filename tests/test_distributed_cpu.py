@@ -35,6 +35,10 @@ def _launch(case, world, port):
     ('shallow_split_wall', 2, 29613),
     ('euler_unsplit_extrap', 3, 29614),
     ('advection_unsplit_periodic', 3, 29615),
+    ('acoustics3d_wall_periodic', 2, 29616),
+    ('acoustics3d_periodic', 2, 29617),
+    ('acoustics3d_wall_periodic', 3, 29618),
+    ('euler3d_unsplit_extrap', 2, 29619),
 ])
 def test_slab_decomposition_matches_serial(case, world, port, oracle_lib):
     codes, outs = _launch(case, world, port)
