@@ -247,6 +247,8 @@ def main():
     _lib.check(dev.L.claw_time_sweep(dev.handle, _lib.dp(dev.delta), float(solver.dt), 5, ctypes.byref(avg_ms)),
                dev.handle)
     sweep_ms = avg_ms.value
+    linfo = (ctypes.c_int * 5)()
+    _lib.check(dev.L.claw_last_launch_info(dev.handle, linfo), dev.handle)
 
     out = None
     if rank == 0:
@@ -257,18 +259,32 @@ def main():
         hbm_peak, hbm_src = 6650.0, 'fallback (B200_PROFILING.md)'
         if os.path.exists(peaks_file):
             hbm_peak, hbm_src = float(json.load(open(peaks_file))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
-        issues_per_s = ops['fp64_issues'] * cells_local / (sweep_ms * 1e-3)
+        # Roofline of the dominant kernel.  The stencil is FP64-pipe bound (arithmetic intensity ~19 flop/B vs a
+        # machine balance of ~5.5), so: achieved = ALGORITHMIC flops of the reference algorithm per launch
+        # (add, mul, div, sqrt each counted as ONE flop; exact counts from the counting oracle, Roe averages once per
+        # interface) / measured kernel time; peak = 2 flop x the DFMA issue rate measured in this run.  A division
+        # or square root costs ~9-10 FP64-pipe issues for its one flop, so 1.0 is not attainable by this algorithm;
+        # `fp64_pipe` carries the hardware view (ncu: cycles the FP64 pipe was busy) of the last committed capture.
+        flops_per_s = ops['flops'] * cells_local / (sweep_ms * 1e-3)
         hbm_gbs = 64.0 * cells_local / (sweep_ms * 1e-3) / 1e9
+        ncu = {}
+        ncu_file = os.path.join(ROOT, 'profiles', 'latest_ncu.json')
+        if os.path.exists(ncu_file):
+            ncu = json.load(open(ncu_file)).get('sweep2_unsplit_euler_%s' % args.precision, {})
         roofline = {
             'bound': 'fp64',
-            'achieved': issues_per_s / 1e12, 'peak': peak.value / 1e3, 'unit': 'T fp64-pipe issues/s',
-            'frac': issues_per_s / 1e9 / peak.value,
-            'traffic': None,
-            'kernel': 'sweep2_unsplit<RpEuler4Wave2D,128> (%s)' % args.precision,
+            'achieved': flops_per_s / 1e12, 'peak': 2.0 * peak.value / 1e3, 'unit': 'TFLOP/s',
+            'frac': flops_per_s / 1e9 / (2.0 * peak.value),
+            'traffic': ncu.get('dram_bytes_per_launch'),
+            'kernel': 'sweep2_unsplit<RpEuler4Wave2D,%d> (%s)' % (linfo[2], args.precision),
             'kernel_ms': sweep_ms,
-            'peak_source': 'DFMA issue rate measured in this run (claw_measure_fp64_peak); nominal 18.6 T/s',
-            'algorithmic_per_cell': {k: round(v, 2) for k, v in ops.items()},
-            'algorithmic_tflops': ops['flops'] * cells_local / (sweep_ms * 1e-3) / 1e12,
+            'launch': {'grid': [linfo[0], linfo[1]], 'block': linfo[2], 'smem_bytes': linfo[3],
+                       'ctas_per_sm': linfo[4]},
+            'peak_source': '2 x DFMA issue rate measured in this run (claw_measure_fp64_peak: %.2f T DFMA/s; nominal '
+                           '18.6)' % (peak.value / 1e3),
+            'algorithmic_per_cell': {k: round(v, 2) for k, v in ops.items() if k != 'fp64_issues'},
+            'algorithmic_bytes_per_launch': 64 * cells_local,
+            'fp64_pipe': ncu.get('fp64_pipe'),
             'hbm': {'achieved': hbm_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': hbm_gbs / hbm_peak,
                     'bytes_per_cell': 64, 'peak_source': hbm_src},
         }

@@ -60,6 +60,9 @@ struct claw_solver {
   int seg_rows = 0;
   double* h_cfl = nullptr;   // pinned
   cudaEvent_t ev_cfl = nullptr;
+  // transfer/compute pipeline of the f2py-shaped host entry points
+  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[64] = {}, ev_cmp[64] = {};
   uint64_t launches = 0;
   LaunchInfo last_launch{};
   std::string err;
@@ -358,8 +361,10 @@ int fill_ghosts_array(claw_solver* h, double* arr, int ncomp, const int* lo, con
 }
 
 int launch_step2(claw_solver* h, double dx, double dy, double dt, int kind, int do_x, int do_y,
-                 const double* src, double* dst) {
+                 const double* src, double* dst, int j0 = 0, int j1 = 0, cudaStream_t stream_override = nullptr) {
   Sweep2Params P{};
+  P.j0 = j0; P.j1 = j1;                                // 0,0 = whole grid
+  cudaStream_t st = stream_override ? stream_override : h->stream;
   P.qin = src;
   P.qout = dst;
   P.cfl_bits = reinterpret_cast<unsigned long long*>(h->work);
@@ -374,8 +379,8 @@ int launch_step2(claw_solver* h, double dx, double dy, double dt, int kind, int 
   P.do_x = do_x; P.do_y = do_y;
   for (int k = 0; k < 4; ++k) P.rp.p[k] = h->cparam[k];
   cudaError_t e = (h->mode == CLAW_MODE_FAST)
-                      ? fast::launch_sweep2(h->rp_id, kind, P, h->seg_rows, h->num_sms, h->stream, &h->last_launch)
-                      : strict::launch_sweep2(h->rp_id, kind, P, h->seg_rows, h->num_sms, h->stream, &h->last_launch);
+                      ? fast::launch_sweep2(h->rp_id, kind, P, h->seg_rows, h->num_sms, st, &h->last_launch)
+                      : strict::launch_sweep2(h->rp_id, kind, P, h->seg_rows, h->num_sms, st, &h->last_launch);
   ++h->launches;
   if (e != cudaSuccess) return fail(h, 100 + (int)e, "sweep kernel launch failed: %s", cudaGetErrorString(e));
   return 0;
@@ -536,6 +541,10 @@ int claw_destroy(claw_solver* h) {
   }
   if (h->h_cfl) cudaFreeHost(h->h_cfl);
   if (h->ev_cfl) cudaEventDestroy(h->ev_cfl);
+  if (h->s_in) {
+    cudaStreamDestroy(h->s_in); cudaStreamDestroy(h->s_cmp); cudaStreamDestroy(h->s_out);
+    for (int k = 0; k < 64; ++k) { cudaEventDestroy(h->ev_in[k]); cudaEventDestroy(h->ev_cmp[k]); }
+  }
   delete h;
   return 0;
 }
@@ -794,6 +803,13 @@ int claw_time_sweep(claw_solver* h, const double* delta, double dt, int reps, do
   return 0;
 }
 
+int claw_last_launch_info(const claw_solver* h, int* info5) {
+  if (check_handle(h)) return 1;
+  info5[0] = h->last_launch.grid_x; info5[1] = h->last_launch.grid_y; info5[2] = h->last_launch.block;
+  info5[3] = h->last_launch.smem_bytes; info5[4] = h->last_launch.ctas_per_sm;
+  return 0;
+}
+
 int claw_launch_count(const claw_solver* h, uint64_t* count) {
   if (check_handle(h)) return 1;
   *count = h->launches;
@@ -826,6 +842,74 @@ int host_fail(claw_solver* h, int rc) {
 }
 }  // namespace
 
+namespace {
+// claw_step2_host for large grids: the rows are cut into chunks and three streams overlap
+//   H2D + AoS->SoA of chunk c+1  |  sweep of chunk c  |  SoA->AoS + D2H of chunk c-1
+// (PCIe is full duplex, so the step costs ~max(H2D, D2H) instead of H2D + sweep + D2H).  Chunk c needs the input
+// rows [j0-2, j1+2) of its output rows [j0, j1); uploads are disjoint row ranges issued in order.
+int step2_host_pipelined(claw_solver* h, const double* qold, double* qnew, double dx, double dy, double dt,
+                         double* cfl) {
+  const Dev2& g = h->g;
+  const int meqn = h->meqn, mx = g.n[0], my = g.n[1], nx = g.nt[0], ny = g.nt[1];
+  if (int rc = ensure_buffers(h)) return rc;
+  CK(h, cudaSetDevice(h->device));
+  if (!h->s_in) {
+    CK(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CK(h, cudaStreamCreateWithFlags(&h->s_cmp, cudaStreamNonBlocking));
+    CK(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (int k = 0; k < 64; ++k) {
+      CK(h, cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming));
+      CK(h, cudaEventCreateWithFlags(&h->ev_cmp[k], cudaEventDisableTiming));
+    }
+  }
+  CK(h, cudaStreamSynchronize(h->stream));
+  int nchunk = (my + 511) / 512;
+  if (nchunk > 64) nchunk = 64;
+  if (nchunk < 2) nchunk = 2;
+  const int rows = (my + nchunk - 1) / nchunk;
+  nchunk = (my + rows - 1) / rows;
+  double* stage = h->work + WORK_HDR;                  // AoS image of the whole ghosted array
+  const size_t row_elems = (size_t)meqn * nx;
+  const double* src = h->q[h->cur];
+  double* dst = h->q[h->cur ^ 1];
+  CK(h, cudaMemsetAsync(h->work, 0, sizeof(double), h->s_cmp));
+  int uploaded = 0;                                    // rows [0, uploaded) are on the device
+  for (int c = 0; c < nchunk; ++c) {
+    const int j0 = g.ng + c * rows, j1 = (c == nchunk - 1) ? g.ng + my : j0 + rows;
+    const int need = (c == nchunk - 1) ? ny : j1 + 2;
+    if (need > uploaded) {
+      CK(h, cudaMemcpyAsync(stage + (size_t)uploaded * row_elems, qold + (size_t)uploaded * row_elems,
+                            (size_t)(need - uploaded) * row_elems * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
+      const long long ncell = (long long)nx * (need - uploaded);
+      aos_to_soa<<<grid_for(ncell, 256), 256, 0, h->s_in>>>(stage + (size_t)uploaded * row_elems, h->q[h->cur], meqn, 0,
+                                                            nx, uploaded, need, 0, 1, g.pitch, g.kstride, g.plane);
+      ++h->launches;
+      uploaded = need;
+    }
+    CK(h, cudaEventRecord(h->ev_in[c], h->s_in));
+    CK(h, cudaStreamWaitEvent(h->s_cmp, h->ev_in[c], 0));
+    if (int rc = launch_step2(h, dx, dy, dt, 0, 1, 1, src, dst, j0, j1, h->s_cmp)) return rc;
+    CK(h, cudaEventRecord(h->ev_cmp[c], h->s_cmp));
+    CK(h, cudaStreamWaitEvent(h->s_out, h->ev_cmp[c], 0));
+    // interior cells of rows [j0, j1) -> staging (same rows of the AoS image, already consumed) -> qnew
+    double* ostage = stage + (size_t)j0 * row_elems;
+    const long long ncell = (long long)mx * (j1 - j0);
+    soa_to_aos<<<grid_for(ncell, 256), 256, 0, h->s_out>>>(dst, ostage, meqn, g.ng, g.ng + mx, j0, j1, 0, 1, g.pitch,
+                                                           g.kstride, g.plane);
+    ++h->launches;
+    const size_t wbytes = (size_t)meqn * mx * sizeof(double);
+    CK(h, cudaMemcpy2DAsync(qnew + ((size_t)j0 * nx + g.ng) * meqn, row_elems * sizeof(double), ostage, wbytes, wbytes,
+                            (size_t)(j1 - j0), cudaMemcpyDeviceToHost, h->s_out));
+  }
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(h->h_cfl, h->work, sizeof(double), cudaMemcpyDeviceToHost, h->s_cmp));
+  CK(h, cudaStreamSynchronize(h->s_cmp));
+  CK(h, cudaStreamSynchronize(h->s_out));
+  if (cfl) *cfl = *h->h_cfl;
+  return 0;
+}
+}  // namespace
+
 int claw_step2_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, int mx, int my, const double* qold,
                     double* qnew, const double* aux, double dx, double dy, double dt, const int* method7,
                     const int* mthlim, int use_fwave, int rp_id, const double* cparam, int ncparam, int mode,
@@ -841,6 +925,10 @@ int claw_step2_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, int
   if ((rc = claw_set_cparam(h, cparam, ncparam))) return host_fail(h, rc);
   if ((rc = claw_set_method(h, method7, mthlim, use_fwave))) return host_fail(h, rc);
   if (h->method[2] < 0) return host_fail(h, fail(h, 41, "claw_step2_host: method(3) = -1 (dimensional splitting) belongs to step2ds"));
+  if (maux == 0 && (long long)mx * my >= (1LL << 20) && my >= 64) {
+    rc = step2_host_pipelined(h, qold, qnew, dx, dy, dt, cfl);
+    return rc ? host_fail(h, rc) : 0;
+  }
   if ((rc = claw_put_qbc(h, qold))) return host_fail(h, rc);
   if (maux > 0 && (rc = claw_put_auxbc(h, aux))) return host_fail(h, rc);
   const double delta[2] = {dx, dy};

@@ -43,8 +43,14 @@ struct RpVcAcoustics3D {
     const double delta2 = qr[MU] - ql[MU];
     const double zi = auxr[0];
     const double zim = auxl[0];
+#ifdef CLAW_STRICT
     const double a1 = ddiv(-delta1 + zi * delta2, zim + zi);
     const double a2 = ddiv(delta1 + zim * delta2, zim + zi);
+#else
+    const double rz = rcp_fast(zim + zi);
+    const double a1 = (-delta1 + zi * delta2) * rz;
+    const double a2 = (delta1 + zim * delta2) * rz;
+#endif
     wave[0][0] = -a1 * zim; wave[0][MU] = a1; wave[0][MV] = 0.0; wave[0][MW] = 0.0;
     s[0] = -auxl[1];
     wave[1][0] = a2 * zi; wave[1][MU] = a2; wave[1][MV] = 0.0; wave[1][MW] = 0.0;
@@ -59,8 +65,16 @@ struct RpVcAcoustics3D {
     // iuvw = ixyz + icoor, wrapped into 2..4 (rpt3_vc_acoustics.f90:80-81); 0-based here
     constexpr int IU = (IXYZ + 1 + ICOOR > 4) ? (IXYZ + 1 + ICOOR - 3 - 1) : (IXYZ + 1 + ICOOR - 1);
     const double zm = auxm[0], zz = auxz[0], zp = auxp[0], cm = auxm[1], cp = auxp[1];
+#ifdef CLAW_STRICT
     const double a1 = ddiv(-asdq[0] + asdq[IU] * zz, zm + zz);
     const double a2 = ddiv(asdq[0] + asdq[IU] * zz, zz + zp);
+#else
+    // the reciprocals depend on the aux cells only: the 4 solves of a cell that share an aux triple (amdq, apdq
+    // and the two cqxx splits) reuse them after inlining (common-subexpression elimination): 12 reciprocals per
+    // cell and sweep instead of 32 divisions
+    const double a1 = (-asdq[0] + asdq[IU] * zz) * rcp_fast(zm + zz);
+    const double a2 = (asdq[0] + asdq[IU] * zz) * rcp_fast(zz + zp);
+#endif
     bm[0] = cm * a1 * zm; bm[1] = 0.0; bm[2] = 0.0; bm[3] = 0.0; bm[IU] = -cm * a1;
     bp[0] = cp * a2 * zp; bp[1] = 0.0; bp[2] = 0.0; bp[3] = 0.0; bp[IU] = cp * a2;
   }
@@ -80,6 +94,7 @@ struct RpEuler3D {
     const double gamma = P.p[0];
     const double gamma1 = gamma - 1.0;
     // Roe averages, rpn3_euler.f90:138-180 (left state qr(:,i-1) = ql here)
+#ifdef CLAW_STRICT
     const double rhsqrtl = sqrt(ql[0]);
     const double rhsqrtr = sqrt(qr[0]);
     const double pl = gamma1 * (ql[4] - ddiv(0.5 * (ql[MU] * ql[MU] + ql[MV] * ql[MV] + ql[MW] * ql[MW]), ql[0]));
@@ -93,8 +108,29 @@ struct RpEuler3D {
     const double asqrd = gamma1 * (enth - .5 * u2v2w2);
     const double a = sqrt(asqrd);
     const double g1a2 = ddiv(gamma1, asqrd);
+#else
+    // fast mode: rsqrt / reciprocal sharing as in RpEuler4Wave2D (rp2.cuh)
+    const double irl = rsqrt_fast(ql[0]), irr = rsqrt_fast(qr[0]);
+    const double iql0 = irl * irl, iqr0 = irr * irr;
+    const double pl = gamma1 * (ql[4] - 0.5 * (ql[MU] * ql[MU] + ql[MV] * ql[MV] + ql[MW] * ql[MW]) * iql0);
+    const double pr = gamma1 * (qr[4] - 0.5 * (qr[MU] * qr[MU] + qr[MV] * qr[MV] + qr[MW] * qr[MW]) * iqr0);
+    const double irs = rcp_fast(ql[0] * irl + qr[0] * irr);
+    const double u = (ql[MU] * irl + qr[MU] * irr) * irs;
+    const double v = (ql[MV] * irl + qr[MV] * irr) * irs;
+    const double w = (ql[MW] * irl + qr[MW] * irr) * irs;
+    const double enth = ((ql[4] + pl) * irl + (qr[4] + pr) * irr) * irs;
+    const double u2v2w2 = u * u + v * v + w * w;
+    const double asqrd = gamma1 * (enth - .5 * u2v2w2);
+    const double ia = rsqrt_fast(asqrd);
+    const double a = asqrd * ia;
+    const double g1a2 = gamma1 * (ia * ia);
+    const double r2a = 0.5 * ia;
+#endif
     const double euv = enth - u2v2w2;
     ctx[0] = u; ctx[1] = v; ctx[2] = w; ctx[3] = enth; ctx[4] = a; ctx[5] = g1a2; ctx[6] = euv; ctx[7] = u2v2w2;
+#ifndef CLAW_STRICT
+    ctx[6] = r2a;      // fast mode carries 1/(2a) instead of euv (= enth - u2v2w2, one subtraction to rebuild)
+#endif
     // waves, :184-221
     const double d1 = qr[0] - ql[0];
     const double d2 = qr[MU] - ql[MU];
@@ -104,7 +140,11 @@ struct RpEuler3D {
     const double al4 = g1a2 * (euv * d1 + u * d2 + v * d3 + w * d4 - d5);
     const double al2 = d3 - v * d1;
     const double al3 = d4 - w * d1;
+#ifdef CLAW_STRICT
     const double al5 = ddiv(d2 + (a - u) * d1 - a * al4, 2.0 * a);
+#else
+    const double al5 = (d2 + (a - u) * d1 - a * al4) * r2a;
+#endif
     const double al1 = d1 - al4 - al5;
     wave[0][0] = al1; wave[0][MU] = al1 * (u - a); wave[0][MV] = al1 * v; wave[0][MW] = al1 * w;
     wave[0][4] = al1 * (enth - u * a);
@@ -118,17 +158,29 @@ struct RpEuler3D {
     // entropy fix, :244-303 (amdq pre-zeroed, :224)
 #pragma unroll
     for (int m = 0; m < MEQN; ++m) amdq[m] = 0.0;
+#ifdef CLAW_STRICT
     const double cim1 = sqrt(ddiv(gamma * pl, ql[0]));
     const double s0 = ddiv(ql[MU], ql[0]) - cim1;
+#else
+    const double cim1 = sqrt(gamma * pl * iql0);
+    const double s0 = ql[MU] * iql0 - cim1;
+#endif
     if (!(s0 >= 0.0 && s[0] > 0.0)) {
       const double rho1 = ql[0] + wave[0][0];
       const double rhou1 = ql[MU] + wave[0][MU];
       const double rhov1 = ql[MV] + wave[0][MV];
       const double rhow1 = ql[MW] + wave[0][MW];
       const double en1 = ql[4] + wave[0][4];
+#ifdef CLAW_STRICT
       const double p1 = gamma1 * (en1 - ddiv(0.5 * (rhou1 * rhou1 + rhov1 * rhov1 + rhow1 * rhow1), rho1));
       const double c1 = sqrt(ddiv(gamma * p1, rho1));
       const double s1 = ddiv(rhou1, rho1) - c1;
+#else
+      const double irho1 = rcp_fast(rho1);
+      const double p1 = gamma1 * (en1 - 0.5 * (rhou1 * rhou1 + rhov1 * rhov1 + rhow1 * rhow1) * irho1);
+      const double c1 = sqrt(gamma * p1 * irho1);
+      const double s1 = rhou1 * irho1 - c1;
+#endif
       double sfract;
       if (s0 < 0.0 && s1 > 0.0) sfract = ddiv(s0 * (s1 - s[0]), s1 - s0);
       else if (s[0] < 0.0) sfract = s[0];
@@ -138,16 +190,25 @@ struct RpEuler3D {
       if (!(s[1] >= 0.0)) {
 #pragma unroll
         for (int m = 0; m < MEQN; ++m) amdq[m] = amdq[m] + s[1] * wave[1][m];
-        const double ci = sqrt(ddiv(gamma * pr, qr[0]));
-        const double s3 = ddiv(qr[MU], qr[0]) + ci;
         const double rho2 = qr[0] - wave[2][0];
         const double rhou2 = qr[MU] - wave[2][MU];
         const double rhov2 = qr[MV] - wave[2][MV];
         const double rhow2 = qr[MW] - wave[2][MW];
         const double en2 = qr[4] - wave[2][4];
+#ifdef CLAW_STRICT
+        const double ci = sqrt(ddiv(gamma * pr, qr[0]));
+        const double s3 = ddiv(qr[MU], qr[0]) + ci;
         const double p2 = gamma1 * (en2 - ddiv(0.5 * (rhou2 * rhou2 + rhov2 * rhov2 + rhow2 * rhow2), rho2));
         const double c2 = sqrt(ddiv(gamma * p2, rho2));
         const double s2 = ddiv(rhou2, rho2) + c2;
+#else
+        const double ci = sqrt(gamma * pr * iqr0);
+        const double s3 = qr[MU] * iqr0 + ci;
+        const double irho2 = rcp_fast(rho2);
+        const double p2 = gamma1 * (en2 - 0.5 * (rhou2 * rhou2 + rhov2 * rhov2 + rhow2 * rhow2) * irho2);
+        const double c2 = sqrt(gamma * p2 * irho2);
+        const double s2 = rhou2 * irho2 + c2;
+#endif
         bool add3 = true;
         if (s2 < 0.0 && s3 > 0.0) sfract = ddiv(s2 * (s3 - s[2]), s3 - s2);
         else if (s[2] < 0.0) sfract = s[2];
@@ -170,8 +231,14 @@ struct RpEuler3D {
   __device__ __forceinline__ static void transverse(const RpParams&, const double* ctx, const double*, const double*,
                                                     const double*, const double* asdq, double* bm, double* bp) {
     constexpr int MU = Dirs3<IXYZ>::MU, MV = Dirs3<IXYZ>::MV, MW = Dirs3<IXYZ>::MW;
+#ifdef CLAW_STRICT
     const double u = ctx[0], v = ctx[1], w = ctx[2], enth = ctx[3], a = ctx[4], g1a2 = ctx[5], euv = ctx[6],
                  u2v2w2 = ctx[7];
+#else
+    const double u = ctx[0], v = ctx[1], w = ctx[2], enth = ctx[3], a = ctx[4], g1a2 = ctx[5], r2a = ctx[6],
+                 u2v2w2 = ctx[7];
+    const double euv = enth - u2v2w2;
+#endif
     // rpt3_euler.f90:118-187 (== rptt3_euler.f90)
     const double al4 = g1a2 * (euv * asdq[0] + u * asdq[MU] + v * asdq[MV] + w * asdq[MW] - asdq[4]);
     const double al2 = asdq[MU] - u * asdq[0];
@@ -179,7 +246,11 @@ struct RpEuler3D {
     double sb0, sb1, sb2;
     if (ICOOR == 2) {
       const double al3 = asdq[MW] - w * asdq[0];
+#ifdef CLAW_STRICT
       const double al5 = ddiv(asdq[MV] + (a - v) * asdq[0] - a * al4, 2.0 * a);
+#else
+      const double al5 = (asdq[MV] + (a - v) * asdq[0] - a * al4) * r2a;
+#endif
       const double al1 = asdq[0] - al4 - al5;
       wb[0][0] = al1; wb[0][MU] = al1 * u; wb[0][MV] = al1 * (v - a); wb[0][MW] = al1 * w;
       wb[0][4] = al1 * (enth - v * a);
@@ -192,7 +263,11 @@ struct RpEuler3D {
       sb2 = v + a;
     } else {
       const double al3 = asdq[MV] - v * asdq[0];
+#ifdef CLAW_STRICT
       const double al5 = ddiv(asdq[MW] + (a - w) * asdq[0] - a * al4, 2.0 * a);
+#else
+      const double al5 = (asdq[MW] + (a - w) * asdq[0] - a * al4) * r2a;
+#endif
       const double al1 = asdq[0] - al4 - al5;
       wb[0][0] = al1; wb[0][MU] = al1 * u; wb[0][MV] = al1 * v; wb[0][MW] = al1 * (w - a);
       wb[0][4] = al1 * (enth - w * a);

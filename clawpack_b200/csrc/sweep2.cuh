@@ -43,6 +43,8 @@ struct Sweep2Params {
   int limit;                // any(mthlim > 0)
   int mthlim[8];
   int seg_rows;             // rows per march segment
+  int j0, j1;               // output rows [j0, j1) of this launch (whole grid: [2, my+2); x-only sweep: [0, my+4));
+                            // a sub-range lets the host pipeline transfers against compute chunk by chunk
   int do_x, do_y;           // split kernel: which sweeps to perform (fused step: both)
   RpParams rp;
 };
@@ -206,8 +208,8 @@ __device__ __forceinline__ void x_face(const Sweep2Params& P, const double* q, i
 // =====================================================================================
 // Unsplit step (step2.f90 semantics), method(3) in {0,1,2}
 // =====================================================================================
-template <class RP, int NT>
-__global__ void __launch_bounds__(NT) sweep2_unsplit(const __grid_constant__ Sweep2Params P) {
+template <class RP, int NT, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant__ Sweep2Params P) {
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE;
   using S = Smem2<RP, NT>;
   constexpr int TX = NT - 4;
@@ -224,8 +226,8 @@ __global__ void __launch_bounds__(NT) sweep2_unsplit(const __grid_constant__ Swe
   const int nx = P.mx + 4;
   const int I = blockIdx.x * TX + t;                       // my column (array coords): 2 + bx*TX - 2 + t
   const int Ic = I < nx ? I : nx - 1;                      // clamped for loads
-  const int Jb = 2 + blockIdx.y * P.seg_rows;              // first output row
-  const int Je = min(Jb + P.seg_rows, P.my + 2);           // one past the last output row
+  const int Jb = P.j0 + blockIdx.y * P.seg_rows;           // first output row
+  const int Je = min(Jb + P.seg_rows, P.j1);               // one past the last output row
   const int tl = t > 0 ? -1 : 0;                           // neighbour offsets (clamped at the strip edge)
   const int tr = t < NT - 1 ? 1 : 0;
 
@@ -450,8 +452,8 @@ __global__ void __launch_bounds__(NT) sweep2_split(const __grid_constant__ Sweep
 
   if (!do_y) {
     // ---- x-sweep only: rows [Jb, Je) of the whole array -------------------------------
-    const int Jb = blockIdx.y * P.seg_rows;
-    const int Je = min(Jb + P.seg_rows, P.my + 4);
+    const int Jb = P.j0 + blockIdx.y * P.seg_rows;
+    const int Je = min(Jb + P.seg_rows, P.j1);
     for (int J = Jb; J < Je; ++J) {
       double q[M];
 #pragma unroll
@@ -476,8 +478,8 @@ __global__ void __launch_bounds__(NT) sweep2_split(const __grid_constant__ Sweep
     return;
   }
 
-  const int Jb = 2 + blockIdx.y * P.seg_rows;
-  const int Je = min(Jb + P.seg_rows, P.my + 2);
+  const int Jb = P.j0 + blockIdx.y * P.seg_rows;
+  const int Je = min(Jb + P.seg_rows, P.j1);
   double qx0[M], qx1[M];                                   // x-updated rows J, J+1 (natural frame)
   double yI_apdq[M], yI_fadd[M];
 #pragma unroll

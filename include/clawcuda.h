@@ -131,6 +131,9 @@ int claw_halo_unpack_aux(claw_solver* h, int side, const double* d_buf);
    events on the handle's stream; returns the average duration in milliseconds (bench.py roofline) */
 int claw_time_sweep(claw_solver* h, const double* delta, double dt, int reps, double* avg_ms);
 
+/* geometry of the last sweep launch: grid.x, grid.y(*z), threads per CTA, dynamic shared memory bytes, resident CTAs
+   per SM (occupancy calculator) -- diagnostics for bench.py / profiles */
+int claw_last_launch_info(const claw_solver* h, int* info5);
 /* kernels launched by this handle so far (bench.py `gpu_launches`) */
 int claw_launch_count(const claw_solver* h, uint64_t* count);
 

@@ -159,6 +159,34 @@ def test_plugin_fmod_matches_oracle_fmod():
                 assert np.array_equal(qa, qb), ids     # whole array incl. the updated ghost rows / columns
 
 
+def test_plugin_pipelined_large_grid_matches_oracle():
+    """claw_step2_host switches to the chunked transfer/compute pipeline above 2^20 cells: same result, bit for
+    bit, as the oracle plug-in (threaded oracle = serial oracle, tests/test_oracle.py)."""
+    from clawpack_b200 import riemann
+    from clawpack_b200.pyclaw import cuda_classic
+    from oracle_fmod import OracleFmod
+    mx, my = 1200, 1100
+    sc = S.shock_bubble(mx=mx, my=my)
+    r = ref_solver(sc)
+    r.apply_bcs()
+    rp = riemann.euler_4wave_2D
+    rp.cparam.gamma = 1.4
+    dx, dy = r.delta
+    dt = 0.9 * dx / 3.5
+    method = np.array([1, 2, 2, 0, 0, 0, 0], dtype=np.intc)
+    mthlim = [4, 4, 4, 4]
+    cu, orc = cuda_classic.fmod(2), OracleFmod(nthreads=8)
+    qa, qb = r.qbc.copy('F'), r.qbc.copy('F')
+    for _ in range(2):      # twice: the second call reuses the pipeline's streams / staging
+        qa, ca = cu.step2(mx, 2, mx, my, qa.copy('F'), qa, None, dx, dy, dt, method, mthlim, 0, 0, 0, 0, False, rp, rp)
+        qb, cb = orc.step2(mx, 2, mx, my, qb.copy('F'), qb, None, dx, dy, dt, method, mthlim, 0, 0, 0, 0, False, rp, rp)
+        assert ca == cb
+        assert np.array_equal(qa[:, 2:-2, 2:-2], qb[:, 2:-2, 2:-2])
+        # ghost cells of qnew are left as passed (include/clawcuda.h)
+        qa[:, :2, :], qa[:, -2:, :], qa[:, :, :2], qa[:, :, -2:] = qb[:, :2, :], qb[:, -2:, :], qb[:, :, :2], qb[:, :, -2:]
+    cu.L.claw_host_release()
+
+
 def test_no_cpu_fallback_symbols_loaded():
     """The CUDA path must run in libclawcuda.so, not in the oracle."""
     import ctypes
