@@ -34,6 +34,19 @@ template <int IXYZ> struct Dirs3 {
 // ------------------------------------------------------------------------------------
 struct RpVcAcoustics3D {
   static constexpr int MEQN = 4, MWAVES = 2, MAUX = 2, NCTX = 0;
+  // Structurally non-zero components of a transverse solve's outputs: pressure and the velocity along the split
+  // direction (rpt3_vc_acoustics.f90:134-145 sets the other two to 0.d0).  Fast mode stores / adds only those
+  // (adding the reference's exact zeros cannot change a value); strict mode keeps all four, op for op.
+  template <int IXYZ, int ICOOR> struct TV {
+    static constexpr int IU = (IXYZ + 1 + ICOOR > 4) ? (IXYZ + 1 + ICOOR - 3 - 1) : (IXYZ + 1 + ICOOR - 1);
+#ifdef CLAW_STRICT
+    static constexpr int N = MEQN;
+    __host__ __device__ static constexpr int comp(int k) { return k; }
+#else
+    static constexpr int N = 2;
+    __host__ __device__ static constexpr int comp(int k) { return k == 0 ? 0 : IU; }
+#endif
+  };
   template <int IXYZ>
   __device__ __forceinline__ static void normal(const RpParams&, const double* ql, const double* qr,
                                                 const double* auxl, const double* auxr, double (*wave)[MEQN],
@@ -58,7 +71,9 @@ struct RpVcAcoustics3D {
 #pragma unroll
     for (int m = 0; m < MEQN; ++m) { amdq[m] = s[0] * wave[0][m]; apdq[m] = s[1] * wave[1][m]; }
   }
-  template <int IXYZ, int ICOOR>
+  // TT: a double-transverse (rptt3) solve -- its input is the output of a split in the OTHER transverse
+  // direction, whose velocity component along this direction is an exact zero
+  template <int IXYZ, int ICOOR, bool TT = false>
   __device__ __forceinline__ static void transverse(const RpParams&, const double*, const double* auxm,
                                                     const double* auxz, const double* auxp, const double* asdq,
                                                     double* bm, double* bp) {
@@ -72,8 +87,8 @@ struct RpVcAcoustics3D {
     // the reciprocals depend on the aux cells only: the 4 solves of a cell that share an aux triple (amdq, apdq
     // and the two cqxx splits) reuse them after inlining (common-subexpression elimination): 12 reciprocals per
     // cell and sweep instead of 32 divisions
-    const double a1 = (-asdq[0] + asdq[IU] * zz) * rcp_fast(zm + zz);
-    const double a2 = (asdq[0] + asdq[IU] * zz) * rcp_fast(zz + zp);
+    const double a1 = (TT ? -asdq[0] : (-asdq[0] + asdq[IU] * zz)) * rcp_fast(zm + zz);
+    const double a2 = (TT ? asdq[0] : (asdq[0] + asdq[IU] * zz)) * rcp_fast(zz + zp);
 #endif
     bm[0] = cm * a1 * zm; bm[1] = 0.0; bm[2] = 0.0; bm[3] = 0.0; bm[IU] = -cm * a1;
     bp[0] = cp * a2 * zp; bp[1] = 0.0; bp[2] = 0.0; bp[3] = 0.0; bp[IU] = cp * a2;
@@ -86,6 +101,10 @@ struct RpVcAcoustics3D {
 // ------------------------------------------------------------------------------------
 struct RpEuler3D {
   static constexpr int MEQN = 5, MWAVES = 3, MAUX = 0, NCTX = 8;
+  template <int IXYZ, int ICOOR> struct TV {          // every component of a transverse output can be non-zero
+    static constexpr int N = MEQN;
+    __host__ __device__ static constexpr int comp(int k) { return k; }
+  };
   template <int IXYZ>
   __device__ __forceinline__ static void normal(const RpParams& P, const double* ql, const double* qr,
                                                 const double*, const double*, double (*wave)[MEQN], double* s,
@@ -227,7 +246,7 @@ struct RpEuler3D {
       apdq[m] = df - amdq[m];
     }
   }
-  template <int IXYZ, int ICOOR>
+  template <int IXYZ, int ICOOR, bool TT = false>
   __device__ __forceinline__ static void transverse(const RpParams&, const double* ctx, const double*, const double*,
                                                     const double*, const double* asdq, double* bm, double* bp) {
     constexpr int MU = Dirs3<IXYZ>::MU, MV = Dirs3<IXYZ>::MV, MW = Dirs3<IXYZ>::MW;

@@ -120,8 +120,11 @@ template <class RP, int IXYZ, int SIDE>
 __device__ __forceinline__ void flux3_side(const RpParams& P, int m3, int m4, double dtdx, double dty, double dtz,
                                            const double* asdq, const double* cqxx, const double* ctx,
                                            const double (*A)[3][RP::MAUX > 0 ? RP::MAUX : 1],
-                                           double (*g)[RP::MEQN], double (*h)[RP::MEQN]) {
+                                           double (*g)[RP::template TV<IXYZ, 2>::N],
+                                           double (*h)[RP::template TV<IXYZ, 3>::N]) {
   constexpr int M = RP::MEQN;
+  using TY = typename RP::template TV<IXYZ, 2>;            // non-zero components of y-like splits (G terms)
+  using TZ = typename RP::template TV<IXYZ, 3>;            // ... of z-like splits (H terms)
   constexpr double SGN = (SIDE == 0) ? -1.0 : 1.0;        // cqxx enters the p-side with -, the m-side with +
   const double hd = 0.5 * dtdx;
   const double sixth = 1.0 / 6.0;
@@ -145,28 +148,32 @@ __device__ __forceinline__ void flux3_side(const RpParams& P, int m3, int m4, do
     if (m4 > 0) {
       double cp2[M], cm2[M];
 #pragma unroll
-      for (int m = 0; m < M; ++m) {
+      for (int m = 0; m < M; ++m) { cp2[m] = 0.0; cm2[m] = 0.0; }
+#pragma unroll
+      for (int k = 0; k < TZ::N; ++k) {
+        const int m = TZ::comp(k);
         if (m4 == 2) { cp2[m] = cp[m] + SGN * (3.0 * cpq[m]); cm2[m] = cm[m] + SGN * (3.0 * cmq[m]); }
         else { cp2[m] = cp[m]; cm2[m] = cm[m]; }
       }
-      RP::template transverse<IXYZ, 2>(P, ctx, A[0][2], A[1][2], A[2][2], cp2, bmcp, bpcp);   // impt = 2
-      RP::template transverse<IXYZ, 2>(P, ctx, A[0][0], A[1][0], A[2][0], cm2, bmcm, bpcm);   // impt = 1
+      RP::template transverse<IXYZ, 2, true>(P, ctx, A[0][2], A[1][2], A[2][2], cp2, bmcp, bpcp);   // impt = 2
+      RP::template transverse<IXYZ, 2, true>(P, ctx, A[0][0], A[1][0], A[2][0], cm2, bmcm, bpcm);   // impt = 1
     }
 #pragma unroll
-    for (int m = 0; m < M; ++m) {
-      g[2][m] = g[2][m] - hd * bm[m];                                  // gadd(m,1,0,.)
-      g[3][m] = g[3][m] - hd * bp[m];                                  // gadd(m,2,0,.)
+    for (int k = 0; k < TY::N; ++k) {
+      const int m = TY::comp(k);
+      g[2][k] = g[2][k] - hd * bm[m];                                  // gadd(m,1,0,.)
+      g[3][k] = g[3][k] - hd * bp[m];                                  // gadd(m,2,0,.)
       if (m4 > 0) {
-        g[3][m] = g[3][m] + sdz * (bpcp[m] - bpcm[m]);
-        g[2][m] = g[2][m] + sdz * (bmcp[m] - bmcm[m]);
-        g[5][m] = g[5][m] - sdz * bpcp[m];                             // gadd(m,2,1,.)
-        g[4][m] = g[4][m] - sdz * bmcp[m];                             // gadd(m,1,1,.)
-        g[1][m] = g[1][m] + sdz * bpcm[m];                             // gadd(m,2,-1,.)
-        g[0][m] = g[0][m] + sdz * bmcm[m];                             // gadd(m,1,-1,.)
+        g[3][k] = g[3][k] + sdz * (bpcp[m] - bpcm[m]);
+        g[2][k] = g[2][k] + sdz * (bmcp[m] - bmcm[m]);
+        g[5][k] = g[5][k] - sdz * bpcp[m];                             // gadd(m,2,1,.)
+        g[4][k] = g[4][k] - sdz * bmcp[m];                             // gadd(m,1,1,.)
+        g[1][k] = g[1][k] + sdz * bpcm[m];                             // gadd(m,2,-1,.)
+        g[0][k] = g[0][k] + sdz * bmcm[m];                             // gadd(m,1,-1,.)
       }
       if (m3 >= 2) {
-        if (SIDE == 0) { g[3][m] = g[3][m] + dtdx * bpq[m]; g[2][m] = g[2][m] + dtdx * bmq[m]; }
-        else           { g[3][m] = g[3][m] - dtdx * bpq[m]; g[2][m] = g[2][m] - dtdx * bmq[m]; }
+        if (SIDE == 0) { g[3][k] = g[3][k] + dtdx * bpq[m]; g[2][k] = g[2][k] + dtdx * bmq[m]; }
+        else           { g[3][k] = g[3][k] - dtdx * bpq[m]; g[2][k] = g[2][k] - dtdx * bmq[m]; }
       }
     }
   }
@@ -176,82 +183,153 @@ __device__ __forceinline__ void flux3_side(const RpParams& P, int m3, int m4, do
     if (m4 > 0) {
       double bp2[M], bm2[M];
 #pragma unroll
-      for (int m = 0; m < M; ++m) {
+      for (int m = 0; m < M; ++m) { bp2[m] = 0.0; bm2[m] = 0.0; }
+#pragma unroll
+      for (int k = 0; k < TY::N; ++k) {
+        const int m = TY::comp(k);
         if (m4 == 2) { bp2[m] = bp[m] + SGN * (3.0 * bpq[m]); bm2[m] = bm[m] + SGN * (3.0 * bmq[m]); }
         else { bp2[m] = bp[m]; bm2[m] = bm[m]; }
       }
-      RP::template transverse<IXYZ, 3>(P, ctx, A[2][0], A[2][1], A[2][2], bp2, bmcp, bpcp);   // impt = 2
-      RP::template transverse<IXYZ, 3>(P, ctx, A[0][0], A[0][1], A[0][2], bm2, bmcm, bpcm);   // impt = 1
+      RP::template transverse<IXYZ, 3, true>(P, ctx, A[2][0], A[2][1], A[2][2], bp2, bmcp, bpcp);   // impt = 2
+      RP::template transverse<IXYZ, 3, true>(P, ctx, A[0][0], A[0][1], A[0][2], bm2, bmcm, bpcm);   // impt = 1
     }
 #pragma unroll
-    for (int m = 0; m < M; ++m) {
-      h[2][m] = h[2][m] - hd * cm[m];
-      h[3][m] = h[3][m] - hd * cp[m];
+    for (int k = 0; k < TZ::N; ++k) {
+      const int m = TZ::comp(k);
+      h[2][k] = h[2][k] - hd * cm[m];
+      h[3][k] = h[3][k] - hd * cp[m];
       if (m4 > 0) {
-        h[3][m] = h[3][m] + sdy * (bpcp[m] - bpcm[m]);
-        h[2][m] = h[2][m] + sdy * (bmcp[m] - bmcm[m]);
-        h[5][m] = h[5][m] - sdy * bpcp[m];
-        h[4][m] = h[4][m] - sdy * bmcp[m];
-        h[1][m] = h[1][m] + sdy * bpcm[m];
-        h[0][m] = h[0][m] + sdy * bmcm[m];
+        h[3][k] = h[3][k] + sdy * (bpcp[m] - bpcm[m]);
+        h[2][k] = h[2][k] + sdy * (bmcp[m] - bmcm[m]);
+        h[5][k] = h[5][k] - sdy * bpcp[m];
+        h[4][k] = h[4][k] - sdy * bmcp[m];
+        h[1][k] = h[1][k] + sdy * bpcm[m];
+        h[0][k] = h[0][k] + sdy * bmcm[m];
       }
       if (m3 >= 2) {
-        if (SIDE == 0) { h[3][m] = h[3][m] + dtdx * cpq[m]; h[2][m] = h[2][m] + dtdx * cmq[m]; }
-        else           { h[3][m] = h[3][m] - dtdx * cpq[m]; h[2][m] = h[2][m] - dtdx * cmq[m]; }
+        if (SIDE == 0) { h[3][k] = h[3][k] + dtdx * cpq[m]; h[2][k] = h[2][k] + dtdx * cmq[m]; }
+        else           { h[3][k] = h[3][k] - dtdx * cpq[m]; h[2][k] = h[2][k] - dtdx * cmq[m]; }
       }
     }
   }
 }
 
-// Both sides of cell c, results to shared memory: sm[(e*M + m)*NT] (g) and sm[((6+e)*M + m)*NT] (h)
+// shared-memory image of a cell's gadd/hadd: g entry e, k-th non-zero component at sm[(e*NG + k)*NT],
+// h at sm[(6*NG + e*NH + k)*NT]
+template <class RP, int IXYZ> struct GH3 {
+  static constexpr int NG = RP::template TV<IXYZ, 2>::N, NH = RP::template TV<IXYZ, 3>::N;
+  static constexpr int PER_THREAD = 6 * (NG + NH);
+};
+
+// Both sides of cell c, results to shared memory
 template <class RP, int IXYZ, int NT>
 __device__ __forceinline__ void flux3_cell(const Sweep3Params& P, double dtdx, double dty, double dtz,
                                            const double* apdqC, const double* cqxxC, const double* ctxC,
                                            const double* amdqR, const double* cqxxR, const double* ctxR,
                                            const double (*A)[3][RP::MAUX > 0 ? RP::MAUX : 1], double* sm) {
-  constexpr int M = RP::MEQN;
-  double g[6][M], h[6][M];
+  constexpr int NG = GH3<RP, IXYZ>::NG, NH = GH3<RP, IXYZ>::NH;
+  double g[6][NG], h[6][NH];
 #pragma unroll
-  for (int e = 0; e < 6; ++e)
+  for (int e = 0; e < 6; ++e) {
 #pragma unroll
-    for (int m = 0; m < M; ++m) { g[e][m] = 0.0; h[e][m] = 0.0; }
+    for (int k = 0; k < NG; ++k) g[e][k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NH; ++k) h[e][k] = 0.0;
+  }
   flux3_side<RP, IXYZ, 0>(P.rp, P.m3, P.m4, dtdx, dty, dtz, apdqC, cqxxC, ctxC, A, g, h);   // iteration i = c
   flux3_side<RP, IXYZ, 1>(P.rp, P.m3, P.m4, dtdx, dty, dtz, amdqR, cqxxR, ctxR, A, g, h);   // iteration i = c+1
 #pragma unroll
-  for (int e = 0; e < 6; ++e)
+  for (int e = 0; e < 6; ++e) {
 #pragma unroll
-    for (int m = 0; m < M; ++m) { sm[(e * M + m) * NT] = g[e][m]; sm[((6 + e) * M + m) * NT] = h[e][m]; }
+    for (int k = 0; k < NG; ++k) sm[(e * NG + k) * NT] = g[e][k];
+#pragma unroll
+    for (int k = 0; k < NH; ++k) sm[(6 * NG + e * NH + k) * NT] = h[e][k];
+  }
 }
 
 // The (a, b) target term of a source pencil (step3.f90:198-225): a / b = offset of the target
 // pencil in the y-like / z-like direction.  sm = shared-memory slot of the SOURCE thread.
-template <int A, int B, int M, int NT>
+// G terms touch the components TY::comp(k), H terms TZ::comp(k); per component the g term is
+// added before the h term, as the reference's expression does.
+template <class RP, int IXYZ, int A, int B, int NT>
 __device__ __forceinline__ void apply_target(double* acc, const double* sm, double dty, double dtz) {
-#define G_(side, slice) sm[((((slice) + 1) * 2 + (side)-1) * M + m) * NT]
-#define H_(side, slice) sm[((6 + ((slice) + 1) * 2 + (side)-1) * M + m) * NT]
+  using TY = typename RP::template TV<IXYZ, 2>;
+  using TZ = typename RP::template TV<IXYZ, 3>;
+  constexpr int NG = TY::N, NH = TZ::N;
+#define G_(side, slice) sm[((((slice) + 1) * 2 + (side)-1) * NG + k) * NT]
+#define H_(side, slice) sm[(6 * NG + (((slice) + 1) * 2 + (side)-1) * NH + k) * NT]
+  if (NG == RP::MEQN && NH == RP::MEQN) {
+    // dense: interleave per component exactly like the reference statement
 #pragma unroll
-  for (int m = 0; m < M; ++m) {
-    double r = acc[m];
-    if (A == -1 && B == 0) { r = r - dty * G_(1, 0); r = r - dtz * (H_(2, -1) - H_(1, -1)); }
-    if (A == -1 && B == -1) { r = r - dty * G_(1, -1); r = r - dtz * H_(1, -1); }
-    if (A == 0 && B == -1) { r = r - dty * (G_(2, -1) - G_(1, -1)); r = r - dtz * H_(1, 0); }
-    if (A == 1 && B == -1) { r = r + dty * G_(2, -1); r = r - dtz * H_(1, 1); }
-    if (A == 1 && B == 0) { r = r + dty * G_(2, 0); r = r - dtz * (H_(2, 1) - H_(1, 1)); }
-    if (A == 1 && B == 1) { r = r + dty * G_(2, 1); r = r + dtz * H_(2, 1); }
-    if (A == 0 && B == 1) { r = r - dty * (G_(2, 1) - G_(1, 1)); r = r + dtz * H_(2, 0); }
-    if (A == -1 && B == 1) { r = r - dty * G_(1, 1); r = r + dtz * H_(2, -1); }
-    acc[m] = r;
+    for (int k = 0; k < RP::MEQN; ++k) {
+      double r = acc[k];
+      if (A == -1 && B == 0) { r = r - dty * G_(1, 0); r = r - dtz * (H_(2, -1) - H_(1, -1)); }
+      if (A == -1 && B == -1) { r = r - dty * G_(1, -1); r = r - dtz * H_(1, -1); }
+      if (A == 0 && B == -1) { r = r - dty * (G_(2, -1) - G_(1, -1)); r = r - dtz * H_(1, 0); }
+      if (A == 1 && B == -1) { r = r + dty * G_(2, -1); r = r - dtz * H_(1, 1); }
+      if (A == 1 && B == 0) { r = r + dty * G_(2, 0); r = r - dtz * (H_(2, 1) - H_(1, 1)); }
+      if (A == 1 && B == 1) { r = r + dty * G_(2, 1); r = r + dtz * H_(2, 1); }
+      if (A == 0 && B == 1) { r = r - dty * (G_(2, 1) - G_(1, 1)); r = r + dtz * H_(2, 0); }
+      if (A == -1 && B == 1) { r = r - dty * G_(1, 1); r = r + dtz * H_(2, -1); }
+      acc[k] = r;
+    }
+  } else {
+    // sparse: the g term of every touched component, then the h term (for a component touched by both,
+    // e.g. the pressure, this is still g before h)
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+      const int m = TY::comp(k);
+      double r = acc[m];
+      if (A == -1 && B == 0) r = r - dty * G_(1, 0);
+      if (A == -1 && B == -1) r = r - dty * G_(1, -1);
+      if (A == 0 && B == -1) r = r - dty * (G_(2, -1) - G_(1, -1));
+      if (A == 1 && B == -1) r = r + dty * G_(2, -1);
+      if (A == 1 && B == 0) r = r + dty * G_(2, 0);
+      if (A == 1 && B == 1) r = r + dty * G_(2, 1);
+      if (A == 0 && B == 1) r = r - dty * (G_(2, 1) - G_(1, 1));
+      if (A == -1 && B == 1) r = r - dty * G_(1, 1);
+      acc[m] = r;
+    }
+#pragma unroll
+    for (int k = 0; k < NH; ++k) {
+      const int m = TZ::comp(k);
+      double r = acc[m];
+      if (A == -1 && B == 0) r = r - dtz * (H_(2, -1) - H_(1, -1));
+      if (A == -1 && B == -1) r = r - dtz * H_(1, -1);
+      if (A == 0 && B == -1) r = r - dtz * H_(1, 0);
+      if (A == 1 && B == -1) r = r - dtz * H_(1, 1);
+      if (A == 1 && B == 0) r = r - dtz * (H_(2, 1) - H_(1, 1));
+      if (A == 1 && B == 1) r = r + dtz * H_(2, 1);
+      if (A == 0 && B == 1) r = r + dtz * H_(2, 0);
+      if (A == -1 && B == 1) r = r + dtz * H_(2, -1);
+      acc[m] = r;
+    }
   }
 }
 // the pencil's own cell (step3.f90:194-197)
-template <int M, int NT>
+template <class RP, int IXYZ, int NT>
 __device__ __forceinline__ void apply_center(double* acc, const double* sm, const double* qadd, const double* fdiff,
                                              double dtdn, double dty, double dtz, bool transverse) {
+  using TY = typename RP::template TV<IXYZ, 2>;
+  using TZ = typename RP::template TV<IXYZ, 3>;
+  constexpr int NG = TY::N, NH = TZ::N;
 #pragma unroll
-  for (int m = 0; m < M; ++m) {
-    double r = (acc[m] + qadd[m]) - dtdn * fdiff[m];
-    if (transverse) { r = r - dty * (G_(2, 0) - G_(1, 0)); r = r - dtz * (H_(2, 0) - H_(1, 0)); }
-    acc[m] = r;
+  for (int m = 0; m < RP::MEQN; ++m) acc[m] = (acc[m] + qadd[m]) - dtdn * fdiff[m];
+  if (transverse) {
+    if (NG == RP::MEQN && NH == RP::MEQN) {
+#pragma unroll
+      for (int k = 0; k < RP::MEQN; ++k) {
+        double r = acc[k];
+        r = r - dty * (G_(2, 0) - G_(1, 0));
+        r = r - dtz * (H_(2, 0) - H_(1, 0));
+        acc[k] = r;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NG; ++k) { const int m = TY::comp(k); acc[m] = acc[m] - dty * (G_(2, 0) - G_(1, 0)); }
+#pragma unroll
+      for (int k = 0; k < NH; ++k) { const int m = TZ::comp(k); acc[m] = acc[m] - dtz * (H_(2, 0) - H_(1, 0)); }
+    }
   }
 }
 #undef G_
@@ -273,19 +351,35 @@ template <int NT> __device__ __forceinline__ void block_max_cfl3(double cfl, uns
   }
 }
 
+// 8-byte asynchronous global -> shared copy (LDGSTS): prefetches the next march step's operands without
+// holding registers; the issuing thread reads its own slots after cp_async_wait_all()
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 
-template <class RP, int NT> struct Smem3 {
-  static constexpr size_t BYTES = (size_t)12 * RP::MEQN * NT * sizeof(double) + 64 * sizeof(double);
+template <class RP, int IXYZ, int NT> struct Smem3 {
+  static constexpr int PER_THREAD = GH3<RP, IXYZ>::PER_THREAD;
+  // march kernels: two stages of per-thread prefetch slots: q(n) [M], aux(n) [MA], the 3x3 aux neighbourhood of
+  // cell n-2 [9 MA] and the old qout(n-2) [M]
+  static constexpr int MA = RP::MAUX > 0 ? RP::MAUX : 0;
+  static constexpr int PF = (IXYZ == 0) ? 0 : (2 * RP::MEQN + 10 * MA);
+  static constexpr int OFF_RED = PER_THREAD * NT;
+  static constexpr int OFF_PF = OFF_RED + 64;
+  static constexpr size_t BYTES = (size_t)(OFF_PF + 2 * PF * NT) * sizeof(double);
 };
 
 // =====================================================================================
 // x-sweep: block (32, BY); lanes <-> I (28 owner lanes + 2 halo lanes per side), thread-y <-> J,
 // march in K.   step3.f90:124-276 (unsplit) / step3ds.f90 idir = 1.
 // =====================================================================================
-template <class RP, int BY>
-__global__ void __launch_bounds__(32 * BY) sweep3_x(const __grid_constant__ Sweep3Params P) {
+template <class RP, int BY, int MINB = 1>
+__global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant__ Sweep3Params P) {
   constexpr int M = RP::MEQN, W = RP::MWAVES, MA = RP::MAUX > 0 ? RP::MAUX : 1, NC = RP::NCTX > 0 ? RP::NCTX : 1;
   constexpr int NT = 32 * BY;
   constexpr int TX = 28;
@@ -293,7 +387,7 @@ __global__ void __launch_bounds__(32 * BY) sweep3_x(const __grid_constant__ Swee
   const int t = threadIdx.x, ty = threadIdx.y;
   const int tid = ty * 32 + t;
   double* const sm = smem + tid;
-  double* const sred = smem + 12 * M * NT;
+  double* const sred = smem + Smem3<RP, 0, NT>::OFF_RED;
 
   const bool split = P.m3 < 0;
   const int nx = P.n[0] + 4, ny = P.n[1] + 4, nz = P.n[2] + 4;
@@ -427,17 +521,17 @@ __global__ void __launch_bounds__(32 * BY) sweep3_x(const __grid_constant__ Swee
       if (transverse) {
         // pencils (J-1, k), (J, k), (J+1, k) in this order (step3.f90:124-125: k outer, j inner);
         // a = J_target - J_source, b = plane_target - k
-        apply_target<1, -1, M, NT>(acc0, sm - 32, dtdy, dtdz);
-        apply_target<0, -1, M, NT>(acc0, sm, dtdy, dtdz);
-        apply_target<-1, -1, M, NT>(acc0, sm + 32, dtdy, dtdz);
-        apply_target<1, 0, M, NT>(acc1, sm - 32, dtdy, dtdz);
-        apply_center<M, NT>(acc1, sm, qadd, fdiff, dtdx, dtdy, dtdz, true);
-        apply_target<-1, 0, M, NT>(acc1, sm + 32, dtdy, dtdz);
-        apply_target<1, 1, M, NT>(acc2, sm - 32, dtdy, dtdz);
-        apply_target<0, 1, M, NT>(acc2, sm, dtdy, dtdz);
-        apply_target<-1, 1, M, NT>(acc2, sm + 32, dtdy, dtdz);
+        apply_target<RP, 0, 1, -1, NT>(acc0, sm - 32, dtdy, dtdz);
+        apply_target<RP, 0, 0, -1, NT>(acc0, sm, dtdy, dtdz);
+        apply_target<RP, 0, -1, -1, NT>(acc0, sm + 32, dtdy, dtdz);
+        apply_target<RP, 0, 1, 0, NT>(acc1, sm - 32, dtdy, dtdz);
+        apply_center<RP, 0, NT>(acc1, sm, qadd, fdiff, dtdx, dtdy, dtdz, true);
+        apply_target<RP, 0, -1, 0, NT>(acc1, sm + 32, dtdy, dtdz);
+        apply_target<RP, 0, 1, 1, NT>(acc2, sm - 32, dtdy, dtdz);
+        apply_target<RP, 0, 0, 1, NT>(acc2, sm, dtdy, dtdz);
+        apply_target<RP, 0, -1, 1, NT>(acc2, sm + 32, dtdy, dtdz);
       } else {
-        apply_center<M, NT>(acc1, sm, qadd, fdiff, dtdx, dtdy, dtdz, false);
+        apply_center<RP, 0, NT>(acc1, sm, qadd, fdiff, dtdx, dtdy, dtdz, false);
       }
       if (owner_lane && interior_i && k - 1 >= kb && k - 1 < ke) {
 #pragma unroll
@@ -456,8 +550,8 @@ __global__ void __launch_bounds__(32 * BY) sweep3_x(const __grid_constant__ Swee
 // y-sweep (IXYZ = 1: march J, thread-y <-> K) and z-sweep (IXYZ = 2: march K, thread-y <-> J);
 // thread-x <-> I.   step3.f90:283-431 / 439-593, step3ds.f90 idir = 2 / 3.
 // =====================================================================================
-template <class RP, int IXYZ, int BX, int BY>
-__global__ void __launch_bounds__(BX * BY) sweep3_march(const __grid_constant__ Sweep3Params P) {
+template <class RP, int IXYZ, int BX, int BY, int MINB = 1>
+__global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_constant__ Sweep3Params P) {
   constexpr int M = RP::MEQN, W = RP::MWAVES, MA = RP::MAUX > 0 ? RP::MAUX : 1, NC = RP::NCTX > 0 ? RP::NCTX : 1;
   constexpr int NT = BX * BY;
   constexpr int TD = (IXYZ == 1) ? 2 : 1;                    // array dimension carried by thread-y
@@ -465,7 +559,9 @@ __global__ void __launch_bounds__(BX * BY) sweep3_march(const __grid_constant__ 
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int tid = ty * BX + tx;
   double* const sm = smem + tid;
-  double* const sred = smem + 12 * M * NT;
+  double* const sred = smem + Smem3<RP, IXYZ, NT>::OFF_RED;
+  using SM3 = Smem3<RP, IXYZ, NT>;
+  double* const spf = smem + SM3::OFF_PF + tid;               // my prefetch slots: stage s, slot j at spf[(s*PF + j)*NT]
 
   const bool split = P.m3 < 0;
   const int nx = P.n[0] + 4, nT = P.n[TD] + 4, nlen = P.n[IXYZ] + 4, mlen = P.n[IXYZ];
@@ -516,13 +612,54 @@ __global__ void __launch_bounds__(BX * BY) sweep3_march(const __grid_constant__ 
   for (int ma = 0; ma < MA; ++ma) auxP[ma] = 1.0;
   double cfl = 0.0;
 
-  for (int n = cb - 2; n <= ce + 1; ++n) {
+  // operands of march step n, fetched asynchronously one step ahead into stage (n & 1):
+  //   slots [0, M): q(n);  [M, M+MA): aux(n);  [M+MA, M+10MA): aux 3x3 of cell n-2;  [M+10MA, 2M+10MA): old qout(n-2)
+  constexpr int PFQ = 0, PFA = M, PFN = M + SM3::MA, PFO = M + 10 * SM3::MA;
+  const bool rmw = !split && !P.first_pass;
+  auto prefetch = [&](int n) {
+    double* st = spf + (size_t)((n & 1) * SM3::PF) * NT;
     const int nc = n < 0 ? 0 : (n < nlen ? n : nlen - 1);
+#pragma unroll
+    for (int m = 0; m < M; ++m) cp_async8(st + (PFQ + m) * NT, qcol + m * P.plane + (long long)nc * strideN);
+    if (RP::MAUX > 0) {
+#pragma unroll
+      for (int ma = 0; ma < SM3::MA; ++ma)
+        cp_async8(st + (PFA + ma) * NT, P.aux + ma * P.plane + col + (long long)nc * strideN);
+      const int c = n - 2;
+      if (c >= cb && c < ce && P.m3 > 0) {
+        // A[dy][dz]: y-sweep: dy <-> thread-y (K), dz <-> thread-x (I); z-sweep: dy <-> I, dz <-> J
+        const int ti[3] = {Im, Ic, Ip};
+        const int tt[3] = {Tm, Tc, Tp};
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dz = 0; dz < 3; ++dz) {
+            const int ii = (IXYZ == 1) ? ti[dz] : ti[dy];
+            const int tj = (IXYZ == 1) ? tt[dy] : tt[dz];
+#pragma unroll
+            for (int ma = 0; ma < SM3::MA; ++ma)
+              cp_async8(st + (PFN + (dy * 3 + dz) * SM3::MA + ma) * NT,
+                        P.aux + ma * P.plane + (long long)tj * strideT + ii + (long long)c * strideN);
+          }
+      }
+    }
+    if (rmw && out_thread && n - 2 >= cb && n - 2 < ce) {
+#pragma unroll
+      for (int m = 0; m < M; ++m) cp_async8(st + (PFO + m) * NT, ocol + m * P.plane + (long long)(n - 2) * strideN);
+    }
+    cp_async_commit();
+  };
+  prefetch(cb - 2);
+
+  for (int n = cb - 2; n <= ce + 1; ++n) {
+    cp_async_wait_all();                                     // operands of step n have landed (my own slots)
+    if (n < ce + 1) prefetch(n + 1);
+    const double* st = spf + (size_t)((n & 1) * SM3::PF) * NT;
     double qN[M], auxN[MA];
 #pragma unroll
-    for (int m = 0; m < M; ++m) qN[m] = qcol[m * P.plane + (long long)nc * strideN];
+    for (int m = 0; m < M; ++m) qN[m] = st[(PFQ + m) * NT];
 #pragma unroll
-    for (int ma = 0; ma < MA; ++ma) auxN[ma] = (RP::MAUX > 0) ? P.aux[ma * P.plane + col + (long long)nc * strideN] : 0.0;
+    for (int ma = 0; ma < MA; ++ma) auxN[ma] = (RP::MAUX > 0) ? st[(PFA + ma) * NT] : 0.0;
     // ---- interface n (raw) ---------------------------------------------------------------
     double waveN[W][M], sN[W], amdqN[M], apdqN[M], ctxN[NC];
     RP::template normal<IXYZ>(P.rp, q1, qN, auxP, auxN, waveN, sN, amdqN, apdqN, ctxN);
@@ -567,19 +704,12 @@ __global__ void __launch_bounds__(BX * BY) sweep3_march(const __grid_constant__ 
       if (transverse) {
         double A[3][3][MA];
         if (RP::MAUX > 0) {
-          // A[dy][dz]: y-sweep: dy <-> thread-y (K), dz <-> thread-x (I); z-sweep: dy <-> I, dz <-> J
-          const int ti[3] = {Im, Ic, Ip};
-          const int tt[3] = {Tm, Tc, Tp};
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-            for (int dz = 0; dz < 3; ++dz) {
-              const int ii = (IXYZ == 1) ? ti[dz] : ti[dy];
-              const int tj = (IXYZ == 1) ? tt[dy] : tt[dz];
+            for (int dz = 0; dz < 3; ++dz)
 #pragma unroll
-              for (int ma = 0; ma < MA; ++ma)
-                A[dy][dz][ma] = P.aux[ma * P.plane + (long long)tj * strideT + ii + (long long)c * strideN];
-            }
+              for (int ma = 0; ma < MA; ++ma) A[dy][dz][ma] = st[(PFN + (dy * 3 + dz) * SM3::MA + ma) * NT];
         }
         flux3_cell<RP, IXYZ, NT>(P, dtdn, dty, dtz, apdqC, cqxxC, ctxC, amdqP, cqxxP, ctxP, A, sm);
       }
@@ -587,33 +717,33 @@ __global__ void __launch_bounds__(BX * BY) sweep3_march(const __grid_constant__ 
       if (out_thread) {
         double acc[M];
 #pragma unroll
-        for (int m = 0; m < M; ++m) acc[m] = P.first_pass ? q2[m] : ocol[m * P.plane + (long long)c * strideN];
+        for (int m = 0; m < M; ++m) acc[m] = P.first_pass ? q2[m] : st[(PFO + m) * NT];
         if (transverse) {
           // source pencils in the reference's loop order: thread-y outer, thread-x inner
           // (step3.f90:283-284 "do k / do i", :439-440 "do j / do i")
           if (IXYZ == 1) {   // a <-> thread-y, b <-> thread-x;   (a, b) = -(source offset)
-            apply_target<1, 1, M, NT>(acc, sm - BX - 1, dty, dtz);
-            apply_target<1, 0, M, NT>(acc, sm - BX, dty, dtz);
-            apply_target<1, -1, M, NT>(acc, sm - BX + 1, dty, dtz);
-            apply_target<0, 1, M, NT>(acc, sm - 1, dty, dtz);
-            apply_center<M, NT>(acc, sm, qadd, fdiff, dtdn, dty, dtz, true);
-            apply_target<0, -1, M, NT>(acc, sm + 1, dty, dtz);
-            apply_target<-1, 1, M, NT>(acc, sm + BX - 1, dty, dtz);
-            apply_target<-1, 0, M, NT>(acc, sm + BX, dty, dtz);
-            apply_target<-1, -1, M, NT>(acc, sm + BX + 1, dty, dtz);
+            apply_target<RP, IXYZ, 1, 1, NT>(acc, sm - BX - 1, dty, dtz);
+            apply_target<RP, IXYZ, 1, 0, NT>(acc, sm - BX, dty, dtz);
+            apply_target<RP, IXYZ, 1, -1, NT>(acc, sm - BX + 1, dty, dtz);
+            apply_target<RP, IXYZ, 0, 1, NT>(acc, sm - 1, dty, dtz);
+            apply_center<RP, IXYZ, NT>(acc, sm, qadd, fdiff, dtdn, dty, dtz, true);
+            apply_target<RP, IXYZ, 0, -1, NT>(acc, sm + 1, dty, dtz);
+            apply_target<RP, IXYZ, -1, 1, NT>(acc, sm + BX - 1, dty, dtz);
+            apply_target<RP, IXYZ, -1, 0, NT>(acc, sm + BX, dty, dtz);
+            apply_target<RP, IXYZ, -1, -1, NT>(acc, sm + BX + 1, dty, dtz);
           } else {           // a <-> thread-x, b <-> thread-y
-            apply_target<1, 1, M, NT>(acc, sm - BX - 1, dty, dtz);
-            apply_target<0, 1, M, NT>(acc, sm - BX, dty, dtz);
-            apply_target<-1, 1, M, NT>(acc, sm - BX + 1, dty, dtz);
-            apply_target<1, 0, M, NT>(acc, sm - 1, dty, dtz);
-            apply_center<M, NT>(acc, sm, qadd, fdiff, dtdn, dty, dtz, true);
-            apply_target<-1, 0, M, NT>(acc, sm + 1, dty, dtz);
-            apply_target<1, -1, M, NT>(acc, sm + BX - 1, dty, dtz);
-            apply_target<0, -1, M, NT>(acc, sm + BX, dty, dtz);
-            apply_target<-1, -1, M, NT>(acc, sm + BX + 1, dty, dtz);
+            apply_target<RP, IXYZ, 1, 1, NT>(acc, sm - BX - 1, dty, dtz);
+            apply_target<RP, IXYZ, 0, 1, NT>(acc, sm - BX, dty, dtz);
+            apply_target<RP, IXYZ, -1, 1, NT>(acc, sm - BX + 1, dty, dtz);
+            apply_target<RP, IXYZ, 1, 0, NT>(acc, sm - 1, dty, dtz);
+            apply_center<RP, IXYZ, NT>(acc, sm, qadd, fdiff, dtdn, dty, dtz, true);
+            apply_target<RP, IXYZ, -1, 0, NT>(acc, sm + 1, dty, dtz);
+            apply_target<RP, IXYZ, 1, -1, NT>(acc, sm + BX - 1, dty, dtz);
+            apply_target<RP, IXYZ, 0, -1, NT>(acc, sm + BX, dty, dtz);
+            apply_target<RP, IXYZ, -1, -1, NT>(acc, sm + BX + 1, dty, dtz);
           }
         } else {
-          apply_center<M, NT>(acc, sm, qadd, fdiff, dtdn, dty, dtz, false);
+          apply_center<RP, IXYZ, NT>(acc, sm, qadd, fdiff, dtdn, dty, dtz, false);
         }
 #pragma unroll
         for (int m = 0; m < M; ++m) ocol[m * P.plane + (long long)c * strideN] = acc[m];

@@ -1,5 +1,6 @@
 // 3-D kernel instantiations + launch heuristics.  Compiled twice (see csrc/build.py), like
 // sweep_inst.cu:  -DCLAW_NS=strict -fmad=false  /  -DCLAW_NS=fast -fmad=true.
+#include <cstdlib>
 #include "launch.h"
 #include "sweep3.cuh"
 
@@ -16,11 +17,11 @@ static int pick_seg(int len, long long tiles, int num_sms) {
   return seg < 1 ? 1 : seg;
 }
 
-template <class RP, int BY>
+template <class RP, int BY, int MINB>
 static cudaError_t launch_x(Sweep3Params& P, int num_sms, cudaStream_t st, LaunchInfo* info) {
   constexpr int NT = 32 * BY;
-  auto kern = sweep3_x<RP, BY>;
-  const int smem = (int)Smem3<RP, NT>::BYTES;
+  auto kern = sweep3_x<RP, BY, MINB>;
+  const int smem = (int)Smem3<RP, 0, NT>::BYTES;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   const bool split = P.m3 < 0;
@@ -28,18 +29,21 @@ static cudaError_t launch_x(Sweep3Params& P, int num_sms, cudaStream_t st, Launc
   const int gx = (nx - 2 + 27) / 28;
   const int gy = split ? (ny + BY - 1) / BY : (P.n[1] + BY - 3) / (BY - 2);
   const int len = split ? nz : P.n[2];
-  P.seg = pick_seg(len, (long long)gx * gy, num_sms);
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+  if (occ < 1) occ = 1;
+  P.seg = pick_seg(len, (long long)gx * gy, num_sms * occ);
   dim3 grid(gx, gy, (len + P.seg - 1) / P.seg), block(32, BY);
   kern<<<grid, block, smem, st>>>(P);
-  if (info) { info->grid_x = grid.x; info->grid_y = grid.y * grid.z; info->block = NT; info->smem_bytes = smem; info->ctas_per_sm = 1; }
+  if (info) { info->grid_x = grid.x; info->grid_y = grid.y * grid.z; info->block = NT; info->smem_bytes = smem; info->ctas_per_sm = occ; }
   return cudaGetLastError();
 }
 
-template <class RP, int IXYZ, int BX, int BY>
+template <class RP, int IXYZ, int BX, int BY, int MINB>
 static cudaError_t launch_march(Sweep3Params& P, int num_sms, cudaStream_t st, LaunchInfo* info) {
   constexpr int NT = BX * BY;
-  auto kern = sweep3_march<RP, IXYZ, BX, BY>;
-  const int smem = (int)Smem3<RP, NT>::BYTES;
+  auto kern = sweep3_march<RP, IXYZ, BX, BY, MINB>;
+  const int smem = (int)Smem3<RP, IXYZ, NT>::BYTES;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   const bool split = P.m3 < 0;
@@ -48,28 +52,35 @@ static cudaError_t launch_march(Sweep3Params& P, int num_sms, cudaStream_t st, L
   const int gx = split ? (nx + BX - 1) / BX : (P.n[0] + BX - 3) / (BX - 2);
   const int gy = split ? (nT + BY - 1) / BY : (P.n[TD] + BY - 3) / (BY - 2);
   const int len = split ? nlen : P.n[IXYZ];
-  P.seg = pick_seg(len, (long long)gx * gy, num_sms);
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+  if (occ < 1) occ = 1;
+  P.seg = pick_seg(len, (long long)gx * gy, num_sms * occ);
   dim3 grid(gx, gy, (len + P.seg - 1) / P.seg), block(BX, BY);
   kern<<<grid, block, smem, st>>>(P);
-  if (info) { info->grid_x = grid.x; info->grid_y = grid.y * grid.z; info->block = NT; info->smem_bytes = smem; info->ctas_per_sm = 1; }
+  if (info) { info->grid_x = grid.x; info->grid_y = grid.y * grid.z; info->block = NT; info->smem_bytes = smem; info->ctas_per_sm = occ; }
   return cudaGetLastError();
 }
 
-template <class RP>
+template <class RP, int BY, int MINB>
 static cudaError_t launch_dir(int dir, Sweep3Params& P, int num_sms, cudaStream_t st, LaunchInfo* info) {
   switch (dir) {
-    case 0: return launch_x<RP, 8>(P, num_sms, st, info);
-    case 1: return launch_march<RP, 1, 32, 8>(P, num_sms, st, info);
-    case 2: return launch_march<RP, 2, 32, 8>(P, num_sms, st, info);
+    case 0: return launch_x<RP, BY, MINB>(P, num_sms, st, info);
+    case 1: return launch_march<RP, 1, 32, BY, MINB>(P, num_sms, st, info);
+    case 2: return launch_march<RP, 2, 32, BY, MINB>(P, num_sms, st, info);
   }
   return cudaErrorInvalidValue;
 }
 
 // dir: 0 = x-sweep, 1 = y-sweep, 2 = z-sweep
 cudaError_t launch_sweep3(int rp_id, int dir, Sweep3Params& P, int num_sms, cudaStream_t st, LaunchInfo* info) {
+  static const int variant = getenv("CLAW_VARIANT3") ? atoi(getenv("CLAW_VARIANT3")) : 0;   // tuning experiments
   switch (rp_id) {
-    case 5: return launch_dir<RpVcAcoustics3D>(dir, P, num_sms, st, info);
-    case 6: return launch_dir<RpEuler3D>(dir, P, num_sms, st, info);
+    case 5:
+      if (variant == 2) return launch_dir<RpVcAcoustics3D, 8, 2>(dir, P, num_sms, st, info);
+      if (variant == 3) return launch_dir<RpVcAcoustics3D, 16, 1>(dir, P, num_sms, st, info);
+      return launch_dir<RpVcAcoustics3D, 8, 1>(dir, P, num_sms, st, info);
+    case 6: return launch_dir<RpEuler3D, 8, 1>(dir, P, num_sms, st, info);
   }
   return cudaErrorInvalidValue;
 }
