@@ -181,7 +181,7 @@ struct RpEuler3D {
     const double cim1 = sqrt(ddiv(gamma * pl, ql[0]));
     const double s0 = ddiv(ql[MU], ql[0]) - cim1;
 #else
-    const double cim1 = sqrt(gamma * pl * iql0);
+    const double cim1 = sqrt_fast(gamma * pl * iql0);
     const double s0 = ql[MU] * iql0 - cim1;
 #endif
     if (!(s0 >= 0.0 && s[0] > 0.0)) {
@@ -197,7 +197,7 @@ struct RpEuler3D {
 #else
       const double irho1 = rcp_fast(rho1);
       const double p1 = gamma1 * (en1 - 0.5 * (rhou1 * rhou1 + rhov1 * rhov1 + rhow1 * rhow1) * irho1);
-      const double c1 = sqrt(gamma * p1 * irho1);
+      const double c1 = sqrt_fast(gamma * p1 * irho1);
       const double s1 = rhou1 * irho1 - c1;
 #endif
       double sfract;
@@ -221,11 +221,11 @@ struct RpEuler3D {
         const double c2 = sqrt(ddiv(gamma * p2, rho2));
         const double s2 = ddiv(rhou2, rho2) + c2;
 #else
-        const double ci = sqrt(gamma * pr * iqr0);
+        const double ci = sqrt_fast(gamma * pr * iqr0);
         const double s3 = qr[MU] * iqr0 + ci;
         const double irho2 = rcp_fast(rho2);
         const double p2 = gamma1 * (en2 - 0.5 * (rhou2 * rhou2 + rhov2 * rhov2 + rhow2 * rhow2) * irho2);
-        const double c2 = sqrt(gamma * p2 * irho2);
+        const double c2 = sqrt_fast(gamma * p2 * irho2);
         const double s2 = rhou2 * irho2 + c2;
 #endif
         bool add3 = true;

@@ -122,6 +122,21 @@ __device__ __forceinline__ void second_order(double dtd, const double (*wave)[RP
   }
 }
 
+// flux2.f90:111-119 for one interface: cfl = max(cfl, dtd*s, -dtd*s) over the wave families.  dtd > 0, so
+// max(dtd*s, -dtd*s) = dtd*|s| bit for bit; fast mode uses that and, for solvers whose speeds are ordered
+// (s[0] <= ... <= s[W-1]: all of rp2.cuh / rp3.cuh), only the two extreme speeds.
+template <int W>
+__device__ __forceinline__ double cfl_update(double cfl, double dtd, const double* s) {
+#ifdef CLAW_STRICT
+#pragma unroll
+  for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtd * s[mw]), -dtd * s[mw]);
+  return cfl;
+#else
+  const double a = fabs(s[0]), b = fabs(s[W - 1]);
+  return fmax2(cfl, dtd * ((b > a) ? b : a));
+#endif
+}
+
 __device__ __forceinline__ void atomic_max_cfl(unsigned long long* addr, double v) {
   // v >= 0: the IEEE bit patterns of non-negative doubles are ordered like unsigned integers
   atomicMax(addr, (unsigned long long)__double_as_longlong(v));
@@ -270,8 +285,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
         RP::normal(P.rp, 1, ql, qr, waveN, sN, amdqN, apdqN, roeN);
       }
       if (y_cfl_col && (J + 2 >= 2) && (J + 2 <= P.my + 2)) {             // flux2.f90:111-119
-#pragma unroll
-        for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtdy * sN[mw]), -dtdy * sN[mw]);
+        cfl = cfl_update<W>(cfl, dtdy, sN);
       }
       double dotn[W];
 #pragma unroll
@@ -356,8 +370,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
       double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
       x_face<RP, NT>(P, q1, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
       if (x_cfl_col && (J + 1 >= 1) && (J + 1 <= P.my + 2)) {             // flux2.f90:111-119
-#pragma unroll
-        for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtdx * s[mw]), -dtdx * s[mw]);
+        cfl = cfl_update<W>(cfl, dtdx, s);
       }
       double bmA[M], bpA[M], bmP[M], bpP[M];
 #pragma unroll
@@ -461,8 +474,7 @@ __global__ void __launch_bounds__(NT) sweep2_split(const __grid_constant__ Sweep
       double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
       x_face<RP, NT>(P, q, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
       if (x_cfl_col) {
-#pragma unroll
-        for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtdx * s[mw]), -dtdx * s[mw]);
+        cfl = cfl_update<W>(cfl, dtdx, s);
       }
 #pragma unroll
       for (int m = 0; m < M; ++m) { sxw[m * NT] = amdq[m]; sxw[(M + m) * NT] = fadd[m]; }
@@ -494,8 +506,7 @@ __global__ void __launch_bounds__(NT) sweep2_split(const __grid_constant__ Sweep
       double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
       x_face<RP, NT>(P, qx2, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
       if (x_cfl_col) {
-#pragma unroll
-        for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtdx * s[mw]), -dtdx * s[mw]);
+        cfl = cfl_update<W>(cfl, dtdx, s);
       }
 #pragma unroll
       for (int m = 0; m < M; ++m) { sxw[m * NT] = amdq[m]; sxw[(M + m) * NT] = fadd[m]; }
@@ -517,8 +528,7 @@ __global__ void __launch_bounds__(NT) sweep2_split(const __grid_constant__ Sweep
         RP::normal(P.rp, 1, ql, qr, waveN, sN, amdqN, apdqN, roeN);
       }
       if (col_ok && (J + 2 >= 2) && (J + 2 <= P.my + 2)) {
-#pragma unroll
-        for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtdy * sN[mw]), -dtdy * sN[mw]);
+        cfl = cfl_update<W>(cfl, dtdy, sN);
       }
       double dotn[W];
 #pragma unroll

@@ -368,7 +368,8 @@ template <class RP, int IXYZ, int NT> struct Smem3 {
   // march kernels: two stages of per-thread prefetch slots: q(n) [M], aux(n) [MA], the 3x3 aux neighbourhood of
   // cell n-2 [9 MA] and the old qout(n-2) [M]
   static constexpr int MA = RP::MAUX > 0 ? RP::MAUX : 0;
-  static constexpr int PF = (IXYZ == 0) ? 0 : (2 * RP::MEQN + 10 * MA);
+  // x-sweep: ring of 4 K-plane slots x 3 rows x MA aux values per thread (slot = plane & 3)
+  static constexpr int PF = (IXYZ == 0) ? (6 * MA) : (2 * RP::MEQN + 10 * MA);
   static constexpr int OFF_RED = PER_THREAD * NT;
   static constexpr int OFF_PF = OFF_RED + 64;
   static constexpr size_t BYTES = (size_t)(OFF_PF + 2 * PF * NT) * sizeof(double);
@@ -418,25 +419,31 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
   const double* abase = P.aux + Ic;
   double q[M], qnext[M];
   double acc0[M], acc1[M], acc2[M];
-  double A[3][3][MA];
 #pragma unroll
   for (int m = 0; m < M; ++m) {
     qnext[m] = qbase[m * P.plane + (long long)k0 * P.kstride];
     acc0[m] = 0.0; acc1[m] = qnext[m]; acc2[m] = 0.0;
   }
-  if (RP::MAUX > 0) {
-    // planes k0-1 (dz slot 1 after the first rotation -> slot 0) and k0 (-> slot 1)
-    const int kz[2] = {k0 > 0 ? k0 - 1 : 0, k0};
-    const int jr[3] = {Jm, Jc, Jp};
+  // aux(I, J-1..J+1, plane p) lives in my shared-memory ring slot p & 3, fetched asynchronously two planes ahead
+  using SM3 = Smem3<RP, 0, NT>;
+  double* const ring = smem + SM3::OFF_PF + tid;
+  auto fetch_plane = [&](int p) {
+    if (RP::MAUX > 0) {
+      const int pc = p < 0 ? 0 : (p < nz ? p : nz - 1);
+      const int jr[3] = {Jm, Jc, Jp};
+      double* slot = ring + (size_t)((p & 3) * 3 * SM3::MA) * NT;
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
+      for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-      for (int ma = 0; ma < MA; ++ma) {
-        A[dy][0][ma] = 0.0;
-        A[dy][1][ma] = abase[ma * P.plane + (long long)kz[0] * P.kstride + (long long)jr[dy] * P.pitch];
-        A[dy][2][ma] = abase[ma * P.plane + (long long)kz[1] * P.kstride + (long long)jr[dy] * P.pitch];
-      }
-  }
+        for (int ma = 0; ma < SM3::MA; ++ma)
+          cp_async8(slot + (dy * SM3::MA + ma) * NT,
+                    abase + ma * P.plane + (long long)pc * P.kstride + (long long)jr[dy] * P.pitch);
+    }
+    cp_async_commit();
+  };
+  fetch_plane(k0 - 1);
+  fetch_plane(k0);
+  fetch_plane(k0 + 1);
   double cfl = 0.0;
 
   for (int k = k0; k <= k1; ++k) {
@@ -448,16 +455,18 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
       qnext[m] = qbase[m * P.plane + (long long)kn * P.kstride];
       acc2[m] = qnext[m];
     }
+    cp_async_wait_all();                                     // planes k-1, k, k+1 are in my ring
+    fetch_plane(k + 2);
+    double A[3][3][MA];
     if (RP::MAUX > 0) {
-      const int jr[3] = {Jm, Jc, Jp};
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
+      for (int dz = 0; dz < 3; ++dz) {
+        const double* slot = ring + (size_t)(((k - 1 + dz) & 3) * 3 * SM3::MA) * NT;
 #pragma unroll
-        for (int ma = 0; ma < MA; ++ma) {
-          A[dy][0][ma] = A[dy][1][ma];
-          A[dy][1][ma] = A[dy][2][ma];
-          A[dy][2][ma] = abase[ma * P.plane + (long long)kn * P.kstride + (long long)jr[dy] * P.pitch];
-        }
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int ma = 0; ma < MA; ++ma) A[dy][dz][ma] = slot[(dy * SM3::MA + ma) * NT];
+      }
     }
     const bool plane_pencil = (k >= P.zlo && k <= P.zhi);    // Fortran k in 0..mz+1
     // ---- interface I (my left face) ------------------------------------------------------
@@ -469,8 +478,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
     double wave[W][M], s[W], amdq[M], apdq[M], ctx[NC], cqxx[M];
     RP::template normal<0>(P.rp, ql, q, auxl, A[1][1], wave, s, amdq, apdq, ctx);      // flux3.f90:201
     if (cfl_lane && plane_pencil) {                                                     // flux3.f90:211-218
-#pragma unroll
-      for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtdx * s[mw]), -dtdx * s[mw]);
+        cfl = cfl_update<W>(cfl, dtdx, s);
     }
 #pragma unroll
     for (int m = 0; m < M; ++m) cqxx[m] = 0.0;
@@ -664,8 +672,7 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
     double waveN[W][M], sN[W], amdqN[M], apdqN[M], ctxN[NC];
     RP::template normal<IXYZ>(P.rp, q1, qN, auxP, auxN, waveN, sN, amdqN, apdqN, ctxN);
     if (pencil && n >= 2 && n <= mlen + 2 && n > cb - 2) {                              // flux3.f90:211-218
-#pragma unroll
-      for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtdn * sN[mw]), -dtdn * sN[mw]);
+        cfl = cfl_update<W>(cfl, dtdn, sN);
     }
     // ---- finish interface n-1: limiter (needs waves n-2 via dotl, n-1, n) + cqxx -----------
     double cqxxP[M];
