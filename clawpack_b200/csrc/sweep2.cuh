@@ -432,8 +432,8 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
 // Segments: blockIdx.y covers output rows [Jb, Je) of [2, my+2) (fused / y-only) or of
 // [0, my+4) (x-only).
 // =====================================================================================
-template <class RP, int NT>
-__global__ void __launch_bounds__(NT) sweep2_split(const __grid_constant__ Sweep2Params P) {
+template <class RP, int NT, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__ Sweep2Params P) {
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE;
   using S = Smem2<RP, NT>;
   constexpr int TX = NT - 4;

@@ -11,7 +11,7 @@ template <class RP, int NT, int MINB = 1>
 static cudaError_t launch_one(int kind, Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st,
                               LaunchInfo* info) {
   using S = Smem2<RP, NT>;
-  auto kern = (kind == 0) ? sweep2_unsplit<RP, NT, MINB> : sweep2_split<RP, NT>;
+  auto kern = (kind == 0) ? sweep2_unsplit<RP, NT, MINB> : sweep2_split<RP, NT, MINB>;
   const int smem = (int)S::BYTES;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
@@ -63,7 +63,15 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
       if (kind == 0 && variant == 0) return launch_one<RpEuler4Wave2D, 64, 6>(kind, P, seg_hint, num_sms, st, info);
       return launch_one<RpEuler4Wave2D, 128>(kind, P, seg_hint, num_sms, st, info);
     }
-    case 4: return launch_one<RpShallowRoeEfix2D, 128>(kind, P, seg_hint, num_sms, st, info);
+    case 4: {
+      static const int variant = getenv("CLAW_VARIANT") ? atoi(getenv("CLAW_VARIANT")) : 0;   // tuning experiments
+      if (variant == 2) return launch_one<RpShallowRoeEfix2D, 128, 2>(kind, P, seg_hint, num_sms, st, info);
+      if (variant == 3) return launch_one<RpShallowRoeEfix2D, 128, 3>(kind, P, seg_hint, num_sms, st, info);
+      if (variant == 4) return launch_one<RpShallowRoeEfix2D, 128, 4>(kind, P, seg_hint, num_sms, st, info);
+      if (variant == 5) return launch_one<RpShallowRoeEfix2D, 64, 6>(kind, P, seg_hint, num_sms, st, info);
+      if (variant == 6) return launch_one<RpShallowRoeEfix2D, 64, 8>(kind, P, seg_hint, num_sms, st, info);
+      return launch_one<RpShallowRoeEfix2D, 128>(kind, P, seg_hint, num_sms, st, info);
+    }
   }
   return cudaErrorInvalidValue;
 }
