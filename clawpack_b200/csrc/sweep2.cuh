@@ -91,12 +91,12 @@ __device__ __forceinline__ void wave_dots(const double (*wave)[RP::MEQN], const 
 }
 
 // limiter.f90:39-50 for one interface, given the dot products with both neighbours
-template <class RP>
+template <class RP, int LIM = 0>
 __device__ __forceinline__ void limit_waves(const Sweep2Params& P, double (*wave)[RP::MEQN], const double* s,
                                             const double* wnorm2, const double* dotl, const double* dotr) {
 #pragma unroll
   for (int mw = 0; mw < RP::MWAVES; ++mw) {
-    const int meth = P.mthlim[mw];
+    const int meth = LIM ? LIM : P.mthlim[mw];
     if (meth == 0) continue;
     if (wnorm2[mw] == 0.0) continue;
     const double wl = philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
@@ -176,7 +176,7 @@ template <class RP, int NT> struct Smem2 {
 // normal solve + (limiter via neighbour exchange) + second-order correction at my left face.
 // On return: wave limited, s, amdq/apdq ORIGINAL fluctuations, cqxx, fadd (= 0.5 cqxx or 0).
 // Contains __syncthreads(): must be called by all threads of the CTA.
-template <class RP, int NT>
+template <class RP, int NT, int LIM = 0>
 __device__ __forceinline__ void x_face(const Sweep2Params& P, const double* q, int t, int tl, int tr,
                                        bool second, bool limit, double* sq, double* sxw, double* sdot,
                                        double (*wave)[RP::MEQN], double* s, double* amdq, double* apdq,
@@ -212,7 +212,7 @@ __device__ __forceinline__ void x_face(const Sweep2Params& P, const double* q, i
       __syncthreads();                                                    // (C)
 #pragma unroll
       for (int mw = 0; mw < W; ++mw) dotl[mw] = sdot[mw * NT + tl];
-      limit_waves<RP>(P, wave, s, wnorm2, dotl, dotr);
+      limit_waves<RP, LIM>(P, wave, s, wnorm2, dotl, dotr);
     }
     second_order<RP>(P.dtdx, wave, s, cqxx);                              // flux2.f90:134-146
 #pragma unroll
@@ -223,9 +223,16 @@ __device__ __forceinline__ void x_face(const Sweep2Params& P, const double* q, i
 // =====================================================================================
 // Unsplit step (step2.f90 semantics), method(3) in {0,1,2}
 // =====================================================================================
-template <class RP, int NT, int MINB = 1>
+// SPEC bit 0: compile-time specialisation for the headline method set -- order 2, every wave family limited with
+//   the same limiter id SPEC >> 4 (4 = MC), method(3) = 2 -- which removes the mode branches (and the register
+//   moves / zero fills at their merge points) from the march loop and lets the warm-up rows run the full body
+//   (their results never reach an output row, see below); SPEC = 0 is the generic kernel.
+// SPEC bit 1: fetch row J+3 one march step ahead.
+template <class RP, int NT, int MINB = 1, int SPEC = 0>
 __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant__ Sweep2Params P) {
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE;
+  constexpr bool SP = (SPEC & 1) != 0, PF = (SPEC & 2) != 0;
+  constexpr int LIM = SP ? (SPEC >> 4) : 0;
   using S = Smem2<RP, NT>;
   constexpr int TX = NT - 4;
   extern __shared__ double smem[];
@@ -248,9 +255,9 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
 
   const double dtdx = P.dtdx, dtdy = P.dtdy;
   const double hdx = 0.5 * dtdx, hdy = 0.5 * dtdy;
-  const bool second = (P.order != 1);
-  const bool limit = second && (P.limit != 0);
-  const int mt = P.mtrans;
+  const bool second = SP ? true : (P.order != 1);
+  const bool limit = SP ? true : (second && (P.limit != 0));
+  const int mt = SP ? 2 : P.mtrans;
 
   const double* qcol = P.qin + Ic;
   double q1[M], qn0[M], qn1[M];
@@ -265,12 +272,28 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
   const bool y_cfl_col = (I >= 1) && (I <= P.mx + 2);
   const bool store_col = (t >= 2) && (t <= NT - 3) && (I <= P.mx + 1);
 
+  // Warm-up rows (J < Jb).  The generic kernel skips the stages whose inputs do not exist yet.  The specialised
+  // kernel runs the full body from the first step: what the skipped stages would have produced only feeds cells
+  // J < Jb (never stored) -- row Jb's accumulator is created fresh at step Jb-2 (qn2 = qN + ...), the carried
+  // y-interface data are overwritten at step Jb-1 -- so the stored values are bit-identical.
+  double qP[M];
+  if (PF) {
+#pragma unroll
+    for (int m = 0; m < M; ++m) qP[m] = qcol[m * P.plane + (long long)(Jb - 1) * P.pitch];
+  }
+  const int Jlast = P.my + 3;
   for (int J = Jb - 3; J < Je; ++J) {
     double* const sgy = sgy0 + (J & 1) * (2 * M * NT);
     // ---- load row J+2 ---------------------------------------------------------------
     double qN[M];
+    if (PF) {
+      const int Jn = (J + 3 < Jlast) ? J + 3 : Jlast;
 #pragma unroll
-    for (int m = 0; m < M; ++m) qN[m] = qcol[m * P.plane + (long long)(J + 2) * P.pitch];
+      for (int m = 0; m < M; ++m) { qN[m] = qP[m]; qP[m] = qcol[m * P.plane + (long long)Jn * P.pitch]; }
+    } else {
+#pragma unroll
+      for (int m = 0; m < M; ++m) qN[m] = qcol[m * P.plane + (long long)(J + 2) * P.pitch];
+    }
 
     // =========================== y-pipeline ==========================================
     double ycomb[M];                                       // (qadd - dtdy*df) - dtdx*(g2 - g1), natural frame
@@ -290,7 +313,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
       double dotn[W];
 #pragma unroll
       for (int mw = 0; mw < W; ++mw) dotn[mw] = 0.0;
-      if (J >= Jb - 2) {
+      if (SP || J >= Jb - 2) {
         double waveC[W][M], wnorm2[W];
 #pragma unroll
         for (int mw = 0; mw < W; ++mw) {
@@ -299,7 +322,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
           for (int m = 0; m < M; ++m) waveC[mw][m] = syw[(mw * M + m) * NT];
         }
         if (limit) wave_dots<RP, true>(waveC, waveN, wnorm2, dotn);
-        if (J >= Jb - 1) {
+        if (SP || J >= Jb - 1) {
           double sC[W], amdqC[M], apdqC[M], roeC[NR], dotl[W];
 #pragma unroll
           for (int m = 0; m < M; ++m) { amdqC[m] = sya[m * NT]; apdqC[m] = sya[(M + m) * NT]; }
@@ -319,7 +342,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
 #pragma unroll
           for (int m = 0; m < M; ++m) fadd[m] = 0.0;
           if (second) {
-            if (limit) limit_waves<RP>(P, waveC, sC, wnorm2, dotl, dotn);
+            if (limit) limit_waves<RP, LIM>(P, waveC, sC, wnorm2, dotl, dotn);
             double cqxx[M];
             second_order<RP>(dtdy, waveC, sC, cqxx);
 #pragma unroll
@@ -366,9 +389,9 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
     double qn2[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) qn2[m] = qN[m];
-    if (J >= Jb - 2) {
+    if (SP || J >= Jb - 2) {
       double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
-      x_face<RP, NT>(P, q1, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
+      x_face<RP, NT, LIM>(P, q1, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
       if (x_cfl_col && (J + 1 >= 1) && (J + 1 <= P.my + 2)) {             // flux2.f90:111-119
         cfl = cfl_update<W>(cfl, dtdx, s);
       }

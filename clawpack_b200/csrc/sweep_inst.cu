@@ -7,12 +7,9 @@
 namespace clawcuda {
 namespace CLAW_NS {
 
-template <class RP, int NT, int MINB = 1>
-static cudaError_t launch_one(int kind, Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st,
-                              LaunchInfo* info) {
-  using S = Smem2<RP, NT>;
-  auto kern = (kind == 0) ? sweep2_unsplit<RP, NT, MINB> : sweep2_split<RP, NT, MINB>;
-  const int smem = (int)S::BYTES;
+template <class KERN>
+static cudaError_t launch_kernel(KERN kern, int NT, int smem, bool x_only, Sweep2Params& P, int seg_hint, int num_sms,
+                                 cudaStream_t st, LaunchInfo* info) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int occ = 1;
@@ -21,7 +18,6 @@ static cudaError_t launch_one(int kind, Sweep2Params& P, int seg_hint, int num_s
   if (occ < 1) occ = 1;
   const int TX = NT - 4;
   const int strips = (P.mx + TX - 1) / TX;
-  const bool x_only = (kind == 1) && !P.do_y;
   if (P.j1 <= P.j0) {                         // default: the whole grid
     P.j0 = x_only ? 0 : 2;
     P.j1 = x_only ? P.my + 4 : P.my + 2;
@@ -46,6 +42,28 @@ static cudaError_t launch_one(int kind, Sweep2Params& P, int seg_hint, int num_s
   return cudaGetLastError();
 }
 
+template <class RP, int NT, int MINB = 1>
+static cudaError_t launch_one(int kind, Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st,
+                              LaunchInfo* info) {
+  using S = Smem2<RP, NT>;
+  auto kern = (kind == 0) ? sweep2_unsplit<RP, NT, MINB> : sweep2_split<RP, NT, MINB>;
+  return launch_kernel(kern, NT, (int)S::BYTES, (kind == 1) && !P.do_y, P, seg_hint, num_sms, st, info);
+}
+
+// unsplit kernel specialised at compile time for the headline method set (see sweep2.cuh)
+template <class RP, int NT, int MINB, int SPEC>
+static cudaError_t launch_spec(Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
+  using S = Smem2<RP, NT>;
+  return launch_kernel(sweep2_unsplit<RP, NT, MINB, SPEC>, NT, (int)S::BYTES, false, P, seg_hint, num_sms, st, info);
+}
+
+// order 2, transverse mode 2, every wave family limited with limiter id `lim`
+template <int W> static bool headline_method(const Sweep2Params& P, int lim) {
+  if (P.order == 1 || P.mtrans != 2 || !P.limit) return false;
+  for (int mw = 0; mw < W; ++mw) if (P.mthlim[mw] != lim) return false;
+  return true;
+}
+
 cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st,
                           LaunchInfo* info) {
   switch (rp_id) {
@@ -53,14 +71,21 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
     case 2: return launch_one<RpAcoustics2D, 128>(kind, P, seg_hint, num_sms, st, info);
     case 3: {
       static const int variant = getenv("CLAW_VARIANT") ? atoi(getenv("CLAW_VARIANT")) : 0;   // tuning experiments
-      if (kind == 0 && variant == 3) return launch_one<RpEuler4Wave2D, 128, 3>(kind, P, seg_hint, num_sms, st, info);
-      if (kind == 0 && variant == 4) return launch_one<RpEuler4Wave2D, 128, 4>(kind, P, seg_hint, num_sms, st, info);
-      if (kind == 0 && variant == 5) return launch_one<RpEuler4Wave2D, 256, 1>(kind, P, seg_hint, num_sms, st, info);
-      if (kind == 0 && variant == 6) return launch_one<RpEuler4Wave2D, 256, 2>(kind, P, seg_hint, num_sms, st, info);
-      if (kind == 0 && variant == 7) return launch_one<RpEuler4Wave2D, 64, 4>(kind, P, seg_hint, num_sms, st, info);
-      if (kind == 0 && variant == 8) return launch_one<RpEuler4Wave2D, 192, 2>(kind, P, seg_hint, num_sms, st, info);
-      if (kind == 0 && variant == 2) return launch_one<RpEuler4Wave2D, 128, 2>(kind, P, seg_hint, num_sms, st, info);
-      if (kind == 0 && variant == 0) return launch_one<RpEuler4Wave2D, 64, 6>(kind, P, seg_hint, num_sms, st, info);
+      if (kind == 0 && headline_method<4>(P, 4)) {
+        constexpr int MC = 4 << 4;
+        switch (variant) {
+          case 0: return launch_spec<RpEuler4Wave2D, 64, 6, MC | 1>(P, seg_hint, num_sms, st, info);
+          case 1: return launch_spec<RpEuler4Wave2D, 64, 6, MC | 3>(P, seg_hint, num_sms, st, info);
+          case 2: return launch_spec<RpEuler4Wave2D, 64, 7, MC | 1>(P, seg_hint, num_sms, st, info);
+          case 3: return launch_spec<RpEuler4Wave2D, 64, 8, MC | 1>(P, seg_hint, num_sms, st, info);
+          case 4: return launch_spec<RpEuler4Wave2D, 64, 5, MC | 3>(P, seg_hint, num_sms, st, info);
+          case 5: return launch_spec<RpEuler4Wave2D, 96, 4, MC | 1>(P, seg_hint, num_sms, st, info);
+          case 6: return launch_spec<RpEuler4Wave2D, 128, 3, MC | 1>(P, seg_hint, num_sms, st, info);
+          case 7: return launch_spec<RpEuler4Wave2D, 64, 8, MC | 3>(P, seg_hint, num_sms, st, info);
+          default: break;     // 9: the generic kernel
+        }
+      }
+      if (kind == 0) return launch_one<RpEuler4Wave2D, 64, 6>(kind, P, seg_hint, num_sms, st, info);
       return launch_one<RpEuler4Wave2D, 128>(kind, P, seg_hint, num_sms, st, info);
     }
     case 4: {
