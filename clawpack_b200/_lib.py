@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libclawcuda.so')
+LIB_PATH = os.environ.get('CLAWCUDA_LIB') or os.path.join(_HERE, 'libclawcuda.so')   # override: tuning A/B builds
 
 _lib = None
 

@@ -10,6 +10,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), 'libclawcuda.so')
+EXTRA = os.environ.get('CLAW_EXTRA_NVCC', '').split()     # tuning experiments only
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 HOSTCXX = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
 COMMON = ['nvcc', '-ccbin', HOSTCXX] + ARCH + ['-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '--threads', '4']
@@ -44,7 +45,7 @@ def build(force=False, verbose=False):
         for ns, flags in (('strict', ['-DCLAW_NS=strict', '-DCLAW_STRICT=1', '-fmad=false']),
                           ('fast', ['-DCLAW_NS=fast', '-fmad=true'])):
             o = os.path.join(bdir, '%s_%s.o' % (stem, ns))
-            jobs.append(subprocess.Popen(COMMON + extra + flags + ['-c', unit, '-o', o], cwd=HERE))
+            jobs.append(subprocess.Popen(COMMON + extra + EXTRA + flags + ['-c', unit, '-o', o], cwd=HERE))
             objs.append(o)
     o = os.path.join(bdir, 'clawcuda.o')
     have3 = os.path.exists(os.path.join(HERE, 'sweep3_inst.cu'))

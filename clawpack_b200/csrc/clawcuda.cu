@@ -377,6 +377,7 @@ int launch_step2(claw_solver* h, double dx, double dy, double dt, int kind, int 
   P.limit = 0;
   for (int mw = 0; mw < h->mwaves; ++mw) { P.mthlim[mw] = h->mthlim[mw]; if (h->mthlim[mw] > 0) P.limit = 1; }
   P.do_x = do_x; P.do_y = do_y;
+  P.aux = h->aux; P.maux = h->maux; P.capa = h->method[5]; P.fwave = h->use_fwave;
   for (int k = 0; k < 4; ++k) P.rp.p[k] = h->cparam[k];
   cudaError_t e = (h->mode == CLAW_MODE_FAST)
                       ? fast::launch_sweep2(h->rp_id, kind, P, h->seg_rows, h->num_sms, st, &h->last_launch)
@@ -436,13 +437,28 @@ int launch_step(claw_solver* h, const double* delta, double dt, const double* sr
   return launch_step2(h, delta[0], delta[1], dt, kind, 1, 1, src, dst);
 }
 
+// aux planes read by the 2-D Riemann solvers (rp2.cuh: none; rp2_aux.cuh: RP::MAUX); -1 = unknown id
+int rp2_aux_planes(int rp_id) {
+  switch (rp_id) {
+    case 1: case 2: case 3: case 4: return 0;
+    case 7: return 2;      // vc_acoustics_2D: density, sound speed
+    case 8: return 2;      // vc_advection_2D: edge velocities
+  }
+  return -1;
+}
+
 int validate_config(claw_solver* h) {
   if (h->g.ndim == 2) {
-    if (h->rp_id < 1 || h->rp_id > 4) return fail(h, 30, "rp_id %d is not a 2-D Riemann solver of this build", h->rp_id);
-    if (h->maux != 0 || h->method[5] != 0)
-      return fail(h, 31, "aux arrays / capacity functions are not supported by the 2-D CUDA kernels yet "
-                         "(num_aux=%d, index_capa=%d)", h->maux, h->method[5] - 1);
-    if (h->use_fwave) return fail(h, 32, "f-wave solvers are not supported by the CUDA kernels yet");
+    const int need_aux = rp2_aux_planes(h->rp_id);          // aux planes the solver reads (-1: not a 2-D solver)
+    if (need_aux < 0) return fail(h, 30, "rp_id %d is not a 2-D Riemann solver of this build", h->rp_id);
+    if (h->maux < need_aux)
+      return fail(h, 31, "Riemann solver %d reads %d aux components, the state has num_aux=%d", h->rp_id, need_aux, h->maux);
+    if (h->method[5] < 0 || h->method[5] > h->maux)
+      return fail(h, 31, "index_capa=%d is outside the aux array (num_aux=%d)", h->method[5] - 1, h->maux);
+    if (need_aux == 0 && h->method[5] != 0)
+      return fail(h, 31, "capacity functions are only implemented for the aux-reading 2-D solvers (rp_id %d reads none)", h->rp_id);
+    if (need_aux == 0 && h->use_fwave)
+      return fail(h, 32, "rp_id %d is not an f-wave solver", h->rp_id);
     if (h->method[1] != 1 && h->method[1] != 2) return fail(h, 33, "order must be 1 or 2 (got %d)", h->method[1]);
     if (h->method[2] < -1 || h->method[2] > 2) return fail(h, 34, "transverse_waves must be 0, 1 or 2 in 2-D (got %d)", h->method[2]);
     for (int mw = 0; mw < h->mwaves; ++mw)
@@ -489,8 +505,9 @@ int claw_create(claw_solver** out, int ndim, int rp_id, int meqn, int mwaves, in
   if (num_ghost != 2) return fail(nullptr, 3, "claw_create: num_ghost must be 2 (classic solvers), got %d", num_ghost);
   if (meqn < 1 || meqn > 8 || mwaves < 1 || mwaves > 8 || maux < 0)
     return fail(nullptr, 4, "claw_create: bad sizes meqn=%d mwaves=%d maux=%d", meqn, mwaves, maux);
-  static const int k_meqn[] = {0, 1, 3, 4, 3, 4, 5}, k_mwaves[] = {0, 1, 2, 4, 3, 2, 3}, k_ndim[] = {0, 2, 2, 2, 2, 3, 3};
-  if (rp_id < 1 || rp_id > 6) return fail(nullptr, 5, "claw_create: unknown rp_id %d", rp_id);
+  static const int k_meqn[] = {0, 1, 3, 4, 3, 4, 5, 3, 1}, k_mwaves[] = {0, 1, 2, 4, 3, 2, 3, 2, 1},
+                   k_ndim[] = {0, 2, 2, 2, 2, 3, 3, 2, 2};
+  if (rp_id < 1 || rp_id > 8) return fail(nullptr, 5, "claw_create: unknown rp_id %d", rp_id);
   if (k_meqn[rp_id] != meqn || k_mwaves[rp_id] != mwaves || k_ndim[rp_id] != ndim)
     return fail(nullptr, 6, "claw_create: rp_id %d expects ndim=%d meqn=%d mwaves=%d (got %d, %d, %d)", rp_id,
                 k_ndim[rp_id], k_meqn[rp_id], k_mwaves[rp_id], ndim, meqn, mwaves);

@@ -1,0 +1,80 @@
+// Point-wise 2-D Riemann solvers that read aux arrays (device functors for sweep2_aux.cuh).
+// Rotated frame as in rp2.cuh: component 1 = momentum/velocity normal to the interface (`mu`), 2 = transverse (`mv`).
+// normal():      ql/axl = state/aux of the LEFT cell (Fortran qr(:,i-1), auxr(:,i-1)), qr/axr = RIGHT cell (ql(:,i), auxl(:,i))
+// transverse():  ax1/ax2/ax3 = aux of the cell the fluctuation enters (i1 = i-2+imp) in pencils 1, 2, 3
+//                (rows j-1, j, j+1 for an x-sweep; columns i-1, i, i+1 for a y-sweep)
+#pragma once
+#include "rp2.cuh"
+
+namespace clawcuda {
+namespace CLAW_NS {
+
+// ------------------------------------------------------------------------------------
+// vc_acoustics_2D -- riemann/src/rpn2_vc_acoustics.f90:62-101, rpt2_vc_acoustics.f90:27-77
+// aux(1) = density, aux(2) = sound speed; no common block.   roe = (c_left, c_right)
+// ------------------------------------------------------------------------------------
+struct RpVcAcoustics2D {
+  static constexpr int MEQN = 3, MWAVES = 2, NROE = 2, NCELL = 0, MAUX = 2;
+  __device__ __forceinline__ static void normal(const RpParams& P, int dir, const double* ql, const double* qr,
+                                                const double* axl, const double* axr, double (*wave)[MEQN],
+                                                double* s, double* amdq, double* apdq, double* roe) {
+    const double delta1 = qr[0] - ql[0];
+    const double delta2 = qr[1] - ql[1];
+    const double zi = axr[0] * axr[1];                       // :76  auxl(1,i)*auxl(2,i)
+    const double zim = axl[0] * axl[1];                      // :77  auxr(1,i-1)*auxr(2,i-1)
+    const double a1 = ddiv(-delta1 + zi * delta2, zim + zi);
+    const double a2 = ddiv(delta1 + zim * delta2, zim + zi);
+    wave[0][0] = -a1 * zim; wave[0][1] = a1; wave[0][2] = 0.0;
+    s[0] = -axl[1];
+    wave[1][0] = a2 * zi;   wave[1][1] = a2; wave[1][2] = 0.0;
+    s[1] = axr[1];
+#pragma unroll
+    for (int m = 0; m < MEQN; ++m) { amdq[m] = s[0] * wave[0][m]; apdq[m] = s[1] * wave[1][m]; }
+    roe[0] = axl[1]; roe[1] = axr[1];
+  }
+  __device__ __forceinline__ static void speeds(const RpParams& P, int dir, const double* roe, double* s) {
+    s[0] = -roe[0]; s[1] = roe[1];
+  }
+  __device__ __forceinline__ static void transverse(const RpParams& P, int dir, const double* roe, const double* ax1,
+                                                    const double* ax2, const double* ax3, const double* asdq,
+                                                    double* bm, double* bp) {
+    const double cm = ax1[1], cp = ax3[1];
+    const double zm = ax1[0] * ax1[1];
+    const double zz = ax2[0] * ax2[1];
+    const double zp = ax3[0] * ax3[1];
+    const double a1 = ddiv(-asdq[0] + asdq[2] * zz, zm + zz);     // :58-59
+    const double a2 = ddiv(asdq[0] + asdq[2] * zz, zz + zp);      // :61-62
+    bm[0] = cm * a1 * zm; bm[1] = 0.0; bm[2] = -cm * a1;
+    bp[0] = cp * a2 * zp; bp[1] = 0.0; bp[2] = cp * a2;
+  }
+};
+
+// ------------------------------------------------------------------------------------
+// vc_advection_2D -- riemann/src/rpn2_vc_advection.f90, rpt2_vc_advection.f90 (colour equation, edge velocities)
+// aux(1) = u at the left edge, aux(2) = v at the bottom edge of the cell
+// ------------------------------------------------------------------------------------
+struct RpVcAdvection2D {
+  static constexpr int MEQN = 1, MWAVES = 1, NROE = 1, NCELL = 0, MAUX = 2;
+  __device__ __forceinline__ static void normal(const RpParams& P, int dir, const double* ql, const double* qr,
+                                                const double* axl, const double* axr, double (*wave)[MEQN],
+                                                double* s, double* amdq, double* apdq, double* roe) {
+    wave[0][0] = qr[0] - ql[0];
+    s[0] = axr[dir];                                          // auxl(ixy,i)
+    amdq[0] = fmin2(axr[dir], 0.0) * wave[0][0];
+    apdq[0] = fmax2(axr[dir], 0.0) * wave[0][0];
+    roe[0] = axr[dir];
+  }
+  __device__ __forceinline__ static void speeds(const RpParams& P, int dir, const double* roe, double* s) {
+    s[0] = roe[0];
+  }
+  __device__ __forceinline__ static void transverse(const RpParams& P, int dir, const double* roe, const double* ax1,
+                                                    const double* ax2, const double* ax3, const double* asdq,
+                                                    double* bm, double* bp) {
+    const int kv = 1 - dir;                                   // kv = 3-ixy
+    bm[0] = fmin2(ax2[kv], 0.0) * asdq[0];
+    bp[0] = fmax2(ax3[kv], 0.0) * asdq[0];
+  }
+};
+
+}  // namespace CLAW_NS
+}  // namespace clawcuda

@@ -47,6 +47,11 @@ struct Sweep2Params {
                             // a sub-range lets the host pipeline transfers against compute chunk by chunk
   int do_x, do_y;           // split kernel: which sweeps to perform (fused step: both)
   RpParams rp;
+  // aux-reading solvers / capacity functions / f-waves (sweep2_aux.cuh)
+  const double* aux;        // SoA planes like q (same pitch / plane stride), ghost cells filled
+  int maux;                 // planes present
+  int capa;                 // method(6) = index_capa + 1 (1-based aux plane of the capacity function), 0 = none
+  int fwave;                // use_fwave
 };
 #endif
 
@@ -98,8 +103,15 @@ __device__ __forceinline__ void limit_waves(const Sweep2Params& P, double (*wave
   for (int mw = 0; mw < RP::MWAVES; ++mw) {
     const int meth = LIM ? LIM : P.mthlim[mw];
     if (meth == 0) continue;
+#if defined(CLAW_STRICT) || !defined(CLAW_BRANCHFREE_LIMITER)
     if (wnorm2[mw] == 0.0) continue;
     const double wl = philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
+#else
+    // experiment (off by default, no gain measured): branch-free, so that the divisions of the wave families are
+    // independent chains (a zero wave yields NaN here and is left untouched by the select)
+    double wl = philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
+    wl = (wnorm2[mw] == 0.0) ? 1.0 : wl;
+#endif
 #pragma unroll
     for (int m = 0; m < RP::MEQN; ++m) wave[mw][m] = wl * wave[mw][m];
   }
@@ -158,13 +170,14 @@ template <int NT> __device__ __forceinline__ void block_max_cfl(double cfl, unsi
 }
 
 template <class RP, int NT> struct Smem2 {
-  static constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE;
+  static constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE, NC = RP::NCELL;
   static constexpr int XW = (W * M > 4 * M) ? W * M : 4 * M;
+  static constexpr int QC = (M + NC > W) ? M + NC : W;
   // doubles per thread column
-  static constexpr int OFF_Q = 0;               // [M]     q of the x-row (neighbour access)
-  static constexpr int OFF_XW = OFF_Q + M;      // [XW]    x waves, then x outputs (aliased)
-  static constexpr int OFF_DOT = OFF_XW + XW;   // [W]     dotr exchange
-  static constexpr int OFF_GY = OFF_DOT + W;    // [2][2M] y gadd exchange, double-buffered by step parity
+  static constexpr int OFF_Q = 0;               // [M+NC]  q and per-cell data of the x-row (neighbour access);
+  static constexpr int OFF_DOT = OFF_Q;         // [W]     ... then the dotr exchange (q slot is free after barrier B)
+  static constexpr int OFF_XW = OFF_Q + QC;     // [XW]    x waves, then x outputs (aliased)
+  static constexpr int OFF_GY = OFF_XW + XW;    // [2][2M] y gadd exchange, double-buffered by step parity
   static constexpr int OFF_YW = OFF_GY + 4 * M; // [W*M]   private: waves of the pending y-interface
   static constexpr int OFF_YA = OFF_YW + W * M; // [2M+NR+W] private: amdq, apdq, roe, dotl
   static constexpr int PER_THREAD = OFF_YA + 2 * M + NR + W;
@@ -177,18 +190,22 @@ template <class RP, int NT> struct Smem2 {
 // On return: wave limited, s, amdq/apdq ORIGINAL fluctuations, cqxx, fadd (= 0.5 cqxx or 0).
 // Contains __syncthreads(): must be called by all threads of the CTA.
 template <class RP, int NT, int LIM = 0>
-__device__ __forceinline__ void x_face(const Sweep2Params& P, const double* q, int t, int tl, int tr,
+__device__ __forceinline__ void x_face(const Sweep2Params& P, const double* q, const double* c, int t, int tl, int tr,
                                        bool second, bool limit, double* sq, double* sxw, double* sdot,
                                        double (*wave)[RP::MEQN], double* s, double* amdq, double* apdq,
                                        double* roe, double* cqxx, double* fadd) {
-  constexpr int M = RP::MEQN, W = RP::MWAVES;
+  constexpr int M = RP::MEQN, W = RP::MWAVES, NC = RP::NCELL;
 #pragma unroll
   for (int m = 0; m < M; ++m) sq[m * NT] = q[m];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) sq[(M + k) * NT] = c[k];
   __syncthreads();                                                        // (A)
-  double ql[M];
+  double ql[M], cl[NC > 0 ? NC : 1];
 #pragma unroll
   for (int m = 0; m < M; ++m) ql[m] = sq[m * NT + tl];
-  RP::normal(P.rp, 0, ql, q, wave, s, amdq, apdq, roe);                  // flux2.f90:101
+#pragma unroll
+  for (int k = 0; k < NC; ++k) cl[k] = sq[(M + k) * NT + tl];
+  RP::normal(P.rp, 0, ql, q, cl, c, wave, s, amdq, apdq, roe);           // flux2.f90:101
 #pragma unroll
   for (int m = 0; m < M; ++m) { cqxx[m] = 0.0; fadd[m] = 0.0; }
   if (second) {
@@ -232,6 +249,7 @@ template <class RP, int NT, int MINB = 1, int SPEC = 0>
 __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant__ Sweep2Params P) {
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE;
   constexpr bool SP = (SPEC & 1) != 0, PF = (SPEC & 2) != 0;
+  constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
   constexpr int LIM = SP ? (SPEC >> 4) : 0;
   using S = Smem2<RP, NT>;
   constexpr int TX = NT - 4;
@@ -260,13 +278,14 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
   const int mt = SP ? 2 : P.mtrans;
 
   const double* qcol = P.qin + Ic;
-  double q1[M], qn0[M], qn1[M];
+  double q1[M], qn0[M], qn1[M], c1[NC1];
   double yI_apdq[M], yI_fadd[M], yI_bm[M], yI_bp[M];      // finished y-interface J (rotated frame)
 #pragma unroll
   for (int m = 0; m < M; ++m) {
     q1[m] = qcol[m * P.plane + (long long)(Jb - 2) * P.pitch];
     qn0[m] = 0.0; qn1[m] = 0.0; yI_apdq[m] = 0.0; yI_fadd[m] = 0.0; yI_bm[m] = 0.0; yI_bp[m] = 0.0;
   }
+  if constexpr (NC > 0) RP::cell(P.rp, q1, c1);
   double cfl = 0.0;
   const bool x_cfl_col = (t >= 1) && (I >= 2) && (I <= P.mx + 2);
   const bool y_cfl_col = (I >= 1) && (I <= P.mx + 2);
@@ -294,6 +313,8 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
 #pragma unroll
       for (int m = 0; m < M; ++m) qN[m] = qcol[m * P.plane + (long long)(J + 2) * P.pitch];
     }
+    double cN[NC1];
+    if constexpr (NC > 0) RP::cell(P.rp, qN, cN);
 
     // =========================== y-pipeline ==========================================
     double ycomb[M];                                       // (qadd - dtdy*df) - dtdx*(g2 - g1), natural frame
@@ -305,7 +326,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
         double ql[M], qr[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) { ql[m] = q1[rot<M>(m)]; qr[m] = qN[rot<M>(m)]; }
-        RP::normal(P.rp, 1, ql, qr, waveN, sN, amdqN, apdqN, roeN);
+        RP::normal(P.rp, 1, ql, qr, c1, cN, waveN, sN, amdqN, apdqN, roeN);
       }
       if (y_cfl_col && (J + 2 >= 2) && (J + 2 <= P.my + 2)) {             // flux2.f90:111-119
         cfl = cfl_update<W>(cfl, dtdy, sN);
@@ -391,7 +412,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
     for (int m = 0; m < M; ++m) qn2[m] = qN[m];
     if (SP || J >= Jb - 2) {
       double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
-      x_face<RP, NT, LIM>(P, q1, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
+      x_face<RP, NT, LIM>(P, q1, c1, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
       if (x_cfl_col && (J + 1 >= 1) && (J + 1 <= P.my + 2)) {             // flux2.f90:111-119
         cfl = cfl_update<W>(cfl, dtdx, s);
       }
@@ -443,6 +464,8 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
     }
 #pragma unroll
     for (int m = 0; m < M; ++m) { qn0[m] = qn1[m]; qn1[m] = qn2[m]; q1[m] = qN[m]; }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) c1[k] = cN[k];
   }
   block_max_cfl<NT>(cfl, P.cfl_bits, sred);
 }
@@ -478,6 +501,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__
   const bool second = (P.order != 1);
   const bool limit = second && (P.limit != 0);
   const bool do_x = P.do_x != 0, do_y = P.do_y != 0;
+  constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
   const double* qcol = P.qin + Ic;
   double cfl = 0.0;
   const bool x_cfl_col = (t >= 1) && (I >= 2) && (I <= P.mx + 2);
@@ -494,8 +518,10 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__
       double q[M];
 #pragma unroll
       for (int m = 0; m < M; ++m) q[m] = qcol[m * P.plane + (long long)J * P.pitch];
+      double cq[NC1];
+      if constexpr (NC > 0) RP::cell(P.rp, q, cq);
       double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
-      x_face<RP, NT>(P, q, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
+      x_face<RP, NT>(P, q, cq, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
       if (x_cfl_col) {
         cfl = cfl_update<W>(cfl, dtdx, s);
       }
@@ -515,10 +541,12 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__
 
   const int Jb = P.j0 + blockIdx.y * P.seg_rows;
   const int Je = min(Jb + P.seg_rows, P.j1);
-  double qx0[M], qx1[M];                                   // x-updated rows J, J+1 (natural frame)
+  double qx0[M], qx1[M], cx1[NC1];                         // x-updated rows J, J+1 (natural frame)
   double yI_apdq[M], yI_fadd[M];
 #pragma unroll
   for (int m = 0; m < M; ++m) { qx0[m] = 0.0; qx1[m] = 0.0; yI_apdq[m] = 0.0; yI_fadd[m] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < NC1; ++k) cx1[k] = 0.0;
 
   for (int J = Jb - 4; J < Je; ++J) {
     // ---- x-sweep of row J+2 ----------------------------------------------------------
@@ -526,8 +554,10 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__
 #pragma unroll
     for (int m = 0; m < M; ++m) qx2[m] = qcol[m * P.plane + (long long)(J + 2) * P.pitch];
     if (do_x) {
+      double cq[NC1];
+      if constexpr (NC > 0) RP::cell(P.rp, qx2, cq);
       double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
-      x_face<RP, NT>(P, qx2, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
+      x_face<RP, NT>(P, qx2, cq, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
       if (x_cfl_col) {
         cfl = cfl_update<W>(cfl, dtdx, s);
       }
@@ -542,13 +572,15 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__
       }
     }
     // ---- y-pipeline --------------------------------------------------------------------
+    double cx2[NC1];
+    if constexpr (NC > 0) RP::cell(P.rp, qx2, cx2);                                // of the x-updated cell
     if (J >= Jb - 3) {
       double waveN[W][M], sN[W], amdqN[M], apdqN[M], roeN[NR];
       {
         double ql[M], qr[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) { ql[m] = qx1[rot<M>(m)]; qr[m] = qx2[rot<M>(m)]; }
-        RP::normal(P.rp, 1, ql, qr, waveN, sN, amdqN, apdqN, roeN);
+        RP::normal(P.rp, 1, ql, qr, cx1, cx2, waveN, sN, amdqN, apdqN, roeN);
       }
       if (col_ok && (J + 2 >= 2) && (J + 2 <= P.my + 2)) {
         cfl = cfl_update<W>(cfl, dtdy, sN);
@@ -608,6 +640,8 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__
     }
 #pragma unroll
     for (int m = 0; m < M; ++m) { qx0[m] = qx1[m]; qx1[m] = qx2[m]; }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) cx1[k] = cx2[k];
   }
   block_max_cfl<NT>(cfl, P.cfl_bits, sred);
 }

@@ -1,0 +1,256 @@
+// Warp-synchronous variant of the fused unsplit 2-D sweep (same algorithm, same accumulation order and therefore
+// the same bits as sweep2_unsplit in sweep2.cuh; see the header comment there for the march).
+//
+// Why: ncu on sweep2_unsplit<RpEuler4Wave2D,64,6> shows the LSU data pipe 65 % busy (shared-memory exchange of
+// neighbouring interfaces: 177 eight-byte accesses per cell-step = 2 wavefronts each, plus register spills) next
+// to an FP64 pipe that is 53 % busy: the kernel is co-limited by shared-memory wavefronts, not by arithmetic
+// alone.  Here every warp owns its own strip (32 columns, 28 owned + 2 halo columns per side) and exchanges the
+// x-neighbour data with warp shuffles -- one SHFL moves what a STS + LDS pair moved -- so the march loop has no
+// __syncthreads and shared memory only holds the thread-private pending y-interface (waves, fluctuations, Roe
+// data, limiter dot products) that must survive one march step.
+#pragma once
+#include "sweep2.cuh"
+
+namespace clawcuda {
+namespace CLAW_NS {
+
+__device__ __forceinline__ double shfl_left(double v) {          // value of lane-1 (lane 0: its own)
+  return __shfl_up_sync(0xffffffffu, v, 1);
+}
+__device__ __forceinline__ double shfl_right(double v) {         // value of lane+1 (lane 31: its own)
+  return __shfl_down_sync(0xffffffffu, v, 1);
+}
+
+template <class RP, int NW> struct Smem2ws {
+  static constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE;
+  static constexpr int OFF_YW = 0;                  // [W*M]   waves of the pending y-interface
+  static constexpr int OFF_YA = OFF_YW + W * M;     // [2M+NR+W] amdq, apdq, roe, dotl
+  static constexpr int PER_THREAD = OFF_YA + 2 * M + NR + W;
+  static constexpr size_t BYTES = (size_t)PER_THREAD * NW * 32 * sizeof(double) + 64 * sizeof(double);
+};
+
+template <class RP, int NW, int MINB = 1, int SPEC = 0>
+__global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_constant__ Sweep2Params P) {
+  constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE, NT = NW * 32;
+  constexpr bool SP = (SPEC & 1) != 0;
+  constexpr int LIM = SP ? (SPEC >> 4) : 0;
+  constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
+  using S = Smem2ws<RP, NW>;
+  constexpr int TX = 28;                                   // owned columns per warp
+  extern __shared__ double smem[];
+  const int t = threadIdx.x, lane = t & 31;
+  double* const syw = smem + S::OFF_YW * NT + t;
+  double* const sya = smem + S::OFF_YA * NT + t;
+  double* const sred = smem + S::PER_THREAD * NT;
+
+  const int nx = P.mx + 4;
+  const int I = (blockIdx.x * NW + (t >> 5)) * TX + lane;  // my column (array coords)
+  const int Ic = I < nx ? I : nx - 1;                      // clamped for loads
+  const int Jb = P.j0 + blockIdx.y * P.seg_rows;           // first output row
+  const int Je = min(Jb + P.seg_rows, P.j1);               // one past the last output row
+
+  const double dtdx = P.dtdx, dtdy = P.dtdy;
+  const double hdx = 0.5 * dtdx, hdy = 0.5 * dtdy;
+  const bool second = SP ? true : (P.order != 1);
+  const bool limit = SP ? true : (second && (P.limit != 0));
+  const int mt = SP ? 2 : P.mtrans;
+
+  const double* qcol = P.qin + Ic;
+  double q1[M], qn0[M], qn1[M], c1[NC1];
+  double yI_apdq[M], yI_fadd[M], yI_bm[M], yI_bp[M];      // finished y-interface J (rotated frame)
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    q1[m] = qcol[m * P.plane + (long long)(Jb - 2) * P.pitch];
+    qn0[m] = 0.0; qn1[m] = 0.0; yI_apdq[m] = 0.0; yI_fadd[m] = 0.0; yI_bm[m] = 0.0; yI_bp[m] = 0.0;
+  }
+  if constexpr (NC > 0) RP::cell(P.rp, q1, c1);
+  double cfl = 0.0;
+  const bool x_cfl_col = (lane >= 1) && (I >= 2) && (I <= P.mx + 2);
+  const bool y_cfl_col = (I >= 1) && (I <= P.mx + 2);
+  const bool store_col = (lane >= 2) && (lane <= 29) && (I <= P.mx + 1);
+
+  // warm-up rows: see sweep2_unsplit (the specialised kernel runs the full body from the first step)
+  for (int J = Jb - 3; J < Je; ++J) {
+    double qN[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) qN[m] = qcol[m * P.plane + (long long)(J + 2) * P.pitch];
+    double cN[NC1];
+    if constexpr (NC > 0) RP::cell(P.rp, qN, cN);
+
+    // =========================== y-pipeline ==========================================
+    double ycomb[M], gy1[M], gy2[M];                       // natural frame
+#pragma unroll
+    for (int m = 0; m < M; ++m) { ycomb[m] = 0.0; gy1[m] = 0.0; gy2[m] = 0.0; }
+    {
+      double waveN[W][M], sN[W], amdqN[M], apdqN[M], roeN[NR];
+      {
+        double ql[M], qr[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) { ql[m] = q1[rot<M>(m)]; qr[m] = qN[rot<M>(m)]; }
+        RP::normal(P.rp, 1, ql, qr, c1, cN, waveN, sN, amdqN, apdqN, roeN);
+      }
+      if (y_cfl_col && (J + 2 >= 2) && (J + 2 <= P.my + 2)) {             // flux2.f90:111-119
+        cfl = cfl_update<W>(cfl, dtdy, sN);
+      }
+      double dotn[W];
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw) dotn[mw] = 0.0;
+      if (SP || J >= Jb - 2) {
+        double waveC[W][M], wnorm2[W];
+#pragma unroll
+        for (int mw = 0; mw < W; ++mw) {
+          wnorm2[mw] = 0.0;
+#pragma unroll
+          for (int m = 0; m < M; ++m) waveC[mw][m] = syw[(mw * M + m) * NT];
+        }
+        if (limit) wave_dots<RP, true>(waveC, waveN, wnorm2, dotn);
+        if (SP || J >= Jb - 1) {
+          double sC[W], amdqC[M], apdqC[M], roeC[NR], dotl[W];
+#pragma unroll
+          for (int m = 0; m < M; ++m) { amdqC[m] = sya[m * NT]; apdqC[m] = sya[(M + m) * NT]; }
+#pragma unroll
+          for (int k = 0; k < NR; ++k) roeC[k] = sya[(2 * M + k) * NT];
+#pragma unroll
+          for (int mw = 0; mw < W; ++mw) dotl[mw] = sya[(2 * M + NR + mw) * NT];
+          RP::speeds(P.rp, 1, roeC, sC);
+          // first-order increment of cell J uses the ORIGINAL fluctuations (flux2.f90:105-108)
+          double qadd[M];
+#pragma unroll
+          for (int m = 0; m < M; ++m) {
+            qadd[m] = (0.0 - dtdy * yI_apdq[m]) - dtdy * amdqC[m];
+            yI_apdq[m] = apdqC[m];                                         // carry: original apdq of interface J+1
+          }
+          double fadd[M];
+#pragma unroll
+          for (int m = 0; m < M; ++m) fadd[m] = 0.0;
+          if (second) {
+            if (limit) limit_waves<RP, LIM>(P, waveC, sC, wnorm2, dotl, dotn);
+            double cqxx[M];
+            second_order<RP>(dtdy, waveC, sC, cqxx);
+#pragma unroll
+            for (int m = 0; m < M; ++m) fadd[m] = 0.0 + 0.5 * cqxx[m];
+            if (mt == 2) {                                                 // flux2.f90:167-173
+#pragma unroll
+              for (int m = 0; m < M; ++m) { amdqC[m] = amdqC[m] + cqxx[m]; apdqC[m] = apdqC[m] - cqxx[m]; }
+            }
+          }
+          double bmA[M], bpA[M], bmP[M], bpP[M];
+#pragma unroll
+          for (int m = 0; m < M; ++m) { bmA[m] = 0.0; bpA[m] = 0.0; bmP[m] = 0.0; bpP[m] = 0.0; }
+          if (mt > 0) {
+            RP::transverse(P.rp, 1, roeC, amdqC, bmA, bpA);               // flux2.f90:181
+            RP::transverse(P.rp, 1, roeC, apdqC, bmP, bpP);               // flux2.f90:194
+          }
+          // cell J of this y-pencil: interface J (carried) and interface J+1 (just finished)
+#pragma unroll
+          for (int m = 0; m < M; ++m) {
+            const double g1 = (0.0 - hdy * bmA[m]) - hdy * yI_bm[m];      // flux2.f90:185-203
+            const double g2 = (0.0 - hdy * bpA[m]) - hdy * yI_bp[m];
+            // step2.f90:223-225: qadd - dtdy*(fadd(j+1)-fadd(j)) - dtdx*(gadd(2)-gadd(1))
+            ycomb[rot<M>(m)] = (qadd[m] - dtdy * (fadd[m] - yI_fadd[m])) - dtdx * (g2 - g1);
+            gy1[rot<M>(m)] = g1;
+            gy2[rot<M>(m)] = g2;
+            yI_fadd[m] = fadd[m]; yI_bm[m] = bmP[m]; yI_bp[m] = bpP[m];
+          }
+        }
+      }
+      // the new interface becomes the pending one
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw)
+#pragma unroll
+        for (int m = 0; m < M; ++m) syw[(mw * M + m) * NT] = waveN[mw][m];
+#pragma unroll
+      for (int m = 0; m < M; ++m) { sya[m * NT] = amdqN[m]; sya[(M + m) * NT] = apdqN[m]; }
+#pragma unroll
+      for (int k = 0; k < NR; ++k) sya[(2 * M + k) * NT] = roeN[k];
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw) sya[(2 * M + NR + mw) * NT] = dotn[mw];
+    }
+
+    // =========================== x-pipeline on row J+1 ===============================
+    double qn2[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) qn2[m] = qN[m];
+    if (SP || J >= Jb - 2) {
+      double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
+      {
+        double ql[M], cl[NC1];
+#pragma unroll
+        for (int m = 0; m < M; ++m) ql[m] = shfl_left(q1[m]);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) cl[k] = shfl_left(c1[k]);
+        RP::normal(P.rp, 0, ql, q1, cl, c1, wave, s, amdq, apdq, roe);    // flux2.f90:101
+      }
+#pragma unroll
+      for (int m = 0; m < M; ++m) { cqxx[m] = 0.0; fadd[m] = 0.0; }
+      if (second) {
+        if (limit) {                                                       // flux2.f90:127
+          double wnorm2[W], dotr[W], dotl[W];
+          {
+            double waveR[W][M];
+#pragma unroll
+            for (int mw = 0; mw < W; ++mw)
+#pragma unroll
+              for (int m = 0; m < M; ++m) waveR[mw][m] = shfl_right(wave[mw][m]);
+            wave_dots<RP, false>(wave, waveR, wnorm2, dotr);
+          }
+#pragma unroll
+          for (int mw = 0; mw < W; ++mw) dotl[mw] = shfl_left(dotr[mw]);
+          limit_waves<RP, LIM>(P, wave, s, wnorm2, dotl, dotr);
+        }
+        second_order<RP>(dtdx, wave, s, cqxx);                             // flux2.f90:134-146
+#pragma unroll
+        for (int m = 0; m < M; ++m) fadd[m] = 0.0 + 0.5 * cqxx[m];
+      }
+      if (x_cfl_col && (J + 1 >= 1) && (J + 1 <= P.my + 2)) {             // flux2.f90:111-119
+        cfl = cfl_update<W>(cfl, dtdx, s);
+      }
+      double bmA[M], bpA[M], bmP[M], bpP[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) { bmA[m] = 0.0; bpA[m] = 0.0; bmP[m] = 0.0; bpP[m] = 0.0; }
+      if (mt > 0) {
+        double tm[M], tp[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) { tm[m] = amdq[m]; tp[m] = apdq[m]; }
+        if (second && mt == 2) {                                           // flux2.f90:167-173
+#pragma unroll
+          for (int m = 0; m < M; ++m) { tm[m] = tm[m] + cqxx[m]; tp[m] = tp[m] - cqxx[m]; }
+        }
+        RP::transverse(P.rp, 0, roe, tm, bmA, bpA);                        // flux2.f90:181
+        RP::transverse(P.rp, 0, roe, tp, bmP, bpP);                        // flux2.f90:194
+      }
+      // my left-face results belong to the cell on my left: fetch the right neighbour's
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const double amdqR = shfl_right(amdq[m]), faddR = shfl_right(fadd[m]);
+        const double bmAR = shfl_right(bmA[m]), bpAR = shfl_right(bpA[m]);
+        const double qadd = (0.0 - dtdx * apdq[m]) - dtdx * amdqR;         // flux2.f90:105-108
+        const double g1 = (0.0 - hdx * bmAR) - hdx * bmP[m];              // flux2.f90:185-203
+        const double g2 = (0.0 - hdx * bpAR) - hdx * bpP[m];
+        // step2.f90:139-147, pencil J+1: rows J, J+1, J+2
+        qn0[m] = qn0[m] - dtdy * g1;
+        qn1[m] = ((qn1[m] + qadd) - dtdx * (faddR - fadd[m])) - dtdy * (g2 - g1);
+        qn2[m] = qN[m] + dtdy * g2;
+      }
+    }
+
+    // =========================== cell (I, J) is complete =============================
+    // (the shuffles are executed by the whole warp on every step; only the stores are guarded)
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      // step2.f90:221-229, columns I-1, I, I+1
+      double r = qn0[m] + dtdx * shfl_left(gy2[m]);
+      r = r + ycomb[m];
+      r = r - dtdx * shfl_right(gy1[m]);
+      if (store_col && J >= Jb) P.qout[m * P.plane + (long long)J * P.pitch + I] = r;
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) { qn0[m] = qn1[m]; qn1[m] = qn2[m]; q1[m] = qN[m]; }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) c1[k] = cN[k];
+  }
+  block_max_cfl<NT>(cfl, P.cfl_bits, sred);
+}
+
+}  // namespace CLAW_NS
+}  // namespace clawcuda

@@ -3,20 +3,23 @@
 //   -DCLAW_NS=fast   -fmad=true                      FMA contraction allowed
 #include <cstdlib>
 #include "launch.h"
+#include "sweep2_ws.cuh"
+#include "sweep2_aux.cuh"
+#include "rp2_aux.cuh"
 
 namespace clawcuda {
 namespace CLAW_NS {
 
 template <class KERN>
 static cudaError_t launch_kernel(KERN kern, int NT, int smem, bool x_only, Sweep2Params& P, int seg_hint, int num_sms,
-                                 cudaStream_t st, LaunchInfo* info) {
+                                 cudaStream_t st, LaunchInfo* info, int cols_per_cta = 0) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int occ = 1;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
   if (e != cudaSuccess) return e;
   if (occ < 1) occ = 1;
-  const int TX = NT - 4;
+  const int TX = cols_per_cta > 0 ? cols_per_cta : NT - 4;
   const int strips = (P.mx + TX - 1) / TX;
   if (P.j1 <= P.j0) {                         // default: the whole grid
     P.j0 = x_only ? 0 : 2;
@@ -57,6 +60,23 @@ static cudaError_t launch_spec(Sweep2Params& P, int seg_hint, int num_sms, cudaS
   return launch_kernel(sweep2_unsplit<RP, NT, MINB, SPEC>, NT, (int)S::BYTES, false, P, seg_hint, num_sms, st, info);
 }
 
+// warp-synchronous unsplit kernel (sweep2_ws.cuh): NW independent 28-column strips per CTA
+template <class RP, int NW, int MINB, int SPEC>
+static cudaError_t launch_ws(Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
+  using S = Smem2ws<RP, NW>;
+  return launch_kernel(sweep2_unsplit_ws<RP, NW, MINB, SPEC>, NW * 32, (int)S::BYTES, false, P, seg_hint, num_sms, st,
+                       info, NW * 28);
+}
+
+// aux-reading solvers (sweep2_aux.cuh): warp-synchronous, NW strips per CTA
+template <class RP, int NW>
+static cudaError_t launch_aux(int kind, Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
+  using S = Smem2aux<RP, NW>;
+  if (kind == 0)
+    return launch_kernel(sweep2_unsplit_aux<RP, NW>, NW * 32, (int)S::BYTES, false, P, seg_hint, num_sms, st, info, NW * 28);
+  return launch_kernel(sweep2_split_aux<RP, NW>, NW * 32, (int)S::BYTES, !P.do_y, P, seg_hint, num_sms, st, info, NW * 28);
+}
+
 // order 2, transverse mode 2, every wave family limited with limiter id `lim`
 template <int W> static bool headline_method(const Sweep2Params& P, int lim) {
   if (P.order == 1 || P.mtrans != 2 || !P.limit) return false;
@@ -74,17 +94,14 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
       if (kind == 0 && headline_method<4>(P, 4)) {
         constexpr int MC = 4 << 4;
         switch (variant) {
-          case 0: return launch_spec<RpEuler4Wave2D, 64, 6, MC | 1>(P, seg_hint, num_sms, st, info);
-          case 1: return launch_spec<RpEuler4Wave2D, 64, 6, MC | 3>(P, seg_hint, num_sms, st, info);
-          case 2: return launch_spec<RpEuler4Wave2D, 64, 7, MC | 1>(P, seg_hint, num_sms, st, info);
-          case 3: return launch_spec<RpEuler4Wave2D, 64, 8, MC | 1>(P, seg_hint, num_sms, st, info);
-          case 4: return launch_spec<RpEuler4Wave2D, 64, 5, MC | 3>(P, seg_hint, num_sms, st, info);
-          case 5: return launch_spec<RpEuler4Wave2D, 96, 4, MC | 1>(P, seg_hint, num_sms, st, info);
-          case 6: return launch_spec<RpEuler4Wave2D, 128, 3, MC | 1>(P, seg_hint, num_sms, st, info);
-          case 7: return launch_spec<RpEuler4Wave2D, 64, 8, MC | 3>(P, seg_hint, num_sms, st, info);
+          case 0: return launch_ws<RpEuler4Wave2D, 1, 12, MC | 1>(P, seg_hint, num_sms, st, info);    // fastest measured
+          case 15: return launch_spec<RpEuler4Wave2D, 64, 6, MC | 1>(P, seg_hint, num_sms, st, info);
+          case 8: return launch_spec<RpEuler4Wave2D, 64, 4, MC | 1>(P, seg_hint, num_sms, st, info);
+          case 10: return launch_ws<RpEuler4Wave2D, 2, 6, MC | 1>(P, seg_hint, num_sms, st, info);
           default: break;     // 9: the generic kernel
         }
       }
+      if (kind == 0 && variant == 20) return launch_ws<RpEuler4Wave2D, 2, 6, 0>(P, seg_hint, num_sms, st, info);
       if (kind == 0) return launch_one<RpEuler4Wave2D, 64, 6>(kind, P, seg_hint, num_sms, st, info);
       return launch_one<RpEuler4Wave2D, 128>(kind, P, seg_hint, num_sms, st, info);
     }
@@ -97,6 +114,8 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
       if (variant == 6) return launch_one<RpShallowRoeEfix2D, 64, 8>(kind, P, seg_hint, num_sms, st, info);
       return launch_one<RpShallowRoeEfix2D, 128>(kind, P, seg_hint, num_sms, st, info);
     }
+    case 7: return launch_aux<RpVcAcoustics2D, 2>(kind, P, seg_hint, num_sms, st, info);
+    case 8: return launch_aux<RpVcAdvection2D, 2>(kind, P, seg_hint, num_sms, st, info);
   }
   return cudaErrorInvalidValue;
 }

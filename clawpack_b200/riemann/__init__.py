@@ -13,6 +13,8 @@ _SOLVERS = {
     'shallow_roe_with_efix_2D': (4, ('grav',), 2),            # rpn2_shallow_roe_with_efix.f90:59
     'vc_acoustics_3D': (5, (), 3),                            # rpn3_vc_acoustics.f90 (no common block)
     'euler_3D': (6, ('gamma',), 3),                           # rpn3_euler.f90 / rpt3_euler.f90 / rptt3_euler.f90
+    'vc_acoustics_2D': (7, (), 2),                            # rpn2_vc_acoustics.f90 (coefficients in aux)
+    'vc_advection_2D': (8, (), 2),                            # rpn2_vc_advection.f90 (edge velocities in aux)
 }
 
 for _name, (_id, _cp, _nd) in _SOLVERS.items():
@@ -22,4 +24,4 @@ for _name, (_id, _cp, _nd) in _SOLVERS.items():
 
 from . import acoustics_2D_constants, advection_2D_constants, euler_4wave_2D_constants  # noqa: E402,F401
 from . import shallow_roe_with_efix_2D_constants, vc_acoustics_3D_constants             # noqa: E402,F401
-from . import euler_3D_constants                                                        # noqa: E402,F401
+from . import euler_3D_constants, vc_acoustics_2D_constants, vc_advection_2D_constants   # noqa: E402,F401

@@ -70,6 +70,27 @@ def acoustics_2d(mx=100, my=100, tfinal=0.12, num_output_times=10):
                  num_output_times=num_output_times)
 
 
+def acoustics_2d_variable(mx=50, my=50, tfinal=0.6, num_output_times=20, dimensional_split=False,
+                          transverse_waves=1):
+    """pyclaw/examples/acoustics_2d_variable/acoustics_2d_interface.py:22-101 (classic branch): two materials,
+    aux = (density, sound speed), wall / extrap, unsplit with the default transverse_waves = trans_inc
+    (classic/solver.py:446), MC."""
+    X, Y = _grid((-1., -1.), (1., 1.), (mx, my))
+    rho_left, rho_right, bulk_left, bulk_right = 4.0, 1.0, 4.0, 4.0
+    c_left, c_right = np.sqrt(bulk_left / rho_left), np.sqrt(bulk_right / rho_right)
+    aux = np.empty((2, mx, my), order='F')
+    aux[0] = rho_left * (X < 0.) + rho_right * (X >= 0.)
+    aux[1] = c_left * (X < 0.) + c_right * (X >= 0.)
+    r = np.sqrt((X + 0.5) ** 2 + Y ** 2)
+    width, rad = 0.1, 0.25
+    q = np.zeros((3, mx, my), order='F')
+    q[0] = (np.abs(r - rad) <= width) * (1. + np.cos(np.pi * (r - rad) / width))
+    return _base('vc_acoustics_2D', (-1., -1.), (1., 1.), (mx, my), q, aux=aux, limiters=MC,
+                 dimensional_split=bool(dimensional_split), transverse_waves=transverse_waves,
+                 bc_lower=[WALL, WALL], bc_upper=[EXTRAP, EXTRAP], aux_bc_lower=[WALL, WALL],
+                 aux_bc_upper=[EXTRAP, EXTRAP], tfinal=tfinal, num_output_times=num_output_times)
+
+
 def quadrants(mx=100, my=100, tfinal=0.8):
     xx, yy = _grid((0., 0.), (1., 1.), (mx, my))
     gamma = 1.4

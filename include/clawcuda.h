@@ -45,7 +45,9 @@ enum {
   CLAW_RP_EULER_4WAVE_2D = 3,          /* rpn2_euler_4wave.f90, rpt2_euler.f90 */
   CLAW_RP_SHALLOW_ROE_EFIX_2D = 4,     /* rpn2_shallow_roe_with_efix.f90, rpt2_shallow_roe_with_efix.f90 */
   CLAW_RP_VC_ACOUSTICS_3D = 5,         /* rpn3_vc_acoustics.f90, rpt3_vc_acoustics.f90, rptt3_vc_acoustics.f90 */
-  CLAW_RP_EULER_3D = 6                 /* rpn3_euler.f90, rpt3_euler.f90, rptt3_euler.f90 */
+  CLAW_RP_EULER_3D = 6,                /* rpn3_euler.f90, rpt3_euler.f90, rptt3_euler.f90 */
+  CLAW_RP_VC_ACOUSTICS_2D = 7,         /* rpn2_vc_acoustics.f90, rpt2_vc_acoustics.f90 (aux: density, sound speed) */
+  CLAW_RP_VC_ADVECTION_2D = 8          /* rpn2_vc_advection.f90, rpt2_vc_advection.f90 (aux: edge velocities) */
 };
 
 /* Boundary-condition ids = pyclaw.BC (pyclaw/src/pyclaw/solver.py:13-19) */

@@ -67,6 +67,7 @@ enum RpId {
   RP_EULER_4WAVE_2D = 3,
   RP_SHALLOW_ROE_EFIX_2D = 4,
   RP_VC_ACOUSTICS_3D = 5,
+  RP_VC_ACOUSTICS_2D = 7,       // (6 = euler_3D, clawref3.hpp)
 };
 
 // =====================================================================
@@ -516,12 +517,67 @@ void rpt2_shallow_roe_efix(int ixy, int, int maxm, int meqn, int mwaves, int, in
   }
 }
 
+// =====================================================================
+// vc_acoustics_2D -- riemann/src/rpn2_vc_acoustics.f90:40-97, rpt2_vc_acoustics.f90:27-80
+// aux(1) = density, aux(2) = sound speed; no common block
+// =====================================================================
+template <class R>
+void rpn2_vc_acoustics(int ixy, int, int meqn, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R> auxl, V2<R> auxr,
+                       V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double*) {
+  int mu, mv;
+  if (ixy == 1) { mu = 2; mv = 3; } else { mu = 3; mv = 2; }   // rpn2_vc_acoustics.f90:62-68
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {                   // loop 20, :73-91
+    R delta1 = ql(1, i) - qr(1, i - 1);
+    R delta2 = ql(mu, i) - qr(mu, i - 1);
+    R zi = auxl(1, i) * auxl(2, i);
+    R zim = auxr(1, i - 1) * auxr(2, i - 1);
+    R a1 = (-delta1 + zi * delta2) / (zim + zi);
+    R a2 = (delta1 + zim * delta2) / (zim + zi);
+    wave(1, 1, i) = -a1 * zim;
+    wave(mu, 1, i) = a1;
+    wave(mv, 1, i) = R(0.0);
+    s(1, i) = -auxr(2, i - 1);
+    wave(1, 2, i) = a2 * zi;
+    wave(mu, 2, i) = a2;
+    wave(mv, 2, i) = R(0.0);
+    s(2, i) = auxl(2, i);
+  }
+  for (int m = 1; m <= meqn; ++m)                               // :96-101
+    for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+      amdq(m, i) = s(1, i) * wave(m, 1, i);
+      apdq(m, i) = s(2, i) * wave(m, 2, i);
+    }
+}
+template <class R>
+void rpt2_vc_acoustics(int ixy, int imp, int, int, int, int, int mbc, int mx, V2<R>, V2<R>, V2<R> aux1, V2<R> aux2,
+                       V2<R> aux3, V2<R> asdq, V2<R> bmasdq, V2<R> bpasdq, const double*) {
+  int mu, mv;
+  if (ixy == 1) { mu = 2; mv = 3; } else { mu = 3; mv = 2; }   // rpt2_vc_acoustics.f90:27-33
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {                   // loop 20, :36-77
+    const int i1 = (imp == 1) ? i - 1 : i;                      // :41-45
+    R cm = aux1(2, i1), c = aux2(2, i1), cp = aux3(2, i1);
+    (void)c;
+    R zm = aux1(1, i1) * aux1(2, i1);
+    R zz = aux2(1, i1) * aux2(2, i1);
+    R zp = aux3(1, i1) * aux3(2, i1);
+    R a1 = (-asdq(1, i) + asdq(mv, i) * zz) / (zm + zz);        // :58-59
+    R a2 = (asdq(1, i) + asdq(mv, i) * zz) / (zz + zp);         // :61-62
+    bmasdq(1, i) = cm * a1 * zm;                                // :66-68
+    bmasdq(mu, i) = R(0.0);
+    bmasdq(mv, i) = -cm * a1;
+    bpasdq(1, i) = cp * a2 * zp;                                // :72-74
+    bpasdq(mu, i) = R(0.0);
+    bpasdq(mv, i) = cp * a2;
+  }
+}
+
 template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt) {
   switch (rp_id) {
     case RP_ADVECTION_2D: rpn = rpn2_advection<R>; rpt = rpt2_advection<R>; return true;
     case RP_ACOUSTICS_2D: rpn = rpn2_acoustics<R>; rpt = rpt2_acoustics<R>; return true;
     case RP_EULER_4WAVE_2D: rpn = rpn2_euler_4wave<R>; rpt = rpt2_euler<R>; return true;
     case RP_SHALLOW_ROE_EFIX_2D: rpn = rpn2_shallow_roe_efix<R>; rpt = rpt2_shallow_roe_efix<R>; return true;
+    case RP_VC_ACOUSTICS_2D: rpn = rpn2_vc_acoustics<R>; rpt = rpt2_vc_acoustics<R>; return true;
   }
   return false;
 }

@@ -25,6 +25,7 @@ RP_IDS = {
     'shallow_roe_with_efix_2D': 4,
     'vc_acoustics_3D': 5,
     'euler_3D': 6,
+    'vc_acoustics_2D': 7,
 }
 # COMMON /cparam/ member order of each solver (rpn2_advection.f90, rpn2_acoustics.f90:52,
 # rpn2_euler_4wave.f90:71, rpn2_shallow_roe_with_efix.f90:59; vc_acoustics_3D has none)
@@ -35,11 +36,12 @@ CPARAM_NAMES = {
     'shallow_roe_with_efix_2D': ('grav',),
     'vc_acoustics_3D': (),
     'euler_3D': ('gamma',),           # rpn3_euler.f90: COMMON /cparam/ gamma
+    'vc_acoustics_2D': (),            # rpn2_vc_acoustics.f90: coefficients live in aux
 }
 NUM_EQN = {'advection_2D': 1, 'acoustics_2D': 3, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
-           'vc_acoustics_3D': 4, 'euler_3D': 5}
+           'vc_acoustics_3D': 4, 'euler_3D': 5, 'vc_acoustics_2D': 3}
 NUM_WAVES = {'advection_2D': 1, 'acoustics_2D': 2, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
-             'vc_acoustics_3D': 2, 'euler_3D': 3}
+             'vc_acoustics_3D': 2, 'euler_3D': 3, 'vc_acoustics_2D': 2}
 
 BC_CUSTOM, BC_EXTRAP, BC_PERIODIC, BC_WALL = 0, 1, 2, 3
 

@@ -1,0 +1,75 @@
+"""GPU parity tests for the 2-D solvers that read aux arrays, capacity functions and f-waves
+(csrc/sweep2_aux.cuh, rp2_aux.cuh) against the oracle, through the C ABI.  Same bars as test_cuda_parity.py:
+bit-exact in 'strict' arithmetic, 1e-12 / 1e-10 relative L-inf in 'fast', identical step logs."""
+import os
+
+import numpy as np
+import pytest
+
+from clawpack_b200 import scenarios as S
+from refutil import ROOT, ref_solver
+from test_cuda_parity import _rel_linf, _run_cuda, _run_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def goldens2():
+    return np.load(os.path.join(ROOT, 'tests', 'golden', 'reference_goldens2.npz'))
+
+
+CASES = {
+    'vcac_unsplit_inc': lambda: S.acoustics_2d_variable(),
+    'vcac_unsplit_cor': lambda: S.acoustics_2d_variable(mx=64, my=37, transverse_waves=2),
+    'vcac_unsplit_notrans': lambda: dict(S.acoustics_2d_variable(mx=31, my=58, transverse_waves=0), cfl_max=0.5,
+                                         cfl_desired=0.45),
+    'vcac_split': lambda: S.acoustics_2d_variable(mx=57, my=40, dimensional_split=True),
+    'vcac_first_order': lambda: dict(S.acoustics_2d_variable(mx=40, my=40), order=1),
+    'vcac_superbee_periodic': lambda: dict(S.acoustics_2d_variable(mx=45, my=30, transverse_waves=2),
+                                           limiters=[S.SUPERBEE, S.VANLEER], bc_lower=[S.PERIODIC, S.WALL],
+                                           bc_upper=[S.PERIODIC, S.EXTRAP], aux_bc_lower=[S.PERIODIC, S.WALL],
+                                           aux_bc_upper=[S.PERIODIC, S.EXTRAP]),
+    'vcac_tiny': lambda: S.acoustics_2d_variable(mx=3, my=2, transverse_waves=2),
+    'vcac_strip_edges': lambda: S.acoustics_2d_variable(mx=57, my=5, transverse_waves=2),   # 2 warps + 1 column
+}
+for _k, _f in list(S.AUX_CASES.items()) if hasattr(S, 'AUX_CASES') else []:
+    CASES[_k] = _f
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_strict_bit_exact_vs_oracle(name):
+    sc = CASES[name]()
+    q, log, _ = _run_cuda(sc, 6, 'strict')
+    qr, logr = _run_ref(sc, 6)
+    assert log == logr, 'dt / CFL sequence differs: %r vs %r' % (log[:3], logr[:3])
+    assert np.array_equal(q, qr), 'max abs diff %g' % np.max(np.abs(q - qr))
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_fast_within_tolerance(name):
+    sc = CASES[name]()
+    q, log, _ = _run_cuda(sc, 2, 'fast')
+    qr, logr = _run_ref(sc, 2)
+    assert [s[2] for s in log] == [s[2] for s in logr]
+    assert _rel_linf(q, qr) <= 1e-12
+
+
+@pytest.mark.parametrize('name', ['vcac_unsplit_inc', 'vcac_split'])
+def test_100_steps(name):
+    sc = CASES[name]()
+    qr, logr = _run_ref(sc, 101)
+    for precision, tol in (('strict', 0.0), ('fast', 1e-10)):
+        q, log, _ = _run_cuda(sc, 101, precision)
+        assert [s[2] for s in log] == [s[2] for s in logr], 'accept/reject sequence differs (%s)' % precision
+        assert _rel_linf(q, qr) <= tol, (precision, _rel_linf(q, qr))
+
+
+@pytest.mark.parametrize('precision', ['strict', 'fast'])
+def test_acoustics_2d_variable_golden(precision):
+    """pyclaw/examples/acoustics_2d_variable/test_acoustics_2d_variable.py:8-23 (classic, 50x50): max-abs < 1e-1 there;
+    the CUDA path reproduces the stored vector to round-off."""
+    sc = S.acoustics_2d_variable()
+    claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision=precision)
+    claw.run()
+    p = claw.frames[claw.num_output_times].state.get_q_global()[0]
+    expected = goldens2()['acoustics_2d_variable__pressure_classic']
+    assert np.max(np.abs(p.reshape(-1) - expected.reshape(-1))) < 1e-12

@@ -160,3 +160,19 @@ def test_op_counts(oracle_lib):
     assert 900 < ops['add'] + ops['mul'] < 1400
     assert 30 < ops['div'] < 70 and 6 < ops['sqrt'] < 16
     assert ops['repeated']['div'] > 30          # the reference redoes the Roe averages in both rpt2 calls
+
+
+def goldens2():
+    import os
+    from refutil import ROOT
+    return np.load(os.path.join(ROOT, 'tests', 'golden', 'reference_goldens2.npz'))
+
+
+def test_acoustics_2d_variable_golden(oracle_lib):
+    # pyclaw/examples/acoustics_2d_variable/test_acoustics_2d_variable.py:8-23 (max-abs < 1e-1): pins step2 unsplit
+    # with aux1/aux2/aux3 pencils + rpn2_vc_acoustics / rpt2_vc_acoustics (default transverse_waves = trans_inc)
+    sc = S.acoustics_2d_variable()
+    s = ref_solver(sc)
+    s.run(sc['tfinal'], sc['num_output_times'])
+    g = goldens2()['acoustics_2d_variable__pressure_classic']
+    assert np.max(np.abs(s.q[0].reshape(-1) - g.reshape(-1))) < 1e-13
