@@ -323,7 +323,10 @@ int get_all(claw_solver* h, const double* dsoa, int ncomp, double* host) {
 int fill_ghosts_array(claw_solver* h, double* arr, int ncomp, const int* lo, const int* up, bool is_q) {
   const Dev2& g = h->g;
   for (int d = 0; d < g.ndim; ++d) {
-    if ((h->on_lower[d] && (lo[d] < 1 || lo[d] > 3)) || (h->on_upper[d] && (up[d] < 1 || up[d] > 3)))
+    // BC.custom (0) on an AUX face is allowed: the host filled those ghost cells once (claw_put_auxbc) and the
+    // kernels below leave type 0 untouched; on q it needs a host round trip every step
+    const int tmin = is_q ? 1 : 0;
+    if ((h->on_lower[d] && (lo[d] < tmin || lo[d] > 3)) || (h->on_upper[d] && (up[d] < tmin || up[d] > 3)))
       return fail(h, 21, "boundary condition %d/%d in dimension %d cannot run on the device "
                          "(BC.custom needs a host round trip)", lo[d], up[d], d);
   }

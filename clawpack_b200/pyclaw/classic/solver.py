@@ -100,7 +100,9 @@ class ClawSolver(Solver):
         from ..solver import BC
         if self.fmod is not None or self.before_step is not None or self.step_source is not None:
             return False
-        for lst in (self.bc_lower, self.bc_upper, self.aux_bc_lower, self.aux_bc_upper):
+        # BC.custom on q needs the host every step; BC.custom on aux alone does not: aux is static on the device
+        # path, so the user's aux ghost fill is evaluated once at setup (cuda_classic.DeviceStepper)
+        for lst in (self.bc_lower, self.bc_upper):
             if any(b == BC.custom for b in lst):
                 return False
         return True

@@ -85,8 +85,16 @@ class DeviceStepper(object):
         self.pre_step_hook = None   # e.g. the multi-GPU ghost exchange (petclaw)
         self.post_step_hook = None  # e.g. the CFL all-reduce
         if state.num_aux > 0:
-            aux = np.asfortranarray(state.aux)
-            _lib.check(L.claw_put_aux(h, aux.ctypes.data_as(ctypes.c_void_p)), h)
+            if any(b == 0 for b in list(solver.aux_bc_lower) + list(solver.aux_bc_upper)):
+                # BC.custom aux faces (e.g. edge velocities on the extended grid, examples/advection_2d_annulus):
+                # the host callbacks run ONCE here, the filled array goes to the device, and the device-side ghost
+                # fill leaves custom faces untouched (aux is static in the device-resident mode)
+                solver._allocate_bc_arrays(state)
+                auxbc = np.asfortranarray(solver.auxbc)
+                _lib.check(L.claw_put_auxbc(h, auxbc.ctypes.data_as(ctypes.c_void_p)), h)
+            else:
+                aux = np.asfortranarray(state.aux)
+                _lib.check(L.claw_put_aux(h, aux.ctypes.data_as(ctypes.c_void_p)), h)
         state._device = self
 
     # ---- coherence protocol used by State.q --------------------------------------------------

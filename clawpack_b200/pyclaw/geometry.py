@@ -182,6 +182,14 @@ class Grid(_DimensionHolder):
     def p_centers_with_ghost(self, num_ghost):
         return self.mapc2p(*self.c_centers_with_ghost(num_ghost))
 
+    def c_nodes_with_ghost(self, num_ghost):
+        ns = [d.nodes_with_ghost(num_ghost) for d in self.dimensions]
+        index = np.indices([n + 2 * num_ghost + 1 for n in self.num_cells])
+        return [c[index[i, ...]] for i, c in enumerate(ns)]
+
+    def p_nodes_with_ghost(self, num_ghost):
+        return self.mapc2p(*self.c_nodes_with_ghost(num_ghost))
+
     def __str__(self):
         return '%s-dimensional domain (%s)\n' % (self.num_dim, ','.join(self._dimensions)) + \
             '\n'.join(str(d) for d in self.dimensions)

@@ -35,7 +35,8 @@ def _base(rp, lower, upper, n, q, **kw):
              q=np.asfortranarray(q), aux=None, problem_data={}, limiters=MINMOD, order=2,
              dimensional_split=True, transverse_waves=None, cfl_max=1.0, cfl_desired=0.9,
              dt_initial=0.1, bc_lower=None, bc_upper=None, aux_bc_lower=None, aux_bc_upper=None,
-             tfinal=1.0, num_output_times=10)
+             tfinal=1.0, num_output_times=10, index_capa=-1, custom_aux_bc_lower=None, custom_aux_bc_upper=None,
+             mapc2p=None)
     d.update(kw)
     return d
 
@@ -89,6 +90,63 @@ def acoustics_2d_variable(mx=50, my=50, tfinal=0.6, num_output_times=20, dimensi
                  dimensional_split=bool(dimensional_split), transverse_waves=transverse_waves,
                  bc_lower=[WALL, WALL], bc_upper=[EXTRAP, EXTRAP], aux_bc_lower=[WALL, WALL],
                  aux_bc_upper=[EXTRAP, EXTRAP], tfinal=tfinal, num_output_times=num_output_times)
+
+
+def _nodes_with_ghost(lower, upper, n, g=2):
+    # Dimension.nodes / nodes_with_ghost (pyclaw/src/pyclaw/geometry.py:538-545, 591-597)
+    delta = (upper - lower) / float(n)
+    nodes = np.array([lower + i * delta for i in range(n + 1)])
+    pre = np.linspace(lower - g * delta, lower - delta, g)
+    post = np.linspace(upper + delta, upper + g * delta, g)
+    return np.hstack((pre, nodes, post))
+
+
+def advection_annulus(mr=40, mtheta=120, tfinal=1.0, num_output_times=10, dimensional_split=False,
+                      transverse_waves=2, order=2):
+    """pyclaw/examples/advection_2d_annulus/advection_annulus.py:22-205: colour equation on an annulus in polar
+    computational coordinates (r, theta); aux = (u at left edges, v at bottom edges, capacity = cell area ratio)
+    from the stream function pi*(x^2+y^2) (one rotation per unit time); index_capa = 2; extrap in r with
+    custom aux ghost cells (edge velocities evaluated on the extended grid), periodic in theta; van Leer."""
+    lower, upper = (0.2, 0.0), (1.0, np.pi * 2.0)
+    dx, dy = (upper[0] - lower[0]) / mr, (upper[1] - lower[1]) / mtheta
+    rn = _nodes_with_ghost(lower[0], upper[0], mr)
+    tn = _nodes_with_ghost(lower[1], upper[1], mtheta)
+    RN, TN = np.meshgrid(rn, tn, indexing='ij')          # computational nodes incl. ghost cells
+    XN, YN = RN * np.cos(TN), RN * np.sin(TN)            # mapc2p_annulus (:22-38)
+
+    def edge_data(X, Y):                                  # edge_velocities_and_area (:94-134)
+        def stream(xp, yp):
+            return np.pi * (xp ** 2 + yp ** 2)
+        x0, y0 = X[:-1, :-1], Y[:-1, :-1]
+        x1, y1 = X[:-1, 1:], Y[:-1, 1:]
+        x2, y2 = X[1:, 1:], Y[1:, 1:]
+        x3, y3 = X[1:, :-1], Y[1:, :-1]
+        a = np.empty((3,) + x0.shape, order='F')
+        a[0] = (stream(x1, y1) - stream(x0, y0)) / dy
+        a[1] = -(stream(x3, y3) - stream(x0, y0)) / dx
+        area = 1. / 2. * ((y0 + y1) * (x1 - x0) + (y1 + y2) * (x2 - x1) + (y2 + y3) * (x3 - x2) + (y3 + y0) * (x0 - x3))
+        a[2] = area / (dx * dy)
+        return a
+
+    aux = edge_data(XN[2:-2, 2:-2], YN[2:-2, 2:-2])
+
+    def aux_lower(auxbc, g):                              # ghost_velocities_lower (:78-91): all theta incl. ghosts
+        auxbc[:, 0:g, :] = edge_data(XN[0:g + 1, :], YN[0:g + 1, :])
+
+    def aux_upper(auxbc, g):                              # ghost_velocities_upper (:62-75)
+        auxbc[:, -g:, :] = edge_data(XN[-g - 1:, :], YN[-g - 1:, :])
+
+    RC, TC = _grid(lower, upper, (mr, mtheta))
+    R, Theta = RC * np.cos(TC), RC * np.sin(TC)           # p_centers (qinit uses the PHYSICAL centres, :58-60)
+    q = np.empty((1, mr, mtheta), order='F')
+    q[0] = (1. * np.exp(-40. * (np.square(R + 0.5) + np.square(Theta - 0.)))
+            + -1. * np.exp(-40. * (np.square(R - 0.5) + np.square(Theta - 0.))))
+    return _base('vc_advection_2D', lower, upper, (mr, mtheta), q, aux=aux, limiters=VANLEER, order=order,
+                 dimensional_split=bool(dimensional_split), transverse_waves=transverse_waves,
+                 cfl_max=0.5, cfl_desired=0.4, bc_lower=[EXTRAP, PERIODIC], bc_upper=[EXTRAP, PERIODIC],
+                 aux_bc_lower=[0, PERIODIC], aux_bc_upper=[0, PERIODIC], custom_aux_bc_lower=aux_lower,
+                 custom_aux_bc_upper=aux_upper, index_capa=2, tfinal=tfinal, num_output_times=num_output_times,
+                 mapc2p=lambda xc, yc: [xc * np.cos(yc), xc * np.sin(yc)])
 
 
 def quadrants(mx=100, my=100, tfinal=0.8):
@@ -268,17 +326,26 @@ def make_claw(sc, kernel_language='CUDA', pyclaw=None, **solver_kw):
     if sc.get('custom_bc_lower') is not None:           # BC.custom (solver.py:393-398): q fill of one face
         f = sc['custom_bc_lower']
         solver.user_bc_lower = lambda state, dim, t, qbc, auxbc, num_ghost: f(qbc, num_ghost)
+    if sc.get('custom_aux_bc_lower') is not None:
+        fl = sc['custom_aux_bc_lower']
+        solver.user_aux_bc_lower = lambda state, dim, t, qbc, auxbc, num_ghost: fl(auxbc, num_ghost)
+    if sc.get('custom_aux_bc_upper') is not None:
+        fu = sc['custom_aux_bc_upper']
+        solver.user_aux_bc_upper = lambda state, dim, t, qbc, auxbc, num_ghost: fu(auxbc, num_ghost)
     for k, v in solver_kw.items():
         setattr(solver, k, v)
     names = ['x', 'y', 'z'][:ndim]
     dims = [pyclaw.Dimension(lo, up, n, name=nm)
             for lo, up, n, nm in zip(sc['lower'], sc['upper'], sc['num_cells'], names)]
     domain = pyclaw.Domain(dims)
+    if sc.get('mapc2p') is not None:
+        domain.grid.mapc2p = sc['mapc2p']
     num_aux = 0 if sc['aux'] is None else sc['aux'].shape[0]
     state = pyclaw.State(domain, sc['q'].shape[0], num_aux)
     state.q[...] = sc['q']
     if num_aux:
         state.aux[...] = sc['aux']
+    state.index_capa = sc.get('index_capa', -1)
     state.problem_data.update(sc['problem_data'])
     claw = pyclaw.Controller()
     claw.tfinal = sc['tfinal']

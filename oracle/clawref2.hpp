@@ -68,6 +68,7 @@ enum RpId {
   RP_SHALLOW_ROE_EFIX_2D = 4,
   RP_VC_ACOUSTICS_3D = 5,
   RP_VC_ACOUSTICS_2D = 7,       // (6 = euler_3D, clawref3.hpp)
+  RP_VC_ADVECTION_2D = 8,
 };
 
 // =====================================================================
@@ -571,6 +572,31 @@ void rpt2_vc_acoustics(int ixy, int imp, int, int, int, int, int mbc, int mx, V2
   }
 }
 
+// =====================================================================
+// vc_advection_2D -- riemann/src/rpn2_vc_advection.f90:47-53, rpt2_vc_advection.f90:33-41
+// colour equation; aux(1) = u at the left edge, aux(2) = v at the bottom edge of each cell
+// =====================================================================
+template <class R>
+void rpn2_vc_advection(int ixy, int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R> auxl, V2<R>,
+                       V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {          // loop 30
+    wave(1, 1, i) = ql(1, i) - qr(1, i - 1);
+    s(1, i) = auxl(ixy, i);
+    amdq(1, i) = r_min(auxl(ixy, i), R(0.0)) * wave(1, 1, i);
+    apdq(1, i) = r_max(auxl(ixy, i), R(0.0)) * wave(1, 1, i);
+  }
+}
+template <class R>
+void rpt2_vc_advection(int ixy, int imp, int, int, int, int, int mbc, int mx, V2<R>, V2<R>, V2<R>, V2<R> aux2,
+                       V2<R> aux3, V2<R> asdq, V2<R> bmasdq, V2<R> bpasdq, const double*) {
+  const int kv = 3 - ixy;                               // rpt2_vc_advection.f90:33
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {           // loop 10
+    const int i1 = i - 2 + imp;
+    bmasdq(1, i) = r_min(aux2(kv, i1), R(0.0)) * asdq(1, i);
+    bpasdq(1, i) = r_max(aux3(kv, i1), R(0.0)) * asdq(1, i);
+  }
+}
+
 template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt) {
   switch (rp_id) {
     case RP_ADVECTION_2D: rpn = rpn2_advection<R>; rpt = rpt2_advection<R>; return true;
@@ -578,6 +604,7 @@ template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt)
     case RP_EULER_4WAVE_2D: rpn = rpn2_euler_4wave<R>; rpt = rpt2_euler<R>; return true;
     case RP_SHALLOW_ROE_EFIX_2D: rpn = rpn2_shallow_roe_efix<R>; rpt = rpt2_shallow_roe_efix<R>; return true;
     case RP_VC_ACOUSTICS_2D: rpn = rpn2_vc_acoustics<R>; rpt = rpt2_vc_acoustics<R>; return true;
+    case RP_VC_ADVECTION_2D: rpn = rpn2_vc_advection<R>; rpt = rpt2_vc_advection<R>; return true;
   }
   return false;
 }

@@ -26,6 +26,7 @@ RP_IDS = {
     'vc_acoustics_3D': 5,
     'euler_3D': 6,
     'vc_acoustics_2D': 7,
+    'vc_advection_2D': 8,
 }
 # COMMON /cparam/ member order of each solver (rpn2_advection.f90, rpn2_acoustics.f90:52,
 # rpn2_euler_4wave.f90:71, rpn2_shallow_roe_with_efix.f90:59; vc_acoustics_3D has none)
@@ -37,11 +38,12 @@ CPARAM_NAMES = {
     'vc_acoustics_3D': (),
     'euler_3D': ('gamma',),           # rpn3_euler.f90: COMMON /cparam/ gamma
     'vc_acoustics_2D': (),            # rpn2_vc_acoustics.f90: coefficients live in aux
+    'vc_advection_2D': (),            # rpn2_vc_advection.f90: edge velocities live in aux
 }
 NUM_EQN = {'advection_2D': 1, 'acoustics_2D': 3, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
-           'vc_acoustics_3D': 4, 'euler_3D': 5, 'vc_acoustics_2D': 3}
+           'vc_acoustics_3D': 4, 'euler_3D': 5, 'vc_acoustics_2D': 3, 'vc_advection_2D': 1}
 NUM_WAVES = {'advection_2D': 1, 'acoustics_2D': 2, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
-             'vc_acoustics_3D': 2, 'euler_3D': 3, 'vc_acoustics_2D': 2}
+             'vc_acoustics_3D': 2, 'euler_3D': 3, 'vc_acoustics_2D': 2, 'vc_advection_2D': 1}
 
 BC_CUSTOM, BC_EXTRAP, BC_PERIODIC, BC_WALL = 0, 1, 2, 3
 
@@ -173,6 +175,8 @@ class RefSolver(object):
         self.reflect_index = list(range(1, num_dim + 1))
         self.user_bc_lower = None           # f(idim, qbc, num_ghost): BC.custom fill of q (solver.py:393-398)
         self.user_bc_upper = None
+        self.user_aux_bc_lower = None       # f(idim, auxbc, num_ghost): BC.custom fill of aux
+        self.user_aux_bc_upper = None
         self.nthreads = 1
         self.cparam = np.array([float(problem_data[k]) for k in CPARAM_NAMES[rp_name]] + [0.0], dtype=np.float64)
         self.dt = self.dt_initial
@@ -225,7 +229,8 @@ class RefSolver(object):
         self._interior(self.qbc)[...] = self.q                              # state.py:257-272
         if self.num_aux > 0:
             self._interior(self.auxbc)[...] = self.aux
-            fill_ghosts(self.auxbc, self.aux_bc_lower, self.aux_bc_upper, g, is_q=False)
+            fill_ghosts(self.auxbc, self.aux_bc_lower, self.aux_bc_upper, g, is_q=False,
+                        custom_lower=self.user_aux_bc_lower, custom_upper=self.user_aux_bc_upper)
         fill_ghosts(self.qbc, self.bc_lower, self.bc_upper, g, self.reflect_index, is_q=True,
                     custom_lower=self.user_bc_lower, custom_upper=self.user_bc_upper)
 

@@ -31,6 +31,13 @@ def ref_solver(sc, nthreads=1):
     if sc.get('custom_bc_lower') is not None:
         f = sc['custom_bc_lower']
         s.user_bc_lower = lambda idim, qbc, g: f(qbc, g)
+    if sc.get('custom_aux_bc_lower') is not None:
+        fl = sc['custom_aux_bc_lower']
+        s.user_aux_bc_lower = lambda idim, auxbc, g: fl(auxbc, g)
+    if sc.get('custom_aux_bc_upper') is not None:
+        fu = sc['custom_aux_bc_upper']
+        s.user_aux_bc_upper = lambda idim, auxbc, g: fu(auxbc, g)
+    s.index_capa = sc.get('index_capa', -1)
     s.nthreads = nthreads
     delta = [(u - l) / float(n) for l, u, n in zip(sc['lower'], sc['upper'], sc['num_cells'])]
     s.setup(sc['q'], sc['aux'], delta)

@@ -31,8 +31,13 @@ CASES = {
     'vcac_tiny': lambda: S.acoustics_2d_variable(mx=3, my=2, transverse_waves=2),
     'vcac_strip_edges': lambda: S.acoustics_2d_variable(mx=57, my=5, transverse_waves=2),   # 2 warps + 1 column
 }
-for _k, _f in list(S.AUX_CASES.items()) if hasattr(S, 'AUX_CASES') else []:
-    CASES[_k] = _f
+CASES.update({
+    # capacity function + aux edge velocities + custom aux ghost cells (mapped annulus grid)
+    'annulus_unsplit_cor': lambda: S.advection_annulus(),
+    'annulus_unsplit_inc': lambda: S.advection_annulus(mr=33, mtheta=61, transverse_waves=1),
+    'annulus_split': lambda: S.advection_annulus(mr=30, mtheta=58, dimensional_split=True),
+    'annulus_first_order': lambda: S.advection_annulus(mr=29, mtheta=40, order=1, transverse_waves=1),
+})
 
 
 @pytest.mark.parametrize('name', sorted(CASES))
@@ -53,7 +58,7 @@ def test_fast_within_tolerance(name):
     assert _rel_linf(q, qr) <= 1e-12
 
 
-@pytest.mark.parametrize('name', ['vcac_unsplit_inc', 'vcac_split'])
+@pytest.mark.parametrize('name', ['vcac_unsplit_inc', 'vcac_split', 'annulus_unsplit_cor'])
 def test_100_steps(name):
     sc = CASES[name]()
     qr, logr = _run_ref(sc, 101)
@@ -73,3 +78,17 @@ def test_acoustics_2d_variable_golden(precision):
     p = claw.frames[claw.num_output_times].state.get_q_global()[0]
     expected = goldens2()['acoustics_2d_variable__pressure_classic']
     assert np.max(np.abs(p.reshape(-1) - expected.reshape(-1))) < 1e-12
+
+
+@pytest.mark.parametrize('precision', ['strict', 'fast'])
+def test_advection_annulus_golden(precision):
+    """pyclaw/examples/advection_2d_annulus/test_2d_advection_annulus.py:9-30: area-weighted L1 < 1e-6."""
+    sc = S.advection_annulus()
+    claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision=precision)
+    claw.run()
+    q = claw.frames[claw.num_output_times].state.get_q_global()[0].reshape(-1)
+    dx, dy = claw.solution.domain.grid.delta
+    area = (sc['aux'][2] * dx * dy).reshape(-1)
+    expected = goldens2()['advection_annulus__classic']
+    assert np.sum(np.abs(area * (q - expected))) < 1e-6
+    assert np.max(np.abs(q - expected)) < 1e-12

@@ -176,3 +176,17 @@ def test_acoustics_2d_variable_golden(oracle_lib):
     s.run(sc['tfinal'], sc['num_output_times'])
     g = goldens2()['acoustics_2d_variable__pressure_classic']
     assert np.max(np.abs(s.q[0].reshape(-1) - g.reshape(-1))) < 1e-13
+
+
+def test_advection_annulus_golden(oracle_lib):
+    # pyclaw/examples/advection_2d_annulus/test_2d_advection_annulus.py:9-30 (area-weighted L1 < 1e-6): pins the
+    # capacity-function branches of step2 / flux2 (dtdx1d = dtdx/aux(capa), update / capa), rpn2/rpt2_vc_advection,
+    # custom aux ghost cells and method(3) = 2 on a mapped grid
+    sc = S.advection_annulus()
+    s = ref_solver(sc)
+    s.run(sc['tfinal'], sc['num_output_times'])
+    g = goldens2()['advection_annulus__classic']
+    dx, dy = s.delta
+    area = (sc['aux'][2] * dx * dy).reshape(-1)
+    assert np.sum(np.abs(area * (s.q[0].reshape(-1) - g))) < 1e-6
+    assert np.max(np.abs(s.q[0].reshape(-1) - g)) < 1e-12
