@@ -41,7 +41,7 @@ W_DIV, W_SQRT = 8.0, 9.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
     ap.add_argument('--n', type=int, default=8192, help='cells per side per GPU')
@@ -123,7 +123,7 @@ def algorithmic_ops(n_sample=192):
     return ops
 
 
-def cpu_baseline(n, nthreads, min_seconds=10.0, max_steps=50):
+def cpu_baseline(n, nthreads, min_seconds=10.0, max_steps=400):
     """The oracle (C++ restatement of the reference's f2py Fortran step) on a bounded sample of the
     same workload, threaded over pencils."""
     from clawpack_b200 import scenarios as S
@@ -276,7 +276,8 @@ def main():
             'achieved': flops_per_s / 1e12, 'peak': 2.0 * peak.value / 1e3, 'unit': 'TFLOP/s',
             'frac': flops_per_s / 1e9 / (2.0 * peak.value),
             'traffic': ncu.get('dram_bytes_per_launch'),
-            'kernel': 'sweep2_unsplit<RpEuler4Wave2D,%d> (%s)' % (linfo[2], args.precision),
+            'kernel': ('sweep2_unsplit_ws<RpEuler4Wave2D,1 warp/CTA,12 CTAs/SM,MC|spec> (%s)' % args.precision)
+                      if linfo[2] == 32 else 'sweep2_unsplit<RpEuler4Wave2D,%d> (%s)' % (linfo[2], args.precision),
             'kernel_ms': sweep_ms,
             'launch': {'grid': [linfo[0], linfo[1]], 'block': linfo[2], 'smem_bytes': linfo[3],
                        'ctas_per_sm': linfo[4]},

@@ -136,7 +136,20 @@ __device__ __forceinline__ void second_order(double dtd, const double (*wave)[RP
 
 // flux2.f90:111-119 for one interface: cfl = max(cfl, dtd*s, -dtd*s) over the wave families.  dtd > 0, so
 // max(dtd*s, -dtd*s) = dtd*|s| bit for bit; fast mode uses that and, for solvers whose speeds are ordered
-// (s[0] <= ... <= s[W-1]: all of rp2.cuh / rp3.cuh), only the two extreme speeds.
+// (s[0] = smallest, s[RP::S_HI] = largest: all of rp2.cuh), only the two extreme speeds.
+template <class RP>
+__device__ __forceinline__ double cfl_update(double cfl, double dtd, const double* s) {
+#ifdef CLAW_STRICT
+#pragma unroll
+  for (int mw = 0; mw < RP::MWAVES; ++mw) cfl = fmax2(fmax2(cfl, dtd * s[mw]), -dtd * s[mw]);
+  return cfl;
+#else
+  const double a = fabs(s[0]), b = fabs(s[RP::S_HI]);
+  return fmax2(cfl, dtd * ((b > a) ? b : a));
+#endif
+}
+
+// ordered speeds s[0] <= ... <= s[W-1] (the 3-D solvers of rp3.cuh)
 template <int W>
 __device__ __forceinline__ double cfl_update(double cfl, double dtd, const double* s) {
 #ifdef CLAW_STRICT
@@ -329,7 +342,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
         RP::normal(P.rp, 1, ql, qr, c1, cN, waveN, sN, amdqN, apdqN, roeN);
       }
       if (y_cfl_col && (J + 2 >= 2) && (J + 2 <= P.my + 2)) {             // flux2.f90:111-119
-        cfl = cfl_update<W>(cfl, dtdy, sN);
+        cfl = cfl_update<RP>(cfl, dtdy, sN);
       }
       double dotn[W];
 #pragma unroll
@@ -414,7 +427,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
       double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
       x_face<RP, NT, LIM>(P, q1, c1, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
       if (x_cfl_col && (J + 1 >= 1) && (J + 1 <= P.my + 2)) {             // flux2.f90:111-119
-        cfl = cfl_update<W>(cfl, dtdx, s);
+        cfl = cfl_update<RP>(cfl, dtdx, s);
       }
       double bmA[M], bpA[M], bmP[M], bpP[M];
 #pragma unroll
@@ -523,7 +536,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__
       double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
       x_face<RP, NT>(P, q, cq, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
       if (x_cfl_col) {
-        cfl = cfl_update<W>(cfl, dtdx, s);
+        cfl = cfl_update<RP>(cfl, dtdx, s);
       }
 #pragma unroll
       for (int m = 0; m < M; ++m) { sxw[m * NT] = amdq[m]; sxw[(M + m) * NT] = fadd[m]; }
@@ -559,7 +572,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__
       double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
       x_face<RP, NT>(P, qx2, cq, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
       if (x_cfl_col) {
-        cfl = cfl_update<W>(cfl, dtdx, s);
+        cfl = cfl_update<RP>(cfl, dtdx, s);
       }
 #pragma unroll
       for (int m = 0; m < M; ++m) { sxw[m * NT] = amdq[m]; sxw[(M + m) * NT] = fadd[m]; }
@@ -583,7 +596,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__
         RP::normal(P.rp, 1, ql, qr, cx1, cx2, waveN, sN, amdqN, apdqN, roeN);
       }
       if (col_ok && (J + 2 >= 2) && (J + 2 <= P.my + 2)) {
-        cfl = cfl_update<W>(cfl, dtdy, sN);
+        cfl = cfl_update<RP>(cfl, dtdy, sN);
       }
       double dotn[W];
 #pragma unroll

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
         RP::normal(P.rp, 1, ql, qr, c1, cN, waveN, sN, amdqN, apdqN, roeN);
       }
       if (y_cfl_col && (J + 2 >= 2) && (J + 2 <= P.my + 2)) {             // flux2.f90:111-119
-        cfl = cfl_update<W>(cfl, dtdy, sN);
+        cfl = cfl_update<RP>(cfl, dtdy, sN);
       }
       double dotn[W];
 #pragma unroll
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
         for (int m = 0; m < M; ++m) fadd[m] = 0.0 + 0.5 * cqxx[m];
       }
       if (x_cfl_col && (J + 1 >= 1) && (J + 1 <= P.my + 2)) {             // flux2.f90:111-119
-        cfl = cfl_update<W>(cfl, dtdx, s);
+        cfl = cfl_update<RP>(cfl, dtdx, s);
       }
       double bmA[M], bpA[M], bmP[M], bpP[M];
 #pragma unroll

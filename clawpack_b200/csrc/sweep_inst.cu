@@ -114,6 +114,7 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
       if (variant == 6) return launch_one<RpShallowRoeEfix2D, 64, 8>(kind, P, seg_hint, num_sms, st, info);
       return launch_one<RpShallowRoeEfix2D, 128>(kind, P, seg_hint, num_sms, st, info);
     }
+    case 9: return launch_one<RpEuler5Wave2D, 128>(kind, P, seg_hint, num_sms, st, info);
     case 7: return launch_aux<RpVcAcoustics2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 8: return launch_aux<RpVcAdvection2D, 2>(kind, P, seg_hint, num_sms, st, info);
   }

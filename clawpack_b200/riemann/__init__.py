@@ -14,6 +14,7 @@ _SOLVERS = {
     'vc_acoustics_3D': (5, (), 3),                            # rpn3_vc_acoustics.f90 (no common block)
     'euler_3D': (6, ('gamma',), 3),                           # rpn3_euler.f90 / rpt3_euler.f90 / rptt3_euler.f90
     'vc_acoustics_2D': (7, (), 2),                            # rpn2_vc_acoustics.f90 (coefficients in aux)
+    'euler_5wave_2D': (9, ('gamma',), 2),                     # rpn2_euler_5wave.f90:64
     'vc_advection_2D': (8, (), 2),                            # rpn2_vc_advection.f90 (edge velocities in aux)
 }
 
@@ -25,3 +26,4 @@ for _name, (_id, _cp, _nd) in _SOLVERS.items():
 from . import acoustics_2D_constants, advection_2D_constants, euler_4wave_2D_constants  # noqa: E402,F401
 from . import shallow_roe_with_efix_2D_constants, vc_acoustics_3D_constants             # noqa: E402,F401
 from . import euler_3D_constants, vc_acoustics_2D_constants, vc_advection_2D_constants   # noqa: E402,F401
+from . import euler_5wave_2D_constants                                                   # noqa: E402,F401

@@ -36,7 +36,7 @@ def _base(rp, lower, upper, n, q, **kw):
              dimensional_split=True, transverse_waves=None, cfl_max=1.0, cfl_desired=0.9,
              dt_initial=0.1, bc_lower=None, bc_upper=None, aux_bc_lower=None, aux_bc_upper=None,
              tfinal=1.0, num_output_times=10, index_capa=-1, custom_aux_bc_lower=None, custom_aux_bc_upper=None,
-             mapc2p=None)
+             mapc2p=None, step_source=None, source_split=1, before_step=None, fwave=False)
     d.update(kw)
     return d
 
@@ -147,6 +147,74 @@ def advection_annulus(mr=40, mtheta=120, tfinal=1.0, num_output_times=10, dimens
                  aux_bc_lower=[0, PERIODIC], aux_bc_upper=[0, PERIODIC], custom_aux_bc_lower=aux_lower,
                  custom_aux_bc_upper=aux_upper, index_capa=2, tfinal=tfinal, num_output_times=num_output_times,
                  mapc2p=lambda xc, yc: [xc * np.cos(yc), xc * np.sin(yc)])
+
+
+def quadrants_tracer(mx=60, my=50, **kw):
+    """The four-quadrant Riemann problem of `quadrants` with a fifth, passively advected component, for
+    euler_5wave_2D without host callbacks (device-resident path)."""
+    sc = quadrants(mx=mx, my=my)
+    X, Y = _grid((0., 0.), (1., 1.), (mx, my))
+    q = np.empty((5, mx, my), order='F')
+    q[:4] = sc['q']
+    q[4] = 1.0 * ((X - 0.5) ** 2 + (Y - 0.5) ** 2 < 0.09)
+    sc.update(rp='euler_5wave_2D', q=q, limiters=[MC, MC, MC, MC, SUPERBEE])
+    sc.update(kw)
+    return sc
+
+
+def shock_bubble_interaction(q0, tfinal=0.2, num_output_times=1, dimensional_split=True, transverse_waves=None):
+    """pyclaw/examples/euler_2d/shock_bubble_interaction.py:93-215 (classic branch): axisymmetric Euler + tracer
+    (euler_5wave_2D), Mach-2.95 shock hitting a light bubble; aux(1) = radial coordinate of the cell centre;
+    Godunov-split geometric source term advanced on the HOST by a 2-stage Runge-Kutta step; inflow (BC.custom) at
+    x-lower, wall at the axis.  `q0` is the example's initial state (cells cut by the bubble edge carry sub-cell
+    volume fractions from scipy.integrate.quad): tests/golden/reference_goldens2.npz
+    ['euler_2d__shock_bubble_interaction_q0'], produced by running the reference's own qinit."""
+    gamma = 1.4
+    gamma1 = gamma - 1.
+    mx, my = q0.shape[1:]
+    lower, upper = (0.0, 0.0), (2.0, 0.5)
+    pinf = 5.
+    rinf = (gamma1 + pinf * (gamma + 1.)) / ((gamma + 1.) + gamma1 * pinf)
+    vinf = 1. / np.sqrt(gamma) * (pinf - 1.) / np.sqrt(0.5 * ((gamma + 1.) / gamma) * pinf + 0.5 * gamma1 / gamma)
+    einf = 0.5 * rinf * vinf ** 2 + pinf / gamma1
+    aux = np.empty((1, mx, my), order='F')
+    aux[0, :, :] = centers(lower[1], upper[1], my)[None, :]
+
+    def inflow(qbc, g):                                  # incoming_shock (:93-109)
+        for i in range(g):
+            qbc[0, i, ...] = rinf
+            qbc[1, i, ...] = rinf * vinf
+            qbc[2, i, ...] = 0.
+            qbc[3, i, ...] = einf
+            qbc[4, i, ...] = 0.
+
+    def radial_source(q, aux_, dt):                      # step_Euler_radial (:112-143): RK2 on the geometric terms
+        dt2 = dt / 2.
+        rad = aux_[0, :, :]
+        rho = q[0, :, :]
+        u = q[1, :, :] / rho
+        v = q[2, :, :] / rho
+        press = (gamma - 1.) * (q[3, :, :] - 0.5 * rho * (u ** 2 + v ** 2))
+        qs = np.empty(q.shape)
+        qs[0, :, :] = q[0, :, :] - dt2 / rad * q[2, :, :]
+        qs[1, :, :] = q[1, :, :] - dt2 / rad * rho * u * v
+        qs[2, :, :] = q[2, :, :] - dt2 / rad * rho * v * v
+        qs[3, :, :] = q[3, :, :] - dt2 / rad * v * (q[3, :, :] + press)
+        rho = qs[0, :, :]
+        u = qs[1, :, :] / rho
+        v = qs[2, :, :] / rho
+        press = (gamma - 1.) * (qs[3, :, :] - 0.5 * rho * (u ** 2 + v ** 2))
+        q[0, :, :] = q[0, :, :] - dt / rad * qs[2, :, :]
+        q[1, :, :] = q[1, :, :] - dt / rad * rho * u * v
+        q[2, :, :] = q[2, :, :] - dt / rad * rho * v * v
+        q[3, :, :] = q[3, :, :] - dt / rad * v * (qs[3, :, :] + press)
+
+    return _base('euler_5wave_2D', lower, upper, (mx, my), q0, aux=aux, problem_data={'gamma': gamma},
+                 limiters=[MC, MC, MC, MC, SUPERBEE], dimensional_split=bool(dimensional_split),
+                 transverse_waves=transverse_waves, cfl_max=0.5, cfl_desired=0.45,
+                 bc_lower=[0, WALL], bc_upper=[EXTRAP, EXTRAP], aux_bc_lower=[EXTRAP, EXTRAP],
+                 aux_bc_upper=[EXTRAP, EXTRAP], custom_bc_lower=inflow, step_source=radial_source, source_split=1,
+                 tfinal=tfinal, num_output_times=num_output_times)
 
 
 def quadrants(mx=100, my=100, tfinal=0.8):
@@ -332,6 +400,15 @@ def make_claw(sc, kernel_language='CUDA', pyclaw=None, **solver_kw):
     if sc.get('custom_aux_bc_upper') is not None:
         fu = sc['custom_aux_bc_upper']
         solver.user_aux_bc_upper = lambda state, dim, t, qbc, auxbc, num_ghost: fu(auxbc, num_ghost)
+    if sc.get('step_source') is not None:               # host callbacks: f(q, aux, dt) / f(q, aux) on the interior arrays
+        fs = sc['step_source']
+        solver.step_source = lambda solver_, state, dt: fs(state.q, state.aux, dt)
+        solver.source_split = sc.get('source_split', 1)
+    if sc.get('before_step') is not None:
+        fb = sc['before_step']
+        solver.before_step = lambda solver_, state: fb(state.q, state.aux)
+    if sc.get('fwave'):
+        solver.fwave = True
     for k, v in solver_kw.items():
         setattr(solver, k, v)
     names = ['x', 'y', 'z'][:ndim]

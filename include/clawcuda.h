@@ -47,7 +47,8 @@ enum {
   CLAW_RP_VC_ACOUSTICS_3D = 5,         /* rpn3_vc_acoustics.f90, rpt3_vc_acoustics.f90, rptt3_vc_acoustics.f90 */
   CLAW_RP_EULER_3D = 6,                /* rpn3_euler.f90, rpt3_euler.f90, rptt3_euler.f90 */
   CLAW_RP_VC_ACOUSTICS_2D = 7,         /* rpn2_vc_acoustics.f90, rpt2_vc_acoustics.f90 (aux: density, sound speed) */
-  CLAW_RP_VC_ADVECTION_2D = 8          /* rpn2_vc_advection.f90, rpt2_vc_advection.f90 (aux: edge velocities) */
+  CLAW_RP_VC_ADVECTION_2D = 8,         /* rpn2_vc_advection.f90, rpt2_vc_advection.f90 (aux: edge velocities) */
+  CLAW_RP_EULER_5WAVE_2D = 9           /* rpn2_euler_5wave.f90, rpt2_euler_5wave.f90 (Euler + tracer) */
 };
 
 /* Boundary-condition ids = pyclaw.BC (pyclaw/src/pyclaw/solver.py:13-19) */

@@ -69,6 +69,7 @@ enum RpId {
   RP_VC_ACOUSTICS_3D = 5,
   RP_VC_ACOUSTICS_2D = 7,       // (6 = euler_3D, clawref3.hpp)
   RP_VC_ADVECTION_2D = 8,
+  RP_EULER_5WAVE_2D = 9,
 };
 
 // =====================================================================
@@ -573,6 +574,150 @@ void rpt2_vc_acoustics(int ixy, int imp, int, int, int, int, int mbc, int mx, V2
 }
 
 // =====================================================================
+// euler_5wave_2D -- riemann/src/rpn2_euler_5wave.f90:66-232, rpt2_euler_5wave.f90:52-118   cparam = (gamma)
+// 4-equation Roe solver with entropy fix + a passively advected tracer (component 5, wave 5).
+// =====================================================================
+template <class R>
+void rpn2_euler_5wave(int ixy, int, int meqn, int mwaves, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>,
+                      V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double* cparam) {
+  const R gamma = R(cparam[0]);
+  const R gamma1 = gamma - R(1.0);                      // :66
+  int mu, mv;
+  if (ixy == 1) { mu = 2; mv = 3; } else { mu = 3; mv = 2; }   // :69-75
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {           // :82-147 (wave = 0, s = 0 first, :78-79)
+    for (int mw = 1; mw <= mwaves; ++mw) { s(mw, i) = R(0.0); for (int m = 1; m <= meqn; ++m) wave(m, mw, i) = R(0.0); }
+    R rho_sqrtl = r_sqrt(qr(1, i - 1));
+    R rho_sqrtr = r_sqrt(ql(1, i));
+    R rho_sq2 = rho_sqrtl + rho_sqrtr;
+    R u = (qr(mu, i - 1) / rho_sqrtl + ql(mu, i) / rho_sqrtr) / rho_sq2;
+    R v = (qr(mv, i - 1) / rho_sqrtl + ql(mv, i) / rho_sqrtr) / rho_sq2;
+    R u2v2 = u * u + v * v;
+    R pl = gamma1 * (qr(4, i - 1) - R(0.5) * (qr(2, i - 1) * qr(2, i - 1) + qr(3, i - 1) * qr(3, i - 1)) / qr(1, i - 1));
+    R pr = gamma1 * (ql(4, i) - R(0.5) * (ql(2, i) * ql(2, i) + ql(3, i) * ql(3, i)) / ql(1, i));
+    R enth = (((qr(4, i - 1) + pl) / rho_sqrtl + (ql(4, i) + pr) / rho_sqrtr)) / rho_sq2;
+    R c = r_sqrt(gamma1 * (enth - R(0.5) * u2v2));
+    R g1c2 = gamma1 / (gamma1 * (enth - R(0.5) * u2v2));
+    R euv = enth - u2v2;
+    R d1 = ql(1, i) - qr(1, i - 1);
+    R d2 = ql(mu, i) - qr(mu, i - 1);
+    R d3 = ql(mv, i) - qr(mv, i - 1);
+    R d4 = ql(4, i) - qr(4, i - 1);
+    R a3 = g1c2 * (euv * d1 + u * d2 + v * d3 - d4);
+    R a2 = d3 - v * d1;
+    R a4 = (d2 + (c - u) * d1 - c * a3) / (R(2.0) * c);
+    R a1 = d1 - a3 - a4;
+    wave(1, 1, i) = a1; wave(mu, 1, i) = a1 * (u - c); wave(mv, 1, i) = a1 * v; wave(4, 1, i) = a1 * (enth - u * c);
+    wave(5, 1, i) = R(0.0);
+    s(1, i) = u - c;
+    wave(1, 2, i) = R(0.0); wave(mu, 2, i) = R(0.0); wave(mv, 2, i) = a2; wave(4, 2, i) = a2 * v; wave(5, 2, i) = R(0.0);
+    s(2, i) = u;
+    wave(1, 3, i) = a3; wave(mu, 3, i) = a3 * u; wave(mv, 3, i) = a3 * v; wave(4, 3, i) = a3 * R(0.5) * u2v2;
+    wave(5, 3, i) = R(0.0);
+    s(3, i) = u;
+    wave(1, 4, i) = a4; wave(mu, 4, i) = a4 * (u + c); wave(mv, 4, i) = a4 * v; wave(4, 4, i) = a4 * (enth + u * c);
+    wave(5, 4, i) = R(0.0);
+    s(4, i) = u + c;
+    wave(5, 5, i) = ql(5, i) - qr(5, i - 1);
+    s(5, i) = u;
+  }
+  // efix = .true. (:60), :163-232
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    for (int m = 1; m <= meqn; ++m) { amdq(m, i) = R(0.0); apdq(m, i) = R(0.0); }
+    R rhoim1 = qr(1, i - 1);
+    R pim1 = gamma1 * (qr(4, i - 1) - R(0.5) * (qr(mu, i - 1) * qr(mu, i - 1) + qr(mv, i - 1) * qr(mv, i - 1)) / rhoim1);
+    R cim1 = r_sqrt(gamma * pim1 / rhoim1);
+    R s0 = qr(mu, i - 1) / rhoim1 - cim1;
+    if (s0 >= R(0.0) && s(1, i) > R(0.0)) continue;     // :172-174
+    R rho1 = qr(1, i - 1) + wave(1, 1, i);
+    R rhou1 = qr(mu, i - 1) + wave(mu, 1, i);
+    R rhov1 = qr(mv, i - 1) + wave(mv, 1, i);
+    R en1 = qr(4, i - 1) + wave(4, 1, i);
+    R p1 = gamma1 * (en1 - R(0.5) * (rhou1 * rhou1 + rhov1 * rhov1) / rho1);
+    R c1 = r_sqrt(gamma * p1 / rho1);
+    R s1 = rhou1 / rho1 - c1;
+    R sfract;
+    if (s0 < R(0.0) && s1 > R(0.0)) sfract = s0 * (s1 - s(1, i)) / (s1 - s0);
+    else if (s(1, i) < R(0.0)) sfract = s(1, i);
+    else sfract = R(0.0);
+    for (int m = 1; m <= meqn; ++m) amdq(m, i) = sfract * wave(m, 1, i);
+    if (s(2, i) >= R(0.0)) continue;                    // :197-199
+    for (int m = 1; m <= meqn; ++m) amdq(m, i) = amdq(m, i) + s(2, i) * wave(m, 2, i);
+    for (int m = 1; m <= meqn; ++m) amdq(m, i) = amdq(m, i) + s(3, i) * wave(m, 3, i);
+    for (int m = 1; m <= meqn; ++m) amdq(m, i) = amdq(m, i) + s(5, i) * wave(m, 5, i);
+    R rhoi = ql(1, i);
+    R pi = gamma1 * (ql(4, i) - R(0.5) * (ql(mu, i) * ql(mu, i) + ql(mv, i) * ql(mv, i)) / rhoi);
+    R ci = r_sqrt(gamma * pi / rhoi);
+    R s3 = ql(mu, i) / rhoi + ci;
+    R rho2 = ql(1, i) - wave(1, 4, i);
+    R rhou2 = ql(mu, i) - wave(mu, 4, i);
+    R rhov2 = ql(mv, i) - wave(mv, 4, i);
+    R en2 = ql(4, i) - wave(4, 4, i);
+    R p2 = gamma1 * (en2 - R(0.5) * (rhou2 * rhou2 + rhov2 * rhov2) / rho2);
+    R c2 = r_sqrt(gamma * p2 / rho2);
+    R s2 = rhou2 / rho2 + c2;
+    if (s2 < R(0.0) && s3 > R(0.0)) sfract = s2 * (s3 - s(4, i)) / (s3 - s2);
+    else if (s(4, i) < R(0.0)) sfract = s(4, i);
+    else continue;
+    for (int m = 1; m <= meqn; ++m) amdq(m, i) = amdq(m, i) + sfract * wave(m, 4, i);
+  }
+  for (int m = 1; m <= meqn; ++m)                       // :223-231
+    for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+      R df = R(0.0);
+      for (int mw = 1; mw <= mwaves; ++mw) df = df + s(mw, i) * wave(m, mw, i);
+      apdq(m, i) = df - amdq(m, i);
+    }
+}
+
+template <class R>
+void rpt2_euler_5wave(int ixy, int, int, int meqn, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>, V2<R>,
+                      V2<R> asdq, V2<R> bmasdq, V2<R> bpasdq, const double* cparam) {
+  const R gamma = R(cparam[0]);
+  const R gamma1 = gamma - R(1.0);
+  int mu, mv;
+  if (ixy == 1) { mu = 2; mv = 3; } else { mu = 3; mv = 2; }
+  R waveb[6][5]; R sb[5];
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {           // rpt2_euler_5wave.f90:52-117
+    for (int m = 1; m <= meqn; ++m) { bmasdq(m, i) = R(0.0); bpasdq(m, i) = R(0.0); }
+    R u, v, u2v2, enth, c;
+    {
+      RecomputeScope scope;                             // the Roe averages rpn2 already produced
+      R rho_sqrtl = r_sqrt(qr(1, i - 1));
+      R rho_sqrtr = r_sqrt(ql(1, i));
+      R rho_sq2 = rho_sqrtl + rho_sqrtr;
+      u = (qr(mu, i - 1) / rho_sqrtl + ql(mu, i) / rho_sqrtr) / rho_sq2;
+      v = (qr(mv, i - 1) / rho_sqrtl + ql(mv, i) / rho_sqrtr) / rho_sq2;
+      u2v2 = u * u + v * v;
+      R pl = gamma1 * (qr(4, i - 1) - R(0.5) * (qr(2, i - 1) * qr(2, i - 1) + qr(3, i - 1) * qr(3, i - 1)) / qr(1, i - 1));
+      R pr = gamma1 * (ql(4, i) - R(0.5) * (ql(2, i) * ql(2, i) + ql(3, i) * ql(3, i)) / ql(1, i));
+      enth = (((qr(4, i - 1) + pl) / rho_sqrtl + (ql(4, i) + pr) / rho_sqrtr)) / rho_sq2;
+      c = r_sqrt(gamma1 * (enth - R(0.5) * u2v2));
+    }
+    R g1c2 = gamma1 / (c * c);                          // :71  (NOT the rpn2 expression)
+    R euv = enth - u2v2;
+    R a3 = g1c2 * (euv * asdq(1, i) + u * asdq(mu, i) + v * asdq(mv, i) - asdq(4, i));
+    R a2 = asdq(mu, i) - u * asdq(1, i);
+    R a4 = (asdq(mv, i) + (c - v) * asdq(1, i) - c * a3) / (R(2.0) * c);
+    R a1 = asdq(1, i) - a3 - a4;
+    waveb[1][1] = a1; waveb[mu][1] = a1 * u; waveb[mv][1] = a1 * (v - c); waveb[4][1] = a1 * (enth - v * c);
+    waveb[5][1] = R(0.0);
+    sb[1] = v - c;
+    waveb[1][2] = a3; waveb[mu][2] = a3 * u + a2; waveb[mv][2] = a3 * v; waveb[4][2] = a3 * R(0.5) * u2v2 + a2 * u;
+    waveb[5][2] = R(0.0);
+    sb[2] = v;
+    waveb[1][3] = a4; waveb[mu][3] = a4 * u; waveb[mv][3] = a4 * (v + c); waveb[4][3] = a4 * (enth + v * c);
+    waveb[5][3] = R(0.0);
+    sb[3] = v + c;
+    waveb[1][4] = R(0.0); waveb[mu][4] = R(0.0); waveb[mv][4] = R(0.0); waveb[4][4] = R(0.0); waveb[5][4] = asdq(5, i);
+    sb[4] = v;
+    for (int mw = 1; mw <= 4; ++mw)                     // :112-115
+      for (int m = 1; m <= meqn; ++m) {
+        bmasdq(m, i) = bmasdq(m, i) + r_min(sb[mw], R(0.0)) * waveb[m][mw];
+        bpasdq(m, i) = bpasdq(m, i) + r_max(sb[mw], R(0.0)) * waveb[m][mw];
+      }
+  }
+}
+
+// =====================================================================
 // vc_advection_2D -- riemann/src/rpn2_vc_advection.f90:47-53, rpt2_vc_advection.f90:33-41
 // colour equation; aux(1) = u at the left edge, aux(2) = v at the bottom edge of each cell
 // =====================================================================
@@ -605,6 +750,7 @@ template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt)
     case RP_SHALLOW_ROE_EFIX_2D: rpn = rpn2_shallow_roe_efix<R>; rpt = rpt2_shallow_roe_efix<R>; return true;
     case RP_VC_ACOUSTICS_2D: rpn = rpn2_vc_acoustics<R>; rpt = rpt2_vc_acoustics<R>; return true;
     case RP_VC_ADVECTION_2D: rpn = rpn2_vc_advection<R>; rpt = rpt2_vc_advection<R>; return true;
+    case RP_EULER_5WAVE_2D: rpn = rpn2_euler_5wave<R>; rpt = rpt2_euler_5wave<R>; return true;
   }
   return false;
 }

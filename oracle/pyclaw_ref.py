@@ -27,6 +27,7 @@ RP_IDS = {
     'euler_3D': 6,
     'vc_acoustics_2D': 7,
     'vc_advection_2D': 8,
+    'euler_5wave_2D': 9,
 }
 # COMMON /cparam/ member order of each solver (rpn2_advection.f90, rpn2_acoustics.f90:52,
 # rpn2_euler_4wave.f90:71, rpn2_shallow_roe_with_efix.f90:59; vc_acoustics_3D has none)
@@ -39,11 +40,12 @@ CPARAM_NAMES = {
     'euler_3D': ('gamma',),           # rpn3_euler.f90: COMMON /cparam/ gamma
     'vc_acoustics_2D': (),            # rpn2_vc_acoustics.f90: coefficients live in aux
     'vc_advection_2D': (),            # rpn2_vc_advection.f90: edge velocities live in aux
+    'euler_5wave_2D': ('gamma',),     # rpn2_euler_5wave.f90:64
 }
 NUM_EQN = {'advection_2D': 1, 'acoustics_2D': 3, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
-           'vc_acoustics_3D': 4, 'euler_3D': 5, 'vc_acoustics_2D': 3, 'vc_advection_2D': 1}
+           'vc_acoustics_3D': 4, 'euler_3D': 5, 'vc_acoustics_2D': 3, 'vc_advection_2D': 1, 'euler_5wave_2D': 5}
 NUM_WAVES = {'advection_2D': 1, 'acoustics_2D': 2, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
-             'vc_acoustics_3D': 2, 'euler_3D': 3, 'vc_acoustics_2D': 2, 'vc_advection_2D': 1}
+             'vc_acoustics_3D': 2, 'euler_3D': 3, 'vc_acoustics_2D': 2, 'vc_advection_2D': 1, 'euler_5wave_2D': 5}
 
 BC_CUSTOM, BC_EXTRAP, BC_PERIODIC, BC_WALL = 0, 1, 2, 3
 
@@ -175,6 +177,9 @@ class RefSolver(object):
         self.reflect_index = list(range(1, num_dim + 1))
         self.user_bc_lower = None           # f(idim, qbc, num_ghost): BC.custom fill of q (solver.py:393-398)
         self.user_bc_upper = None
+        self.step_source = None             # f(q, aux, dt): in-place source step on the interior q (classic/solver.py:126-144)
+        self.source_split = 1
+        self.before_step = None             # f(q, aux): solver.py:609-610
         self.user_aux_bc_lower = None       # f(idim, auxbc, num_ghost): BC.custom fill of aux
         self.user_aux_bc_upper = None
         self.nthreads = 1
@@ -299,7 +304,7 @@ class RefSolver(object):
             if tend - t - self.dt < 1.e-14 * t:
                 self.dt = tend - t
 
-    # -- evolve_to_time: solver.py:554-666 (no source terms / before_step in the oracle) ------
+    # -- evolve_to_time: solver.py:554-666 + ClawSolver.step (classic/solver.py:96-146) ------
     def evolve_to_time(self, tend=None):
         take_one_step = tend is None
         tstart = self.t
@@ -320,10 +325,19 @@ class RefSolver(object):
             if self.dt_variable:
                 q_backup = self.q.copy('F')
                 told = self.t
+            if self.before_step is not None:                                 # solver.py:609-610
+                self.before_step(self.q, self.aux)
             self.get_dt(self.t, tstart, tend, take_one_step)                 # classic/solver.py:122
             self.cfl = 0.0                                                   # cfl.set_global_max(0.) (:124)
+            if self.source_split == 2 and self.step_source is not None:      # :126-127
+                self.step_source(self.q, self.aux, self.dt / 2.0)
             self.step_hyperbolic()
             cfl = self.cfl
+            if not (cfl >= self.cfl_max) and self.step_source is not None:   # :134-144
+                if self.source_split == 2:
+                    self.step_source(self.q, self.aux, self.dt / 2.0)
+                if self.source_split == 1:
+                    self.step_source(self.q, self.aux, self.dt)
             accept = not (cfl > self.cfl_max)                                # solver.py:524-529
             self.step_log.append((self.dt, cfl, accept))
             if accept:

@@ -38,6 +38,13 @@ def ref_solver(sc, nthreads=1):
         fu = sc['custom_aux_bc_upper']
         s.user_aux_bc_upper = lambda idim, auxbc, g: fu(auxbc, g)
     s.index_capa = sc.get('index_capa', -1)
+    if sc.get('step_source') is not None:
+        s.step_source = sc['step_source']
+        s.source_split = sc.get('source_split', 1)
+    if sc.get('before_step') is not None:
+        s.before_step = sc['before_step']
+    if sc.get('fwave'):
+        s.fwave = True
     s.nthreads = nthreads
     delta = [(u - l) / float(n) for l, u, n in zip(sc['lower'], sc['upper'], sc['num_cells'])]
     s.setup(sc['q'], sc['aux'], delta)

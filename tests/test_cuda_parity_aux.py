@@ -37,6 +37,14 @@ CASES.update({
     'annulus_unsplit_inc': lambda: S.advection_annulus(mr=33, mtheta=61, transverse_waves=1),
     'annulus_split': lambda: S.advection_annulus(mr=30, mtheta=58, dimensional_split=True),
     'annulus_first_order': lambda: S.advection_annulus(mr=29, mtheta=40, order=1, transverse_waves=1),
+    # euler_5wave_2D: device-resident (no host callbacks) ...
+    'euler5_split': lambda: S.quadrants_tracer(),
+    'euler5_unsplit_cor': lambda: S.quadrants_tracer(mx=45, my=70, dimensional_split=False, transverse_waves=2),
+    'euler5_unsplit_inc': lambda: S.quadrants_tracer(mx=33, my=20, dimensional_split=False, transverse_waves=1),
+    # ... and the reference example: host source term + BC.custom inflow -> f2py-shaped plug-in mode (with an aux array)
+    'sbi_split': lambda: S.shock_bubble_interaction(goldens2()['euler_2d__shock_bubble_interaction_q0']),
+    'sbi_unsplit_cor': lambda: S.shock_bubble_interaction(goldens2()['euler_2d__shock_bubble_interaction_q0'][:, :80, :],
+                                                          dimensional_split=False, transverse_waves=2),
 })
 
 
@@ -92,3 +100,18 @@ def test_advection_annulus_golden(precision):
     expected = goldens2()['advection_annulus__classic']
     assert np.sum(np.abs(area * (q - expected))) < 1e-6
     assert np.max(np.abs(q - expected)) < 1e-12
+
+
+@pytest.mark.parametrize('precision', ['strict', 'fast'])
+def test_shock_bubble_interaction_golden(precision):
+    """pyclaw/examples/euler_2d/test_euler2d.py:35-37 (160x40, tfinal 0.2, one output time): L1 < 1e-6.  The host
+    source term and the BC.custom inflow put the solver in plug-in mode: every step goes through claw_step2ds_host."""
+    sc = S.shock_bubble_interaction(goldens2()['euler_2d__shock_bubble_interaction_q0'])
+    claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision=precision)
+    claw.run()
+    assert claw.solver._dev is None and claw.solver.fmod is not None        # plug-in mode
+    rho = claw.frames[claw.num_output_times].state.get_q_global()[0].reshape(-1)
+    dx, dy = claw.solution.domain.grid.delta
+    expected = goldens2()['euler_2d__shock_bubble_interaction']
+    assert dx * dy * np.sum(np.abs(rho - expected)) < 1e-6
+    assert np.max(np.abs(rho - expected)) < (1e-11 if precision == 'strict' else 1e-8)

@@ -190,3 +190,16 @@ def test_advection_annulus_golden(oracle_lib):
     area = (sc['aux'][2] * dx * dy).reshape(-1)
     assert np.sum(np.abs(area * (s.q[0].reshape(-1) - g))) < 1e-6
     assert np.max(np.abs(s.q[0].reshape(-1) - g)) < 1e-12
+
+
+def test_shock_bubble_interaction_golden(oracle_lib):
+    # pyclaw/examples/euler_2d/test_euler2d.py:35-37 (L1 < 1e-6): pins rpn2_euler_5wave (+ entropy fix), step2ds,
+    # limiters [MC x4, superbee], the Godunov-split host source step, BC.custom inflow and BC.wall
+    g2 = goldens2()
+    sc = S.shock_bubble_interaction(g2['euler_2d__shock_bubble_interaction_q0'])
+    s = ref_solver(sc)
+    s.run(sc['tfinal'], sc['num_output_times'])
+    g = g2['euler_2d__shock_bubble_interaction']
+    dx, dy = s.delta
+    assert dx * dy * np.sum(np.abs(s.q[0].reshape(-1) - g)) < 1e-6
+    assert np.max(np.abs(s.q[0].reshape(-1) - g)) < 1e-12
