@@ -37,6 +37,7 @@ def _declare(L):
         'claw_put_q': (i, [H, vp]),
         'claw_get_q': (i, [H, vp]),
         'claw_put_aux': (i, [H, vp]),
+        'claw_get_cells': (i, [H, i, c_int_p, c_double_p]),
         'claw_put_qbc': (i, [H, vp]),
         'claw_get_qbc': (i, [H, vp]),
         'claw_put_auxbc': (i, [H, vp]),

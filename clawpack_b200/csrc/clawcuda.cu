@@ -216,6 +216,15 @@ __global__ void scatter_runs(double* dst, long long dst_stride, const double* sr
     dst[(k / len) * dst_stride + (k % len)] = src[k];
 }
 
+// gauges: values of up to 32 cells (array coordinates incl. ghosts) -> out[c*ncomp + m]
+struct CellList { int n; long long off[32]; };
+__global__ void gather_cells(const double* q, int ncomp, long long plane, CellList cells, double* out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cells.n * ncomp) return;
+  const int c = k / ncomp, m = k % ncomp;
+  out[k] = q[m * plane + cells.off[c]];
+}
+
 // FP64 issue-rate probe: 8 independent DFMA chains per thread
 __global__ void dfma_probe(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -446,6 +455,7 @@ int rp2_aux_planes(int rp_id) {
     case 1: case 2: case 3: case 4: case 9: return 0;
     case 7: return 2;      // vc_acoustics_2D: density, sound speed
     case 8: return 2;      // vc_advection_2D: edge velocities
+    case 10: return 4;     // psystem_2D: density, modulus, stress-strain relation id, strain
   }
   return -1;
 }
@@ -646,6 +656,33 @@ int claw_get_q(claw_solver* h, double* host_q) {
   if (int rc = ensure_buffers(h)) return rc;
   CK(h, cudaSetDevice(h->device));
   return get_interior(h, h->q[h->cur], h->meqn, host_q, false);
+}
+
+// q of `ncells` interior cells (0-based interior indices, ndim ints per cell) of the CURRENT state -> host_out[c*meqn+m]
+// (gauges, solver.py:680-715: a few cells per step instead of a full-array download)
+int claw_get_cells(claw_solver* h, int ncells, const int* idx, double* host_out) {
+  if (check_handle(h)) return 1;
+  if (ncells < 0 || (ncells > 0 && (!idx || !host_out))) return fail(h, 12, "claw_get_cells: bad arguments");
+  if (int rc = ensure_buffers(h)) return rc;
+  CK(h, cudaSetDevice(h->device));
+  const Dev2& g = h->g;
+  double* stage = h->work + WORK_HDR;
+  for (int c0 = 0; c0 < ncells; c0 += 32) {
+    CellList cl{};
+    cl.n = ncells - c0 < 32 ? ncells - c0 : 32;
+    for (int c = 0; c < cl.n; ++c) {
+      const int* ix = idx + (size_t)(c0 + c) * g.ndim;
+      for (int d = 0; d < g.ndim; ++d)
+        if (ix[d] < 0 || ix[d] >= g.n[d]) return fail(h, 12, "claw_get_cells: cell index %d out of range in dimension %d", ix[d], d);
+      cl.off[c] = (long long)(ix[0] + 2) + (long long)(ix[1] + 2) * g.pitch + (g.ndim == 3 ? (long long)(ix[2] + 2) * g.kstride : 0);
+    }
+    gather_cells<<<(cl.n * h->meqn + 63) / 64, 64, 0, h->stream>>>(h->q[h->cur], h->meqn, g.plane, cl, stage);
+    ++h->launches;
+    CK(h, cudaMemcpyAsync(host_out + (size_t)c0 * h->meqn, stage, sizeof(double) * cl.n * h->meqn, cudaMemcpyDeviceToHost,
+                          h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+  }
+  return 0;
 }
 
 int claw_put_aux(claw_solver* h, const double* host_aux) {

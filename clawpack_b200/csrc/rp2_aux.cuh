@@ -76,5 +76,71 @@ struct RpVcAdvection2D {
   }
 };
 
+// ------------------------------------------------------------------------------------
+// psystem_2D -- riemann/src/rpn2_psystem.f90:83-192, rpt2_psystem.f90:46-114 (f-wave solver, no common block)
+// aux(1) = density, aux(2) = elastic modulus, aux(3) = stress-strain relation id (1 linear, 2 exponential, 3 cubic),
+// aux(4) = strain of the cell (filled by the user's before_step for rpt2).   roe = (s1, s2)
+// The exponential relation calls exp(): CUDA's and the host libm's results may differ in the last bit, so this
+// material is compared with a tolerance; relations 1 and 3 are bit-exact in strict mode.
+// ------------------------------------------------------------------------------------
+struct RpPsystem2D {
+  static constexpr int MEQN = 3, MWAVES = 2, NROE = 2, NCELL = 0, MAUX = 4;
+  __device__ __forceinline__ static int nint_(double x) { return (int)llround(x); }
+  __device__ __forceinline__ static double sigma(double eps, double E, int lin) {        // rpn2_psystem.f90:156-173
+    switch (lin) {
+      case 1: return E * eps;
+      case 2: return exp(E * eps) - 1.0;
+      case 3: return (double)0.1f * E * eps + 5.0 * (eps * eps * eps) * (E * E * E);       // `0.1` is single precision there
+    }
+    return 0.0;
+  }
+  __device__ __forceinline__ static double sigmap(double eps, double E, int lin) {       // rpn2_psystem.f90:175-192
+    switch (lin) {
+      case 1: return E;
+      case 2: return E * exp(E * eps);
+      case 3: return (double)0.1f * E + 15.0 * (eps * eps) * (E * E * E);
+    }
+    return 0.0;
+  }
+  __device__ __forceinline__ static void normal(const RpParams& P, int dir, const double* ql, const double* qr,
+                                                const double* axl, const double* axr, double (*wave)[MEQN],
+                                                double* s, double* amdq, double* apdq, double* roe) {
+    const double pim = axl[0], pi = axr[0], Eim = axl[1], Ei = axr[1];
+    const int lin_i = nint_(axr[2]), lin_im = nint_(axl[2]);
+    const double sigmai = sigma(qr[0], Ei, lin_i), sigmaim = sigma(ql[0], Eim, lin_im);
+    const double sigmapi = sigmap(qr[0], Ei, lin_i), sigmapim = sigmap(ql[0], Eim, lin_im);
+    const double r11 = ddiv(1.0, sqrt(sigmapim * pim));                           // :106-107
+    const double r13 = -ddiv(1.0, sqrt(sigmapi * pi));
+    s[0] = -sqrt(ddiv(sigmapim, pim));                                            // :109-110
+    s[1] = sqrt(ddiv(sigmapi, pi));
+    const double dF1 = -(ddiv(qr[1], pi) - ddiv(ql[1], pim));                     // :114 / :129 (normal momentum)
+    const double dF2 = -(sigmai - sigmaim);
+    const double beta1 = ddiv(dF1 - r13 * dF2, r11 - r13);
+    const double beta3 = ddiv(-dF1 + r11 * dF2, r11 - r13);
+    wave[0][0] = beta1 * r11; wave[0][1] = beta1 * 1.0; wave[0][2] = beta1 * 0.0;
+    wave[1][0] = beta3 * r13; wave[1][1] = beta3 * 1.0; wave[1][2] = beta3 * 0.0;
+#pragma unroll
+    for (int m = 0; m < MEQN; ++m) { amdq[m] = wave[0][m]; apdq[m] = wave[1][m]; }
+    roe[0] = s[0]; roe[1] = s[1];
+  }
+  __device__ __forceinline__ static void speeds(const RpParams& P, int dir, const double* roe, double* s) {
+    s[0] = roe[0]; s[1] = roe[1];
+  }
+  __device__ __forceinline__ static void transverse(const RpParams& P, int dir, const double* roe, const double* ax1,
+                                                    const double* ax2, const double* ax3, const double* asdq,
+                                                    double* bm, double* bp) {
+    const double sigmapjm = sigmap(ax1[3], ax1[1], nint_(ax1[2]));
+    const double sigmapjp = sigmap(ax3[3], ax3[1], nint_(ax3[2]));
+    const double r11 = ddiv(1.0, sqrt(sigmapjm * ax1[0]));
+    const double r13 = -ddiv(1.0, sqrt(sigmapjp * ax3[0]));
+    const double s1 = -sqrt(ddiv(sigmapjm, ax1[0]));
+    const double s2 = sqrt(ddiv(sigmapjp, ax3[0]));
+    const double gamma1 = ddiv(asdq[0] - r13 * asdq[2], r11 - r13);               // :86-87 / :100-101
+    const double gamma3 = ddiv(-asdq[0] + r11 * asdq[2], r11 - r13);
+    bm[0] = s1 * gamma1 * r11; bm[1] = s1 * gamma1 * 0.0; bm[2] = s1 * gamma1 * 1.0;
+    bp[0] = s2 * gamma3 * r13; bp[1] = s2 * gamma3 * 0.0; bp[2] = s2 * gamma3 * 1.0;
+  }
+};
+
 }  // namespace CLAW_NS
 }  // namespace clawcuda

@@ -96,22 +96,26 @@ __device__ __forceinline__ void wave_dots(const double (*wave)[RP::MEQN], const 
 }
 
 // limiter.f90:39-50 for one interface, given the dot products with both neighbours
-template <class RP, int LIM = 0>
+template <class RP, int LIM = 0, bool BF = false>
 __device__ __forceinline__ void limit_waves(const Sweep2Params& P, double (*wave)[RP::MEQN], const double* s,
                                             const double* wnorm2, const double* dotl, const double* dotr) {
 #pragma unroll
   for (int mw = 0; mw < RP::MWAVES; ++mw) {
     const int meth = LIM ? LIM : P.mthlim[mw];
     if (meth == 0) continue;
-#if defined(CLAW_STRICT) || !defined(CLAW_BRANCHFREE_LIMITER)
-    if (wnorm2[mw] == 0.0) continue;
-    const double wl = philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
-#else
-    // experiment (off by default, no gain measured): branch-free, so that the divisions of the wave families are
-    // independent chains (a zero wave yields NaN here and is left untouched by the select)
-    double wl = philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
-    wl = (wnorm2[mw] == 0.0) ? 1.0 : wl;
+    double wl;
+#ifndef CLAW_STRICT
+    if constexpr (BF) {
+      // branch-free (fast mode only): the divisions of the wave families become independent chains the scheduler
+      // can overlap (a zero wave yields NaN here and is left untouched by the select)
+      wl = philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
+      wl = (wnorm2[mw] == 0.0) ? 1.0 : wl;
+    } else
 #endif
+    {
+      if (wnorm2[mw] == 0.0) continue;
+      wl = philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
+    }
 #pragma unroll
     for (int m = 0; m < RP::MEQN; ++m) wave[mw][m] = wl * wave[mw][m];
   }

@@ -21,11 +21,23 @@ __device__ __forceinline__ double shfl_right(double v) {         // value of lan
   return __shfl_down_sync(0xffffffffu, v, 1);
 }
 
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int LEVEL> __device__ __forceinline__ void prefetch_row(const double* g) {
+  if constexpr (LEVEL == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(g));
+  else asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
+}
+
 template <class RP, int NW> struct Smem2ws {
   static constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE;
   static constexpr int OFF_YW = 0;                  // [W*M]   waves of the pending y-interface
   static constexpr int OFF_YA = OFF_YW + W * M;     // [2M+NR+W] amdq, apdq, roe, dotl
-  static constexpr int PER_THREAD = OFF_YA + 2 * M + NR + W;
+  static constexpr int OFF_PF = OFF_YA + 2 * M + NR + W;   // [2*M] two-stage ring of prefetched q rows (cp.async)
+  static constexpr int PER_THREAD = OFF_PF + 2 * M;
   static constexpr size_t BYTES = (size_t)PER_THREAD * NW * 32 * sizeof(double) + 64 * sizeof(double);
 };
 
@@ -34,6 +46,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE, NT = NW * 32;
   constexpr bool SP = (SPEC & 1) != 0;
   constexpr int LIM = SP ? (SPEC >> 4) : 0;
+  constexpr bool BFL = (SPEC & 8) != 0;                    // branch-free limiter (fast mode)
+  constexpr int PF = (SPEC >> 1) & 3;                      // q-row prefetch: 0 none, 1 L1 hint, 2 L2 hint, 3 cp.async ring
   constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
   using S = Smem2ws<RP, NW>;
   constexpr int TX = 28;                                   // owned columns per warp
@@ -41,6 +55,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
   const int t = threadIdx.x, lane = t & 31;
   double* const syw = smem + S::OFF_YW * NT + t;
   double* const sya = smem + S::OFF_YA * NT + t;
+  double* const spf = smem + S::OFF_PF * NT + t;
   double* const sred = smem + S::PER_THREAD * NT;
 
   const int nx = P.mx + 4;
@@ -69,11 +84,39 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
   const bool y_cfl_col = (I >= 1) && (I <= P.mx + 2);
   const bool store_col = (lane >= 2) && (lane <= 29) && (I <= P.mx + 1);
 
+  // The first consumer of a freshly loaded row is the Roe average of the y-interface: without a prefetch the warp
+  // sits on the DRAM latency once per march step (ncu: 13 % of all stall samples on that one instruction).  PF=3
+  // keeps row J+3 in flight (cp.async into a thread-private two-stage ring) while row J+2 is being worked on.
+  if constexpr (PF == 3) {
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+      cp_async8(spf + (((Jb - 3) & 1) * M + m) * NT, qcol + m * P.plane + (long long)(Jb - 1) * P.pitch);
+    cp_async_commit();
+  }
+
   // warm-up rows: see sweep2_unsplit (the specialised kernel runs the full body from the first step)
   for (int J = Jb - 3; J < Je; ++J) {
     double qN[M];
+    if constexpr (PF == 3) {
+      cp_async_wait_all();
 #pragma unroll
-    for (int m = 0; m < M; ++m) qN[m] = qcol[m * P.plane + (long long)(J + 2) * P.pitch];
+      for (int m = 0; m < M; ++m) qN[m] = spf[((J & 1) * M + m) * NT];
+      if (J + 1 < Je) {
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+          cp_async8(spf + (((J + 1) & 1) * M + m) * NT, qcol + m * P.plane + (long long)(J + 3) * P.pitch);
+      }
+      cp_async_commit();
+    } else {
+#pragma unroll
+      for (int m = 0; m < M; ++m) qN[m] = qcol[m * P.plane + (long long)(J + 2) * P.pitch];
+      if constexpr (PF == 1 || PF == 2) {
+        if (J + 1 < Je) {
+#pragma unroll
+          for (int m = 0; m < M; ++m) prefetch_row<PF>(qcol + m * P.plane + (long long)(J + 3) * P.pitch);
+        }
+      }
+    }
     double cN[NC1];
     if constexpr (NC > 0) RP::cell(P.rp, qN, cN);
 
@@ -124,7 +167,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
 #pragma unroll
           for (int m = 0; m < M; ++m) fadd[m] = 0.0;
           if (second) {
-            if (limit) limit_waves<RP, LIM>(P, waveC, sC, wnorm2, dotl, dotn);
+            if (limit) limit_waves<RP, LIM, BFL>(P, waveC, sC, wnorm2, dotl, dotn);
             double cqxx[M];
             second_order<RP>(dtdy, waveC, sC, cqxx);
 #pragma unroll
@@ -196,7 +239,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
           }
 #pragma unroll
           for (int mw = 0; mw < W; ++mw) dotl[mw] = shfl_left(dotr[mw]);
-          limit_waves<RP, LIM>(P, wave, s, wnorm2, dotl, dotr);
+          limit_waves<RP, LIM, BFL>(P, wave, s, wnorm2, dotl, dotr);
         }
         second_order<RP>(dtdx, wave, s, cqxx);                             // flux2.f90:134-146
 #pragma unroll

@@ -94,7 +94,23 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
       if (kind == 0 && headline_method<4>(P, 4)) {
         constexpr int MC = 4 << 4;
         switch (variant) {
-          case 0: return launch_ws<RpEuler4Wave2D, 1, 12, MC | 1>(P, seg_hint, num_sms, st, info);    // fastest measured
+          case 0: return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);   // fastest measured (profiles/r01_h)
+          case 21: return launch_ws<RpEuler4Wave2D, 1, 12, MC | 1>(P, seg_hint, num_sms, st, info);    // the r01_g default
+          case 1: return launch_ws<RpEuler4Wave2D, 1, 12, MC | 1 | 2>(P, seg_hint, num_sms, st, info);   // L1 prefetch hint
+          case 2: return launch_ws<RpEuler4Wave2D, 1, 12, MC | 1 | 4>(P, seg_hint, num_sms, st, info);   // L2 prefetch hint
+          case 3: return launch_ws<RpEuler4Wave2D, 1, 12, MC | 1 | 6>(P, seg_hint, num_sms, st, info);   // cp.async ring
+          case 4: return launch_ws<RpEuler4Wave2D, 1, 16, MC | 1>(P, seg_hint, num_sms, st, info);
+          case 5: return launch_ws<RpEuler4Wave2D, 1, 16, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
+          case 6: return launch_ws<RpEuler4Wave2D, 2, 5, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
+          case 7: return launch_ws<RpEuler4Wave2D, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
+          case 11: return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);  // shared cell data
+          case 12: return launch_ws<RpEuler4Wave2DT<3>, 1, 12, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
+          case 13: return launch_ws<RpEuler4Wave2D, 2, 4, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
+          case 14: return launch_ws<RpEuler4Wave2D, 1, 8, MC | 1 | 6 | 8>(P, seg_hint, num_sms, st, info);   // branch-free limiter
+          case 16: return launch_ws<RpEuler4Wave2DT<0, 1>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);  // branch-free efix
+          case 17: return launch_ws<RpEuler4Wave2DT<0, 1>, 1, 8, MC | 1 | 6 | 8>(P, seg_hint, num_sms, st, info);
+          case 18: return launch_ws<RpEuler4Wave2DT<3, 1>, 1, 8, MC | 1 | 6 | 8>(P, seg_hint, num_sms, st, info);
+          case 19: return launch_ws<RpEuler4Wave2DT<3, 0>, 1, 8, MC | 1 | 6 | 8>(P, seg_hint, num_sms, st, info);
           case 15: return launch_spec<RpEuler4Wave2D, 64, 6, MC | 1>(P, seg_hint, num_sms, st, info);
           case 8: return launch_spec<RpEuler4Wave2D, 64, 4, MC | 1>(P, seg_hint, num_sms, st, info);
           case 10: return launch_ws<RpEuler4Wave2D, 2, 6, MC | 1>(P, seg_hint, num_sms, st, info);
@@ -117,6 +133,7 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
     case 9: return launch_one<RpEuler5Wave2D, 128>(kind, P, seg_hint, num_sms, st, info);
     case 7: return launch_aux<RpVcAcoustics2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 8: return launch_aux<RpVcAdvection2D, 2>(kind, P, seg_hint, num_sms, st, info);
+    case 10: return launch_aux<RpPsystem2D, 2>(kind, P, seg_hint, num_sms, st, info);
   }
   return cudaErrorInvalidValue;
 }

@@ -54,10 +54,14 @@ class Controller(object):
         if self.solver is None or self.solution is None:
             raise Exception('To run, a Controller must have a Solver and a Solution.')
         self.start_frame = self.solution.start_frame
+        grid = self.solution.state.grid
+        if len(grid.gauges) > 0 and self.output_format is not None:     # controller.py:296-297 (files only with output)
+            grid.setup_gauge_files(self.outdir)
         if not self.solver._is_set_up:
             self.solver.setup(self.solution)
             self.solver.dt = self.solver.dt_initial
         self.check_validity()
+        self.solver.write_gauge_values(self.solution)                    # initial gauge values (controller.py:308-309)
 
         if self.output_style == 1:
             output_times = np.linspace(self.solution.t, self.tfinal, self.num_output_times + 1)
@@ -93,5 +97,7 @@ class Controller(object):
                 self.solution.write(frame, self.outdir, self.output_format, self.output_file_prefix,
                                     self.write_aux_always, self.output_options)
             self.logger.info('Solution %s computed for time t=%f' % (frame, self.solution.t))
+        for gfile in grid.gauge_files:
+            gfile.close()
         self.solution._start_frame = len(self.frames)
         return status

@@ -132,6 +132,14 @@ class DeviceStepper(object):
         _lib.check(self.L.claw_step_launch(self.handle, _lib.dp(self.delta), float(dt), 1), self.handle)
         return self.post_step_hook(self)
 
+    def get_cells(self, state, cells):
+        """q[:, cell] for a list of interior cell index tuples (gauges) without downloading the array."""
+        self._upload_if_needed(state)
+        idx = np.ascontiguousarray(cells, dtype=np.intc).reshape(len(cells), self.num_dim)
+        out = np.empty((len(cells), state.num_eqn), dtype=np.float64)
+        _lib.check(self.L.claw_get_cells(self.handle, len(cells), _lib.ip(idx), _lib.dp(out)), self.handle)
+        return out
+
     def accept(self):
         _lib.check(self.L.claw_accept(self.handle), self.handle)
         self.host_valid = False

@@ -145,6 +145,24 @@ class Grid(_DimensionHolder):
             return self.get_dim_attribute(key)
         raise AttributeError("'Grid' object has no attribute '" + key + "'")
 
+    def add_gauges(self, gauge_coords):
+        """Cell indices of the gauges that lie on this grid (geometry.py:392-405)."""
+        for gauge in gauge_coords:
+            if all(self.lower[n] <= gauge[n] < self.upper[n] for n in range(self.num_dim)):
+                self.gauges.append([int((gauge[n] - self.lower[n]) // self.delta[n]) for n in range(self.num_dim)])
+                self.gauge_file_names.append('gauge' + '_'.join(str(coord) for coord in gauge) + '.txt')
+
+    def setup_gauge_files(self, outdir):
+        """Open one text file per gauge under outdir/_gauges (geometry.py:407-423)."""
+        import os
+        gauge_path = os.path.join(outdir, self.gauge_dir_name)
+        os.makedirs(gauge_path, exist_ok=True)
+        for name in self.gauge_file_names:
+            path = os.path.join(gauge_path, name)
+            if os.path.isfile(path):
+                os.remove(path)
+            self.gauge_files.append(open(path, 'a'))
+
     @property
     def mapc2p(self):
         return self._mapc2p if self._mapc2p is not None else _identity_map

@@ -320,5 +320,28 @@ class Solver(object):
         raise NotImplementedError('No stepping routine has been defined!')
 
     def write_gauge_values(self, solution):
-        if len(solution.state.grid.gauges) > 0:
-            raise NotImplementedError('gauges are outside this build (SURVEY.md section 2, row 13)')
+        """Record (t, compute_gauge_values(q, aux)) at every gauge cell (solver.py:680-715): appended to
+        ``state.gauge_data`` when ``state.keep_gauges`` and written to the gauge files when they are open.  On the
+        device-resident path only the gauge cells are read back (claw_get_cells), not the whole array."""
+        state = solution.state
+        gauges = state.grid.gauges
+        if len(gauges) == 0:
+            return
+        dev = getattr(self, '_dev', None)
+        qcells = dev.get_cells(state, gauges) if (dev is not None and not dev.host_valid) else None
+        for i, gauge in enumerate(gauges):
+            ix = tuple(gauge)
+            aux = state.aux[(slice(None),) + ix] if state.num_aux > 0 else None
+            q = qcells[i] if qcells is not None else state.q[(slice(None),) + ix]
+            p = self.compute_gauge_values(q, aux)
+            if not hasattr(p, '__iter__'):
+                p = [p]
+            t = solution.t
+            if state.keep_gauges:
+                gauge_data = state.gauge_data
+                if len(gauge_data) == len(gauges):
+                    gauge_data[i] = np.vstack((gauge_data[i], np.append(t, p)))
+                else:
+                    gauge_data.append(np.append(t, p))
+            if len(state.grid.gauge_files) > i:
+                state.grid.gauge_files[i].write(str(t) + ' ' + ' '.join(str(j) for j in p) + '\n')

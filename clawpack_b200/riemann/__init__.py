@@ -16,6 +16,7 @@ _SOLVERS = {
     'vc_acoustics_2D': (7, (), 2),                            # rpn2_vc_acoustics.f90 (coefficients in aux)
     'euler_5wave_2D': (9, ('gamma',), 2),                     # rpn2_euler_5wave.f90:64
     'vc_advection_2D': (8, (), 2),                            # rpn2_vc_advection.f90 (edge velocities in aux)
+    'psystem_2D': (10, (), 2),                                # rpn2_psystem.f90 (f-wave; coefficients + strain in aux)
 }
 
 for _name, (_id, _cp, _nd) in _SOLVERS.items():

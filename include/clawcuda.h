@@ -48,7 +48,8 @@ enum {
   CLAW_RP_EULER_3D = 6,                /* rpn3_euler.f90, rpt3_euler.f90, rptt3_euler.f90 */
   CLAW_RP_VC_ACOUSTICS_2D = 7,         /* rpn2_vc_acoustics.f90, rpt2_vc_acoustics.f90 (aux: density, sound speed) */
   CLAW_RP_VC_ADVECTION_2D = 8,         /* rpn2_vc_advection.f90, rpt2_vc_advection.f90 (aux: edge velocities) */
-  CLAW_RP_EULER_5WAVE_2D = 9           /* rpn2_euler_5wave.f90, rpt2_euler_5wave.f90 (Euler + tracer) */
+  CLAW_RP_EULER_5WAVE_2D = 9,          /* rpn2_euler_5wave.f90, rpt2_euler_5wave.f90 (Euler + tracer) */
+  CLAW_RP_PSYSTEM_2D = 10              /* rpn2_psystem.f90, rpt2_psystem.f90 (f-wave; aux: density, modulus, relation id, strain) */
 };
 
 /* Boundary-condition ids = pyclaw.BC (pyclaw/src/pyclaw/solver.py:13-19) */
@@ -95,6 +96,10 @@ int claw_set_tuning(claw_solver* h, int seg_rows);
    (state.q / state.aux, pyclaw/src/pyclaw/state.py:316-321) */
 int claw_put_q(claw_solver* h, const double* host_q);
 int claw_get_q(claw_solver* h, double* host_q);
+/* q of a few interior cells (0-based interior indices, ndim ints per cell) of the current state ->
+ * host_out[c*meqn + m]: the gauge read of Solver.write_gauge_values (pyclaw/src/pyclaw/solver.py:680-715) without
+ * a full-array download. */
+int claw_get_cells(claw_solver* h, int ncells, const int* idx, double* host_out);
 int claw_put_aux(claw_solver* h, const double* host_aux);
 /* same WITH ghost cells (qbc / auxbc, solver.py:341-347) */
 int claw_put_qbc(claw_solver* h, const double* host_qbc);

@@ -39,6 +39,8 @@ inline Counted r_abs(Counted x) { ++g_tally.abs; return Counted(std::fabs(x.v));
 inline Counted r_max(Counted a, Counted b) { ++g_tally.cmp; return (b.v > a.v) ? b : a; }
 inline Counted r_min(Counted a, Counted b) { ++g_tally.cmp; return (b.v < a.v) ? b : a; }
 inline Counted r_sign1(Counted s) { return Counted(std::copysign(1.0, s.v)); }
+inline Counted r_exp(Counted x) { ++g_tally.sqrt; return Counted(std::exp(x.v)); }     // tallied with the square roots
+inline int r_nint(Counted x) { return (int)std::lround(x.v); }
 
 }  // namespace clawref
 

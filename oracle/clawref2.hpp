@@ -41,6 +41,8 @@ inline double r_abs(double x) { return std::fabs(x); }
 inline double r_max(double a, double b) { return (b > a) ? b : a; }
 inline double r_min(double a, double b) { return (b < a) ? b : a; }
 inline double r_sign1(double s) { return std::copysign(1.0, s); }  // dsign(1.d0,s)
+inline double r_exp(double x) { return std::exp(x); }               // dexp
+inline int r_nint(double x) { return (int)std::lround(x); }         // nint: nearest, halves away from zero
 
 template <class R> inline R r_max3(R a, R b, R c) { return r_max(r_max(a, b), c); }
 template <class R> inline R r_min3(R a, R b, R c) { return r_min(r_min(a, b), c); }
@@ -70,6 +72,7 @@ enum RpId {
   RP_VC_ACOUSTICS_2D = 7,       // (6 = euler_3D, clawref3.hpp)
   RP_VC_ADVECTION_2D = 8,
   RP_EULER_5WAVE_2D = 9,
+  RP_PSYSTEM_2D = 10,
 };
 
 // =====================================================================
@@ -742,6 +745,91 @@ void rpt2_vc_advection(int ixy, int imp, int, int, int, int, int mbc, int mx, V2
   }
 }
 
+// =====================================================================
+// psystem_2D -- riemann/src/rpn2_psystem.f90:83-192, rpt2_psystem.f90:46-119   (no common block)
+// nonlinear p-system (elasticity) with variable coefficients, f-wave form: 3 equations, 2 f-waves.
+// aux(1) = density, aux(2) = elastic modulus, aux(3) = stress-strain relation id, aux(4) = strain (set by the
+// example's before_step for the transverse solver).
+// =====================================================================
+template <class R> inline R psystem_sigma(R eps, R E, int linearity_mat) {       // rpn2_psystem.f90:156-173
+  const R beta = R(5.0);
+  switch (linearity_mat) {
+    case 1: return E * eps;
+    case 2: return r_exp(E * eps) - R(1.0);
+    // `0.1` is a default-kind (single precision) literal in the Fortran source: its value is float(0.1)
+    case 3: return R((double)0.1f) * E * eps + beta * (eps * eps * eps) * (E * E * E);
+  }
+  return R(0.0);      // select case without a default leaves the result undefined in the reference
+}
+template <class R> inline R psystem_sigmap(R eps, R E, int linearity_mat) {      // rpn2_psystem.f90:175-192
+  switch (linearity_mat) {
+    case 1: return E;
+    case 2: return E * r_exp(E * eps);
+    case 3: return R((double)0.1f) * E + R(15.0) * (eps * eps) * (E * E * E);     // 3*beta folds to 15
+  }
+  return R(0.0);
+}
+template <class R>
+void rpn2_psystem(int ixy, int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R> auxl, V2<R> auxr,
+                  V3<R> fwave, V2<R> s, V2<R> amdq, V2<R> apdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {                   // loop 10, :83-150
+    R pim = auxr(1, i - 1), pi = auxl(1, i), Eim = auxr(2, i - 1), Ei = auxl(2, i);
+    R epsi = ql(1, i), urhoi = ql(2, i), vrhoi = ql(3, i);
+    R epsim = qr(1, i - 1), urhoim = qr(2, i - 1), vrhoim = qr(3, i - 1);
+    const int lin_i = r_nint(auxl(3, i)), lin_im = r_nint(auxr(3, i - 1));
+    R sigmai = psystem_sigma(epsi, Ei, lin_i);
+    R sigmaim = psystem_sigma(epsim, Eim, lin_im);
+    R sigmapi = psystem_sigmap(epsi, Ei, lin_i);
+    R sigmapim = psystem_sigmap(epsim, Eim, lin_im);
+    R r11 = R(1.0) / r_sqrt(sigmapim * pim);                    // :106-107
+    R r13 = -(R(1.0) / r_sqrt(sigmapi * pi));
+    s(1, i) = -r_sqrt(sigmapim / pim);                          // :109-110
+    s(2, i) = r_sqrt(sigmapi / pi);
+    R dF1, dF2;
+    if (ixy == 1) dF1 = -(urhoi / pi - urhoim / pim);           // :114 / :129
+    else dF1 = -(vrhoi / pi - vrhoim / pim);
+    dF2 = -(sigmai - sigmaim);
+    R beta1 = (dF1 - r13 * dF2) / (r11 - r13);
+    R beta3 = (-dF1 + r11 * dF2) / (r11 - r13);
+    const int mu = (ixy == 1) ? 2 : 3, mv = (ixy == 1) ? 3 : 2;
+    fwave(1, 1, i) = beta1 * r11;
+    fwave(mu, 1, i) = beta1 * R(1.0);
+    fwave(mv, 1, i) = beta1 * R(0.0);
+    fwave(1, 2, i) = beta3 * r13;
+    fwave(mu, 2, i) = beta3 * R(1.0);
+    fwave(mv, 2, i) = beta3 * R(0.0);
+    for (int m = 1; m <= 3; ++m) { amdq(m, i) = fwave(m, 1, i); apdq(m, i) = fwave(m, 2, i); }   // :142-147
+  }
+}
+template <class R>
+void rpt2_psystem(int ixy, int imp, int, int, int, int, int mbc, int mx, V2<R>, V2<R>, V2<R> aux1, V2<R> aux2,
+                  V2<R> aux3, V2<R> asdq, V2<R> bmasdq, V2<R> bpasdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {                   // loop 10, :46-114
+    const int ix = (imp == 1) ? i - 1 : i;
+    R pjm = aux1(1, ix), pjp = aux3(1, ix);
+    R Ejm = aux1(2, ix), Ejp = aux3(2, ix);
+    const int lin_jm = r_nint(aux1(3, ix)), lin_jp = r_nint(aux3(3, ix));
+    R epsjm = aux1(4, ix), epsjp = aux3(4, ix);
+    R sigmapjm = psystem_sigmap(epsjm, Ejm, lin_jm);            // (sigmapj of the middle row is computed but unused)
+    R sigmapjp = psystem_sigmap(epsjp, Ejp, lin_jp);
+    (void)aux2;
+    R r11 = R(1.0) / r_sqrt(sigmapjm * pjm);
+    R r13 = -(R(1.0) / r_sqrt(sigmapjp * pjp));
+    R s1 = -r_sqrt(sigmapjm / pjm);
+    R s2 = r_sqrt(sigmapjp / pjp);
+    // the transverse momentum is component 3 for an x-sweep and 2 for a y-sweep (:86-87 / :100-101)
+    const int mt = (ixy == 1) ? 3 : 2, mn = (ixy == 1) ? 2 : 3;
+    R gamma1 = (asdq(1, i) - r13 * asdq(mt, i)) / (r11 - r13);
+    R gamma3 = (-asdq(1, i) + r11 * asdq(mt, i)) / (r11 - r13);
+    bmasdq(1, i) = s1 * gamma1 * r11;
+    bmasdq(mn, i) = s1 * gamma1 * R(0.0);
+    bmasdq(mt, i) = s1 * gamma1 * R(1.0);
+    bpasdq(1, i) = s2 * gamma3 * r13;
+    bpasdq(mn, i) = s2 * gamma3 * R(0.0);
+    bpasdq(mt, i) = s2 * gamma3 * R(1.0);
+  }
+}
+
 template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt) {
   switch (rp_id) {
     case RP_ADVECTION_2D: rpn = rpn2_advection<R>; rpt = rpt2_advection<R>; return true;
@@ -751,6 +839,7 @@ template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt)
     case RP_VC_ACOUSTICS_2D: rpn = rpn2_vc_acoustics<R>; rpt = rpt2_vc_acoustics<R>; return true;
     case RP_VC_ADVECTION_2D: rpn = rpn2_vc_advection<R>; rpt = rpt2_vc_advection<R>; return true;
     case RP_EULER_5WAVE_2D: rpn = rpn2_euler_5wave<R>; rpt = rpt2_euler_5wave<R>; return true;
+    case RP_PSYSTEM_2D: rpn = rpn2_psystem<R>; rpt = rpt2_psystem<R>; return true;
   }
   return false;
 }

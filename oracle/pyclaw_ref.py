@@ -28,6 +28,7 @@ RP_IDS = {
     'vc_acoustics_2D': 7,
     'vc_advection_2D': 8,
     'euler_5wave_2D': 9,
+    'psystem_2D': 10,
 }
 # COMMON /cparam/ member order of each solver (rpn2_advection.f90, rpn2_acoustics.f90:52,
 # rpn2_euler_4wave.f90:71, rpn2_shallow_roe_with_efix.f90:59; vc_acoustics_3D has none)
@@ -41,11 +42,14 @@ CPARAM_NAMES = {
     'vc_acoustics_2D': (),            # rpn2_vc_acoustics.f90: coefficients live in aux
     'vc_advection_2D': (),            # rpn2_vc_advection.f90: edge velocities live in aux
     'euler_5wave_2D': ('gamma',),     # rpn2_euler_5wave.f90:64
+    'psystem_2D': (),                 # rpn2_psystem.f90: coefficients live in aux
 }
 NUM_EQN = {'advection_2D': 1, 'acoustics_2D': 3, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
-           'vc_acoustics_3D': 4, 'euler_3D': 5, 'vc_acoustics_2D': 3, 'vc_advection_2D': 1, 'euler_5wave_2D': 5}
+           'vc_acoustics_3D': 4, 'euler_3D': 5, 'vc_acoustics_2D': 3, 'vc_advection_2D': 1, 'euler_5wave_2D': 5,
+           'psystem_2D': 3}
 NUM_WAVES = {'advection_2D': 1, 'acoustics_2D': 2, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
-             'vc_acoustics_3D': 2, 'euler_3D': 3, 'vc_acoustics_2D': 2, 'vc_advection_2D': 1, 'euler_5wave_2D': 5}
+             'vc_acoustics_3D': 2, 'euler_3D': 3, 'vc_acoustics_2D': 2, 'vc_advection_2D': 1, 'euler_5wave_2D': 5,
+             'psystem_2D': 2}
 
 BC_CUSTOM, BC_EXTRAP, BC_PERIODIC, BC_WALL = 0, 1, 2, 3
 
