@@ -134,6 +134,8 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
     case 7: return launch_aux<RpVcAcoustics2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 8: return launch_aux<RpVcAdvection2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 10: return launch_aux<RpPsystem2D, 2>(kind, P, seg_hint, num_sms, st, info);
+    case 11: return launch_one<RpEulerHlle2D, 128>(kind, P, seg_hint, num_sms, st, info);
+    case 12: return launch_one<RpShallowHlle2D, 128>(kind, P, seg_hint, num_sms, st, info);
   }
   return cudaErrorInvalidValue;
 }

@@ -17,6 +17,12 @@ def world_size():
     return d.get_world_size() if d else 1
 
 
+def barrier():
+    d = _dist()
+    if d is not None and world_size() > 1:
+        d.barrier()
+
+
 def slab_range(n, nranks, r):
     """Cells [start, stop) of the slowest dimension owned by rank r (balanced block partition, the
     same rule as PETSc's default DMDA split: the first n % nranks ranks get one extra cell)."""

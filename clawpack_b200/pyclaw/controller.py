@@ -1,8 +1,7 @@
 """Controller: the output-time loop around ``solver.evolve_to_time`` (pyclaw/src/pyclaw/controller.py:275-397).
 
-Kept thin: output styles 1-3, ``keep_copy`` frames, ``tfinal``, ``num_output_times``.  Frame file
-output (``output_format``) is outside this build's scope; the default here is ``None`` (no files),
-and any other value raises in ``Solution.write``."""
+Kept thin: output styles 1-3, ``keep_copy`` frames, ``tfinal``, ``num_output_times``, frame files through
+``Solution.write`` (``output_format='ascii'`` as in the reference, ``None`` for no files), gauge files."""
 import copy
 import logging
 
@@ -17,7 +16,7 @@ class Controller(object):
         self.frames = []
         self.write_aux_init = False
         self.write_aux_always = False
-        self.output_format = None
+        self.output_format = 'ascii'                     # controller.py:141
         self.output_file_prefix = None
         self.output_options = {}
         self.outdir = './_output'
@@ -55,7 +54,7 @@ class Controller(object):
             raise Exception('To run, a Controller must have a Solver and a Solution.')
         self.start_frame = self.solution.start_frame
         grid = self.solution.state.grid
-        if len(grid.gauges) > 0 and self.output_format is not None:     # controller.py:296-297 (files only with output)
+        if len(grid.gauges) > 0:                                         # controller.py:296-297
             grid.setup_gauge_files(self.outdir)
         if not self.solver._is_set_up:
             self.solver.setup(self.solution)

@@ -1,6 +1,9 @@
-"""Solution = states + domain (pyclaw/src/pyclaw/solution.py:17-253).  File I/O (write/read of
-frames) is outside this build's scope: ``write`` supports the
-reference's ascii layout only as far as the controller needs it and is otherwise a stub."""
+"""Solution = states + domain (pyclaw/src/pyclaw/solution.py:17-253), with ``write`` / ``read`` of frame files in
+the classic ascii layout (fileio/ascii.py; the hdf5 / netcdf / petsc formats of the reference need libraries
+outside this build)."""
+import logging
+import os
+
 from .geometry import Dimension, Domain, Patch
 
 
@@ -50,11 +53,19 @@ class Solution(object):
                 self.states.append(State(self.domain, st))
             if self.states == [] or self.domain is None:
                 raise Exception('Invalid arguments for Solution initialization.')
+        elif len(arg) == 1 and isinstance(arg[0], int):        # Solution(frame, path=..., file_format=...): solution.py:150-165
+            frame = arg[0]
+            if 'count_from_zero' in kargs and kargs['count_from_zero'] is True:
+                self._start_frame = 0
+            else:
+                self._start_frame = frame
+            kargs.pop('count_from_zero', None)
+            kargs.pop('claw_package', None)
+            self.read(frame, **kargs)
         elif len(arg) == 0 and not [k for k in kargs if k != 'claw_package']:
             pass
         else:
-            raise NotImplementedError('Reading a Solution from file is outside this build (frame I/O is host-side '
-                                      'and out of scope); construct it from a State and a Domain.')
+            raise Exception('Invalid arguments for Solution initialization.')
 
     def __getattr__(self, key):
         if key in Solution._state_attrs:
@@ -88,10 +99,44 @@ class Solution(object):
         result.domain = copy.deepcopy(self.domain)
         return result
 
+    # ---- frame files (solution.py:254-378) ------------------------------------------------------
+    def get_write_func(self, file_format):
+        if file_format == 'ascii':
+            from .fileio import ascii
+            return ascii.write
+        raise ValueError("File format '%s' is not part of this build (only 'ascii'; hdf5 / netcdf / petsc / vtk "
+                         "need libraries that are not available here)." % file_format)
+
+    def get_read_func(self, file_format):
+        if file_format == 'ascii':
+            from .fileio import ascii
+            return ascii.read
+        raise ValueError("File format '%s' cannot be read by this build (only 'ascii')." % file_format)
+
     def write(self, frame, path='./', file_format='ascii', file_prefix=None, write_aux=False, options={},
               write_p=False):
-        raise NotImplementedError('Solution.write: frame file I/O is outside this build (set '
-                                  'controller.output_format = None and use controller.frames / state.q).')
+        """Write frame `frame` in every requested format; state.q of a device-resident run is downloaded on access."""
+        path = os.path.expandvars(os.path.expanduser(path))
+        os.makedirs(path, exist_ok=True)
+        format_list = [file_format] if isinstance(file_format, str) else list(file_format)
+        for form in format_list:
+            write_func = self.get_write_func(form)
+            if file_prefix is None:
+                write_func(self, frame, path, write_aux=write_aux, options=options, write_p=write_p)
+            else:
+                write_func(self, frame, path, file_prefix=file_prefix, write_aux=write_aux, options=options,
+                           write_p=write_p)
+            logging.getLogger('pyclaw.fileio').info('Wrote out solution in format %s for time t=%s' % (form, self.t))
+
+    def read(self, frame, path='./_output', file_format=None, file_prefix='fort', read_aux=True, options={}, **kargs):
+        """Fill this (empty) Solution from the files of frame `frame`; the format is taken from the .t header when
+        not given (solution.py:301-378)."""
+        path = os.path.expandvars(os.path.expanduser(path))
+        if file_format is None:
+            from .fileio.ascii import read_t
+            file_format = read_t(frame, path, file_prefix)[6] or 'ascii'
+        self.get_read_func(file_format)(self, frame, path, file_prefix=file_prefix, read_aux=read_aux, options=options)
+        logging.getLogger('pyclaw.fileio').info('Read in solution for time t=%s' % self.t)
 
     def __str__(self):
         return 'states:\n' + ''.join(str(s) for s in self.states)

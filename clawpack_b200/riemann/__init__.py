@@ -16,6 +16,8 @@ _SOLVERS = {
     'vc_acoustics_2D': (7, (), 2),                            # rpn2_vc_acoustics.f90 (coefficients in aux)
     'euler_5wave_2D': (9, ('gamma',), 2),                     # rpn2_euler_5wave.f90:64
     'vc_advection_2D': (8, (), 2),                            # rpn2_vc_advection.f90 (edge velocities in aux)
+    'euler_hlle_2D': (11, ('gamma',), 2),                     # rpn2_euler_hlle.f90:32 (+ rpt2_dummy.f90)
+    'shallow_hlle_2D': (12, ('grav',), 2),                    # rpn2_shallow_hlle.f90:31 (+ rpt2_dummy.f90)
     'psystem_2D': (10, (), 2),                                # rpn2_psystem.f90 (f-wave; coefficients + strain in aux)
 }
 

@@ -36,7 +36,8 @@ def _base(rp, lower, upper, n, q, **kw):
              dimensional_split=True, transverse_waves=None, cfl_max=1.0, cfl_desired=0.9,
              dt_initial=0.1, bc_lower=None, bc_upper=None, aux_bc_lower=None, aux_bc_upper=None,
              tfinal=1.0, num_output_times=10, index_capa=-1, custom_aux_bc_lower=None, custom_aux_bc_upper=None,
-             mapc2p=None, step_source=None, source_split=1, before_step=None, fwave=False)
+             mapc2p=None, step_source=None, source_split=1, before_step=None, fwave=False, gauges=None,
+             compute_gauge_values=None)
     d.update(kw)
     return d
 
@@ -217,7 +218,59 @@ def shock_bubble_interaction(q0, tfinal=0.2, num_output_times=1, dimensional_spl
                  tfinal=tfinal, num_output_times=num_output_times)
 
 
-def quadrants(mx=100, my=100, tfinal=0.8):
+def psystem_2d(cells_per_layer=6, tfinal=1.0, num_output_times=10, stress_rel=2, dimensional_split=False,
+               transverse_waves=None, size=20.0):
+    """pyclaw/examples/psystem_2d/psystem_2d.py:126-226 (classic branch): nonlinear elasticity in a checkerboard
+    medium, f-wave solver psystem_2D, superbee, unsplit; aux = (density, modulus, stress-strain relation id, strain);
+    `before_step` copies q[0] into aux[3] for the transverse solver (:90-95); four gauges record the stress
+    (:121-123, :221-223).  `stress_rel`: 1 linear, 2 exponential (the example), 3 cubic."""
+    KA, KB, rhoA, rhoB = 1., 4., 1., 4.
+    lower, upper = (0.25, 0.25), (0.25 + size, 0.25 + size)
+    mx = int((upper[0] - lower[0]) * cells_per_layer)
+    my = int((upper[1] - lower[1]) * cells_per_layer)
+    x, y = centers(lower[0], upper[0], mx), centers(lower[1], upper[1], my)
+    alphax = alphay = 0.5
+    deltax = deltay = 1.
+    xfrac = x - np.floor(x / deltax) * deltax                  # setaux, checkerboard medium (:38-66)
+    yfrac = y - np.floor(y / deltay) * deltay
+    yf, xf = np.meshgrid(yfrac, xfrac)
+    aux = np.empty((4, mx, my), order='F')
+    a_ = (xf <= alphax * deltax) * (yf <= alphay * deltay)
+    b_ = (xf > alphax * deltax) * (yf > alphay * deltay)
+    c_ = (xf > alphax * deltax) * (yf <= alphay * deltay)
+    d_ = (xf <= alphax * deltax) * (yf > alphay * deltay)
+    aux[0] = rhoA * a_ + rhoA * b_ + rhoB * c_ + rhoB * d_
+    aux[1] = KA * a_ + KA * b_ + KB * c_ + KB * d_
+    aux[2] = stress_rel
+    aux[3] = 0.0
+    X, Y = _grid(lower, upper, (mx, my))
+    A, x0, y0, varx, vary = 10., 0.25, 0.25, 0.5, 0.5          # qinit (:27-36)
+    stress = A * np.exp(-(X - x0) ** 2 / (2 * varx) - (Y - y0) ** 2 / (2 * vary))
+    q = np.zeros((3, mx, my), order='F')
+    K = aux[1]
+    if stress_rel == 1:
+        q[0] = stress / K
+    elif stress_rel == 2:
+        q[0] = np.log(stress + 1) / K
+    else:                                                      # cubic law has no closed-form inverse: small-strain data
+        q[0] = 0.05 * stress / K
+
+    def b4step(q_, aux_):                                      # :90-95
+        aux_[3, :, :] = q_[0, :, :]
+
+    def gauge_stress(q_, aux_):                                # :121-123
+        p = np.exp(q_[0] * aux_[1]) - 1
+        return [p, 10 * p]
+
+    return _base('psystem_2D', lower, upper, (mx, my), q, aux=aux, limiters=SUPERBEE,
+                 dimensional_split=bool(dimensional_split), transverse_waves=transverse_waves,
+                 cfl_max=0.9, cfl_desired=0.8, bc_lower=[WALL, WALL], bc_upper=[EXTRAP, EXTRAP],
+                 aux_bc_lower=[WALL, WALL], aux_bc_upper=[EXTRAP, EXTRAP], fwave=True, before_step=b4step,
+                 tfinal=tfinal, num_output_times=num_output_times,
+                 gauges=[[0.25, 0.25], [17.85, 1.25], [3.25, 18.75], [11.75, 11.75]], compute_gauge_values=gauge_stress)
+
+
+def quadrants(mx=100, my=100, tfinal=0.8, riemann_solver='roe'):
     xx, yy = _grid((0., 0.), (1., 1.), (mx, my))
     gamma = 1.4
     l = xx < 0.8
@@ -232,18 +285,23 @@ def quadrants(mx=100, my=100, tfinal=0.8):
     q[1] = q[0] * u
     q[2] = q[0] * v
     q[3] = 0.5 * q[0] * (u ** 2 + v ** 2) + p / (gamma - 1.0)
+    if riemann_solver == 'hlle':                      # quadrants.py:82-86
+        return _base('euler_hlle_2D', (0., 0.), (1., 1.), (mx, my), q, problem_data={'gamma': gamma},
+                     limiters=MINMOD, dimensional_split=True, transverse_waves=0, cfl_desired=0.4, cfl_max=0.5,
+                     bc_lower=[EXTRAP, EXTRAP], bc_upper=[EXTRAP, EXTRAP], tfinal=tfinal)
     # quadrants.py sets transverse_waves=2 but leaves dimensional_split at its default True
     return _base('euler_4wave_2D', (0., 0.), (1., 1.), (mx, my), q, problem_data={'gamma': gamma},
                  limiters=MINMOD, dimensional_split=True, transverse_waves=2,
                  bc_lower=[EXTRAP, EXTRAP], bc_upper=[EXTRAP, EXTRAP], tfinal=tfinal)
 
 
-def radial_dam_break(mx=150, my=150, tfinal=2.5):
+def radial_dam_break(mx=150, my=150, tfinal=2.5, riemann_solver='roe'):
     X, Y = _grid((-2.5, -2.5), (2.5, 2.5), (mx, my))
     r = np.sqrt((X - 0.) ** 2 + (Y - 0.) ** 2)
     q = np.zeros((3, mx, my), order='F')
     q[0] = 2. * (r <= 0.5) + 1. * (r > 0.5)
-    return _base('shallow_roe_with_efix_2D', (-2.5, -2.5), (2.5, 2.5), (mx, my), q,
+    rp = 'shallow_hlle_2D' if riemann_solver == 'hlle' else 'shallow_roe_with_efix_2D'     # radial_dam_break.py:41-44
+    return _base(rp, (-2.5, -2.5), (2.5, 2.5), (mx, my), q,
                  problem_data={'grav': 1.0}, limiters=MC, dimensional_split=True,
                  bc_lower=[EXTRAP, EXTRAP], bc_upper=[WALL, WALL], tfinal=tfinal)
 
@@ -409,6 +467,8 @@ def make_claw(sc, kernel_language='CUDA', pyclaw=None, **solver_kw):
         solver.before_step = lambda solver_, state: fb(state.q, state.aux)
     if sc.get('fwave'):
         solver.fwave = True
+    if sc.get('compute_gauge_values') is not None:
+        solver.compute_gauge_values = sc['compute_gauge_values']
     for k, v in solver_kw.items():
         setattr(solver, k, v)
     names = ['x', 'y', 'z'][:ndim]
@@ -424,7 +484,11 @@ def make_claw(sc, kernel_language='CUDA', pyclaw=None, **solver_kw):
         state.aux[...] = sc['aux']
     state.index_capa = sc.get('index_capa', -1)
     state.problem_data.update(sc['problem_data'])
+    if sc.get('gauges'):
+        state.grid.add_gauges(sc['gauges'])
+        state.keep_gauges = True
     claw = pyclaw.Controller()
+    claw.output_format = None          # no frame files unless the caller asks (the reference tests pass disable_output)
     claw.tfinal = sc['tfinal']
     claw.num_output_times = sc['num_output_times']
     claw.solution = pyclaw.Solution(state, domain)

@@ -49,7 +49,9 @@ enum {
   CLAW_RP_VC_ACOUSTICS_2D = 7,         /* rpn2_vc_acoustics.f90, rpt2_vc_acoustics.f90 (aux: density, sound speed) */
   CLAW_RP_VC_ADVECTION_2D = 8,         /* rpn2_vc_advection.f90, rpt2_vc_advection.f90 (aux: edge velocities) */
   CLAW_RP_EULER_5WAVE_2D = 9,          /* rpn2_euler_5wave.f90, rpt2_euler_5wave.f90 (Euler + tracer) */
-  CLAW_RP_PSYSTEM_2D = 10              /* rpn2_psystem.f90, rpt2_psystem.f90 (f-wave; aux: density, modulus, relation id, strain) */
+  CLAW_RP_PSYSTEM_2D = 10,             /* rpn2_psystem.f90, rpt2_psystem.f90 (f-wave; aux: density, modulus, relation id, strain) */
+  CLAW_RP_EULER_HLLE_2D = 11,          /* rpn2_euler_hlle.f90 + rpt2_dummy.f90 (no transverse solver) */
+  CLAW_RP_SHALLOW_HLLE_2D = 12         /* rpn2_shallow_hlle.f90 + rpt2_dummy.f90 (no transverse solver) */
 };
 
 /* Boundary-condition ids = pyclaw.BC (pyclaw/src/pyclaw/solver.py:13-19) */

@@ -73,6 +73,8 @@ enum RpId {
   RP_VC_ADVECTION_2D = 8,
   RP_EULER_5WAVE_2D = 9,
   RP_PSYSTEM_2D = 10,
+  RP_EULER_HLLE_2D = 11,
+  RP_SHALLOW_HLLE_2D = 12,
 };
 
 // =====================================================================
@@ -830,6 +832,124 @@ void rpt2_psystem(int ixy, int imp, int, int, int, int, int mbc, int mx, V2<R>, 
   }
 }
 
+// =====================================================================
+// euler_hlle_2D -- riemann/src/rpn2_euler_hlle.f90:40-114 (+ rpt2_dummy.f90)        cparam = (gamma)
+// two-wave HLLE solver.  Kept as written: H_r uses p_l (:60), c_l/c_r use gamma1*H - u**2/2 (:62-63).
+// =====================================================================
+template <class R>
+void rpn2_euler_hlle(int ixy, int, int meqn, int mwaves, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>,
+                     V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double* cparam) {
+  const R gamma = R(cparam[0]);
+  const R gamma1 = gamma - R(1.0);
+  const int rho = 1, E = 4;
+  int mu, mv;
+  if (ixy == 1) { mu = 2; mv = 3; } else { mu = 3; mv = 2; }
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R u_l = qr(mu, i - 1) / qr(rho, i - 1);
+    R u_r = ql(mu, i) / ql(rho, i);
+    R v_l = qr(mv, i - 1) / qr(rho, i - 1);
+    R v_r = ql(mv, i) / ql(rho, i);
+    R p_l = gamma1 * (qr(E, i - 1) - qr(rho, i - 1) * (u_l * u_l + v_l * v_l) / R(2.0));
+    R p_r = gamma1 * (ql(E, i) - ql(rho, i) * (u_r * u_r + v_r * v_r) / R(2.0));
+    R H_l = (qr(E, i - 1) + p_l) / qr(rho, i - 1);
+    R H_r = (ql(E, i) + p_l) / ql(rho, i);                               // p_l, as in the reference (:60)
+    R c_l = r_sqrt(gamma1 * H_l - u_l * u_l / R(2.0));
+    R c_r = r_sqrt(gamma1 * H_r - u_r * u_r / R(2.0));
+    R E_l = qr(E, i - 1), E_r = ql(E, i);
+    R rhsqrt_l = r_sqrt(qr(rho, i - 1));
+    R rhsqrt_r = r_sqrt(ql(rho, i));
+    R rhsq2 = rhsqrt_l + rhsqrt_r;
+    R u_hat = (qr(mu, i - 1) / rhsqrt_l + ql(mu, i) / rhsqrt_r) / rhsq2;
+    R v_hat = (qr(mv, i - 1) / rhsqrt_l + ql(mv, i) / rhsqrt_r) / rhsq2;
+    R H_hat = (((qr(E, i - 1) + p_l) / rhsqrt_l + (ql(E, i) + p_r) / rhsqrt_r)) / rhsq2;
+    R c_hat = r_sqrt(gamma1 * (H_hat - R(0.5) * (u_hat * u_hat + v_hat * v_hat)));
+    R s1 = r_min(u_l - c_l, u_hat - c_hat);
+    R s2 = r_max(u_r + c_r, u_hat + c_hat);
+    R rho_m = (ql(mu, i) - qr(mu, i - 1) - s2 * ql(rho, i) + s1 * qr(rho, i - 1)) / (s1 - s2);
+    R rhou_m = (ql(rho, i) * (u_r * u_r) - qr(rho, i - 1) * (u_l * u_l) + p_r - p_l - s2 * ql(mu, i)
+                + s1 * qr(mu, i - 1)) / (s1 - s2);
+    R rhov_m = (ql(mv, i) * u_r - qr(mv, i - 1) * u_l - s2 * ql(mv, i) + s1 * qr(mv, i - 1)) / (s1 - s2);
+    R E_m = (u_r * (E_r + p_r) - u_l * (E_l + p_l) - s2 * E_r + s1 * E_l) / (s1 - s2);
+    wave(rho, 1, i) = rho_m - qr(rho, i - 1);
+    wave(mu, 1, i) = rhou_m - qr(mu, i - 1);
+    wave(mv, 1, i) = rhov_m - qr(mv, i - 1);
+    wave(E, 1, i) = E_m - qr(E, i - 1);
+    s(1, i) = s1;
+    wave(rho, 2, i) = ql(rho, i) - rho_m;
+    wave(mu, 2, i) = ql(mu, i) - rhou_m;
+    wave(mv, 2, i) = ql(mv, i) - rhov_m;
+    wave(E, 2, i) = ql(E, i) - E_m;
+    s(2, i) = s2;
+  }
+  for (int m = 1; m <= meqn; ++m)                                        // :101-112
+    for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+      amdq(m, i) = R(0.0); apdq(m, i) = R(0.0);
+      for (int mw = 1; mw <= mwaves; ++mw) {
+        if (s(mw, i) < R(0.0)) amdq(m, i) = amdq(m, i) + s(mw, i) * wave(m, mw, i);
+        else apdq(m, i) = apdq(m, i) + s(mw, i) * wave(m, mw, i);
+      }
+    }
+}
+
+// =====================================================================
+// shallow_hlle_2D -- riemann/src/rpn2_shallow_hlle.f90:35-100 (+ rpt2_dummy.f90)    cparam = (grav)
+// =====================================================================
+template <class R>
+void rpn2_shallow_hlle(int ixy, int, int meqn, int mwaves, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>,
+                       V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double* cparam) {
+  const R grav = R(cparam[0]);
+  const int depth = 1;
+  int mu, mv;
+  if (ixy == 1) { mu = 2; mv = 3; } else { mu = 3; mv = 2; }
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R h_l = qr(depth, i - 1), h_r = ql(depth, i);
+    R u_l = qr(mu, i - 1) / qr(depth, i - 1);
+    R u_r = ql(mu, i) / ql(depth, i);
+    R v_l = qr(mv, i - 1) / qr(depth, i - 1);
+    R v_r = ql(mv, i) / ql(depth, i);
+    R c_l = r_sqrt(grav * h_l);
+    R c_r = r_sqrt(grav * h_r);
+    R hsqrt_l = r_sqrt(qr(depth, i - 1));
+    R hsqrt_r = r_sqrt(ql(depth, i));
+    R hsq2 = hsqrt_l + hsqrt_r;
+    R h_hat = R(0.5) * (h_l + h_r);
+    R u_hat = (u_l * hsqrt_l + u_r * hsqrt_r) / hsq2;
+    R v_hat = (v_l * hsqrt_l + v_r * hsqrt_r) / hsq2;
+    (void)v_hat;
+    R c_hat = r_sqrt(grav * h_hat);
+    R s1 = r_min(u_l - c_l, u_hat - c_hat);
+    R s2 = r_max(u_r + c_r, u_hat + c_hat);
+    R h_m = (ql(mu, i) - qr(mu, i - 1) - s2 * ql(depth, i) + s1 * qr(depth, i - 1)) / (s1 - s2);
+    R hu_m = (ql(mu, i) * (u_r - s2) - qr(mu, i - 1) * (u_l - s1) + R(0.5) * grav * (h_r * h_r - h_l * h_l)) / (s1 - s2);
+    R hv_m = (ql(mv, i) * u_r - qr(mv, i - 1) * u_l - s2 * ql(mv, i) + s1 * qr(mv, i - 1)) / (s1 - s2);
+    wave(depth, 1, i) = h_m - h_l;
+    wave(mu, 1, i) = hu_m - qr(mu, i - 1);
+    wave(mv, 1, i) = hv_m - qr(mv, i - 1);
+    s(1, i) = s1;
+    wave(depth, 2, i) = h_r - h_m;
+    wave(mu, 2, i) = ql(mu, i) - hu_m;
+    wave(mv, 2, i) = ql(mv, i) - hv_m;
+    s(2, i) = s2;
+  }
+  for (int m = 1; m <= meqn; ++m)                                        // :87-98
+    for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+      amdq(m, i) = R(0.0); apdq(m, i) = R(0.0);
+      for (int mw = 1; mw <= mwaves; ++mw) {
+        if (s(mw, i) < R(0.0)) amdq(m, i) = amdq(m, i) + s(mw, i) * wave(m, mw, i);
+        else apdq(m, i) = apdq(m, i) + s(mw, i) * wave(m, mw, i);
+      }
+    }
+}
+
+// rpt2_dummy.f90: prints an error and leaves its outputs unset; only legal with method(3) <= 0.  The oracle returns
+// zeros and step2/step2ds refuse transverse modes for these solvers (select_rp2 sets `dummy_rpt`).
+template <class R>
+void rpt2_dummy(int, int, int, int meqn, int, int, int mbc, int mx, V2<R>, V2<R>, V2<R>, V2<R>, V2<R>, V2<R>,
+                V2<R> bmasdq, V2<R> bpasdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i)
+    for (int m = 1; m <= meqn; ++m) { bmasdq(m, i) = R(0.0); bpasdq(m, i) = R(0.0); }
+}
+
 template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt) {
   switch (rp_id) {
     case RP_ADVECTION_2D: rpn = rpn2_advection<R>; rpt = rpt2_advection<R>; return true;
@@ -840,6 +960,8 @@ template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt)
     case RP_VC_ADVECTION_2D: rpn = rpn2_vc_advection<R>; rpt = rpt2_vc_advection<R>; return true;
     case RP_EULER_5WAVE_2D: rpn = rpn2_euler_5wave<R>; rpt = rpt2_euler_5wave<R>; return true;
     case RP_PSYSTEM_2D: rpn = rpn2_psystem<R>; rpt = rpt2_psystem<R>; return true;
+    case RP_EULER_HLLE_2D: rpn = rpn2_euler_hlle<R>; rpt = rpt2_dummy<R>; return true;
+    case RP_SHALLOW_HLLE_2D: rpn = rpn2_shallow_hlle<R>; rpt = rpt2_dummy<R>; return true;
   }
   return false;
 }
@@ -1040,6 +1162,8 @@ int step2(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int 
           bool use_fwave, int rp_id, const double* cparam, int nthreads) {
   Rpn2<R> rpn2; Rpt2<R> rpt2;
   if (!select_rp2<R>(rp_id, rpn2, rpt2)) return 1;
+  // rpt2_dummy.f90 ("Error: Dummy transverse Riemann solver called!") leaves its outputs unset: refuse instead
+  if ((rp_id == RP_EULER_HLLE_2D || rp_id == RP_SHALLOW_HLLE_2D) && method[2] > 0) return 2;
   if (maxm < mx || maxm < my) return 2;
   const int nx = mx + 2 * num_ghost;
   const int maux_eff = method[6];                       // step2.f90:75  num_aux = method(7)

@@ -29,6 +29,8 @@ RP_IDS = {
     'vc_advection_2D': 8,
     'euler_5wave_2D': 9,
     'psystem_2D': 10,
+    'euler_hlle_2D': 11,
+    'shallow_hlle_2D': 12,
 }
 # COMMON /cparam/ member order of each solver (rpn2_advection.f90, rpn2_acoustics.f90:52,
 # rpn2_euler_4wave.f90:71, rpn2_shallow_roe_with_efix.f90:59; vc_acoustics_3D has none)
@@ -43,13 +45,15 @@ CPARAM_NAMES = {
     'vc_advection_2D': (),            # rpn2_vc_advection.f90: edge velocities live in aux
     'euler_5wave_2D': ('gamma',),     # rpn2_euler_5wave.f90:64
     'psystem_2D': (),                 # rpn2_psystem.f90: coefficients live in aux
+    'euler_hlle_2D': ('gamma',),      # rpn2_euler_hlle.f90:32
+    'shallow_hlle_2D': ('grav',),     # rpn2_shallow_hlle.f90:31
 }
 NUM_EQN = {'advection_2D': 1, 'acoustics_2D': 3, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
            'vc_acoustics_3D': 4, 'euler_3D': 5, 'vc_acoustics_2D': 3, 'vc_advection_2D': 1, 'euler_5wave_2D': 5,
-           'psystem_2D': 3}
+           'psystem_2D': 3, 'euler_hlle_2D': 4, 'shallow_hlle_2D': 3}
 NUM_WAVES = {'advection_2D': 1, 'acoustics_2D': 2, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
              'vc_acoustics_3D': 2, 'euler_3D': 3, 'vc_acoustics_2D': 2, 'vc_advection_2D': 1, 'euler_5wave_2D': 5,
-             'psystem_2D': 2}
+             'psystem_2D': 2, 'euler_hlle_2D': 2, 'shallow_hlle_2D': 2}
 
 BC_CUSTOM, BC_EXTRAP, BC_PERIODIC, BC_WALL = 0, 1, 2, 3
 
@@ -184,6 +188,9 @@ class RefSolver(object):
         self.step_source = None             # f(q, aux, dt): in-place source step on the interior q (classic/solver.py:126-144)
         self.source_split = 1
         self.before_step = None             # f(q, aux): solver.py:609-610
+        self.gauges = []                    # interior cell index tuples (geometry.py:392-405)
+        self.compute_gauge_values = lambda q, aux: q      # solver.py:22-26
+        self.gauge_data = []                # per gauge: rows (t, p...) (solver.py:680-708)
         self.user_aux_bc_lower = None       # f(idim, auxbc, num_ghost): BC.custom fill of aux
         self.user_aux_bc_upper = None
         self.nthreads = 1
@@ -350,6 +357,7 @@ class RefSolver(object):
                     self.t += self.dt
                 else:
                     self.t = tstart + (n + 1) * self.dt
+                self.write_gauge_values()                                    # solver.py:636
                 num_steps += 1
                 self.status['numsteps'] += 1
             else:
@@ -368,8 +376,22 @@ class RefSolver(object):
                 raise Exception('Maximum number of timesteps have been taken')
         return self.status
 
+    # -- gauges: solver.py:680-708 (keep_gauges branch) ------------------------------------------
+    def write_gauge_values(self):
+        for i, g in enumerate(self.gauges):
+            ix = (slice(None),) + tuple(g)
+            p = self.compute_gauge_values(self.q[ix], self.aux[ix] if self.aux is not None else None)
+            if not hasattr(p, '__iter__'):
+                p = [p]
+            row = np.append(self.t, p)
+            if len(self.gauge_data) == len(self.gauges):
+                self.gauge_data[i] = np.vstack((self.gauge_data[i], row))
+            else:
+                self.gauge_data.append(row)
+
     # -- Controller.run, output_style 1: controller.py:336-359 ---------------------------------
     def run(self, tfinal, num_output_times=10, keep_frames=False):
+        self.write_gauge_values()                                            # controller.py:308-309
         frames = [self.q.copy('F')] if keep_frames else None
         for t in np.linspace(self.t, tfinal, num_output_times + 1)[1:]:
             self.evolve_to_time(t)

@@ -38,6 +38,10 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     sc = CASES[case]()
     claw = petclaw.make_claw_distributed(sc, kernel_language='Fortran', fmod=OracleFmod())
+    outdir = os.environ.get('CLAW_TEST_OUTDIR')
+    if outdir:                                     # frame files: gathered on rank 0, serial ascii layout
+        claw.output_format = 'ascii'
+        claw.outdir = outdir
     claw.run()
     q = claw.solution.state.get_q_global()
     log = claw.solver.step_log
@@ -50,6 +54,13 @@ def main():
         print('case %s world %d: q bit-identical to serial: %s, step log identical: %s (%d steps, %d rejected)'
               % (case, world, same_q, same_log, len(log), sum(1 for s in log if not s[2])))
         ok = same_q and same_log
+        if outdir:
+            from clawpack_b200 import pyclaw
+            back = pyclaw.Solution(sc['num_output_times'], path=outdir)
+            same_file = (back.state.q.shape == r.q.shape and
+                         np.max(np.abs(back.state.q - r.q)) <= 5e-9 * max(1.0, np.max(np.abs(r.q))))
+            print('frame file of the gathered solution matches the serial result: %s' % same_file)
+            ok = ok and same_file
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -13,6 +13,9 @@ d = np.load(os.path.join(REF, 'advection_2d_annulus/expected_sols.npy'), allow_p
 out['advection_annulus__classic'] = np.asarray(d['classic'], dtype=np.float64)
 d = np.load(os.path.join(REF, 'euler_2d/expected_sols.npy'), allow_pickle=True).item()
 out['euler_2d__shock_bubble_interaction'] = np.asarray(d['shock_bubble_interaction'], dtype=np.float64)
+out['euler_2d__quadrants_hlle'] = np.asarray(d['quadrants_hlle'], dtype=np.float64)
+d = np.load(os.path.join(REF, 'shallow_2d/expected_sols.npy'), allow_pickle=True).item()
+out['shallow_2d__radialdambreak_classic_hlle'] = np.asarray(d['radialdambreak_classic_hlle'], dtype=np.float64)
 for g in ('0.25_0.25', '11.75_11.75', '17.85_1.25', '3.25_18.75'):
     out['psystem_2d__gauge' + g] = np.loadtxt(os.path.join(REF, 'psystem_2d/verify_gauge%s.txt' % g))
 

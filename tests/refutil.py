@@ -45,6 +45,12 @@ def ref_solver(sc, nthreads=1):
         s.before_step = sc['before_step']
     if sc.get('fwave'):
         s.fwave = True
+    if sc.get('gauges'):
+        s.gauges = [[int((g[n] - sc['lower'][n]) // ((sc['upper'][n] - sc['lower'][n]) / float(sc['num_cells'][n])))
+                     for n in range(ndim)] for g in sc['gauges']
+                    if all(sc['lower'][n] <= g[n] < sc['upper'][n] for n in range(ndim))]   # geometry.py:398
+        if sc.get('compute_gauge_values') is not None:
+            s.compute_gauge_values = sc['compute_gauge_values']
     s.nthreads = nthreads
     delta = [(u - l) / float(n) for l, u, n in zip(sc['lower'], sc['upper'], sc['num_cells'])]
     s.setup(sc['q'], sc['aux'], delta)

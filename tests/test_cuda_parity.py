@@ -37,6 +37,9 @@ CASES = {
     'shallow_split': lambda: S.radial_dam_break(mx=150, my=150),
     'shallow_unsplit_cor': lambda: dict(S.radial_dam_break(mx=64, my=50), dimensional_split=False, transverse_waves=2),
     'euler_first_order': lambda: dict(S.quadrants(mx=48, my=48), order=1, dimensional_split=False, transverse_waves=1),
+    'euler_hlle_split': lambda: S.quadrants(mx=70, my=50, riemann_solver='hlle'),
+    'euler_hlle_unsplit_notrans': lambda: dict(S.quadrants(mx=40, my=66, riemann_solver='hlle'), dimensional_split=False),
+    'shallow_hlle_split': lambda: S.radial_dam_break(mx=60, my=45, riemann_solver='hlle'),
     'euler_tiny': lambda: dict(S.quadrants(mx=3, my=2), dimensional_split=False, transverse_waves=2),
     'euler_wide_strip_edge': lambda: dict(S.quadrants(mx=249, my=9), dimensional_split=False, transverse_waves=2),
 }

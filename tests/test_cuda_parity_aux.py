@@ -48,6 +48,17 @@ CASES.update({
 })
 
 
+CASES.update({
+    # psystem_2D (f-wave, 4 aux planes, before_step -> plug-in mode); relations 1 (linear) and 3 (cubic) are
+    # exp-free and therefore bit-exact; the example's exponential relation is compared with a tolerance below
+    'psystem_linear': lambda: S.psystem_2d(cells_per_layer=3, stress_rel=1, size=10.0),
+    'psystem_cubic_inc': lambda: S.psystem_2d(cells_per_layer=4, stress_rel=3, size=7.0, transverse_waves=1),
+    'psystem_linear_split': lambda: S.psystem_2d(cells_per_layer=3, stress_rel=1, size=9.0, dimensional_split=True),
+    # ... and device-resident (no before_step: the strain plane of aux keeps its initial zeros)
+    'psystem_linear_resident': lambda: dict(S.psystem_2d(cells_per_layer=3, stress_rel=1, size=10.0), before_step=None),
+})
+
+
 @pytest.mark.parametrize('name', sorted(CASES))
 def test_strict_bit_exact_vs_oracle(name):
     sc = CASES[name]()
@@ -115,3 +126,44 @@ def test_shock_bubble_interaction_golden(precision):
     expected = goldens2()['euler_2d__shock_bubble_interaction']
     assert dx * dy * np.sum(np.abs(rho - expected)) < 1e-6
     assert np.max(np.abs(rho - expected)) < (1e-11 if precision == 'strict' else 1e-8)
+
+
+@pytest.mark.parametrize('precision', ['strict', 'fast'])
+def test_psystem_exponential_within_tolerance(precision):
+    """The example's exponential stress-strain relation goes through exp(): CUDA's and glibc's results may differ in
+    the last bit, so both arithmetic modes are held to the north-star tolerance (1e-12 per step), with identical
+    accept/reject sequences."""
+    sc = S.psystem_2d(cells_per_layer=4, size=10.0)
+    q, log, _ = _run_cuda(sc, 3, precision)
+    qr, logr = _run_ref(sc, 3)
+    assert [s[2] for s in log] == [s[2] for s in logr]
+    assert _rel_linf(q, qr) <= 3e-12
+
+
+@pytest.mark.parametrize('resident', [False, True])
+def test_psystem_2d_gauges_golden(resident, tmp_path):
+    """pyclaw/examples/psystem_2d/test_2d_psystem.py:9-25: the four gauge records, in memory and in the gauge files,
+    against the reference's stored files (np.allclose there; 12 stored digits) -- plug-in mode, because of the
+    before_step callback.  `resident` drops the callback to put the same run on the device-resident path, where the
+    gauge cells are read through claw_get_cells: the last record must equal the downloaded final state."""
+    sc = S.psystem_2d()
+    if resident:
+        sc['before_step'] = None
+    claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision='strict')
+    claw.outdir = str(tmp_path)
+    claw.output_format = None
+    claw.run()
+    state = claw.solution.state
+    assert (claw.solver._dev is not None) == resident
+    if resident:
+        # last record of every gauge == the downloaded final state at the gauge cell
+        for i, g in enumerate(state.grid.gauges):
+            p = sc['compute_gauge_values'](state.q[:, g[0], g[1]], state.aux[:, g[0], g[1]])
+            assert np.array_equal(state.gauge_data[i][-1, 1:], np.asarray(p))
+            assert state.gauge_data[i][-1, 0] == claw.solution.t
+        return
+    g2 = goldens2()
+    for i, name in enumerate(('0.25_0.25', '17.85_1.25', '3.25_18.75', '11.75_11.75')):
+        gold = g2['psystem_2d__gauge' + name]
+        assert state.gauge_data[i].shape == gold.shape
+        assert np.allclose(gold, state.gauge_data[i], rtol=1e-9, atol=1e-12)

@@ -11,10 +11,12 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _launch(case, world, port):
+def _launch(case, world, port, outdir=None):
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), OMP_NUM_THREADS='1')
+        if outdir:
+            env['CLAW_TEST_OUTDIR'] = outdir
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, 'dist_worker.py'), case, str(port)],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []
@@ -44,3 +46,13 @@ def test_slab_decomposition_matches_serial(case, world, port, oracle_lib):
     codes, outs = _launch(case, world, port)
     assert codes == [0] * world, '\n'.join(outs)
     assert 'q bit-identical to serial: True, step log identical: True' in outs[0], outs[0]
+
+
+def test_distributed_frame_output(oracle_lib, tmp_path):
+    """Solution.write on a slab-decomposed run (the replacement of petclaw/fileio + get_q_global,
+    petclaw/state.py:267-287): slabs gathered, rank 0 writes the serial ascii layout of the GLOBAL grid."""
+    out = str(tmp_path / 'frames')
+    codes, outs = _launch('shallow_split_wall', 2, 29621, outdir=out)
+    assert codes == [0, 0], '\n'.join(outs)
+    assert 'frame file of the gathered solution matches the serial result: True' in outs[0], outs[0]
+    assert sorted(f for f in os.listdir(out) if f.startswith('fort.q')) == ['fort.q0000', 'fort.q0001', 'fort.q0002']

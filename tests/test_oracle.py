@@ -203,3 +203,53 @@ def test_shock_bubble_interaction_golden(oracle_lib):
     dx, dy = s.delta
     assert dx * dy * np.sum(np.abs(s.q[0].reshape(-1) - g)) < 1e-6
     assert np.max(np.abs(s.q[0].reshape(-1) - g)) < 1e-12
+
+
+PSYSTEM_GAUGES = ('0.25_0.25', '17.85_1.25', '3.25_18.75', '11.75_11.75')
+
+
+def test_psystem_2d_gauges_golden(oracle_lib):
+    # pyclaw/examples/psystem_2d/test_2d_psystem.py:9-25 (np.allclose on four gauge records, 120x120, tfinal 1):
+    # pins rpn2_psystem / rpt2_psystem, the f-wave branch of flux2 (:148-160), step2 with method(3)=2 and four aux
+    # planes, before_step, wall BCs on q and aux, the gauge logic and -- through the time column of every record --
+    # the whole accepted-step sequence.  The stored files carry 12 significant digits.
+    sc = S.psystem_2d()
+    s = ref_solver(sc)
+    s.run(sc['tfinal'], sc['num_output_times'])
+    g2 = goldens2()
+    for i, name in enumerate(PSYSTEM_GAUGES):
+        gold = g2['psystem_2d__gauge' + name]
+        assert s.gauge_data[i].shape == gold.shape
+        assert np.allclose(gold, s.gauge_data[i], rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize('stress_rel', [1, 3])
+def test_psystem_other_materials_conserve_momentum_free_state(oracle_lib, stress_rel):
+    # linear / cubic stress-strain relations (rpn2_psystem.f90:163-171) are not run by any reference test:
+    # sanity only -- the solution stays finite and the strain pulse spreads (its maximum decays)
+    sc = S.psystem_2d(cells_per_layer=3, tfinal=0.5, num_output_times=1, stress_rel=stress_rel, size=8.0)
+    s = ref_solver(sc)
+    m0 = np.max(sc['q'][0])
+    s.run(sc['tfinal'], sc['num_output_times'])
+    assert np.all(np.isfinite(s.q)) and np.max(s.q[0]) < m0
+
+
+def test_hlle_goldens(oracle_lib):
+    # pyclaw/examples/euler_2d/test_euler2d.py:29-30 (L1 < 1e-6) and shallow_2d/test_shallow2d.py:25-34 (L1 < 1e-5):
+    # pin rpn2_euler_hlle / rpn2_shallow_hlle with step2ds (their rpt2 is rpt2_dummy: no transverse solves)
+    g2 = goldens2()
+    for sc, key in ((S.quadrants(riemann_solver='hlle'), 'euler_2d__quadrants_hlle'),
+                    (S.radial_dam_break(riemann_solver='hlle'), 'shallow_2d__radialdambreak_classic_hlle')):
+        s = ref_solver(sc, nthreads=4)
+        s.run(sc['tfinal'], sc['num_output_times'])
+        dx, dy = s.delta
+        assert dx * dy * np.sum(np.abs(s.q[0].reshape(-1) - g2[key])) < 1e-6
+        assert np.max(np.abs(s.q[0].reshape(-1) - g2[key])) < 1e-11
+
+
+def test_dummy_transverse_solver_is_refused(oracle_lib):
+    # rpt2_dummy.f90 only prints an error and leaves its outputs unset: an unsplit step with transverse waves is refused
+    sc = dict(S.quadrants(mx=10, my=10, riemann_solver='hlle'), dimensional_split=False, transverse_waves=1)
+    s = ref_solver(sc)
+    with pytest.raises(Exception):
+        s.evolve_to_time()
