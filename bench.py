@@ -276,7 +276,8 @@ def main():
             'achieved': flops_per_s / 1e12, 'peak': 2.0 * peak.value / 1e3, 'unit': 'TFLOP/s',
             'frac': flops_per_s / 1e9 / (2.0 * peak.value),
             'traffic': ncu.get('dram_bytes_per_launch'),
-            'kernel': ('sweep2_unsplit_ws<RpEuler4Wave2D,1 warp/CTA,12 CTAs/SM,MC|spec> (%s)' % args.precision)
+            'kernel': ('sweep2_unsplit_ws<RpEuler4Wave2D,1 warp/CTA,%d CTAs/SM,MC|spec|cp.async row prefetch> (%s)'
+                       % (linfo[4], args.precision))
                       if linfo[2] == 32 else 'sweep2_unsplit<RpEuler4Wave2D,%d> (%s)' % (linfo[2], args.precision),
             'kernel_ms': sweep_ms,
             'launch': {'grid': [linfo[0], linfo[1]], 'block': linfo[2], 'smem_bytes': linfo[3],
