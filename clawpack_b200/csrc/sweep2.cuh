@@ -59,7 +59,11 @@ namespace CLAW_NS {
 
 __device__ __forceinline__ double philim(double a, double b, int meth) {
   // philim.f90:14-35
+#ifdef CLAW_STRICT
   const double r = ddiv(b, a);
+#else
+  const double r = b * rcp_fast(a);              // fast mode: ~2 ulp instead of the correctly rounded quotient
+#endif
   switch (meth) {
     case 1: return fmax2(0.0, fmin2(1.0, r));
     case 2: return fmax2(fmax2(0.0, fmin2(1.0, 2.0 * r)), fmin2(2.0, r));
@@ -134,6 +138,31 @@ __device__ __forceinline__ void second_order(double dtd, const double (*wave)[RP
       const double t = fabs(s[mw]) * (1.0 - fabs(s[mw]) * dtdxave) * wave[mw][m];
       c = (mw == 0) ? from0(t) : c + t;
     }
+    cqxx[m] = c;
+  }
+}
+
+// Fast mode only: limiter.f90:39-50 + flux2.f90:134-146 fused.  After the limiter the waves are used by nothing but
+// cqxx, so phi is folded into the per-family coefficient |s|(1 - |s| dtdx) instead of rescaling MEQN components of
+// every wave (W multiplies instead of W*MEQN; the products are associated differently than in the reference).
+template <class RP, int LIM>
+__device__ __forceinline__ void limited_second_order(const Sweep2Params& P, double dtd, const double (*wave)[RP::MEQN],
+                                                     const double* s, const double* wnorm2, const double* dotl,
+                                                     const double* dotr, double* cqxx) {
+  double coef[RP::MWAVES];
+#pragma unroll
+  for (int mw = 0; mw < RP::MWAVES; ++mw) {
+    const double as = fabs(s[mw]);
+    double c = as * (1.0 - as * dtd);
+    const int meth = LIM ? LIM : P.mthlim[mw];
+    if (meth != 0 && wnorm2[mw] != 0.0) c *= philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
+    coef[mw] = c;
+  }
+#pragma unroll
+  for (int m = 0; m < RP::MEQN; ++m) {
+    double c = coef[0] * wave[0][m];
+#pragma unroll
+    for (int mw = 1; mw < RP::MWAVES; ++mw) c = fma(coef[mw], wave[mw][m], c);
     cqxx[m] = c;
   }
 }

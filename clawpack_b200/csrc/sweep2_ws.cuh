@@ -167,9 +167,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
 #pragma unroll
           for (int m = 0; m < M; ++m) fadd[m] = 0.0;
           if (second) {
-            if (limit) limit_waves<RP, LIM, BFL>(P, waveC, sC, wnorm2, dotl, dotn);
             double cqxx[M];
-            second_order<RP>(dtdy, waveC, sC, cqxx);
+#ifndef CLAW_STRICT
+            if constexpr (SP && !BFL) {
+              limited_second_order<RP, LIM>(P, dtdy, waveC, sC, wnorm2, dotl, dotn, cqxx);
+            } else
+#endif
+            {
+              if (limit) limit_waves<RP, LIM, BFL>(P, waveC, sC, wnorm2, dotl, dotn);
+              second_order<RP>(dtdy, waveC, sC, cqxx);
+            }
 #pragma unroll
             for (int m = 0; m < M; ++m) fadd[m] = 0.0 + 0.5 * cqxx[m];
             if (mt == 2) {                                                 // flux2.f90:167-173
@@ -227,6 +234,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
 #pragma unroll
       for (int m = 0; m < M; ++m) { cqxx[m] = 0.0; fadd[m] = 0.0; }
       if (second) {
+        bool done = false;
         if (limit) {                                                       // flux2.f90:127
           double wnorm2[W], dotr[W], dotl[W];
           {
@@ -239,9 +247,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
           }
 #pragma unroll
           for (int mw = 0; mw < W; ++mw) dotl[mw] = shfl_left(dotr[mw]);
+#ifndef CLAW_STRICT
+          if constexpr (SP && !BFL) {
+            limited_second_order<RP, LIM>(P, dtdx, wave, s, wnorm2, dotl, dotr, cqxx);
+            done = true;
+          } else
+#endif
           limit_waves<RP, LIM, BFL>(P, wave, s, wnorm2, dotl, dotr);
         }
-        second_order<RP>(dtdx, wave, s, cqxx);                             // flux2.f90:134-146
+        if (!done) second_order<RP>(dtdx, wave, s, cqxx);                  // flux2.f90:134-146
 #pragma unroll
         for (int m = 0; m < M; ++m) fadd[m] = 0.0 + 0.5 * cqxx[m];
       }
