@@ -309,5 +309,216 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
   block_max_cfl<NT>(cfl, P.cfl_bits, sred);
 }
 
+// =====================================================================================
+// Dimension-split step, warp-synchronous (same algorithm, order of operations and bits as sweep2_split in
+// sweep2.cuh): x-sweep of row J+2 with the neighbouring interfaces exchanged by warp shuffle, then the y-pipeline on
+// the x-updated rows in thread-private registers / shared memory; no __syncthreads in the march loop.  Rows are
+// prefetched one march step ahead with cp.async (PF != 0).  do_y = 0: x-sweep only, over rows [j0, j1).
+// =====================================================================================
+template <class RP, int NW, int MINB = 1, int PF = 1>
+__global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_constant__ Sweep2Params P) {
+  constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE, NT = NW * 32;
+  constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
+  using S = Smem2ws<RP, NW>;
+  constexpr int TX = 28;
+  extern __shared__ double smem[];
+  const int t = threadIdx.x, lane = t & 31;
+  double* const syw = smem + S::OFF_YW * NT + t;
+  double* const sya = smem + S::OFF_YA * NT + t;
+  double* const spf = smem + S::OFF_PF * NT + t;
+  double* const sred = smem + S::PER_THREAD * NT;
+
+  const int nx = P.mx + 4;
+  const int I = (blockIdx.x * NW + (t >> 5)) * TX + lane;
+  const int Ic = I < nx ? I : nx - 1;
+  const double dtdx = P.dtdx, dtdy = P.dtdy;
+  const bool second = (P.order != 1);
+  const bool limit = second && (P.limit != 0);
+  const bool do_x = P.do_x != 0, do_y = P.do_y != 0;
+  const double* qcol = P.qin + Ic;
+  double cfl = 0.0;
+  const bool x_cfl_col = (lane >= 1) && (I >= 2) && (I <= P.mx + 2);
+  const bool interior_col = (I >= 2) && (I <= P.mx + 1);
+  const bool x_ok = (lane >= 2) && (lane <= 29);            // my x-updated value is complete
+  const bool col_ok = (I <= P.mx + 3) && (!do_x || !interior_col || x_ok);
+  const int Jb = P.j0 + blockIdx.y * P.seg_rows;
+  const int Je = min(Jb + P.seg_rows, P.j1);
+
+  // x-sweep of one row (step2ds.f90:96-160 with ids = 1): q -> x-updated value of my cell
+  auto x_sweep = [&](const double* q, double* out) {
+    double cq[NC1], cl[NC1], ql[M];
+    if constexpr (NC > 0) RP::cell(P.rp, q, cq);
+#pragma unroll
+    for (int m = 0; m < M; ++m) ql[m] = shfl_left(q[m]);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) cl[k] = shfl_left(cq[k]);
+    double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
+    RP::normal(P.rp, 0, ql, q, cl, cq, wave, s, amdq, apdq, roe);          // flux2.f90:101
+    if (x_cfl_col) cfl = cfl_update<RP>(cfl, dtdx, s);                     // flux2.f90:111-119
+#pragma unroll
+    for (int m = 0; m < M; ++m) { cqxx[m] = 0.0; fadd[m] = 0.0; }
+    if (second) {
+      bool done = false;
+      if (limit) {                                                         // flux2.f90:127
+        double wnorm2[W], dotr[W], dotl[W];
+        {
+          double waveR[W][M];
+#pragma unroll
+          for (int mw = 0; mw < W; ++mw)
+#pragma unroll
+            for (int m = 0; m < M; ++m) waveR[mw][m] = shfl_right(wave[mw][m]);
+          wave_dots<RP, false>(wave, waveR, wnorm2, dotr);
+        }
+#pragma unroll
+        for (int mw = 0; mw < W; ++mw) dotl[mw] = shfl_left(dotr[mw]);
+#ifndef CLAW_STRICT
+        limited_second_order<RP, 0>(P, dtdx, wave, s, wnorm2, dotl, dotr, cqxx);
+        done = true;
+#else
+        limit_waves<RP, 0>(P, wave, s, wnorm2, dotl, dotr);
+#endif
+      }
+      if (!done) second_order<RP>(dtdx, wave, s, cqxx);                    // flux2.f90:134-146
+#pragma unroll
+      for (int m = 0; m < M; ++m) fadd[m] = 0.0 + 0.5 * cqxx[m];
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      const double amdqR = shfl_right(amdq[m]), faddR = shfl_right(fadd[m]);
+      const double qadd = (0.0 - dtdx * apdq[m]) - dtdx * amdqR;           // flux2.f90:105-108
+      out[m] = (q[m] + qadd) - dtdx * (faddR - fadd[m]);                   // step2ds.f90:149-152
+    }
+  };
+
+  // rows through the two-stage cp.async ring: row(J) is consumed while row(J+1) is in flight
+  auto prefetch = [&](int slot, int Jrow) {
+#pragma unroll
+    for (int m = 0; m < M; ++m) cp_async8(spf + ((slot & 1) * M + m) * NT, qcol + m * P.plane + (long long)Jrow * P.pitch);
+  };
+  auto fetch = [&](int slot, int Jrow, int Jnext, bool more, double* q) {
+    if constexpr (PF != 0) {
+      cp_async_wait_all();
+#pragma unroll
+      for (int m = 0; m < M; ++m) q[m] = spf[((slot & 1) * M + m) * NT];
+      if (more) prefetch(slot + 1, Jnext);
+      cp_async_commit();
+    } else {
+#pragma unroll
+      for (int m = 0; m < M; ++m) q[m] = qcol[m * P.plane + (long long)Jrow * P.pitch];
+    }
+  };
+
+  if (!do_y) {
+    if constexpr (PF != 0) { prefetch(Jb, Jb); cp_async_commit(); }
+    for (int J = Jb; J < Je; ++J) {
+      double q[M], r[M];
+      fetch(J, J, J + 1, J + 1 < Je, q);
+      x_sweep(q, r);
+      if (interior_col && x_ok) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) P.qout[m * P.plane + (long long)J * P.pitch + I] = r[m];
+      }
+    }
+    block_max_cfl<NT>(cfl, P.cfl_bits, sred);
+    return;
+  }
+
+  double qx0[M], qx1[M], cx1[NC1];                         // x-updated rows J, J+1 (natural frame)
+  double yI_apdq[M], yI_fadd[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) { qx0[m] = 0.0; qx1[m] = 0.0; yI_apdq[m] = 0.0; yI_fadd[m] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < NC1; ++k) cx1[k] = 0.0;
+  if constexpr (PF != 0) { prefetch(Jb, Jb - 2); cp_async_commit(); }
+
+  for (int J = Jb - 4; J < Je; ++J) {
+    // ---- x-sweep of row J+2 ----------------------------------------------------------
+    double qx2[M];
+    fetch(J - (Jb - 4) + Jb, J + 2, J + 3, J + 1 < Je, qx2);
+    if (do_x) {
+      double r[M];
+      x_sweep(qx2, r);
+      if (interior_col) {                                  // ghost columns are not updated by the x-sweep
+#pragma unroll
+        for (int m = 0; m < M; ++m) qx2[m] = r[m];
+      }
+    }
+    // ---- y-pipeline --------------------------------------------------------------------
+    double cx2[NC1];
+    if constexpr (NC > 0) RP::cell(P.rp, qx2, cx2);        // of the x-updated cell
+    if (J >= Jb - 3) {
+      double waveN[W][M], sN[W], amdqN[M], apdqN[M], roeN[NR];
+      {
+        double ql[M], qr[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) { ql[m] = qx1[rot<M>(m)]; qr[m] = qx2[rot<M>(m)]; }
+        RP::normal(P.rp, 1, ql, qr, cx1, cx2, waveN, sN, amdqN, apdqN, roeN);
+      }
+      if (col_ok && (J + 2 >= 2) && (J + 2 <= P.my + 2)) cfl = cfl_update<RP>(cfl, dtdy, sN);
+      double dotn[W];
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw) dotn[mw] = 0.0;
+      if (J >= Jb - 2) {
+        double waveC[W][M], wnorm2[W];
+#pragma unroll
+        for (int mw = 0; mw < W; ++mw) {
+          wnorm2[mw] = 0.0;
+#pragma unroll
+          for (int m = 0; m < M; ++m) waveC[mw][m] = syw[(mw * M + m) * NT];
+        }
+        if (limit) wave_dots<RP, true>(waveC, waveN, wnorm2, dotn);
+        if (J >= Jb - 1) {
+          double sC[W], amdqC[M], apdqC[M], roeC[NR], dotl[W];
+#pragma unroll
+          for (int m = 0; m < M; ++m) { amdqC[m] = sya[m * NT]; apdqC[m] = sya[(M + m) * NT]; }
+#pragma unroll
+          for (int k = 0; k < NR; ++k) roeC[k] = sya[(2 * M + k) * NT];
+#pragma unroll
+          for (int mw = 0; mw < W; ++mw) dotl[mw] = sya[(2 * M + NR + mw) * NT];
+          RP::speeds(P.rp, 1, roeC, sC);
+          double fadd[M];
+#pragma unroll
+          for (int m = 0; m < M; ++m) fadd[m] = 0.0;
+          if (second) {
+            double cqxx[M];
+#ifndef CLAW_STRICT
+            if (limit) limited_second_order<RP, 0>(P, dtdy, waveC, sC, wnorm2, dotl, dotn, cqxx);
+            else second_order<RP>(dtdy, waveC, sC, cqxx);
+#else
+            if (limit) limit_waves<RP>(P, waveC, sC, wnorm2, dotl, dotn);
+            second_order<RP>(dtdy, waveC, sC, cqxx);
+#endif
+#pragma unroll
+            for (int m = 0; m < M; ++m) fadd[m] = 0.0 + 0.5 * cqxx[m];
+          }
+#pragma unroll
+          for (int m = 0; m < M; ++m) {
+            const double qadd = (0.0 - dtdy * yI_apdq[m]) - dtdy * amdqC[m];
+            const double r = (qx0[rot<M>(m)] + qadd) - dtdy * (fadd[m] - yI_fadd[m]);     // step2ds.f90:237-240
+            if (J >= Jb && col_ok && (do_x ? interior_col : true))
+              P.qout[rot<M>(m) * P.plane + (long long)J * P.pitch + I] = r;
+            yI_apdq[m] = apdqC[m]; yI_fadd[m] = fadd[m];
+          }
+        }
+      }
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw)
+#pragma unroll
+        for (int m = 0; m < M; ++m) syw[(mw * M + m) * NT] = waveN[mw][m];
+#pragma unroll
+      for (int m = 0; m < M; ++m) { sya[m * NT] = amdqN[m]; sya[(M + m) * NT] = apdqN[m]; }
+#pragma unroll
+      for (int k = 0; k < NR; ++k) sya[(2 * M + k) * NT] = roeN[k];
+#pragma unroll
+      for (int mw = 0; mw < W; ++mw) sya[(2 * M + NR + mw) * NT] = dotn[mw];
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) { qx0[m] = qx1[m]; qx1[m] = qx2[m]; }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) cx1[k] = cx2[k];
+  }
+  block_max_cfl<NT>(cfl, P.cfl_bits, sred);
+}
+
 }  // namespace CLAW_NS
 }  // namespace clawcuda

@@ -68,6 +68,14 @@ static cudaError_t launch_ws(Sweep2Params& P, int seg_hint, int num_sms, cudaStr
                        info, NW * 28);
 }
 
+// warp-synchronous dimension-split kernel (sweep2_ws.cuh)
+template <class RP, int NW, int MINB, int PF = 1>
+static cudaError_t launch_split_ws(Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
+  using S = Smem2ws<RP, NW>;
+  return launch_kernel(sweep2_split_ws<RP, NW, MINB, PF>, NW * 32, (int)S::BYTES, !P.do_y, P, seg_hint, num_sms, st, info,
+                       NW * 28);
+}
+
 // aux-reading solvers (sweep2_aux.cuh): warp-synchronous, NW strips per CTA
 template <class RP, int NW>
 static cudaError_t launch_aux(int kind, Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
@@ -88,7 +96,9 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
                           LaunchInfo* info) {
   switch (rp_id) {
     case 1: return launch_one<RpAdvection2D, 128>(kind, P, seg_hint, num_sms, st, info);
-    case 2: return launch_one<RpAcoustics2D, 128>(kind, P, seg_hint, num_sms, st, info);
+    case 2:
+      if (kind == 1) return launch_split_ws<RpAcoustics2D, 1, 16>(P, seg_hint, num_sms, st, info);
+      return launch_one<RpAcoustics2D, 128>(kind, P, seg_hint, num_sms, st, info);
     case 3: {
       static const int variant = getenv("CLAW_VARIANT") ? atoi(getenv("CLAW_VARIANT")) : 0;   // tuning experiments
       if (kind == 0 && headline_method<4>(P, 4)) {
@@ -119,7 +129,8 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
       }
       if (kind == 0 && variant == 20) return launch_ws<RpEuler4Wave2D, 2, 6, 0>(P, seg_hint, num_sms, st, info);
       if (kind == 0) return launch_one<RpEuler4Wave2D, 64, 6>(kind, P, seg_hint, num_sms, st, info);
-      return launch_one<RpEuler4Wave2D, 128>(kind, P, seg_hint, num_sms, st, info);
+      if (variant == 30) return launch_one<RpEuler4Wave2D, 128>(kind, P, seg_hint, num_sms, st, info);
+      return launch_split_ws<RpEuler4Wave2D, 1, 8>(P, seg_hint, num_sms, st, info);
     }
     case 4: {
       static const int variant = getenv("CLAW_VARIANT") ? atoi(getenv("CLAW_VARIANT")) : 0;   // tuning experiments
@@ -128,14 +139,28 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
       if (variant == 4) return launch_one<RpShallowRoeEfix2D, 128, 4>(kind, P, seg_hint, num_sms, st, info);
       if (variant == 5) return launch_one<RpShallowRoeEfix2D, 64, 6>(kind, P, seg_hint, num_sms, st, info);
       if (variant == 6) return launch_one<RpShallowRoeEfix2D, 64, 8>(kind, P, seg_hint, num_sms, st, info);
+      if (kind == 1) {
+        switch (variant) {
+          case 0: return launch_split_ws<RpShallowRoeEfix2D, 1, 16>(P, seg_hint, num_sms, st, info);   // 9.5 ms at 16384^2
+          case 7: return launch_split_ws<RpShallowRoeEfix2D, 1, 12>(P, seg_hint, num_sms, st, info);   // 10.3
+          case 8: return launch_split_ws<RpShallowRoeEfix2D, 1, 8>(P, seg_hint, num_sms, st, info);
+          case 9: return launch_split_ws<RpShallowRoeEfix2D, 1, 12, 0>(P, seg_hint, num_sms, st, info);
+          case 10: return launch_split_ws<RpShallowRoeEfix2D, 2, 6>(P, seg_hint, num_sms, st, info);
+          default: break;       // 1: the block kernel
+        }
+      }
       return launch_one<RpShallowRoeEfix2D, 128>(kind, P, seg_hint, num_sms, st, info);
     }
     case 9: return launch_one<RpEuler5Wave2D, 128>(kind, P, seg_hint, num_sms, st, info);
     case 7: return launch_aux<RpVcAcoustics2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 8: return launch_aux<RpVcAdvection2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 10: return launch_aux<RpPsystem2D, 2>(kind, P, seg_hint, num_sms, st, info);
-    case 11: return launch_one<RpEulerHlle2D, 128>(kind, P, seg_hint, num_sms, st, info);
-    case 12: return launch_one<RpShallowHlle2D, 128>(kind, P, seg_hint, num_sms, st, info);
+    case 11:
+      if (kind == 1) return launch_split_ws<RpEulerHlle2D, 1, 12>(P, seg_hint, num_sms, st, info);
+      return launch_one<RpEulerHlle2D, 128>(kind, P, seg_hint, num_sms, st, info);
+    case 12:
+      if (kind == 1) return launch_split_ws<RpShallowHlle2D, 1, 12>(P, seg_hint, num_sms, st, info);
+      return launch_one<RpShallowHlle2D, 128>(kind, P, seg_hint, num_sms, st, info);
   }
   return cudaErrorInvalidValue;
 }
