@@ -98,7 +98,7 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
     case 1: return launch_one<RpAdvection2D, 128>(kind, P, seg_hint, num_sms, st, info);
     case 2:
       if (kind == 1) return launch_split_ws<RpAcoustics2D, 1, 16>(P, seg_hint, num_sms, st, info);
-      return launch_one<RpAcoustics2D, 128>(kind, P, seg_hint, num_sms, st, info);
+      return launch_ws<RpAcoustics2D, 1, 16, 6>(P, seg_hint, num_sms, st, info);          // generic methods + cp.async ring
     case 3: {
       static const int variant = getenv("CLAW_VARIANT") ? atoi(getenv("CLAW_VARIANT")) : 0;   // tuning experiments
       if (kind == 0 && headline_method<4>(P, 4)) {
@@ -106,29 +106,16 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
         switch (variant) {
           case 0: return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);   // fastest measured (profiles/r01_h)
           case 21: return launch_ws<RpEuler4Wave2D, 1, 12, MC | 1>(P, seg_hint, num_sms, st, info);    // the r01_g default
-          case 1: return launch_ws<RpEuler4Wave2D, 1, 12, MC | 1 | 2>(P, seg_hint, num_sms, st, info);   // L1 prefetch hint
-          case 2: return launch_ws<RpEuler4Wave2D, 1, 12, MC | 1 | 4>(P, seg_hint, num_sms, st, info);   // L2 prefetch hint
           case 3: return launch_ws<RpEuler4Wave2D, 1, 12, MC | 1 | 6>(P, seg_hint, num_sms, st, info);   // cp.async ring
-          case 4: return launch_ws<RpEuler4Wave2D, 1, 16, MC | 1>(P, seg_hint, num_sms, st, info);
-          case 5: return launch_ws<RpEuler4Wave2D, 1, 16, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
-          case 6: return launch_ws<RpEuler4Wave2D, 2, 5, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
           case 7: return launch_ws<RpEuler4Wave2D, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
-          case 11: return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);  // shared cell data
-          case 12: return launch_ws<RpEuler4Wave2DT<3>, 1, 12, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
-          case 13: return launch_ws<RpEuler4Wave2D, 2, 4, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
           case 14: return launch_ws<RpEuler4Wave2D, 1, 8, MC | 1 | 6 | 8>(P, seg_hint, num_sms, st, info);   // branch-free limiter
           case 16: return launch_ws<RpEuler4Wave2DT<0, 1>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);  // branch-free efix
-          case 17: return launch_ws<RpEuler4Wave2DT<0, 1>, 1, 8, MC | 1 | 6 | 8>(P, seg_hint, num_sms, st, info);
-          case 18: return launch_ws<RpEuler4Wave2DT<3, 1>, 1, 8, MC | 1 | 6 | 8>(P, seg_hint, num_sms, st, info);
-          case 19: return launch_ws<RpEuler4Wave2DT<3, 0>, 1, 8, MC | 1 | 6 | 8>(P, seg_hint, num_sms, st, info);
           case 15: return launch_spec<RpEuler4Wave2D, 64, 6, MC | 1>(P, seg_hint, num_sms, st, info);
-          case 8: return launch_spec<RpEuler4Wave2D, 64, 4, MC | 1>(P, seg_hint, num_sms, st, info);
-          case 10: return launch_ws<RpEuler4Wave2D, 2, 6, MC | 1>(P, seg_hint, num_sms, st, info);
           default: break;     // 9: the generic kernel
         }
       }
-      if (kind == 0 && variant == 20) return launch_ws<RpEuler4Wave2D, 2, 6, 0>(P, seg_hint, num_sms, st, info);
-      if (kind == 0) return launch_one<RpEuler4Wave2D, 64, 6>(kind, P, seg_hint, num_sms, st, info);
+      if (kind == 0 && variant == 31) return launch_one<RpEuler4Wave2D, 64, 6>(kind, P, seg_hint, num_sms, st, info);
+      if (kind == 0) return launch_ws<RpEuler4Wave2D, 1, 8, 6>(P, seg_hint, num_sms, st, info);
       if (variant == 30) return launch_one<RpEuler4Wave2D, 128>(kind, P, seg_hint, num_sms, st, info);
       return launch_split_ws<RpEuler4Wave2D, 1, 8>(P, seg_hint, num_sms, st, info);
     }
@@ -149,18 +136,21 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
           default: break;       // 1: the block kernel
         }
       }
+      if (kind == 0 && variant == 0) return launch_ws<RpShallowRoeEfix2D, 1, 12, 6>(P, seg_hint, num_sms, st, info);
       return launch_one<RpShallowRoeEfix2D, 128>(kind, P, seg_hint, num_sms, st, info);
     }
-    case 9: return launch_one<RpEuler5Wave2D, 128>(kind, P, seg_hint, num_sms, st, info);
+    case 9:
+      if (kind == 1) return launch_split_ws<RpEuler5Wave2D, 1, 8>(P, seg_hint, num_sms, st, info);
+      return launch_ws<RpEuler5Wave2D, 1, 8, 6>(P, seg_hint, num_sms, st, info);
     case 7: return launch_aux<RpVcAcoustics2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 8: return launch_aux<RpVcAdvection2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 10: return launch_aux<RpPsystem2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 11:
       if (kind == 1) return launch_split_ws<RpEulerHlle2D, 1, 12>(P, seg_hint, num_sms, st, info);
-      return launch_one<RpEulerHlle2D, 128>(kind, P, seg_hint, num_sms, st, info);
+      return launch_ws<RpEulerHlle2D, 1, 12, 6>(P, seg_hint, num_sms, st, info);
     case 12:
       if (kind == 1) return launch_split_ws<RpShallowHlle2D, 1, 12>(P, seg_hint, num_sms, st, info);
-      return launch_one<RpShallowHlle2D, 128>(kind, P, seg_hint, num_sms, st, info);
+      return launch_ws<RpShallowHlle2D, 1, 12, 6>(P, seg_hint, num_sms, st, info);
   }
   return cudaErrorInvalidValue;
 }
