@@ -65,6 +65,7 @@ def _declare(L):
                                           c_double_p]),
         'claw_step3ds_host': (i, [i] * 8 + [vp, vp, vp, d, d, d, d, c_int_p, c_int_p, i, i, i, c_double_p, i, i,
                                             c_double_p]),
+        'claw_step1_host': (i, [i] * 5 + [vp, vp, d, d, c_int_p, c_int_p, i, i, c_double_p, i, i, c_double_p]),
         'claw_host_release': (i, []),
         'claw_host_alloc': (i, [ctypes.POINTER(vp), sz]),
         'claw_host_free': (i, [vp]),

@@ -17,7 +17,7 @@ COMMON = ['nvcc', '-ccbin', HOSTCXX] + ARCH + ['-lineinfo', '-O3', '-std=c++17',
 
 SOURCES = ['clawcuda.cu', 'sweep_inst.cu', 'sweep3_inst.cu', 'sweep2.cuh', 'sweep3.cuh', 'rp2.cuh', 'rp3.cuh', 'launch.h',
            '../../include/clawcuda.h']
-KERNEL_UNITS = ['sweep_inst.cu', 'sweep3_inst.cu']
+KERNEL_UNITS = ['sweep_inst.cu', 'sweep3_inst.cu', 'sweep1_inst.cu']
 
 
 def _stale():

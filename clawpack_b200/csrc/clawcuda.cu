@@ -1086,6 +1086,68 @@ int claw_step3ds_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, i
   return 0;
 }
 
+// ---- 1-D: q,cfl = step1(num_ghost,mx,q,aux,dx,dt,method,mthlim,use_fwave,rp1) (step1.f90:2-3, classic/solver.py:302) ----
+namespace {
+struct Host1 { double* d[4] = {nullptr, nullptr, nullptr, nullptr}; size_t cap[4] = {0, 0, 0, 0}; };
+Host1 g_host1;                        // q in, q out, aux, cfl slot
+int host1_reserve(int k, size_t bytes) {
+  if (g_host1.cap[k] >= bytes) return 0;
+  if (g_host1.d[k]) cudaFree(g_host1.d[k]);
+  g_host1.d[k] = nullptr; g_host1.cap[k] = 0;
+  if (cudaMalloc(&g_host1.d[k], bytes) != cudaSuccess) return 1;
+  g_host1.cap[k] = bytes;
+  return 0;
+}
+}  // namespace
+
+int claw_step1_host(int meqn, int mwaves, int maux, int num_ghost, int mx, double* q, const double* aux, double dx,
+                    double dt, const int* method7, const int* mthlim, int use_fwave, int rp_id, const double* cparam,
+                    int ncparam, int mode, double* cfl) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  if (num_ghost != 2) return fail(nullptr, 3, "claw_step1_host: num_ghost must be 2");
+  if (!q || !method7 || !mthlim || !cfl || mx < 1) return fail(nullptr, 12, "claw_step1_host: bad arguments");
+  static const int k_meqn[] = {1, 2, 1, 2, 2}, k_mwaves[] = {1, 2, 1, 2, 2};
+  if (rp_id < 21 || rp_id > 25) return fail(nullptr, 5, "claw_step1_host: unknown 1-D rp_id %d", rp_id);
+  if (k_meqn[rp_id - 21] != meqn || k_mwaves[rp_id - 21] != mwaves)
+    return fail(nullptr, 6, "claw_step1_host: rp_id %d expects meqn=%d mwaves=%d (got %d, %d)", rp_id,
+                k_meqn[rp_id - 21], k_mwaves[rp_id - 21], meqn, mwaves);
+  if (method7[1] != 1 && method7[1] != 2) return fail(nullptr, 33, "order must be 1 or 2 (got %d)", method7[1]);
+  if (method7[5] < 0 || method7[5] > maux) return fail(nullptr, 31, "index_capa=%d is outside the aux array (num_aux=%d)", method7[5] - 1, maux);
+  if (method7[5] > 0 && !aux) return fail(nullptr, 31, "claw_step1_host: capacity function requested but aux is NULL");
+  for (int mw = 0; mw < mwaves; ++mw)
+    if (mthlim[mw] < 0 || mthlim[mw] > 5)
+      return fail(nullptr, 35, "limiter id %d of wave family %d is not defined by philim.f90 (0..5)", mthlim[mw], mw);
+  const size_t ncell = (size_t)mx + 4, qb = sizeof(double) * ncell * meqn, ab = sizeof(double) * ncell * (maux > 0 ? maux : 1);
+  if (host1_reserve(0, qb) || host1_reserve(1, qb) || host1_reserve(2, ab) || host1_reserve(3, 64))
+    return fail(nullptr, 20, "claw_step1_host: device allocation failed");
+  cudaStream_t st = nullptr;
+  if (cudaMemcpyAsync(g_host1.d[0], q, qb, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(g_host1.d[1], g_host1.d[0], qb, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+      cudaMemsetAsync(g_host1.d[3], 0, 64, st) != cudaSuccess)
+    return fail(nullptr, 21, "claw_step1_host: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (maux > 0 && aux && cudaMemcpyAsync(g_host1.d[2], aux, ab, cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return fail(nullptr, 21, "claw_step1_host: aux upload failed");
+  Sweep2Params P{};
+  P.qin = g_host1.d[0]; P.qout = g_host1.d[1]; P.aux = g_host1.d[2];
+  P.cfl_bits = reinterpret_cast<unsigned long long*>(g_host1.d[3]);
+  P.mx = mx; P.my = 1; P.pitch = meqn; P.plane = 1;          // PyClaw's (m, i) order
+  P.dtdx = dt; P.dtdy = dx;                                   // the kernel forms dt/dx or dt/(dx*capa) itself
+  P.order = method7[1]; P.mtrans = 0; P.limit = 0;
+  for (int mw = 0; mw < mwaves; ++mw) { P.mthlim[mw] = mthlim[mw]; if (mthlim[mw] > 0) P.limit = 1; }
+  P.maux = maux; P.capa = method7[5]; P.fwave = use_fwave;
+  for (int k = 0; k < 4; ++k) P.rp.p[k] = (cparam && k < ncparam) ? cparam[k] : 0.0;
+  cudaError_t e = (mode == CLAW_MODE_FAST) ? fast::launch_sweep1(rp_id, P, st, nullptr)
+                                           : strict::launch_sweep1(rp_id, P, st, nullptr);
+  if (e != cudaSuccess) return fail(nullptr, 100 + (int)e, "1-D sweep kernel launch failed: %s", cudaGetErrorString(e));
+  double c = 0.0;
+  if (cudaMemcpyAsync(q, g_host1.d[1], qb, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaMemcpyAsync(&c, g_host1.d[3], sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess)
+    return fail(nullptr, 22, "claw_step1_host: download failed: %s", cudaGetErrorString(cudaGetLastError()));
+  *cfl = c;
+  return 0;
+}
+
 int claw_host_release(void) {
   std::lock_guard<std::mutex> lock(g_host_mutex);
   if (g_host) { claw_destroy(g_host); g_host = nullptr; }

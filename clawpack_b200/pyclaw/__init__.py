@@ -15,7 +15,7 @@ from .geometry import Dimension, Domain, Grid, Patch  # noqa: F401
 from .state import State  # noqa: F401
 from .solution import Solution  # noqa: F401
 from .solver import BC, CFLError, Solver  # noqa: F401
-from .classic.solver import ClawSolver, ClawSolver2D, ClawSolver3D  # noqa: F401
+from .classic.solver import ClawSolver, ClawSolver1D, ClawSolver2D, ClawSolver3D  # noqa: F401
 from .controller import Controller  # noqa: F401
 
 _logging.getLogger('pyclaw').addHandler(_logging.NullHandler())

@@ -115,7 +115,7 @@ class ClawSolver(Solver):
             from .. import cuda_classic
             self._set_method(solution.state)
             solution.state.set_cparam(self.rp)
-            if self._device_path_eligible():
+            if self.num_dim > 1 and self._device_path_eligible():
                 self._dev = cuda_classic.DeviceStepper(self, solution.state)
             else:
                 self.fmod = cuda_classic.fmod(self.num_dim, precision=self.cuda_precision)
@@ -170,6 +170,32 @@ class ClawSolver(Solver):
             f = getattr(self.rp, nm, None)
             out.append(f._cpointer if f is not None and hasattr(f, '_cpointer') else self.rp)
         return out
+
+
+class ClawSolver1D(ClawSolver):
+    """1-D classic solver (classic/solver.py:249-387, Fortran branch).  ``kernel_language='CUDA'`` always runs in
+    plug-in mode: every step calls ``fmod.step1`` (claw_step1_host) on the host arrays -- 1-D problems are small and
+    the device-resident machinery would buy nothing.  The reference's pure-Python 1-D kernel is not part of this
+    build."""
+
+    def __init__(self, riemann_solver=None, claw_package=None):
+        self.num_dim = 1
+        self.reflect_index = [1]
+        super(ClawSolver1D, self).__init__(riemann_solver, claw_package)
+
+    def step_hyperbolic(self, solution):
+        state = solution.states[0]
+        grid = state.grid
+        self._apply_bcs(state)
+        mx = grid.num_cells[0]
+        dx, dt = grid.delta[0], self.dt
+        rp1, = self._rp_args(('rp1',))
+        self.qbc, cfl = self.fmod.step1(self.num_ghost, mx, self.qbc, self.auxbc, dx, dt, self._method, self._mthlim,
+                                        self.fwave, rp1)
+        self.cfl.update_global_max(cfl)
+        state.set_q_from_qbc(self.num_ghost, self.qbc)
+        if state.num_aux > 0:
+            state.set_aux_from_auxbc(self.num_ghost, self.auxbc)
 
 
 class ClawSolver2D(ClawSolver):

@@ -191,6 +191,22 @@ class _CudaFmod(object):
     def _vp(a):
         return ctypes.c_void_p(0) if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
+    def step1(self, num_ghost, mx, q, aux, dx, dt, method, mthlim, use_fwave, rp1):
+        """q, cfl = step1(...) of the f2py module classic1 as called at classic/solver.py:302: q (with ghost cells)
+        is updated in place and returned."""
+        if not (isinstance(q, np.ndarray) and q.flags['F_CONTIGUOUS'] and q.dtype == np.float64):
+            q = np.asfortranarray(q, dtype=np.float64)
+        aux = None if aux is None or aux.size == 0 else np.asfortranarray(aux, dtype=np.float64)
+        method = np.ascontiguousarray(method, dtype=np.intc)
+        mth = _iarr(mthlim)
+        cp, ncp = _cparam_of(rp1)
+        cfl = ctypes.c_double(0.0)
+        _lib.check(self.L.claw_step1_host(q.shape[0], len(mth), 0 if aux is None else aux.shape[0], num_ghost, mx,
+                                          self._vp(q), self._vp(aux), dx, dt, _lib.ip(method), _lib.ip(mth),
+                                          int(bool(use_fwave)), int(rp1.rp_id), _lib.dp(cp), ncp, self.mode,
+                                          ctypes.byref(cfl)))
+        return q, cfl.value
+
     def step2(self, maxm, num_ghost, mx, my, qold, qnew, aux, dx, dy, dt, method, mthlim, aux1, aux2, aux3, work,
               use_fwave, rpn2, rpt2):
         qold, qnew, aux, method, mth = self._prep(qold, qnew, aux, method, mthlim)

@@ -19,6 +19,12 @@ _SOLVERS = {
     'euler_hlle_2D': (11, ('gamma',), 2),                     # rpn2_euler_hlle.f90:32 (+ rpt2_dummy.f90)
     'shallow_hlle_2D': (12, ('grav',), 2),                    # rpn2_shallow_hlle.f90:31 (+ rpt2_dummy.f90)
     'psystem_2D': (10, (), 2),                                # rpn2_psystem.f90 (f-wave; coefficients + strain in aux)
+    # 1-D (claw_step1_host): riemann/src/rp1_*.f90
+    'advection_1D': (21, ('u',), 1),
+    'acoustics_1D': (22, ('rho', 'bulk', 'cc', 'zz'), 1),
+    'burgers_1D': (23, (), 1),
+    'shallow_roe_with_efix_1D': (24, ('grav',), 1),
+    'shallow_hlle_1D': (25, ('grav',), 1),
 }
 
 for _name, (_id, _cp, _nd) in _SOLVERS.items():

@@ -7,6 +7,7 @@ num_eqn = {
     'euler_5wave_2D': 5, 'euler_4wave_2D': 4, 'euler_hlle_2D': 4, 'kpp_2D': 1, 'psystem_2D': 3,
     'shallow_roe_with_efix_2D': 3, 'shallow_hlle_2D': 3, 'shallow_sphere_2D': 4, 'vc_advection_2D': 1,
     'vc_acoustics_2D': 3, 'vc_elasticity_2D': 5, 'vc_acoustics_3D': 4, 'euler_3D': 5,
+    'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2,
 }
 
 num_waves = {
@@ -14,6 +15,7 @@ num_waves = {
     'euler_5wave_2D': 5, 'euler_4wave_2D': 4, 'euler_hlle_2D': 2, 'kpp_2D': 1, 'psystem_2D': 2,
     'shallow_roe_with_efix_2D': 3, 'shallow_hlle_2D': 2, 'shallow_sphere_2D': 3, 'vc_advection_2D': 1,
     'vc_acoustics_2D': 2, 'vc_elasticity_2D': 4, 'vc_acoustics_3D': 2, 'euler_3D': 3,
+    'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2,
 }
 
 fwave = {name: False for name in num_eqn}

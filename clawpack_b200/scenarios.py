@@ -426,20 +426,63 @@ def euler_3d_shock_bubble(q0, consts, tfinal=0.1, num_output_times=10, dimension
                  tfinal=tfinal, num_output_times=num_output_times)
 
 
+# ---- 1-D (ClawSolver1D / step1.f90) ------------------------------------------------------------------
+def advection_1d(nx=400, tfinal=1.0):
+    """pyclaw/examples/advection_1d/advection_1d.py:30-78 (Fortran classic): Gaussian pulse, periodic."""
+    xc = centers(0.0, 1.0, nx)
+    q = np.empty((1, nx), order='F')
+    beta, gamma, x0 = 100, 0, 0.75
+    q[0] = np.exp(-beta * (xc - x0) ** 2) * np.cos(gamma * (xc - x0))
+    return _base('advection_1D', (0.0,), (1.0,), (nx,), q, problem_data={'u': 1.0}, limiters=MINMOD,
+                 bc_lower=[PERIODIC], bc_upper=[PERIODIC], tfinal=tfinal)
+
+
+def acoustics_1d(num_cells=100, tfinal=1.0):
+    """pyclaw/examples/acoustics_1d_homogeneous/acoustics_1d.py:47-114 (classic): MC limiter, periodic."""
+    xc = centers(0.0, 1.0, num_cells)
+    q = np.zeros((2, num_cells), order='F')
+    q[0] = np.exp(-200 * (xc - 0.5) ** 2) * np.cos(0 * (xc - 0.5))
+    rho, bulk = 1.0, 1.0
+    zz, cc = np.sqrt(rho * bulk), np.sqrt(bulk / rho)
+    return _base('acoustics_1D', (0.0,), (1.0,), (num_cells,), q,
+                 problem_data={'rho': rho, 'bulk': bulk, 'zz': zz, 'cc': cc}, limiters=MC,
+                 bc_lower=[PERIODIC], bc_upper=[PERIODIC], dt_initial=(1.0 / num_cells) / cc * 0.1, tfinal=tfinal)
+
+
+def burgers_1d(mx=500, tfinal=0.5):
+    """pyclaw/examples/burgers_1d/burgers_1d.py:22-64 (classic): van Leer, periodic, sine + 0.5."""
+    xc = centers(0.0, 1.0, mx)
+    q = np.empty((1, mx), order='F')
+    q[0] = np.sin(np.pi * 2 * xc) + 0.50
+    return _base('burgers_1D', (0.0,), (1.0,), (mx,), q, limiters=VANLEER, bc_lower=[PERIODIC], bc_upper=[PERIODIC],
+                 tfinal=tfinal)
+
+
+def dam_break_1d(mx=500, riemann_solver='roe', tfinal=2.0):
+    """pyclaw/examples/shallow_1d/dam_break.py:22-99 (classic): van Leer, extrapolation, h = 3 | 1."""
+    xc = centers(-5.0, 5.0, mx)
+    q = np.zeros((2, mx), order='F')
+    q[0] = 3. * (xc <= 0.) + 1. * (xc > 0.)
+    rp = 'shallow_hlle_1D' if riemann_solver == 'hlle' else 'shallow_roe_with_efix_1D'
+    return _base(rp, (-5.0,), (5.0,), (mx,), q, problem_data={'grav': 1.0}, limiters=VANLEER,
+                 bc_lower=[EXTRAP], bc_upper=[EXTRAP], tfinal=tfinal)
+
+
 def make_claw(sc, kernel_language='CUDA', pyclaw=None, **solver_kw):
     """Build a PyClaw-API Controller (solver + solution) from a scenario dict."""
     if pyclaw is None:
         from clawpack_b200 import pyclaw
     from clawpack_b200 import riemann
     ndim = len(sc['num_cells'])
-    Solver = pyclaw.ClawSolver2D if ndim == 2 else pyclaw.ClawSolver3D
+    Solver = {1: pyclaw.ClawSolver1D, 2: pyclaw.ClawSolver2D, 3: pyclaw.ClawSolver3D}[ndim]
     solver = Solver(getattr(riemann, sc['rp']))
     solver.kernel_language = kernel_language
     solver.limiters = sc['limiters']
     solver.order = sc['order']
-    solver.dimensional_split = sc['dimensional_split']
-    if sc['transverse_waves'] is not None:
-        solver.transverse_waves = sc['transverse_waves']
+    if ndim > 1:
+        solver.dimensional_split = sc['dimensional_split']
+        if sc['transverse_waves'] is not None:
+            solver.transverse_waves = sc['transverse_waves']
     solver.cfl_max = sc['cfl_max']
     solver.cfl_desired = sc['cfl_desired']
     solver.dt_initial = sc['dt_initial']

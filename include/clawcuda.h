@@ -13,6 +13,7 @@
  *        claw_step2ds_host  <->  step2ds  (pyclaw/src/pyclaw/classic/step2ds.f90:2-5)
  *        claw_step3_host    <->  step3    (pyclaw/src/pyclaw/classic/step3.f90:2-5)
  *        claw_step3ds_host  <->  step3ds  (pyclaw/src/pyclaw/classic/step3ds.f90:2-5)
+ *        claw_step1_host    <->  step1    (pyclaw/src/pyclaw/classic/step1.f90:2-3; module classic1)
  *      Arrays are float64, Fortran-contiguous, WITH ghost cells, exactly as PyClaw passes
  *      them (qbc / auxbc).  The (rpn, rpt[, rptt]) C-function-pointer arguments of the
  *      reference (classic/solver.py:516-521) become `rp_id` + `cparam` (the COMMON /cparam/
@@ -51,7 +52,13 @@ enum {
   CLAW_RP_EULER_5WAVE_2D = 9,          /* rpn2_euler_5wave.f90, rpt2_euler_5wave.f90 (Euler + tracer) */
   CLAW_RP_PSYSTEM_2D = 10,             /* rpn2_psystem.f90, rpt2_psystem.f90 (f-wave; aux: density, modulus, relation id, strain) */
   CLAW_RP_EULER_HLLE_2D = 11,          /* rpn2_euler_hlle.f90 + rpt2_dummy.f90 (no transverse solver) */
-  CLAW_RP_SHALLOW_HLLE_2D = 12         /* rpn2_shallow_hlle.f90 + rpt2_dummy.f90 (no transverse solver) */
+  CLAW_RP_SHALLOW_HLLE_2D = 12,        /* rpn2_shallow_hlle.f90 + rpt2_dummy.f90 (no transverse solver) */
+  /* 1-D (claw_step1_host only) */
+  CLAW_RP_ADVECTION_1D = 21,           /* riemann/src/rp1_advection.f90 */
+  CLAW_RP_ACOUSTICS_1D = 22,           /* rp1_acoustics.f90 */
+  CLAW_RP_BURGERS_1D = 23,             /* rp1_burgers.f90 */
+  CLAW_RP_SHALLOW_ROE_EFIX_1D = 24,    /* rp1_shallow_roe_with_efix.f90 */
+  CLAW_RP_SHALLOW_HLLE_1D = 25         /* rp1_shallow_hlle.f90 */
 };
 
 /* Boundary-condition ids = pyclaw.BC (pyclaw/src/pyclaw/solver.py:13-19) */
@@ -169,6 +176,14 @@ int claw_step3ds_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, i
                       const double* qold, double* qnew, const double* aux, double dx, double dy, double dz, double dt,
                       const int* method7, const int* mthlim, int idir, int use_fwave,
                       int rp_id, const double* cparam, int ncparam, int mode, double* cfl);
+/* 1-D: claw_step1_host <-> step1 (pyclaw/src/pyclaw/classic/step1.f90:2-3 as called at classic/solver.py:302):
+   q(meqn, mx+2*num_ghost) with ghost cells is updated IN PLACE (interior and the ghost cells the Fortran touches),
+   aux(maux, mx+2*num_ghost) may be NULL when maux == 0; the f2py scratch arguments (f, wave, s, amdq, apdq, dtdx) are
+   internal.  1-D Riemann solver ids: 21 advection_1D, 22 acoustics_1D, 23 burgers_1D, 24 shallow_roe_with_efix_1D,
+   25 shallow_hlle_1D (riemann/src/rp1_*.f90). */
+int claw_step1_host(int meqn, int mwaves, int maux, int num_ghost, int mx, double* q, const double* aux,
+                    double dx, double dt, const int* method7, const int* mthlim, int use_fwave,
+                    int rp_id, const double* cparam, int ncparam, int mode, double* cfl);
 /* drop the cached device state of the host entry points */
 int claw_host_release(void);
 

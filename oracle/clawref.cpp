@@ -2,6 +2,7 @@
 //
 // build:  make -C oracle        (g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC)
 #include "clawref2.hpp"
+#include "clawref1.hpp"
 #ifdef CLAWREF_WITH_3D
 #include "clawref3.hpp"
 #endif
@@ -147,6 +148,15 @@ int clawref_count_ops3(int maxm, int num_eqn, int num_waves, int num_aux, int nu
 }
 
 #endif
+
+// q,cfl = step1(num_ghost,mx,q,aux,dx,dt,method,mthlim,use_fwave,rp1)  (f2py signature of
+// pyclaw/src/pyclaw/classic/step1.f90:2-3 as called at classic/solver.py:302); q is updated in place.
+int clawref_step1(int num_eqn, int num_waves, int num_ghost, int num_aux, int mx, double* q, double* aux, double dx,
+                  double dt, const int* method, const int* mthlim, double* cfl, int use_fwave, int rp_id,
+                  const double* cparam) {
+  return step1<double>(num_eqn, num_waves, num_ghost, num_aux, mx, q, aux, dx, dt, method, mthlim, cfl,
+                       use_fwave != 0, rp_id, cparam);
+}
 
 int clawref_max_threads(void) {
 #ifdef _OPENMP

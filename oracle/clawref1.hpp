@@ -1,0 +1,222 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see clawref2.hpp header).  1-D classic step.
+//
+// Restatement of pyclaw/src/pyclaw/classic/step1.f90:2-148 and of the 1-D Riemann solvers
+//   riemann/src/rp1_advection.f90:40-50, rp1_acoustics.f90:45-80, rp1_burgers.f90:34-48,
+//   rp1_shallow_roe_with_efix.f90:60-193, rp1_shallow_hlle.f90:35-87.
+// Pinned by the reference's stored vectors burgers_1d `fortran_classic`, shallow_1d
+// `dambreak_fortran_classic_roe / _hlle` and by the error values asserted in advection_1d/test_advection.py:30-31
+// and acoustics_1d_homogeneous/test_acoustics.py:28-29 (tests/test_oracle.py).
+#pragma once
+#include "clawref2.hpp"
+
+namespace clawref {
+
+enum RpId1 {
+  RP_ADVECTION_1D = 21,
+  RP_ACOUSTICS_1D = 22,
+  RP_BURGERS_1D = 23,
+  RP_SHALLOW_ROE_EFIX_1D = 24,
+  RP_SHALLOW_HLLE_1D = 25,
+};
+
+template <class R>
+using Rp1 = void (*)(int maxmx, int meqn, int mwaves, int maux, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R> auxl,
+                     V2<R> auxr, V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double* cparam);
+
+template <class R>
+void rp1_advection(int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>, V3<R> wave, V2<R> s,
+                   V2<R> amdq, V2<R> apdq, const double* cparam) {
+  const R u = R(cparam[0]);
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    wave(1, 1, i) = ql(1, i) - qr(1, i - 1);
+    s(1, i) = u;
+    amdq(1, i) = r_min(u, R(0.0)) * wave(1, 1, i);
+    apdq(1, i) = r_max(u, R(0.0)) * wave(1, 1, i);
+  }
+}
+
+template <class R>
+void rp1_acoustics(int, int meqn, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>, V3<R> wave, V2<R> s,
+                   V2<R> amdq, V2<R> apdq, const double* cparam) {
+  const R cc = R(cparam[2]), zz = R(cparam[3]);           // common /cparam/ rho,bulk,cc,zz
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R d1 = ql(1, i) - qr(1, i - 1);
+    R d2 = ql(2, i) - qr(2, i - 1);
+    R a1 = (-d1 + zz * d2) / (R(2.0) * zz);
+    R a2 = (d1 + zz * d2) / (R(2.0) * zz);
+    wave(1, 1, i) = -a1 * zz; wave(2, 1, i) = a1; s(1, i) = -cc;
+    wave(1, 2, i) = a2 * zz;  wave(2, 2, i) = a2; s(2, i) = cc;
+  }
+  for (int m = 1; m <= meqn; ++m)
+    for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+      amdq(m, i) = s(1, i) * wave(m, 1, i);
+      apdq(m, i) = s(2, i) * wave(m, 2, i);
+    }
+}
+
+template <class R>
+void rp1_burgers(int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>, V3<R> wave, V2<R> s,
+                 V2<R> amdq, V2<R> apdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    wave(1, 1, i) = ql(1, i) - qr(1, i - 1);
+    s(1, i) = R(0.5) * (qr(1, i - 1) + ql(1, i));
+    amdq(1, i) = r_min(s(1, i), R(0.0)) * wave(1, 1, i);
+    apdq(1, i) = r_max(s(1, i), R(0.0)) * wave(1, 1, i);
+    if (ql(1, i) > R(0.0) && qr(1, i - 1) < R(0.0)) {      // efix = .true. (:31, :41-46)
+      amdq(1, i) = -(R(0.5) * (qr(1, i - 1) * qr(1, i - 1)));   // - 1.d0/2.d0 * q**2 : the constant folds to 0.5
+      apdq(1, i) = R(0.5) * (ql(1, i) * ql(1, i));
+    }
+  }
+}
+
+template <class R>
+void rp1_shallow_roe_efix(int, int, int num_waves, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>,
+                          V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double* cparam) {
+  const R grav = R(cparam[0]);
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {              // loop 30
+    R ubar = (qr(2, i - 1) / r_sqrt(qr(1, i - 1)) + ql(2, i) / r_sqrt(ql(1, i))) /
+             (r_sqrt(qr(1, i - 1)) + r_sqrt(ql(1, i)));
+    R cbar = r_sqrt(R(0.5) * grav * (qr(1, i - 1) + ql(1, i)));
+    R d1 = ql(1, i) - qr(1, i - 1);
+    R d2 = ql(2, i) - qr(2, i - 1);
+    R a1 = R(0.5) * (-d2 + (ubar + cbar) * d1) / cbar;
+    R a2 = R(0.5) * (d2 - (ubar - cbar) * d1) / cbar;
+    wave(1, 1, i) = a1; wave(2, 1, i) = a1 * (ubar - cbar); s(1, i) = ubar - cbar;
+    wave(1, 2, i) = a2; wave(2, 2, i) = a2 * (ubar + cbar); s(2, i) = ubar + cbar;
+  }
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {              // efix = .true.: loop 200
+    // (amdq is NOT zeroed on entry by the Fortran; every path below assigns it before use)
+    R s0 = qr(2, i - 1) / qr(1, i - 1) - r_sqrt(grav * qr(1, i - 1));
+    if (s0 >= R(0.0) && s(1, i) > R(0.0)) {
+      for (int m = 1; m <= 2; ++m) amdq(m, i) = R(0.0);
+      continue;
+    }
+    R hr1 = qr(1, i - 1) + wave(1, 1, i);
+    R uhr1 = qr(2, i - 1) + wave(2, 1, i);
+    R s1 = uhr1 / hr1 - r_sqrt(grav * hr1);
+    R sfract;
+    if (s0 < R(0.0) && s1 > R(0.0)) sfract = s0 * (s1 - s(1, i)) / (s1 - s0);
+    else if (s(1, i) < R(0.0)) sfract = s(1, i);
+    else sfract = R(0.0);
+    for (int m = 1; m <= 2; ++m) amdq(m, i) = sfract * wave(m, 1, i);
+    R s3 = ql(2, i) / ql(1, i) + r_sqrt(grav * ql(1, i));
+    R hl2 = ql(1, i) - wave(1, 2, i);
+    R uhl2 = ql(2, i) - wave(2, 2, i);
+    R s2 = uhl2 / hl2 + r_sqrt(grav * hl2);
+    if (s2 < R(0.0) && s3 > R(0.0)) sfract = s2 * (s3 - s(2, i)) / (s3 - s2);
+    else if (s(2, i) < R(0.0)) sfract = s(2, i);
+    else continue;
+    for (int m = 1; m <= 2; ++m) amdq(m, i) = amdq(m, i) + sfract * wave(m, 2, i);
+  }
+  for (int m = 1; m <= 2; ++m)
+    for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+      R df = R(0.0);
+      for (int mw = 1; mw <= num_waves; ++mw) df = df + s(mw, i) * wave(m, mw, i);
+      apdq(m, i) = df - amdq(m, i);
+    }
+}
+
+template <class R>
+void rp1_shallow_hlle(int, int meqn, int mwaves, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>,
+                      V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double* cparam) {
+  const R grav = R(cparam[0]);
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R h_l = qr(1, i - 1), h_r = ql(1, i);
+    R u_l = qr(2, i - 1) / qr(1, i - 1);
+    R u_r = ql(2, i) / ql(1, i);
+    R c_l = r_sqrt(grav * h_l);
+    R c_r = r_sqrt(grav * h_r);
+    // `1.e-14` is a single-precision literal in the Fortran source
+    if (h_l < R((double)1.e-14f) && h_r < R((double)1.e-14f)) {
+      wave(1, 1, i) = R(0.0); wave(2, 1, i) = R(0.0); s(1, i) = R(0.0);
+      wave(1, 2, i) = R(0.0); wave(2, 2, i) = R(0.0); s(2, i) = R(0.0);
+    } else {
+      R hsqrt_l = r_sqrt(qr(1, i - 1));
+      R hsqrt_r = r_sqrt(ql(1, i));
+      R h_hat = R(0.5) * (h_l + h_r);
+      R u_hat = (hsqrt_l * u_l + hsqrt_r * u_r) / (hsqrt_l + hsqrt_r);
+      R c_hat = r_sqrt(grav * h_hat);
+      R s1 = r_min(u_l - c_l, u_hat - c_hat);
+      R s2 = r_max(u_r + c_r, u_hat + c_hat);
+      R h_m = (ql(2, i) - qr(2, i - 1) - s2 * h_r + s1 * h_l) / (s1 - s2);
+      R hu_m = (ql(2, i) * (u_r - s2) - qr(2, i - 1) * (u_l - s1) + R(0.5) * grav * (h_r * h_r - h_l * h_l)) / (s1 - s2);
+      wave(1, 1, i) = h_m - h_l; wave(2, 1, i) = hu_m - qr(2, i - 1); s(1, i) = s1;
+      wave(1, 2, i) = h_r - h_m; wave(2, 2, i) = ql(2, i) - hu_m;     s(2, i) = s2;
+    }
+  }
+  for (int m = 1; m <= meqn; ++m)
+    for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+      amdq(m, i) = R(0.0); apdq(m, i) = R(0.0);
+      for (int mw = 1; mw <= mwaves; ++mw) {
+        if (s(mw, i) < R(0.0)) amdq(m, i) = amdq(m, i) + s(mw, i) * wave(m, mw, i);
+        else apdq(m, i) = apdq(m, i) + s(mw, i) * wave(m, mw, i);
+      }
+    }
+}
+
+template <class R> inline bool select_rp1(int rp_id, Rp1<R>& rp) {
+  switch (rp_id) {
+    case RP_ADVECTION_1D: rp = rp1_advection<R>; return true;
+    case RP_ACOUSTICS_1D: rp = rp1_acoustics<R>; return true;
+    case RP_BURGERS_1D: rp = rp1_burgers<R>; return true;
+    case RP_SHALLOW_ROE_EFIX_1D: rp = rp1_shallow_roe_efix<R>; return true;
+    case RP_SHALLOW_HLLE_1D: rp = rp1_shallow_hlle<R>; return true;
+  }
+  return false;
+}
+
+// =====================================================================
+// step1 -- pyclaw/src/pyclaw/classic/step1.f90:2-148.  q(num_eqn, 1-num_ghost:mx+num_ghost) is updated IN PLACE.
+// =====================================================================
+template <class R>
+int step1(int num_eqn, int num_waves, int num_ghost, int num_aux, int mx, R* q_, R* aux_, R dx, R dt,
+          const int* method, const int* mthlim, R* cfl_out, bool use_fwave, int rp_id, const double* cparam) {
+  Rp1<R> rp1;
+  if (!select_rp1<R>(rp_id, rp1)) return 1;
+  const int lo = 1 - num_ghost, n = mx + 2 * num_ghost;
+  const int na = num_aux > 0 ? num_aux : 1;
+  V2<R> q{q_, num_eqn, lo}, aux{aux_, na, lo};
+  std::vector<R> f_(n * num_eqn), s_(n * num_waves), wave_((size_t)n * num_eqn * num_waves), amdq_(n * num_eqn),
+      apdq_(n * num_eqn), dtdx_(n);
+  V2<R> f{f_.data(), num_eqn, lo}, s{s_.data(), num_waves, lo}, amdq{amdq_.data(), num_eqn, lo},
+      apdq{apdq_.data(), num_eqn, lo};
+  V3<R> wave{wave_.data(), num_eqn, num_waves, lo};
+  V1<R> dtdx{dtdx_.data(), lo};
+  bool limit = false;                                                   // :64-67
+  for (int mw = 0; mw < num_waves; ++mw) if (mthlim[mw] > 0) limit = true;
+  const int index_capa = method[5];                                     // :69-80
+  for (int i = lo; i <= mx + num_ghost; ++i) {
+    if (index_capa > 0) {
+      if (aux(index_capa, i) <= R(0.0)) return 3;                       // 'Error -- capa must be positive'
+      dtdx(i) = dt / (dx * aux(index_capa, i));
+    } else {
+      dtdx(i) = dt / dx;
+    }
+  }
+  rp1(mx, num_eqn, num_waves, num_aux, num_ghost, mx, q, q, aux, aux, wave, s, amdq, apdq, cparam);   // :86-87
+  // forall with two statements: each statement completes for ALL (i, m) before the next starts (:93-96)
+  for (int i = 1; i <= mx + 1; ++i)
+    for (int m = 1; m <= num_eqn; ++m) q(m, i) = q(m, i) - dtdx(i) * apdq(m, i);
+  for (int i = 1; i <= mx + 1; ++i)
+    for (int m = 1; m <= num_eqn; ++m) q(m, i - 1) = q(m, i - 1) - dtdx(i - 1) * amdq(m, i);
+  R cfl = R(0.0);                                                       // :100-105
+  for (int mw = 1; mw <= num_waves; ++mw)
+    for (int i = 1; i <= mx + 1; ++i) cfl = r_max3(cfl, dtdx(i) * s(mw, i), -dtdx(i - 1) * s(mw, i));
+  *cfl_out = cfl;
+  if (method[1] == 1) return 0;                                         // :107
+  for (int i = lo; i <= mx + num_ghost; ++i)
+    for (int m = 1; m <= num_eqn; ++m) f(m, i) = R(0.0);                // :111-113
+  if (limit) limiter<R>(mx, num_eqn, num_waves, num_ghost, mx, wave, s, mthlim);   // :116-117
+  for (int i = 1; i <= mx + 1; ++i)                                     // :119-141
+    for (int m = 1; m <= num_eqn; ++m)
+      for (int mw = 1; mw <= num_waves; ++mw) {
+        R dtdxave = R(0.5) * (dtdx(i - 1) + dtdx(i));
+        R lead = use_fwave ? r_sign1(s(mw, i)) : r_abs(s(mw, i));
+        f(m, i) = f(m, i) + R(0.5) * lead * (R(1.0) - r_abs(s(mw, i)) * dtdxave) * wave(m, mw, i);
+      }
+  for (int i = 1; i <= mx + 1; ++i)                                     // :145-147
+    for (int m = 1; m <= num_eqn; ++m) q(m, i) = q(m, i) - dtdx(i) * (f(m, i + 1) - f(m, i));
+  return 0;
+}
+
+}  // namespace clawref

@@ -31,6 +31,11 @@ RP_IDS = {
     'psystem_2D': 10,
     'euler_hlle_2D': 11,
     'shallow_hlle_2D': 12,
+    'advection_1D': 21,
+    'acoustics_1D': 22,
+    'burgers_1D': 23,
+    'shallow_roe_with_efix_1D': 24,
+    'shallow_hlle_1D': 25,
 }
 # COMMON /cparam/ member order of each solver (rpn2_advection.f90, rpn2_acoustics.f90:52,
 # rpn2_euler_4wave.f90:71, rpn2_shallow_roe_with_efix.f90:59; vc_acoustics_3D has none)
@@ -47,13 +52,20 @@ CPARAM_NAMES = {
     'psystem_2D': (),                 # rpn2_psystem.f90: coefficients live in aux
     'euler_hlle_2D': ('gamma',),      # rpn2_euler_hlle.f90:32
     'shallow_hlle_2D': ('grav',),     # rpn2_shallow_hlle.f90:31
+    'advection_1D': ('u',),           # rp1_advection.f90
+    'acoustics_1D': ('rho', 'bulk', 'cc', 'zz'),   # rp1_acoustics.f90
+    'burgers_1D': (),
+    'shallow_roe_with_efix_1D': ('grav',),
+    'shallow_hlle_1D': ('grav',),
 }
 NUM_EQN = {'advection_2D': 1, 'acoustics_2D': 3, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
            'vc_acoustics_3D': 4, 'euler_3D': 5, 'vc_acoustics_2D': 3, 'vc_advection_2D': 1, 'euler_5wave_2D': 5,
-           'psystem_2D': 3, 'euler_hlle_2D': 4, 'shallow_hlle_2D': 3}
+           'psystem_2D': 3, 'euler_hlle_2D': 4, 'shallow_hlle_2D': 3,
+           'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2}
 NUM_WAVES = {'advection_2D': 1, 'acoustics_2D': 2, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
              'vc_acoustics_3D': 2, 'euler_3D': 3, 'vc_acoustics_2D': 2, 'vc_advection_2D': 1, 'euler_5wave_2D': 5,
-             'psystem_2D': 2, 'euler_hlle_2D': 2, 'shallow_hlle_2D': 2}
+             'psystem_2D': 2, 'euler_hlle_2D': 2, 'shallow_hlle_2D': 2,
+             'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2}
 
 BC_CUSTOM, BC_EXTRAP, BC_PERIODIC, BC_WALL = 0, 1, 2, 3
 
@@ -80,6 +92,7 @@ def lib():
         L.clawref_step2ds.argtypes = [i] * 7 + [dp, dp, dp, d, d, d, ip, ip, dp, i, i, i, dp, i]
         L.clawref_count_ops2.argtypes = [i] * 7 + [dp, dp, d, d, d, ip, ip, i, i, i, dp,
                                                    ctypes.POINTER(ctypes.c_uint64)]
+        L.clawref_step1.argtypes = [i] * 5 + [dp, dp, d, d, ip, ip, dp, i, i, dp]
         if hasattr(L, 'clawref_step3'):
             L.clawref_step3.argtypes = [i] * 8 + [dp, dp, dp, d, d, d, d, ip, ip, dp, i, i, dp, i]
             L.clawref_step3ds.argtypes = [i] * 8 + [dp, dp, dp, d, d, d, d, ip, ip, dp, i, i, i, dp, i]
@@ -172,7 +185,7 @@ class RefSolver(object):
         self.cfl_max = 1.0
         self.cfl_desired = 0.9
         self.dimensional_split = True
-        self.transverse_waves = 1 if num_dim == 2 else 22     # trans_inc (2-D :446), trans_cor (3-D :605)
+        self.transverse_waves = {1: 0, 2: 1, 3: 22}[num_dim]  # trans_inc (2-D :446), trans_cor (3-D :605)
         self.dt_initial = 0.1
         self.dt_max = 1e99
         self.max_steps = 10000
@@ -221,6 +234,8 @@ class RefSolver(object):
         m[0] = int(self.dt_variable)
         m[1] = self.order
         m[2] = -1 if self.dimensional_split else self.transverse_waves
+        if self.num_dim == 1:
+            m[2] = 0                                                         # classic/solver.py:181-182
         m[3] = 0
         m[4] = 0
         m[5] = self.index_capa + 1
@@ -261,7 +276,13 @@ class RefSolver(object):
         maxm = max(n)
         common = (maxm, self.num_eqn, self.num_waves, self.num_aux, g) + tuple(n)
         tail = (int(self.fwave), self.rp_id, _dp(self.cparam), self.nthreads)
-        if self.num_dim == 2:
+        if self.num_dim == 1:                                                # classic/solver.py:279-303: in place on qbc
+            rc = L.clawref_step1(self.num_eqn, self.num_waves, g, self.num_aux, n[0], _dp(self.qbc), _dp(self.auxbc),
+                                 self.delta[0], self.dt, _ip(self._method), _ip(self._mthlim), ctypes.byref(cfl),
+                                 int(self.fwave), self.rp_id, _dp(self.cparam))
+            assert rc == 0, rc
+            c = cfl.value
+        elif self.num_dim == 2:
             dx, dy = self.delta
             if self.dimensional_split:
                 rc = L.clawref_step2ds(*common, _dp(qold), _dp(self.qbc), _dp(self.auxbc), dx, dy, self.dt,

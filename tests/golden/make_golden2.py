@@ -16,6 +16,11 @@ out['euler_2d__shock_bubble_interaction'] = np.asarray(d['shock_bubble_interacti
 out['euler_2d__quadrants_hlle'] = np.asarray(d['quadrants_hlle'], dtype=np.float64)
 d = np.load(os.path.join(REF, 'shallow_2d/expected_sols.npy'), allow_pickle=True).item()
 out['shallow_2d__radialdambreak_classic_hlle'] = np.asarray(d['radialdambreak_classic_hlle'], dtype=np.float64)
+d = np.load(os.path.join(REF, 'burgers_1d/expected_sols.npy'), allow_pickle=True).item()
+out['burgers_1d__fortran_classic'] = np.asarray(d['fortran_classic'], dtype=np.float64)
+d = np.load(os.path.join(REF, 'shallow_1d/expected_sols.npy'), allow_pickle=True).item()
+out['shallow_1d__dambreak_fortran_classic_roe'] = np.asarray(d['dambreak_fortran_classic_roe'], dtype=np.float64)
+out['shallow_1d__dambreak_fortran_classic_hlle'] = np.asarray(d['dambreak_fortran_classic_hlle'], dtype=np.float64)
 for g in ('0.25_0.25', '11.75_11.75', '17.85_1.25', '3.25_18.75'):
     out['psystem_2d__gauge' + g] = np.loadtxt(os.path.join(REF, 'psystem_2d/verify_gauge%s.txt' % g))
 

@@ -24,6 +24,17 @@ class OracleFmod(object):
             return np.zeros((1,) + tuple(shape), order='F')
         return np.asfortranarray(aux)
 
+    def step1(self, num_ghost, mx, q, aux, dx, dt, method, mthlim, use_fwave, rp1):
+        m = np.ascontiguousarray(method, dtype=np.intc)
+        ml = np.array(mthlim, dtype=np.intc)
+        aux = self._aux(aux, q.shape[1:])
+        cp = _cparam(rp1)
+        cfl = ctypes.c_double()
+        rc = self.L.clawref_step1(q.shape[0], len(ml), num_ghost, int(m[6]), mx, R._dp(q), R._dp(aux), dx, dt,
+                                  R._ip(m), R._ip(ml), ctypes.byref(cfl), int(use_fwave), int(rp1.rp_id), R._dp(cp))
+        assert rc == 0
+        return q, cfl.value
+
     def step2(self, maxm, num_ghost, mx, my, qold, qnew, aux, dx, dy, dt, method, mthlim, aux1, aux2, aux3, work,
               use_fwave, rpn2, rpt2):
         m = np.ascontiguousarray(method, dtype=np.intc)

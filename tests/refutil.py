@@ -17,9 +17,12 @@ def ref_solver(sc, nthreads=1):
     s = pyclaw_ref.RefSolver(sc['rp'], ndim, sc['problem_data'], num_aux=num_aux)
     s.limiters = sc['limiters']
     s.order = sc['order']
-    s.dimensional_split = sc['dimensional_split']
-    if sc['transverse_waves'] is not None:
-        s.transverse_waves = sc['transverse_waves']
+    if ndim > 1:
+        s.dimensional_split = sc['dimensional_split']
+        if sc['transverse_waves'] is not None:
+            s.transverse_waves = sc['transverse_waves']
+    else:
+        s.dimensional_split = False
     s.cfl_max = sc['cfl_max']
     s.cfl_desired = sc['cfl_desired']
     s.dt_initial = sc['dt_initial']

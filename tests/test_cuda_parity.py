@@ -3,6 +3,8 @@
 Bars (BASELINE.json north_star): relative L-inf <= 1e-12 after one step, <= 1e-10 after 100 steps,
 identical accept/reject sequences.  In 'strict' arithmetic (no FMA contraction) the kernels are
 op-for-op the reference, so we additionally demand BIT-EXACT equality with the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -197,3 +199,60 @@ def test_no_cpu_fallback_symbols_loaded():
     L = _lib.lib()
     assert L.claw_device_count() >= 1
     assert b'clawcuda' in L.claw_version()
+
+
+# ---- 1-D: claw_step1_host (csrc/sweep1.cuh, rp1.cuh) behind ClawSolver1D ------------------------------
+CASES_1D = {
+    'advection_1d': lambda: S.advection_1d(nx=300, tfinal=0.3),
+    'acoustics_1d': lambda: S.acoustics_1d(num_cells=257, tfinal=0.3),
+    'burgers_1d': lambda: S.burgers_1d(mx=500),
+    'burgers_1d_first_order': lambda: dict(S.burgers_1d(mx=123), order=1),
+    'dam_break_1d_roe': lambda: S.dam_break_1d(mx=500),
+    'dam_break_1d_hlle': lambda: S.dam_break_1d(mx=250, riemann_solver='hlle'),
+    'dam_break_1d_tiny': lambda: S.dam_break_1d(mx=3),
+    'acoustics_1d_tile_edge': lambda: dict(S.acoustics_1d(num_cells=124 * 2 - 4 + 1), limiters=[S.SUPERBEE, S.MINMOD]),
+    'acoustics_1d_wall': lambda: dict(S.acoustics_1d(num_cells=90), bc_lower=[S.WALL], bc_upper=[S.EXTRAP]),
+}
+
+
+@pytest.mark.parametrize('name', sorted(CASES_1D))
+def test_1d_strict_bit_exact_vs_oracle(name):
+    sc = CASES_1D[name]()
+    q, log, solver = _run_cuda(sc, 40, 'strict')
+    qr, logr = _run_ref(sc, 40)
+    assert solver._dev is None and solver.fmod is not None          # 1-D always runs through the plug-in call
+    assert log == logr, 'dt / CFL sequence differs: %r vs %r' % (log[:3], logr[:3])
+    assert np.array_equal(q, qr), 'max abs diff %g' % np.max(np.abs(q - qr))
+
+
+@pytest.mark.parametrize('name', sorted(CASES_1D))
+def test_1d_fast_within_tolerance(name):
+    sc = CASES_1D[name]()
+    qr, logr = _run_ref(sc, 101)
+    q, log, _ = _run_cuda(sc, 101, 'fast')
+    assert [s[2] for s in log] == [s[2] for s in logr]
+    assert _rel_linf(q, qr) <= 1e-10
+
+
+@pytest.mark.parametrize('precision', ['strict', 'fast'])
+def test_1d_reference_goldens(precision):
+    """burgers_1d/test_burgers_1d.py:34-35, shallow_1d/test_shallow1d.py:25-34 (L1 < 1e-6 against the stored vectors)
+    and the error values of advection_1d/test_advection.py:30-31, acoustics_1d_homogeneous/test_acoustics.py:28-29,
+    through Controller.run() with kernel_language='CUDA'."""
+    g2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_goldens2.npz'))
+    for sc, key in ((S.burgers_1d(), 'burgers_1d__fortran_classic'),
+                    (S.dam_break_1d(riemann_solver='roe'), 'shallow_1d__dambreak_fortran_classic_roe'),
+                    (S.dam_break_1d(riemann_solver='hlle'), 'shallow_1d__dambreak_fortran_classic_hlle')):
+        claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision=precision)
+        claw.run()
+        q = claw.frames[claw.num_output_times].state.get_q_global()[0].reshape(-1)
+        dx = claw.solution.domain.grid.delta[0]
+        assert dx * np.sum(np.abs(q - g2[key])) < 1e-6, key
+        assert np.max(np.abs(q - g2[key])) < 1e-10, key
+    for sc, val, tol in ((S.advection_1d(), 3.203924e-04, 1e-4), (S.acoustics_1d(), 0.001981, 1e-5)):
+        claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision=precision)
+        claw.run()
+        q0 = claw.frames[0].state.get_q_global().reshape(-1)
+        qf = claw.frames[claw.num_output_times].state.get_q_global().reshape(-1)
+        err = claw.solution.domain.grid.delta[0] * np.sum(np.abs(qf - q0))
+        assert abs(err - val) < tol, (sc['rp'], err)

@@ -205,3 +205,15 @@ def test_controller_writes_frames(oracle_lib, tmp_path):
     assert np.max(np.abs(back.state.q - claw.solution.state.q)) <= 5e-9 * max(1.0, np.max(np.abs(claw.solution.state.q)))
     with pytest.raises(ValueError):
         claw.solution.write(0, claw.outdir, 'hdf5')
+
+
+def test_host_loop_1d_with_plugin_matches_oracle_loop(oracle_lib):
+    """ClawSolver1D (classic/solver.py:249-303, Fortran branch) with the oracle plug-in: step1 updates qbc in place."""
+    for sc in (S.burgers_1d(mx=60, tfinal=0.2), S.dam_break_1d(mx=50, tfinal=0.5), S.acoustics_1d(num_cells=40, tfinal=0.3),
+               S.advection_1d(nx=30, tfinal=0.2), S.dam_break_1d(mx=50, tfinal=0.5, riemann_solver='hlle')):
+        claw = S.make_claw(sc, kernel_language='Fortran', fmod=OracleFmod())
+        claw.run()
+        r = ref_solver(sc)
+        r.run(sc['tfinal'], sc['num_output_times'])
+        assert np.array_equal(claw.solution.state.q, r.q), sc['rp']
+        assert claw.solver.step_log == r.step_log

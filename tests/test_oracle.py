@@ -253,3 +253,29 @@ def test_dummy_transverse_solver_is_refused(oracle_lib):
     s = ref_solver(sc)
     with pytest.raises(Exception):
         s.evolve_to_time()
+
+
+# ---- 1-D: step1.f90 + rp1_* -------------------------------------------------------------------------
+def test_step1_goldens(oracle_lib):
+    # burgers_1d/test_burgers_1d.py:34-35 (L1 < 1e-6) and shallow_1d/test_shallow1d.py:25-34 (L1 < 1e-6): pin step1
+    # (first-order update, limiter, second-order flux), rp1_burgers (+ entropy fix), rp1_shallow_roe_with_efix,
+    # rp1_shallow_hlle, periodic and extrapolation BCs in 1-D
+    g2 = goldens2()
+    for sc, key in ((S.burgers_1d(), 'burgers_1d__fortran_classic'),
+                    (S.dam_break_1d(riemann_solver='roe'), 'shallow_1d__dambreak_fortran_classic_roe'),
+                    (S.dam_break_1d(riemann_solver='hlle'), 'shallow_1d__dambreak_fortran_classic_hlle')):
+        s = ref_solver(sc)
+        s.run(sc['tfinal'], sc['num_output_times'])
+        dx = s.delta[0]
+        assert dx * np.sum(np.abs(s.q[0] - g2[key])) < 1e-6, key
+        assert np.max(np.abs(s.q[0] - g2[key])) < 1e-11, (key, np.max(np.abs(s.q[0] - g2[key])))
+
+
+def test_step1_reference_error_values(oracle_lib):
+    # advection_1d/test_advection.py:30-31: |err - 3.203924e-04| < 1e-4; acoustics_1d_homogeneous/test_acoustics.py:28-29:
+    # |err - 0.001981| < 1e-5 (err = dx * sum |q_final - q_initial| after one period)
+    for sc, val, tol in ((S.advection_1d(), 3.203924e-04, 1e-4), (S.acoustics_1d(), 0.001981, 1e-5)):
+        s = ref_solver(sc)
+        s.run(sc['tfinal'], sc['num_output_times'])
+        err = s.delta[0] * np.sum(np.abs(s.q - sc['q']))
+        assert abs(err - val) < tol, (sc['rp'], err)
