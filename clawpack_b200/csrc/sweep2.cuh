@@ -57,6 +57,17 @@ struct Sweep2Params {
 
 namespace CLAW_NS {
 
+// limiter.f90:40: a wave of zero norm is left alone.  Fast mode widens "zero" to wnorm2 <= 2^-900 (waves below
+// ~1e-135, e.g. the exponentially decaying numerical tail ahead of a front): the approximate-reciprocal seed flushes
+// denormal inputs to zero and would turn the ratio into NaN, and a wave that small cannot move q by 1e-12.
+__device__ __forceinline__ bool wave_is_zero(double wnorm2) {
+#ifdef CLAW_STRICT
+  return wnorm2 == 0.0;
+#else
+  return !(wnorm2 > 0x1p-900);
+#endif
+}
+
 __device__ __forceinline__ double philim(double a, double b, int meth) {
   // philim.f90:14-35
 #ifdef CLAW_STRICT
@@ -113,11 +124,11 @@ __device__ __forceinline__ void limit_waves(const Sweep2Params& P, double (*wave
       // branch-free (fast mode only): the divisions of the wave families become independent chains the scheduler
       // can overlap (a zero wave yields NaN here and is left untouched by the select)
       wl = philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
-      wl = (wnorm2[mw] == 0.0) ? 1.0 : wl;
+      wl = wave_is_zero(wnorm2[mw]) ? 1.0 : wl;
     } else
 #endif
     {
-      if (wnorm2[mw] == 0.0) continue;
+      if (wave_is_zero(wnorm2[mw])) continue;
       wl = philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
     }
 #pragma unroll
@@ -155,7 +166,7 @@ __device__ __forceinline__ void limited_second_order(const Sweep2Params& P, doub
     const double as = fabs(s[mw]);
     double c = as * (1.0 - as * dtd);
     const int meth = LIM ? LIM : P.mthlim[mw];
-    if (meth != 0 && wnorm2[mw] != 0.0) c *= philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
+    if (meth != 0 && !wave_is_zero(wnorm2[mw])) c *= philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
     coef[mw] = c;
   }
 #pragma unroll

@@ -84,7 +84,7 @@ __device__ __forceinline__ void limit_waves3(const int* mthlim, double (*wave)[M
   for (int mw = 0; mw < W; ++mw) {
     const int meth = mthlim[mw];
     if (meth == 0) continue;
-    if (wnorm2[mw] == 0.0) continue;
+    if (wave_is_zero(wnorm2[mw])) continue;
     const double wl = philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
 #pragma unroll
     for (int m = 0; m < M; ++m) wave[mw][m] = wl * wave[mw][m];
