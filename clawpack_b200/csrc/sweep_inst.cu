@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include "launch.h"
 #include "sweep2_ws.cuh"
+#include "sweep2_wsp.cuh"
 #include "sweep2_aux.cuh"
 #include "rp2_aux.cuh"
 
@@ -76,6 +77,13 @@ static cudaError_t launch_split_ws(Sweep2Params& P, int seg_hint, int num_sms, c
                        NW * 28);
 }
 
+// warp-specialised unsplit kernel for the headline method set (sweep2_wsp.cuh): a pair of warps per 28-column strip
+template <class RP, int MINB, int LIM>
+static cudaError_t launch_wsp(Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
+  using S = Smem2wsp<RP>;
+  return launch_kernel(sweep2_unsplit_wsp<RP, MINB, LIM>, 64, (int)S::BYTES, false, P, seg_hint, num_sms, st, info, 28);
+}
+
 // aux-reading solvers (sweep2_aux.cuh): warp-synchronous, NW strips per CTA
 template <class RP, int NW>
 static cudaError_t launch_aux(int kind, Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
@@ -110,6 +118,7 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
           case 7: return launch_ws<RpEuler4Wave2D, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
           case 14: return launch_ws<RpEuler4Wave2D, 1, 8, MC | 1 | 6 | 8>(P, seg_hint, num_sms, st, info);   // branch-free limiter
           case 16: return launch_ws<RpEuler4Wave2DT<0, 1>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);  // branch-free efix
+          case 40: return launch_wsp<RpEuler4Wave2DT<3>, 6, 4>(P, seg_hint, num_sms, st, info);   // warp pair per strip, 168 registers: 5.21 ms (profiles/r01_j)
           case 15: return launch_spec<RpEuler4Wave2D, 64, 6, MC | 1>(P, seg_hint, num_sms, st, info);
           default: break;     // 9: the generic kernel
         }
