@@ -2,7 +2,9 @@
 // Rotated frame as in rp2.cuh: component 1 = momentum/velocity normal to the interface (`mu`), 2 = transverse (`mv`).
 // normal():      ql/axl = state/aux of the LEFT cell (Fortran qr(:,i-1), auxr(:,i-1)), qr/axr = RIGHT cell (ql(:,i), auxl(:,i))
 // transverse():  ax1/ax2/ax3 = aux of the cell the fluctuation enters (i1 = i-2+imp) in pencils 1, 2, 3
-//                (rows j-1, j, j+1 for an x-sweep; columns i-1, i, i+1 for a y-sweep)
+//                (rows j-1, j, j+1 for an x-sweep; columns i-1, i, i+1 for a y-sweep);
+//                bx1/bx2/bx3 = aux of cell i (the cell on the right of the interface) in the same pencils -- equal to
+//                ax* for imp = 2; only rpt2_acoustics_mapped reads geometry at i regardless of imp
 #pragma once
 #include "rp2.cuh"
 
@@ -36,8 +38,8 @@ struct RpVcAcoustics2D {
     s[0] = -roe[0]; s[1] = roe[1];
   }
   __device__ __forceinline__ static void transverse(const RpParams& P, int dir, const double* roe, const double* ax1,
-                                                    const double* ax2, const double* ax3, const double* asdq,
-                                                    double* bm, double* bp) {
+                                                    const double* ax2, const double* ax3, const double*, const double*,
+                                                    const double*, const double* asdq, double* bm, double* bp) {
     const double cm = ax1[1], cp = ax3[1];
     const double zm = ax1[0] * ax1[1];
     const double zz = ax2[0] * ax2[1];
@@ -68,8 +70,8 @@ struct RpVcAdvection2D {
     s[0] = roe[0];
   }
   __device__ __forceinline__ static void transverse(const RpParams& P, int dir, const double* roe, const double* ax1,
-                                                    const double* ax2, const double* ax3, const double* asdq,
-                                                    double* bm, double* bp) {
+                                                    const double* ax2, const double* ax3, const double*, const double*,
+                                                    const double*, const double* asdq, double* bm, double* bp) {
     const int kv = 1 - dir;                                   // kv = 3-ixy
     bm[0] = fmin2(ax2[kv], 0.0) * asdq[0];
     bp[0] = fmax2(ax3[kv], 0.0) * asdq[0];
@@ -127,8 +129,8 @@ struct RpPsystem2D {
     s[0] = roe[0]; s[1] = roe[1];
   }
   __device__ __forceinline__ static void transverse(const RpParams& P, int dir, const double* roe, const double* ax1,
-                                                    const double* ax2, const double* ax3, const double* asdq,
-                                                    double* bm, double* bp) {
+                                                    const double* ax2, const double* ax3, const double*, const double*,
+                                                    const double*, const double* asdq, double* bm, double* bp) {
     const double sigmapjm = sigmap(ax1[3], ax1[1], nint_(ax1[2]));
     const double sigmapjp = sigmap(ax3[3], ax3[1], nint_(ax3[2]));
     const double r11 = ddiv(1.0, sqrt(sigmapjm * ax1[0]));
@@ -139,6 +141,62 @@ struct RpPsystem2D {
     const double gamma3 = ddiv(-asdq[0] + r11 * asdq[2], r11 - r13);
     bm[0] = s1 * gamma1 * r11; bm[1] = s1 * gamma1 * 0.0; bm[2] = s1 * gamma1 * 1.0;
     bp[0] = s2 * gamma3 * r13; bp[1] = s2 * gamma3 * 0.0; bp[2] = s2 * gamma3 * 1.0;
+  }
+};
+
+// ------------------------------------------------------------------------------------
+// acoustics_mapped_2D -- riemann/src/rpn2_acoustics_mapped.f90:60-131, rpt2_acoustics_mapped.f90:41-88
+// aux planes (0-based): 0-2 normal + length ratio of the left edge, 3-5 of the bottom edge, 6 capacity, 7 impedance,
+// 8 sound speed.  The solver works with the PHYSICAL velocity components (no mu/mv swap), so the rotated frame of the
+// sweep kernels is undone here: natural u = q[1 + dir], v = q[2 - dir].   roe = (s1, s2)
+// ------------------------------------------------------------------------------------
+struct RpAcousticsMapped2D {
+  static constexpr int MEQN = 3, MWAVES = 2, NROE = 2, NCELL = 0, MAUX = 9;
+  __device__ __forceinline__ static void normal(const RpParams& P, int dir, const double* ql, const double* qr,
+                                                const double* axl, const double* axr, double (*wave)[MEQN],
+                                                double* s, double* amdq, double* apdq, double* roe) {
+    const int iu = 1 + dir, iv = 2 - dir;                   // rotated slots of the natural components 2 and 3
+    const int inx = 3 * dir, iny = 3 * dir + 1, ilen = 3 * dir + 2;
+    const double alpha = axr[inx], beta = axr[iny];
+    const double unorl = alpha * qr[iu] + beta * qr[iv];    // Fortran ql(:,i)   = right cell
+    const double unorr = alpha * ql[iu] + beta * ql[iv];    // Fortran qr(:,i-1) = left cell
+    const double d1 = qr[0] - ql[0];
+    const double d2 = unorl - unorr;
+    const double zi = axr[7], zim = axl[7], ci = axr[8], cim = axl[8];
+    const double a1 = ddiv(-d1 + zi * d2, zim + zi);
+    const double a2 = ddiv(d1 + zim * d2, zim + zi);
+    wave[0][0] = -a1 * zim; wave[0][iu] = a1 * alpha; wave[0][iv] = a1 * beta;
+    s[0] = -cim * axr[ilen];
+    wave[1][0] = a2 * zi;   wave[1][iu] = a2 * alpha; wave[1][iv] = a2 * beta;
+    s[1] = ci * axr[ilen];
+#pragma unroll
+    for (int m = 0; m < MEQN; ++m) { amdq[m] = s[0] * wave[0][m]; apdq[m] = s[1] * wave[1][m]; }
+    roe[0] = s[0]; roe[1] = s[1];
+  }
+  __device__ __forceinline__ static void speeds(const RpParams& P, int dir, const double* roe, double* s) {
+    s[0] = roe[0]; s[1] = roe[1];
+  }
+  __device__ __forceinline__ static void transverse(const RpParams& P, int dir, const double* roe, const double* ax1,
+                                                    const double* ax2, const double* ax3, const double* bx1,
+                                                    const double* bx2, const double* bx3, const double* asdq,
+                                                    double* bm, double* bp) {
+    const int iu = 1 + dir, iv = 2 - dir;
+    const int ixt = 3 * (1 - dir), iyt = ixt + 1, ilen = ixt + 2;   // geometry of the TRANSVERSE edges
+    const double asdqp = asdq[0];
+    const double cm = ax1[8], cp = ax3[8];
+    const double zm = ax1[7], zz = ax2[7], zp = ax3[7];
+    double xtran = bx3[ixt], ytran = bx3[iyt];
+    double asdqt = xtran * asdq[iu] + ytran * asdq[iv];
+    const double a2 = ddiv(asdqp + zz * asdqt, zz + zp);
+    const double bpasdqp = a2 * zp, bpasdqt = a2;
+    bp[0] = cp * bpasdqp; bp[iu] = cp * xtran * bpasdqt; bp[iv] = cp * ytran * bpasdqt;
+    xtran = bx2[ixt]; ytran = bx2[iyt];
+    asdqt = xtran * asdq[iu] + ytran * asdq[iv];
+    const double a1 = ddiv(-asdqp + zz * asdqt, zm + zz);
+    const double bmasdqp = -a1 * zm, bmasdqt = a1;
+    bm[0] = -cm * bmasdqp; bm[iu] = -cm * xtran * bmasdqt; bm[iv] = -cm * ytran * bmasdqt;
+#pragma unroll
+    for (int m = 0; m < MEQN; ++m) { bm[m] = bm[m] * bx2[ilen]; bp[m] = bp[m] * bx3[ilen]; }
   }
 };
 

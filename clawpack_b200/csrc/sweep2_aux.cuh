@@ -13,7 +13,7 @@
 //   RP::MAUX                                  aux planes the solver reads (the first MAUX planes)
 //   RP::normal(P, dir, ql, qr, axl, axr, wave, s, amdq, apdq, roe)   ql/axl = left cell, qr/axr = right cell
 //   RP::speeds(P, dir, roe, s)
-//   RP::transverse(P, dir, roe, ax1, ax2, ax3, asdq, bm, bp)         ax* = aux of the cell the fluctuation enters
+//   RP::transverse(P, dir, roe, ax1, ax2, ax3, bx1, bx2, bx3, asdq, bm, bp)   ax* = aux of the cell the fluctuation enters
 //                                                                    (i1 = i-2+imp) in pencils 1, 2, 3
 #pragma once
 #include "sweep2_ws.cuh"
@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(NW * 32) sweep2_unsplit_aux(const __grid_const
 #pragma unroll
           for (int m = 0; m < M; ++m) { bmA[m] = 0.0; bpA[m] = 0.0; bmP[m] = 0.0; bpP[m] = 0.0; }
           if (mt > 0) {
-            RP::transverse(P.rp, 1, roeC, aL0, a0, aR0, amdqC, bmA, bpA);  // imp = 1: cell J      (flux2.f90:181)
-            RP::transverse(P.rp, 1, roeC, aL1, a1, aR1, apdqC, bmP, bpP);  // imp = 2: cell J+1    (flux2.f90:194)
+            RP::transverse(P.rp, 1, roeC, aL0, a0, aR0, aL1, a1, aR1, amdqC, bmA, bpA);  // imp = 1: cell J  (flux2.f90:181)
+            RP::transverse(P.rp, 1, roeC, aL1, a1, aR1, aL1, a1, aR1, apdqC, bmP, bpP);  // imp = 2: cell J+1 (:194)
           }
           const double hd0 = 0.5 * dy0;
 #pragma unroll
@@ -264,8 +264,8 @@ __global__ void __launch_bounds__(NW * 32) sweep2_unsplit_aux(const __grid_const
 #pragma unroll
             for (int m = 0; m < M; ++m) { tm[m] = tm[m] + cqxx[m]; tp[m] = tp[m] - cqxx[m]; }
           }
-          RP::transverse(P.rp, 0, roe, aLl0, aLl1, aLlN, tm, bmA, bpA);     // imp = 1: cell I-1
-          RP::transverse(P.rp, 0, roe, a0, a1, aN, tp, bmP, bpP);           // imp = 2: cell I
+          RP::transverse(P.rp, 0, roe, aLl0, aLl1, aLlN, a0, a1, aN, tm, bmA, bpA);     // imp = 1: cell I-1
+          RP::transverse(P.rp, 0, roe, a0, a1, aN, a0, a1, aN, tp, bmP, bpP);           // imp = 2: cell I
         }
         const double hdC = 0.5 * dxC;
 #pragma unroll

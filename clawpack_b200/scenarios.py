@@ -36,7 +36,7 @@ def _base(rp, lower, upper, n, q, **kw):
              dimensional_split=True, transverse_waves=None, cfl_max=1.0, cfl_desired=0.9,
              dt_initial=0.1, bc_lower=None, bc_upper=None, aux_bc_lower=None, aux_bc_upper=None,
              tfinal=1.0, num_output_times=10, index_capa=-1, custom_aux_bc_lower=None, custom_aux_bc_upper=None,
-             mapc2p=None, step_source=None, source_split=1, before_step=None, fwave=False, gauges=None,
+             mapc2p=None, step_source=None, source_split=1, before_step=None, fwave=False, gauges=None, custom_bc_lower_full=None,
              compute_gauge_values=None)
     d.update(kw)
     return d
@@ -216,6 +216,93 @@ def shock_bubble_interaction(q0, tfinal=0.2, num_output_times=1, dimensional_spl
                  bc_lower=[0, WALL], bc_upper=[EXTRAP, EXTRAP], aux_bc_lower=[EXTRAP, EXTRAP],
                  aux_bc_upper=[EXTRAP, EXTRAP], custom_bc_lower=inflow, step_source=radial_source, source_split=1,
                  tfinal=tfinal, num_output_times=num_output_times)
+
+
+def acoustics_2d_mapped(num_cells=100, tfinal=0.9, num_output_times=1, transverse_waves=None):
+    """pyclaw/examples/acoustics_2d_mapped/acoustics_2d_inclusions.py:150-235 (classic branch): acoustics on a mapped
+    grid with two circular inclusions (impedance 12 / 10, sound speed 0.3 / 1.5), solver acoustics_mapped_2D, unsplit,
+    MC; aux = (left-edge normal x, y, length ratio, bottom-edge normal x, y, length ratio, cell area ratio [capacity],
+    impedance, sound speed); an incoming square wave enters through a BC.custom fill at x-lower that reads auxbc."""
+    circles = (((0.15, 0.204), (0.45, 0.3)), ((0.15, 0.204), (0.7, 0.75)))
+    impedance, sound_speed = (12., 10.), (0.3, 1.5)
+
+    def inclusion_mapping(xc, yc):                          # :30-82: square -> circle inside every inclusion box
+        xp, yp = xc + 0., yc + 0.
+        for (r1, r2), (x0, y0) in circles:
+            xdist, ydist = np.abs(xc - x0), np.abs(yc - y0)
+            insquare = np.where(np.maximum(xdist, ydist) <= r2)
+            xc0, yc0 = (xc[insquare] - x0) / r2, (yc[insquare] - y0) / r2
+            xc1, yc1 = np.abs(xc0), np.abs(yc0)
+            d = np.maximum(xc1, yc1)
+            d = np.maximum(d, 1.e-10)
+            d = np.minimum(d, 0.99999)
+            d1 = d * r2 / np.sqrt(2)
+            R = r1 ** 2 / (r2 * d)
+            ij = np.where(d > (r1 / r2))                    # morph back to the square outside the circle
+            d1[ij] = r1 / np.sqrt(2) + (d[ij] - r1 / r2) * (r2 - r1 / np.sqrt(2)) / (1. - r1 / r2)
+            R[ij] = r1 * ((1. - r1 / r2) / (1. - d[ij])) ** (r2 / r1 + 0.5)
+            xp2, yp2 = d1 / d * xc1, d1 / d * yc1
+            center = d1 - np.sqrt(R ** 2 - d1 ** 2)
+            ij = np.where(xc1 >= yc1)
+            xp2[ij] = center[ij] + np.sqrt(R[ij] ** 2 - yp2[ij] ** 2)
+            ij = np.where(yc1 >= xc1)
+            yp2[ij] = center[ij] + np.sqrt(R[ij] ** 2 - xp2[ij] ** 2)
+            xp[insquare] = x0 + np.sign(xc0) * xp2
+            yp[insquare] = y0 + np.sign(yc0) * yp2
+        return xp, yp
+
+    n = num_cells
+    lower, upper = (0., 0.), (1., 1.)
+    dx = dy = 1.0 / n
+    xn = lower[0] + np.arange(n + 1) * dx                   # Dimension.nodes
+    index = np.indices((n + 1, n + 1))
+    xcor, ycor = inclusion_mapping(xn[index[0]], xn[index[1]])          # grid.p_nodes
+    llx, lly = xcor[:-1, :-1], ycor[:-1, :-1]               # compute_geometry (:84-127)
+    ulx, uly = xcor[:-1, 1:], ycor[:-1, 1:]
+    lrx, lry = xcor[1:, :-1], ycor[1:, :-1]
+    urx, ury = xcor[1:, 1:], ycor[1:, 1:]
+    a_x, a_y = uly - lly, -(ulx - llx)
+    anorm = np.sqrt(a_x ** 2 + a_y ** 2)
+    a_x, a_y = a_x / anorm, a_y / anorm
+    b_x, b_y = -(lry - lly), lrx - llx
+    bnorm = np.sqrt(b_x ** 2 + b_y ** 2)
+    b_x, b_y = b_x / bnorm, b_y / bnorm
+    area = 0 * a_x
+    area += 0.5 * (lly + uly) * (ulx - llx)
+    area += 0.5 * (uly + ury) * (urx - ulx)
+    area += 0.5 * (ury + lry) * (lrx - urx)
+    area += 0.5 * (lry + lly) * (llx - lrx)
+    area = area / (dx * dy)
+    aux = np.empty((9, n, n), order='F')
+    aux[0], aux[1], aux[2] = a_x, a_y, anorm / dy
+    aux[3], aux[4], aux[5] = b_x, b_y, bnorm / dx
+    aux[6] = area
+    aux[7] = 1.0
+    aux[8] = 1.0
+    X, Y = _grid(lower, upper, (n, n))
+    xp, yp = inclusion_mapping(X, Y)                        # grid.p_centers
+    for i, ((r1, r2), (x0, y0)) in enumerate(circles):
+        in_circle = np.where(np.sqrt((xp - x0) ** 2 + (yp - y0) ** 2) <= r1)
+        aux[7][in_circle] = impedance[i]
+        aux[8][in_circle] = sound_speed[i]
+    q = np.zeros((3, n, n), order='F')
+
+    def incoming_square_wave(qbc, auxbc, t, g):             # :129-147
+        s_ = 1.0 if t < 0.05 else 0.0
+        for i in range(g):
+            ri = 2 * g - i - 1
+            alpha, beta = auxbc[0, i, :], auxbc[1, i, :]
+            u_normal = alpha * qbc[1, ri, :] + beta * qbc[2, ri, :]
+            u_tangential = -beta * qbc[1, ri, :] + alpha * qbc[2, ri, :]
+            u_normal = 2.0 * s_ - u_normal
+            qbc[0, i, :] = qbc[0, ri, :]
+            qbc[1, i, :] = alpha * u_normal - beta * u_tangential
+            qbc[2, i, :] = beta * u_normal + alpha * u_tangential
+
+    return _base('acoustics_mapped_2D', lower, upper, (n, n), q, aux=aux, limiters=MC, dimensional_split=False,
+                 transverse_waves=transverse_waves, bc_lower=[0, EXTRAP], bc_upper=[EXTRAP, EXTRAP],
+                 aux_bc_lower=[EXTRAP, EXTRAP], aux_bc_upper=[EXTRAP, EXTRAP], custom_bc_lower_full=incoming_square_wave,
+                 index_capa=6, tfinal=tfinal, num_output_times=num_output_times, mapc2p=inclusion_mapping)
 
 
 def psystem_2d(cells_per_layer=6, tfinal=1.0, num_output_times=10, stress_rel=2, dimensional_split=False,
@@ -495,6 +582,9 @@ def make_claw(sc, kernel_language='CUDA', pyclaw=None, **solver_kw):
     if sc.get('custom_bc_lower') is not None:           # BC.custom (solver.py:393-398): q fill of one face
         f = sc['custom_bc_lower']
         solver.user_bc_lower = lambda state, dim, t, qbc, auxbc, num_ghost: f(qbc, num_ghost)
+    if sc.get('custom_bc_lower_full') is not None:      # BC.custom fill that also reads auxbc and t
+        ff = sc['custom_bc_lower_full']
+        solver.user_bc_lower = lambda state, dim, t, qbc, auxbc, num_ghost: ff(qbc, auxbc, t, num_ghost)
     if sc.get('custom_aux_bc_lower') is not None:
         fl = sc['custom_aux_bc_lower']
         solver.user_aux_bc_lower = lambda state, dim, t, qbc, auxbc, num_ghost: fl(auxbc, num_ghost)

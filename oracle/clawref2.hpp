@@ -75,6 +75,7 @@ enum RpId {
   RP_PSYSTEM_2D = 10,
   RP_EULER_HLLE_2D = 11,
   RP_SHALLOW_HLLE_2D = 12,
+  RP_ACOUSTICS_MAPPED_2D = 13,
 };
 
 // =====================================================================
@@ -950,6 +951,67 @@ void rpt2_dummy(int, int, int, int meqn, int, int, int mbc, int mx, V2<R>, V2<R>
     for (int m = 1; m <= meqn; ++m) { bmasdq(m, i) = R(0.0); bpasdq(m, i) = R(0.0); }
 }
 
+// =====================================================================
+// acoustics_mapped_2D -- riemann/src/rpn2_acoustics_mapped.f90:60-131, rpt2_acoustics_mapped.f90:41-88
+// acoustics on a mapped quadrilateral grid.  aux(1:3) = unit normal + length ratio of the left edge, aux(4:6) = the
+// same of the bottom edge, aux(7) = capacity (cell area ratio), aux(8) = impedance, aux(9) = sound speed.
+// =====================================================================
+template <class R>
+void rpn2_acoustics_mapped(int ixy, int, int meqn, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R> auxl, V2<R>,
+                           V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double*) {
+  int inx, iny, ilenrat;
+  if (ixy == 1) { inx = 1; iny = 2; ilenrat = 3; } else { inx = 4; iny = 5; ilenrat = 6; }
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R alpha = auxl(inx, i), beta = auxl(iny, i);
+    R unorl = alpha * ql(2, i) + beta * ql(3, i);
+    R unorr = alpha * qr(2, i - 1) + beta * qr(3, i - 1);
+    R d1 = ql(1, i) - qr(1, i - 1);
+    R d2 = unorl - unorr;
+    R zi = auxl(8, i), zim = auxl(8, i - 1), ci = auxl(9, i), cim = auxl(9, i - 1);
+    R a1 = (-d1 + zi * d2) / (zim + zi);
+    R a2 = (d1 + zim * d2) / (zim + zi);
+    wave(1, 1, i) = -a1 * zim; wave(2, 1, i) = a1 * alpha; wave(3, 1, i) = a1 * beta;
+    s(1, i) = -cim * auxl(ilenrat, i);
+    wave(1, 2, i) = a2 * zi; wave(2, 2, i) = a2 * alpha; wave(3, 2, i) = a2 * beta;
+    s(2, i) = ci * auxl(ilenrat, i);
+  }
+  for (int m = 1; m <= meqn; ++m)
+    for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+      amdq(m, i) = s(1, i) * wave(m, 1, i);
+      apdq(m, i) = s(2, i) * wave(m, 2, i);
+    }
+}
+template <class R>
+void rpt2_acoustics_mapped(int ixy, int imp, int, int, int, int, int mbc, int mx, V2<R>, V2<R>, V2<R> aux1, V2<R> aux2,
+                           V2<R> aux3, V2<R> asdq, V2<R> bmasdq, V2<R> bpasdq, const double*) {
+  int ixtran, iytran, ilenrat;
+  if (ixy == 1) { ixtran = 4; iytran = 5; ilenrat = 6; } else { ixtran = 1; iytran = 2; ilenrat = 3; }
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    const int i1 = (imp == 1) ? i - 1 : i;
+    R asdqp = asdq(1, i);
+    R cm = aux1(9, i1), cp = aux3(9, i1);
+    R zm = aux1(8, i1), zz = aux2(8, i1), zp = aux3(8, i1);
+    R xtran = aux3(ixtran, i), ytran = aux3(iytran, i);        // geometry of cell i, whatever imp is (:56-57)
+    R asdqt = xtran * asdq(2, i) + ytran * asdq(3, i);
+    R a2 = (asdqp + zz * asdqt) / (zz + zp);
+    R bpasdqp = a2 * zp, bpasdqt = a2;
+    bpasdq(1, i) = cp * bpasdqp;
+    bpasdq(2, i) = cp * xtran * bpasdqt;
+    bpasdq(3, i) = cp * ytran * bpasdqt;
+    xtran = aux2(ixtran, i); ytran = aux2(iytran, i);
+    asdqt = xtran * asdq(2, i) + ytran * asdq(3, i);
+    R a1 = (-asdqp + zz * asdqt) / (zm + zz);
+    R bmasdqp = -a1 * zm, bmasdqt = a1;
+    bmasdq(1, i) = -cm * bmasdqp;
+    bmasdq(2, i) = -cm * xtran * bmasdqt;
+    bmasdq(3, i) = -cm * ytran * bmasdqt;
+    for (int m = 1; m <= 3; ++m) {
+      bmasdq(m, i) = bmasdq(m, i) * aux2(ilenrat, i);
+      bpasdq(m, i) = bpasdq(m, i) * aux3(ilenrat, i);
+    }
+  }
+}
+
 template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt) {
   switch (rp_id) {
     case RP_ADVECTION_2D: rpn = rpn2_advection<R>; rpt = rpt2_advection<R>; return true;
@@ -962,6 +1024,7 @@ template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt)
     case RP_PSYSTEM_2D: rpn = rpn2_psystem<R>; rpt = rpt2_psystem<R>; return true;
     case RP_EULER_HLLE_2D: rpn = rpn2_euler_hlle<R>; rpt = rpt2_dummy<R>; return true;
     case RP_SHALLOW_HLLE_2D: rpn = rpn2_shallow_hlle<R>; rpt = rpt2_dummy<R>; return true;
+    case RP_ACOUSTICS_MAPPED_2D: rpn = rpn2_acoustics_mapped<R>; rpt = rpt2_acoustics_mapped<R>; return true;
   }
   return false;
 }

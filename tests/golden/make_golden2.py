@@ -21,6 +21,8 @@ out['burgers_1d__fortran_classic'] = np.asarray(d['fortran_classic'], dtype=np.f
 d = np.load(os.path.join(REF, 'shallow_1d/expected_sols.npy'), allow_pickle=True).item()
 out['shallow_1d__dambreak_fortran_classic_roe'] = np.asarray(d['dambreak_fortran_classic_roe'], dtype=np.float64)
 out['shallow_1d__dambreak_fortran_classic_hlle'] = np.asarray(d['dambreak_fortran_classic_hlle'], dtype=np.float64)
+out['acoustics_2d_mapped__pressure'] = np.asarray(np.load(os.path.join(REF, 'acoustics_2d_mapped/pressure.npz'))['arr_0'],
+                                                   dtype=np.float64)
 for g in ('0.25_0.25', '11.75_11.75', '17.85_1.25', '3.25_18.75'):
     out['psystem_2d__gauge' + g] = np.loadtxt(os.path.join(REF, 'psystem_2d/verify_gauge%s.txt' % g))
 

@@ -34,6 +34,9 @@ def ref_solver(sc, nthreads=1):
     if sc.get('custom_bc_lower') is not None:
         f = sc['custom_bc_lower']
         s.user_bc_lower = lambda idim, qbc, g: f(qbc, g)
+    if sc.get('custom_bc_lower_full') is not None:       # BC.custom fill reading auxbc and t (solver.py:393-398)
+        ff = sc['custom_bc_lower_full']
+        s.user_bc_lower = lambda idim, qbc, g: ff(qbc, s.auxbc, s.t, g)
     if sc.get('custom_aux_bc_lower') is not None:
         fl = sc['custom_aux_bc_lower']
         s.user_aux_bc_lower = lambda idim, auxbc, g: fl(auxbc, g)

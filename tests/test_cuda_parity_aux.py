@@ -59,6 +59,24 @@ CASES.update({
 })
 
 
+CASES.update({
+    # acoustics_mapped_2D: 9 aux planes, capacity function, mapped grid; BC.custom inflow -> plug-in mode ...
+    'mapped_acoustics_cor': lambda: S.acoustics_2d_mapped(num_cells=60, transverse_waves=2),
+    'mapped_acoustics_inc': lambda: S.acoustics_2d_mapped(num_cells=45),
+    # ... and device-resident with plain extrapolation at x-lower (a pulse is put into the initial data)
+    'mapped_acoustics_resident': lambda: _mapped_resident(),
+})
+
+
+def _mapped_resident():
+    sc = S.acoustics_2d_mapped(num_cells=50, transverse_waves=2)
+    sc['custom_bc_lower_full'] = None
+    sc['bc_lower'] = [S.EXTRAP, S.EXTRAP]
+    x = (np.arange(50) + 0.5) / 50
+    sc['q'][0] = np.exp(-200 * (x[:, None] - 0.2) ** 2) * np.ones((1, 50))
+    return sc
+
+
 @pytest.mark.parametrize('name', sorted(CASES))
 def test_strict_bit_exact_vs_oracle(name):
     sc = CASES[name]()
@@ -167,3 +185,13 @@ def test_psystem_2d_gauges_golden(resident, tmp_path):
         gold = g2['psystem_2d__gauge' + name]
         assert state.gauge_data[i].shape == gold.shape
         assert np.allclose(gold, state.gauge_data[i], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize('precision', ['strict', 'fast'])
+def test_acoustics_2d_mapped_golden(precision):
+    """pyclaw/examples/acoustics_2d_mapped/test_acoustics_2d_mapped.py:6-21: max-abs < 1e-7 against pressure.npz."""
+    sc = S.acoustics_2d_mapped()
+    claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision=precision)
+    claw.run()
+    p = claw.frames[-1].q[0, :, :]
+    assert np.max(np.abs(p - goldens2()['acoustics_2d_mapped__pressure'])) < (1e-12 if precision == 'strict' else 1e-9)

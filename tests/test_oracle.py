@@ -279,3 +279,13 @@ def test_step1_reference_error_values(oracle_lib):
         s.run(sc['tfinal'], sc['num_output_times'])
         err = s.delta[0] * np.sum(np.abs(s.q - sc['q']))
         assert abs(err - val) < tol, (sc['rp'], err)
+
+
+def test_acoustics_2d_mapped_golden(oracle_lib):
+    # pyclaw/examples/acoustics_2d_mapped/test_acoustics_2d_mapped.py:6-21 (max-abs < 1e-7 against pressure.npz, 100x100,
+    # t = 0.9): pins rpn2/rpt2_acoustics_mapped (edge normals, length ratios, transverse geometry read at cell i for
+    # both imp), the capacity-function form of step2 on a mapped grid, and a BC.custom fill that reads auxbc and t
+    sc = S.acoustics_2d_mapped()
+    s = ref_solver(sc, nthreads=4)
+    s.run(sc['tfinal'], sc['num_output_times'])
+    assert np.max(np.abs(s.q[0] - goldens2()['acoustics_2d_mapped__pressure'])) < 1e-12
