@@ -200,5 +200,73 @@ struct RpAcousticsMapped2D {
   }
 };
 
+// ------------------------------------------------------------------------------------
+// shallow_bathymetry_fwave_2D -- riemann/src/rpn2_shallow_bathymetry_fwave.f90:60-140   cparam = (grav, dry_tolerance,
+// sea_level), aux(1) = bathymetry, 3 f-waves.   roe = (s1, s2, s3).  No usable transverse solver (its rpt2 reads an
+// unassigned s(2), rpt2_shallow_bathymetry_fwave.f90:80): validate_config refuses method(3) > 0.
+// ------------------------------------------------------------------------------------
+struct RpShallowBathymetryFwave2D {
+  static constexpr int MEQN = 3, MWAVES = 3, NROE = 3, NCELL = 0, MAUX = 1;
+  __device__ __forceinline__ static void normal(const RpParams& P, int dir, const double* ql, const double* qr,
+                                                const double* axl, const double* axr, double (*wave)[MEQN],
+                                                double* s, double* amdq, double* apdq, double* roe) {
+    const double grav = P.p[0], dry_tolerance = P.p[1];
+    const double dry_l = (ql[0] < dry_tolerance) ? 0.0 : 1.0;
+    const double dry_r = (qr[0] < dry_tolerance) ? 0.0 : 1.0;
+    const double hl = ql[0] * dry_l;
+    const double ul = ddiv(ql[1], ql[0]) * dry_l;
+    const double vl = ddiv(ql[2], ql[0]) * dry_l;
+    const double phil = (0.5 * grav * (hl * hl) + hl * (ul * ul)) * dry_l;
+    const double bl = axl[0];
+    const double hr = qr[0] * dry_r;
+    const double ur = ddiv(qr[1], qr[0]) * dry_r;
+    const double vr = ddiv(qr[2], qr[0]) * dry_r;
+    const double phir = (0.5 * grav * (hr * hr) + hr * (ur * ur)) * dry_r;
+    const double br = axr[0];
+    const double hbar = 0.5 * (hr + hl);
+    const double shr = sqrt(hr), shl = sqrt(hl);
+    const double uhat = ddiv(shr * ur + shl * ul, shr + shl);
+    const double chat = sqrt(grav * hbar);
+    const double fd1 = hr * ur - hl * ul;
+    const double fd2 = phir - phil + grav * hbar * (br - bl);
+    const double fd3 = hr * ur * vr - hl * ul * vl;
+    s[0] = fmin2(uhat - chat, ul - sqrt(grav * hl));
+    s[2] = fmax2(uhat + chat, ur + sqrt(grav * hr));
+    s[1] = 0.5 * (s[0] + s[2]);
+    const double beta1 = ddiv(s[2] * fd1 - fd2, s[2] - s[0]);
+    const double beta3 = ddiv(fd2 - s[0] * fd1, s[2] - s[0]);
+    const double beta2 = fd3 - beta1 * vl - beta3 * vr;
+    wave[0][0] = beta1 * 1.0; wave[0][1] = beta1 * s[0]; wave[0][2] = beta1 * vl;
+    wave[1][0] = beta2 * 0.0; wave[1][1] = beta2 * 0.0;  wave[1][2] = beta2 * 1.0;
+    wave[2][0] = beta3 * 1.0; wave[2][1] = beta3 * s[2]; wave[2][2] = beta3 * vr;
+    const double eps = (double)1.0e-14f;                      // single-precision literals in the Fortran source
+#pragma unroll
+    for (int m = 0; m < MEQN; ++m) { amdq[m] = 0.0; apdq[m] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < MWAVES; ++k) {
+      if (s[k] < -eps) {
+#pragma unroll
+        for (int m = 0; m < MEQN; ++m) amdq[m] = amdq[m] + wave[k][m];
+      } else if (s[k] > eps) {
+#pragma unroll
+        for (int m = 0; m < MEQN; ++m) apdq[m] = apdq[m] + wave[k][m];
+      } else {
+#pragma unroll
+        for (int m = 0; m < MEQN; ++m) { amdq[m] = amdq[m] + 0.5 * wave[k][m]; apdq[m] = apdq[m] + 0.5 * wave[k][m]; }
+      }
+    }
+    roe[0] = s[0]; roe[1] = s[1]; roe[2] = s[2];
+  }
+  __device__ __forceinline__ static void speeds(const RpParams& P, int dir, const double* roe, double* s) {
+    s[0] = roe[0]; s[1] = roe[1]; s[2] = roe[2];
+  }
+  __device__ __forceinline__ static void transverse(const RpParams& P, int dir, const double* roe, const double*,
+                                                    const double*, const double*, const double*, const double*,
+                                                    const double*, const double* asdq, double* bm, double* bp) {
+#pragma unroll
+    for (int m = 0; m < MEQN; ++m) { bm[m] = 0.0; bp[m] = 0.0; }
+  }
+};
+
 }  // namespace CLAW_NS
 }  // namespace clawcuda

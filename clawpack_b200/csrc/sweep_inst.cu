@@ -155,6 +155,7 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
     case 8: return launch_aux<RpVcAdvection2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 10: return launch_aux<RpPsystem2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 13: return launch_aux<RpAcousticsMapped2D, 1>(kind, P, seg_hint, num_sms, st, info);
+    case 14: return launch_aux<RpShallowBathymetryFwave2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 11:
       if (kind == 1) return launch_split_ws<RpEulerHlle2D, 1, 12>(P, seg_hint, num_sms, st, info);
       return launch_ws<RpEulerHlle2D, 1, 12, 6>(P, seg_hint, num_sms, st, info);

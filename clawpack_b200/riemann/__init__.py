@@ -19,6 +19,7 @@ _SOLVERS = {
     'euler_hlle_2D': (11, ('gamma',), 2),                     # rpn2_euler_hlle.f90:32 (+ rpt2_dummy.f90)
     'shallow_hlle_2D': (12, ('grav',), 2),                    # rpn2_shallow_hlle.f90:31 (+ rpt2_dummy.f90)
     'acoustics_mapped_2D': (13, (), 2),                       # rpn2_acoustics_mapped.f90 (geometry + coefficients in aux)
+    'shallow_bathymetry_fwave_2D': (14, ('grav', 'dry_tolerance', 'sea_level'), 2),   # rpn2_shallow_bathymetry_fwave.f90
     'psystem_2D': (10, (), 2),                                # rpn2_psystem.f90 (f-wave; coefficients + strain in aux)
     # 1-D (claw_step1_host): riemann/src/rp1_*.f90
     'advection_1D': (21, ('u',), 1),

@@ -305,6 +305,32 @@ def acoustics_2d_mapped(num_cells=100, tfinal=0.9, num_output_times=1, transvers
                  index_capa=6, tfinal=tfinal, num_output_times=num_output_times, mapc2p=inclusion_mapping)
 
 
+def sill(my=20, tfinal=10.0, num_output_times=40):
+    """pyclaw/examples/shallow_2d/sill.py:27-86: shallow water over a Gaussian hump, f-wave solver
+    shallow_bathymetry_fwave_2D (bathymetry in aux), dimensionally split, minmod; a wave maker (BC.custom) at x-lower
+    sets only part of the ghost cells -- the rest keep their previous contents, as in the reference."""
+    mx = 4 * my
+    lower, upper = (0., 0.), (4., 1.)
+    X, Y = _grid(lower, upper, (mx, my))
+    aux = np.empty((1, mx, my), order='F')
+    aux[0] = 0.8 * np.exp(-10 * ((X - 1.) ** 2 + (Y - 0.5) ** 2))
+    q = np.zeros((3, mx, my), order='F')
+    q[0] = 1. - aux[0]
+    amplitude, t_bdy = 0.1, 5.
+
+    def wave_maker_bc(qbc, auxbc, t, g):                    # :31-42
+        qbc[0, :g, :] = qbc[0, g, :]
+        vwall = amplitude * (np.sin(t * np.pi / 1.5)) if t <= t_bdy else 0.
+        for ibc in range(g - 1):
+            qbc[1, g - ibc - 1, :] = 2 * vwall - qbc[1, g + ibc, :]
+
+    return _base('shallow_bathymetry_fwave_2D', lower, upper, (mx, my), q, aux=aux,
+                 problem_data={'grav': 1.0, 'dry_tolerance': 1.e-3, 'sea_level': 0.}, limiters=MINMOD,
+                 dimensional_split=True, bc_lower=[0, WALL], bc_upper=[EXTRAP, WALL], aux_bc_lower=[EXTRAP, EXTRAP],
+                 aux_bc_upper=[EXTRAP, EXTRAP], custom_bc_lower_full=wave_maker_bc, fwave=True, tfinal=tfinal,
+                 num_output_times=num_output_times)
+
+
 def psystem_2d(cells_per_layer=6, tfinal=1.0, num_output_times=10, stress_rel=2, dimensional_split=False,
                transverse_waves=None, size=20.0):
     """pyclaw/examples/psystem_2d/psystem_2d.py:126-226 (classic branch): nonlinear elasticity in a checkerboard

@@ -76,6 +76,7 @@ enum RpId {
   RP_EULER_HLLE_2D = 11,
   RP_SHALLOW_HLLE_2D = 12,
   RP_ACOUSTICS_MAPPED_2D = 13,
+  RP_SHALLOW_BATHYMETRY_FWAVE_2D = 14,
 };
 
 // =====================================================================
@@ -1012,6 +1013,65 @@ void rpt2_acoustics_mapped(int ixy, int imp, int, int, int, int, int mbc, int mx
   }
 }
 
+// =====================================================================
+// shallow_bathymetry_fwave_2D -- riemann/src/rpn2_shallow_bathymetry_fwave.f90:60-140
+// cparam = (grav, dry_tolerance, sea_level); aux(1) = bathymetry; 3 f-waves.
+// Its rpt2 (rpt2_shallow_bathymetry_fwave.f90:80) reads s(2) before assigning it (`s(2) = 0.5d0*(s(1)+s(2))`), so the
+// transverse solver has no defined result: like rpt2_dummy it is refused (the reference example, shallow_2d/sill.py:48,
+// runs dimensionally split: "No transverse solver available").
+// =====================================================================
+template <class R>
+void rpn2_shallow_bathymetry_fwave(int ixy, int, int num_eqn, int num_waves, int, int mbc, int mx, V2<R> ql, V2<R> qr,
+                                   V2<R> auxl, V2<R> auxr, V3<R> fwave, V2<R> s, V2<R> amdq, V2<R> apdq,
+                                   const double* cparam) {
+  const R grav = R(cparam[0]), dry_tolerance = R(cparam[1]);
+  const int ni = (ixy == 1) ? 2 : 3, ti = (ixy == 1) ? 3 : 2;
+  // `-1.0e-14` / `1.0e-14` in the fluctuation split are single-precision literals
+  const R eps = R((double)1.0e-14f);
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    for (int m = 1; m <= num_eqn; ++m) { amdq(m, i) = R(0.0); apdq(m, i) = R(0.0); }     // amdq = 0.d0; apdq = 0.d0
+    R dry_l = (qr(1, i - 1) < dry_tolerance) ? R(0.0) : R(1.0);
+    R dry_r = (ql(1, i) < dry_tolerance) ? R(0.0) : R(1.0);
+    R hl = qr(1, i - 1) * dry_l;
+    R ul = qr(ni, i - 1) / qr(1, i - 1) * dry_l;
+    R vl = qr(ti, i - 1) / qr(1, i - 1) * dry_l;
+    R phil = (R(0.5) * grav * (hl * hl) + hl * (ul * ul)) * dry_l;
+    R bl = auxr(1, i - 1);
+    R hr = ql(1, i) * dry_r;
+    R ur = ql(ni, i) / ql(1, i) * dry_r;
+    R vr = ql(ti, i) / ql(1, i) * dry_r;
+    R phir = (R(0.5) * grav * (hr * hr) + hr * (ur * ur)) * dry_r;
+    R br = auxl(1, i);
+    R hbar = R(0.5) * (hr + hl);
+    R uhat = (r_sqrt(hr) * ur + r_sqrt(hl) * ul) / (r_sqrt(hr) + r_sqrt(hl));
+    R chat = r_sqrt(grav * hbar);
+    R fd1 = hr * ur - hl * ul;
+    R fd2 = phir - phil + grav * hbar * (br - bl);
+    R fd3 = hr * ur * vr - hl * ul * vl;
+    s(1, i) = r_min(uhat - chat, ul - r_sqrt(grav * hl));
+    s(3, i) = r_max(uhat + chat, ur + r_sqrt(grav * hr));
+    s(2, i) = R(0.5) * (s(1, i) + s(3, i));
+    R beta1 = (s(3, i) * fd1 - fd2) / (s(3, i) - s(1, i));
+    R beta3 = (fd2 - s(1, i) * fd1) / (s(3, i) - s(1, i));
+    R beta2 = fd3 - beta1 * vl - beta3 * vr;
+    fwave(1, 1, i) = beta1 * R(1.0); fwave(ni, 1, i) = beta1 * s(1, i); fwave(ti, 1, i) = beta1 * vl;
+    fwave(1, 2, i) = beta2 * R(0.0); fwave(ni, 2, i) = beta2 * R(0.0);  fwave(ti, 2, i) = beta2 * R(1.0);
+    fwave(1, 3, i) = beta3 * R(1.0); fwave(ni, 3, i) = beta3 * s(3, i); fwave(ti, 3, i) = beta3 * vr;
+    for (int k = 1; k <= num_waves; ++k) {
+      if (s(k, i) < -eps) {
+        for (int m = 1; m <= num_eqn; ++m) amdq(m, i) = amdq(m, i) + fwave(m, k, i);
+      } else if (s(k, i) > eps) {
+        for (int m = 1; m <= num_eqn; ++m) apdq(m, i) = apdq(m, i) + fwave(m, k, i);
+      } else {
+        for (int m = 1; m <= num_eqn; ++m) {
+          amdq(m, i) = amdq(m, i) + R(0.5) * fwave(m, k, i);
+          apdq(m, i) = apdq(m, i) + R(0.5) * fwave(m, k, i);
+        }
+      }
+    }
+  }
+}
+
 template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt) {
   switch (rp_id) {
     case RP_ADVECTION_2D: rpn = rpn2_advection<R>; rpt = rpt2_advection<R>; return true;
@@ -1025,6 +1085,7 @@ template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt)
     case RP_EULER_HLLE_2D: rpn = rpn2_euler_hlle<R>; rpt = rpt2_dummy<R>; return true;
     case RP_SHALLOW_HLLE_2D: rpn = rpn2_shallow_hlle<R>; rpt = rpt2_dummy<R>; return true;
     case RP_ACOUSTICS_MAPPED_2D: rpn = rpn2_acoustics_mapped<R>; rpt = rpt2_acoustics_mapped<R>; return true;
+    case RP_SHALLOW_BATHYMETRY_FWAVE_2D: rpn = rpn2_shallow_bathymetry_fwave<R>; rpt = rpt2_dummy<R>; return true;
   }
   return false;
 }
@@ -1226,7 +1287,8 @@ int step2(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int 
   Rpn2<R> rpn2; Rpt2<R> rpt2;
   if (!select_rp2<R>(rp_id, rpn2, rpt2)) return 1;
   // rpt2_dummy.f90 ("Error: Dummy transverse Riemann solver called!") leaves its outputs unset: refuse instead
-  if ((rp_id == RP_EULER_HLLE_2D || rp_id == RP_SHALLOW_HLLE_2D) && method[2] > 0) return 2;
+  if ((rp_id == RP_EULER_HLLE_2D || rp_id == RP_SHALLOW_HLLE_2D || rp_id == RP_SHALLOW_BATHYMETRY_FWAVE_2D) && method[2] > 0)
+    return 2;
   if (maxm < mx || maxm < my) return 2;
   const int nx = mx + 2 * num_ghost;
   const int maux_eff = method[6];                       // step2.f90:75  num_aux = method(7)

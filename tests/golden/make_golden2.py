@@ -15,6 +15,7 @@ d = np.load(os.path.join(REF, 'euler_2d/expected_sols.npy'), allow_pickle=True).
 out['euler_2d__shock_bubble_interaction'] = np.asarray(d['shock_bubble_interaction'], dtype=np.float64)
 out['euler_2d__quadrants_hlle'] = np.asarray(d['quadrants_hlle'], dtype=np.float64)
 d = np.load(os.path.join(REF, 'shallow_2d/expected_sols.npy'), allow_pickle=True).item()
+out['shallow_2d__sill'] = np.asarray(d['sill'], dtype=np.float64)
 out['shallow_2d__radialdambreak_classic_hlle'] = np.asarray(d['radialdambreak_classic_hlle'], dtype=np.float64)
 d = np.load(os.path.join(REF, 'burgers_1d/expected_sols.npy'), allow_pickle=True).item()
 out['burgers_1d__fortran_classic'] = np.asarray(d['fortran_classic'], dtype=np.float64)

@@ -68,6 +68,18 @@ CASES.update({
 })
 
 
+CASES.update({
+    # shallow_bathymetry_fwave_2D (3 f-waves, bathymetry in aux): wave-maker BC.custom -> plug-in mode, and
+    # device-resident with walls all round
+    'sill_split': lambda: S.sill(my=12, tfinal=2.0, num_output_times=2),
+    # (unsplit only with complete ghost fills: the wave maker leaves ghost cells stale, and the unsplit Fortran
+    # step leaves partial sums in them that claw_step2_host documents it does not reproduce)
+    'sill_unsplit_notrans': lambda: dict(S.sill(my=10), dimensional_split=False, transverse_waves=0, cfl_max=0.5,
+                                         cfl_desired=0.45, custom_bc_lower_full=None, bc_lower=[S.EXTRAP, S.WALL]),
+    'sill_resident': lambda: dict(S.sill(my=16), custom_bc_lower_full=None, bc_lower=[S.WALL, S.WALL]),
+})
+
+
 def _mapped_resident():
     sc = S.acoustics_2d_mapped(num_cells=50, transverse_waves=2)
     sc['custom_bc_lower_full'] = None
@@ -195,3 +207,28 @@ def test_acoustics_2d_mapped_golden(precision):
     claw.run()
     p = claw.frames[-1].q[0, :, :]
     assert np.max(np.abs(p - goldens2()['acoustics_2d_mapped__pressure'])) < (1e-12 if precision == 'strict' else 1e-9)
+
+
+@pytest.mark.parametrize('precision', ['strict', 'fast'])
+def test_sill_golden(precision):
+    """pyclaw/examples/shallow_2d/test_shallow2d.py:36-37: L1 < 1e-6 against expected_sols['sill']."""
+    sc = S.sill()
+    claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision=precision)
+    claw.run()
+    h = claw.frames[claw.num_output_times].state.get_q_global()[0].reshape(-1)
+    dx, dy = claw.solution.domain.grid.delta
+    g = goldens2()['shallow_2d__sill']
+    assert dx * dy * np.sum(np.abs(h - g)) < 1e-6
+    assert np.max(np.abs(h - g)) < (1e-12 if precision == 'strict' else 1e-9)
+
+
+def test_missing_transverse_solver_is_refused():
+    """rpt2_dummy solvers and shallow_bathymetry_fwave_2D (whose rpt2 reads an unassigned value) cannot take transverse
+    corrections: the library says so instead of producing garbage like the reference would."""
+    from clawpack_b200._lib import ClawCudaError
+    for sc in (dict(S.sill(my=8), dimensional_split=False, transverse_waves=2, custom_bc_lower_full=None,
+                    bc_lower=[S.WALL, S.WALL]),
+               dict(S.quadrants(mx=12, my=12, riemann_solver='hlle'), dimensional_split=False, transverse_waves=1)):
+        claw = S.make_claw(sc, kernel_language='CUDA')
+        with pytest.raises(ClawCudaError):
+            claw.run()

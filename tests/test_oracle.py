@@ -289,3 +289,16 @@ def test_acoustics_2d_mapped_golden(oracle_lib):
     s = ref_solver(sc, nthreads=4)
     s.run(sc['tfinal'], sc['num_output_times'])
     assert np.max(np.abs(s.q[0] - goldens2()['acoustics_2d_mapped__pressure'])) < 1e-12
+
+
+def test_sill_golden(oracle_lib):
+    # pyclaw/examples/shallow_2d/test_shallow2d.py:36-37 (L1 < 1e-6 against expected_sols['sill'], 80x20, t = 10):
+    # pins rpn2_shallow_bathymetry_fwave (3 f-waves, bathymetry source in the flux difference), the f-wave branch of
+    # flux2 under step2ds, and a BC.custom wave maker that leaves part of the ghost cells untouched
+    sc = S.sill()
+    s = ref_solver(sc)
+    s.run(sc['tfinal'], sc['num_output_times'])
+    g = goldens2()['shallow_2d__sill']
+    dx, dy = s.delta
+    assert dx * dy * np.sum(np.abs(s.q[0].reshape(-1) - g)) < 1e-6
+    assert np.max(np.abs(s.q[0].reshape(-1) - g)) < 1e-12
