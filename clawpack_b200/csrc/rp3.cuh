@@ -310,5 +310,40 @@ struct RpEuler3D {
   }
 };
 
+// ------------------------------------------------------------------------------------
+// burgers_3D -- riemann/src/rpn3_burgers.f90:50-68, rpt3_burgers.f90:55-61, rptt3_burgers.f90:60-66
+// cparam = coeff(3); ctx = (q_left + q_right) of the interface (the transverse speeds are built from it)
+// ------------------------------------------------------------------------------------
+struct RpBurgers3D {
+  static constexpr int MEQN = 1, MWAVES = 1, MAUX = 0, NCTX = 1;
+  template <int IXYZ, int ICOOR> struct TV {
+    static constexpr int N = MEQN;
+    __host__ __device__ static constexpr int comp(int k) { return k; }
+  };
+  template <int IXYZ>
+  __device__ __forceinline__ static void normal(const RpParams& P, const double* ql, const double* qr,
+                                                const double*, const double*, double (*wave)[MEQN], double* s,
+                                                double* amdq, double* apdq, double* ctx) {
+    const double coeff = P.p[IXYZ];
+    wave[0][0] = qr[0] - ql[0];
+    ctx[0] = ql[0] + qr[0];
+    s[0] = coeff * 0.5 * ctx[0];
+    amdq[0] = fmin2(s[0], 0.0) * wave[0][0];
+    apdq[0] = fmax2(s[0], 0.0) * wave[0][0];
+    if (ql[0] < 0.0 && qr[0] > 0.0) {                        // transonic rarefaction (:61-66)
+      amdq[0] = -(coeff * 0.5 * (ql[0] * ql[0]));
+      apdq[0] = coeff * 0.5 * (qr[0] * qr[0]);
+    }
+  }
+  template <int IXYZ, int ICOOR, bool TT = false>
+  __device__ __forceinline__ static void transverse(const RpParams& P, const double* ctx, const double*, const double*,
+                                                    const double*, const double* asdq, double* bm, double* bp) {
+    constexpr int IUVW = (IXYZ + ICOOR - 1) % 3;             // 0-based form of iuvw = ixyz + icoor - 1 (wrapped)
+    const double sb = P.p[IUVW] * 0.5 * ctx[0];
+    bm[0] = fmin2(sb, 0.0) * asdq[0];
+    bp[0] = fmax2(sb, 0.0) * asdq[0];
+  }
+};
+
 }  // namespace CLAW_NS
 }  // namespace clawcuda

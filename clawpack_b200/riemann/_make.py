@@ -20,7 +20,8 @@ class _CParam(object):
         return list(self._names)
 
     def values(self):
-        return [float(getattr(self, n)) for n in self._names]
+        import numpy as np
+        return [float(v) for n in self._names for v in np.atleast_1d(getattr(self, n))]      # arrays (coeff(3)) flatten
 
 
 def make(name, rp_id, cparam_names, num_dim):

@@ -504,6 +504,19 @@ def acoustics_3d_general(mx=18, my=15, mz=13, **kw):
     return sc
 
 
+def burgers_3d(mx=24, my=20, mz=18, coeff=(1.0, 0.7, -0.5), dimensional_split=False, transverse_waves=22, tfinal=0.2,
+               num_output_times=2):
+    """3-D Burgers equation (riemann burgers_3D; the reference ships the solver but no example): smooth data with both
+    signs, so that transonic rarefactions (the entropy fix) and all three coefficient signs occur; periodic."""
+    X, Y, Z = _grid((0., 0., 0.), (1., 1., 1.), (mx, my, mz))
+    q = np.empty((1, mx, my, mz), order='F')
+    q[0] = np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y) + 0.4 * np.sin(2 * np.pi * (Z + 0.3 * X)) + 0.1
+    return _base('burgers_3D', (0., 0., 0.), (1., 1., 1.), (mx, my, mz), q, problem_data={'coeff': list(coeff)},
+                 limiters=VANLEER, dimensional_split=bool(dimensional_split), transverse_waves=transverse_waves,
+                 cfl_max=1.0, cfl_desired=0.8, dt_initial=0.01, bc_lower=[PERIODIC] * 3, bc_upper=[PERIODIC] * 3,
+                 tfinal=tfinal, num_output_times=num_output_times)
+
+
 def euler_3d_shocktube(mx=10, my=10, mz=128, tfinal=0.2, num_output_times=10):
     """pyclaw/examples/euler_3d/shocktube.py:17-66 as run by test_euler3d.py:27 (dimension-split, MC)."""
     gamma = 1.4

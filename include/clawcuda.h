@@ -55,6 +55,7 @@ enum {
   CLAW_RP_SHALLOW_HLLE_2D = 12,        /* rpn2_shallow_hlle.f90 + rpt2_dummy.f90 (no transverse solver) */
   CLAW_RP_ACOUSTICS_MAPPED_2D = 13,    /* rpn2_acoustics_mapped.f90, rpt2_acoustics_mapped.f90 (9 aux planes, mapped grid) */
   CLAW_RP_SHALLOW_BATHYMETRY_FWAVE_2D = 14, /* rpn2_shallow_bathymetry_fwave.f90 (f-wave, aux: bathymetry; no transverse solver) */
+  CLAW_RP_BURGERS_3D = 15,             /* rpn3_burgers.f90, rpt3_burgers.f90, rptt3_burgers.f90 (cparam = coeff(3)) */
   /* 1-D (claw_step1_host only) */
   CLAW_RP_ADVECTION_1D = 21,           /* riemann/src/rp1_advection.f90 */
   CLAW_RP_ACOUSTICS_1D = 22,           /* rp1_acoustics.f90 */

@@ -14,7 +14,7 @@
 
 namespace clawref {
 
-enum RpId3 { RP_EULER_3D = 6 };
+enum RpId3 { RP_EULER_3D = 6, RP_BURGERS_3D = 15 };
 
 // gadd(m, side 1:2, slice -1:1, i)    (flux3.f90:121-122)
 template <class R> struct V4 {
@@ -358,10 +358,56 @@ void rptt3_euler(int ixyz, int icoor, int, int, int maxm, int meqn, int mwaves, 
   euler3_transverse(ixyz, icoor, maxm, meqn, mwaves, mbc, mx, ql, qr, bsasdq, cmbsasdq, cpbsasdq, cparam);
 }
 
+// =====================================================================
+// burgers_3D -- riemann/src/rpn3_burgers.f90:50-68, rpt3_burgers.f90:55-61, rptt3_burgers.f90:60-66
+// q_t + (a u^2/2)_x + (b u^2/2)_y + (c u^2/2)_z = 0;  cparam = coeff(3) = (a, b, c).  Parity unpinned: no reference
+// example or test runs this solver.
+// =====================================================================
+template <class R>
+void rpn3_burgers(int ixyz, int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>,
+                  V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double* cparam) {
+  const R coeff = R(cparam[ixyz - 1]);
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    wave(1, 1, i) = ql(1, i) - qr(1, i - 1);
+    s(1, i) = coeff * R(0.5) * (qr(1, i - 1) + ql(1, i));
+    amdq(1, i) = r_min(s(1, i), R(0.0)) * wave(1, 1, i);
+    apdq(1, i) = r_max(s(1, i), R(0.0)) * wave(1, 1, i);
+    if (qr(1, i - 1) < R(0.0) && ql(1, i) > R(0.0)) {              // efix = .true. (:43, :61-66)
+      amdq(1, i) = -(coeff * R(0.5) * (qr(1, i - 1) * qr(1, i - 1)));
+      apdq(1, i) = coeff * R(0.5) * (ql(1, i) * ql(1, i));
+    }
+  }
+}
+template <class R>
+void rpt3_burgers(int ixyz, int icoor, int, int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr,
+                  A3<R>, A3<R>, A3<R>, V2<R> asdq, V2<R> bmasdq, V2<R> bpasdq, const double* cparam) {
+  int iuvw = ixyz + icoor - 1;
+  if (iuvw > 3) iuvw -= 3;
+  const R coeff = R(cparam[iuvw - 1]);
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R sb = coeff * R(0.5) * (qr(1, i - 1) + ql(1, i));
+    bmasdq(1, i) = r_min(sb, R(0.0)) * asdq(1, i);
+    bpasdq(1, i) = r_max(sb, R(0.0)) * asdq(1, i);
+  }
+}
+template <class R>
+void rptt3_burgers(int ixyz, int icoor, int, int, int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr,
+                   A3<R>, A3<R>, A3<R>, V2<R> bsasdq, V2<R> cmbsasdq, V2<R> cpbsasdq, const double* cparam) {
+  int iuvw = ixyz + icoor - 1;
+  if (iuvw > 3) iuvw -= 3;
+  const R coeff = R(cparam[iuvw - 1]);
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R sc = coeff * R(0.5) * (qr(1, i - 1) + ql(1, i));
+    cmbsasdq(1, i) = r_min(sc, R(0.0)) * bsasdq(1, i);
+    cpbsasdq(1, i) = r_max(sc, R(0.0)) * bsasdq(1, i);
+  }
+}
+
 template <class R> inline bool select_rp3(int rp_id, Rpn3<R>& rpn, Rpt3<R>& rpt, Rptt3<R>& rptt) {
   switch (rp_id) {
     case RP_VC_ACOUSTICS_3D: rpn = rpn3_vc_acoustics<R>; rpt = rpt3_vc_acoustics<R>; rptt = rptt3_vc_acoustics<R>; return true;
     case RP_EULER_3D: rpn = rpn3_euler<R>; rpt = rpt3_euler<R>; rptt = rptt3_euler<R>; return true;
+    case RP_BURGERS_3D: rpn = rpn3_burgers<R>; rpt = rpt3_burgers<R>; rptt = rptt3_burgers<R>; return true;
   }
   return false;
 }

@@ -33,6 +33,7 @@ RP_IDS = {
     'shallow_hlle_2D': 12,
     'acoustics_mapped_2D': 13,
     'shallow_bathymetry_fwave_2D': 14,
+    'burgers_3D': 15,
     'advection_1D': 21,
     'acoustics_1D': 22,
     'burgers_1D': 23,
@@ -56,6 +57,7 @@ CPARAM_NAMES = {
     'shallow_hlle_2D': ('grav',),     # rpn2_shallow_hlle.f90:31
     'acoustics_mapped_2D': (),        # rpn2_acoustics_mapped.f90: everything lives in aux
     'shallow_bathymetry_fwave_2D': ('grav', 'dry_tolerance', 'sea_level'),   # rpn2_shallow_bathymetry_fwave.f90:44-45
+    'burgers_3D': ('coeff',),         # rpn3_burgers.f90:45: common /cparam/ coeff(3)
     'advection_1D': ('u',),           # rp1_advection.f90
     'acoustics_1D': ('rho', 'bulk', 'cc', 'zz'),   # rp1_acoustics.f90
     'burgers_1D': (),
@@ -65,11 +67,11 @@ CPARAM_NAMES = {
 NUM_EQN = {'advection_2D': 1, 'acoustics_2D': 3, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
            'vc_acoustics_3D': 4, 'euler_3D': 5, 'vc_acoustics_2D': 3, 'vc_advection_2D': 1, 'euler_5wave_2D': 5,
            'psystem_2D': 3, 'euler_hlle_2D': 4, 'shallow_hlle_2D': 3,
-           'acoustics_mapped_2D': 3, 'shallow_bathymetry_fwave_2D': 3, 'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2}
+           'acoustics_mapped_2D': 3, 'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2}
 NUM_WAVES = {'advection_2D': 1, 'acoustics_2D': 2, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
              'vc_acoustics_3D': 2, 'euler_3D': 3, 'vc_acoustics_2D': 2, 'vc_advection_2D': 1, 'euler_5wave_2D': 5,
              'psystem_2D': 2, 'euler_hlle_2D': 2, 'shallow_hlle_2D': 2,
-             'acoustics_mapped_2D': 2, 'shallow_bathymetry_fwave_2D': 3, 'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2}
+             'acoustics_mapped_2D': 2, 'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2}
 
 BC_CUSTOM, BC_EXTRAP, BC_PERIODIC, BC_WALL = 0, 1, 2, 3
 
@@ -211,7 +213,8 @@ class RefSolver(object):
         self.user_aux_bc_lower = None       # f(idim, auxbc, num_ghost): BC.custom fill of aux
         self.user_aux_bc_upper = None
         self.nthreads = 1
-        self.cparam = np.array([float(problem_data[k]) for k in CPARAM_NAMES[rp_name]] + [0.0], dtype=np.float64)
+        self.cparam = np.array([float(v) for k in CPARAM_NAMES[rp_name] for v in np.atleast_1d(problem_data[k])] + [0.0],
+                               dtype=np.float64)
         self.dt = self.dt_initial
         self.dt_old = None
         self.cfl = self.cfl_desired          # Solver.__init__: CFL(self.cfl_desired)  (solver.py:199)

@@ -56,6 +56,11 @@ CASES3 = {
     'ac_general_21_superbee': lambda: _ac_general(mx=11, my=17, mz=9, transverse_waves=21, limiters=S.SUPERBEE),
     'ac_general_11_o1': lambda: _ac_general(mx=8, my=9, mz=19, transverse_waves=11, order=1),
     'ac_general_split': lambda: _ac_general(mx=13, my=8, mz=11, dimensional_split=True),
+    # burgers_3D: scalar, coefficient per direction, entropy fix; no reference example (parity unpinned)
+    'burgers3_unsplit_22': lambda: S.burgers_3d(),
+    'burgers3_unsplit_11': lambda: S.burgers_3d(mx=30, my=9, mz=11, transverse_waves=11),
+    'burgers3_unsplit_21_minmod': lambda: dict(S.burgers_3d(mx=13, my=17, mz=10, transverse_waves=21), limiters=S.MINMOD),
+    'burgers3_split': lambda: S.burgers_3d(mx=16, my=12, mz=20, dimensional_split=True),
     'ac_tiny': lambda: _ac(mx=3, my=2, mz=4),
     'ac_tile_edges': lambda: _ac(mx=57, my=7, mz=13),          # 28-lane strips, 6-row tiles: ragged edges
     'ac_tile_edges2': lambda: _ac(mx=31, my=13, mz=6),
