@@ -30,12 +30,14 @@ static cudaError_t launch_kernel(KERN kern, int NT, int smem, bool x_only, Sweep
   int seg = seg_hint;
   if (seg <= 0) {
     // enough CTAs for >= 6 waves of resident CTAs, but segments not shorter than 32 rows
-    // (each segment pays 3-4 warm-up rows) nor longer than 256
+    // (each segment pays 3-4 warm-up rows) nor longer than 256.  Small grids that cannot even fill the GPU once with
+    // 32-row segments are latency-bound on the march length instead: there the floor is 8 rows.
     const long long want = 6LL * num_sms * occ;
     long long nseg = (want + strips - 1) / strips;
     if (nseg < 1) nseg = 1;
     seg = (int)((rows + nseg - 1) / nseg);
-    if (seg < 32) seg = 32;
+    const int min_seg = ((long long)strips * ((rows + 31) / 32) >= (long long)num_sms * occ) ? 32 : 8;
+    if (seg < min_seg) seg = min_seg;
     if (seg > 256) seg = 256;
   }
   if (seg > rows) seg = rows;
