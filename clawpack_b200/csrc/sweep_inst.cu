@@ -156,6 +156,9 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
     case 7: return launch_aux<RpVcAcoustics2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 8: return launch_aux<RpVcAdvection2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 10: return launch_aux<RpPsystem2D, 2>(kind, P, seg_hint, num_sms, st, info);
+    case 16:
+      if (kind == 1) return launch_split_ws<RpBurgers2D, 1, 16>(P, seg_hint, num_sms, st, info);
+      return launch_ws<RpBurgers2D, 1, 16, 6>(P, seg_hint, num_sms, st, info);
     case 13: return launch_aux<RpAcousticsMapped2D, 1>(kind, P, seg_hint, num_sms, st, info);
     case 14: return launch_aux<RpShallowBathymetryFwave2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 11:

@@ -504,6 +504,17 @@ def acoustics_3d_general(mx=18, my=15, mz=13, **kw):
     return sc
 
 
+def burgers_2d(mx=60, my=50, dimensional_split=False, transverse_waves=2, tfinal=0.3, num_output_times=2):
+    """2-D Burgers equation (riemann burgers_2D; no reference example): data of both signs, periodic."""
+    X, Y = _grid((0., 0.), (1., 1.), (mx, my))
+    q = np.empty((1, mx, my), order='F')
+    q[0] = np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y) + 0.3
+    return _base('burgers_2D', (0., 0.), (1., 1.), (mx, my), q, limiters=VANLEER,
+                 dimensional_split=bool(dimensional_split), transverse_waves=transverse_waves, dt_initial=0.01,
+                 bc_lower=[PERIODIC, PERIODIC], bc_upper=[PERIODIC, PERIODIC], tfinal=tfinal,
+                 num_output_times=num_output_times)
+
+
 def burgers_3d(mx=24, my=20, mz=18, coeff=(1.0, 0.7, -0.5), dimensional_split=False, transverse_waves=22, tfinal=0.2,
                num_output_times=2):
     """3-D Burgers equation (riemann burgers_3D; the reference ships the solver but no example): smooth data with both

@@ -77,6 +77,7 @@ enum RpId {
   RP_SHALLOW_HLLE_2D = 12,
   RP_ACOUSTICS_MAPPED_2D = 13,
   RP_SHALLOW_BATHYMETRY_FWAVE_2D = 14,
+  RP_BURGERS_2D = 16,                // (15 = burgers_3D, clawref3.hpp)
 };
 
 // =====================================================================
@@ -1072,6 +1073,34 @@ void rpn2_shallow_bathymetry_fwave(int ixy, int, int num_eqn, int num_waves, int
   }
 }
 
+// =====================================================================
+// burgers_2D -- riemann/src/rpn2_burgers.f90:40-56, rpt2_burgers.f90:38-42   q_t + (q^2/2)_x + (q^2/2)_y = 0
+// Parity unpinned: the reference ships no 2-D Burgers example or test.
+// =====================================================================
+template <class R>
+void rpn2_burgers(int, int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>,
+                  V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    wave(1, 1, i) = ql(1, i) - qr(1, i - 1);
+    s(1, i) = R(0.5) * (qr(1, i - 1) + ql(1, i));
+    amdq(1, i) = r_min(s(1, i), R(0.0)) * wave(1, 1, i);
+    apdq(1, i) = r_max(s(1, i), R(0.0)) * wave(1, 1, i);
+    if (qr(1, i - 1) < R(0.0) && ql(1, i) > R(0.0)) {          // efix = .true.
+      amdq(1, i) = -(R(0.5) * (qr(1, i - 1) * qr(1, i - 1)));
+      apdq(1, i) = R(0.5) * (ql(1, i) * ql(1, i));
+    }
+  }
+}
+template <class R>
+void rpt2_burgers(int, int, int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>, V2<R>,
+                  V2<R> asdq, V2<R> bmasdq, V2<R> bpasdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R sb = R(0.5) * (qr(1, i - 1) + ql(1, i));
+    bmasdq(1, i) = r_min(sb, R(0.0)) * asdq(1, i);
+    bpasdq(1, i) = r_max(sb, R(0.0)) * asdq(1, i);
+  }
+}
+
 template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt) {
   switch (rp_id) {
     case RP_ADVECTION_2D: rpn = rpn2_advection<R>; rpt = rpt2_advection<R>; return true;
@@ -1086,6 +1115,7 @@ template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt)
     case RP_SHALLOW_HLLE_2D: rpn = rpn2_shallow_hlle<R>; rpt = rpt2_dummy<R>; return true;
     case RP_ACOUSTICS_MAPPED_2D: rpn = rpn2_acoustics_mapped<R>; rpt = rpt2_acoustics_mapped<R>; return true;
     case RP_SHALLOW_BATHYMETRY_FWAVE_2D: rpn = rpn2_shallow_bathymetry_fwave<R>; rpt = rpt2_dummy<R>; return true;
+    case RP_BURGERS_2D: rpn = rpn2_burgers<R>; rpt = rpt2_burgers<R>; return true;
   }
   return false;
 }

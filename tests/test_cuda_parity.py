@@ -42,6 +42,9 @@ CASES = {
     'euler_hlle_split': lambda: S.quadrants(mx=70, my=50, riemann_solver='hlle'),
     'euler_hlle_unsplit_notrans': lambda: dict(S.quadrants(mx=40, my=66, riemann_solver='hlle'), dimensional_split=False),
     'shallow_hlle_split': lambda: S.radial_dam_break(mx=60, my=45, riemann_solver='hlle'),
+    'burgers2_unsplit_cor': lambda: S.burgers_2d(),
+    'burgers2_unsplit_inc_minmod': lambda: dict(S.burgers_2d(mx=31, my=77, transverse_waves=1), limiters=S.MINMOD),
+    'burgers2_split': lambda: S.burgers_2d(mx=90, my=33, dimensional_split=True),
     'euler_tiny': lambda: dict(S.quadrants(mx=3, my=2), dimensional_split=False, transverse_waves=2),
     'euler_wide_strip_edge': lambda: dict(S.quadrants(mx=249, my=9), dimensional_split=False, transverse_waves=2),
 }
