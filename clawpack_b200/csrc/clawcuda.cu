@@ -484,8 +484,13 @@ int validate_config(claw_solver* h) {
         return fail(h, 35, "limiter id %d of wave family %d is not defined by philim.f90 (0..5)", h->mthlim[mw], mw);
     return 0;
   }
-  if (h->rp_id != 5 && h->rp_id != 6 && h->rp_id != 15)
+  if (h->rp_id != 5 && h->rp_id != 6 && h->rp_id != 15 && h->rp_id != 17)
     return fail(h, 30, "rp_id %d is not a 3-D Riemann solver of this build", h->rp_id);
+  {
+    const int need_aux = (h->rp_id == 5) ? 2 : (h->rp_id == 17 ? 3 : 0);      // RP::MAUX of rp3.cuh
+    if (h->maux < need_aux)
+      return fail(h, 31, "Riemann solver %d reads %d aux components, the state has num_aux=%d", h->rp_id, need_aux, h->maux);
+  }
   if (h->method[5] != 0) return fail(h, 31, "capacity functions are not supported by the 3-D CUDA kernels yet (index_capa=%d)", h->method[5] - 1);
   if (h->use_fwave) return fail(h, 32, "f-wave solvers are not supported by the CUDA kernels yet");
   if (h->method[1] != 1 && h->method[1] != 2) return fail(h, 33, "order must be 1 or 2 (got %d)", h->method[1]);
@@ -524,10 +529,10 @@ int claw_create(claw_solver** out, int ndim, int rp_id, int meqn, int mwaves, in
   if (num_ghost != 2) return fail(nullptr, 3, "claw_create: num_ghost must be 2 (classic solvers), got %d", num_ghost);
   if (meqn < 1 || meqn > 8 || mwaves < 1 || mwaves > 8 || maux < 0)
     return fail(nullptr, 4, "claw_create: bad sizes meqn=%d mwaves=%d maux=%d", meqn, mwaves, maux);
-  static const int k_meqn[] = {0, 1, 3, 4, 3, 4, 5, 3, 1, 5, 3, 4, 3, 3, 3, 1, 1},
-                   k_mwaves[] = {0, 1, 2, 4, 3, 2, 3, 2, 1, 5, 2, 2, 2, 2, 3, 1, 1},
-                   k_ndim[] = {0, 2, 2, 2, 2, 3, 3, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2};
-  if (rp_id < 1 || rp_id > 16) return fail(nullptr, 5, "claw_create: unknown rp_id %d", rp_id);
+  static const int k_meqn[] = {0, 1, 3, 4, 3, 4, 5, 3, 1, 5, 3, 4, 3, 3, 3, 1, 1, 1},
+                   k_mwaves[] = {0, 1, 2, 4, 3, 2, 3, 2, 1, 5, 2, 2, 2, 2, 3, 1, 1, 1},
+                   k_ndim[] = {0, 2, 2, 2, 2, 3, 3, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 3};
+  if (rp_id < 1 || rp_id > 17) return fail(nullptr, 5, "claw_create: unknown rp_id %d", rp_id);
   if (k_meqn[rp_id] != meqn || k_mwaves[rp_id] != mwaves || k_ndim[rp_id] != ndim)
     return fail(nullptr, 6, "claw_create: rp_id %d expects ndim=%d meqn=%d mwaves=%d (got %d, %d, %d)", rp_id,
                 k_ndim[rp_id], k_meqn[rp_id], k_mwaves[rp_id], ndim, meqn, mwaves);

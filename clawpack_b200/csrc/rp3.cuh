@@ -345,5 +345,35 @@ struct RpBurgers3D {
   }
 };
 
+// ------------------------------------------------------------------------------------
+// vc_advection_3D -- riemann/src/rpn3_vc_advection.f90:52-57, rpt3_vc_advection.f90:60-72, rptt3_vc_advection.f90:62-84
+// aux = edge velocities (u, v, w at the lower x-, y-, z-face of the cell).  In every rpt3 / rptt3 variant the
+// down-going part uses the velocity of the cell "at" and the up-going part that of the cell "above" in the split
+// direction -- exactly the (auxz, auxp) pair sweep3.cuh hands over.
+// ------------------------------------------------------------------------------------
+struct RpVcAdvection3D {
+  static constexpr int MEQN = 1, MWAVES = 1, MAUX = 3, NCTX = 0;
+  template <int IXYZ, int ICOOR> struct TV {
+    static constexpr int N = MEQN;
+    __host__ __device__ static constexpr int comp(int k) { return k; }
+  };
+  template <int IXYZ>
+  __device__ __forceinline__ static void normal(const RpParams&, const double* ql, const double* qr,
+                                                const double*, const double* auxr, double (*wave)[MEQN], double* s,
+                                                double* amdq, double* apdq, double*) {
+    wave[0][0] = qr[0] - ql[0];
+    s[0] = auxr[IXYZ];                                       // auxl(ixyz, i)
+    amdq[0] = fmin2(auxr[IXYZ], 0.0) * wave[0][0];
+    apdq[0] = fmax2(auxr[IXYZ], 0.0) * wave[0][0];
+  }
+  template <int IXYZ, int ICOOR, bool TT = false>
+  __device__ __forceinline__ static void transverse(const RpParams&, const double*, const double*, const double* auxz,
+                                                    const double* auxp, const double* asdq, double* bm, double* bp) {
+    constexpr int IUVW = (IXYZ + ICOOR - 1) % 3;
+    bm[0] = fmin2(auxz[IUVW], 0.0) * asdq[0];
+    bp[0] = fmax2(auxp[IUVW], 0.0) * asdq[0];
+  }
+};
+
 }  // namespace CLAW_NS
 }  // namespace clawcuda

@@ -82,6 +82,7 @@ cudaError_t launch_sweep3(int rp_id, int dir, Sweep3Params& P, int num_sms, cuda
       return launch_dir<RpVcAcoustics3D, 8, 1>(dir, P, num_sms, st, info);
     case 6: return launch_dir<RpEuler3D, 8, 1>(dir, P, num_sms, st, info);
     case 15: return launch_dir<RpBurgers3D, 8, 1>(dir, P, num_sms, st, info);
+    case 17: return launch_dir<RpVcAdvection3D, 8, 1>(dir, P, num_sms, st, info);
   }
   return cudaErrorInvalidValue;
 }

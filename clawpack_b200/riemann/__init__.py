@@ -22,7 +22,8 @@ _SOLVERS = {
     'shallow_bathymetry_fwave_2D': (14, ('grav', 'dry_tolerance', 'sea_level'), 2),   # rpn2_shallow_bathymetry_fwave.f90
     'psystem_2D': (10, (), 2),                                # rpn2_psystem.f90 (f-wave; coefficients + strain in aux)
     'burgers_2D': (16, (), 2),                                # rpn2_burgers.f90, rpt2_burgers.f90
-    'burgers_3D': (15, ('coeff',), 3),                        # rpn3_burgers.f90:45: common /cparam/ coeff(3)
+    'burgers_3D': (15, ('coeff',), 3),
+    'vc_advection_3D': (17, (), 3),                           # rpn3_vc_advection.f90 (edge velocities in aux)                        # rpn3_burgers.f90:45: common /cparam/ coeff(3)
     # 1-D (claw_step1_host): riemann/src/rp1_*.f90
     'advection_1D': (21, ('u',), 1),
     'acoustics_1D': (22, ('rho', 'bulk', 'cc', 'zz'), 1),

@@ -8,7 +8,7 @@ num_eqn = {
     'shallow_roe_with_efix_2D': 3, 'shallow_hlle_2D': 3, 'shallow_sphere_2D': 4, 'vc_advection_2D': 1,
     'vc_acoustics_2D': 3, 'vc_elasticity_2D': 5, 'vc_acoustics_3D': 4, 'euler_3D': 5,
     'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2,
-    'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1,
+    'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'vc_advection_3D': 1,
 }
 
 num_waves = {
@@ -17,7 +17,7 @@ num_waves = {
     'shallow_roe_with_efix_2D': 3, 'shallow_hlle_2D': 2, 'shallow_sphere_2D': 3, 'vc_advection_2D': 1,
     'vc_acoustics_2D': 2, 'vc_elasticity_2D': 4, 'vc_acoustics_3D': 2, 'euler_3D': 3,
     'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2,
-    'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1,
+    'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'vc_advection_3D': 1,
 }
 
 fwave = {name: False for name in num_eqn}

@@ -515,6 +515,25 @@ def burgers_2d(mx=60, my=50, dimensional_split=False, transverse_waves=2, tfinal
                  num_output_times=num_output_times)
 
 
+def advection_3d_variable(mx=20, my=16, mz=18, dimensional_split=False, transverse_waves=22, tfinal=0.3,
+                          num_output_times=2):
+    """Colour-equation advection in a divergence-free 3-D velocity field given by edge velocities (riemann
+    vc_advection_3D; the reference ships the solver but no example): u = sin(2 pi y) + 0.3 at x-faces,
+    v = cos(2 pi z) - 0.2 at y-faces, w = sin(2 pi x) at z-faces (each independent of its own direction); periodic."""
+    lower, upper, n = (0., 0., 0.), (1., 1., 1.), (mx, my, mz)
+    X, Y, Z = _grid(lower, upper, n)
+    aux = np.empty((3, mx, my, mz), order='F')
+    aux[0] = np.sin(2 * np.pi * Y) + 0.3
+    aux[1] = np.cos(2 * np.pi * Z) - 0.2
+    aux[2] = np.sin(2 * np.pi * X)
+    q = np.empty((1, mx, my, mz), order='F')
+    q[0] = np.exp(-40 * ((X - 0.5) ** 2 + (Y - 0.4) ** 2 + (Z - 0.6) ** 2)) + 0.1 * (X > 0.7)
+    return _base('vc_advection_3D', lower, upper, n, q, aux=aux, limiters=VANLEER,
+                 dimensional_split=bool(dimensional_split), transverse_waves=transverse_waves, cfl_max=1.0,
+                 cfl_desired=0.8, dt_initial=0.01, bc_lower=[PERIODIC] * 3, bc_upper=[PERIODIC] * 3,
+                 aux_bc_lower=[PERIODIC] * 3, aux_bc_upper=[PERIODIC] * 3, tfinal=tfinal, num_output_times=num_output_times)
+
+
 def burgers_3d(mx=24, my=20, mz=18, coeff=(1.0, 0.7, -0.5), dimensional_split=False, transverse_waves=22, tfinal=0.2,
                num_output_times=2):
     """3-D Burgers equation (riemann burgers_3D; the reference ships the solver but no example): smooth data with both

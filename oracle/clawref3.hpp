@@ -14,7 +14,7 @@
 
 namespace clawref {
 
-enum RpId3 { RP_EULER_3D = 6, RP_BURGERS_3D = 15 };
+enum RpId3 { RP_EULER_3D = 6, RP_BURGERS_3D = 15, RP_VC_ADVECTION_3D = 17 };
 
 // gadd(m, side 1:2, slice -1:1, i)    (flux3.f90:121-122)
 template <class R> struct V4 {
@@ -403,11 +403,63 @@ void rptt3_burgers(int ixyz, int icoor, int, int, int, int, int, int, int mbc, i
   }
 }
 
+// =====================================================================
+// vc_advection_3D -- riemann/src/rpn3_vc_advection.f90:52-57, rpt3_vc_advection.f90:60-72, rptt3_vc_advection.f90:62-84
+// colour equation q_t + u q_x + v q_y + w q_z = 0 with edge velocities aux(1:3) = (u at the x-lower face, v at the
+// y-lower face, w at the z-lower face of each cell).  Parity unpinned: no reference example or test runs it.
+// =====================================================================
+template <class R>
+void rpn3_vc_advection(int ixyz, int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R> auxl, V2<R>,
+                       V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    wave(1, 1, i) = ql(1, i) - qr(1, i - 1);
+    s(1, i) = auxl(ixyz, i);
+    amdq(1, i) = r_min(auxl(ixyz, i), R(0.0)) * wave(1, 1, i);
+    apdq(1, i) = r_max(auxl(ixyz, i), R(0.0)) * wave(1, 1, i);
+  }
+}
+template <class R>
+void rpt3_vc_advection(int ixyz, int icoor, int imp, int, int, int, int, int mbc, int mx, V2<R>, V2<R>,
+                       A3<R>, A3<R> aux2, A3<R> aux3, V2<R> asdq, V2<R> bmasdq, V2<R> bpasdq, const double*) {
+  int iuvw = ixyz + icoor - 1;
+  if (iuvw > 3) iuvw -= 3;
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    const int i1 = i - 2 + imp;
+    if (icoor == 2) {
+      bmasdq(1, i) = r_min(aux2(iuvw, i1, 2), R(0.0)) * asdq(1, i);
+      bpasdq(1, i) = r_max(aux3(iuvw, i1, 2), R(0.0)) * asdq(1, i);
+    } else {
+      bmasdq(1, i) = r_min(aux2(iuvw, i1, 2), R(0.0)) * asdq(1, i);
+      bpasdq(1, i) = r_max(aux2(iuvw, i1, 3), R(0.0)) * asdq(1, i);
+    }
+  }
+}
+template <class R>
+void rptt3_vc_advection(int ixyz, int icoor, int imp, int impt, int, int, int, int, int mbc, int mx, V2<R>, V2<R>,
+                        A3<R> aux1, A3<R> aux2, A3<R> aux3, V2<R> bsasdq, V2<R> cmbsasdq, V2<R> cpbsasdq,
+                        const double*) {
+  int iuvw = ixyz + icoor - 1;
+  if (iuvw > 3) iuvw -= 3;
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    const int i1 = i - 2 + imp;
+    if (icoor == 2) {
+      const int pl = (impt == 1) ? 1 : 3;
+      cmbsasdq(1, i) = r_min(aux2(iuvw, i1, pl), R(0.0)) * bsasdq(1, i);
+      cpbsasdq(1, i) = r_max(aux3(iuvw, i1, pl), R(0.0)) * bsasdq(1, i);
+    } else {
+      A3<R> a = (impt == 1) ? aux1 : aux3;
+      cmbsasdq(1, i) = r_min(a(iuvw, i1, 2), R(0.0)) * bsasdq(1, i);
+      cpbsasdq(1, i) = r_max(a(iuvw, i1, 3), R(0.0)) * bsasdq(1, i);
+    }
+  }
+}
+
 template <class R> inline bool select_rp3(int rp_id, Rpn3<R>& rpn, Rpt3<R>& rpt, Rptt3<R>& rptt) {
   switch (rp_id) {
     case RP_VC_ACOUSTICS_3D: rpn = rpn3_vc_acoustics<R>; rpt = rpt3_vc_acoustics<R>; rptt = rptt3_vc_acoustics<R>; return true;
     case RP_EULER_3D: rpn = rpn3_euler<R>; rpt = rpt3_euler<R>; rptt = rptt3_euler<R>; return true;
     case RP_BURGERS_3D: rpn = rpn3_burgers<R>; rpt = rpt3_burgers<R>; rptt = rptt3_burgers<R>; return true;
+    case RP_VC_ADVECTION_3D: rpn = rpn3_vc_advection<R>; rpt = rpt3_vc_advection<R>; rptt = rptt3_vc_advection<R>; return true;
   }
   return false;
 }

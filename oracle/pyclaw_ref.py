@@ -35,6 +35,7 @@ RP_IDS = {
     'shallow_bathymetry_fwave_2D': 14,
     'burgers_3D': 15,
     'burgers_2D': 16,
+    'vc_advection_3D': 17,
     'advection_1D': 21,
     'acoustics_1D': 22,
     'burgers_1D': 23,
@@ -59,6 +60,7 @@ CPARAM_NAMES = {
     'acoustics_mapped_2D': (),        # rpn2_acoustics_mapped.f90: everything lives in aux
     'shallow_bathymetry_fwave_2D': ('grav', 'dry_tolerance', 'sea_level'),   # rpn2_shallow_bathymetry_fwave.f90:44-45
     'burgers_2D': (),
+    'vc_advection_3D': (),
     'burgers_3D': ('coeff',),         # rpn3_burgers.f90:45: common /cparam/ coeff(3)
     'advection_1D': ('u',),           # rp1_advection.f90
     'acoustics_1D': ('rho', 'bulk', 'cc', 'zz'),   # rp1_acoustics.f90
@@ -69,11 +71,11 @@ CPARAM_NAMES = {
 NUM_EQN = {'advection_2D': 1, 'acoustics_2D': 3, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
            'vc_acoustics_3D': 4, 'euler_3D': 5, 'vc_acoustics_2D': 3, 'vc_advection_2D': 1, 'euler_5wave_2D': 5,
            'psystem_2D': 3, 'euler_hlle_2D': 4, 'shallow_hlle_2D': 3,
-           'acoustics_mapped_2D': 3, 'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'burgers_2D': 1, 'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2}
+           'acoustics_mapped_2D': 3, 'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'burgers_2D': 1, 'vc_advection_3D': 1, 'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2}
 NUM_WAVES = {'advection_2D': 1, 'acoustics_2D': 2, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
              'vc_acoustics_3D': 2, 'euler_3D': 3, 'vc_acoustics_2D': 2, 'vc_advection_2D': 1, 'euler_5wave_2D': 5,
              'psystem_2D': 2, 'euler_hlle_2D': 2, 'shallow_hlle_2D': 2,
-             'acoustics_mapped_2D': 2, 'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'burgers_2D': 1, 'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2}
+             'acoustics_mapped_2D': 2, 'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'burgers_2D': 1, 'vc_advection_3D': 1, 'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2}
 
 BC_CUSTOM, BC_EXTRAP, BC_PERIODIC, BC_WALL = 0, 1, 2, 3
 

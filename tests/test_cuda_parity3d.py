@@ -61,6 +61,11 @@ CASES3 = {
     'burgers3_unsplit_11': lambda: S.burgers_3d(mx=30, my=9, mz=11, transverse_waves=11),
     'burgers3_unsplit_21_minmod': lambda: dict(S.burgers_3d(mx=13, my=17, mz=10, transverse_waves=21), limiters=S.MINMOD),
     'burgers3_split': lambda: S.burgers_3d(mx=16, my=12, mz=20, dimensional_split=True),
+    # vc_advection_3D: edge velocities in aux, every transverse mode (parity unpinned by the reference)
+    'vcadv3_unsplit_22': lambda: S.advection_3d_variable(),
+    'vcadv3_unsplit_21': lambda: S.advection_3d_variable(mx=13, my=30, mz=9, transverse_waves=21),
+    'vcadv3_unsplit_11_superbee': lambda: dict(S.advection_3d_variable(mx=11, my=10, mz=31, transverse_waves=11), limiters=S.SUPERBEE),
+    'vcadv3_split': lambda: S.advection_3d_variable(mx=16, my=12, mz=14, dimensional_split=True),
     'ac_tiny': lambda: _ac(mx=3, my=2, mz=4),
     'ac_tile_edges': lambda: _ac(mx=57, my=7, mz=13),          # 28-lane strips, 6-row tiles: ragged edges
     'ac_tile_edges2': lambda: _ac(mx=31, my=13, mz=6),
