@@ -52,6 +52,8 @@ def _declare(L):
         'claw_halo_elems': (i, [H, ctypes.POINTER(sz)]),
         'claw_halo_pack': (i, [H, i, vp]),
         'claw_halo_unpack': (i, [H, i, vp]),
+        'claw_halo_pack_next': (i, [H, i, vp]),
+        'claw_halo_unpack_next': (i, [H, i, vp]),
         'claw_halo_elems_aux': (i, [H, ctypes.POINTER(sz)]),
         'claw_halo_pack_aux': (i, [H, i, vp]),
         'claw_halo_unpack_aux': (i, [H, i, vp]),

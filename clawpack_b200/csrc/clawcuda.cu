@@ -833,6 +833,16 @@ int claw_halo_unpack(claw_solver* h, int side, const double* d_buf) {
   if (check_handle(h)) return 1;
   return halo_move(h, h->q[h->cur], h->meqn, side, const_cast<double*>(d_buf), false);
 }
+// the same on the buffer the last claw_step_launch WROTE (the state that becomes current on claw_accept): lets the
+// host queue the next step's exchange right behind the sweep, before it has read the CFL number back
+int claw_halo_pack_next(claw_solver* h, int side, double* d_buf) {
+  if (check_handle(h)) return 1;
+  return halo_move(h, h->q[h->cur ^ 1], h->meqn, side, d_buf, true);
+}
+int claw_halo_unpack_next(claw_solver* h, int side, const double* d_buf) {
+  if (check_handle(h)) return 1;
+  return halo_move(h, h->q[h->cur ^ 1], h->meqn, side, const_cast<double*>(d_buf), false);
+}
 int claw_halo_elems_aux(const claw_solver* h, size_t* elems) {
   if (check_handle(h)) return 1;
   *elems = halo_elems_of(h, h->maux);

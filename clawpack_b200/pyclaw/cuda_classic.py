@@ -84,6 +84,7 @@ class DeviceStepper(object):
         self.host_dirty = True      # state._q may have been changed on the host since the last upload
         self.pre_step_hook = None   # e.g. the multi-GPU ghost exchange (petclaw)
         self.post_step_hook = None  # e.g. the CFL all-reduce
+        self.ghosts_current = False # multi-GPU: the slab-face ghost rows of the CURRENT buffer hold the neighbours' data
         if state.num_aux > 0:
             if any(b == 0 for b in list(solver.aux_bc_lower) + list(solver.aux_bc_upper)):
                 # BC.custom aux faces (e.g. edge velocities on the extended grid, examples/advection_2d_annulus):
@@ -117,6 +118,7 @@ class DeviceStepper(object):
             q = np.asfortranarray(state._q, dtype=np.float64)
             _lib.check(self.L.claw_put_q(self.handle, q.ctypes.data_as(ctypes.c_void_p)), self.handle)
             self.host_dirty = False
+            self.ghosts_current = False
 
     # ---- stepping ------------------------------------------------------------------------------
     def step(self, state, dt):

@@ -144,6 +144,10 @@ int claw_sync(claw_solver* h);
 int claw_halo_elems(const claw_solver* h, size_t* elems);
 int claw_halo_pack(claw_solver* h, int side, double* d_buf);
 int claw_halo_unpack(claw_solver* h, int side, const double* d_buf);
+/* the same on the buffer the last claw_step_launch wrote (current after claw_accept): the next step's exchange can be
+   queued right behind the sweep, before the host has read the CFL number; a rejected step simply discards it */
+int claw_halo_pack_next(claw_solver* h, int side, double* d_buf);
+int claw_halo_unpack_next(claw_solver* h, int side, const double* d_buf);
 /* the same for the (static) aux array: exchanged once at setup (petclaw/state.py:233-241) */
 int claw_halo_elems_aux(const claw_solver* h, size_t* elems);
 int claw_halo_pack_aux(claw_solver* h, int side, double* d_buf);
