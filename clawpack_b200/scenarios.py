@@ -624,6 +624,129 @@ def dam_break_1d(mx=500, riemann_solver='roe', tfinal=2.0):
                  bc_lower=[EXTRAP], bc_upper=[EXTRAP], tfinal=tfinal)
 
 
+def traffic_1d(mx=500, tfinal=2.0):
+    """pyclaw/examples/traffic/traffic.py:14-50 (classic): LWR traffic flow, minmod (default), extrapolation."""
+    xc = centers(-1.0, 1.0, mx)
+    q = np.empty((1, mx), order='F')
+    q[0] = 0.75 * (xc < 0) + 0.1 * (xc > 0.)
+    return _base('traffic_1D', (-1.0,), (1.0,), (mx,), q, problem_data={'efix': True, 'umax': 1.}, limiters=MINMOD,
+                 bc_lower=[EXTRAP], bc_upper=[EXTRAP], tfinal=tfinal)
+
+
+def advection_1d_variable(mx=100, tfinal=1.0):
+    """pyclaw/examples/advection_1d_variable/variable_coefficient_advection.py:22-107 (Fortran classic): colour
+    equation q_t + u(x) q_x = 0 with u = 2 + sin(2 pi x) in aux, MC limiter, periodic."""
+    x = centers(0.0, 1.0, mx)
+    beta, gamma, x0, x1, x2 = 100., 0., 0.3, 0.7, 0.9
+    qg = np.exp(-beta * (x - x0) ** 2) * np.cos(gamma * (x - x0))
+    qs = (x > x1) * 1.0 - (x > x2) * 1.0
+    q = np.empty((1, mx), order='F')
+    q[0] = qg + qs
+    aux = np.empty((1, mx), order='F')
+    aux[0] = np.sin(2. * np.pi * x) + 2
+    return _base('advection_color_1D', (0.0,), (1.0,), (mx,), q, aux=aux, limiters=MC, bc_lower=[PERIODIC],
+                 bc_upper=[PERIODIC], aux_bc_lower=[PERIODIC], aux_bc_upper=[PERIODIC], tfinal=tfinal)
+
+
+def sill_1d(mx=500, tfinal=1.0):
+    """pyclaw/examples/shallow_1d/sill.py:22-70 (Fortran): flow over a sill, f-wave solver with bathymetry in aux,
+    van Leer, extrapolation."""
+    xc = centers(-1.0, 1.0, mx)
+    aux = np.empty((1, mx), order='F')
+    aux[0] = 0.8 * np.exp(-xc ** 2 / 0.2 ** 2) - 1.0
+    q = np.zeros((2, mx), order='F')
+    q[0] = 0.1 * np.exp(-(xc + 0.4) ** 2 / 0.2 ** 2) - aux[0]
+    return _base('shallow_bathymetry_fwave_1D', (-1.0,), (1.0,), (mx,), q, aux=aux,
+                 problem_data={'grav': 9.8, 'dry_tolerance': 1e-3, 'sea_level': 0.0}, limiters=VANLEER, fwave=True,
+                 bc_lower=[EXTRAP], bc_upper=[EXTRAP], aux_bc_lower=[EXTRAP], aux_bc_upper=[EXTRAP], tfinal=tfinal)
+
+
+def stegoton_1d(xupper=300.0, cells_per_layer=12, tfinal=50.0, num_output_times=20, exponential=True):
+    """pyclaw/examples/stegoton_1d/stegoton.py:33-170 (Fortran classic): nonlinear elasticity in a layered medium,
+    f-waves, minmod (default); the pulse enters through a moving-wall ``BC.custom`` on the left (:62-76) that reads
+    the time and the interior aux and leaves the outermost momentum ghost cell untouched; extrapolation on the
+    right.  ``exponential=False`` switches to the linear stress relation (coefA = 0, coefB = K), which involves no
+    ``exp`` and is therefore bit-reproducible across math libraries."""
+    mx = int(round(xupper - 0.0)) * cells_per_layer
+    x = centers(0.0, xupper, mx)
+    alpha, KA, KB, rhoA, rhoB = 0.5, 1.0, 4.0, 1.0, 4.0
+    xfrac = x - np.floor(x)
+    aux = np.empty((3, mx), order='F')
+    aux[0] = rhoA * (xfrac < alpha) + rhoB * (xfrac >= alpha)
+    aux[1] = KA * (xfrac < alpha) + KB * (xfrac >= alpha)
+    aux[2] = 0.
+    if not exponential:
+        aux[2] = aux[1]
+        aux[1] = 0.
+    q = np.zeros((2, mx), order='F')
+    t1, tw1, a1 = 10.0, 10.0, 0.1
+    kwall = 1 if exponential else 2
+
+    def moving_wall(qbc, auxbc, t, g):
+        qbc[0, :g] = qbc[0, g]
+        t0 = (t - t1) / tw1
+        vwall = -a1 * (1. + np.cos(t0 * np.pi)) if abs(t0) <= 1. else 0.
+        for ibc in range(g - 1):
+            qbc[1, g - ibc - 1] = 2 * vwall * auxbc[kwall, g + ibc] - qbc[1, g + ibc]
+
+    return _base('nonlinear_elasticity_fwave_1D', (0.0,), (xupper,), (mx,), q, aux=aux, limiters=MINMOD, fwave=True,
+                 bc_lower=[0], bc_upper=[EXTRAP], aux_bc_lower=[EXTRAP], aux_bc_upper=[EXTRAP],
+                 custom_bc_lower_full=moving_wall, tfinal=tfinal, num_output_times=num_output_times)
+
+
+def shocktube_1d(mx=800, tfinal=0.4, riemann_solver='hlle'):
+    """pyclaw/examples/euler_1d/shocktube.py:24-68 (classic, Fortran branch = euler_hlle_1D): Sod shock tube,
+    minmod (default), extrapolation.  ``riemann_solver='roe'`` runs the same data through euler_with_efix_1D."""
+    gamma = 1.4
+    x = centers(-1.0, 1.0, mx)
+    q = np.zeros((3, mx), order='F')
+    q[0] = (x < 0.) * 1. + (x >= 0.) * (1. / 8)
+    velocity = q[1] / q[0]
+    pressure = (x < 0.) * 1. + (x >= 0.) * 0.1
+    q[2] = pressure / (gamma - 1.) + 0.5 * q[0] * velocity ** 2
+    rp = 'euler_hlle_1D' if riemann_solver == 'hlle' else 'euler_with_efix_1D'
+    return _base(rp, (-1.0,), (1.0,), (mx,), q, problem_data={'gamma': gamma, 'gamma1': gamma - 1.},
+                 limiters=MINMOD, bc_lower=[EXTRAP], bc_upper=[EXTRAP], tfinal=tfinal)
+
+
+def blast_1d(mx=800, tfinal=0.038):
+    """pyclaw/examples/euler_1d/woodward_colella_blast.py:27-82 with solver_type='classic': euler_with_efix_1D, MC
+    limiter, solid walls."""
+    gamma = 1.4
+    x = centers(0.0, 1.0, mx)
+    q = np.zeros((3, mx), order='F')
+    q[0] = 1.
+    q[2] = ((x < 0.1) * 1.e3 + (0.1 <= x) * (x < 0.9) * 1.e-2 + (0.9 <= x) * 1.e2) / (gamma - 1.)
+    return _base('euler_with_efix_1D', (0.0,), (1.0,), (mx,), q, problem_data={'gamma': gamma}, limiters=MC,
+                 bc_lower=[WALL], bc_upper=[WALL], tfinal=tfinal)
+
+
+def cubic_1d(mx=1000, tfinal=0.2, qL=4.0, qR=-2.0):
+    """pyclaw/examples/cubic_1d/cubic.py:14-54 (classic): q_t + (q^3)_x = 0, Riemann data qL | qR at x = -0.5,
+    van Leer, cfl_desired 0.5, extrapolation.  test_cubic.py:3-21 checks the shock position x0 = -0.5 + 12 t."""
+    x = centers(-1.0, 3.0, mx)
+    q = np.empty((1, mx), order='F')
+    q[0] = (x < -0.5) * qL + (x >= -0.5) * qR
+    return _base('cubic_1D', (-1.0,), (3.0,), (mx,), q, limiters=VANLEER, cfl_max=1.0, cfl_desired=0.5,
+                 bc_lower=[EXTRAP], bc_upper=[EXTRAP], tfinal=tfinal)
+
+
+def acoustics_1d_variable(mx=400, tfinal=0.6):
+    """acoustics_variable_1D (riemann/src/rp1_acoustics_variable.f90; the reference ships no PyClaw example for the
+    classic solver): a pulse crossing an impedance jump at x = 0.5, aux = (Z, c), MC, extrapolation."""
+    x = centers(0.0, 1.0, mx)
+    rho = 1.0 + 3.0 * (x > 0.5)
+    bulk = 1.0 + 0.0 * x
+    aux = np.empty((2, mx), order='F')
+    aux[1] = np.sqrt(bulk / rho)
+    aux[0] = rho * aux[1]
+    q = np.zeros((2, mx), order='F')
+    q[0] = np.exp(-400 * (x - 0.3) ** 2)
+    q[1] = q[0] / aux[0]
+    return _base('acoustics_variable_1D', (0.0,), (1.0,), (mx,), q, aux=aux, limiters=MC, bc_lower=[EXTRAP],
+                 bc_upper=[EXTRAP], aux_bc_lower=[EXTRAP], aux_bc_upper=[EXTRAP], tfinal=tfinal)
+
+
 def make_claw(sc, kernel_language='CUDA', pyclaw=None, **solver_kw):
     """Build a PyClaw-API Controller (solver + solution) from a scenario dict."""
     if pyclaw is None:

@@ -17,6 +17,14 @@ enum RpId1 {
   RP_BURGERS_1D = 23,
   RP_SHALLOW_ROE_EFIX_1D = 24,
   RP_SHALLOW_HLLE_1D = 25,
+  RP_TRAFFIC_1D = 26,
+  RP_ADVECTION_COLOR_1D = 27,
+  RP_ACOUSTICS_VARIABLE_1D = 28,
+  RP_SHALLOW_BATHYMETRY_FWAVE_1D = 29,
+  RP_EULER_EFIX_1D = 30,
+  RP_EULER_HLLE_1D = 31,
+  RP_NONLINEAR_ELASTICITY_FWAVE_1D = 32,
+  RP_CUBIC_1D = 33,
 };
 
 template <class R>
@@ -154,6 +162,272 @@ void rp1_shallow_hlle(int, int meqn, int mwaves, int, int mbc, int mx, V2<R> ql,
     }
 }
 
+// traffic_1D -- riemann/src/rp1_traffic.f90:40-64     cparam = (umax); entropy fix for transonic rarefactions
+template <class R>
+void rp1_traffic(int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>, V3<R> wave, V2<R> s,
+                 V2<R> amdq, V2<R> apdq, const double* cparam) {
+  const R umax = R(cparam[0]);
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    wave(1, 1, i) = ql(1, i) - qr(1, i - 1);
+    s(1, i) = umax * (R(1.0) - (qr(1, i - 1) + ql(1, i)));
+    amdq(1, i) = r_min(s(1, i), R(0.0)) * wave(1, 1, i);
+    apdq(1, i) = r_max(s(1, i), R(0.0)) * wave(1, 1, i);
+    R sim1 = umax * (R(1.0) - R(2.0) * qr(1, i - 1));
+    R si = umax * (R(1.0) - R(2.0) * ql(1, i));
+    if (sim1 < R(0.0) && si > R(0.0)) {
+      R flux0 = R(0.25) * umax;
+      R fluxim1 = qr(1, i - 1) * umax * (R(1.0) - qr(1, i - 1));
+      R fluxi = ql(1, i) * umax * (R(1.0) - ql(1, i));
+      amdq(1, i) = flux0 - fluxim1;
+      apdq(1, i) = fluxi - flux0;
+    }
+  }
+}
+
+// advection_color_1D -- riemann/src/rp1_advection_color.f90:44-56     aux(1) = cell-centred velocity
+template <class R>
+void rp1_advection_color(int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R> auxl, V2<R> auxr,
+                         V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R u = r_min(auxr(1, i - 1), R(0.0)) + r_max(auxl(1, i), R(0.0));
+    wave(1, 1, i) = ql(1, i) - qr(1, i - 1);
+    s(1, i) = u;
+    amdq(1, i) = r_min(auxr(1, i - 1), R(0.0)) * wave(1, 1, i);
+    apdq(1, i) = r_max(auxl(1, i), R(0.0)) * wave(1, 1, i);
+  }
+}
+
+// acoustics_variable_1D -- riemann/src/rp1_acoustics_variable.f90:49-82     aux = (impedance Z, sound speed c)
+template <class R>
+void rp1_acoustics_variable(int, int meqn, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R> auxl, V2<R> auxr,
+                            V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R d1 = ql(1, i) - qr(1, i - 1);
+    R d2 = ql(2, i) - qr(2, i - 1);
+    R zi = auxl(1, i), zim = auxr(1, i - 1);
+    R a1 = (-d1 + zi * d2) / (zim + zi);
+    R a2 = (d1 + zim * d2) / (zim + zi);
+    wave(1, 1, i) = -a1 * zim; wave(2, 1, i) = a1; s(1, i) = -auxr(2, i - 1);
+    wave(1, 2, i) = a2 * zi;   wave(2, 2, i) = a2; s(2, i) = auxl(2, i);
+  }
+  for (int m = 1; m <= meqn; ++m)
+    for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+      amdq(m, i) = s(1, i) * wave(m, 1, i);
+      apdq(m, i) = s(2, i) * wave(m, 2, i);
+    }
+}
+
+// shallow_bathymetry_fwave_1D -- riemann/src/rp1_shallow_bathymetry_fwave.f90:35-118
+// cparam = (grav, dry_tolerance, sea_level); aux(1) = bathymetry; f-waves
+template <class R>
+void rp1_shallow_bathymetry_fwave(int, int, int num_waves, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R> auxl,
+                                  V2<R> auxr, V3<R> fwave, V2<R> s, V2<R> amdq, V2<R> apdq, const double* cparam) {
+  const R grav = R(cparam[0]), dry_tolerance = R(cparam[1]);
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    for (int m = 1; m <= 2; ++m) { amdq(m, i) = R(0.0); apdq(m, i) = R(0.0); }    // amdq = 0.d0; apdq = 0.d0 (:52-53)
+    R hl = qr(1, i - 1), ul, phil;
+    if (hl > dry_tolerance) {
+      ul = qr(2, i - 1) / hl;
+      phil = qr(1, i - 1) * (ul * ul) + R(0.5) * grav * (qr(1, i - 1) * qr(1, i - 1));
+    } else { ul = R(0.0); phil = R(0.0); }
+    R bl = auxr(1, i - 1);
+    R hr = ql(1, i), ur, phir;
+    if (hr > dry_tolerance) {
+      ur = ql(2, i) / hr;
+      phir = ql(1, i) * (ur * ur) + R(0.5) * grav * (ql(1, i) * ql(1, i));
+    } else { ur = R(0.0); phir = R(0.0); }
+    R br = auxl(1, i);
+    R hbar = R(0.5) * (hr + hl);
+    R uhat = (r_sqrt(hl) * ul + r_sqrt(hr) * ur) / (r_sqrt(hl) + r_sqrt(hr));
+    R chat = r_sqrt(grav * hbar);
+    R fd1 = (hr * ur) - (hl * ul);
+    R fd2 = phir - phil + grav * hbar * (br - bl);
+    s(1, i) = r_min(ul - r_sqrt(grav * hl), uhat - chat);
+    s(2, i) = r_max(ur + r_sqrt(grav * hr), uhat + chat);
+    R beta1 = (s(2, i) * fd1 - fd2) / (s(2, i) - s(1, i));
+    R beta2 = (fd2 - s(1, i) * fd1) / (s(2, i) - s(1, i));
+    fwave(1, 1, i) = beta1 * R(1.0); fwave(2, 1, i) = beta1 * s(1, i);
+    fwave(1, 2, i) = beta2 * R(1.0); fwave(2, 2, i) = beta2 * s(2, i);
+    for (int k = 1; k <= num_waves; ++k) {
+      if (s(k, i) < R(0.0)) {
+        for (int m = 1; m <= 2; ++m) amdq(m, i) = amdq(m, i) + fwave(m, k, i);
+      } else if (s(k, i) > R(0.0)) {
+        for (int m = 1; m <= 2; ++m) apdq(m, i) = apdq(m, i) + fwave(m, k, i);
+      } else {
+        for (int m = 1; m <= 2; ++m) {
+          amdq(m, i) = amdq(m, i) + R(0.5) * fwave(m, k, i);
+          apdq(m, i) = apdq(m, i) + R(0.5) * fwave(m, k, i);
+        }
+      }
+    }
+  }
+}
+
+// euler_with_efix_1D -- riemann/src/rp1_euler_with_efix.f90:47-226     cparam = (gamma); Roe solver + entropy fix
+template <class R>
+void rp1_euler_efix(int, int, int mwaves, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>, V3<R> wave,
+                    V2<R> s, V2<R> amdq, V2<R> apdq, const double* cparam) {
+  const R gamma = R(cparam[0]);
+  const R gamma1 = gamma - R(1.0);
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    // loop 20: Roe averages
+    R rhsqrtl = r_sqrt(qr(1, i - 1));
+    R rhsqrtr = r_sqrt(ql(1, i));
+    R pl = gamma1 * (qr(3, i - 1) - R(0.5) * (qr(2, i - 1) * qr(2, i - 1)) / qr(1, i - 1));
+    R pr = gamma1 * (ql(3, i) - R(0.5) * (ql(2, i) * ql(2, i)) / ql(1, i));
+    R rhsq2 = rhsqrtl + rhsqrtr;
+    R u = (qr(2, i - 1) / rhsqrtl + ql(2, i) / rhsqrtr) / rhsq2;
+    R enth = ((qr(3, i - 1) + pl) / rhsqrtl + (ql(3, i) + pr) / rhsqrtr) / rhsq2;
+    R a2 = gamma1 * (enth - R(0.5) * (u * u));
+    R a = r_sqrt(a2);
+    // loop 30: wave strengths
+    R d1 = ql(1, i) - qr(1, i - 1);
+    R d2 = ql(2, i) - qr(2, i - 1);
+    R d3 = ql(3, i) - qr(3, i - 1);
+    a2 = gamma1 / (a * a) * ((enth - u * u) * d1 + u * d2 - d3);
+    R a3 = (d2 + (a - u) * d1 - a * a2) / (R(2.0) * a);
+    R a1 = d1 - a2 - a3;
+    wave(1, 1, i) = a1; wave(2, 1, i) = a1 * (u - a); wave(3, 1, i) = a1 * (enth - u * a); s(1, i) = u - a;
+    wave(1, 2, i) = a2; wave(2, 2, i) = a2 * u;       wave(3, 2, i) = a2 * R(0.5) * (u * u); s(2, i) = u;
+    wave(1, 3, i) = a3; wave(2, 3, i) = a3 * (u + a); wave(3, 3, i) = a3 * (enth + u * a); s(3, i) = u + a;
+  }
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {              // efix = .true.: loop 200 (:140-213)
+    R rhoim1 = qr(1, i - 1);
+    R pim1 = gamma1 * (qr(3, i - 1) - R(0.5) * (qr(2, i - 1) * qr(2, i - 1)) / rhoim1);
+    R cim1 = r_sqrt(gamma * pim1 / rhoim1);
+    R s0 = qr(2, i - 1) / rhoim1 - cim1;
+    if (s0 >= R(0.0) && s(1, i) > R(0.0)) {
+      for (int m = 1; m <= 3; ++m) amdq(m, i) = R(0.0);
+      continue;
+    }
+    R rho1 = qr(1, i - 1) + wave(1, 1, i);
+    R rhou1 = qr(2, i - 1) + wave(2, 1, i);
+    R en1 = qr(3, i - 1) + wave(3, 1, i);
+    R p1 = gamma1 * (en1 - R(0.5) * (rhou1 * rhou1) / rho1);
+    R c1 = r_sqrt(gamma * p1 / rho1);
+    R s1 = rhou1 / rho1 - c1;
+    R sfract;
+    if (s0 < R(0.0) && s1 > R(0.0)) sfract = s0 * (s1 - s(1, i)) / (s1 - s0);
+    else if (s(1, i) < R(0.0)) sfract = s(1, i);
+    else sfract = R(0.0);
+    for (int m = 1; m <= 3; ++m) amdq(m, i) = sfract * wave(m, 1, i);
+    if (s(2, i) >= R(0.0)) continue;                       // 2-wave is rightgoing
+    for (int m = 1; m <= 3; ++m) amdq(m, i) = amdq(m, i) + s(2, i) * wave(m, 2, i);
+    R rhoi = ql(1, i);
+    R pi = gamma1 * (ql(3, i) - R(0.5) * (ql(2, i) * ql(2, i)) / rhoi);
+    R ci = r_sqrt(gamma * pi / rhoi);
+    R s3 = ql(2, i) / rhoi + ci;
+    R rho2 = ql(1, i) - wave(1, 3, i);
+    R rhou2 = ql(2, i) - wave(2, 3, i);
+    R en2 = ql(3, i) - wave(3, 3, i);
+    R p2 = gamma1 * (en2 - R(0.5) * (rhou2 * rhou2) / rho2);
+    R c2 = r_sqrt(gamma * p2 / rho2);
+    R s2 = rhou2 / rho2 + c2;
+    if (s2 < R(0.0) && s3 > R(0.0)) sfract = s2 * (s3 - s(3, i)) / (s3 - s2);
+    else if (s(3, i) < R(0.0)) sfract = s(3, i);
+    else continue;
+    for (int m = 1; m <= 3; ++m) amdq(m, i) = amdq(m, i) + sfract * wave(m, 3, i);
+  }
+  for (int m = 1; m <= 3; ++m)
+    for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+      R df = R(0.0);
+      for (int mw = 1; mw <= mwaves; ++mw) df = df + s(mw, i) * wave(m, mw, i);
+      apdq(m, i) = df - amdq(m, i);
+    }
+}
+
+// euler_hlle_1D -- riemann/src/rp1_euler_hlle.f90:36-112     cparam = (gamma).  `H_r` is formed with p_l, as the
+// reference has it (:62).
+template <class R>
+void rp1_euler_hlle(int, int, int mwaves, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>, V3<R> wave,
+                    V2<R> s, V2<R> amdq, V2<R> apdq, const double* cparam) {
+  const R gamma = R(cparam[0]);
+  const R gamma1 = gamma - R(1.0);
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R u_l = qr(2, i - 1) / qr(1, i - 1);
+    R u_r = ql(2, i) / ql(1, i);
+    R p_l = gamma1 * (qr(3, i - 1) - qr(1, i - 1) * (u_l * u_l) / R(2.0));
+    R p_r = gamma1 * (ql(3, i) - ql(1, i) * (u_r * u_r) / R(2.0));
+    R H_l = (qr(3, i - 1) + p_l) / qr(1, i - 1);
+    R H_r = (ql(3, i) + p_l) / ql(1, i);
+    R c_l = r_sqrt(gamma1 * H_l - (u_l * u_l) / R(2.0));
+    R c_r = r_sqrt(gamma1 * H_r - (u_r * u_r) / R(2.0));
+    R E_l = qr(3, i - 1), E_r = ql(3, i);
+    R rhsqrt_l = r_sqrt(qr(1, i - 1));
+    R rhsqrt_r = r_sqrt(ql(1, i));
+    R rhsq2 = rhsqrt_l + rhsqrt_r;
+    R u_hat = (qr(2, i - 1) / rhsqrt_l + ql(2, i) / rhsqrt_r) / rhsq2;
+    R H_hat = ((qr(3, i - 1) + p_l) / rhsqrt_l + (ql(3, i) + p_r) / rhsqrt_r) / rhsq2;
+    R c_hat = r_sqrt(gamma1 * (H_hat - R(0.5) * (u_hat * u_hat)));
+    R s1 = r_min(u_l - c_l, u_hat - c_hat);
+    R s2 = r_max(u_r + c_r, u_hat + c_hat);
+    R rho_m = (ql(2, i) - qr(2, i - 1) - s2 * ql(1, i) + s1 * qr(1, i - 1)) / (s1 - s2);
+    R rhou_m = (ql(1, i) * (u_r * u_r) - qr(1, i - 1) * (u_l * u_l) + p_r - p_l - s2 * ql(2, i) + s1 * qr(2, i - 1)) /
+               (s1 - s2);
+    R E_m = (u_r * (E_r + p_r) - u_l * (E_l + p_l) - s2 * E_r + s1 * E_l) / (s1 - s2);
+    wave(1, 1, i) = rho_m - qr(1, i - 1); wave(2, 1, i) = rhou_m - qr(2, i - 1); wave(3, 1, i) = E_m - qr(3, i - 1);
+    s(1, i) = s1;
+    wave(1, 2, i) = ql(1, i) - rho_m; wave(2, 2, i) = ql(2, i) - rhou_m; wave(3, 2, i) = ql(3, i) - E_m;
+    s(2, i) = s2;
+  }
+  for (int m = 1; m <= 3; ++m)
+    for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+      amdq(m, i) = R(0.0); apdq(m, i) = R(0.0);
+      for (int mw = 1; mw <= mwaves; ++mw) {
+        if (s(mw, i) < R(0.0)) amdq(m, i) = amdq(m, i) + s(mw, i) * wave(m, mw, i);
+        else apdq(m, i) = apdq(m, i) + s(mw, i) * wave(m, mw, i);
+      }
+    }
+}
+
+// nonlinear_elasticity_fwave_1D -- riemann/src/rp1_nonlinear_elasticity_fwave.f90:47-128
+// aux = (density, coefA, coefB): sigma = exp(coefA*eps) - 1 if coefA > 0 else coefB*eps; f-waves
+template <class R> inline R ne_sigma(R eps, R coefA, R coefB) {
+  if (coefA > R(0.0)) return r_exp(coefA * eps) - R(1.0);
+  return coefB * eps;
+}
+template <class R> inline R ne_sigmap(R eps, R coefA, R coefB) {
+  if (coefA > R(0.0)) return coefA * r_exp(coefA * eps);
+  return coefB;
+}
+template <class R>
+void rp1_nonlinear_elasticity_fwave(int, int meqn, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R> auxl,
+                                    V2<R> auxr, V3<R> fwave, V2<R> s, V2<R> amdq, V2<R> apdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R rhoi = auxl(1, i), rhoim = auxr(1, i - 1);
+    R epsi = ql(1, i), epsim = qr(1, i - 1);
+    R urhoi = ql(2, i), urhoim = qr(2, i - 1);
+    R bulki = ne_sigmap(epsi, auxl(2, i), auxl(3, i));
+    R bulkim = ne_sigmap(epsim, auxr(2, i - 1), auxr(3, i - 1));
+    R ci = r_sqrt(bulki / rhoi);
+    R cim = r_sqrt(bulkim / rhoim);
+    R zi = ci * rhoi, zim = cim * rhoim;
+    R du = urhoi / rhoi - urhoim / rhoim;
+    R dsig = ne_sigma(epsi, auxl(2, i), auxl(3, i)) - ne_sigma(epsim, auxr(2, i - 1), auxr(3, i - 1));
+    R b1 = -(zi * du + dsig) / (zim + zi);
+    R b2 = -(zim * du - dsig) / (zim + zi);
+    fwave(1, 1, i) = b1; fwave(2, 1, i) = b1 * zim;   s(1, i) = -cim;
+    fwave(1, 2, i) = b2; fwave(2, 2, i) = b2 * (-zi); s(2, i) = ci;
+  }
+  for (int m = 1; m <= meqn; ++m)
+    for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+      amdq(m, i) = fwave(m, 1, i);
+      apdq(m, i) = fwave(m, 2, i);
+    }
+}
+
+// cubic_1D -- riemann/src/rp1_cubic.f90:25-38 (q_t + (q^3)_x = 0; all fluctuation to the right)
+template <class R>
+void rp1_cubic(int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>, V3<R> wave, V2<R> s,
+               V2<R> amdq, V2<R> apdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    wave(1, 1, i) = ql(1, i) - qr(1, i - 1);
+    s(1, i) = ql(1, i) * ql(1, i) + ql(1, i) * qr(1, i - 1) + qr(1, i - 1) * qr(1, i - 1);
+    amdq(1, i) = R(0.0);
+    apdq(1, i) = ql(1, i) * ql(1, i) * ql(1, i) - qr(1, i - 1) * qr(1, i - 1) * qr(1, i - 1);
+  }
+}
+
 template <class R> inline bool select_rp1(int rp_id, Rp1<R>& rp) {
   switch (rp_id) {
     case RP_ADVECTION_1D: rp = rp1_advection<R>; return true;
@@ -161,6 +435,14 @@ template <class R> inline bool select_rp1(int rp_id, Rp1<R>& rp) {
     case RP_BURGERS_1D: rp = rp1_burgers<R>; return true;
     case RP_SHALLOW_ROE_EFIX_1D: rp = rp1_shallow_roe_efix<R>; return true;
     case RP_SHALLOW_HLLE_1D: rp = rp1_shallow_hlle<R>; return true;
+    case RP_TRAFFIC_1D: rp = rp1_traffic<R>; return true;
+    case RP_ADVECTION_COLOR_1D: rp = rp1_advection_color<R>; return true;
+    case RP_ACOUSTICS_VARIABLE_1D: rp = rp1_acoustics_variable<R>; return true;
+    case RP_SHALLOW_BATHYMETRY_FWAVE_1D: rp = rp1_shallow_bathymetry_fwave<R>; return true;
+    case RP_EULER_EFIX_1D: rp = rp1_euler_efix<R>; return true;
+    case RP_EULER_HLLE_1D: rp = rp1_euler_hlle<R>; return true;
+    case RP_NONLINEAR_ELASTICITY_FWAVE_1D: rp = rp1_nonlinear_elasticity_fwave<R>; return true;
+    case RP_CUBIC_1D: rp = rp1_cubic<R>; return true;
   }
   return false;
 }

@@ -41,6 +41,14 @@ RP_IDS = {
     'burgers_1D': 23,
     'shallow_roe_with_efix_1D': 24,
     'shallow_hlle_1D': 25,
+    'traffic_1D': 26,
+    'advection_color_1D': 27,
+    'acoustics_variable_1D': 28,
+    'shallow_bathymetry_fwave_1D': 29,
+    'euler_with_efix_1D': 30,
+    'euler_hlle_1D': 31,
+    'nonlinear_elasticity_fwave_1D': 32,
+    'cubic_1D': 33,
 }
 # COMMON /cparam/ member order of each solver (rpn2_advection.f90, rpn2_acoustics.f90:52,
 # rpn2_euler_4wave.f90:71, rpn2_shallow_roe_with_efix.f90:59; vc_acoustics_3D has none)
@@ -67,6 +75,14 @@ CPARAM_NAMES = {
     'burgers_1D': (),
     'shallow_roe_with_efix_1D': ('grav',),
     'shallow_hlle_1D': ('grav',),
+    'traffic_1D': ('umax',),   # rp1_traffic.f90:39-40
+    'advection_color_1D': (),   # rp1_advection_color.f90: velocity in aux
+    'acoustics_variable_1D': (),   # rp1_acoustics_variable.f90: Z, c in aux
+    'shallow_bathymetry_fwave_1D': ('grav', 'dry_tolerance', 'sea_level'),   # rp1_shallow_bathymetry_fwave.f90:42-43
+    'euler_with_efix_1D': ('gamma',),   # rp1_euler_with_efix.f90:66
+    'euler_hlle_1D': ('gamma',),   # rp1_euler_hlle.f90:47
+    'nonlinear_elasticity_fwave_1D': (),   # rp1_nonlinear_elasticity_fwave.f90: rho, coefA, coefB in aux
+    'cubic_1D': (),   # rp1_cubic.f90
 }
 NUM_EQN = {'advection_2D': 1, 'acoustics_2D': 3, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
            'vc_acoustics_3D': 4, 'euler_3D': 5, 'vc_acoustics_2D': 3, 'vc_advection_2D': 1, 'euler_5wave_2D': 5,
@@ -76,6 +92,9 @@ NUM_WAVES = {'advection_2D': 1, 'acoustics_2D': 2, 'euler_4wave_2D': 4, 'shallow
              'vc_acoustics_3D': 2, 'euler_3D': 3, 'vc_acoustics_2D': 2, 'vc_advection_2D': 1, 'euler_5wave_2D': 5,
              'psystem_2D': 2, 'euler_hlle_2D': 2, 'shallow_hlle_2D': 2,
              'acoustics_mapped_2D': 2, 'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'burgers_2D': 1, 'vc_advection_3D': 1, 'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2}
+
+NUM_EQN.update({'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2, 'euler_with_efix_1D': 3, 'euler_hlle_1D': 3, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1})
+NUM_WAVES.update({'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2, 'euler_with_efix_1D': 3, 'euler_hlle_1D': 2, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1})
 
 BC_CUSTOM, BC_EXTRAP, BC_PERIODIC, BC_WALL = 0, 1, 2, 3
 

@@ -65,3 +65,9 @@ def ref_solver(sc, nthreads=1):
 
 def goldens():
     return np.load(os.path.join(ROOT, 'tests', 'golden', 'reference_goldens.npz'))
+
+
+def goldens4():
+    """1-D vectors of tests/golden/make_golden4.py (traffic, advection_1d_variable, stegoton_1d, shallow_1d sill,
+    euler_1d shock-tube density)."""
+    return np.load(os.path.join(ROOT, 'tests', 'golden', 'reference_goldens4.npz'))
