@@ -8,10 +8,15 @@
 // The reference updates q in place; here input and output are separate buffers (the halo reads of neighbouring CTAs
 // must see the old values).  1-D problems are small: this kernel is about completeness and parity, not throughput.
 #pragma once
+#include <type_traits>
 #include "sweep2.cuh"
 
 namespace clawcuda {
 namespace CLAW_NS {
+
+// number of aux components a 1-D functor reads (0 unless it declares MAUX; see rp1.cuh)
+template <class RP, class = void> struct Rp1Aux { static constexpr int N = 0; };
+template <class RP> struct Rp1Aux<RP, std::void_t<decltype(RP::MAUX)>> { static constexpr int N = RP::MAUX; };
 
 template <class RP, int NT>
 __global__ void __launch_bounds__(NT) sweep1(const __grid_constant__ Sweep2Params P) {
@@ -42,7 +47,19 @@ __global__ void __launch_bounds__(NT) sweep1(const __grid_constant__ Sweep2Param
 
   // interface at my left face: Fortran i = I-1; rp1 range i = 2-mbc .. mx+mbc  <=>  I = 1 .. mx+3
   double wave[W][M], s[W], amdq[M], apdq[M];
-  RP::normal(P.rp, ql, q, wave, s, amdq, apdq);
+  if constexpr (Rp1Aux<RP>::N > 0) {                               // aux columns of the left cell and of mine
+    constexpr int NA = Rp1Aux<RP>::N;
+    const int Il = Ic > 0 ? Ic - 1 : 0;
+    double al[NA], ar[NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+      al[k] = P.aux[k + (long long)Il * P.maux];
+      ar[k] = P.aux[k + (long long)Ic * P.maux];
+    }
+    RP::normal(P.rp, ql, q, al, ar, wave, s, amdq, apdq);
+  } else {
+    RP::normal(P.rp, ql, q, wave, s, amdq, apdq);
+  }
   const bool active = (I >= 2) && (I <= P.mx + 2) && (t >= 1);   // i = 1 .. mx+1: update / CFL / second-order range
 
   double cfl = 0.0;

@@ -24,6 +24,14 @@ cudaError_t launch_sweep1(int rp_id, Sweep2Params& P, cudaStream_t st, LaunchInf
     case 23: return launch1<RpBurgers1D>(P, st, info);
     case 24: return launch1<RpShallowRoeEfix1D>(P, st, info);
     case 25: return launch1<RpShallowHlle1D>(P, st, info);
+    case 26: return launch1<RpTraffic1D>(P, st, info);
+    case 27: return launch1<RpAdvectionColor1D>(P, st, info);
+    case 28: return launch1<RpAcousticsVariable1D>(P, st, info);
+    case 29: return launch1<RpShallowBathymetryFwave1D>(P, st, info);
+    case 30: return launch1<RpEulerEfix1D>(P, st, info);
+    case 31: return launch1<RpEulerHlle1D>(P, st, info);
+    case 32: return launch1<RpNonlinearElasticityFwave1D>(P, st, info);
+    case 33: return launch1<RpCubic1D>(P, st, info);
   }
   return cudaErrorInvalidValue;
 }

@@ -30,6 +30,14 @@ _SOLVERS = {
     'burgers_1D': (23, (), 1),
     'shallow_roe_with_efix_1D': (24, ('grav',), 1),
     'shallow_hlle_1D': (25, ('grav',), 1),
+    'traffic_1D': (26, ('umax',), 1),                         # rp1_traffic.f90:39
+    'advection_color_1D': (27, (), 1),                        # rp1_advection_color.f90 (velocity in aux)
+    'acoustics_variable_1D': (28, (), 1),                     # rp1_acoustics_variable.f90 (Z, c in aux)
+    'shallow_bathymetry_fwave_1D': (29, ('grav', 'dry_tolerance', 'sea_level'), 1),   # rp1_shallow_bathymetry_fwave.f90:42
+    'euler_with_efix_1D': (30, ('gamma',), 1),                # rp1_euler_with_efix.f90:66
+    'euler_hlle_1D': (31, ('gamma',), 1),                     # rp1_euler_hlle.f90:47
+    'nonlinear_elasticity_fwave_1D': (32, (), 1),             # rp1_nonlinear_elasticity_fwave.f90 (rho, coefA, coefB in aux)
+    'cubic_1D': (33, (), 1),                                  # rp1_cubic.f90
 }
 
 for _name, (_id, _cp, _nd) in _SOLVERS.items():

@@ -9,6 +9,8 @@ num_eqn = {
     'vc_acoustics_2D': 3, 'vc_elasticity_2D': 5, 'vc_acoustics_3D': 4, 'euler_3D': 5,
     'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2,
     'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'vc_advection_3D': 1,
+    'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2,
+    'euler_with_efix_1D': 3, 'euler_hlle_1D': 3, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1,
 }
 
 num_waves = {
@@ -18,7 +20,10 @@ num_waves = {
     'vc_acoustics_2D': 2, 'vc_elasticity_2D': 4, 'vc_acoustics_3D': 2, 'euler_3D': 3,
     'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2,
     'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'vc_advection_3D': 1,
+    'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2,
+    'euler_with_efix_1D': 3, 'euler_hlle_1D': 2, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1,
 }
 
 fwave = {name: False for name in num_eqn}
-fwave.update({'psystem_2D': True, 'shallow_bathymetry_fwave_2D': True})      # riemann/riemann/static.py:155,158
+fwave.update({'psystem_2D': True, 'shallow_bathymetry_fwave_2D': True,
+              'shallow_bathymetry_fwave_1D': True, 'nonlinear_elasticity_fwave_1D': True})      # riemann/riemann/static.py:155,158

@@ -63,7 +63,15 @@ enum {
   CLAW_RP_ACOUSTICS_1D = 22,           /* rp1_acoustics.f90 */
   CLAW_RP_BURGERS_1D = 23,             /* rp1_burgers.f90 */
   CLAW_RP_SHALLOW_ROE_EFIX_1D = 24,    /* rp1_shallow_roe_with_efix.f90 */
-  CLAW_RP_SHALLOW_HLLE_1D = 25         /* rp1_shallow_hlle.f90 */
+  CLAW_RP_SHALLOW_HLLE_1D = 25,        /* rp1_shallow_hlle.f90 */
+  CLAW_RP_TRAFFIC_1D = 26,             /* rp1_traffic.f90 (cparam = umax) */
+  CLAW_RP_ADVECTION_COLOR_1D = 27,     /* rp1_advection_color.f90 (aux: velocity) */
+  CLAW_RP_ACOUSTICS_VARIABLE_1D = 28,  /* rp1_acoustics_variable.f90 (aux: impedance, sound speed) */
+  CLAW_RP_SHALLOW_BATHYMETRY_FWAVE_1D = 29, /* rp1_shallow_bathymetry_fwave.f90 (f-wave; aux: bathymetry) */
+  CLAW_RP_EULER_EFIX_1D = 30,          /* rp1_euler_with_efix.f90 (cparam = gamma) */
+  CLAW_RP_EULER_HLLE_1D = 31,          /* rp1_euler_hlle.f90 (cparam = gamma) */
+  CLAW_RP_NONLINEAR_ELASTICITY_FWAVE_1D = 32, /* rp1_nonlinear_elasticity_fwave.f90 (f-wave; aux: density, coefA, coefB) */
+  CLAW_RP_CUBIC_1D = 33                /* rp1_cubic.f90 */
 };
 
 /* Boundary-condition ids = pyclaw.BC (pyclaw/src/pyclaw/solver.py:13-19) */
@@ -188,8 +196,8 @@ int claw_step3ds_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, i
 /* 1-D: claw_step1_host <-> step1 (pyclaw/src/pyclaw/classic/step1.f90:2-3 as called at classic/solver.py:302):
    q(meqn, mx+2*num_ghost) with ghost cells is updated IN PLACE (interior and the ghost cells the Fortran touches),
    aux(maux, mx+2*num_ghost) may be NULL when maux == 0; the f2py scratch arguments (f, wave, s, amdq, apdq, dtdx) are
-   internal.  1-D Riemann solver ids: 21 advection_1D, 22 acoustics_1D, 23 burgers_1D, 24 shallow_roe_with_efix_1D,
-   25 shallow_hlle_1D (riemann/src/rp1_*.f90). */
+   internal.  1-D Riemann solver ids: CLAW_RP_*_1D above, 21..33 (riemann/src/rp1_*.f90); solvers that read aux
+   (27, 28, 29, 32) fail with code 7 when aux is NULL or has too few components. */
 int claw_step1_host(int meqn, int mwaves, int maux, int num_ghost, int mx, double* q, const double* aux,
                     double dx, double dt, const int* method7, const int* mthlim, int use_fwave,
                     int rp_id, const double* cparam, int ncparam, int mode, double* cfl);

@@ -158,6 +158,20 @@ int clawref_step1(int num_eqn, int num_waves, int num_ghost, int num_aux, int mx
                        use_fwave != 0, rp_id, cparam);
 }
 
+// One rp1 call on a pencil of n = mx + 2*num_ghost cells: q(num_eqn, n), aux(num_aux, n); interface slot k (array
+// index, k = 1 .. n-1) lies between cells k-1 and k: wave(num_eqn, num_waves, n), s(num_waves, n), amdq/apdq(num_eqn, n).
+// Used by tests/test_host_functors.py to compare the device functor source (host-compiled) with the oracle.
+int clawref_rp1(int num_eqn, int num_waves, int num_ghost, int num_aux, int mx, double* q, double* aux, double* wave,
+                double* s, double* amdq, double* apdq, int rp_id, const double* cparam) {
+  Rp1<double> rp;
+  if (!select_rp1<double>(rp_id, rp)) return 1;
+  const int lo = 1 - num_ghost, na = num_aux > 0 ? num_aux : 1;
+  V2<double> Q{q, num_eqn, lo}, A{aux, na, lo}, S{s, num_waves, lo}, AM{amdq, num_eqn, lo}, AP{apdq, num_eqn, lo};
+  V3<double> W{wave, num_eqn, num_waves, lo};
+  rp(mx, num_eqn, num_waves, num_aux, num_ghost, mx, Q, Q, A, A, W, S, AM, AP, cparam);
+  return 0;
+}
+
 int clawref_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

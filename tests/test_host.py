@@ -217,3 +217,29 @@ def test_host_loop_1d_with_plugin_matches_oracle_loop(oracle_lib):
         r.run(sc['tfinal'], sc['num_output_times'])
         assert np.array_equal(claw.solution.state.q, r.q), sc['rp']
         assert claw.solver.step_log == r.step_log
+
+
+def test_host_loop_1d_aux_fwave_custom_bc_with_plugin(oracle_lib):
+    """ClawSolver1D with solvers that read aux (periodic / extrapolated aux ghost cells), f-wave solvers, and the
+    stegoton example's moving-wall ``BC.custom`` (reads t and aux, leaves one ghost cell stale): the host mirror with
+    the oracle plug-in against the oracle's own loop, and -- end to end through Controller.run() -- against the
+    reference's stored vectors (traffic/test_traffic.py:21-22, advection_1d_variable/...:35-36,
+    shallow_1d/test_shallow1d.py:41-44; L1 < 1e-6)."""
+    from refutil import goldens4
+    g4 = goldens4()
+    for sc, key in ((S.traffic_1d(), 'traffic__classic'),
+                    (S.advection_1d_variable(), 'advection_1d_variable__fortran_classic'),
+                    (S.sill_1d(), 'shallow_1d__sill_Fortran'),
+                    (S.stegoton_1d(xupper=40.0, tfinal=25.0, num_output_times=5), None),
+                    (S.stegoton_1d(xupper=30.0, tfinal=22.0, num_output_times=4, exponential=False), None),
+                    (S.shocktube_1d(mx=100), None), (S.blast_1d(mx=120, tfinal=0.01), None),
+                    (S.cubic_1d(mx=80, tfinal=0.05), None), (S.acoustics_1d_variable(mx=90, tfinal=0.4), None)):
+        claw = S.make_claw(sc, kernel_language='Fortran', fmod=OracleFmod())
+        claw.run()
+        r = ref_solver(sc)
+        r.run(sc['tfinal'], sc['num_output_times'])
+        assert np.array_equal(claw.solution.state.q, r.q), sc['rp']
+        assert claw.solver.step_log == r.step_log
+        if key is not None:
+            q = claw.frames[claw.num_output_times].state.get_q_global()[0].reshape(-1)
+            assert claw.solution.domain.grid.delta[0] * np.sum(np.abs(q - g4[key])) < 1e-6, key

@@ -1,0 +1,124 @@
+"""The DEVICE functor source of the 1-D Riemann solvers (clawpack_b200/csrc/rp1.cuh), compiled by the host compiler
+with the strict mode's unfused IEEE arithmetic (tests/host_functors/rp1_host.cpp), against the oracle's rp1 routines
+on the same pencils: bit for bit.  This checks the arithmetic the GPU will execute in strict mode on a machine without
+a GPU; the kernels around the functors (sweep1.cuh) are covered by the `-m gpu` parity tests."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from refutil import pyclaw_ref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, 'host_functors', 'rp1_host.cpp')
+CXX = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
+
+
+@pytest.fixture(scope='module')
+def hostlib(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp('hostfun') / 'librp1_host.so')
+    subprocess.run([CXX, '-O2', '-ffp-contract=off', '-std=c++17', '-fPIC', '-shared', '-Wno-unknown-pragmas',
+                    '-o', out, SRC], check=True)
+    L = ctypes.CDLL(out)
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.hostfun_rp1.argtypes = [ctypes.c_int, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [dp] * 6
+    L.hostfun_rp1.restype = ctypes.c_int
+    R = pyclaw_ref.lib()
+    R.clawref_rp1.argtypes = [ctypes.c_int] * 5 + [dp] * 6 + [ctypes.c_int, dp]
+    R.clawref_rp1.restype = ctypes.c_int
+    return L, R
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _pencils(name, rng, n):
+    """Random states of a physically admissible kind for each solver, mixing smooth data, jumps, sign changes and
+    (where the solver has one) states that trigger the entropy fix / dry-state branches."""
+    aux = None
+    cp = []
+    if name in ('advection_1D',):
+        q = rng.standard_normal((1, n)); cp = [rng.choice([-0.7, 1.3])]
+    elif name == 'acoustics_1D':
+        q = rng.standard_normal((2, n)); cp = [1.3, 2.9, np.sqrt(2.9 / 1.3), 1.3 * np.sqrt(2.9 / 1.3)]
+    elif name in ('burgers_1D', 'cubic_1D'):
+        q = rng.standard_normal((1, n)) * 2
+    elif name == 'traffic_1D':
+        q = rng.uniform(0, 1, (1, n)); cp = [rng.uniform(0.5, 2.0)]
+    elif name in ('shallow_roe_with_efix_1D', 'shallow_hlle_1D'):
+        h = rng.uniform(0.05, 3.0, n); u = rng.standard_normal(n) * 2
+        q = np.stack([h, h * u]); cp = [9.81]
+    elif name == 'advection_color_1D':
+        q = rng.standard_normal((1, n)); aux = rng.standard_normal((1, n))
+    elif name == 'acoustics_variable_1D':
+        q = rng.standard_normal((2, n)); aux = rng.uniform(0.5, 4.0, (2, n))
+    elif name == 'shallow_bathymetry_fwave_1D':
+        h = rng.uniform(0.0, 2.0, n); h[rng.random(n) < 0.2] = 5e-4          # some cells below dry_tolerance
+        u = rng.standard_normal(n)
+        q = np.stack([h, h * u]); aux = rng.uniform(-1.0, 0.0, (1, n)); cp = [9.8, 1e-3, 0.0]
+    elif name in ('euler_with_efix_1D', 'euler_hlle_1D'):
+        rho = rng.uniform(0.1, 3.0, n); u = rng.standard_normal(n) * 2; p = rng.uniform(0.1, 5.0, n)
+        if name == 'euler_hlle_1D':
+            # rp1_euler_hlle.f90:62-64 forms H_r with p_l and c^2 as gamma1*H - u^2/2 (= 1.4 p/rho - 0.3 u^2): keep the
+            # square roots real with mild pressure jumps and |u| < 1.5
+            rho = rng.uniform(0.8, 1.2, n); p = rng.uniform(1.0, 1.3, n); u = rng.uniform(-1.5, 1.5, n)
+        q = np.stack([rho, rho * u, p / 0.4 + 0.5 * rho * u * u]); cp = [1.4]
+    elif name == 'nonlinear_elasticity_fwave_1D':
+        q = np.stack([rng.uniform(-0.2, 0.5, n), rng.standard_normal(n)])
+        aux = np.stack([rng.uniform(1.0, 4.0, n), np.zeros(n), rng.uniform(1.0, 4.0, n)])     # linear relation: no exp()
+    else:
+        raise KeyError(name)
+    # smooth stretches and exact repeats (zero-strength waves) as well
+    q[:, n // 2: n // 2 + 8] = q[:, n // 2: n // 2 + 1]
+    return np.asfortranarray(q), (None if aux is None else np.asfortranarray(aux)), np.array(cp + [0.0])
+
+
+NAMES_1D = sorted(k for k in pyclaw_ref.RP_IDS if k.endswith('_1D'))
+
+
+@pytest.mark.parametrize('name', NAMES_1D)
+def test_device_functor_source_matches_oracle_rp1(hostlib, name):
+    L, R = hostlib
+    rp_id = pyclaw_ref.RP_IDS[name]
+    M, W = pyclaw_ref.NUM_EQN[name], pyclaw_ref.NUM_WAVES[name]
+    rng = np.random.default_rng(1234 + rp_id)
+    mx, g = 4093, 2
+    n = mx + 2 * g
+    q, aux, cp = _pencils(name, rng, n)
+    maux = 0 if aux is None else aux.shape[0]
+    auxo = np.zeros((1, n), order='F') if aux is None else aux
+    wo, so = np.zeros((M, W, n), order='F'), np.zeros((W, n), order='F')
+    amo, apo = np.zeros((M, n), order='F'), np.zeros((M, n), order='F')
+    assert R.clawref_rp1(M, W, g, maux, mx, _dp(q), _dp(auxo), _dp(wo), _dp(so), _dp(amo), _dp(apo), rp_id, _dp(cp)) == 0
+    # host-compiled device functor: interface k between cells k and k+1  <->  oracle slot k+1
+    wd, sd = np.zeros((M, W, n - 1), order='F'), np.zeros((W, n - 1), order='F')
+    amd, apd = np.zeros((M, n - 1), order='F'), np.zeros((M, n - 1), order='F')
+    assert L.hostfun_rp1(rp_id, _dp(cp), len(cp) - 1, n - 1, maux, _dp(q), _dp(auxo), _dp(wd), _dp(sd), _dp(amd),
+                         _dp(apd)) == 0
+    for a, b, what in ((wd, wo[..., 1:], 'wave'), (sd, so[:, 1:], 's'), (amd, amo[:, 1:], 'amdq'), (apd, apo[:, 1:], 'apdq')):
+        assert np.isfinite(b).all(), (name, what)
+        assert np.array_equal(a, b), (name, what, float(np.max(np.abs(a - b))))
+
+
+def test_nonlinear_elasticity_exponential_relation_within_roundoff(hostlib):
+    """coefA > 0: sigma = exp(coefA*eps) - 1.  Same library on both sides here (so equal bits); on the GPU exp() may
+    differ in the last bit, which is why the GPU parity tests hold this material to the 1e-12 tolerance."""
+    L, R = hostlib
+    name = 'nonlinear_elasticity_fwave_1D'
+    rp_id = pyclaw_ref.RP_IDS[name]
+    rng = np.random.default_rng(7)
+    mx, g = 509, 2
+    n = mx + 2 * g
+    q = np.asfortranarray(np.stack([rng.uniform(-0.2, 0.5, n), rng.standard_normal(n)]))
+    aux = np.asfortranarray(np.stack([rng.uniform(1.0, 4.0, n), rng.uniform(1.0, 4.0, n), np.zeros(n)]))
+    cp = np.zeros(1)
+    wo, so = np.zeros((2, 2, n), order='F'), np.zeros((2, n), order='F')
+    amo, apo = np.zeros((2, n), order='F'), np.zeros((2, n), order='F')
+    assert R.clawref_rp1(2, 2, g, 3, mx, _dp(q), _dp(aux), _dp(wo), _dp(so), _dp(amo), _dp(apo), rp_id, _dp(cp)) == 0
+    wd, sd = np.zeros((2, 2, n - 1), order='F'), np.zeros((2, n - 1), order='F')
+    amd, apd = np.zeros((2, n - 1), order='F'), np.zeros((2, n - 1), order='F')
+    assert L.hostfun_rp1(rp_id, _dp(cp), 0, n - 1, 3, _dp(q), _dp(aux), _dp(wd), _dp(sd), _dp(amd), _dp(apd)) == 0
+    assert np.array_equal(wd, wo[..., 1:]) and np.array_equal(sd, so[:, 1:])

@@ -1,0 +1,96 @@
+"""GPU parity tests of the 1-D solvers added after the first batch (rp_id 26..33: traffic, advection_color,
+acoustics_variable, shallow_bathymetry_fwave, euler_with_efix, euler_hlle, nonlinear_elasticity_fwave, cubic) through
+claw_step1_host behind ClawSolver1D: bit-exact against the oracle in strict mode, within the north_star tolerance in
+fast mode, and against the reference's stored vectors through Controller.run().  The functor arithmetic itself is also
+checked without a GPU by tests/test_host_functors.py.  (File name: collected after the older GPU test files.)"""
+import numpy as np
+import pytest
+
+from clawpack_b200 import scenarios as S
+from refutil import goldens4
+from test_cuda_parity import _rel_linf, _run_cuda, _run_ref
+
+pytestmark = pytest.mark.gpu
+
+CASES_1D_MORE = {
+    'traffic': lambda: S.traffic_1d(mx=500),
+    'traffic_first_order': lambda: dict(S.traffic_1d(mx=77), order=1),
+    'advection_color': lambda: S.advection_1d_variable(mx=100),
+    'advection_color_tile_edge': lambda: dict(S.advection_1d_variable(mx=124 * 3 - 4 + 1), limiters=S.SUPERBEE),
+    'acoustics_variable': lambda: S.acoustics_1d_variable(mx=400),
+    'sill': lambda: S.sill_1d(mx=500),
+    'sill_tiny': lambda: S.sill_1d(mx=5),
+    'shocktube_hlle': lambda: S.shocktube_1d(mx=800),
+    'shocktube_roe': lambda: S.shocktube_1d(mx=300, riemann_solver='roe'),
+    'blast_roe_walls': lambda: S.blast_1d(mx=800),
+    'stegoton_linear': lambda: S.stegoton_1d(xupper=60.0, exponential=False),
+    'cubic': lambda: S.cubic_1d(mx=250),
+}
+
+
+@pytest.mark.parametrize('name', sorted(CASES_1D_MORE))
+def test_1d_more_strict_bit_exact_vs_oracle(name):
+    sc = CASES_1D_MORE[name]()
+    q, log, solver = _run_cuda(sc, 60, 'strict')
+    qr, logr = _run_ref(sc, 60)
+    assert solver._dev is None and solver.fmod is not None          # 1-D always runs through the plug-in call
+    assert log == logr, 'dt / CFL sequence differs: %r vs %r' % (log[:3], logr[:3])
+    assert np.array_equal(q, qr), 'max abs diff %g' % np.max(np.abs(q - qr))
+
+
+@pytest.mark.parametrize('name', sorted(CASES_1D_MORE))
+def test_1d_more_fast_within_tolerance(name):
+    sc = CASES_1D_MORE[name]()
+    qr, logr = _run_ref(sc, 101)
+    q, log, _ = _run_cuda(sc, 101, 'fast')
+    assert [s[2] for s in log] == [s[2] for s in logr]
+    assert _rel_linf(q, qr) <= 1e-10
+
+
+@pytest.mark.parametrize('precision', ['strict', 'fast'])
+def test_stegoton_exponential_relation(precision):
+    """sigma = exp(K eps) - 1 calls exp(): CUDA's and glibc's results may differ in the last bit, so this material is
+    held to the tolerance (1e-12 per step, 1e-10 after 100 steps) in both arithmetic modes, like psystem_2D."""
+    sc = S.stegoton_1d(xupper=60.0)
+    for nsteps, tol in ((1, 1e-12), (120, 1e-10)):
+        qr, logr = _run_ref(sc, nsteps)
+        q, log, _ = _run_cuda(sc, nsteps, precision)
+        assert [s[2] for s in log] == [s[2] for s in logr]
+        assert np.allclose([s[0] for s in log], [s[0] for s in logr], rtol=1e-12, atol=0)
+        assert np.max(np.abs(q - qr)) <= tol * max(np.max(np.abs(qr)), 1e-3)
+
+
+@pytest.mark.parametrize('precision', ['strict', 'fast'])
+def test_1d_more_reference_goldens(precision):
+    """traffic/test_traffic.py:21-22, advection_1d_variable/test_variable_coefficient_advection.py:35-36,
+    shallow_1d/test_shallow1d.py:41-44, stegoton_1d/test_stego.py:21-22 (each: L1 < 1e-6 against expected_sols.npy) and
+    the envelope of euler_1d/test_shocktube.py:17-26, through Controller.run() with kernel_language='CUDA'."""
+    g4 = goldens4()
+    for sc, key in ((S.traffic_1d(), 'traffic__classic'),
+                    (S.advection_1d_variable(), 'advection_1d_variable__fortran_classic'),
+                    (S.sill_1d(), 'shallow_1d__sill_Fortran'),
+                    (S.stegoton_1d(), 'stegoton_1d__fortran_classic')):
+        claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision=precision)
+        claw.run()
+        q = claw.frames[claw.num_output_times].state.get_q_global()[0].reshape(-1)
+        dx = claw.solution.domain.grid.delta[0]
+        assert dx * np.sum(np.abs(q - g4[key])) < 1e-6, key
+        assert np.max(np.abs(q - g4[key])) < 1e-10, key
+    claw = S.make_claw(S.shocktube_1d(), kernel_language='CUDA', cuda_precision=precision)
+    claw.run()
+    rho = claw.frames[claw.num_output_times].state.get_q_global()[0].reshape(-1)
+    assert np.max(np.abs(rho - g4['euler_1d__shocktube_regression_density'])) < 0.04 - 1e-4
+
+
+def test_aux_solver_without_aux_is_refused():
+    """claw_step1_host: a solver that reads aux fails loudly (code 7) when no aux array is handed over."""
+    import ctypes
+    from clawpack_b200 import _lib
+    L = _lib.lib()
+    q = np.zeros((1, 14), order='F')
+    method = np.array([1, 2, 0, 0, 0, 0, 0], dtype=np.intc)
+    mth = np.array([1], dtype=np.intc)
+    cfl = ctypes.c_double(0.0)
+    rc = L.claw_step1_host(1, 1, 0, 2, 10, q.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(0), 0.1, 0.01,
+                           _lib.ip(method), _lib.ip(mth), 0, 27, _lib.dp(np.zeros(1)), 0, 0, ctypes.byref(cfl))
+    assert rc == 7
