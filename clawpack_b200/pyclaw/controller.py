@@ -1,9 +1,13 @@
 """Controller: the output-time loop around ``solver.evolve_to_time`` (pyclaw/src/pyclaw/controller.py:275-397).
 
-Kept thin: output styles 1-3, ``keep_copy`` frames, ``tfinal``, ``num_output_times``, frame files through
-``Solution.write`` (``output_format='ascii'`` as in the reference, ``None`` for no files), gauge files."""
+Output styles 1-3, ``keep_copy`` frames, ``tfinal``, ``num_output_times``, frame files through ``Solution.write``
+(``output_format='ascii'`` as in the reference, ``'binary'`` / ``'binary32'`` for raw dumps of large grids, ``None``
+for no files), derived quantities (``compute_p`` -> ``<outdir>/_p/claw_p.*``), output functionals (``compute_F`` ->
+``<outdir>/F.txt``), the ``overwrite`` guard, gauge files.  The plotting / xclaw-runner attributes of the reference
+Controller are not part of this build."""
 import copy
 import logging
+import os
 
 import numpy as np
 
@@ -30,8 +34,20 @@ class Controller(object):
         self.nstepout = 1
         self.start_frame = 0
         self.setplot = None
-        self.compute_p = None
-        self.compute_F = None
+        self.file_prefix_p = 'claw_p'                    # controller.py:186
+        self.compute_p = None                            # f(state): fills state.p (controller.py:188-190)
+        self.compute_F = None                            # f(state): fills state.F (controller.py:192-195)
+        self.F_file_name = 'F'
+
+    @property
+    def outdir_p(self):
+        """Directory of the derived-quantity frames (controller.py:73-75)."""
+        return os.path.join(self.outdir, '_p')
+
+    @property
+    def F_path(self):
+        """File of the output functionals (controller.py:77-79)."""
+        return os.path.join(self.outdir, self.F_file_name + '.txt')
 
     @property
     def verbosity(self):
@@ -78,9 +94,14 @@ class Controller(object):
         if self.keep_copy:
             self.frames.append(copy.deepcopy(self.solution))
         if self.output_format is not None:
+            if os.path.exists(self.outdir) and self.overwrite is False:              # controller.py:331-333
+                raise Exception('Refusing to overwrite existing output data. \n'
+                                'Either delete/move the directory or set controller.overwrite=True.')
+            self._write_p(frame)
             self.solution.write(frame, self.outdir, self.output_format, self.output_file_prefix,
                                 self.write_aux_always or self.write_aux_init, self.output_options)
-        self.logger.info('Solution %s computed for time t=%f' % (frame, self.solution.t))
+        self.write_F('w')
+        self.log_info('Solution %s computed for time t=%f' % (frame, self.solution.t))
 
         status = None
         for t in output_times[1:]:
@@ -93,10 +114,39 @@ class Controller(object):
             if self.keep_copy:
                 self.frames.append(copy.deepcopy(self.solution))
             if self.output_format is not None:
+                self._write_p(frame)
                 self.solution.write(frame, self.outdir, self.output_format, self.output_file_prefix,
                                     self.write_aux_always, self.output_options)
-            self.logger.info('Solution %s computed for time t=%f' % (frame, self.solution.t))
+            self.write_F()
+            self.log_info('Solution %s computed for time t=%f' % (frame, self.solution.t))
+            for gfile in grid.gauge_files:                                           # controller.py:388-389
+                gfile.flush()
         for gfile in grid.gauge_files:
             gfile.close()
         self.solution._start_frame = len(self.frames)
         return status
+
+    # ---- derived quantities and functionals (controller.py:334-342, 399-409) ------------------------
+    def _write_p(self, frame):
+        if self.compute_p is None:
+            return
+        self.compute_p(self.solution.state)
+        self.solution.write(frame, self.outdir_p, self.output_format, self.file_prefix_p, write_aux=False,
+                            options=self.output_options, write_p=True)
+
+    def write_F(self, mode='a'):
+        if self.compute_F is None:
+            return
+        state = self.solution.state
+        self.compute_F(state)
+        F = [state.sum_F(i) for i in range(state.mF)]
+        if self.is_proc_0():
+            os.makedirs(self.outdir, exist_ok=True)
+            with open(self.F_path, mode) as f:
+                f.write(str(self.solution.t) + ' ' + ' '.join(str(j) for j in F) + '\n')
+
+    def is_proc_0(self):
+        return True
+
+    def log_info(self, msg):
+        self.logger.info(msg)

@@ -104,14 +104,26 @@ class Solution(object):
         if file_format == 'ascii':
             from .fileio import ascii
             return ascii.write
-        raise ValueError("File format '%s' is not part of this build (only 'ascii'; hdf5 / netcdf / petsc / vtk "
-                         "need libraries that are not available here)." % file_format)
+        if file_format[:6] == 'binary':                 # 'binary' / 'binary64' / 'binary32' (solution.py:286-293)
+            from .fileio import binary
+            if file_format == 'binary':
+                return binary.write
+            return lambda sol, frame, path, **kw: binary.write(
+                sol, frame, path, **dict(kw, options=dict(kw.get('options') or {}, format=file_format)))
+        raise ValueError("File format '%s' is not part of this build ('ascii', 'binary', 'binary32'; hdf5 / netcdf / "
+                         "petsc / vtk need libraries that are not available here)." % file_format)
 
     def get_read_func(self, file_format):
         if file_format == 'ascii':
             from .fileio import ascii
             return ascii.read
-        raise ValueError("File format '%s' cannot be read by this build (only 'ascii')." % file_format)
+        if file_format[:6] == 'binary':
+            from .fileio import binary
+            if file_format == 'binary':
+                return binary.read
+            return lambda sol, frame, path, **kw: binary.read(
+                sol, frame, path, **dict(kw, options=dict(kw.get('options') or {}, format=file_format)))
+        raise ValueError("File format '%s' cannot be read by this build ('ascii', 'binary', 'binary32')." % file_format)
 
     def write(self, frame, path='./', file_format='ascii', file_prefix=None, write_aux=False, options={},
               write_p=False):

@@ -243,3 +243,108 @@ def test_host_loop_1d_aux_fwave_custom_bc_with_plugin(oracle_lib):
         if key is not None:
             q = claw.frames[claw.num_output_times].state.get_q_global()[0].reshape(-1)
             assert claw.solution.domain.grid.delta[0] * np.sum(np.abs(q - g4[key])) < 1e-6, key
+
+
+def _golden_binary_solutions():
+    src = open(os.path.join(ROOT, 'tests', 'golden', 'make_golden5.py')).read()
+    src = src.split('def small_solutions')[1].split("if __name__")[0]
+    ns = {'pyclaw': pyclaw, 'np': np}
+    exec('def small_solutions' + src, ns)
+    return ns['small_solutions']()
+
+
+def test_binary_frames_are_what_the_reference_reader_parses(tmp_path):
+    """Solution.write(file_format='binary' | 'binary32') reproduces the committed files (tests/golden/binary_frames,
+    written by this package and read back there by the REFERENCE's own reader, pyclaw/src/pyclaw/fileio/binary.py:19-208,
+    see tests/golden/make_golden5.py), and Solution.read returns exactly what the reference reader parsed."""
+    gdir = os.path.join(ROOT, 'tests', 'golden', 'binary_frames')
+    ref = np.load(os.path.join(gdir, 'reference_parsed.npz'))
+    for name, sol, frame, fmt in _golden_binary_solutions():
+        out = tmp_path / name
+        sol.write(frame, str(out), fmt, write_aux=True)
+        for fname in sorted(os.listdir(os.path.join(gdir, name))):
+            assert open(out / fname, 'rb').read() == open(os.path.join(gdir, name, fname), 'rb').read(), (name, fname)
+        back = pyclaw.Solution(frame, path=os.path.join(gdir, name), file_format=fmt, read_aux=True)
+        assert back.state.q.flags['F_CONTIGUOUS'] and back.state.q.dtype == np.float64
+        assert np.array_equal(back.state.q, ref[name + '__q'])
+        assert back.t == float(ref[name + '__t'])
+        assert [d.num_cells for d in back.domain.patch.dimensions] == list(ref[name + '__num_cells'])
+        assert np.array_equal([d.lower for d in back.domain.patch.dimensions], ref[name + '__lower'])
+        assert np.array_equal([d.delta for d in back.domain.patch.dimensions], ref[name + '__delta'])
+        if sol.num_aux:
+            # the reference reader slices aux with [mbc:-mbc] even when mbc == 0 (fileio/binary.py:195-199; its q branch
+            # has the mbc == 0 case, :104-107) and so hands back an EMPTY aux for ghost-free frames; this reader
+            # returns the stored values
+            assert ref[name + '__aux'].size == 0
+            want = sol.state.aux if fmt == 'binary64' else sol.state.aux.astype(np.float32).astype(np.float64)
+            assert np.array_equal(back.state.aux, want)
+        if fmt == 'binary64':
+            assert np.array_equal(back.state.q, sol.state.q)          # lossless, unlike the 8-digit ascii format
+        # format (and precision) auto-detected from the .t header
+        assert np.array_equal(pyclaw.Solution(frame, path=str(out)).state.q, back.state.q)
+
+
+def test_binary_reader_strips_ghost_cells(tmp_path):
+    """AMRClaw writes its binary frames WITH ghost cells and says so in the .t header; the reader drops them
+    (fileio/binary.py:104-121)."""
+    dom = pyclaw.Domain([pyclaw.Dimension(0.0, 1.0, 5, name='x'), pyclaw.Dimension(0.0, 1.0, 4, name='y')])
+    st = pyclaw.State(dom, 2, 0)
+    st.q[...] = np.arange(40.0).reshape((2, 5, 4), order='F')
+    sol = pyclaw.Solution(st, dom)
+    sol.write(1, str(tmp_path), 'binary')
+    g = 2
+    big = np.full((2, 5 + 2 * g, 4 + 2 * g), -7.0, order='F')
+    big[:, g:-g, g:-g] = st.q
+    big.ravel(order='F').tofile(str(tmp_path / 'fort.b0001'))
+    t = open(tmp_path / 'fort.t0001').read().replace('    0                  num_ghost', '    2                  num_ghost')
+    open(tmp_path / 'fort.t0001', 'w').write(t)
+    back = pyclaw.Solution(1, path=str(tmp_path), file_format='binary')
+    assert np.array_equal(back.state.q, st.q)
+
+
+def test_controller_binary_output_restart_functionals_and_overwrite_guard(oracle_lib, tmp_path):
+    """Controller.run with output_format='binary': lossless frames, a run restarted from a frame file continues
+    bit-identically; compute_p / compute_F products (controller.py:334-342, 399-409); overwrite=False refuses an
+    existing outdir (controller.py:331-333)."""
+    sc = S.acoustics_2d(mx=14, my=10, tfinal=0.06, num_output_times=3)
+    claw = S.make_claw(sc, kernel_language='Fortran', fmod=OracleFmod())
+    claw.output_format = 'binary'
+    claw.outdir = str(tmp_path / 'out')
+
+    def compute_p(state):
+        state.p[0] = state.q[0] ** 2
+
+    def compute_F(state):
+        state.F[0] = state.q[0] * state.grid.delta[0] * state.grid.delta[1]
+
+    claw.solution.state.mp = 1
+    claw.solution.state.mF = 1
+    claw.compute_p = compute_p
+    claw.compute_F = compute_F
+    claw.run()
+    names = sorted(os.listdir(claw.outdir))
+    assert [n for n in names if n.startswith('fort.b')] == ['fort.b000%d' % k for k in range(4)]
+    back = pyclaw.Solution(3, path=claw.outdir)
+    assert back.t == float('%18.8e' % claw.solution.t)
+    assert np.array_equal(back.state.q, claw.solution.state.q)
+    pback = pyclaw.Solution(3, path=claw.outdir_p, file_prefix='claw_p')
+    assert pback.state.q.shape[0] == 1 and np.array_equal(pback.state.q[0], claw.solution.state.q[0] ** 2)
+    rows = [list(map(float, ln.split())) for ln in open(claw.F_path)]
+    assert len(rows) == 4 and rows[0][0] == 0.0
+    assert abs(rows[-1][1] - np.sum(np.abs(claw.solution.state.q[0])) * np.prod(claw.solution.state.grid.delta)) < 1e-14
+    # restart from frame 1 and run to the same tfinal: same final state as the uninterrupted run
+    mid = pyclaw.Solution(1, path=claw.outdir)
+    claw2 = S.make_claw(sc, kernel_language='Fortran', fmod=OracleFmod())
+    claw2.solution.state.q[...] = mid.state.q
+    claw2.solution.state.t = claw.frames[1].t                      # the .t header keeps 8 digits; use the exact time
+    claw2.num_output_times = 2
+    claw2.solver.dt_initial = [s for s in claw.solver.step_log][0][0]
+    claw2.run()
+    assert abs(claw2.solution.t - sc['tfinal']) < 1e-12
+    assert np.max(np.abs(claw2.solution.state.q - claw.solution.state.q)) < 1e-12
+    claw3 = S.make_claw(sc, kernel_language='Fortran', fmod=OracleFmod())
+    claw3.output_format = 'binary'
+    claw3.outdir = claw.outdir
+    claw3.overwrite = False
+    with pytest.raises(Exception, match='Refusing to overwrite'):
+        claw3.run()
