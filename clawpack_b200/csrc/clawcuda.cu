@@ -452,7 +452,7 @@ int launch_step(claw_solver* h, const double* delta, double dt, const double* sr
 // aux planes read by the 2-D Riemann solvers (rp2.cuh: none; rp2_aux.cuh: RP::MAUX); -1 = unknown id
 int rp2_aux_planes(int rp_id) {
   switch (rp_id) {
-    case 1: case 2: case 3: case 4: case 9: case 11: case 12: case 16: return 0;
+    case 1: case 2: case 3: case 4: case 9: case 11: case 12: case 16: case 18: return 0;
     case 7: return 2;      // vc_acoustics_2D: density, sound speed
     case 8: return 2;      // vc_advection_2D: edge velocities
     case 10: return 4;     // psystem_2D: density, modulus, stress-strain relation id, strain
@@ -474,7 +474,7 @@ int validate_config(claw_solver* h) {
       return fail(h, 31, "capacity functions are only implemented for the aux-reading 2-D solvers (rp_id %d reads none)", h->rp_id);
     if (need_aux == 0 && h->use_fwave)
       return fail(h, 32, "rp_id %d is not an f-wave solver", h->rp_id);
-    if ((h->rp_id == 11 || h->rp_id == 12 || h->rp_id == 14) && h->method[2] > 0)
+    if ((h->rp_id == 11 || h->rp_id == 12 || h->rp_id == 14 || h->rp_id == 18) && h->method[2] > 0)
       return fail(h, 36, "rp_id %d has no usable transverse Riemann solver (rpt2_dummy.f90; rpt2_shallow_bathymetry_fwave "
                          "reads an unassigned value): transverse_waves must be 0 or the step dimensionally split", h->rp_id);
     if (h->method[1] != 1 && h->method[1] != 2) return fail(h, 33, "order must be 1 or 2 (got %d)", h->method[1]);
@@ -529,10 +529,10 @@ int claw_create(claw_solver** out, int ndim, int rp_id, int meqn, int mwaves, in
   if (num_ghost != 2) return fail(nullptr, 3, "claw_create: num_ghost must be 2 (classic solvers), got %d", num_ghost);
   if (meqn < 1 || meqn > 8 || mwaves < 1 || mwaves > 8 || maux < 0)
     return fail(nullptr, 4, "claw_create: bad sizes meqn=%d mwaves=%d maux=%d", meqn, mwaves, maux);
-  static const int k_meqn[] = {0, 1, 3, 4, 3, 4, 5, 3, 1, 5, 3, 4, 3, 3, 3, 1, 1, 1},
-                   k_mwaves[] = {0, 1, 2, 4, 3, 2, 3, 2, 1, 5, 2, 2, 2, 2, 3, 1, 1, 1},
-                   k_ndim[] = {0, 2, 2, 2, 2, 3, 3, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 3};
-  if (rp_id < 1 || rp_id > 17) return fail(nullptr, 5, "claw_create: unknown rp_id %d", rp_id);
+  static const int k_meqn[] = {0, 1, 3, 4, 3, 4, 5, 3, 1, 5, 3, 4, 3, 3, 3, 1, 1, 1, 1},
+                   k_mwaves[] = {0, 1, 2, 4, 3, 2, 3, 2, 1, 5, 2, 2, 2, 2, 3, 1, 1, 1, 1},
+                   k_ndim[] = {0, 2, 2, 2, 2, 3, 3, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 3, 2};
+  if (rp_id < 1 || rp_id > 18) return fail(nullptr, 5, "claw_create: unknown rp_id %d", rp_id);
   if (k_meqn[rp_id] != meqn || k_mwaves[rp_id] != mwaves || k_ndim[rp_id] != ndim)
     return fail(nullptr, 6, "claw_create: rp_id %d expects ndim=%d meqn=%d mwaves=%d (got %d, %d, %d)", rp_id,
                 k_ndim[rp_id], k_meqn[rp_id], k_mwaves[rp_id], ndim, meqn, mwaves);

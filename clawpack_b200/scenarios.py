@@ -582,6 +582,18 @@ def euler_3d_shock_bubble(q0, consts, tfinal=0.1, num_output_times=10, dimension
                  tfinal=tfinal, num_output_times=num_output_times)
 
 
+def kpp_2d(mx=200, my=200, tfinal=1.0, num_output_times=10):
+    """pyclaw/examples/kpp/kpp.py:18-55 (classic): q_t + sin(q)_x + cos(q)_y = 0, disc of 3.5 pi in a sea of pi/4,
+    dimensional splitting, minmod, extrapolation."""
+    X, Y = _grid((-2., -2.), (2., 2.), (mx, my))
+    r = np.sqrt(X ** 2 + Y ** 2)
+    q = np.empty((1, mx, my), order='F')
+    q[0] = 0.25 * np.pi + 3.25 * np.pi * (r <= 1.0)
+    return _base('kpp_2D', (-2., -2.), (2., 2.), (mx, my), q, limiters=MINMOD, dimensional_split=True,
+                 cfl_max=1.0, cfl_desired=0.9, bc_lower=[EXTRAP, EXTRAP], bc_upper=[EXTRAP, EXTRAP], tfinal=tfinal,
+                 num_output_times=num_output_times)
+
+
 # ---- 1-D (ClawSolver1D / step1.f90) ------------------------------------------------------------------
 def advection_1d(nx=400, tfinal=1.0):
     """pyclaw/examples/advection_1d/advection_1d.py:30-78 (Fortran classic): Gaussian pulse, periodic."""

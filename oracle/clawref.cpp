@@ -35,6 +35,7 @@ inline bool operator<(Counted a, Counted b) { ++g_tally.cmp; return a.v < b.v; }
 inline bool operator>=(Counted a, Counted b) { ++g_tally.cmp; return a.v >= b.v; }
 inline bool operator<=(Counted a, Counted b) { ++g_tally.cmp; return a.v <= b.v; }
 inline bool operator==(Counted a, Counted b) { ++g_tally.cmp; return a.v == b.v; }
+inline bool operator!=(Counted a, Counted b) { ++g_tally.cmp; return a.v != b.v; }
 inline Counted r_sqrt(Counted x) { ++g_tally.sqrt; return Counted(std::sqrt(x.v)); }
 inline Counted r_abs(Counted x) { ++g_tally.abs; return Counted(std::fabs(x.v)); }
 inline Counted r_max(Counted a, Counted b) { ++g_tally.cmp; return (b.v > a.v) ? b : a; }
@@ -42,6 +43,10 @@ inline Counted r_min(Counted a, Counted b) { ++g_tally.cmp; return (b.v < a.v) ?
 inline Counted r_sign1(Counted s) { return Counted(std::copysign(1.0, s.v)); }
 inline Counted r_exp(Counted x) { ++g_tally.sqrt; return Counted(std::exp(x.v)); }     // tallied with the square roots
 inline int r_nint(Counted x) { return (int)std::lround(x.v); }
+inline Counted r_sin(Counted x) { ++g_tally.sqrt; return Counted(std::sin(x.v)); }     // library calls: tallied with the square roots
+inline Counted r_cos(Counted x) { ++g_tally.sqrt; return Counted(std::cos(x.v)); }
+inline Counted r_atan(Counted x) { return Counted(std::atan(x.v)); }
+inline Counted r_mod(Counted a, Counted p) { ++g_tally.div; return Counted(std::fmod(a.v, p.v)); }
 
 }  // namespace clawref
 
@@ -169,6 +174,28 @@ int clawref_rp1(int num_eqn, int num_waves, int num_ghost, int num_aux, int mx, 
   V2<double> Q{q, num_eqn, lo}, A{aux, na, lo}, S{s, num_waves, lo}, AM{amdq, num_eqn, lo}, AP{apdq, num_eqn, lo};
   V3<double> W{wave, num_eqn, num_waves, lo};
   rp(mx, num_eqn, num_waves, num_aux, num_ghost, mx, Q, Q, A, A, W, S, AM, AP, cparam);
+  return 0;
+}
+
+// One rpn2 call followed by rpt2 on its two fluctuations (imp = 1 on amdq, imp = 2 on apdq) on a pencil of
+// n = mx + 2*num_ghost cells of a solver WITHOUT aux: q(num_eqn, n) in the natural component order; outputs in the
+// Fortran layouts with interface slot k between cells k-1 and k.  rpt2 is skipped for solvers with rpt2_dummy.
+// Used by tests/test_host_functors.py.
+int clawref_rp2(int ixy, int num_eqn, int num_waves, int num_ghost, int mx, double* q, double* wave, double* s,
+                double* amdq, double* apdq, double* bm_a, double* bp_a, double* bm_b, double* bp_b, int rp_id,
+                const double* cparam) {
+  Rpn2<double> rpn; Rpt2<double> rpt;
+  if (!select_rp2<double>(rp_id, rpn, rpt)) return 1;
+  const int lo = 1 - num_ghost;
+  std::vector<double> dummy((size_t)(mx + 2 * num_ghost), 0.0);
+  V2<double> Q{q, num_eqn, lo}, A{dummy.data(), 1, lo}, S{s, num_waves, lo}, AM{amdq, num_eqn, lo}, AP{apdq, num_eqn, lo};
+  V3<double> W{wave, num_eqn, num_waves, lo};
+  rpn(ixy, mx, num_eqn, num_waves, 0, num_ghost, mx, Q, Q, A, A, W, S, AM, AP, cparam);
+  if (rpt == rpt2_dummy<double>) return 0;
+  rpt(ixy, 1, mx, num_eqn, num_waves, 0, num_ghost, mx, Q, Q, A, A, A, AM, V2<double>{bm_a, num_eqn, lo},
+      V2<double>{bp_a, num_eqn, lo}, cparam);
+  rpt(ixy, 2, mx, num_eqn, num_waves, 0, num_ghost, mx, Q, Q, A, A, A, AP, V2<double>{bm_b, num_eqn, lo},
+      V2<double>{bp_b, num_eqn, lo}, cparam);
   return 0;
 }
 

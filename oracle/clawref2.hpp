@@ -42,6 +42,10 @@ inline double r_max(double a, double b) { return (b > a) ? b : a; }
 inline double r_min(double a, double b) { return (b < a) ? b : a; }
 inline double r_sign1(double s) { return std::copysign(1.0, s); }  // dsign(1.d0,s)
 inline double r_exp(double x) { return std::exp(x); }               // dexp
+inline double r_sin(double x) { return std::sin(x); }               // dsin
+inline double r_cos(double x) { return std::cos(x); }               // dcos
+inline double r_atan(double x) { return std::atan(x); }             // datan
+inline double r_mod(double a, double p) { return std::fmod(a, p); } // dmod: a - int(a/p)*p, sign of a
 inline int r_nint(double x) { return (int)std::lround(x); }         // nint: nearest, halves away from zero
 
 template <class R> inline R r_max3(R a, R b, R c) { return r_max(r_max(a, b), c); }
@@ -75,6 +79,7 @@ enum RpId {
   RP_PSYSTEM_2D = 10,
   RP_EULER_HLLE_2D = 11,
   RP_SHALLOW_HLLE_2D = 12,
+  RP_KPP_2D = 18,
   RP_ACOUSTICS_MAPPED_2D = 13,
   RP_SHALLOW_BATHYMETRY_FWAVE_2D = 14,
   RP_BURGERS_2D = 16,                // (15 = burgers_3D, clawref3.hpp)
@@ -1101,6 +1106,64 @@ void rpt2_burgers(int, int, int, int, int, int, int mbc, int mx, V2<R> ql, V2<R>
   }
 }
 
+// ---------------------------------------------------------------------
+// kpp_2D -- riemann/src/rpn2_kpp.f90:25-139 (+ rpt2_dummy.f90): q_t + sin(q)_x + cos(q)_y = 0, non-convex flux; the
+// Godunov flux `fedge` is the minimum (ul < ur) or maximum of the flux over [ul, ur], found from where the interval sits
+// relative to the extrema of sin / cos.
+// ---------------------------------------------------------------------
+template <class R>
+void rpn2_kpp(int ixy, int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V2<R>, V3<R> wave, V2<R> s,
+              V2<R> amdq, V2<R> apdq, const double*) {
+  const R pi = R(4.0) * r_atan(R(1.0));
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R ul = qr(1, i - 1), ur = ql(1, i);
+    R fl, fr, fedge;
+    if (ixy == 1) {
+      fl = r_sin(ul); fr = r_sin(ur);
+      if (ul < ur) {
+        fedge = r_min(fl, fr);
+        if (ur - ul > R(2.0) * pi) fedge = R(-1.0);
+        else {
+          R reml = r_mod(ul, R(2.0) * pi), remr = r_mod(ur, R(2.0) * pi);
+          if (remr > R(1.5) * pi && reml < R(1.5) * pi) fedge = R(-1.0);
+          else if (ur - ul > remr + R(0.5) * pi) fedge = R(-1.0);
+        }
+      } else {
+        fedge = r_max(fl, fr);
+        if (ul - ur > R(2.0) * pi) fedge = R(1.0);
+        else {
+          R reml = r_mod(ul, R(2.0) * pi), remr = r_mod(ur, R(2.0) * pi);
+          if (reml > R(0.5) * pi && remr < R(0.5) * pi) fedge = R(1.0);
+          else if (ul - ur > reml + R(1.5) * pi) fedge = R(1.0);
+        }
+      }
+    } else {
+      fl = r_cos(ul); fr = r_cos(ur);
+      if (ul < ur) {
+        fedge = r_min(fl, fr);
+        if (ur - ul > R(2.0) * pi) fedge = R(-1.0);
+        else {
+          R reml = r_mod(ul, R(2.0) * pi), remr = r_mod(ur, R(2.0) * pi);
+          if (remr > R(1.0) * pi && reml < R(1.0) * pi) fedge = R(-1.0);
+          else if (ur - ul > remr + R(1.0) * pi) fedge = R(-1.0);
+        }
+      } else {
+        fedge = r_max(fl, fr);
+        if (ul - ur > R(2.0) * pi) fedge = R(1.0);
+        else {
+          R reml = r_mod(ul, R(2.0) * pi), remr = r_mod(ur, R(2.0) * pi);
+          if (reml < remr) fedge = R(1.0);
+        }
+      }
+    }
+    if (ul != ur) s(1, i) = (fr - fl) / (ur - ul);
+    else s(1, i) = R(0.0);
+    wave(1, 1, i) = ur - ul;
+    amdq(1, i) = fedge - fl;
+    apdq(1, i) = fr - fedge;
+  }
+}
+
 template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt) {
   switch (rp_id) {
     case RP_ADVECTION_2D: rpn = rpn2_advection<R>; rpt = rpt2_advection<R>; return true;
@@ -1116,6 +1179,7 @@ template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt)
     case RP_ACOUSTICS_MAPPED_2D: rpn = rpn2_acoustics_mapped<R>; rpt = rpt2_acoustics_mapped<R>; return true;
     case RP_SHALLOW_BATHYMETRY_FWAVE_2D: rpn = rpn2_shallow_bathymetry_fwave<R>; rpt = rpt2_dummy<R>; return true;
     case RP_BURGERS_2D: rpn = rpn2_burgers<R>; rpt = rpt2_burgers<R>; return true;
+    case RP_KPP_2D: rpn = rpn2_kpp<R>; rpt = rpt2_dummy<R>; return true;
   }
   return false;
 }
@@ -1317,7 +1381,7 @@ int step2(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int 
   Rpn2<R> rpn2; Rpt2<R> rpt2;
   if (!select_rp2<R>(rp_id, rpn2, rpt2)) return 1;
   // rpt2_dummy.f90 ("Error: Dummy transverse Riemann solver called!") leaves its outputs unset: refuse instead
-  if ((rp_id == RP_EULER_HLLE_2D || rp_id == RP_SHALLOW_HLLE_2D || rp_id == RP_SHALLOW_BATHYMETRY_FWAVE_2D) && method[2] > 0)
+  if ((rp_id == RP_EULER_HLLE_2D || rp_id == RP_SHALLOW_HLLE_2D || rp_id == RP_SHALLOW_BATHYMETRY_FWAVE_2D || rp_id == RP_KPP_2D) && method[2] > 0)
     return 2;
   if (maxm < mx || maxm < my) return 2;
   const int nx = mx + 2 * num_ghost;

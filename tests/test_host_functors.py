@@ -122,3 +122,85 @@ def test_nonlinear_elasticity_exponential_relation_within_roundoff(hostlib):
     amd, apd = np.zeros((2, n - 1), order='F'), np.zeros((2, n - 1), order='F')
     assert L.hostfun_rp1(rp_id, _dp(cp), 0, n - 1, 3, _dp(q), _dp(aux), _dp(wd), _dp(sd), _dp(amd), _dp(apd)) == 0
     assert np.array_equal(wd, wo[..., 1:]) and np.array_equal(sd, so[:, 1:])
+
+
+# ---- 2-D solvers without aux (csrc/rp2.cuh): normal() + both transverse() solves per interface ---------------------
+SRC2 = os.path.join(HERE, 'host_functors', 'rp2_host.cpp')
+NO_RPT2 = ('euler_hlle_2D', 'shallow_hlle_2D', 'kpp_2D')           # rpt2_dummy.f90
+
+
+@pytest.fixture(scope='module')
+def hostlib2(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp('hostfun2') / 'librp2_host.so')
+    subprocess.run([CXX, '-O2', '-ffp-contract=off', '-std=c++17', '-fPIC', '-shared', '-Wno-unknown-pragmas',
+                    '-o', out, SRC2], check=True)
+    L = ctypes.CDLL(out)
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.hostfun_rp2.argtypes = [ctypes.c_int, ctypes.c_int, dp, ctypes.c_int, ctypes.c_int] + [dp] * 9
+    L.hostfun_rp2.restype = ctypes.c_int
+    R = pyclaw_ref.lib()
+    R.clawref_rp2.argtypes = [ctypes.c_int] * 5 + [dp] * 9 + [ctypes.c_int, dp]
+    R.clawref_rp2.restype = ctypes.c_int
+    return L, R
+
+
+def _pencils2(name, rng, n):
+    cp = []
+    if name == 'advection_2D':
+        q = rng.standard_normal((1, n)); cp = [0.5, -1.0]
+    elif name == 'acoustics_2D':
+        q = rng.standard_normal((3, n)); cp = [1.3, 2.9, np.sqrt(2.9 / 1.3), 1.3 * np.sqrt(2.9 / 1.3)]
+    elif name == 'burgers_2D':
+        q = rng.standard_normal((1, n)) * 2
+    elif name == 'kpp_2D':
+        q = rng.uniform(-3 * np.pi, 5 * np.pi, (1, n))
+        q[0, ::7] = 0.25 * np.pi; q[0, 1::7] = 3.5 * np.pi       # the states of the reference example
+    elif name in ('shallow_roe_with_efix_2D', 'shallow_hlle_2D'):
+        h = rng.uniform(0.05, 3.0, n); u = rng.standard_normal(n) * 2; v = rng.standard_normal(n) * 2
+        q = np.stack([h, h * u, h * v]); cp = [9.81]
+    elif name in ('euler_4wave_2D', 'euler_5wave_2D', 'euler_hlle_2D'):
+        rho = rng.uniform(0.1, 3.0, n); u = rng.standard_normal(n) * 2; v = rng.standard_normal(n) * 2
+        p = rng.uniform(0.1, 5.0, n)
+        if name == 'euler_hlle_2D':      # rpn2_euler_hlle.f90:60-63 (H_r with p_l, c^2 = gamma1*H - u^2/2): keep the roots real
+            rho = rng.uniform(0.8, 1.2, n); p = rng.uniform(1.0, 1.3, n)
+            u = rng.uniform(-1.0, 1.0, n); v = rng.uniform(-1.0, 1.0, n)
+        rows = [rho, rho * u, rho * v, p / 0.4 + 0.5 * rho * (u * u + v * v)]
+        if name == 'euler_5wave_2D':
+            rows.append(rho * rng.uniform(0, 1, n))
+        q = np.stack(rows); cp = [1.4]
+    else:
+        raise KeyError(name)
+    q[:, n // 2: n // 2 + 8] = q[:, n // 2: n // 2 + 1]
+    return np.asfortranarray(q), np.array(cp + [0.0])
+
+
+NAMES_2D = ['advection_2D', 'acoustics_2D', 'burgers_2D', 'kpp_2D', 'shallow_roe_with_efix_2D', 'shallow_hlle_2D',
+            'euler_4wave_2D', 'euler_5wave_2D', 'euler_hlle_2D']
+
+
+@pytest.mark.parametrize('ixy', [1, 2])
+@pytest.mark.parametrize('name', NAMES_2D)
+def test_device_functor_source_matches_oracle_rp2(hostlib2, name, ixy):
+    L, R = hostlib2
+    rp_id = pyclaw_ref.RP_IDS[name]
+    M, W = pyclaw_ref.NUM_EQN[name], pyclaw_ref.NUM_WAVES[name]
+    rng = np.random.default_rng(4321 + 10 * rp_id + ixy)
+    mx, g = 4093, 2
+    n = mx + 2 * g
+    q, cp = _pencils2(name, rng, n)
+    z = lambda *shape: np.zeros(shape, order='F')
+    wo, so, amo, apo = z(M, W, n), z(W, n), z(M, n), z(M, n)
+    bo = [z(M, n) for _ in range(4)]
+    assert R.clawref_rp2(ixy, M, W, g, mx, _dp(q), _dp(wo), _dp(so), _dp(amo), _dp(apo), *[_dp(b) for b in bo],
+                         rp_id, _dp(cp)) == 0
+    wd, sd, amd, apd = z(M, W, n - 1), z(W, n - 1), z(M, n - 1), z(M, n - 1)
+    bd = [z(M, n - 1) for _ in range(4)]
+    assert L.hostfun_rp2(rp_id, ixy - 1, _dp(cp), len(cp) - 1, n - 1, _dp(q), _dp(wd), _dp(sd), _dp(amd), _dp(apd),
+                         *[_dp(b) for b in bd]) == 0
+    pairs = [(wd, wo[..., 1:], 'wave'), (sd, so[:, 1:], 's'), (amd, amo[:, 1:], 'amdq'), (apd, apo[:, 1:], 'apdq')]
+    if name not in NO_RPT2:
+        pairs += [(bd[k], bo[k][:, 1:], what) for k, what in enumerate(('bmasdq(amdq)', 'bpasdq(amdq)', 'bmasdq(apdq)',
+                                                                        'bpasdq(apdq)'))]
+    for a, b, what in pairs:
+        assert np.isfinite(b).all(), (name, what)
+        assert np.array_equal(a, b), (name, ixy, what, float(np.max(np.abs(a - b))))

@@ -339,6 +339,22 @@ def test_step1_unpinned_solvers_sanity(oracle_lib):
     assert abs(np.sum(s.q[0] / K) - np.sum(sc['q'][0] / K)) < 1e-11
 
 
+def test_kpp_2d_properties(oracle_lib):
+    # pyclaw/examples/kpp/kpp.py has no stored vector (parity unpinned by the reference): the restated rpn2_kpp is held
+    # to the properties of the entropy solution -- maximum principle (pi/4 <= q <= 3.5 pi up to limiter overshoot of
+    # round-off size) and conservation while the far field is undisturbed (equal fluxes in and out of the domain)
+    sc = S.kpp_2d(mx=80, my=80, tfinal=0.5, num_output_times=5)
+    s = ref_solver(sc, nthreads=4)
+    s.run(sc['tfinal'], sc['num_output_times'])
+    q = s.q[0]
+    assert np.isfinite(q).all()
+    assert q.min() >= 0.25 * np.pi - 1e-12 and q.max() <= 3.5 * np.pi + 1e-12
+    assert abs(np.sum(q) - np.sum(sc['q'][0])) < 1e-9 * np.sum(sc['q'][0])
+    assert all(acc for _, _, acc in s.step_log[1:])
+    # the solution has rotated (the characteristic KPP spiral): it is no longer radially symmetric
+    assert np.max(np.abs(q - q[::-1, :])) > 1.0
+
+
 def test_acoustics_2d_mapped_golden(oracle_lib):
     # pyclaw/examples/acoustics_2d_mapped/test_acoustics_2d_mapped.py:6-21 (max-abs < 1e-7 against pressure.npz, 100x100,
     # t = 0.9): pins rpn2/rpt2_acoustics_mapped (edge normals, length ratios, transverse geometry read at cell i for

@@ -1,4 +1,4 @@
-"""GPU parity tests of the 1-D solvers added after the first batch (rp_id 26..33: traffic, advection_color,
+"""GPU parity tests of the solvers added after the first batch: kpp_2D (rp_id 18, at the end of the file) and the 1-D solvers (rp_id 26..33: traffic, advection_color,
 acoustics_variable, shallow_bathymetry_fwave, euler_with_efix, euler_hlle, nonlinear_elasticity_fwave, cubic) through
 claw_step1_host behind ClawSolver1D: bit-exact against the oracle in strict mode, within the north_star tolerance in
 fast mode, and against the reference's stored vectors through Controller.run().  The functor arithmetic itself is also
@@ -94,3 +94,36 @@ def test_aux_solver_without_aux_is_refused():
     rc = L.claw_step1_host(1, 1, 0, 2, 10, q.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(0), 0.1, 0.01,
                            _lib.ip(method), _lib.ip(mth), 0, 27, _lib.dp(np.zeros(1)), 0, 0, ctypes.byref(cfl))
     assert rc == 7
+
+
+# ---- kpp_2D (rp_id 18; rpn2_kpp.f90 + rpt2_dummy.f90) ---------------------------------------------------------------
+KPP_CASES = {
+    'kpp_split': lambda: S.kpp_2d(mx=120, my=90),
+    'kpp_unsplit_notrans': lambda: dict(S.kpp_2d(mx=64, my=50), dimensional_split=False, transverse_waves=0,
+                                        cfl_max=0.5, cfl_desired=0.45),
+    'kpp_superbee_first_order_mix': lambda: dict(S.kpp_2d(mx=33, my=61), limiters=S.SUPERBEE),
+}
+
+
+@pytest.mark.parametrize('precision', ['strict', 'fast'])
+@pytest.mark.parametrize('name', sorted(KPP_CASES))
+def test_kpp_2d_within_tolerance(name, precision):
+    """sin() / cos() are library calls whose last bit may differ between CUDA and the host library, so kpp_2D is held to
+    the north_star tolerance in both arithmetic modes (1e-12 after one step, 1e-10 after 100) with identical
+    accept/reject sequences; every branch of the solver depends only on fmod(), which is exact on both sides."""
+    sc = KPP_CASES[name]()
+    for nsteps, tol in ((1, 1e-12), (100, 1e-10)):
+        qr, logr = _run_ref(sc, nsteps)
+        q, log, _ = _run_cuda(sc, nsteps, precision)
+        assert [s[2] for s in log] == [s[2] for s in logr]
+        assert np.allclose([s[0] for s in log], [s[0] for s in logr], rtol=1e-12, atol=0)
+        assert _rel_linf(q, qr) <= tol
+
+
+def test_kpp_2d_refuses_transverse_modes():
+    """rpt2_dummy.f90: no transverse solver -- the unsplit step with transverse_waves > 0 is refused (code 36)."""
+    from clawpack_b200._lib import ClawCudaError
+    sc = dict(S.kpp_2d(mx=20, my=20), dimensional_split=False, transverse_waves=2)
+    claw = S.make_claw(sc, kernel_language='CUDA')
+    with pytest.raises(ClawCudaError):
+        claw.run()
