@@ -41,7 +41,10 @@ template <class RP, int NW> struct Smem2ws {
   static constexpr size_t BYTES = (size_t)PER_THREAD * NW * 32 * sizeof(double) + 64 * sizeof(double);
 };
 
-template <class RP, int NW, int MINB = 1, int SPEC = 0>
+// UNR > 1 unrolls the march loop so that the row-to-row hand-over of the carried state (q1 <- qN, qn0 <- qn1 <- qn2,
+// c1 <- cN) becomes register renaming instead of moves: statically (scripts/sass_mix.py) 1476 -> 1430 instructions per
+// march step for the headline Euler kernel at UNR = 2 with no spills (UNR = 3 spills); unmeasured on the GPU so far.
+template <class RP, int NW, int MINB = 1, int SPEC = 0, int UNR = 1>
 __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_constant__ Sweep2Params P) {
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE, NT = NW * 32;
   constexpr bool SP = (SPEC & 1) != 0;
@@ -95,6 +98,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
   }
 
   // warm-up rows: see sweep2_unsplit (the specialised kernel runs the full body from the first step)
+#pragma unroll UNR
   for (int J = Jb - 3; J < Je; ++J) {
     double qN[M];
     if constexpr (PF == 3) {

@@ -64,10 +64,10 @@ static cudaError_t launch_spec(Sweep2Params& P, int seg_hint, int num_sms, cudaS
 }
 
 // warp-synchronous unsplit kernel (sweep2_ws.cuh): NW independent 28-column strips per CTA
-template <class RP, int NW, int MINB, int SPEC>
+template <class RP, int NW, int MINB, int SPEC, int UNR = 1>
 static cudaError_t launch_ws(Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
   using S = Smem2ws<RP, NW>;
-  return launch_kernel(sweep2_unsplit_ws<RP, NW, MINB, SPEC>, NW * 32, (int)S::BYTES, false, P, seg_hint, num_sms, st,
+  return launch_kernel(sweep2_unsplit_ws<RP, NW, MINB, SPEC, UNR>, NW * 32, (int)S::BYTES, false, P, seg_hint, num_sms, st,
                        info, NW * 28);
 }
 
@@ -121,6 +121,7 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
           case 14: return launch_ws<RpEuler4Wave2D, 1, 8, MC | 1 | 6 | 8>(P, seg_hint, num_sms, st, info);   // branch-free limiter
           case 16: return launch_ws<RpEuler4Wave2DT<0, 1>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);  // branch-free efix
           case 40: return launch_wsp<RpEuler4Wave2DT<3>, 6, 4>(P, seg_hint, num_sms, st, info);   // warp pair per strip, 168 registers: 5.21 ms (profiles/r01_j)
+          case 50: return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6, 2>(P, seg_hint, num_sms, st, info);   // march loop unrolled x2 (round-2 experiment)
           case 15: return launch_spec<RpEuler4Wave2D, 64, 6, MC | 1>(P, seg_hint, num_sms, st, info);
           default: break;     // 9: the generic kernel
         }
