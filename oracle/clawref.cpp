@@ -199,6 +199,26 @@ int clawref_rp2(int ixy, int num_eqn, int num_waves, int num_ghost, int mx, doub
   return 0;
 }
 
+// The same for solvers that read aux: aux1 / aux2 / aux3 (num_aux, n) are the three pencils rpt2 sees (rows j-1, j, j+1
+// of an x-sweep); rpn2 gets aux2.  with_rpt = 0 skips the transverse solves.
+int clawref_rp2_aux(int ixy, int num_eqn, int num_waves, int num_aux, int num_ghost, int mx, double* q, double* aux1,
+                    double* aux2, double* aux3, double* wave, double* s, double* amdq, double* apdq, double* bm_a,
+                    double* bp_a, double* bm_b, double* bp_b, int rp_id, const double* cparam, int with_rpt) {
+  Rpn2<double> rpn; Rpt2<double> rpt;
+  if (!select_rp2<double>(rp_id, rpn, rpt)) return 1;
+  const int lo = 1 - num_ghost;
+  V2<double> Q{q, num_eqn, lo}, A1{aux1, num_aux, lo}, A2{aux2, num_aux, lo}, A3{aux3, num_aux, lo}, S{s, num_waves, lo},
+      AM{amdq, num_eqn, lo}, AP{apdq, num_eqn, lo};
+  V3<double> W{wave, num_eqn, num_waves, lo};
+  rpn(ixy, mx, num_eqn, num_waves, num_aux, num_ghost, mx, Q, Q, A2, A2, W, S, AM, AP, cparam);
+  if (!with_rpt || rpt == rpt2_dummy<double>) return 0;
+  rpt(ixy, 1, mx, num_eqn, num_waves, num_aux, num_ghost, mx, Q, Q, A1, A2, A3, AM, V2<double>{bm_a, num_eqn, lo},
+      V2<double>{bp_a, num_eqn, lo}, cparam);
+  rpt(ixy, 2, mx, num_eqn, num_waves, num_aux, num_ghost, mx, Q, Q, A1, A2, A3, AP, V2<double>{bm_b, num_eqn, lo},
+      V2<double>{bp_b, num_eqn, lo}, cparam);
+  return 0;
+}
+
 int clawref_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

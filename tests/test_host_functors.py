@@ -204,3 +204,91 @@ def test_device_functor_source_matches_oracle_rp2(hostlib2, name, ixy):
     for a, b, what in pairs:
         assert np.isfinite(b).all(), (name, what)
         assert np.array_equal(a, b), (name, ixy, what, float(np.max(np.abs(a - b))))
+
+
+# ---- 2-D solvers that read aux (csrc/rp2_aux.cuh) ------------------------------------------------------------------
+SRC2A = os.path.join(HERE, 'host_functors', 'rp2_aux_host.cpp')
+
+
+@pytest.fixture(scope='module')
+def hostlib2a(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp('hostfun2a') / 'librp2_aux_host.so')
+    subprocess.run([CXX, '-O2', '-ffp-contract=off', '-std=c++17', '-fPIC', '-shared', '-Wno-unknown-pragmas',
+                    '-o', out, SRC2A], check=True)
+    L = ctypes.CDLL(out)
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.hostfun_rp2_aux.argtypes = [ctypes.c_int, ctypes.c_int, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [dp] * 12 + [ctypes.c_int]
+    L.hostfun_rp2_aux.restype = ctypes.c_int
+    R = pyclaw_ref.lib()
+    R.clawref_rp2_aux.argtypes = [ctypes.c_int] * 6 + [dp] * 12 + [ctypes.c_int, dp, ctypes.c_int]
+    R.clawref_rp2_aux.restype = ctypes.c_int
+    return L, R
+
+
+def _pencils2a(name, rng, n):
+    """q(meqn, n) and three aux pencils (rows j-1, j, j+1) with admissible coefficients."""
+    cp = []
+
+    def three(make):
+        return [np.asfortranarray(make()) for _ in range(3)]
+
+    if name == 'vc_acoustics_2D':
+        q = rng.standard_normal((3, n))
+        aux = three(lambda: np.stack([rng.uniform(0.5, 4.0, n), rng.uniform(0.5, 3.0, n)]))
+    elif name == 'vc_advection_2D':
+        q = rng.standard_normal((1, n))
+        aux = three(lambda: rng.standard_normal((2, n)))
+    elif name == 'psystem_2D':
+        q = np.stack([rng.uniform(-0.2, 0.5, n), rng.standard_normal(n), rng.standard_normal(n)])
+        aux = three(lambda: np.stack([rng.uniform(1.0, 4.0, n), rng.uniform(1.0, 4.0, n),
+                                      rng.choice([1.0, 2.0, 3.0], n), rng.uniform(-0.2, 0.5, n)]))
+    elif name == 'acoustics_mapped_2D':
+        q = rng.standard_normal((3, n))
+
+        def geom():
+            th1, th2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+            return np.stack([np.cos(th1), np.sin(th1), rng.uniform(0.5, 1.5, n), np.cos(th2), np.sin(th2),
+                             rng.uniform(0.5, 1.5, n), rng.uniform(0.5, 1.5, n), rng.uniform(0.5, 4.0, n),
+                             rng.uniform(0.5, 3.0, n)])
+        aux = three(geom)
+    elif name == 'shallow_bathymetry_fwave_2D':
+        h = rng.uniform(0.01, 2.0, n); h[::5] = 5e-4      # isolated dry cells (two adjacent ones give 0/0 in the reference, :77)
+        q = np.stack([h, h * rng.standard_normal(n), h * rng.standard_normal(n)])
+        aux = three(lambda: rng.uniform(-1.0, 0.0, (1, n)))
+        cp = [9.8, 1e-3, 0.0]
+    else:
+        raise KeyError(name)
+    return np.asfortranarray(q), aux, np.array(cp + [0.0])
+
+
+NAMES_2D_AUX = ['vc_acoustics_2D', 'vc_advection_2D', 'psystem_2D', 'acoustics_mapped_2D', 'shallow_bathymetry_fwave_2D']
+
+
+@pytest.mark.parametrize('ixy', [1, 2])
+@pytest.mark.parametrize('name', NAMES_2D_AUX)
+def test_device_aux_functor_source_matches_oracle_rp2(hostlib2a, name, ixy):
+    L, R = hostlib2a
+    rp_id = pyclaw_ref.RP_IDS[name]
+    M, W = pyclaw_ref.NUM_EQN[name], pyclaw_ref.NUM_WAVES[name]
+    rng = np.random.default_rng(999 + 10 * rp_id + ixy)
+    mx, g = 2045, 2
+    n = mx + 2 * g
+    q, aux, cp = _pencils2a(name, rng, n)
+    maux = aux[0].shape[0]
+    with_rpt = 0 if name == 'shallow_bathymetry_fwave_2D' else 1       # its rpt2 reads an unassigned value: refused
+    z = lambda *shape: np.zeros(shape, order='F')
+    wo, so, amo, apo = z(M, W, n), z(W, n), z(M, n), z(M, n)
+    bo = [z(M, n) for _ in range(4)]
+    assert R.clawref_rp2_aux(ixy, M, W, maux, g, mx, _dp(q), _dp(aux[0]), _dp(aux[1]), _dp(aux[2]), _dp(wo), _dp(so),
+                             _dp(amo), _dp(apo), *[_dp(b) for b in bo], rp_id, _dp(cp), with_rpt) == 0
+    wd, sd, amd, apd = z(M, W, n - 1), z(W, n - 1), z(M, n - 1), z(M, n - 1)
+    bd = [z(M, n - 1) for _ in range(4)]
+    assert L.hostfun_rp2_aux(rp_id, ixy - 1, _dp(cp), len(cp) - 1, n - 1, maux, _dp(q), _dp(aux[0]), _dp(aux[1]),
+                             _dp(aux[2]), _dp(wd), _dp(sd), _dp(amd), _dp(apd), *[_dp(b) for b in bd], with_rpt) == 0
+    pairs = [(wd, wo[..., 1:], 'wave'), (sd, so[:, 1:], 's'), (amd, amo[:, 1:], 'amdq'), (apd, apo[:, 1:], 'apdq')]
+    if with_rpt:
+        pairs += [(bd[k], bo[k][:, 1:], what) for k, what in enumerate(('bmasdq(amdq)', 'bpasdq(amdq)', 'bmasdq(apdq)',
+                                                                        'bpasdq(apdq)'))]
+    for a, b, what in pairs:
+        assert np.isfinite(b).all(), (name, what)
+        assert np.array_equal(a, b), (name, ixy, what, float(np.max(np.abs(a - b))))
