@@ -458,6 +458,7 @@ int rp2_aux_planes(int rp_id) {
     case 10: return 4;     // psystem_2D: density, modulus, stress-strain relation id, strain
     case 13: return 9;     // acoustics_mapped_2D: edge normals + length ratios, capacity, impedance, sound speed
     case 14: return 1;     // shallow_bathymetry_fwave_2D: bathymetry
+    case 19: return 5;     // vc_elasticity_2D: density, lambda, mu, cp, cs
   }
   return -1;
 }
@@ -529,10 +530,10 @@ int claw_create(claw_solver** out, int ndim, int rp_id, int meqn, int mwaves, in
   if (num_ghost != 2) return fail(nullptr, 3, "claw_create: num_ghost must be 2 (classic solvers), got %d", num_ghost);
   if (meqn < 1 || meqn > 8 || mwaves < 1 || mwaves > 8 || maux < 0)
     return fail(nullptr, 4, "claw_create: bad sizes meqn=%d mwaves=%d maux=%d", meqn, mwaves, maux);
-  static const int k_meqn[] = {0, 1, 3, 4, 3, 4, 5, 3, 1, 5, 3, 4, 3, 3, 3, 1, 1, 1, 1},
-                   k_mwaves[] = {0, 1, 2, 4, 3, 2, 3, 2, 1, 5, 2, 2, 2, 2, 3, 1, 1, 1, 1},
-                   k_ndim[] = {0, 2, 2, 2, 2, 3, 3, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 3, 2};
-  if (rp_id < 1 || rp_id > 18) return fail(nullptr, 5, "claw_create: unknown rp_id %d", rp_id);
+  static const int k_meqn[] = {0, 1, 3, 4, 3, 4, 5, 3, 1, 5, 3, 4, 3, 3, 3, 1, 1, 1, 1, 5},
+                   k_mwaves[] = {0, 1, 2, 4, 3, 2, 3, 2, 1, 5, 2, 2, 2, 2, 3, 1, 1, 1, 1, 4},
+                   k_ndim[] = {0, 2, 2, 2, 2, 3, 3, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 3, 2, 2};
+  if (rp_id < 1 || rp_id > 19) return fail(nullptr, 5, "claw_create: unknown rp_id %d", rp_id);
   if (k_meqn[rp_id] != meqn || k_mwaves[rp_id] != mwaves || k_ndim[rp_id] != ndim)
     return fail(nullptr, 6, "claw_create: rp_id %d expects ndim=%d meqn=%d mwaves=%d (got %d, %d, %d)", rp_id,
                 k_ndim[rp_id], k_meqn[rp_id], k_mwaves[rp_id], ndim, meqn, mwaves);

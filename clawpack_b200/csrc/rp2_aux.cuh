@@ -268,5 +268,91 @@ struct RpShallowBathymetryFwave2D {
   }
 };
 
+// ------------------------------------------------------------------------------------
+// vc_elasticity_2D -- riemann/src/rpn2_vc_elasticity.f90:60-183, rpt2_vc_elasticity.f90:50-176
+// q = (sigma11, sigma22, sigma12, u, v); aux = (density, lambda, mu, cp, cs).  4 waves: P-, P+, S-, S+ (not ordered
+// by speed).  roe = (cp_left, cp_right, cs_left, cs_right).
+// The reference swaps sigma11 <-> sigma22 and u <-> v for a y-sweep (ksig11/ksig22/ku/kv), which is not the swap of
+// components 2 and 3 the sweep kernels apply (rot<5>): the functor therefore addresses the NATURAL components through
+// their rotated slots -- natural component n sits in slot rot<5>(n) when dir = 1.
+// ------------------------------------------------------------------------------------
+struct RpVcElasticity2D {
+  static constexpr int MEQN = 5, MWAVES = 4, NROE = 4, NCELL = 0, MAUX = 5;
+  // slots of (sigma_nn, sigma_tt, sigma_12, u_n, u_t): n = sweep direction, t = transverse
+  __device__ __forceinline__ static void slots(int dir, int& knn, int& ktt, int& k12, int& kun, int& kut) {
+    if (dir == 0) { knn = 0; ktt = 1; k12 = 2; kun = 3; kut = 4; }
+    else          { knn = 2; ktt = 0; k12 = 1; kun = 4; kut = 3; }      // natural 1, 0, 2, 4, 3 through rot<5>
+  }
+  __device__ __forceinline__ static void normal(const RpParams& P, int dir, const double* ql, const double* qr,
+                                                const double* axl, const double* axr, double (*wave)[MEQN],
+                                                double* s, double* amdq, double* apdq, double* roe) {
+    int knn, ktt, k12, kun, kut;
+    slots(dir, knn, ktt, k12, kun, kut);
+    const double dsig11 = qr[knn] - ql[knn];
+    const double dsig12 = qr[k12] - ql[k12];
+    const double du = qr[kun] - ql[kun];
+    const double dv = qr[kut] - ql[kut];
+    const double alamr = axr[1], amur = axr[2];
+    const double bulkr = alamr + 2.0 * amur;
+    const double cpr = axr[3], csr = axr[4];
+    const double alaml = axl[1], amul = axl[2];
+    const double bulkl = alaml + 2.0 * amul;
+    const double cpl = axl[3], csl = axl[4];
+    const double det = bulkl * cpr + bulkr * cpl;
+    const double a1 = ddiv(cpr * dsig11 + bulkr * du, det);
+    const double a2 = ddiv(cpl * dsig11 - bulkl * du, det);
+    const double det2 = amul * csr + amur * csl;
+    double a3 = 0.0, a4 = 0.0;
+    if (det2 != 0.0) {
+      a3 = ddiv(csr * dsig12 + amur * dv, det2);
+      a4 = ddiv(csl * dsig12 - amul * dv, det2);
+    }
+#pragma unroll
+    for (int mw = 0; mw < MWAVES; ++mw)
+#pragma unroll
+      for (int m = 0; m < MEQN; ++m) wave[mw][m] = 0.0;
+    wave[0][knn] = a1 * bulkl; wave[0][ktt] = a1 * alaml; wave[0][kun] = a1 * cpl;  s[0] = -cpl;
+    wave[1][knn] = a2 * bulkr; wave[1][ktt] = a2 * alamr; wave[1][kun] = -a2 * cpr; s[1] = cpr;
+    wave[2][k12] = a3 * amul;  wave[2][kut] = a3 * csl;                             s[2] = -csl;
+    wave[3][k12] = a4 * amur;  wave[3][kut] = -a4 * csr;                            s[3] = csr;
+#pragma unroll
+    for (int m = 0; m < MEQN; ++m) {
+      amdq[m] = s[0] * wave[0][m] + s[2] * wave[2][m];
+      apdq[m] = s[1] * wave[1][m] + s[3] * wave[3][m];
+    }
+    roe[0] = cpl; roe[1] = cpr; roe[2] = csl; roe[3] = csr;
+  }
+  __device__ __forceinline__ static void speeds(const RpParams& P, int dir, const double* roe, double* s) {
+    s[0] = -roe[0]; s[1] = roe[1]; s[2] = -roe[2]; s[3] = roe[3];
+  }
+  __device__ __forceinline__ static void transverse(const RpParams& P, int dir, const double* roe, const double* ax1,
+                                                    const double* ax2, const double* ax3, const double*, const double*,
+                                                    const double*, const double* asdq, double* bm, double* bp) {
+    int knn, ktt, k12, kun, kut;
+    slots(dir, knn, ktt, k12, kun, kut);
+    const double dsig22 = asdq[ktt], dsig12 = asdq[k12], du = asdq[kun], dv = asdq[kut];
+    const double alamm = ax1[1], alam = ax2[1], alamp = ax3[1];
+    const double amum = ax1[2], amu = ax2[2], amup = ax3[2];
+    const double bulkm = alamm + 2.0 * amum, bulk = alam + 2.0 * amu, bulkp = alamp + 2.0 * amup;
+    const double cpm = ax1[3], cp = ax2[3], cpp = ax3[3];
+    const double csm = ax1[4], cs = ax2[4], csp = ax3[4];
+    const double a1 = ddiv(cp * dsig22 + bulk * dv, bulkm * cp + bulk * cpm);
+    const double a2 = ddiv(cp * dsig22 - bulk * dv, bulk * cpp + bulkp * cp);
+    const double det3 = -(amum * cs + amu * csm), det4 = -(amu * csp + amup * cs);
+    const double a3 = (det3 == 0.0) ? 0.0 : ddiv(cs * dsig12 + amu * du, det3);
+    const double a4 = (det4 == 0.0) ? 0.0 : ddiv(cs * dsig12 - amu * du, det4);
+    bm[knn] = -cpm * a1 * alamm;
+    bm[ktt] = -cpm * a1 * bulkm;
+    bm[k12] = -csm * a3 * (-amum);
+    bm[kun] = -csm * a3 * (-csm);
+    bm[kut] = -cpm * a1 * cpm;
+    bp[knn] = cpp * a2 * alamp;
+    bp[ktt] = cpp * a2 * bulkp;
+    bp[k12] = csp * a4 * (-amup);
+    bp[kun] = csp * a4 * csp;
+    bp[kut] = cpp * a2 * (-cpp);
+  }
+};
+
 }  // namespace CLAW_NS
 }  // namespace clawcuda

@@ -582,6 +582,32 @@ def euler_3d_shock_bubble(q0, consts, tfinal=0.1, num_output_times=10, dimension
                  tfinal=tfinal, num_output_times=num_output_times)
 
 
+def elasticity_2d(mx=80, my=80, tfinal=0.25, num_output_times=5, dimensional_split=False, transverse_waves=2,
+                  inclusion=True):
+    """vc_elasticity_2D (riemann/src/rpn2_vc_elasticity.f90, rpt2_vc_elasticity.f90; the reference ships no PyClaw
+    example for it): a compressional pulse sigma11 = sigma22 = exp(-150 r^2) in a unit square of (rho, lambda, mu) =
+    (1, 2, 1), optionally with a stiff, dense disc (4, 8, 4) off-centre that converts part of it into shear waves.
+    q = (sigma11, sigma22, sigma12, u, v); aux = (rho, lambda, mu, cp, cs); MC limiter, extrapolation."""
+    X, Y = _grid((0., 0.), (1., 1.), (mx, my))
+    q = np.zeros((5, mx, my), order='F')
+    r2 = (X - 0.5) ** 2 + (Y - 0.5) ** 2
+    q[0] = np.exp(-150.0 * r2)
+    q[1] = q[0]
+    inside = ((X - 0.72) ** 2 + (Y - 0.6) ** 2 <= 0.15 ** 2) if inclusion else np.zeros_like(X, dtype=bool)
+    rho = np.where(inside, 4.0, 1.0)
+    lam = np.where(inside, 8.0, 2.0)
+    mu = np.where(inside, 4.0, 1.0)
+    aux = np.empty((5, mx, my), order='F')
+    aux[0], aux[1], aux[2] = rho, lam, mu
+    aux[3] = np.sqrt((lam + 2.0 * mu) / rho)
+    aux[4] = np.sqrt(mu / rho)
+    return _base('vc_elasticity_2D', (0., 0.), (1., 1.), (mx, my), q, aux=aux, limiters=MC,
+                 dimensional_split=bool(dimensional_split), transverse_waves=int(transverse_waves),
+                 cfl_max=1.0, cfl_desired=0.9, dt_initial=0.5 / max(mx, my) / 2.0,
+                 bc_lower=[EXTRAP, EXTRAP], bc_upper=[EXTRAP, EXTRAP], aux_bc_lower=[EXTRAP, EXTRAP],
+                 aux_bc_upper=[EXTRAP, EXTRAP], tfinal=tfinal, num_output_times=num_output_times)
+
+
 def kpp_2d(mx=200, my=200, tfinal=1.0, num_output_times=10):
     """pyclaw/examples/kpp/kpp.py:18-55 (classic): q_t + sin(q)_x + cos(q)_y = 0, disc of 3.5 pi in a sea of pi/4,
     dimensional splitting, minmod, extrapolation."""

@@ -80,6 +80,7 @@ enum RpId {
   RP_EULER_HLLE_2D = 11,
   RP_SHALLOW_HLLE_2D = 12,
   RP_KPP_2D = 18,
+  RP_VC_ELASTICITY_2D = 19,
   RP_ACOUSTICS_MAPPED_2D = 13,
   RP_SHALLOW_BATHYMETRY_FWAVE_2D = 14,
   RP_BURGERS_2D = 16,                // (15 = burgers_3D, clawref3.hpp)
@@ -1164,6 +1165,86 @@ void rpn2_kpp(int ixy, int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, 
   }
 }
 
+// ---------------------------------------------------------------------
+// vc_elasticity_2D -- riemann/src/rpn2_vc_elasticity.f90:60-183, rpt2_vc_elasticity.f90:50-176
+// q = (sigma11, sigma22, sigma12, u, v); aux = (density, lambda, mu, cp, cs); 4 waves: the two P-waves, then the two
+// S-waves (not ordered by speed; the zero-speed fifth wave is not computed).  Where the Fortran STOPs on a zero
+// determinant ("det=0 in rpn2") the division simply yields non-finite values here.
+// ---------------------------------------------------------------------
+template <class R>
+void rpn2_vc_elasticity(int ixy, int, int meqn, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R> auxl, V2<R> auxr,
+                        V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double*) {
+  const int ksig11 = ixy == 1 ? 1 : 2, ksig22 = ixy == 1 ? 2 : 1, ku = ixy == 1 ? 4 : 5, kv = ixy == 1 ? 5 : 4;
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R dsig11 = ql(ksig11, i) - qr(ksig11, i - 1);
+    R dsig12 = ql(3, i) - qr(3, i - 1);
+    R du = ql(ku, i) - qr(ku, i - 1);
+    R dv = ql(kv, i) - qr(kv, i - 1);
+    R alamr = auxl(2, i), amur = auxl(3, i);
+    R bulkr = alamr + R(2.0) * amur;
+    R cpr = auxl(4, i), csr = auxl(5, i);
+    R alaml = auxr(2, i - 1), amul = auxr(3, i - 1);
+    R bulkl = alaml + R(2.0) * amul;
+    R cpl = auxr(4, i - 1), csl = auxr(5, i - 1);
+    R det = bulkl * cpr + bulkr * cpl;
+    R a1 = (cpr * dsig11 + bulkr * du) / det;
+    R a2 = (cpl * dsig11 - bulkl * du) / det;
+    det = amul * csr + amur * csl;
+    R a3, a4;
+    if (det == R(0.0)) { a3 = R(0.0); a4 = R(0.0); }          // no shear wave in a fluid
+    else {
+      a3 = (csr * dsig12 + amur * dv) / det;
+      a4 = (csl * dsig12 - amul * dv) / det;
+    }
+    wave(ksig11, 1, i) = a1 * bulkl; wave(ksig22, 1, i) = a1 * alaml; wave(3, 1, i) = R(0.0);
+    wave(ku, 1, i) = a1 * cpl;       wave(kv, 1, i) = R(0.0);         s(1, i) = -cpl;
+    wave(ksig11, 2, i) = a2 * bulkr; wave(ksig22, 2, i) = a2 * alamr; wave(3, 2, i) = R(0.0);
+    wave(ku, 2, i) = -a2 * cpr;      wave(kv, 2, i) = R(0.0);         s(2, i) = cpr;
+    wave(ksig11, 3, i) = R(0.0);     wave(ksig22, 3, i) = R(0.0);     wave(3, 3, i) = a3 * amul;
+    wave(ku, 3, i) = R(0.0);         wave(kv, 3, i) = a3 * csl;       s(3, i) = -csl;
+    wave(ksig11, 4, i) = R(0.0);     wave(ksig22, 4, i) = R(0.0);     wave(3, 4, i) = a4 * amur;
+    wave(ku, 4, i) = R(0.0);         wave(kv, 4, i) = -a4 * csr;      s(4, i) = csr;
+    for (int m = 1; m <= meqn; ++m) {
+      amdq(m, i) = s(1, i) * wave(m, 1, i) + s(3, i) * wave(m, 3, i);
+      apdq(m, i) = s(2, i) * wave(m, 2, i) + s(4, i) * wave(m, 4, i);
+    }
+  }
+}
+
+template <class R>
+void rpt2_vc_elasticity(int ixy, int imp, int, int, int, int, int mbc, int mx, V2<R>, V2<R>, V2<R> aux1, V2<R> aux2,
+                        V2<R> aux3, V2<R> asdq, V2<R> bmasdq, V2<R> bpasdq, const double*) {
+  const int ksig11 = ixy == 1 ? 1 : 2, ksig22 = ixy == 1 ? 2 : 1, ku = ixy == 1 ? 4 : 5, kv = ixy == 1 ? 5 : 4;
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    const int i1 = (imp == 1) ? i - 1 : i;
+    R dsig22 = asdq(ksig22, i), dsig12 = asdq(3, i), du = asdq(ku, i), dv = asdq(kv, i);
+    R alamm = aux1(2, i1), alam = aux2(2, i1), alamp = aux3(2, i1);
+    R amum = aux1(3, i1), amu = aux2(3, i1), amup = aux3(3, i1);
+    R bulkm = alamm + R(2.0) * amum, bulk = alam + R(2.0) * amu, bulkp = alamp + R(2.0) * amup;
+    R cpm = aux1(4, i1), cp = aux2(4, i1), cpp = aux3(4, i1);
+    R csm = aux1(5, i1), cs = aux2(5, i1), csp = aux3(5, i1);
+    R det = bulkm * cp + bulk * cpm;
+    R a1 = (cp * dsig22 + bulk * dv) / det;
+    det = bulk * cpp + bulkp * cp;
+    R a2 = (cp * dsig22 - bulk * dv) / det;
+    R a3, a4;
+    det = -(amum * cs + amu * csm);
+    if (det == R(0.0)) a3 = R(0.0); else a3 = (cs * dsig12 + amu * du) / det;
+    det = -(amu * csp + amup * cs);
+    if (det == R(0.0)) a4 = R(0.0); else a4 = (cs * dsig12 - amu * du) / det;
+    bmasdq(ksig11, i) = -cpm * a1 * alamm;
+    bmasdq(ksig22, i) = -cpm * a1 * bulkm;
+    bmasdq(3, i) = -csm * a3 * (-amum);
+    bmasdq(ku, i) = -csm * a3 * (-csm);
+    bmasdq(kv, i) = -cpm * a1 * (cpm);
+    bpasdq(ksig11, i) = cpp * a2 * alamp;
+    bpasdq(ksig22, i) = cpp * a2 * bulkp;
+    bpasdq(3, i) = csp * a4 * (-amup);
+    bpasdq(ku, i) = csp * a4 * (csp);
+    bpasdq(kv, i) = cpp * a2 * (-cpp);
+  }
+}
+
 template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt) {
   switch (rp_id) {
     case RP_ADVECTION_2D: rpn = rpn2_advection<R>; rpt = rpt2_advection<R>; return true;
@@ -1180,6 +1261,7 @@ template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt)
     case RP_SHALLOW_BATHYMETRY_FWAVE_2D: rpn = rpn2_shallow_bathymetry_fwave<R>; rpt = rpt2_dummy<R>; return true;
     case RP_BURGERS_2D: rpn = rpn2_burgers<R>; rpt = rpt2_burgers<R>; return true;
     case RP_KPP_2D: rpn = rpn2_kpp<R>; rpt = rpt2_dummy<R>; return true;
+    case RP_VC_ELASTICITY_2D: rpn = rpn2_vc_elasticity<R>; rpt = rpt2_vc_elasticity<R>; return true;
   }
   return false;
 }

@@ -37,6 +37,7 @@ RP_IDS = {
     'burgers_2D': 16,
     'vc_advection_3D': 17,
     'kpp_2D': 18,
+    'vc_elasticity_2D': 19,
     'advection_1D': 21,
     'acoustics_1D': 22,
     'burgers_1D': 23,
@@ -70,6 +71,7 @@ CPARAM_NAMES = {
     'shallow_bathymetry_fwave_2D': ('grav', 'dry_tolerance', 'sea_level'),   # rpn2_shallow_bathymetry_fwave.f90:44-45
     'burgers_2D': (),
     'kpp_2D': (),                     # rpn2_kpp.f90: no parameters
+    'vc_elasticity_2D': (),           # rpn2_vc_elasticity.f90: material in aux
     'vc_advection_3D': (),
     'burgers_3D': ('coeff',),         # rpn3_burgers.f90:45: common /cparam/ coeff(3)
     'advection_1D': ('u',),           # rp1_advection.f90
@@ -95,8 +97,8 @@ NUM_WAVES = {'advection_2D': 1, 'acoustics_2D': 2, 'euler_4wave_2D': 4, 'shallow
              'psystem_2D': 2, 'euler_hlle_2D': 2, 'shallow_hlle_2D': 2,
              'acoustics_mapped_2D': 2, 'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'burgers_2D': 1, 'vc_advection_3D': 1, 'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2}
 
-NUM_EQN.update({'kpp_2D': 1, 'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2, 'euler_with_efix_1D': 3, 'euler_hlle_1D': 3, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1})
-NUM_WAVES.update({'kpp_2D': 1, 'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2, 'euler_with_efix_1D': 3, 'euler_hlle_1D': 2, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1})
+NUM_EQN.update({'kpp_2D': 1, 'vc_elasticity_2D': 5, 'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2, 'euler_with_efix_1D': 3, 'euler_hlle_1D': 3, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1})
+NUM_WAVES.update({'kpp_2D': 1, 'vc_elasticity_2D': 4, 'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2, 'euler_with_efix_1D': 3, 'euler_hlle_1D': 2, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1})
 
 BC_CUSTOM, BC_EXTRAP, BC_PERIODIC, BC_WALL = 0, 1, 2, 3
 

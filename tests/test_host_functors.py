@@ -251,6 +251,14 @@ def _pencils2a(name, rng, n):
                              rng.uniform(0.5, 1.5, n), rng.uniform(0.5, 1.5, n), rng.uniform(0.5, 4.0, n),
                              rng.uniform(0.5, 3.0, n)])
         aux = three(geom)
+    elif name == 'vc_elasticity_2D':
+        q = rng.standard_normal((5, n))
+
+        def material():
+            rho, lam, mu = rng.uniform(1.0, 4.0, n), rng.uniform(1.0, 4.0, n), rng.uniform(0.5, 2.0, n)
+            mu[::6] = 0.0                                # fluid cells: no shear waves (the det == 0 branches)
+            return np.stack([rho, lam, mu, np.sqrt((lam + 2 * mu) / rho), np.sqrt(mu / rho)])
+        aux = three(material)
     elif name == 'shallow_bathymetry_fwave_2D':
         h = rng.uniform(0.01, 2.0, n); h[::5] = 5e-4      # isolated dry cells (two adjacent ones give 0/0 in the reference, :77)
         q = np.stack([h, h * rng.standard_normal(n), h * rng.standard_normal(n)])
@@ -261,7 +269,8 @@ def _pencils2a(name, rng, n):
     return np.asfortranarray(q), aux, np.array(cp + [0.0])
 
 
-NAMES_2D_AUX = ['vc_acoustics_2D', 'vc_advection_2D', 'psystem_2D', 'acoustics_mapped_2D', 'shallow_bathymetry_fwave_2D']
+NAMES_2D_AUX = ['vc_acoustics_2D', 'vc_advection_2D', 'psystem_2D', 'acoustics_mapped_2D', 'shallow_bathymetry_fwave_2D',
+                'vc_elasticity_2D']
 
 
 @pytest.mark.parametrize('ixy', [1, 2])

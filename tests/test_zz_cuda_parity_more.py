@@ -127,3 +127,32 @@ def test_kpp_2d_refuses_transverse_modes():
     claw = S.make_claw(sc, kernel_language='CUDA')
     with pytest.raises(ClawCudaError):
         claw.run()
+
+
+# ---- vc_elasticity_2D (rp_id 19; rpn2/rpt2_vc_elasticity.f90, 5 aux planes) -------------------------------------------
+ELASTICITY_CASES = {
+    'elasticity_unsplit_cor': lambda: S.elasticity_2d(mx=64, my=50),
+    'elasticity_unsplit_inc': lambda: S.elasticity_2d(mx=40, my=57, transverse_waves=1),
+    'elasticity_unsplit_notrans': lambda: dict(S.elasticity_2d(mx=33, my=30, transverse_waves=0), cfl_max=0.5,
+                                               cfl_desired=0.45),
+    'elasticity_split': lambda: S.elasticity_2d(mx=60, my=44, dimensional_split=True),
+    'elasticity_tile_edge_superbee': lambda: dict(S.elasticity_2d(mx=28 * 2 + 1, my=9), limiters=S.SUPERBEE),
+}
+
+
+@pytest.mark.parametrize('name', sorted(ELASTICITY_CASES))
+def test_elasticity_strict_bit_exact_vs_oracle(name):
+    sc = ELASTICITY_CASES[name]()
+    q, log, _ = _run_cuda(sc, 6, 'strict')
+    qr, logr = _run_ref(sc, 6)
+    assert log == logr, 'dt / CFL sequence differs: %r vs %r' % (log[:3], logr[:3])
+    assert np.array_equal(q, qr), 'max abs diff %g' % np.max(np.abs(q - qr))
+
+
+@pytest.mark.parametrize('name', sorted(ELASTICITY_CASES))
+def test_elasticity_fast_within_tolerance(name):
+    sc = ELASTICITY_CASES[name]()
+    qr, logr = _run_ref(sc, 101)
+    q, log, _ = _run_cuda(sc, 101, 'fast')
+    assert [s[2] for s in log] == [s[2] for s in logr]
+    assert _rel_linf(q, qr) <= 1e-10
