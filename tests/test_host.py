@@ -351,3 +351,45 @@ def test_controller_binary_output_restart_functionals_and_overwrite_guard(oracle
     claw3.overwrite = False
     with pytest.raises(Exception, match='Refusing to overwrite'):
         claw3.run()
+
+
+def test_strang_source_splitting_fixed_dt_and_max_steps(oracle_lib):
+    """ClawSolver.step options of classic/solver.py:96-146 and Solver.evolve_to_time (solver.py:554-666) that no
+    reference example on the classic path exercises together: Strang splitting of a source term (source_split = 2:
+    half step before and after the hyperbolic step), fixed time steps (dt_variable = False: t = tstart + n dt, 'dt does
+    not divide' and 'CFL too large, giving up!' errors) and the max_steps guard -- host mirror with the oracle plug-in
+    against the oracle's own loop, step for step."""
+    def damping(q, aux, dt):                       # q_t = -2 q: exact update, so Godunov and Strang splitting differ
+        q *= np.exp(-2.0 * dt)
+
+    base = S.acoustics_2d(mx=20, my=16, tfinal=0.06, num_output_times=2)
+    for split in (1, 2):
+        sc = dict(base, step_source=damping, source_split=split)
+        claw = S.make_claw(sc, kernel_language='Fortran', fmod=OracleFmod())
+        claw.run()
+        r = ref_solver(sc)
+        r.run(sc['tfinal'], sc['num_output_times'])
+        assert claw.solver.source_split == split
+        assert np.array_equal(claw.solution.state.q, r.q), split
+        assert claw.solver.step_log == r.step_log
+    # fixed dt: 12 steps of 0.005
+    claw = S.make_claw(base, kernel_language='Fortran', fmod=OracleFmod(), dt_variable=False, dt_initial=0.005)
+    claw.run()
+    r = ref_solver(dict(base, dt_initial=0.005))
+    r.dt_variable = False
+    r._method[0] = 0
+    r.run(base['tfinal'], base['num_output_times'])
+    # (get_dt still trims the last step of an output interval to land on tend exactly, solver.py:547-552)
+    assert len(claw.solver.step_log) == 12 and np.allclose([s[0] for s in claw.solver.step_log], 0.005, rtol=1e-12)
+    assert claw.solver.step_log == r.step_log
+    assert np.array_equal(claw.solution.state.q, r.q)
+    assert abs(claw.solution.t - 0.06) < 1e-15
+    claw = S.make_claw(base, kernel_language='Fortran', fmod=OracleFmod(), dt_variable=False, dt_initial=0.0047)
+    with pytest.raises(Exception, match='dt does not divide'):
+        claw.run()
+    claw = S.make_claw(base, kernel_language='Fortran', fmod=OracleFmod(), dt_variable=False, dt_initial=0.03)
+    with pytest.raises(Exception, match='CFL too large'):
+        claw.run()
+    claw = S.make_claw(base, kernel_language='Fortran', fmod=OracleFmod(), max_steps=1)
+    with pytest.raises(Exception, match='Maximum number of timesteps'):
+        claw.run()
