@@ -1126,10 +1126,11 @@ int claw_step1_host(int meqn, int mwaves, int maux, int num_ghost, int mx, doubl
   std::lock_guard<std::mutex> lock(g_host_mutex);
   if (num_ghost != 2) return fail(nullptr, 3, "claw_step1_host: num_ghost must be 2");
   if (!q || !method7 || !mthlim || !cfl || mx < 1) return fail(nullptr, 12, "claw_step1_host: bad arguments");
-  // rp_id 21..33 (include/clawcuda.h): num_eqn, num_waves (riemann/riemann/static.py) and the aux components read
-  static const int k_meqn[] = {1, 2, 1, 2, 2, 1, 1, 2, 2, 3, 3, 2, 1}, k_mwaves[] = {1, 2, 1, 2, 2, 1, 1, 2, 2, 3, 2, 2, 1},
-                   k_maux[] = {0, 0, 0, 0, 0, 0, 1, 2, 1, 0, 0, 3, 0};
-  if (rp_id < 21 || rp_id > 33) return fail(nullptr, 5, "claw_step1_host: unknown 1-D rp_id %d", rp_id);
+  // rp_id 21..36 (include/clawcuda.h): num_eqn, num_waves (riemann/riemann/static.py) and the aux components read
+  static const int k_meqn[] = {1, 2, 1, 2, 2, 1, 1, 2, 2, 3, 3, 2, 1, 1, 1, 2},
+                   k_mwaves[] = {1, 2, 1, 2, 2, 1, 1, 2, 2, 3, 2, 2, 1, 1, 1, 2},
+                   k_maux[] = {0, 0, 0, 0, 0, 0, 1, 2, 1, 0, 0, 3, 0, 1, 1, 1};
+  if (rp_id < 21 || rp_id > 36) return fail(nullptr, 5, "claw_step1_host: unknown 1-D rp_id %d", rp_id);
   if (k_meqn[rp_id - 21] != meqn || k_mwaves[rp_id - 21] != mwaves)
     return fail(nullptr, 6, "claw_step1_host: rp_id %d expects meqn=%d mwaves=%d (got %d, %d)", rp_id,
                 k_meqn[rp_id - 21], k_mwaves[rp_id - 21], meqn, mwaves);

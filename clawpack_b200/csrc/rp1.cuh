@@ -393,5 +393,79 @@ struct RpCubic1D {
   }
 };
 
+// traffic_vc_1D / traffic_vc_tracer_1D -- rp1_traffic_vc.f90:38-84, rp1_traffic_vc_tracer.f90:40-97     aux(1) = speed limit
+__device__ __forceinline__ double traffic_vc_f0(double v_l, double v_r, double s_l, double s_r, double f_l, double f_r) {
+  if (f_l >= 0.25 * v_r && s_r > 0.0) return 0.25 * v_r;
+  if (f_r >= 0.25 * v_l && s_l < 0.0) return 0.25 * v_l;
+  if (s_r <= 0.0 && f_l > f_r) return f_r;
+  if (s_l >= 0.0 && f_r > f_l) return f_l;
+  if (s_l <= 0.0 && s_r >= 0.0) return (v_r <= v_l) ? 0.25 * v_r : 0.25 * v_l;
+  if (f_l <= f_r) return f_r;
+  return f_l;
+}
+struct RpTrafficVc1D {
+  static constexpr int MEQN = 1, MWAVES = 1, MAUX = 1;
+  __device__ __forceinline__ static void normal(const RpParams& P, const double* ql, const double* qr,
+                                                const double* al, const double* ar,
+                                                double (*wave)[MEQN], double* s, double* amdq, double* apdq) {
+    const double q_l = ql[0], q_r = qr[0], v_l = al[0], v_r = ar[0];
+    const double s_l = v_l * (1.0 - 2.0 * q_l), s_r = v_r * (1.0 - 2.0 * q_r);
+    const double f_l = v_l * q_l * (1.0 - q_l), f_r = v_r * q_r * (1.0 - q_r);
+    wave[0][0] = q_r - q_l;
+    s[0] = 0.5 * (s_l + s_r);
+    const double f0 = traffic_vc_f0(v_l, v_r, s_l, s_r, f_l, f_r);
+    amdq[0] = f0 - f_l;
+    apdq[0] = f_r - f0;
+  }
+};
+struct RpTrafficVcTracer1D {
+  static constexpr int MEQN = 2, MWAVES = 2, MAUX = 1;
+  __device__ __forceinline__ static void normal(const RpParams& P, const double* ql, const double* qr,
+                                                const double* al, const double* ar,
+                                                double (*wave)[MEQN], double* s, double* amdq, double* apdq) {
+    const double q_l = ql[0], q_r = qr[0], v_l = al[0], v_r = ar[0];
+    const double s_l = v_l * (1.0 - 2.0 * q_l), s_r = v_r * (1.0 - 2.0 * q_r);
+    s[1] = v_r * (1.0 - q_r);
+    const double f_l = v_l * q_l * (1.0 - q_l), f_r = v_r * q_r * (1.0 - q_r);
+    wave[0][0] = q_r - q_l; wave[0][1] = 0.0;
+    wave[1][0] = 0.0;       wave[1][1] = s[1] * (qr[1] - ql[1]);
+    apdq[1] = wave[1][1];
+    amdq[1] = 0.0;
+    s[0] = 0.5 * (s_l + s_r);
+    const double f0 = traffic_vc_f0(v_l, v_r, s_l, s_r, f_l, f_r);
+    amdq[0] = f0 - f_l;
+    apdq[0] = f_r - f0;
+  }
+};
+
+// traffic_vc_fwave_1D -- rp1_traffic_vc_fwave.f90:38-90 (one f-wave)
+struct RpTrafficVcFwave1D {
+  static constexpr int MEQN = 1, MWAVES = 1, MAUX = 1;
+  __device__ __forceinline__ static void normal(const RpParams& P, const double* ql, const double* qr,
+                                                const double* al, const double* ar,
+                                                double (*fwave)[MEQN], double* s, double* amdq, double* apdq) {
+    const double sim1 = al[0] * (1.0 - 2.0 * ql[0]);
+    const double si = ar[0] * (1.0 - 2.0 * qr[0]);
+    const double fim1 = al[0] * ql[0] * (1.0 - ql[0]);
+    const double fi = ar[0] * qr[0] * (1.0 - qr[0]);
+    const double fw = fi - fim1;
+    fwave[0][0] = fw;
+    if (sim1 < 0.0 && si <= 0.0) {
+      s[0] = sim1; amdq[0] = fw; apdq[0] = 0.0;
+    } else if (sim1 >= 0.0 && si > 0.0) {
+      s[0] = si; amdq[0] = 0.0; apdq[0] = fw;
+    } else if (sim1 < 0.0 && si > 0.0) {
+      s[0] = 0.5 * (sim1 + si);
+      const double f0 = fmin2(al[0], ar[0]) * 0.25;
+      amdq[0] = f0 - fim1; apdq[0] = fi - f0;
+    } else {
+      s[0] = 0.5 * (sim1 + si);
+      if (fw < 0.0) { amdq[0] = fw; apdq[0] = 0.0; }
+      else if (fw > 0.0) { amdq[0] = 0.0; apdq[0] = fw; }
+      else { amdq[0] = 0.5 * fw; apdq[0] = 0.5 * fw; }
+    }
+  }
+};
+
 }  // namespace CLAW_NS
 }  // namespace clawcuda

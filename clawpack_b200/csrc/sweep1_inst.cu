@@ -32,6 +32,9 @@ cudaError_t launch_sweep1(int rp_id, Sweep2Params& P, cudaStream_t st, LaunchInf
     case 31: return launch1<RpEulerHlle1D>(P, st, info);
     case 32: return launch1<RpNonlinearElasticityFwave1D>(P, st, info);
     case 33: return launch1<RpCubic1D>(P, st, info);
+    case 34: return launch1<RpTrafficVc1D>(P, st, info);
+    case 35: return launch1<RpTrafficVcFwave1D>(P, st, info);
+    case 36: return launch1<RpTrafficVcTracer1D>(P, st, info);
   }
   return cudaErrorInvalidValue;
 }

@@ -40,6 +40,9 @@ _SOLVERS = {
     'euler_hlle_1D': (31, ('gamma',), 1),                     # rp1_euler_hlle.f90:47
     'nonlinear_elasticity_fwave_1D': (32, (), 1),             # rp1_nonlinear_elasticity_fwave.f90 (rho, coefA, coefB in aux)
     'cubic_1D': (33, (), 1),                                  # rp1_cubic.f90
+    'traffic_vc_1D': (34, (), 1),                             # rp1_traffic_vc.f90 (speed limit in aux)
+    'traffic_vc_fwave_1D': (35, (), 1),                       # rp1_traffic_vc_fwave.f90
+    'traffic_vc_tracer_1D': (36, (), 1),                      # rp1_traffic_vc_tracer.f90
 }
 
 for _name, (_id, _cp, _nd) in _SOLVERS.items():

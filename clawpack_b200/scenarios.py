@@ -759,6 +759,23 @@ def blast_1d(mx=800, tfinal=0.038):
                  bc_lower=[WALL], bc_upper=[WALL], tfinal=tfinal)
 
 
+def traffic_vc_1d(mx=400, tfinal=1.0, kind='vc'):
+    """LWR traffic with a variable speed limit (riemann traffic_vc_1D / traffic_vc_fwave_1D / traffic_vc_tracer_1D; the
+    reference ships no PyClaw example for them): periodic road, speed limit 1 with a slow stretch (0.5) between
+    x = 0.4 and 0.7, a platoon of dense traffic behind it; the tracer variant carries a second, passively advected
+    component.  MC limiter."""
+    x = centers(0.0, 1.0, mx)
+    aux = np.empty((1, mx), order='F')
+    aux[0] = 1.0 - 0.5 * ((x > 0.4) & (x < 0.7))
+    rows = [0.2 + 0.5 * np.exp(-200.0 * (x - 0.2) ** 2)]
+    rp = {'vc': 'traffic_vc_1D', 'fwave': 'traffic_vc_fwave_1D', 'tracer': 'traffic_vc_tracer_1D'}[kind]
+    if kind == 'tracer':
+        rows.append(np.sin(2 * np.pi * x))
+    q = np.asfortranarray(np.stack(rows))
+    return _base(rp, (0.0,), (1.0,), (mx,), q, aux=aux, limiters=MC, fwave=(kind == 'fwave'), bc_lower=[PERIODIC],
+                 bc_upper=[PERIODIC], aux_bc_lower=[PERIODIC], aux_bc_upper=[PERIODIC], tfinal=tfinal)
+
+
 def cubic_1d(mx=1000, tfinal=0.2, qL=4.0, qR=-2.0):
     """pyclaw/examples/cubic_1d/cubic.py:14-54 (classic): q_t + (q^3)_x = 0, Riemann data qL | qR at x = -0.5,
     van Leer, cfl_desired 0.5, extrapolation.  test_cubic.py:3-21 checks the shock position x0 = -0.5 + 12 t."""

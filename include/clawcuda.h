@@ -73,7 +73,10 @@ enum {
   CLAW_RP_EULER_EFIX_1D = 30,          /* rp1_euler_with_efix.f90 (cparam = gamma) */
   CLAW_RP_EULER_HLLE_1D = 31,          /* rp1_euler_hlle.f90 (cparam = gamma) */
   CLAW_RP_NONLINEAR_ELASTICITY_FWAVE_1D = 32, /* rp1_nonlinear_elasticity_fwave.f90 (f-wave; aux: density, coefA, coefB) */
-  CLAW_RP_CUBIC_1D = 33                /* rp1_cubic.f90 */
+  CLAW_RP_CUBIC_1D = 33,               /* rp1_cubic.f90 */
+  CLAW_RP_TRAFFIC_VC_1D = 34,          /* rp1_traffic_vc.f90 (aux: speed limit) */
+  CLAW_RP_TRAFFIC_VC_FWAVE_1D = 35,    /* rp1_traffic_vc_fwave.f90 (f-wave; aux: speed limit) */
+  CLAW_RP_TRAFFIC_VC_TRACER_1D = 36    /* rp1_traffic_vc_tracer.f90 (2 equations; aux: speed limit) */
 };
 
 /* Boundary-condition ids = pyclaw.BC (pyclaw/src/pyclaw/solver.py:13-19) */
@@ -198,8 +201,8 @@ int claw_step3ds_host(int maxm, int meqn, int mwaves, int maux, int num_ghost, i
 /* 1-D: claw_step1_host <-> step1 (pyclaw/src/pyclaw/classic/step1.f90:2-3 as called at classic/solver.py:302):
    q(meqn, mx+2*num_ghost) with ghost cells is updated IN PLACE (interior and the ghost cells the Fortran touches),
    aux(maux, mx+2*num_ghost) may be NULL when maux == 0; the f2py scratch arguments (f, wave, s, amdq, apdq, dtdx) are
-   internal.  1-D Riemann solver ids: CLAW_RP_*_1D above, 21..33 (riemann/src/rp1_*.f90); solvers that read aux
-   (27, 28, 29, 32) fail with code 7 when aux is NULL or has too few components. */
+   internal.  1-D Riemann solver ids: CLAW_RP_*_1D above, 21..36 (riemann/src/rp1_*.f90); solvers that read aux
+   (27, 28, 29, 32, 34, 35, 36) fail with code 7 when aux is NULL or has too few components. */
 int claw_step1_host(int meqn, int mwaves, int maux, int num_ghost, int mx, double* q, const double* aux,
                     double dx, double dt, const int* method7, const int* mthlim, int use_fwave,
                     int rp_id, const double* cparam, int ncparam, int mode, double* cfl);

@@ -25,6 +25,9 @@ enum RpId1 {
   RP_EULER_HLLE_1D = 31,
   RP_NONLINEAR_ELASTICITY_FWAVE_1D = 32,
   RP_CUBIC_1D = 33,
+  RP_TRAFFIC_VC_1D = 34,
+  RP_TRAFFIC_VC_FWAVE_1D = 35,
+  RP_TRAFFIC_VC_TRACER_1D = 36,
 };
 
 template <class R>
@@ -428,6 +431,79 @@ void rp1_cubic(int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R>, V
   }
 }
 
+// traffic_vc_1D / traffic_vc_tracer_1D -- riemann/src/rp1_traffic_vc.f90:38-84, rp1_traffic_vc_tracer.f90:40-97
+// LWR traffic with a spatially varying speed limit aux(1); Godunov flux f0 of the concave flux v q (1 - q) with a
+// discontinuous coefficient.  The tracer variant carries a second component advected at the car speed (wave 2).
+template <class R> inline R traffic_vc_f0(R v_l, R v_r, R s_l, R s_r, R f_l, R f_r) {
+  if (f_l >= R(0.25) * v_r && s_r > R(0.0)) return R(0.25) * v_r;
+  if (f_r >= R(0.25) * v_l && s_l < R(0.0)) return R(0.25) * v_l;
+  if (s_r <= R(0.0) && f_l > f_r) return f_r;
+  if (s_l >= R(0.0) && f_r > f_l) return f_l;
+  if (s_l <= R(0.0) && s_r >= R(0.0)) return (v_r <= v_l) ? R(0.25) * v_r : R(0.25) * v_l;
+  if (f_l <= f_r) return f_r;
+  return f_l;
+}
+template <class R>
+void rp1_traffic_vc(int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R> auxl, V2<R> auxr, V3<R> wave,
+                    V2<R> s, V2<R> amdq, V2<R> apdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R q_r = ql(1, i), q_l = qr(1, i - 1), v_r = auxl(1, i), v_l = auxr(1, i - 1);
+    R s_l = v_l * (R(1.0) - R(2.0) * q_l), s_r = v_r * (R(1.0) - R(2.0) * q_r);
+    R f_l = v_l * q_l * (R(1.0) - q_l), f_r = v_r * q_r * (R(1.0) - q_r);
+    wave(1, 1, i) = q_r - q_l;
+    s(1, i) = R(0.5) * (s_l + s_r);
+    R f0 = traffic_vc_f0(v_l, v_r, s_l, s_r, f_l, f_r);
+    amdq(1, i) = f0 - f_l;
+    apdq(1, i) = f_r - f0;
+  }
+}
+template <class R>
+void rp1_traffic_vc_tracer(int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R> auxl, V2<R> auxr,
+                           V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R q_r = ql(1, i), q_l = qr(1, i - 1), v_r = auxl(1, i), v_l = auxr(1, i - 1);
+    R s_l = v_l * (R(1.0) - R(2.0) * q_l), s_r = v_r * (R(1.0) - R(2.0) * q_r);
+    s(2, i) = v_r * (R(1.0) - q_r);
+    R f_l = v_l * q_l * (R(1.0) - q_l), f_r = v_r * q_r * (R(1.0) - q_r);
+    wave(1, 1, i) = q_r - q_l; wave(2, 1, i) = R(0.0);
+    wave(1, 2, i) = R(0.0);    wave(2, 2, i) = s(2, i) * (ql(2, i) - qr(2, i - 1));     // as the reference has it (:56)
+    apdq(2, i) = wave(2, 2, i);
+    amdq(2, i) = R(0.0);
+    s(1, i) = R(0.5) * (s_l + s_r);
+    R f0 = traffic_vc_f0(v_l, v_r, s_l, s_r, f_l, f_r);
+    amdq(1, i) = f0 - f_l;
+    apdq(1, i) = f_r - f0;
+  }
+}
+
+// traffic_vc_fwave_1D -- riemann/src/rp1_traffic_vc_fwave.f90:38-90 (the same model as one f-wave)
+template <class R>
+void rp1_traffic_vc_fwave(int, int, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R> auxl, V2<R> auxr,
+                          V3<R> fwave, V2<R> s, V2<R> amdq, V2<R> apdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    R sim1 = auxr(1, i - 1) * (R(1.0) - R(2.0) * qr(1, i - 1));
+    R si = auxl(1, i) * (R(1.0) - R(2.0) * ql(1, i));
+    R fim1 = auxr(1, i - 1) * qr(1, i - 1) * (R(1.0) - qr(1, i - 1));
+    R fi = auxl(1, i) * ql(1, i) * (R(1.0) - ql(1, i));
+    fwave(1, 1, i) = fi - fim1;
+    if (sim1 < R(0.0) && si <= R(0.0)) {
+      s(1, i) = sim1; amdq(1, i) = fwave(1, 1, i); apdq(1, i) = R(0.0);
+    } else if (sim1 >= R(0.0) && si > R(0.0)) {
+      s(1, i) = si; amdq(1, i) = R(0.0); apdq(1, i) = fwave(1, 1, i);
+    } else if (sim1 < R(0.0) && si > R(0.0)) {
+      s(1, i) = R(0.5) * (sim1 + si);
+      R f0 = r_min(auxr(1, i - 1), auxl(1, i)) * R(0.25);
+      amdq(1, i) = f0 - fim1; apdq(1, i) = fi - f0;
+    } else {
+      s(1, i) = R(0.5) * (sim1 + si);
+      R d = fi - fim1;
+      if (d < R(0.0)) { amdq(1, i) = fwave(1, 1, i); apdq(1, i) = R(0.0); }
+      else if (d > R(0.0)) { amdq(1, i) = R(0.0); apdq(1, i) = fwave(1, 1, i); }
+      else { amdq(1, i) = R(0.5) * fwave(1, 1, i); apdq(1, i) = R(0.5) * fwave(1, 1, i); }
+    }
+  }
+}
+
 template <class R> inline bool select_rp1(int rp_id, Rp1<R>& rp) {
   switch (rp_id) {
     case RP_ADVECTION_1D: rp = rp1_advection<R>; return true;
@@ -443,6 +519,9 @@ template <class R> inline bool select_rp1(int rp_id, Rp1<R>& rp) {
     case RP_EULER_HLLE_1D: rp = rp1_euler_hlle<R>; return true;
     case RP_NONLINEAR_ELASTICITY_FWAVE_1D: rp = rp1_nonlinear_elasticity_fwave<R>; return true;
     case RP_CUBIC_1D: rp = rp1_cubic<R>; return true;
+    case RP_TRAFFIC_VC_1D: rp = rp1_traffic_vc<R>; return true;
+    case RP_TRAFFIC_VC_FWAVE_1D: rp = rp1_traffic_vc_fwave<R>; return true;
+    case RP_TRAFFIC_VC_TRACER_1D: rp = rp1_traffic_vc_tracer<R>; return true;
   }
   return false;
 }

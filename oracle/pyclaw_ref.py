@@ -51,6 +51,9 @@ RP_IDS = {
     'euler_hlle_1D': 31,
     'nonlinear_elasticity_fwave_1D': 32,
     'cubic_1D': 33,
+    'traffic_vc_1D': 34,
+    'traffic_vc_fwave_1D': 35,
+    'traffic_vc_tracer_1D': 36,
 }
 # COMMON /cparam/ member order of each solver (rpn2_advection.f90, rpn2_acoustics.f90:52,
 # rpn2_euler_4wave.f90:71, rpn2_shallow_roe_with_efix.f90:59; vc_acoustics_3D has none)
@@ -87,6 +90,7 @@ CPARAM_NAMES = {
     'euler_hlle_1D': ('gamma',),   # rp1_euler_hlle.f90:47
     'nonlinear_elasticity_fwave_1D': (),   # rp1_nonlinear_elasticity_fwave.f90: rho, coefA, coefB in aux
     'cubic_1D': (),   # rp1_cubic.f90
+    'traffic_vc_1D': (), 'traffic_vc_fwave_1D': (), 'traffic_vc_tracer_1D': (),   # rp1_traffic_vc*.f90: speed limit in aux
 }
 NUM_EQN = {'advection_2D': 1, 'acoustics_2D': 3, 'euler_4wave_2D': 4, 'shallow_roe_with_efix_2D': 3,
            'vc_acoustics_3D': 4, 'euler_3D': 5, 'vc_acoustics_2D': 3, 'vc_advection_2D': 1, 'euler_5wave_2D': 5,
@@ -97,8 +101,8 @@ NUM_WAVES = {'advection_2D': 1, 'acoustics_2D': 2, 'euler_4wave_2D': 4, 'shallow
              'psystem_2D': 2, 'euler_hlle_2D': 2, 'shallow_hlle_2D': 2,
              'acoustics_mapped_2D': 2, 'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'burgers_2D': 1, 'vc_advection_3D': 1, 'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2}
 
-NUM_EQN.update({'kpp_2D': 1, 'vc_elasticity_2D': 5, 'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2, 'euler_with_efix_1D': 3, 'euler_hlle_1D': 3, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1})
-NUM_WAVES.update({'kpp_2D': 1, 'vc_elasticity_2D': 4, 'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2, 'euler_with_efix_1D': 3, 'euler_hlle_1D': 2, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1})
+NUM_EQN.update({'traffic_vc_1D': 1, 'traffic_vc_fwave_1D': 1, 'traffic_vc_tracer_1D': 2, 'kpp_2D': 1, 'vc_elasticity_2D': 5, 'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2, 'euler_with_efix_1D': 3, 'euler_hlle_1D': 3, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1})
+NUM_WAVES.update({'traffic_vc_1D': 1, 'traffic_vc_fwave_1D': 1, 'traffic_vc_tracer_1D': 2, 'kpp_2D': 1, 'vc_elasticity_2D': 4, 'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2, 'euler_with_efix_1D': 3, 'euler_hlle_1D': 2, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1})
 
 BC_CUSTOM, BC_EXTRAP, BC_PERIODIC, BC_WALL = 0, 1, 2, 3
 

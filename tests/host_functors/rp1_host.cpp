@@ -51,7 +51,8 @@ extern "C" int hostfun_rp1(int rp_id, const double* cparam, int ncparam, int n, 
     CASE(21, RpAdvection1D) CASE(22, RpAcoustics1D) CASE(23, RpBurgers1D) CASE(24, RpShallowRoeEfix1D)
     CASE(25, RpShallowHlle1D) CASE(26, RpTraffic1D) CASE(27, RpAdvectionColor1D) CASE(28, RpAcousticsVariable1D)
     CASE(29, RpShallowBathymetryFwave1D) CASE(30, RpEulerEfix1D) CASE(31, RpEulerHlle1D)
-    CASE(32, RpNonlinearElasticityFwave1D) CASE(33, RpCubic1D)
+    CASE(32, RpNonlinearElasticityFwave1D) CASE(33, RpCubic1D) CASE(34, RpTrafficVc1D)
+    CASE(35, RpTrafficVcFwave1D) CASE(36, RpTrafficVcTracer1D)
   }
 #undef CASE
   return 1;

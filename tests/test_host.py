@@ -236,7 +236,9 @@ def test_host_loop_1d_aux_fwave_custom_bc_with_plugin(oracle_lib):
                     (S.stegoton_1d(xupper=40.0, tfinal=25.0, num_output_times=5), None),
                     (S.stegoton_1d(xupper=30.0, tfinal=22.0, num_output_times=4, exponential=False), None),
                     (S.shocktube_1d(mx=100), None), (S.blast_1d(mx=120, tfinal=0.01), None),
-                    (S.cubic_1d(mx=80, tfinal=0.05), None), (S.acoustics_1d_variable(mx=90, tfinal=0.4), None)):
+                    (S.cubic_1d(mx=80, tfinal=0.05), None), (S.acoustics_1d_variable(mx=90, tfinal=0.4), None),
+                    (S.traffic_vc_1d(mx=60, tfinal=0.3), None), (S.traffic_vc_1d(mx=60, tfinal=0.3, kind='fwave'), None),
+                    (S.traffic_vc_1d(mx=60, tfinal=0.3, kind='tracer'), None)):
         claw = S.make_claw(sc, kernel_language='Fortran', fmod=OracleFmod())
         claw.run()
         r = ref_solver(sc)

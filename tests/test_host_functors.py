@@ -48,6 +48,11 @@ def _pencils(name, rng, n):
         q = rng.standard_normal((1, n)) * 2
     elif name == 'traffic_1D':
         q = rng.uniform(0, 1, (1, n)); cp = [rng.uniform(0.5, 2.0)]
+    elif name in ('traffic_vc_1D', 'traffic_vc_fwave_1D', 'traffic_vc_tracer_1D'):
+        rows = [rng.uniform(0, 1, n)] + ([rng.standard_normal(n)] if name == 'traffic_vc_tracer_1D' else [])
+        q = np.stack(rows)
+        q[0, ::9] = 0.5; q[0, 1::9] = 0.5                     # equal states at the flux maximum: the tie branches
+        aux = rng.choice([0.5, 1.0, 1.0, 2.0], (1, n))
     elif name in ('shallow_roe_with_efix_1D', 'shallow_hlle_1D'):
         h = rng.uniform(0.05, 3.0, n); u = rng.standard_normal(n) * 2
         q = np.stack([h, h * u]); cp = [9.81]

@@ -339,6 +339,26 @@ def test_step1_unpinned_solvers_sanity(oracle_lib):
     assert abs(np.sum(s.q[0] / K) - np.sum(sc['q'][0] / K)) < 1e-11
 
 
+def test_traffic_vc_1d_properties(oracle_lib):
+    # rp1_traffic_vc / _fwave / _tracer have no example or stored vector in the reference (parity unpinned): cars are
+    # conserved on the periodic road, the density stays in [0, 1], the wave and the f-wave formulation of the same
+    # Godunov flux converge to each other, and the tracer variant reproduces the density
+    res = {}
+    for kind in ('vc', 'fwave', 'tracer'):
+        for mx in (200, 400):
+            sc = S.traffic_vc_1d(mx=mx, kind=kind)
+            s = ref_solver(sc)
+            s.run(sc['tfinal'], sc['num_output_times'])
+            assert np.isfinite(s.q).all() and s.q[0].min() >= -1e-12 and s.q[0].max() <= 1 + 1e-12
+            assert abs(np.sum(s.q[0]) - np.sum(sc['q'][0])) < 1e-10 * np.sum(sc['q'][0]), kind
+            res[kind, mx] = s.q.copy()
+    d = [np.mean(np.abs(res['vc', mx][0] - res['fwave', mx][0])) for mx in (200, 400)]
+    assert d[0] < 1e-2 and d[1] < 0.7 * d[0], d
+    # (not bit-equal: the tracer wave's speed enters the CFL number, so the time steps differ)
+    assert np.mean(np.abs(res['tracer', 400][0] - res['vc', 400][0])) < 2e-3
+    assert np.max(np.abs(res['tracer', 400][1])) <= 1.0 + 1e-9
+
+
 def test_kpp_2d_properties(oracle_lib):
     # pyclaw/examples/kpp/kpp.py has no stored vector (parity unpinned by the reference): the restated rpn2_kpp is held
     # to the properties of the entropy solution -- maximum principle (pi/4 <= q <= 3.5 pi up to limiter overshoot of

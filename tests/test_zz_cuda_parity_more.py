@@ -25,6 +25,9 @@ CASES_1D_MORE = {
     'blast_roe_walls': lambda: S.blast_1d(mx=800),
     'stegoton_linear': lambda: S.stegoton_1d(xupper=60.0, exponential=False),
     'cubic': lambda: S.cubic_1d(mx=250),
+    'traffic_vc': lambda: S.traffic_vc_1d(mx=300),
+    'traffic_vc_fwave': lambda: S.traffic_vc_1d(mx=300, kind='fwave'),
+    'traffic_vc_tracer': lambda: S.traffic_vc_1d(mx=211, kind='tracer'),
 }
 
 
