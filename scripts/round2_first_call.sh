@@ -1,0 +1,19 @@
+#!/bin/bash
+# First GPU call of a round, in ONE gpurun invocation (everything lands in gpurun_out/):
+#   1. the GPU parity suite (incl. tests/test_zz_cuda_parity_more.py, which round 1 could only check on the CPU)
+#   2. smoke()
+#   3. the bench line (default workload) and the reference arm
+#   4. kernel-only timings of the tuning variants worth a look (0 = default, 50 = march loop unrolled x2)
+#   5. the ncu launch list of a short bench run
+# usage:  gpurun --timeout 1500 -- 'bash scripts/round2_first_call.sh r02_a'
+tag=${1:-r02_a}
+out=gpurun_out
+mkdir -p $out
+python -m pytest tests -x -q -m gpu > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest exit $?" >> $out/${tag}_pytest_gpu.log
+tail -5 $out/${tag}_pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; tail -2 $out/${tag}_smoke.log
+python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; tail -c 600 $out/${tag}_bench.json
+python bench.py --impl reference --steps 3 --warmup 3 > $out/${tag}_bench_reference_arm.json 2>> $out/${tag}_bench.err
+bash scripts/variant_sweep.sh "0 50 7" $out/${tag}_variants.jsonl
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_bench.csv \
+    python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > $out/${tag}_ncu_bench.log 2>&1
