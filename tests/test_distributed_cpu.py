@@ -11,12 +11,14 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _launch(case, world, port, outdir=None):
+def _launch(case, world, port, outdir=None, fmt=None):
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), OMP_NUM_THREADS='1')
         if outdir:
             env['CLAW_TEST_OUTDIR'] = outdir
+        if fmt:
+            env['CLAW_TEST_FORMAT'] = fmt
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, 'dist_worker.py'), case, str(port)],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []
@@ -41,6 +43,9 @@ def _launch(case, world, port, outdir=None):
     ('acoustics3d_periodic', 2, 29617),
     ('acoustics3d_wall_periodic', 3, 29618),
     ('euler3d_unsplit_extrap', 2, 29619),
+    ('elasticity_unsplit_aux', 2, 29622),
+    ('elasticity_unsplit_aux', 3, 29623),
+    ('kpp_split', 2, 29624),
 ])
 def test_slab_decomposition_matches_serial(case, world, port, oracle_lib):
     codes, outs = _launch(case, world, port)
@@ -56,3 +61,12 @@ def test_distributed_frame_output(oracle_lib, tmp_path):
     assert codes == [0, 0], '\n'.join(outs)
     assert 'frame file of the gathered solution matches the serial result: True' in outs[0], outs[0]
     assert sorted(f for f in os.listdir(out) if f.startswith('fort.q')) == ['fort.q0000', 'fort.q0001', 'fort.q0002']
+
+
+def test_distributed_binary_frame_output(oracle_lib, tmp_path):
+    """The same with output_format='binary': the gathered frame is the serial result bit for bit."""
+    out = str(tmp_path / 'frames')
+    codes, outs = _launch('elasticity_unsplit_aux', 2, 29625, outdir=out, fmt='binary')
+    assert codes == [0, 0], '\n'.join(outs)
+    assert 'frame file of the gathered solution matches the serial result: True' in outs[0], outs[0]
+    assert sorted(f for f in os.listdir(out) if f.startswith('fort.b')) == ['fort.b0000', 'fort.b0001', 'fort.b0002']
