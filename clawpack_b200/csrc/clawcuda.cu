@@ -459,6 +459,7 @@ int rp2_aux_planes(int rp_id) {
     case 13: return 9;     // acoustics_mapped_2D: edge normals + length ratios, capacity, impedance, sound speed
     case 14: return 1;     // shallow_bathymetry_fwave_2D: bathymetry
     case 19: return 5;     // vc_elasticity_2D: density, lambda, mu, cp, cs
+    case 20: return 2;     // vc_advection_vector_2D: edge velocities
   }
   return -1;
 }
@@ -475,7 +476,7 @@ int validate_config(claw_solver* h) {
       return fail(h, 31, "capacity functions are only implemented for the aux-reading 2-D solvers (rp_id %d reads none)", h->rp_id);
     if (need_aux == 0 && h->use_fwave)
       return fail(h, 32, "rp_id %d is not an f-wave solver", h->rp_id);
-    if ((h->rp_id == 11 || h->rp_id == 12 || h->rp_id == 14 || h->rp_id == 18) && h->method[2] > 0)
+    if ((h->rp_id == 11 || h->rp_id == 12 || h->rp_id == 14 || h->rp_id == 18 || h->rp_id == 20) && h->method[2] > 0)
       return fail(h, 36, "rp_id %d has no usable transverse Riemann solver (rpt2_dummy.f90; rpt2_shallow_bathymetry_fwave "
                          "reads an unassigned value): transverse_waves must be 0 or the step dimensionally split", h->rp_id);
     if (h->method[1] != 1 && h->method[1] != 2) return fail(h, 33, "order must be 1 or 2 (got %d)", h->method[1]);
@@ -530,10 +531,10 @@ int claw_create(claw_solver** out, int ndim, int rp_id, int meqn, int mwaves, in
   if (num_ghost != 2) return fail(nullptr, 3, "claw_create: num_ghost must be 2 (classic solvers), got %d", num_ghost);
   if (meqn < 1 || meqn > 8 || mwaves < 1 || mwaves > 8 || maux < 0)
     return fail(nullptr, 4, "claw_create: bad sizes meqn=%d mwaves=%d maux=%d", meqn, mwaves, maux);
-  static const int k_meqn[] = {0, 1, 3, 4, 3, 4, 5, 3, 1, 5, 3, 4, 3, 3, 3, 1, 1, 1, 1, 5},
-                   k_mwaves[] = {0, 1, 2, 4, 3, 2, 3, 2, 1, 5, 2, 2, 2, 2, 3, 1, 1, 1, 1, 4},
-                   k_ndim[] = {0, 2, 2, 2, 2, 3, 3, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 3, 2, 2};
-  if (rp_id < 1 || rp_id > 19) return fail(nullptr, 5, "claw_create: unknown rp_id %d", rp_id);
+  static const int k_meqn[] = {0, 1, 3, 4, 3, 4, 5, 3, 1, 5, 3, 4, 3, 3, 3, 1, 1, 1, 1, 5, 2},
+                   k_mwaves[] = {0, 1, 2, 4, 3, 2, 3, 2, 1, 5, 2, 2, 2, 2, 3, 1, 1, 1, 1, 4, 1},
+                   k_ndim[] = {0, 2, 2, 2, 2, 3, 3, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 3, 2, 2, 2};
+  if (rp_id < 1 || rp_id > 20) return fail(nullptr, 5, "claw_create: unknown rp_id %d", rp_id);
   if (k_meqn[rp_id] != meqn || k_mwaves[rp_id] != mwaves || k_ndim[rp_id] != ndim)
     return fail(nullptr, 6, "claw_create: rp_id %d expects ndim=%d meqn=%d mwaves=%d (got %d, %d, %d)", rp_id,
                 k_ndim[rp_id], k_meqn[rp_id], k_mwaves[rp_id], ndim, meqn, mwaves);

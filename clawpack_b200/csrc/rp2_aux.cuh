@@ -354,5 +354,37 @@ struct RpVcElasticity2D {
   }
 };
 
+// ------------------------------------------------------------------------------------
+// vc_advection_vector_2D -- pyclaw/examples/advection_reaction_2d/rpn2_vc_advection_vector.f90:40-47 (+ rpt2_dummy.f90)
+// Colour equation for two unknowns sharing one velocity field; aux(1) = u at the left edge, aux(2) = v at the bottom
+// edge of the cell (read from the cell on the RIGHT of the interface).   roe = (s).  No transverse solver.
+// ------------------------------------------------------------------------------------
+struct RpVcAdvectionVector2D {
+  static constexpr int MEQN = 2, MWAVES = 1, NROE = 1, NCELL = 0, MAUX = 2;
+  __device__ __forceinline__ static void normal(const RpParams& P, int dir, const double* ql, const double* qr,
+                                                const double* axl, const double* axr, double (*wave)[MEQN],
+                                                double* s, double* amdq, double* apdq, double* roe) {
+    const double vel = axr[dir];
+    s[0] = vel;
+    const double vm = fmin2(vel, 0.0), vp = fmax2(vel, 0.0);
+#pragma unroll
+    for (int m = 0; m < MEQN; ++m) {
+      wave[0][m] = qr[m] - ql[m];
+      amdq[m] = vm * wave[0][m];
+      apdq[m] = vp * wave[0][m];
+    }
+    roe[0] = vel;
+  }
+  __device__ __forceinline__ static void speeds(const RpParams& P, int dir, const double* roe, double* s) {
+    s[0] = roe[0];
+  }
+  __device__ __forceinline__ static void transverse(const RpParams& P, int dir, const double* roe, const double*,
+                                                    const double*, const double*, const double*, const double*,
+                                                    const double*, const double* asdq, double* bm, double* bp) {
+#pragma unroll
+    for (int m = 0; m < MEQN; ++m) { bm[m] = 0.0; bp[m] = 0.0; }
+  }
+};
+
 }  // namespace CLAW_NS
 }  // namespace clawcuda

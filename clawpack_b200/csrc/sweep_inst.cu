@@ -163,6 +163,7 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
     case 18:                                                 // kpp_2D: scalar, like burgers_2D
       if (kind == 1) return launch_split_ws<RpKpp2D, 1, 16>(P, seg_hint, num_sms, st, info);
       return launch_ws<RpKpp2D, 1, 16, 6>(P, seg_hint, num_sms, st, info);
+    case 20: return launch_aux<RpVcAdvectionVector2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 19: return launch_aux<RpVcElasticity2D, 2>(kind, P, seg_hint, num_sms, st, info);
     case 13: return launch_aux<RpAcousticsMapped2D, 1>(kind, P, seg_hint, num_sms, st, info);
     case 14: return launch_aux<RpShallowBathymetryFwave2D, 2>(kind, P, seg_hint, num_sms, st, info);

@@ -23,6 +23,7 @@ _SOLVERS = {
     'psystem_2D': (10, (), 2),                                # rpn2_psystem.f90 (f-wave; coefficients + strain in aux)
     'burgers_2D': (16, (), 2),                                # rpn2_burgers.f90, rpt2_burgers.f90
     'vc_elasticity_2D': (19, (), 2),                          # rpn2_vc_elasticity.f90 (material in aux)
+    'vc_advection_vector_2D': (20, (), 2),                    # examples/advection_reaction_2d/rpn2_vc_advection_vector.f90
     'kpp_2D': (18, (), 2),                                    # rpn2_kpp.f90 (+ rpt2_dummy.f90)
     'burgers_3D': (15, ('coeff',), 3),
     'vc_advection_3D': (17, (), 3),                           # rpn3_vc_advection.f90 (edge velocities in aux)                        # rpn3_burgers.f90:45: common /cparam/ coeff(3)

@@ -11,7 +11,7 @@ num_eqn = {
     'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'vc_advection_3D': 1,
     'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2,
     'euler_with_efix_1D': 3, 'euler_hlle_1D': 3, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1,
-    'traffic_vc_1D': 1, 'traffic_vc_fwave_1D': 1, 'traffic_vc_tracer_1D': 2,
+    'traffic_vc_1D': 1, 'traffic_vc_fwave_1D': 1, 'traffic_vc_tracer_1D': 2, 'vc_advection_vector_2D': 2,
 }
 
 num_waves = {
@@ -23,7 +23,7 @@ num_waves = {
     'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'vc_advection_3D': 1,
     'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2,
     'euler_with_efix_1D': 3, 'euler_hlle_1D': 2, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1,
-    'traffic_vc_1D': 1, 'traffic_vc_fwave_1D': 1, 'traffic_vc_tracer_1D': 2,
+    'traffic_vc_1D': 1, 'traffic_vc_fwave_1D': 1, 'traffic_vc_tracer_1D': 2, 'vc_advection_vector_2D': 1,
 }
 
 fwave = {name: False for name in num_eqn}

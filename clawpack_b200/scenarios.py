@@ -608,6 +608,47 @@ def elasticity_2d(mx=80, my=80, tfinal=0.25, num_output_times=5, dimensional_spl
                  aux_bc_upper=[EXTRAP, EXTRAP], tfinal=tfinal, num_output_times=num_output_times)
 
 
+def advection_reaction_2d(mx=100, my=100, tfinal=4.0, num_output_times=10):
+    """pyclaw/examples/advection_reaction_2d/advection_reaction.py:36-110 (classic, dimensionally split): two unknowns
+    transported by the time-periodic swirl velocity field psi = sin^2(pi x) sin^2(pi y) / pi (edge velocities in aux,
+    rewritten by ``before_step`` from t + dt/2 every step) and coupled by the source term p_t = eps q, q_t = eps p
+    (``step_source``, Godunov splitting); the example's own Riemann solver rpn2_vc_advection_vector + rpt2_dummy;
+    minmod (default), extrapolation."""
+    t_period, epsilon = 4.0, 0.1
+    dx, dy = 1.0 / mx, 1.0 / my
+    xe = np.array([0.0 + i * dx for i in range(mx + 1)])           # Dimension.nodes (geometry.py:541-545)
+    ye = np.array([0.0 + j * dy for j in range(my + 1)])
+    X, Y = np.meshgrid(xe, ye, indexing='ij')
+
+    def psi(x, y):
+        return (np.sin(np.pi * x)) ** 2 * (np.sin(np.pi * y)) ** 2 / np.pi
+
+    def velocities():
+        a = np.empty((2, mx, my), order='F')
+        a[0] = -(psi(X[:-1, 1:], Y[:-1, 1:]) - psi(X[:-1, :-1], Y[:-1, :-1])) / dy
+        a[1] = (psi(X[1:, :-1], Y[1:, :-1]) - psi(X[:-1, :-1], Y[:-1, :-1])) / dx
+        return a
+
+    def set_velocities(q, aux, t, dt):
+        v_t = np.cos(2 * np.pi * (t + dt / 2) / t_period)
+        aux[...] = velocities()
+        aux[:] = v_t * aux[:]
+
+    def source_step(q, aux, dt):
+        qq = q.copy()
+        q[0] = q[0] + epsilon * dt * qq[1]
+        q[1] = q[1] + epsilon * dt * qq[0]
+
+    Xc, Yc = _grid((0., 0.), (1., 1.), (mx, my))
+    q = np.empty((2, mx, my), order='F')
+    q[0] = (Xc <= 0.5)
+    q[1] = (Yc <= 0.5)
+    return _base('vc_advection_vector_2D', (0., 0.), (1., 1.), (mx, my), q, aux=velocities(), limiters=MINMOD,
+                 dimensional_split=True, bc_lower=[EXTRAP, EXTRAP], bc_upper=[EXTRAP, EXTRAP],
+                 aux_bc_lower=[EXTRAP, EXTRAP], aux_bc_upper=[EXTRAP, EXTRAP], before_step_full=set_velocities,
+                 step_source=source_step, source_split=1, tfinal=tfinal, num_output_times=num_output_times)
+
+
 def kpp_2d(mx=200, my=200, tfinal=1.0, num_output_times=10):
     """pyclaw/examples/kpp/kpp.py:18-55 (classic): q_t + sin(q)_x + cos(q)_y = 0, disc of 3.5 pi in a sea of pi/4,
     dimensional splitting, minmod, extrapolation."""
@@ -845,6 +886,9 @@ def make_claw(sc, kernel_language='CUDA', pyclaw=None, **solver_kw):
     if sc.get('before_step') is not None:
         fb = sc['before_step']
         solver.before_step = lambda solver_, state: fb(state.q, state.aux)
+    if sc.get('before_step_full') is not None:          # f(q, aux, t, dt): dt is the size of the PREVIOUS step (solver.py:609)
+        fbf = sc['before_step_full']
+        solver.before_step = lambda solver_, state: fbf(state.q, state.aux, state.t, solver_.dt)
     if sc.get('fwave'):
         solver.fwave = True
     if sc.get('compute_gauge_values') is not None:

@@ -60,6 +60,7 @@ enum {
   CLAW_RP_VC_ADVECTION_3D = 17,        /* rpn3_vc_advection.f90, rpt3_vc_advection.f90, rptt3_vc_advection.f90 (aux: edge velocities) */
   CLAW_RP_KPP_2D = 18,                 /* rpn2_kpp.f90 + rpt2_dummy.f90 (non-convex scalar flux; no transverse solver) */
   CLAW_RP_VC_ELASTICITY_2D = 19,       /* rpn2_vc_elasticity.f90, rpt2_vc_elasticity.f90 (aux: density, lambda, mu, cp, cs) */
+  CLAW_RP_VC_ADVECTION_VECTOR_2D = 20, /* pyclaw/examples/advection_reaction_2d/rpn2_vc_advection_vector.f90 + rpt2_dummy.f90 (aux: edge velocities) */
   /* 1-D (claw_step1_host only) */
   CLAW_RP_ADVECTION_1D = 21,           /* riemann/src/rp1_advection.f90 */
   CLAW_RP_ACOUSTICS_1D = 22,           /* rp1_acoustics.f90 */

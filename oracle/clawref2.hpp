@@ -81,6 +81,7 @@ enum RpId {
   RP_SHALLOW_HLLE_2D = 12,
   RP_KPP_2D = 18,
   RP_VC_ELASTICITY_2D = 19,
+  RP_VC_ADVECTION_VECTOR_2D = 20,
   RP_ACOUSTICS_MAPPED_2D = 13,
   RP_SHALLOW_BATHYMETRY_FWAVE_2D = 14,
   RP_BURGERS_2D = 16,                // (15 = burgers_3D, clawref3.hpp)
@@ -1245,6 +1246,22 @@ void rpt2_vc_elasticity(int ixy, int imp, int, int, int, int, int mbc, int mx, V
   }
 }
 
+// ---------------------------------------------------------------------
+// vc_advection_vector_2D -- pyclaw/examples/advection_reaction_2d/rpn2_vc_advection_vector.f90:40-47 (+ rpt2_dummy.f90):
+// the colour equation for a VECTOR of unknowns sharing one velocity field; aux(ixy) = edge velocity.  (The example
+// builds it as the extension module `advection_2d`; it is not part of clawpack.riemann.)
+// ---------------------------------------------------------------------
+template <class R>
+void rpn2_vc_advection_vector(int ixy, int, int meqn, int, int, int mbc, int mx, V2<R> ql, V2<R> qr, V2<R> auxl, V2<R>,
+                              V3<R> wave, V2<R> s, V2<R> amdq, V2<R> apdq, const double*) {
+  for (int i = 2 - mbc; i <= mx + mbc; ++i) {
+    for (int m = 1; m <= meqn; ++m) wave(m, 1, i) = ql(m, i) - qr(m, i - 1);
+    s(1, i) = auxl(ixy, i);
+    for (int m = 1; m <= meqn; ++m) amdq(m, i) = r_min(auxl(ixy, i), R(0.0)) * wave(m, 1, i);
+    for (int m = 1; m <= meqn; ++m) apdq(m, i) = r_max(auxl(ixy, i), R(0.0)) * wave(m, 1, i);
+  }
+}
+
 template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt) {
   switch (rp_id) {
     case RP_ADVECTION_2D: rpn = rpn2_advection<R>; rpt = rpt2_advection<R>; return true;
@@ -1262,6 +1279,7 @@ template <class R> inline bool select_rp2(int rp_id, Rpn2<R>& rpn, Rpt2<R>& rpt)
     case RP_BURGERS_2D: rpn = rpn2_burgers<R>; rpt = rpt2_burgers<R>; return true;
     case RP_KPP_2D: rpn = rpn2_kpp<R>; rpt = rpt2_dummy<R>; return true;
     case RP_VC_ELASTICITY_2D: rpn = rpn2_vc_elasticity<R>; rpt = rpt2_vc_elasticity<R>; return true;
+    case RP_VC_ADVECTION_VECTOR_2D: rpn = rpn2_vc_advection_vector<R>; rpt = rpt2_dummy<R>; return true;
   }
   return false;
 }
@@ -1463,7 +1481,8 @@ int step2(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int 
   Rpn2<R> rpn2; Rpt2<R> rpt2;
   if (!select_rp2<R>(rp_id, rpn2, rpt2)) return 1;
   // rpt2_dummy.f90 ("Error: Dummy transverse Riemann solver called!") leaves its outputs unset: refuse instead
-  if ((rp_id == RP_EULER_HLLE_2D || rp_id == RP_SHALLOW_HLLE_2D || rp_id == RP_SHALLOW_BATHYMETRY_FWAVE_2D || rp_id == RP_KPP_2D) && method[2] > 0)
+  if ((rp_id == RP_EULER_HLLE_2D || rp_id == RP_SHALLOW_HLLE_2D || rp_id == RP_SHALLOW_BATHYMETRY_FWAVE_2D || rp_id == RP_KPP_2D ||
+       rp_id == RP_VC_ADVECTION_VECTOR_2D) && method[2] > 0)
     return 2;
   if (maxm < mx || maxm < my) return 2;
   const int nx = mx + 2 * num_ghost;

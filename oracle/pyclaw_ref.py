@@ -38,6 +38,7 @@ RP_IDS = {
     'vc_advection_3D': 17,
     'kpp_2D': 18,
     'vc_elasticity_2D': 19,
+    'vc_advection_vector_2D': 20,
     'advection_1D': 21,
     'acoustics_1D': 22,
     'burgers_1D': 23,
@@ -75,6 +76,7 @@ CPARAM_NAMES = {
     'burgers_2D': (),
     'kpp_2D': (),                     # rpn2_kpp.f90: no parameters
     'vc_elasticity_2D': (),           # rpn2_vc_elasticity.f90: material in aux
+    'vc_advection_vector_2D': (),     # examples/advection_reaction_2d/rpn2_vc_advection_vector.f90
     'vc_advection_3D': (),
     'burgers_3D': ('coeff',),         # rpn3_burgers.f90:45: common /cparam/ coeff(3)
     'advection_1D': ('u',),           # rp1_advection.f90
@@ -101,8 +103,8 @@ NUM_WAVES = {'advection_2D': 1, 'acoustics_2D': 2, 'euler_4wave_2D': 4, 'shallow
              'psystem_2D': 2, 'euler_hlle_2D': 2, 'shallow_hlle_2D': 2,
              'acoustics_mapped_2D': 2, 'shallow_bathymetry_fwave_2D': 3, 'burgers_3D': 1, 'burgers_2D': 1, 'vc_advection_3D': 1, 'advection_1D': 1, 'acoustics_1D': 2, 'burgers_1D': 1, 'shallow_roe_with_efix_1D': 2, 'shallow_hlle_1D': 2}
 
-NUM_EQN.update({'traffic_vc_1D': 1, 'traffic_vc_fwave_1D': 1, 'traffic_vc_tracer_1D': 2, 'kpp_2D': 1, 'vc_elasticity_2D': 5, 'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2, 'euler_with_efix_1D': 3, 'euler_hlle_1D': 3, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1})
-NUM_WAVES.update({'traffic_vc_1D': 1, 'traffic_vc_fwave_1D': 1, 'traffic_vc_tracer_1D': 2, 'kpp_2D': 1, 'vc_elasticity_2D': 4, 'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2, 'euler_with_efix_1D': 3, 'euler_hlle_1D': 2, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1})
+NUM_EQN.update({'vc_advection_vector_2D': 2, 'traffic_vc_1D': 1, 'traffic_vc_fwave_1D': 1, 'traffic_vc_tracer_1D': 2, 'kpp_2D': 1, 'vc_elasticity_2D': 5, 'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2, 'euler_with_efix_1D': 3, 'euler_hlle_1D': 3, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1})
+NUM_WAVES.update({'vc_advection_vector_2D': 1, 'traffic_vc_1D': 1, 'traffic_vc_fwave_1D': 1, 'traffic_vc_tracer_1D': 2, 'kpp_2D': 1, 'vc_elasticity_2D': 4, 'traffic_1D': 1, 'advection_color_1D': 1, 'acoustics_variable_1D': 2, 'shallow_bathymetry_fwave_1D': 2, 'euler_with_efix_1D': 3, 'euler_hlle_1D': 2, 'nonlinear_elasticity_fwave_1D': 2, 'cubic_1D': 1})
 
 BC_CUSTOM, BC_EXTRAP, BC_PERIODIC, BC_WALL = 0, 1, 2, 3
 

@@ -1,4 +1,4 @@
-"""Fourth batch of reference regression vectors (1-D classic solvers added after the first batch)
+"""Fourth batch of reference regression vectors (1-D classic solvers added after the first batch, advection_reaction_2d)
 -> tests/golden/reference_goldens4.npz.
 
 Run in the build container only (reads /root/reference):   python tests/golden/make_golden4.py
@@ -19,6 +19,8 @@ out['shallow_1d__sill_Fortran'] = np.asarray(d['sill_Fortran'], dtype=np.float64
 # euler_1d/test_shocktube.py:17-26: the Fortran HLLE run must stay within 0.04 (max norm) of the Python HLLC run, whose
 # density is this stored vector (to 1e-4 in the 2-norm)
 out['euler_1d__shocktube_regression_density'] = np.loadtxt(os.path.join(REF, 'euler_1d/shocktube_regression_density.txt'))
+# advection_reaction_2d/test_advection_reaction.py:13-17: check_diff(reltol=1e-5) of q[0] against this 100x100 array
+out['advection_reaction_2d__density'] = np.loadtxt(os.path.join(REF, 'advection_reaction_2d/advection_reaction.txt'))
 HERE = os.path.dirname(os.path.abspath(__file__))
 np.savez_compressed(os.path.join(HERE, 'reference_goldens4.npz'), **out)
 for k, v in out.items():

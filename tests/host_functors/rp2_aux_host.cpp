@@ -67,7 +67,7 @@ extern "C" int hostfun_rp2_aux(int rp_id, int dir, const double* cparam, int ncp
   case ID: return run<RP>(dir, cparam, ncparam, n, maux, q, a1, a2, a3, wave, s, amdq, apdq, bm_a, bp_a, bm_b, bp_b, with_rpt);
   switch (rp_id) {
     CASE(7, RpVcAcoustics2D) CASE(8, RpVcAdvection2D) CASE(10, RpPsystem2D) CASE(13, RpAcousticsMapped2D)
-    CASE(14, RpShallowBathymetryFwave2D) CASE(19, RpVcElasticity2D)
+    CASE(14, RpShallowBathymetryFwave2D) CASE(19, RpVcElasticity2D) CASE(20, RpVcAdvectionVector2D)
   }
 #undef CASE
   return 1;

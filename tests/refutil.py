@@ -49,6 +49,9 @@ def ref_solver(sc, nthreads=1):
         s.source_split = sc.get('source_split', 1)
     if sc.get('before_step') is not None:
         s.before_step = sc['before_step']
+    if sc.get('before_step_full') is not None:
+        fbf = sc['before_step_full']
+        s.before_step = lambda q, aux: fbf(q, aux, s.t, s.dt)
     if sc.get('fwave'):
         s.fwave = True
     if sc.get('gauges'):

@@ -20,6 +20,7 @@ def test_host_loop_with_plugin_matches_oracle_loop(oracle_lib):
                S.quadrants(mx=40, my=40, tfinal=0.2), S.radial_dam_break(mx=40, my=40, tfinal=0.5),
                S.kpp_2d(mx=30, my=30, tfinal=0.3, num_output_times=3),
                S.elasticity_2d(mx=24, my=20, tfinal=0.1, num_output_times=2),
+               S.advection_reaction_2d(mx=24, my=20, tfinal=1.0, num_output_times=2),
                S.elasticity_2d(mx=20, my=24, tfinal=0.1, num_output_times=2, dimensional_split=True)):
         claw = S.make_claw(sc, kernel_language='Fortran', fmod=OracleFmod())
         claw.run()
@@ -27,7 +28,7 @@ def test_host_loop_with_plugin_matches_oracle_loop(oracle_lib):
         r.run(sc['tfinal'], sc['num_output_times'])
         assert np.array_equal(claw.frames[-1].q, r.q)
         assert claw.solver.step_log == r.step_log
-        assert any(not s[2] for s in r.step_log) or sc['rp'] in ('shallow_roe_with_efix_2D', 'kpp_2D', 'vc_elasticity_2D')
+        assert any(not s[2] for s in r.step_log) or sc['rp'] in ('shallow_roe_with_efix_2D', 'kpp_2D', 'vc_elasticity_2D')    # (advection_reaction: 1 reject)
 
 
 def test_host_loop_reference_golden(oracle_lib):

@@ -256,6 +256,9 @@ def _pencils2a(name, rng, n):
                              rng.uniform(0.5, 1.5, n), rng.uniform(0.5, 1.5, n), rng.uniform(0.5, 4.0, n),
                              rng.uniform(0.5, 3.0, n)])
         aux = three(geom)
+    elif name == 'vc_advection_vector_2D':
+        q = rng.standard_normal((2, n))
+        aux = three(lambda: rng.standard_normal((2, n)))
     elif name == 'vc_elasticity_2D':
         q = rng.standard_normal((5, n))
 
@@ -275,7 +278,7 @@ def _pencils2a(name, rng, n):
 
 
 NAMES_2D_AUX = ['vc_acoustics_2D', 'vc_advection_2D', 'psystem_2D', 'acoustics_mapped_2D', 'shallow_bathymetry_fwave_2D',
-                'vc_elasticity_2D']
+                'vc_elasticity_2D', 'vc_advection_vector_2D']
 
 
 @pytest.mark.parametrize('ixy', [1, 2])
@@ -289,7 +292,7 @@ def test_device_aux_functor_source_matches_oracle_rp2(hostlib2a, name, ixy):
     n = mx + 2 * g
     q, aux, cp = _pencils2a(name, rng, n)
     maux = aux[0].shape[0]
-    with_rpt = 0 if name == 'shallow_bathymetry_fwave_2D' else 1       # its rpt2 reads an unassigned value: refused
+    with_rpt = 0 if name in ('shallow_bathymetry_fwave_2D', 'vc_advection_vector_2D') else 1       # its rpt2 reads an unassigned value: refused
     z = lambda *shape: np.zeros(shape, order='F')
     wo, so, amo, apo = z(M, W, n), z(W, n), z(M, n), z(M, n)
     bo = [z(M, n) for _ in range(4)]

@@ -359,6 +359,21 @@ def test_traffic_vc_1d_properties(oracle_lib):
     assert np.max(np.abs(res['tracer', 400][1])) <= 1.0 + 1e-9
 
 
+def test_advection_reaction_2d_golden(oracle_lib):
+    # pyclaw/examples/advection_reaction_2d/test_advection_reaction.py:13-17 (check_diff reltol 1e-5 against
+    # advection_reaction.txt, 100x100, t = 4): pins step2ds with aux pencils, the example's rpn2_vc_advection_vector,
+    # a before_step that rewrites aux from (t, dt) every step -- including the 11 rejected steps, where q is restored but
+    # the rewritten aux stays --, and the Godunov-split source term
+    from refutil import goldens4
+    sc = S.advection_reaction_2d()
+    s = ref_solver(sc, nthreads=4)
+    s.run(sc['tfinal'], sc['num_output_times'])
+    e = goldens4()['advection_reaction_2d__density']
+    assert np.linalg.norm(e - s.q[0]) / np.linalg.norm(e) < 1e-5
+    assert np.max(np.abs(e - s.q[0])) < 1e-13
+    assert sum(1 for x in s.step_log if not x[2]) == 11
+
+
 def test_kpp_2d_properties(oracle_lib):
     # pyclaw/examples/kpp/kpp.py has no stored vector (parity unpinned by the reference): the restated rpn2_kpp is held
     # to the properties of the entropy solution -- maximum principle (pi/4 <= q <= 3.5 pi up to limiter overshoot of

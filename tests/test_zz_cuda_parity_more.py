@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from clawpack_b200 import scenarios as S
-from refutil import goldens4
+from refutil import goldens4, ref_solver
 from test_cuda_parity import _rel_linf, _run_cuda, _run_ref
 
 pytestmark = pytest.mark.gpu
@@ -159,3 +159,31 @@ def test_elasticity_fast_within_tolerance(name):
     q, log, _ = _run_cuda(sc, 101, 'fast')
     assert [s[2] for s in log] == [s[2] for s in logr]
     assert _rel_linf(q, qr) <= 1e-10
+
+
+# ---- vc_advection_vector_2D (rp_id 20): the reference's advection_reaction_2d example ---------------------------------
+@pytest.mark.parametrize('precision', ['strict', 'fast'])
+def test_advection_reaction_2d_reference_golden(precision):
+    """pyclaw/examples/advection_reaction_2d/test_advection_reaction.py:13-17 (reltol 1e-5 against advection_reaction.txt)
+    through Controller.run() with kernel_language='CUDA': before_step rewrites aux every step and a source term is
+    split off, so the solver runs in plug-in mode (claw_step2ds_host per sweep)."""
+    sc = S.advection_reaction_2d()
+    claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision=precision)
+    claw.run()
+    q = claw.frames[claw.num_output_times].state.get_q_global()
+    e = goldens4()['advection_reaction_2d__density']
+    assert np.linalg.norm(e - q[0]) / np.linalg.norm(e) < 1e-5
+    assert np.max(np.abs(e - q[0])) < 1e-10
+    if precision == 'strict':
+        r = ref_solver(sc, nthreads=4)
+        r.run(sc['tfinal'], sc['num_output_times'])
+        assert claw.solver.step_log == r.step_log
+        assert np.array_equal(q, r.q)
+
+
+def test_advection_vector_unsplit_notrans_bit_exact():
+    sc = dict(S.advection_reaction_2d(mx=45, my=38), dimensional_split=False, transverse_waves=0, cfl_max=0.5,
+              cfl_desired=0.45)
+    q, log, _ = _run_cuda(sc, 12, 'strict')
+    qr, logr = _run_ref(sc, 12)
+    assert log == logr and np.array_equal(q, qr)
