@@ -396,3 +396,32 @@ def test_strang_source_splitting_fixed_dt_and_max_steps(oracle_lib):
     claw = S.make_claw(base, kernel_language='Fortran', fmod=OracleFmod(), max_steps=1)
     with pytest.raises(Exception, match='Maximum number of timesteps'):
         claw.run()
+
+
+def test_reads_the_reference_amrclaw_binary_frame(tmp_path):
+    """pyclaw/src/pyclaw/tests/test_io.py:24-27 (test_io_from_binary): the reference's own regression frame -- written by
+    AMRClaw, 17 patches on three levels, two ghost cells per side in the .b file, old-style .t header without a format
+    line -- is read to exactly what the reference reader parses (tests/golden/make_golden6.py), then written and read
+    back as ascii (8 digits) and as binary (lossless), patch by patch."""
+    gdir = os.path.join(ROOT, 'tests', 'golden', 'amrclaw_binary_frame')
+    ref = np.load(os.path.join(gdir, 'reference_parsed.npz'))
+    sol = pyclaw.Solution(0, path=gdir, file_format='binary')
+    assert len(sol.states) == int(ref['nstates']) == 17 and sol.t == float(ref['t'])
+    for k, st in enumerate(sol.states):
+        meta = ref['meta%02d' % k]
+        dims = st.patch.dimensions
+        assert [st.patch.patch_index, st.patch.level] == [int(meta[0]), int(meta[1])]
+        assert [d.num_cells for d in dims] == [int(meta[2]), int(meta[3])]
+        assert np.array_equal([d.lower for d in dims], meta[4:6]) and np.array_equal([d.delta for d in dims], meta[6:8])
+        assert np.array_equal(st.q, ref['q%02d' % k])
+    for fmt in ('ascii', 'binary'):
+        out = str(tmp_path / fmt)
+        sol.write(0, out, fmt)
+        back = pyclaw.Solution(0, path=out, file_format=fmt)
+        assert len(back.states) == 17
+        for a, b in zip(back.states, sol.states):
+            assert a.patch.level == b.patch.level and a.q.shape == b.q.shape
+            if fmt == 'binary':
+                assert np.array_equal(a.q, b.q)
+            else:
+                assert np.max(np.abs(a.q - b.q)) <= 5e-9 * max(1.0, np.max(np.abs(b.q)))
