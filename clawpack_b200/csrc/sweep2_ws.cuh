@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
 // the x-updated rows in thread-private registers / shared memory; no __syncthreads in the march loop.  Rows are
 // prefetched one march step ahead with cp.async (PF != 0).  do_y = 0: x-sweep only, over rows [j0, j1).
 // =====================================================================================
-template <class RP, int NW, int MINB = 1, int PF = 1>
+template <class RP, int NW, int MINB = 1, int PF = 1, int UNR = 1>      // UNR: see sweep2_unsplit_ws
 __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_constant__ Sweep2Params P) {
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE, NT = NW * 32;
   constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
   for (int k = 0; k < NC1; ++k) cx1[k] = 0.0;
   if constexpr (PF != 0) { prefetch(Jb, Jb - 2); cp_async_commit(); }
 
+#pragma unroll UNR
   for (int J = Jb - 4; J < Je; ++J) {
     // ---- x-sweep of row J+2 ----------------------------------------------------------
     double qx2[M];

@@ -72,10 +72,10 @@ static cudaError_t launch_ws(Sweep2Params& P, int seg_hint, int num_sms, cudaStr
 }
 
 // warp-synchronous dimension-split kernel (sweep2_ws.cuh)
-template <class RP, int NW, int MINB, int PF = 1>
+template <class RP, int NW, int MINB, int PF = 1, int UNR = 1>
 static cudaError_t launch_split_ws(Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
   using S = Smem2ws<RP, NW>;
-  return launch_kernel(sweep2_split_ws<RP, NW, MINB, PF>, NW * 32, (int)S::BYTES, !P.do_y, P, seg_hint, num_sms, st, info,
+  return launch_kernel(sweep2_split_ws<RP, NW, MINB, PF, UNR>, NW * 32, (int)S::BYTES, !P.do_y, P, seg_hint, num_sms, st, info,
                        NW * 28);
 }
 
@@ -145,6 +145,8 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
           case 8: return launch_split_ws<RpShallowRoeEfix2D, 1, 8>(P, seg_hint, num_sms, st, info);
           case 9: return launch_split_ws<RpShallowRoeEfix2D, 1, 12, 0>(P, seg_hint, num_sms, st, info);
           case 10: return launch_split_ws<RpShallowRoeEfix2D, 2, 6>(P, seg_hint, num_sms, st, info);
+          case 51: return launch_split_ws<RpShallowRoeEfix2D, 1, 16, 1, 2>(P, seg_hint, num_sms, st, info);   // march loop unrolled x2 (round-2 experiment)
+          case 52: return launch_split_ws<RpShallowRoeEfix2D, 1, 12, 1, 2>(P, seg_hint, num_sms, st, info);   // the same with 168 registers
           default: break;       // 1: the block kernel
         }
       }
