@@ -319,7 +319,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
 // the x-updated rows in thread-private registers / shared memory; no __syncthreads in the march loop.  Rows are
 // prefetched one march step ahead with cp.async (PF != 0).  do_y = 0: x-sweep only, over rows [j0, j1).
 // =====================================================================================
-template <class RP, int NW, int MINB = 1, int PF = 1, int UNR = 1>      // UNR: see sweep2_unsplit_ws
+// LIM > 0: order 2 with limiter id LIM on every wave family, known at compile time (the generic kernel selects the
+// limiter per wave at run time: a five-way switch per wave and interface in both sweeps).  UNR: see sweep2_unsplit_ws.
+template <class RP, int NW, int MINB = 1, int PF = 1, int UNR = 1, int LIM = 0>
 __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_constant__ Sweep2Params P) {
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE, NT = NW * 32;
   constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
@@ -336,8 +338,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
   const int I = (blockIdx.x * NW + (t >> 5)) * TX + lane;
   const int Ic = I < nx ? I : nx - 1;
   const double dtdx = P.dtdx, dtdy = P.dtdy;
-  const bool second = (P.order != 1);
-  const bool limit = second && (P.limit != 0);
+  const bool second = LIM ? true : (P.order != 1);
+  const bool limit = LIM ? true : (second && (P.limit != 0));
   const bool do_x = P.do_x != 0, do_y = P.do_y != 0;
   const double* qcol = P.qin + Ic;
   double cfl = 0.0;
@@ -376,10 +378,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
 #pragma unroll
         for (int mw = 0; mw < W; ++mw) dotl[mw] = shfl_left(dotr[mw]);
 #ifndef CLAW_STRICT
-        limited_second_order<RP, 0>(P, dtdx, wave, s, wnorm2, dotl, dotr, cqxx);
+        limited_second_order<RP, LIM>(P, dtdx, wave, s, wnorm2, dotl, dotr, cqxx);
         done = true;
 #else
-        limit_waves<RP, 0>(P, wave, s, wnorm2, dotl, dotr);
+        limit_waves<RP, LIM>(P, wave, s, wnorm2, dotl, dotr);
 #endif
       }
       if (!done) second_order<RP>(dtdx, wave, s, cqxx);                    // flux2.f90:134-146
@@ -487,10 +489,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
           if (second) {
             double cqxx[M];
 #ifndef CLAW_STRICT
-            if (limit) limited_second_order<RP, 0>(P, dtdy, waveC, sC, wnorm2, dotl, dotn, cqxx);
+            if (limit) limited_second_order<RP, LIM>(P, dtdy, waveC, sC, wnorm2, dotl, dotn, cqxx);
             else second_order<RP>(dtdy, waveC, sC, cqxx);
 #else
-            if (limit) limit_waves<RP>(P, waveC, sC, wnorm2, dotl, dotn);
+            if (limit) limit_waves<RP, LIM>(P, waveC, sC, wnorm2, dotl, dotn);
             second_order<RP>(dtdy, waveC, sC, cqxx);
 #endif
 #pragma unroll

@@ -72,10 +72,10 @@ static cudaError_t launch_ws(Sweep2Params& P, int seg_hint, int num_sms, cudaStr
 }
 
 // warp-synchronous dimension-split kernel (sweep2_ws.cuh)
-template <class RP, int NW, int MINB, int PF = 1, int UNR = 1>
+template <class RP, int NW, int MINB, int PF = 1, int UNR = 1, int LIM = 0>
 static cudaError_t launch_split_ws(Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
   using S = Smem2ws<RP, NW>;
-  return launch_kernel(sweep2_split_ws<RP, NW, MINB, PF, UNR>, NW * 32, (int)S::BYTES, !P.do_y, P, seg_hint, num_sms, st, info,
+  return launch_kernel(sweep2_split_ws<RP, NW, MINB, PF, UNR, LIM>, NW * 32, (int)S::BYTES, !P.do_y, P, seg_hint, num_sms, st, info,
                        NW * 28);
 }
 
@@ -98,6 +98,13 @@ static cudaError_t launch_aux(int kind, Sweep2Params& P, int seg_hint, int num_s
 // order 2, transverse mode 2, every wave family limited with limiter id `lim`
 template <int W> static bool headline_method(const Sweep2Params& P, int lim) {
   if (P.order == 1 || P.mtrans != 2 || !P.limit) return false;
+  for (int mw = 0; mw < W; ++mw) if (P.mthlim[mw] != lim) return false;
+  return true;
+}
+
+// order 2, every wave family limited with limiter id `lim` (dimension-split step: no transverse mode involved)
+template <int W> static bool split_method(const Sweep2Params& P, int lim) {
+  if (P.order == 1 || !P.limit) return false;
   for (int mw = 0; mw < W; ++mw) if (P.mthlim[mw] != lim) return false;
   return true;
 }
@@ -147,6 +154,12 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
           case 10: return launch_split_ws<RpShallowRoeEfix2D, 2, 6>(P, seg_hint, num_sms, st, info);
           case 51: return launch_split_ws<RpShallowRoeEfix2D, 1, 16, 1, 2>(P, seg_hint, num_sms, st, info);   // march loop unrolled x2 (round-2 experiment)
           case 52: return launch_split_ws<RpShallowRoeEfix2D, 1, 12, 1, 2>(P, seg_hint, num_sms, st, info);   // the same with 168 registers
+          case 53: case 54:                                  // limiter known at compile time (MC on all waves, order 2)
+            if (split_method<3>(P, 4)) {
+              if (variant == 53) return launch_split_ws<RpShallowRoeEfix2D, 1, 16, 1, 1, 4>(P, seg_hint, num_sms, st, info);
+              return launch_split_ws<RpShallowRoeEfix2D, 1, 12, 1, 2, 4>(P, seg_hint, num_sms, st, info);
+            }
+            break;
           default: break;       // 1: the block kernel
         }
       }

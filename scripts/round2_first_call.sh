@@ -15,7 +15,9 @@ python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1;
 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; tail -c 600 $out/${tag}_bench.json
 python bench.py --impl reference --steps 3 --warmup 3 > $out/${tag}_bench_reference_arm.json 2>> $out/${tag}_bench.err
 bash scripts/variant_sweep.sh "0 50 7" $out/${tag}_variants.jsonl
-# shallow-water split kernel variants (config 3) are timed by scripts/bench_configs.py with CLAW_VARIANT=0, 51, 52
-for v in 0 51 52; do CLAW_VARIANT=$v python scripts/bench_configs.py --configs c3 >> $out/${tag}_c3_variants.jsonl 2>>$out/${tag}_bench.err; done
+# shallow-water split kernel variants (config 3) are timed by scripts/bench_configs.py with CLAW_VARIANT=0, 51..54 (53/54: compile-time limiter)
+for v in 0 51 52 53 54; do CLAW_VARIANT=$v python scripts/bench_configs.py --configs c3 >> $out/${tag}_c3_variants.jsonl 2>>$out/${tag}_bench.err; done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_bench.csv \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > $out/${tag}_ncu_bench.log 2>&1
+# parity of the specialised shallow-water split kernel (variant 53) before it may become the default
+CLAW_VARIANT=53 python -m pytest tests -q -m gpu -k "shallow or dam" > $out/${tag}_pytest_gpu_variant53.log 2>&1; tail -2 $out/${tag}_pytest_gpu_variant53.log
