@@ -219,6 +219,35 @@ int clawref_rp2_aux(int ixy, int num_eqn, int num_waves, int num_aux, int num_gh
   return 0;
 }
 
+#ifdef CLAWREF_WITH_3D
+// 3-D: one rpn3 call on a pencil (aux(num_aux, n) is the pencil's own aux row) and, for solvers whose transverse
+// routines read no aux (with_rpt != 0: euler_3D, burgers_3D), rpt3 with `icoor` on amdq (imp = 1) and apdq (imp = 2)
+// and rptt3 (imp = 1, impt = 1) on the first of those results.  Used by tests/test_host_functors.py.
+int clawref_rp3(int ixyz, int icoor, int num_eqn, int num_waves, int num_aux, int num_ghost, int mx, double* q,
+                double* aux, double* wave, double* s, double* amdq, double* apdq, double* bm_a, double* bp_a,
+                double* bm_b, double* bp_b, double* cm_tt, double* cp_tt, int rp_id, const double* cparam,
+                int with_rpt) {
+  Rpn3<double> rpn; Rpt3<double> rpt; Rptt3<double> rptt;
+  if (!select_rp3<double>(rp_id, rpn, rpt, rptt)) return 1;
+  const int lo = 1 - num_ghost, n = mx + 2 * num_ghost, na = num_aux > 0 ? num_aux : 1;
+  std::vector<double> dummy((size_t)3 * n * na, 0.0);
+  V2<double> Q{q, num_eqn, lo}, A{num_aux > 0 ? aux : dummy.data(), na, lo}, S{s, num_waves, lo}, AM{amdq, num_eqn, lo},
+      AP{apdq, num_eqn, lo};
+  V3<double> W{wave, num_eqn, num_waves, lo};
+  rpn(ixyz, mx, num_eqn, num_waves, num_aux, num_ghost, mx, Q, Q, A, A, W, S, AM, AP, cparam);
+  if (!with_rpt) return 0;
+  A3<double> D{dummy.data(), na, lo, n};
+  V2<double> BMA{bm_a, num_eqn, lo}, BPA{bp_a, num_eqn, lo};
+  rpt(ixyz, icoor, 1, mx, num_eqn, num_waves, num_aux, num_ghost, mx, Q, Q, D, D, D, AM, BMA, BPA, cparam);
+  rpt(ixyz, icoor, 2, mx, num_eqn, num_waves, num_aux, num_ghost, mx, Q, Q, D, D, D, AP, V2<double>{bm_b, num_eqn, lo},
+      V2<double>{bp_b, num_eqn, lo}, cparam);
+  // double-transverse solve in the OTHER transverse direction on the up-going part of the first split
+  rptt(ixyz, 5 - icoor, 1, 1, mx, num_eqn, num_waves, num_aux, num_ghost, mx, Q, Q, D, D, D, BPA,
+       V2<double>{cm_tt, num_eqn, lo}, V2<double>{cp_tt, num_eqn, lo}, cparam);
+  return 0;
+}
+#endif
+
 int clawref_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

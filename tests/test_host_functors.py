@@ -309,3 +309,73 @@ def test_device_aux_functor_source_matches_oracle_rp2(hostlib2a, name, ixy):
     for a, b, what in pairs:
         assert np.isfinite(b).all(), (name, what)
         assert np.array_equal(a, b), (name, ixy, what, float(np.max(np.abs(a - b))))
+
+
+# ---- 3-D solvers (csrc/rp3.cuh) ------------------------------------------------------------------------------------
+SRC3 = os.path.join(HERE, 'host_functors', 'rp3_host.cpp')
+
+
+@pytest.fixture(scope='module')
+def hostlib3(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp('hostfun3') / 'librp3_host.so')
+    subprocess.run([CXX, '-O2', '-ffp-contract=off', '-std=c++17', '-fPIC', '-shared', '-Wno-unknown-pragmas',
+                    '-o', out, SRC3], check=True)
+    L = ctypes.CDLL(out)
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.hostfun_rp3.argtypes = [ctypes.c_int] * 3 + [dp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [dp] * 12 + [ctypes.c_int]
+    L.hostfun_rp3.restype = ctypes.c_int
+    R = pyclaw_ref.lib()
+    R.clawref_rp3.argtypes = [ctypes.c_int] * 7 + [dp] * 12 + [ctypes.c_int, dp, ctypes.c_int]
+    R.clawref_rp3.restype = ctypes.c_int
+    return L, R
+
+
+def _pencils3(name, rng, n):
+    aux, cp = None, []
+    if name == 'vc_acoustics_3D':
+        q = rng.standard_normal((4, n)); aux = rng.uniform(0.5, 4.0, (2, n))
+    elif name == 'euler_3D':
+        rho = rng.uniform(0.1, 3.0, n); vel = rng.standard_normal((3, n)) * 2; p = rng.uniform(0.1, 5.0, n)
+        q = np.vstack([rho, rho * vel, p / 0.4 + 0.5 * rho * np.sum(vel * vel, axis=0)]); cp = [1.4]
+    elif name == 'burgers_3D':
+        q = rng.standard_normal((1, n)) * 2; cp = [1.0, 0.5, -0.75]
+    elif name == 'vc_advection_3D':
+        q = rng.standard_normal((1, n)); aux = rng.standard_normal((3, n))
+    else:
+        raise KeyError(name)
+    q[:, n // 2: n // 2 + 8] = q[:, n // 2: n // 2 + 1]
+    return np.asfortranarray(q), (None if aux is None else np.asfortranarray(aux)), np.array(cp + [0.0])
+
+
+@pytest.mark.parametrize('icoor', [2, 3])
+@pytest.mark.parametrize('ixyz', [1, 2, 3])
+@pytest.mark.parametrize('name', ['vc_acoustics_3D', 'euler_3D', 'burgers_3D', 'vc_advection_3D'])
+def test_device_functor_source_matches_oracle_rp3(hostlib3, name, ixyz, icoor):
+    """normal<IXYZ>() of every 3-D functor against rpn3, and -- for the solvers whose transverse routines read no aux --
+    transverse<IXYZ,ICOOR>() against rpt3 (both fluctuations) and rptt3 (on one of the results)."""
+    L, R = hostlib3
+    rp_id = pyclaw_ref.RP_IDS[name]
+    M, W = pyclaw_ref.NUM_EQN[name], pyclaw_ref.NUM_WAVES[name]
+    rng = np.random.default_rng(77 + 100 * rp_id + 10 * ixyz + icoor)
+    mx, g = 1021, 2
+    n = mx + 2 * g
+    q, aux, cp = _pencils3(name, rng, n)
+    maux = 0 if aux is None else aux.shape[0]
+    auxo = np.zeros((1, n), order='F') if aux is None else aux
+    with_rpt = 1 if name in ('euler_3D', 'burgers_3D') else 0
+    z = lambda *shape: np.zeros(shape, order='F')
+    wo, so, amo, apo = z(M, W, n), z(W, n), z(M, n), z(M, n)
+    bo = [z(M, n) for _ in range(6)]
+    assert R.clawref_rp3(ixyz, icoor, M, W, maux, g, mx, _dp(q), _dp(auxo), _dp(wo), _dp(so), _dp(amo), _dp(apo),
+                         *[_dp(b) for b in bo], rp_id, _dp(cp), with_rpt) == 0
+    wd, sd, amd, apd = z(M, W, n - 1), z(W, n - 1), z(M, n - 1), z(M, n - 1)
+    bd = [z(M, n - 1) for _ in range(6)]
+    assert L.hostfun_rp3(rp_id, ixyz - 1, icoor, _dp(cp), len(cp) - 1, n - 1, maux, _dp(q), _dp(auxo), _dp(wd), _dp(sd),
+                         _dp(amd), _dp(apd), *[_dp(b) for b in bd], with_rpt) == 0
+    pairs = [(wd, wo[..., 1:], 'wave'), (sd, so[:, 1:], 's'), (amd, amo[:, 1:], 'amdq'), (apd, apo[:, 1:], 'apdq')]
+    if with_rpt:
+        names = ('bmasdq(amdq)', 'bpasdq(amdq)', 'bmasdq(apdq)', 'bpasdq(apdq)', 'cmbsasdq', 'cpbsasdq')
+        pairs += [(bd[k], bo[k][:, 1:], what) for k, what in enumerate(names)]
+    for a, b, what in pairs:
+        assert np.isfinite(b).all(), (name, what)
+        assert np.array_equal(a, b), (name, ixyz, icoor, what, float(np.max(np.abs(a - b))))
