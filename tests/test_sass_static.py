@@ -1,0 +1,60 @@
+"""Static guards on the compiled hot kernels (no GPU needed: cuobjdump on the in-tree objects, scripts/sass_mix.py).
+They pin the properties the measured numbers in profiles/ depend on, so that a source change which silently adds
+spills, drops the cp.async prefetch ring or bloats the march loop is caught on the CPU."""
+import os
+import shutil
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'scripts'))
+import sass_mix  # noqa: E402
+
+OBJ = os.path.join(ROOT, 'clawpack_b200', 'csrc', 'build', 'sweep_inst_fast.o')
+pytestmark = pytest.mark.skipif(shutil.which('cuobjdump') is None or not os.path.exists(OBJ),
+                                reason='needs cuobjdump and the built objects (python -c "import __graft_entry__ as g; g.build()")')
+
+
+@pytest.fixture(scope='module')
+def fast_kernels():
+    return sass_mix.kernels(OBJ)
+
+
+def _count(c, pred):
+    return sum(v for k, v in c.items() if pred(k))
+
+
+def test_headline_euler_kernel_shape(fast_kernels):
+    """sweep2_unsplit_ws<RpEuler4Wave2DT<3>,1,8,MC|spec|cp.async ring> (fast): the kernel bench.py times."""
+    names = [k for k in fast_kernels if 'sweep2_unsplit_wsINS0_15RpEuler4Wave2DTILi3ELi0EEELi1ELi8ELi71ELi1E' in k]
+    assert len(names) == 1, names
+    c = sass_mix.mix(fast_kernels[names[0]])
+    n = sum(c.values())
+    fp64 = _count(c, lambda k: k.split('.')[0] in ('DFMA', 'DMUL', 'DADD'))
+    assert _count(c, lambda k: k.split('.')[0] in ('LDL', 'STL')) == 0          # spill-free at 255 registers
+    assert _count(c, lambda k: k.startswith('LDGSTS')) >= 4                      # cp.async row prefetch ring
+    assert _count(c, lambda k: k.startswith('SHFL')) >= 90                       # neighbour exchange by shuffle
+    assert _count(c, lambda k: k.startswith('BAR')) <= 2                         # no barrier in the march loop
+    assert n <= 1800 and fp64 / n >= 0.49, (n, fp64)                             # measured build: 1744 / 870
+    assert _count(c, lambda k: k.startswith('MUFU.RCP64H') or k.startswith('MUFU.RSQ64H')) <= 32   # shared reciprocals
+
+
+def test_no_fast_sweep_kernel_of_the_baseline_configs_spills(fast_kernels):
+    """Default kernels of BASELINE configs 2/5 (Euler unsplit), 3 (shallow split) and 1 (acoustics split)."""
+    for pat in ('sweep2_unsplit_wsINS0_15RpEuler4Wave2DTILi3ELi0EEELi1ELi8ELi71ELi1E',
+                'sweep2_split_wsINS0_18RpShallowRoeEfix2DELi1ELi16ELi1ELi1ELi0E',
+                'sweep2_split_wsINS0_13RpAcoustics2D'):
+        names = [k for k in fast_kernels if pat in k]
+        assert names, pat
+        for k in names:
+            c = sass_mix.mix(fast_kernels[k])
+            assert _count(c, lambda x: x.split('.')[0] in ('LDL', 'STL')) == 0, k
+
+
+def test_specialised_split_kernel_is_smaller_than_the_generic_one(fast_kernels):
+    """Opt-in variant 53 (limiter as a template argument) against the generic shallow-water split kernel."""
+    gen = [k for k in fast_kernels if 'sweep2_split_wsINS0_18RpShallowRoeEfix2DELi1ELi16ELi1ELi1ELi0E' in k]
+    spec = [k for k in fast_kernels if 'sweep2_split_wsINS0_18RpShallowRoeEfix2DELi1ELi16ELi1ELi1ELi4E' in k]
+    assert len(gen) == 1 and len(spec) == 1
+    assert len(fast_kernels[spec[0]]) < 0.75 * len(fast_kernels[gen[0]])
