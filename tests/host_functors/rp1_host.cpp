@@ -3,16 +3,20 @@
 // every functor can be compared bit for bit with the oracle on a machine without a GPU (tests/test_host_functors.py).
 // Nothing in the product links this file.
 #define CLAW_HOST_CHECK 1
+#ifdef CLAW_HOST_FAST          // namespace fast: FMA contraction allowed, restructured divisions / square roots
+#define CLAW_NS fast
+#else
 #define CLAW_NS strict
 #define CLAW_STRICT 1
+#endif
 #include <cmath>
 #include <type_traits>
-using std::sqrt; using std::exp; using std::fabs; using std::copysign;
+using std::fma; using std::sqrt; using std::exp; using std::fabs; using std::copysign;
 #include "../../clawpack_b200/csrc/rp1.cuh"
 
 namespace {
 using namespace clawcuda;
-using namespace clawcuda::strict;
+using namespace clawcuda::CLAW_NS;
 
 template <class RP, class = void> struct AuxN { static constexpr int N = 0; };
 template <class RP> struct AuxN<RP, std::void_t<decltype(RP::MAUX)>> { static constexpr int N = RP::MAUX; };

@@ -2,16 +2,20 @@
 // by the host compiler with -DCLAW_HOST_CHECK -ffp-contract=off, for comparison with the oracle's rpn2 / rpt2
 // (tests/test_host_functors.py).  See rp2_host.cpp.  Nothing in the product links this file.
 #define CLAW_HOST_CHECK 1
+#ifdef CLAW_HOST_FAST          // namespace fast: FMA contraction allowed, restructured divisions / square roots
+#define CLAW_NS fast
+#else
 #define CLAW_NS strict
 #define CLAW_STRICT 1
+#endif
 #include <cmath>
 #include <cstddef>
-using std::sqrt; using std::exp; using std::fabs; using std::copysign; using std::llround;
+using std::fma; using std::sqrt; using std::exp; using std::fabs; using std::copysign; using std::llround;
 #include "../../clawpack_b200/csrc/rp2_aux.cuh"
 
 namespace {
 using namespace clawcuda;
-using namespace clawcuda::strict;
+using namespace clawcuda::CLAW_NS;
 
 template <int M> constexpr int rot(int m) { return (M >= 3 && m == 1) ? 2 : ((M >= 3 && m == 2) ? 1 : m); }   // sweep2.cuh:89
 

@@ -2,18 +2,23 @@
 // the host compiler with -DCLAW_HOST_CHECK -ffp-contract=off (strict mode's unfused IEEE arithmetic): normal() and the
 // two transverse() solves per interface, in the rotated frame the sweep kernels use, mapped back to the natural
 // component order for comparison with the oracle's rpn2 / rpt2 (tests/test_host_functors.py).  Nothing in the product
-// links this file.
+// links this file.  euler_4wave_2D is checked as RpEuler4Wave2DT<3> (per-cell quantities shared): the functor both the strict
+// kernels and the default fast kernel of bench.py instantiate.
 #define CLAW_HOST_CHECK 1
+#ifdef CLAW_HOST_FAST          // namespace fast: FMA contraction allowed, restructured divisions / square roots
+#define CLAW_NS fast
+#else
 #define CLAW_NS strict
 #define CLAW_STRICT 1
+#endif
 #include <cmath>
 #include <cstddef>
-using std::sqrt; using std::exp; using std::fabs; using std::copysign; using std::sin; using std::cos; using std::fmod;
+using std::fma; using std::sqrt; using std::exp; using std::fabs; using std::copysign; using std::sin; using std::cos; using std::fmod;
 #include "../../clawpack_b200/csrc/rp2.cuh"
 
 namespace {
 using namespace clawcuda;
-using namespace clawcuda::strict;
+using namespace clawcuda::CLAW_NS;
 
 template <int M> constexpr int rot(int m) { return (M >= 3 && m == 1) ? 2 : ((M >= 3 && m == 2) ? 1 : m); }   // sweep2.cuh:89
 
@@ -62,7 +67,7 @@ extern "C" int hostfun_rp2(int rp_id, int dir, const double* cparam, int ncparam
                            double* bp_b) {
 #define CASE(ID, RP) case ID: return run<RP>(dir, cparam, ncparam, n, q, wave, s, amdq, apdq, bm_a, bp_a, bm_b, bp_b);
   switch (rp_id) {
-    CASE(1, RpAdvection2D) CASE(2, RpAcoustics2D) CASE(3, RpEuler4Wave2D) CASE(4, RpShallowRoeEfix2D)
+    CASE(1, RpAdvection2D) CASE(2, RpAcoustics2D) CASE(3, RpEuler4Wave2DT<3>) CASE(4, RpShallowRoeEfix2D)
     CASE(9, RpEuler5Wave2D) CASE(11, RpEulerHlle2D) CASE(12, RpShallowHlle2D) CASE(16, RpBurgers2D) CASE(18, RpKpp2D)
   }
 #undef CASE

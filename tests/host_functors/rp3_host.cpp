@@ -4,16 +4,20 @@
 // for comparison with the oracle (tests/test_host_functors.py).  Which aux cells a transverse solve of the aux-reading
 // solvers sees is decided by the sweep kernel (flux3_side, sweep3.cuh) and is covered by the -m gpu tests.
 #define CLAW_HOST_CHECK 1
+#ifdef CLAW_HOST_FAST          // namespace fast: FMA contraction allowed, restructured divisions / square roots
+#define CLAW_NS fast
+#else
 #define CLAW_NS strict
 #define CLAW_STRICT 1
+#endif
 #include <cmath>
 #include <cstddef>
-using std::sqrt; using std::exp; using std::fabs; using std::copysign;
+using std::fma; using std::sqrt; using std::exp; using std::fabs; using std::copysign;
 #include "../../clawpack_b200/csrc/rp3.cuh"
 
 namespace {
 using namespace clawcuda;
-using namespace clawcuda::strict;
+using namespace clawcuda::CLAW_NS;
 
 template <class RP, int IXYZ, int ICOOR>
 int run(const double* cparam, int ncparam, int n, int maux, const double* q, const double* aux, double* wave, double* s,
