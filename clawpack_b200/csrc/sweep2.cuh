@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
   constexpr int LIM = SP ? (SPEC >> 4) : 0;
   using S = Smem2<RP, NT>;
   constexpr int TX = NT - 4;
-  extern __shared__ double smem[];
+  CLAW_DYN_SMEM(smem);
   const int t = threadIdx.x;
   double* const sq = smem + S::OFF_Q * NT + t;
   double* const sxw = smem + S::OFF_XW * NT + t;
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE;
   using S = Smem2<RP, NT>;
   constexpr int TX = NT - 4;
-  extern __shared__ double smem[];
+  CLAW_DYN_SMEM(smem);
   const int t = threadIdx.x;
   double* const sq = smem + S::OFF_Q * NT + t;
   double* const sxw = smem + S::OFF_XW * NT + t;

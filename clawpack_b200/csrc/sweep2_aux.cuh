@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(NW * 32) sweep2_unsplit_aux(const __grid_const
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE, MA = RP::MAUX, NT = NW * 32;
   using S = Smem2aux<RP, NW>;
   constexpr int TX = 28;
-  extern __shared__ double smem[];
+  CLAW_DYN_SMEM(smem);
   const int t = threadIdx.x, lane = t & 31;
   double* const syw = smem + S::OFF_YW * NT + t;
   double* const sya = smem + S::OFF_YA * NT + t;
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(NW * 32) sweep2_split_aux(const __grid_constan
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE, MA = RP::MAUX, NT = NW * 32;
   using S = Smem2aux<RP, NW>;
   constexpr int TX = 28;
-  extern __shared__ double smem[];
+  CLAW_DYN_SMEM(smem);
   const int t = threadIdx.x, lane = t & 31;
   double* const syw = smem + S::OFF_YW * NT + t;
   double* const sya = smem + S::OFF_YA * NT + t;

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
   constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
   using S = Smem2ws<RP, NW>;
   constexpr int TX = 28;                                   // owned columns per warp
-  extern __shared__ double smem[];
+  CLAW_DYN_SMEM(smem);
   const int t = threadIdx.x, lane = t & 31;
   double* const syw = smem + S::OFF_YW * NT + t;
   double* const sya = smem + S::OFF_YA * NT + t;
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
   constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
   using S = Smem2ws<RP, NW>;
   constexpr int TX = 28;
-  extern __shared__ double smem[];
+  CLAW_DYN_SMEM(smem);
   const int t = threadIdx.x, lane = t & 31;
   double* const syw = smem + S::OFF_YW * NT + t;
   double* const sya = smem + S::OFF_YA * NT + t;

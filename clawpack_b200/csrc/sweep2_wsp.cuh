@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(64, MINB) sweep2_unsplit_wsp(const __grid_cons
   constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
   using S = Smem2wsp<RP>;
   constexpr int TX = 28;
-  extern __shared__ double smem[];
+  CLAW_DYN_SMEM(smem);
   const int lane = threadIdx.x & 31;
   const bool roleY = threadIdx.x < 32;
   double* const syw = smem + S::OFF_YW * NT + lane;

@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
   constexpr int M = RP::MEQN, W = RP::MWAVES, MA = RP::MAUX > 0 ? RP::MAUX : 1, NC = RP::NCTX > 0 ? RP::NCTX : 1;
   constexpr int NT = 32 * BY;
   constexpr int TX = 28;
-  extern __shared__ double smem[];
+  CLAW_DYN_SMEM(smem);
   const int t = threadIdx.x, ty = threadIdx.y;
   const int tid = ty * 32 + t;
   double* const sm = smem + tid;
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
   constexpr int M = RP::MEQN, W = RP::MWAVES, MA = RP::MAUX > 0 ? RP::MAUX : 1, NC = RP::NCTX > 0 ? RP::NCTX : 1;
   constexpr int NT = BX * BY;
   constexpr int TD = (IXYZ == 1) ? 2 : 1;                    // array dimension carried by thread-y
-  extern __shared__ double smem[];
+  CLAW_DYN_SMEM(smem);
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int tid = ty * BX + tx;
   double* const sm = smem + tid;
