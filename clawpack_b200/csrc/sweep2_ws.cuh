@@ -21,6 +21,12 @@ __device__ __forceinline__ double shfl_right(double v) {         // value of lan
   return __shfl_down_sync(0xffffffffu, v, 1);
 }
 
+#ifdef CLAW_HOST_CHECK                      // kernel emulation (tests/host_functors/cuda_emul.h): the copy completes at once
+inline void cp_async8(double* smem_dst, const double* gsrc) { *smem_dst = *gsrc; }
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
+template <int LEVEL> inline void prefetch_row(const double*) {}
+#else
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
@@ -31,6 +37,7 @@ template <int LEVEL> __device__ __forceinline__ void prefetch_row(const double* 
   if constexpr (LEVEL == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(g));
   else asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
 }
+#endif
 
 template <class RP, int NW> struct Smem2ws {
   static constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE;
