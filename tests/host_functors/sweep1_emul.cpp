@@ -2,17 +2,21 @@
 // exchange of neighbouring interfaces, block-wide CFL reduction) executed on the CPU by the fiber emulation of
 // cuda_emul.h, behind an entry point with the argument list of claw_step1_host (csrc/clawcuda.cu) -- so that the kernel
 // plumbing around the functors (aux columns, f-wave branch, tile edges) can be compared with the oracle's step1 without a
-// GPU (tests/test_kernel_emulation.py).  Strict arithmetic (-ffp-contract=off).  Nothing in the product links this file.
+// GPU (tests/test_kernel_emulation.py).  Strict arithmetic (-ffp-contract=off), or namespace fast with -DCLAW_HOST_FAST.  Nothing in the product links this file.
 #define CLAW_HOST_CHECK 1
+#ifdef CLAW_HOST_FAST          // namespace fast: the kernels' fast-mode code paths (folded limiter, FMA contraction)
+#define CLAW_NS fast
+#else
 #define CLAW_NS strict
 #define CLAW_STRICT 1
+#endif
 #include "cuda_emul.h"
 using std::fma; using std::sqrt; using std::exp; using std::fabs; using std::copysign; using std::fmax;
 #include "../../clawpack_b200/csrc/rp1.cuh"
 #include "../../clawpack_b200/csrc/sweep1.cuh"
 
 using namespace clawcuda;
-using namespace clawcuda::strict;
+using namespace clawcuda::CLAW_NS;
 
 template <class RP> static void run1(const Sweep2Params& P) {
   constexpr int NT = 128;                                  // as launch1() in csrc/sweep1_inst.cu

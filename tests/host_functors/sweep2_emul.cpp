@@ -3,10 +3,14 @@
 // counterparts) executed on the CPU by the fiber emulation of cuda_emul.h, behind entry points with the semantics of
 // claw_step2_host / claw_step2ds_host (csrc/clawcuda.cu: AoS -> SoA planes, one launch over the whole grid in march
 // segments, region read-back).  `variant` selects the instantiation like CLAW_VARIANT does in csrc/sweep_inst.cu.
-// Strict arithmetic (-ffp-contract=off).  Nothing in the product links this file.
+// Strict arithmetic (-ffp-contract=off), or namespace fast with -DCLAW_HOST_FAST.  Nothing in the product links this file.
 #define CLAW_HOST_CHECK 1
+#ifdef CLAW_HOST_FAST          // namespace fast: the kernels' fast-mode code paths (folded limiter, FMA contraction)
+#define CLAW_NS fast
+#else
 #define CLAW_NS strict
 #define CLAW_STRICT 1
+#endif
 #include "cuda_emul.h"
 using std::fma; using std::sqrt; using std::exp; using std::fabs; using std::copysign; using std::fmax; using std::sin;
 using std::cos; using std::fmod; using std::llround;
@@ -16,7 +20,7 @@ using std::cos; using std::fmod; using std::llround;
 #include "../../clawpack_b200/csrc/sweep2_aux.cuh"
 
 using namespace clawcuda;
-using namespace clawcuda::strict;
+using namespace clawcuda::CLAW_NS;
 
 namespace {
 // the grid / segment logic of launch_kernel() in csrc/sweep_inst.cu (seg_hint > 0 as set by claw_set_tuning)
