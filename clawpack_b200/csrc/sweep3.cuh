@@ -353,12 +353,18 @@ template <int NT> __device__ __forceinline__ void block_max_cfl3(double cfl, uns
 
 // 8-byte asynchronous global -> shared copy (LDGSTS): prefetches the next march step's operands without
 // holding registers; the issuing thread reads its own slots after cp_async_wait_all()
+#ifdef CLAW_HOST_CHECK                      // kernel emulation (tests/host_functors/cuda_emul.h): the copy completes at once
+inline void cp_async8(double* smem_dst, const double* gsrc) { *smem_dst = *gsrc; }
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
+#else
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#endif
 
 __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }

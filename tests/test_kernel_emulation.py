@@ -206,3 +206,75 @@ def test_emulated_sweep2_kernels_bit_exact_vs_oracle(emul2lib, name):
         r.evolve_to_time()
     # (kpp_2D: sin / cos come from the same libm on both sides here, so the bits agree as well in strict mode)
     _check(solver, sol, r, emul2lib.mode)
+
+
+# ---- 3-D: sweep3_x and the march kernels (csrc/sweep3.cuh) ---------------------------------------------------------
+class EmulatedFmod3D(object):
+    """``fmod.step3`` / ``fmod.step3ds`` of ClawSolver3D backed by the emulated kernels (semantics of claw_step3_host /
+    claw_step3ds_host).  ``seg`` = cells per march segment."""
+
+    def __init__(self, lib, seg=0):
+        self.L, self.seg = lib, seg
+        i, d, vp = ctypes.c_int, ctypes.c_double, ctypes.c_void_p
+        ip, dp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
+        lib.emul_step3_host.argtypes = [i] * 6 + [vp, vp, vp, d, d, d, d, ip, ip, i, i, dp, i, i, dp]
+        lib.emul_step3_host.restype = i
+
+    def _call(self, idir, mx, my, mz, qold, qnew, aux, dx, dy, dz, dt, method, mthlim, rp):
+        assert qold.flags['F_CONTIGUOUS'] and qnew.flags['F_CONTIGUOUS']
+        aux = None if aux is None or aux.size == 0 else np.asfortranarray(aux, dtype=np.float64)
+        m = np.ascontiguousarray(method, dtype=np.intc)
+        ml = np.array(mthlim, dtype=np.intc)
+        cp = _cparam(rp)
+        cfl = ctypes.c_double(0.0)
+        rc = self.L.emul_step3_host(qold.shape[0], len(ml), 0 if aux is None else aux.shape[0], mx, my, mz,
+                                    qold.ctypes.data_as(ctypes.c_void_p), qnew.ctypes.data_as(ctypes.c_void_p),
+                                    ctypes.c_void_p(0) if aux is None else aux.ctypes.data_as(ctypes.c_void_p),
+                                    dx, dy, dz, dt, m.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                                    ml.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), idir, int(rp.rp_id),
+                                    cp.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(cp) - 1, self.seg,
+                                    ctypes.byref(cfl))
+        assert rc == 0, rc
+        return qnew, cfl.value
+
+    def step3(self, maxm, num_ghost, mx, my, mz, qold, qnew, aux, dx, dy, dz, dt, method, mthlim, aux1, aux2, aux3, work,
+              use_fwave, rpn3, rpt3, rptt3):
+        return self._call(0, mx, my, mz, qold, qnew, aux, dx, dy, dz, dt, method, mthlim, rpn3)
+
+    def step3ds(self, maxm, num_ghost, mx, my, mz, qold, qnew, aux, dx, dy, dz, dt, method, mthlim, aux1, aux2, aux3, work,
+                idir, use_fwave, rpn3, rpt3, rptt3):
+        return self._call(idir, mx, my, mz, qold, qnew, aux, dx, dy, dz, dt, method, mthlim, rpn3)
+
+
+@pytest.fixture(scope='module', params=['strict', 'fast'])
+def emul3lib(tmp_path_factory, request):
+    L = _compile(tmp_path_factory, 'sweep3_emul', request.param)
+    L.mode = request.param
+    return L
+
+
+# all of these kernels are proven on the GPU (tests/test_cuda_parity3d.py); here they make the emulation usable for the
+# 3-D kernel work of the next round.  (scenario, cells per march segment)
+CASES_3D = {
+    'acoustics_unsplit_22_aux': (lambda: S.acoustics_3d_general(mx=12, my=10, mz=9), 0),
+    'acoustics_unsplit_22_segments': (lambda: S.acoustics_3d_general(mx=9, my=14, mz=11), 4),
+    'acoustics_split': (lambda: S.acoustics_3d_general(mx=10, my=9, mz=8, dimensional_split=True), 0),
+    'euler_unsplit': (lambda: dict(S.euler_3d_shocktube(mx=6, my=7, mz=20), dimensional_split=False), 0),
+    'burgers_unsplit_11': (lambda: S.burgers_3d(mx=10, my=9, mz=8, transverse_waves=11), 0),
+    'vc_advection_unsplit_22': (lambda: S.advection_3d_variable(mx=9, my=8, mz=10), 0),
+}
+
+
+@pytest.mark.parametrize('name', sorted(CASES_3D))
+def test_emulated_sweep3_kernels_vs_oracle(emul3lib, name):
+    make, seg = CASES_3D[name]
+    sc = make()
+    claw = S.make_claw(sc, kernel_language='Fortran', fmod=EmulatedFmod3D(emul3lib, seg))
+    sol, solver = claw.solution, claw.solver
+    solver.setup(sol)
+    solver.dt = solver.dt_initial
+    r = ref_solver(sc, nthreads=2)
+    for _ in range(3):
+        solver.evolve_to_time(sol)
+        r.evolve_to_time()
+    _check(solver, sol, r, emul3lib.mode)
