@@ -76,13 +76,13 @@ __device__ __forceinline__ void wave_dots3(const double (*wave)[M], const double
   }
 }
 
-template <int M, int W>
+template <int M, int W, int LIM = 0>      // LIM > 0: every wave family uses limiter id LIM (known at compile time)
 __device__ __forceinline__ void limit_waves3(const int* mthlim, double (*wave)[M], const double* s,
                                              const double* wnorm2, const double* dotl, const double* dotr) {
   // limiter.f90:39-50
 #pragma unroll
   for (int mw = 0; mw < W; ++mw) {
-    const int meth = mthlim[mw];
+    const int meth = LIM ? LIM : mthlim[mw];
     if (meth == 0) continue;
     if (wave_is_zero(wnorm2[mw])) continue;
     const double wl = philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], meth);
@@ -116,13 +116,15 @@ __device__ __forceinline__ void second_order3(double dtd, const double (*wave)[M
 // Statement order follows flux3.f90:272-291 (rpt3), 296-344 (cqxx splits), 353-384 (c*2, rptt3),
 // 390-469 (gadd), 479-507 (b*, rptt3), 513-594 (hadd).
 // -------------------------------------------------------------------------------------------
-template <class RP, int IXYZ, int SIDE>
-__device__ __forceinline__ void flux3_side(const RpParams& P, int m3, int m4, double dtdx, double dty, double dtz,
+// M3C / M4C >= 0: method(3) = 10*M3C + M4C known at compile time (the run-time arguments are then ignored)
+template <class RP, int IXYZ, int SIDE, int M3C = -1, int M4C = -1>
+__device__ __forceinline__ void flux3_side(const RpParams& P, int m3_rt, int m4_rt, double dtdx, double dty, double dtz,
                                            const double* asdq, const double* cqxx, const double* ctx,
                                            const double (*A)[3][RP::MAUX > 0 ? RP::MAUX : 1],
                                            double (*g)[RP::template TV<IXYZ, 2>::N],
                                            double (*h)[RP::template TV<IXYZ, 3>::N]) {
   constexpr int M = RP::MEQN;
+  const int m3 = (M3C >= 0) ? M3C : m3_rt, m4 = (M4C >= 0) ? M4C : m4_rt;
   using TY = typename RP::template TV<IXYZ, 2>;            // non-zero components of y-like splits (G terms)
   using TZ = typename RP::template TV<IXYZ, 3>;            // ... of z-like splits (H terms)
   constexpr double SGN = (SIDE == 0) ? -1.0 : 1.0;        // cqxx enters the p-side with -, the m-side with +
@@ -222,7 +224,7 @@ template <class RP, int IXYZ> struct GH3 {
 };
 
 // Both sides of cell c, results to shared memory
-template <class RP, int IXYZ, int NT>
+template <class RP, int IXYZ, int NT, int M3C = -1, int M4C = -1>
 __device__ __forceinline__ void flux3_cell(const Sweep3Params& P, double dtdx, double dty, double dtz,
                                            const double* apdqC, const double* cqxxC, const double* ctxC,
                                            const double* amdqR, const double* cqxxR, const double* ctxR,
@@ -236,8 +238,8 @@ __device__ __forceinline__ void flux3_cell(const Sweep3Params& P, double dtdx, d
 #pragma unroll
     for (int k = 0; k < NH; ++k) h[e][k] = 0.0;
   }
-  flux3_side<RP, IXYZ, 0>(P.rp, P.m3, P.m4, dtdx, dty, dtz, apdqC, cqxxC, ctxC, A, g, h);   // iteration i = c
-  flux3_side<RP, IXYZ, 1>(P.rp, P.m3, P.m4, dtdx, dty, dtz, amdqR, cqxxR, ctxR, A, g, h);   // iteration i = c+1
+  flux3_side<RP, IXYZ, 0, M3C, M4C>(P.rp, P.m3, P.m4, dtdx, dty, dtz, apdqC, cqxxC, ctxC, A, g, h);   // iteration i = c
+  flux3_side<RP, IXYZ, 1, M3C, M4C>(P.rp, P.m3, P.m4, dtdx, dty, dtz, amdqR, cqxxR, ctxR, A, g, h);   // iteration i = c+1
 #pragma unroll
   for (int e = 0; e < 6; ++e) {
 #pragma unroll
@@ -385,8 +387,13 @@ template <class RP, int IXYZ, int NT> struct Smem3 {
 // x-sweep: block (32, BY); lanes <-> I (28 owner lanes + 2 halo lanes per side), thread-y <-> J,
 // march in K.   step3.f90:124-276 (unsplit) / step3ds.f90 idir = 1.
 // =====================================================================================
-template <class RP, int BY, int MINB = 1>
+// SPEC = 10*LIM + 1: the headline method set of BASELINE config 4 known at compile time -- unsplit, order 2,
+// method(3) = 22, limiter id LIM on every wave family -- so that the run-time method tests, the zero-initialised
+// dummies of the unused branches and the limiter switch disappear (what SPEC does for sweep2_unsplit_ws).
+template <class RP, int BY, int MINB = 1, int SPEC = 0>
 __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant__ Sweep3Params P) {
+  constexpr bool SP = (SPEC & 1) != 0;
+  constexpr int LIM = SP ? SPEC / 10 : 0, M3C = SP ? 2 : -1, M4C = SP ? 2 : -1;
   constexpr int M = RP::MEQN, W = RP::MWAVES, MA = RP::MAUX > 0 ? RP::MAUX : 1, NC = RP::NCTX > 0 ? RP::NCTX : 1;
   constexpr int NT = 32 * BY;
   constexpr int TX = 28;
@@ -396,7 +403,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
   double* const sm = smem + tid;
   double* const sred = smem + Smem3<RP, 0, NT>::OFF_RED;
 
-  const bool split = P.m3 < 0;
+  const bool split = SP ? false : (P.m3 < 0);
   const int nx = P.n[0] + 4, ny = P.n[1] + 4, nz = P.n[2] + 4;
   const int I = blockIdx.x * TX + t;
   const int Ic = I < nx ? I : nx - 1;
@@ -411,9 +418,9 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
   const int k0 = split ? kb : kb - 1, k1 = split ? ke - 1 : ke;     // pencil planes k0..k1
 
   const double dtdx = P.dtd[0], dtdy = P.dtd[1], dtdz = P.dtd[2];
-  const bool second = (P.order != 1);
-  const bool limit = second && (P.limit != 0);
-  const bool transverse = P.m3 > 0;
+  const bool second = SP ? true : (P.order != 1);
+  const bool limit = SP ? true : (second && (P.limit != 0));
+  const bool transverse = SP ? true : (P.m3 > 0);
 
   const bool owner_lane = (t >= 2 && t <= 29 && I < nx) || (blockIdx.x == 0 && t < 2);
   const bool interior_i = (I >= 2 && I <= P.n[0] + 1);
@@ -501,7 +508,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
         }
 #pragma unroll
         for (int mw = 0; mw < W; ++mw) dotl[mw] = shfl_up1(dotr[mw]);
-        limit_waves3<M, W>(P.mthlim, wave, s, wnorm2, dotl, dotr);
+        limit_waves3<M, W, LIM>(P.mthlim, wave, s, wnorm2, dotl, dotr);
       }
       second_order3<M, W>(dtdx, wave, s, cqxx);                                         // flux3.f90:231-259
     }
@@ -529,7 +536,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
       }
       continue;
     }
-    if (transverse) flux3_cell<RP, 0, NT>(P, dtdx, dtdy, dtdz, apdq, cqxx, ctx, amdqR, cqxxR, ctxR, A, sm);
+    if (transverse) flux3_cell<RP, 0, NT, M3C, M4C>(P, dtdx, dtdy, dtdz, apdq, cqxx, ctx, amdqR, cqxxR, ctxR, A, sm);
     __syncthreads();
     if (row_out) {
       if (transverse) {
@@ -564,8 +571,10 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
 // y-sweep (IXYZ = 1: march J, thread-y <-> K) and z-sweep (IXYZ = 2: march K, thread-y <-> J);
 // thread-x <-> I.   step3.f90:283-431 / 439-593, step3ds.f90 idir = 2 / 3.
 // =====================================================================================
-template <class RP, int IXYZ, int BX, int BY, int MINB = 1>
+template <class RP, int IXYZ, int BX, int BY, int MINB = 1, int SPEC = 0>      // SPEC: see sweep3_x
 __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_constant__ Sweep3Params P) {
+  constexpr bool SP = (SPEC & 1) != 0;
+  constexpr int LIM = SP ? SPEC / 10 : 0, M3C = SP ? 2 : -1, M4C = SP ? 2 : -1;
   constexpr int M = RP::MEQN, W = RP::MWAVES, MA = RP::MAUX > 0 ? RP::MAUX : 1, NC = RP::NCTX > 0 ? RP::NCTX : 1;
   constexpr int NT = BX * BY;
   constexpr int TD = (IXYZ == 1) ? 2 : 1;                    // array dimension carried by thread-y
@@ -577,7 +586,7 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
   using SM3 = Smem3<RP, IXYZ, NT>;
   double* const spf = smem + SM3::OFF_PF + tid;               // my prefetch slots: stage s, slot j at spf[(s*PF + j)*NT]
 
-  const bool split = P.m3 < 0;
+  const bool split = SP ? false : (P.m3 < 0);
   const int nx = P.n[0] + 4, nT = P.n[TD] + 4, nlen = P.n[IXYZ] + 4, mlen = P.n[IXYZ];
   const int HT = split ? 0 : 1;
   const int I = (split ? 0 : 1) + blockIdx.x * (BX - 2 * HT) + tx;
@@ -596,9 +605,9 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
   const int cb = c_lo + blockIdx.z * P.seg;
   const int ce = min(cb + P.seg, c_hi);
 
-  const bool second = (P.order != 1);
-  const bool limit = second && (P.limit != 0);
-  const bool transverse = P.m3 > 0;
+  const bool second = SP ? true : (P.order != 1);
+  const bool limit = SP ? true : (second && (P.limit != 0));
+  const bool transverse = SP ? true : (P.m3 > 0);
   const bool pencil = (I >= 1 && I <= P.n[0] + 2) &&
                       (IXYZ == 1 ? (T >= P.zlo && T <= P.zhi) : (T >= 1 && T <= P.n[TD] + 2));
   const bool out_thread = split ? (I < nx && T < nT)
@@ -640,7 +649,7 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
       for (int ma = 0; ma < SM3::MA; ++ma)
         cp_async8(st + (PFA + ma) * NT, P.aux + ma * P.plane + col + (long long)nc * strideN);
       const int c = n - 2;
-      if (c >= cb && c < ce && P.m3 > 0) {
+      if (c >= cb && c < ce && (SP || P.m3 > 0)) {
         // A[dy][dz]: y-sweep: dy <-> thread-y (K), dz <-> thread-x (I); z-sweep: dy <-> I, dz <-> J
         const int ti[3] = {Im, Ic, Ip};
         const int tt[3] = {Tm, Tc, Tp};
@@ -691,7 +700,7 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
       if (limit) {
         double wnorm2[W];
         wave_dots3<M, W>(waveP, waveN, wnorm2, dotn);
-        limit_waves3<M, W>(P.mthlim, waveP, sP, wnorm2, dotlP, dotn);
+        limit_waves3<M, W, LIM>(P.mthlim, waveP, sP, wnorm2, dotlP, dotn);
       }
       second_order3<M, W>(dtdn, waveP, sP, cqxxP);
     }
@@ -724,7 +733,7 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
 #pragma unroll
               for (int ma = 0; ma < MA; ++ma) A[dy][dz][ma] = st[(PFN + (dy * 3 + dz) * SM3::MA + ma) * NT];
         }
-        flux3_cell<RP, IXYZ, NT>(P, dtdn, dty, dtz, apdqC, cqxxC, ctxC, amdqP, cqxxP, ctxP, A, sm);
+        flux3_cell<RP, IXYZ, NT, M3C, M4C>(P, dtdn, dty, dtz, apdqC, cqxxC, ctxC, amdqP, cqxxP, ctxP, A, sm);
       }
       __syncthreads();
       if (out_thread) {

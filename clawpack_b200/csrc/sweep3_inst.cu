@@ -17,10 +17,10 @@ static int pick_seg(int len, long long tiles, int num_sms) {
   return seg < 1 ? 1 : seg;
 }
 
-template <class RP, int BY, int MINB>
+template <class RP, int BY, int MINB, int SPEC = 0>
 static cudaError_t launch_x(Sweep3Params& P, int num_sms, cudaStream_t st, LaunchInfo* info) {
   constexpr int NT = 32 * BY;
-  auto kern = sweep3_x<RP, BY, MINB>;
+  auto kern = sweep3_x<RP, BY, MINB, SPEC>;
   const int smem = (int)Smem3<RP, 0, NT>::BYTES;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
@@ -39,10 +39,10 @@ static cudaError_t launch_x(Sweep3Params& P, int num_sms, cudaStream_t st, Launc
   return cudaGetLastError();
 }
 
-template <class RP, int IXYZ, int BX, int BY, int MINB>
+template <class RP, int IXYZ, int BX, int BY, int MINB, int SPEC = 0>
 static cudaError_t launch_march(Sweep3Params& P, int num_sms, cudaStream_t st, LaunchInfo* info) {
   constexpr int NT = BX * BY;
-  auto kern = sweep3_march<RP, IXYZ, BX, BY, MINB>;
+  auto kern = sweep3_march<RP, IXYZ, BX, BY, MINB, SPEC>;
   const int smem = (int)Smem3<RP, IXYZ, NT>::BYTES;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
@@ -62,14 +62,21 @@ static cudaError_t launch_march(Sweep3Params& P, int num_sms, cudaStream_t st, L
   return cudaGetLastError();
 }
 
-template <class RP, int BY, int MINB>
+template <class RP, int BY, int MINB, int SPEC = 0>
 static cudaError_t launch_dir(int dir, Sweep3Params& P, int num_sms, cudaStream_t st, LaunchInfo* info) {
   switch (dir) {
-    case 0: return launch_x<RP, BY, MINB>(P, num_sms, st, info);
-    case 1: return launch_march<RP, 1, 32, BY, MINB>(P, num_sms, st, info);
-    case 2: return launch_march<RP, 2, 32, BY, MINB>(P, num_sms, st, info);
+    case 0: return launch_x<RP, BY, MINB, SPEC>(P, num_sms, st, info);
+    case 1: return launch_march<RP, 1, 32, BY, MINB, SPEC>(P, num_sms, st, info);
+    case 2: return launch_march<RP, 2, 32, BY, MINB, SPEC>(P, num_sms, st, info);
   }
   return cudaErrorInvalidValue;
+}
+
+// unsplit, order 2, method(3) = 22, every wave family limited with limiter id `lim`
+template <int W> static bool headline_method3(const Sweep3Params& P, int lim) {
+  if (P.order == 1 || P.m3 != 2 || P.m4 != 2 || !P.limit) return false;
+  for (int mw = 0; mw < W; ++mw) if (P.mthlim[mw] != lim) return false;
+  return true;
 }
 
 // dir: 0 = x-sweep, 1 = y-sweep, 2 = z-sweep
@@ -79,6 +86,8 @@ cudaError_t launch_sweep3(int rp_id, int dir, Sweep3Params& P, int num_sms, cuda
     case 5:
       if (variant == 2) return launch_dir<RpVcAcoustics3D, 8, 2>(dir, P, num_sms, st, info);
       if (variant == 3) return launch_dir<RpVcAcoustics3D, 16, 1>(dir, P, num_sms, st, info);
+      if (variant == 5 && headline_method3<2>(P, 4))          // method set known at compile time (round-2 experiment)
+        return launch_dir<RpVcAcoustics3D, 8, 1, 41>(dir, P, num_sms, st, info);
       return launch_dir<RpVcAcoustics3D, 8, 1>(dir, P, num_sms, st, info);
     case 6: return launch_dir<RpEuler3D, 8, 1>(dir, P, num_sms, st, info);
     case 15: return launch_dir<RpBurgers3D, 8, 1>(dir, P, num_sms, st, info);

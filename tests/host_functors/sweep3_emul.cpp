@@ -23,7 +23,7 @@ namespace {
 int pick_seg(int len, int seg_hint) { int s = seg_hint > 0 ? seg_hint : len; if (s > len) s = len; return s < 1 ? 1 : s; }
 
 // grids of launch_x / launch_march in csrc/sweep3_inst.cu (the segment length is a test parameter here)
-template <class RP> void pass_x(Sweep3Params& P, int seg_hint) {
+template <class RP, int SPEC = 0> void pass_x(Sweep3Params& P, int seg_hint) {
   constexpr int BY = 8;
   const bool split = P.m3 < 0;
   const int nx = P.n[0] + 4, ny = P.n[1] + 4, nz = P.n[2] + 4;
@@ -35,9 +35,9 @@ template <class RP> void pass_x(Sweep3Params& P, int seg_hint) {
   grid.z = (len + P.seg - 1) / P.seg;
   block.x = 32; block.y = BY;
   const Sweep3Params Pc = P;
-  emul::launch(grid, block, [&]() { sweep3_x<RP, BY, 1>(Pc); });
+  emul::launch(grid, block, [&]() { sweep3_x<RP, BY, 1, SPEC>(Pc); });
 }
-template <class RP, int IXYZ> void pass_march(Sweep3Params& P, int seg_hint) {
+template <class RP, int IXYZ, int SPEC = 0> void pass_march(Sweep3Params& P, int seg_hint) {
   constexpr int BX = 32, BY = 8, TD = (IXYZ == 1) ? 2 : 1;
   const bool split = P.m3 < 0;
   const int nx = P.n[0] + 4, nT = P.n[TD] + 4, nlen = P.n[IXYZ] + 4;
@@ -49,16 +49,23 @@ template <class RP, int IXYZ> void pass_march(Sweep3Params& P, int seg_hint) {
   grid.z = (len + P.seg - 1) / P.seg;
   block.x = BX; block.y = BY;
   const Sweep3Params Pc = P;
-  emul::launch(grid, block, [&]() { sweep3_march<RP, IXYZ, BX, BY, 1>(Pc); });
+  emul::launch(grid, block, [&]() { sweep3_march<RP, IXYZ, BX, BY, 1, SPEC>(Pc); });
 }
-template <class RP> void pass(int dir, Sweep3Params& P, int seg_hint) {
-  if (dir == 0) pass_x<RP>(P, seg_hint);
-  else if (dir == 1) pass_march<RP, 1>(P, seg_hint);
-  else pass_march<RP, 2>(P, seg_hint);
+template <class RP, int SPEC = 0> void pass(int dir, Sweep3Params& P, int seg_hint) {
+  if (dir == 0) pass_x<RP, SPEC>(P, seg_hint);
+  else if (dir == 1) pass_march<RP, 1, SPEC>(P, seg_hint);
+  else pass_march<RP, 2, SPEC>(P, seg_hint);
 }
-int run_pass(int rp_id, int dir, Sweep3Params& P, int seg_hint) {
+bool headline3(const Sweep3Params& P, int W, int lim) {              // headline_method3() of csrc/sweep3_inst.cu
+  if (P.order == 1 || P.m3 != 2 || P.m4 != 2 || !P.limit) return false;
+  for (int mw = 0; mw < W; ++mw) if (P.mthlim[mw] != lim) return false;
+  return true;
+}
+int run_pass(int rp_id, int dir, Sweep3Params& P, int seg_hint, int variant) {
   switch (rp_id) {
-    case 5: pass<RpVcAcoustics3D>(dir, P, seg_hint); return 0;
+    case 5:
+      if (variant == 5 && headline3(P, 2, 4)) { pass<RpVcAcoustics3D, 41>(dir, P, seg_hint); return 0; }
+      pass<RpVcAcoustics3D>(dir, P, seg_hint); return 0;
     case 6: pass<RpEuler3D>(dir, P, seg_hint); return 0;
     case 15: pass<RpBurgers3D>(dir, P, seg_hint); return 0;
     case 17: pass<RpVcAdvection3D>(dir, P, seg_hint); return 0;
@@ -71,7 +78,7 @@ int run_pass(int rp_id, int dir, Sweep3Params& P, int seg_hint) {
 extern "C" int emul_step3_host(int meqn, int mwaves, int maux, int mx, int my, int mz, const double* qold, double* qnew,
                                const double* auxbc, double dx, double dy, double dz, double dt, const int* method7,
                                const int* mthlim, int idir, int rp_id, const double* cparam, int ncparam, int seg_hint,
-                               double* cfl) {
+                               int variant, double* cfl) {
   const int nx = mx + 4, ny = my + 4, nz = mz + 4, pitch = nx + 1;
   const long long kstride = (long long)pitch * ny, plane = kstride * nz;
   auto to_soa = [&](const double* aos, int nc, std::vector<double>& soa) {
@@ -104,13 +111,13 @@ extern "C" int emul_step3_host(int meqn, int mwaves, int maux, int mx, int my, i
     if (method7[2] < 0) return 41;
     for (int dir = 0; dir < 3; ++dir) {
       Sweep3Params P = params(dir == 0, src.data(), dst.data());
-      if (int rc = run_pass(rp_id, dir, P, seg_hint)) return rc;
+      if (int rc = run_pass(rp_id, dir, P, seg_hint, variant)) return rc;
     }
     i0 = j0 = k0 = 2; i1 = 2 + mx; j1 = 2 + my; k1 = 2 + mz;       // get_interior
   } else {                                                         // claw_step3ds_host: one pass, get_all
     if (method7[2] >= 0) return 41;
     Sweep3Params P = params(1, src.data(), dst.data());
-    if (int rc = run_pass(rp_id, idir - 1, P, seg_hint)) return rc;
+    if (int rc = run_pass(rp_id, idir - 1, P, seg_hint, variant)) return rc;
   }
   for (int k = k0; k < k1; ++k) for (int j = j0; j < j1; ++j) for (int i = i0; i < i1; ++i) for (int m = 0; m < meqn; ++m)
     qnew[m + (size_t)meqn * (i + (size_t)nx * (j + (size_t)ny * k))] = dst[m * plane + k * kstride + (long long)j * pitch + i];

@@ -213,11 +213,11 @@ class EmulatedFmod3D(object):
     """``fmod.step3`` / ``fmod.step3ds`` of ClawSolver3D backed by the emulated kernels (semantics of claw_step3_host /
     claw_step3ds_host).  ``seg`` = cells per march segment."""
 
-    def __init__(self, lib, seg=0):
-        self.L, self.seg = lib, seg
+    def __init__(self, lib, seg=0, variant=0):
+        self.L, self.seg, self.variant = lib, seg, variant
         i, d, vp = ctypes.c_int, ctypes.c_double, ctypes.c_void_p
         ip, dp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
-        lib.emul_step3_host.argtypes = [i] * 6 + [vp, vp, vp, d, d, d, d, ip, ip, i, i, dp, i, i, dp]
+        lib.emul_step3_host.argtypes = [i] * 6 + [vp, vp, vp, d, d, d, d, ip, ip, i, i, dp, i, i, i, dp]
         lib.emul_step3_host.restype = i
 
     def _call(self, idir, mx, my, mz, qold, qnew, aux, dx, dy, dz, dt, method, mthlim, rp):
@@ -233,7 +233,7 @@ class EmulatedFmod3D(object):
                                     dx, dy, dz, dt, m.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
                                     ml.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), idir, int(rp.rp_id),
                                     cp.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(cp) - 1, self.seg,
-                                    ctypes.byref(cfl))
+                                    self.variant, ctypes.byref(cfl))
         assert rc == 0, rc
         return qnew, cfl.value
 
@@ -254,22 +254,26 @@ def emul3lib(tmp_path_factory, request):
 
 
 # all of these kernels are proven on the GPU (tests/test_cuda_parity3d.py); here they make the emulation usable for the
-# 3-D kernel work of the next round.  (scenario, cells per march segment)
+# 3-D kernel work of the next round.  (scenario, cells per march segment, CLAW_VARIANT3)
 CASES_3D = {
-    'acoustics_unsplit_22_aux': (lambda: S.acoustics_3d_general(mx=12, my=10, mz=9), 0),
-    'acoustics_unsplit_22_segments': (lambda: S.acoustics_3d_general(mx=9, my=14, mz=11), 4),
-    'acoustics_split': (lambda: S.acoustics_3d_general(mx=10, my=9, mz=8, dimensional_split=True), 0),
-    'euler_unsplit': (lambda: dict(S.euler_3d_shocktube(mx=6, my=7, mz=20), dimensional_split=False), 0),
-    'burgers_unsplit_11': (lambda: S.burgers_3d(mx=10, my=9, mz=8, transverse_waves=11), 0),
-    'vc_advection_unsplit_22': (lambda: S.advection_3d_variable(mx=9, my=8, mz=10), 0),
+    'acoustics_unsplit_22_aux': (lambda: S.acoustics_3d_general(mx=12, my=10, mz=9), 0, 0),
+    'acoustics_unsplit_22_segments': (lambda: S.acoustics_3d_general(mx=9, my=14, mz=11), 4, 0),
+    'acoustics_split': (lambda: S.acoustics_3d_general(mx=10, my=9, mz=8, dimensional_split=True), 0, 0),
+    'euler_unsplit': (lambda: dict(S.euler_3d_shocktube(mx=6, my=7, mz=20), dimensional_split=False), 0, 0),
+    'burgers_unsplit_11': (lambda: S.burgers_3d(mx=10, my=9, mz=8, transverse_waves=11), 0, 0),
+    'vc_advection_unsplit_22': (lambda: S.advection_3d_variable(mx=9, my=8, mz=10), 0, 0),
+    # not yet run on a GPU: method set (22, order 2, MC) as template arguments (CLAW_VARIANT3=5)
+    'acoustics_unsplit_22_spec_variant5': (lambda: dict(S.acoustics_3d_general(mx=12, my=10, mz=9), limiters=S.MC), 0, 5),
+    'acoustics_unsplit_22_spec_variant5_segments': (lambda: dict(S.acoustics_3d_general(mx=9, my=14, mz=11), limiters=S.MC), 4, 5),
+    'acoustics_reference_example_spec_variant5': (lambda: S.acoustics_3d(mx=10, my=10, mz=10), 0, 5),
 }
 
 
 @pytest.mark.parametrize('name', sorted(CASES_3D))
 def test_emulated_sweep3_kernels_vs_oracle(emul3lib, name):
-    make, seg = CASES_3D[name]
+    make, seg, variant = CASES_3D[name]
     sc = make()
-    claw = S.make_claw(sc, kernel_language='Fortran', fmod=EmulatedFmod3D(emul3lib, seg))
+    claw = S.make_claw(sc, kernel_language='Fortran', fmod=EmulatedFmod3D(emul3lib, seg, variant))
     sol, solver = claw.solution, claw.solver
     solver.setup(sol)
     solver.dt = solver.dt_initial
