@@ -58,3 +58,22 @@ def test_specialised_split_kernel_is_smaller_than_the_generic_one(fast_kernels):
     spec = [k for k in fast_kernels if 'sweep2_split_wsINS0_18RpShallowRoeEfix2DELi1ELi16ELi1ELi1ELi4E' in k]
     assert len(gen) == 1 and len(spec) == 1
     assert len(fast_kernels[spec[0]]) < 0.75 * len(fast_kernels[gen[0]])
+
+
+def test_specialised_3d_kernels_are_smaller_and_spill_free():
+    """Opt-in CLAW_VARIANT3=5 (method set as template arguments) against the generic vc_acoustics_3D kernels."""
+    obj = os.path.join(ROOT, 'clawpack_b200', 'csrc', 'build', 'sweep3_inst_fast.o')
+    if not os.path.exists(obj):
+        pytest.skip('sweep3_inst_fast.o not built')
+    k = sass_mix.kernels(obj)
+    for gen, spec in (('sweep3_xINS0_15RpVcAcoustics3DELi8ELi1ELi0E', 'sweep3_xINS0_15RpVcAcoustics3DELi8ELi1ELi41E'),
+                      ('sweep3_marchINS0_15RpVcAcoustics3DELi1ELi32ELi8ELi1ELi0E',
+                       'sweep3_marchINS0_15RpVcAcoustics3DELi1ELi32ELi8ELi1ELi41E'),
+                      ('sweep3_marchINS0_15RpVcAcoustics3DELi2ELi32ELi8ELi1ELi0E',
+                       'sweep3_marchINS0_15RpVcAcoustics3DELi2ELi32ELi8ELi1ELi41E')):
+        g = [n for n in k if gen in n]
+        s = [n for n in k if spec in n]
+        assert len(g) == 1 and len(s) == 1, (gen, g, s)
+        assert len(k[s[0]]) < 0.82 * len(k[g[0]]), (gen, len(k[g[0]]), len(k[s[0]]))
+        c = sass_mix.mix(k[s[0]])
+        assert _count(c, lambda x: x.split('.')[0] in ('LDL', 'STL')) == 0, spec
