@@ -282,3 +282,42 @@ def test_emulated_sweep3_kernels_vs_oracle(emul3lib, name):
         solver.evolve_to_time(sol)
         r.evolve_to_time()
     _check(solver, sol, r, emul3lib.mode)
+
+
+# ---- edge sizes: grids smaller than a tile, tile-edge widths, one- to three-row march segments ---------------------
+def _agree(sc, fmod, nsteps):
+    claw = S.make_claw(sc, kernel_language='Fortran', fmod=fmod)
+    sol, solver = claw.solution, claw.solver
+    solver.setup(sol)
+    solver.dt = solver.dt_initial
+    r = ref_solver(sc)
+    for _ in range(nsteps):
+        solver.evolve_to_time(sol)
+        r.evolve_to_time()
+    return solver.step_log == r.step_log and np.array_equal(sol.state.q, r.q)
+
+
+def test_emulated_kernels_edge_sizes(tmp_path_factory):
+    """A sample of the size sweep run during development (424 cases, all bit-exact): 1 x 1 grids, widths 27 / 28 / 29
+    around the 28-column strip, 120 / 124 / 125 cells around the 124-cell 1-D tile, march segments of 1-3 rows, the
+    compile-time variants on degenerate grids."""
+    l1 = EmulatedFmod1D(_compile(tmp_path_factory, 'sweep1_emul'))
+    l2 = _compile(tmp_path_factory, 'sweep2_emul')
+    l3 = _compile(tmp_path_factory, 'sweep3_emul')
+    bad = []
+    for mx in (1, 2, 4, 120, 124, 125, 249):
+        for make in (lambda: S.sill_1d(mx=mx), lambda: S.traffic_vc_1d(mx=mx, kind='tracer')):
+            if not _agree(make(), l1, 4):
+                bad.append(('1d', make()['rp'], mx))
+    for mx, my, seg in ((1, 1, 0), (2, 3, 1), (27, 2, 2), (28, 9, 3), (29, 1, 1), (57, 3, 2)):
+        for make, variant in ((lambda: S.shock_bubble(mx=mx, my=my), 0),
+                              (lambda: dict(S.radial_dam_break(mx=mx, my=my), limiters=S.MC), 53),
+                              (lambda: S.elasticity_2d(mx=mx, my=my), 0)):
+            if not _agree(make(), EmulatedFmod2D(l2, variant, seg), 2):
+                bad.append(('2d', make()['rp'], mx, my, seg, variant))
+    for (mx, my, mz), seg, variant in (((1, 1, 1), 0, 0), ((1, 1, 1), 0, 5), ((29, 2, 3), 1, 5), ((3, 7, 2), 3, 0),
+                                       ((5, 6, 13), 3, 5)):
+        sc = dict(S.acoustics_3d_general(mx=mx, my=my, mz=mz), limiters=S.MC)
+        if not _agree(sc, EmulatedFmod3D(l3, seg, variant), 2):
+            bad.append(('3d', mx, my, mz, seg, variant))
+    assert not bad, bad
