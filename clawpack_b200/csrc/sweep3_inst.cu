@@ -88,6 +88,10 @@ cudaError_t launch_sweep3(int rp_id, int dir, Sweep3Params& P, int num_sms, cuda
       if (variant == 3) return launch_dir<RpVcAcoustics3D, 16, 1>(dir, P, num_sms, st, info);
       if (variant == 5 && headline_method3<2>(P, 4))          // method set known at compile time (round-2 experiment)
         return launch_dir<RpVcAcoustics3D, 8, 1, 41>(dir, P, num_sms, st, info);
+      if (variant == 6 && headline_method3<2>(P, 4)) {        // the same, x-sweep as two 32x6 CTAs per SM (168 registers, no spills)
+        if (dir == 0) return launch_x<RpVcAcoustics3D, 6, 2, 41>(P, num_sms, st, info);
+        return launch_dir<RpVcAcoustics3D, 8, 1, 41>(dir, P, num_sms, st, info);
+      }
       return launch_dir<RpVcAcoustics3D, 8, 1>(dir, P, num_sms, st, info);
     case 6: return launch_dir<RpEuler3D, 8, 1>(dir, P, num_sms, st, info);
     case 15: return launch_dir<RpBurgers3D, 8, 1>(dir, P, num_sms, st, info);

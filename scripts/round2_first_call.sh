@@ -23,4 +23,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 CLAW_VARIANT=53 python -m pytest tests -q -m gpu -k "shallow or dam" > $out/${tag}_pytest_gpu_variant53.log 2>&1; tail -2 $out/${tag}_pytest_gpu_variant53.log
 # 3-D: method set as template arguments (CLAW_VARIANT3=5) -- parity on the hardware, then timing against the generic kernels
 CLAW_VARIANT3=5 python -m pytest tests/test_cuda_parity3d.py -q -m gpu > $out/${tag}_pytest_gpu_variant3_5.log 2>&1; tail -2 $out/${tag}_pytest_gpu_variant3_5.log
-for v in 0 5; do CLAW_VARIANT3=$v python scripts/bench_configs.py --configs c4s >> $out/${tag}_c4_variants.jsonl 2>>$out/${tag}_bench.err; done
+for v in 0 5 6; do CLAW_VARIANT3=$v python scripts/bench_configs.py --configs c4s >> $out/${tag}_c4_variants.jsonl 2>>$out/${tag}_bench.err; done

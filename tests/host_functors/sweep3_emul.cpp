@@ -23,8 +23,7 @@ namespace {
 int pick_seg(int len, int seg_hint) { int s = seg_hint > 0 ? seg_hint : len; if (s > len) s = len; return s < 1 ? 1 : s; }
 
 // grids of launch_x / launch_march in csrc/sweep3_inst.cu (the segment length is a test parameter here)
-template <class RP, int SPEC = 0> void pass_x(Sweep3Params& P, int seg_hint) {
-  constexpr int BY = 8;
+template <class RP, int SPEC = 0, int BY = 8> void pass_x(Sweep3Params& P, int seg_hint) {
   const bool split = P.m3 < 0;
   const int nx = P.n[0] + 4, ny = P.n[1] + 4, nz = P.n[2] + 4;
   const int len = split ? nz : P.n[2];
@@ -65,6 +64,10 @@ int run_pass(int rp_id, int dir, Sweep3Params& P, int seg_hint, int variant) {
   switch (rp_id) {
     case 5:
       if (variant == 5 && headline3(P, 2, 4)) { pass<RpVcAcoustics3D, 41>(dir, P, seg_hint); return 0; }
+      if (variant == 6 && headline3(P, 2, 4)) {                      // x-sweep with 32 x 6 tiles
+        if (dir == 0) pass_x<RpVcAcoustics3D, 41, 6>(P, seg_hint); else pass<RpVcAcoustics3D, 41>(dir, P, seg_hint);
+        return 0;
+      }
       pass<RpVcAcoustics3D>(dir, P, seg_hint); return 0;
     case 6: pass<RpEuler3D>(dir, P, seg_hint); return 0;
     case 15: pass<RpBurgers3D>(dir, P, seg_hint); return 0;

@@ -266,6 +266,7 @@ CASES_3D = {
     'acoustics_unsplit_22_spec_variant5': (lambda: dict(S.acoustics_3d_general(mx=12, my=10, mz=9), limiters=S.MC), 0, 5),
     'acoustics_unsplit_22_spec_variant5_segments': (lambda: dict(S.acoustics_3d_general(mx=9, my=14, mz=11), limiters=S.MC), 4, 5),
     'acoustics_reference_example_spec_variant5': (lambda: S.acoustics_3d(mx=10, my=10, mz=10), 0, 5),
+    'acoustics_unsplit_22_spec_variant6_x_tiles_32x6': (lambda: dict(S.acoustics_3d_general(mx=30, my=11, mz=7), limiters=S.MC), 3, 6),
 }
 
 
