@@ -114,7 +114,12 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
   switch (rp_id) {
     case 1: return launch_one<RpAdvection2D, 128>(kind, P, seg_hint, num_sms, st, info);
     case 2:
-      if (kind == 1) return launch_split_ws<RpAcoustics2D, 1, 16>(P, seg_hint, num_sms, st, info);
+      if (kind == 1) {
+        static const int variant = getenv("CLAW_VARIANT") ? atoi(getenv("CLAW_VARIANT")) : 0;   // tuning experiments
+        if (variant == 53 && split_method<2>(P, 4))            // BASELINE config 1: MC limiter as a template argument
+          return launch_split_ws<RpAcoustics2D, 1, 16, 1, 1, 4>(P, seg_hint, num_sms, st, info);
+        return launch_split_ws<RpAcoustics2D, 1, 16>(P, seg_hint, num_sms, st, info);
+      }
       return launch_ws<RpAcoustics2D, 1, 16, 6>(P, seg_hint, num_sms, st, info);          // generic methods + cp.async ring
     case 3: {
       static const int variant = getenv("CLAW_VARIANT") ? atoi(getenv("CLAW_VARIANT")) : 0;   // tuning experiments

@@ -53,7 +53,12 @@ template <class RP> void aux_k(int kind, Sweep2Params& P, int seg) {
 
 int run(int rp_id, int kind, int variant, Sweep2Params& P, int seg) {
   switch (rp_id) {
-    case 2: kind ? split_ws<RpAcoustics2D>(P, seg) : unsplit_ws<RpAcoustics2D>(P, seg); return 0;
+    case 2:
+      if (kind == 1 && variant == 53 && all_limiters<2>(P, 4)) {
+        launch(sweep2_split_ws<RpAcoustics2D, 1, 1, 1, 1, 4>, 32, !P.do_y, P, seg);
+        return 0;
+      }
+      kind ? split_ws<RpAcoustics2D>(P, seg) : unsplit_ws<RpAcoustics2D>(P, seg); return 0;
     case 3:
       if (kind == 0 && P.mtrans == 2 && all_limiters<4>(P, 4) && variant != 9) {      // the headline kernel of bench.py
         launch(sweep2_unsplit_ws<RpEuler4Wave2DT<3>, 1, 1, (4 << 4) | 1 | 6, 1>, 32, false, P, seg);
