@@ -141,6 +141,8 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
       if (kind == 0 && variant == 31) return launch_one<RpEuler4Wave2D, 64, 6>(kind, P, seg_hint, num_sms, st, info);
       if (kind == 0) return launch_ws<RpEuler4Wave2D, 1, 8, 6>(P, seg_hint, num_sms, st, info);
       if (variant == 30) return launch_one<RpEuler4Wave2D, 128>(kind, P, seg_hint, num_sms, st, info);
+      if (variant == 53 && split_method<4>(P, 4))             // MC limiter as a template argument
+        return launch_split_ws<RpEuler4Wave2D, 1, 8, 1, 1, 4>(P, seg_hint, num_sms, st, info);
       return launch_split_ws<RpEuler4Wave2D, 1, 8>(P, seg_hint, num_sms, st, info);
     }
     case 4: {

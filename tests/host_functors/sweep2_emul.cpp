@@ -64,6 +64,10 @@ int run(int rp_id, int kind, int variant, Sweep2Params& P, int seg) {
         launch(sweep2_unsplit_ws<RpEuler4Wave2DT<3>, 1, 1, (4 << 4) | 1 | 6, 1>, 32, false, P, seg);
         return 0;
       }
+      if (kind == 1 && variant == 53 && all_limiters<4>(P, 4)) {
+        launch(sweep2_split_ws<RpEuler4Wave2D, 1, 1, 1, 1, 4>, 32, !P.do_y, P, seg);
+        return 0;
+      }
       kind ? split_ws<RpEuler4Wave2D>(P, seg) : unsplit_ws<RpEuler4Wave2D>(P, seg); return 0;
     case 4:
       if (kind == 1 && (variant == 53 || variant == 54) && all_limiters<3>(P, 4)) {     // limiter as a template argument

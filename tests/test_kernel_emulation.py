@@ -181,6 +181,8 @@ CASES_2D = {
     'shallow_split_variant53_segments': (lambda: dict(S.radial_dam_break(mx=61, my=33), limiters=S.MC), 53, 9),
     'shallow_split_variant53_falls_back': (lambda: S.radial_dam_break(mx=30, my=30), 53, 0),     # not MC: generic kernel
     'acoustics_split_limiter_template_variant53': (lambda: S.acoustics_2d(mx=40, my=36), 53, 8),     # BASELINE config 1
+    'euler_split_limiter_template_variant53': (lambda: dict(S.quadrants(mx=40, my=30), limiters=S.MC), 53, 7),
+    'euler_split_generic': (lambda: S.quadrants(mx=40, my=30), 0, 7),
     'kpp_split': (lambda: S.kpp_2d(mx=40, my=40), 0, 0),
     'kpp_unsplit_notrans': (lambda: dict(S.kpp_2d(mx=33, my=29), dimensional_split=False, transverse_waves=0,
                                          cfl_max=0.5, cfl_desired=0.45), 0, 8),
