@@ -302,7 +302,7 @@ def _agree(sc, fmod, nsteps):
 
 
 def test_emulated_kernels_edge_sizes(tmp_path_factory):
-    """A sample of the size sweep run during development (424 cases, all bit-exact): 1 x 1 grids, widths 27 / 28 / 29
+    """A sample of the size sweeps run during development (640 cases incl. variant 53 of the three split kernels, all bit-exact): 1 x 1 grids, widths 27 / 28 / 29
     around the 28-column strip, 120 / 124 / 125 cells around the 124-cell 1-D tile, march segments of 1-3 rows, the
     compile-time variants on degenerate grids."""
     l1 = EmulatedFmod1D(_compile(tmp_path_factory, 'sweep1_emul'))
