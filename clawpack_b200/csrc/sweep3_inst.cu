@@ -81,14 +81,13 @@ template <int W> static bool headline_method3(const Sweep3Params& P, int lim) {
 
 // dir: 0 = x-sweep, 1 = y-sweep, 2 = z-sweep
 cudaError_t launch_sweep3(int rp_id, int dir, Sweep3Params& P, int num_sms, cudaStream_t st, LaunchInfo* info) {
-  static const int variant = getenv("CLAW_VARIANT3") ? atoi(getenv("CLAW_VARIANT3")) : 0;   // tuning experiments
+  static const int variant = getenv("CLAW_VARIANT3") ? atoi(getenv("CLAW_VARIANT3")) : 0;   // 1: generic kernels only (A/B timing, tests)
   switch (rp_id) {
     case 5:
-      if (variant == 2) return launch_dir<RpVcAcoustics3D, 8, 2>(dir, P, num_sms, st, info);
-      if (variant == 3) return launch_dir<RpVcAcoustics3D, 16, 1>(dir, P, num_sms, st, info);
-      if (variant == 5 && headline_method3<2>(P, 4))          // method set known at compile time (round-2 experiment)
-        return launch_dir<RpVcAcoustics3D, 8, 1, 41>(dir, P, num_sms, st, info);
-      if (variant == 6 && headline_method3<2>(P, 4)) {        // the same, x-sweep as two 32x6 CTAs per SM (168 registers, no spills)
+      // Method set as template arguments when it is the BASELINE config-4 set (unsplit, order 2, method(3) = 22, MC on
+      // every wave), x-sweep as two 32x6 CTAs per SM (168 registers, no spills).  Measured on B200 at 512^3
+      // (profiles/r02_b_c4_variants.jsonl): 49.6 ms generic -> 35.4 ms specialised -> 32.4 ms with the 32x6 x-sweep.
+      if (variant != 1 && headline_method3<2>(P, 4)) {
         if (dir == 0) return launch_x<RpVcAcoustics3D, 6, 2, 41>(P, num_sms, st, info);
         return launch_dir<RpVcAcoustics3D, 8, 1, 41>(dir, P, num_sms, st, info);
       }

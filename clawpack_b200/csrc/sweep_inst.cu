@@ -4,7 +4,6 @@
 #include <cstdlib>
 #include "launch.h"
 #include "sweep2_ws.cuh"
-#include "sweep2_wsp.cuh"
 #include "sweep2_aux.cuh"
 #include "rp2_aux.cuh"
 
@@ -56,13 +55,6 @@ static cudaError_t launch_one(int kind, Sweep2Params& P, int seg_hint, int num_s
   return launch_kernel(kern, NT, (int)S::BYTES, (kind == 1) && !P.do_y, P, seg_hint, num_sms, st, info);
 }
 
-// unsplit kernel specialised at compile time for the headline method set (see sweep2.cuh)
-template <class RP, int NT, int MINB, int SPEC>
-static cudaError_t launch_spec(Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
-  using S = Smem2<RP, NT>;
-  return launch_kernel(sweep2_unsplit<RP, NT, MINB, SPEC>, NT, (int)S::BYTES, false, P, seg_hint, num_sms, st, info);
-}
-
 // warp-synchronous unsplit kernel (sweep2_ws.cuh): NW independent 28-column strips per CTA
 template <class RP, int NW, int MINB, int SPEC, int UNR = 1>
 static cudaError_t launch_ws(Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
@@ -77,13 +69,6 @@ static cudaError_t launch_split_ws(Sweep2Params& P, int seg_hint, int num_sms, c
   using S = Smem2ws<RP, NW>;
   return launch_kernel(sweep2_split_ws<RP, NW, MINB, PF, UNR, LIM>, NW * 32, (int)S::BYTES, !P.do_y, P, seg_hint, num_sms, st, info,
                        NW * 28);
-}
-
-// warp-specialised unsplit kernel for the headline method set (sweep2_wsp.cuh): a pair of warps per 28-column strip
-template <class RP, int MINB, int LIM>
-static cudaError_t launch_wsp(Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
-  using S = Smem2wsp<RP>;
-  return launch_kernel(sweep2_unsplit_wsp<RP, MINB, LIM>, 64, (int)S::BYTES, false, P, seg_hint, num_sms, st, info, 28);
 }
 
 // aux-reading solvers (sweep2_aux.cuh): warp-synchronous, NW strips per CTA
@@ -115,63 +100,37 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
     case 1: return launch_one<RpAdvection2D, 128>(kind, P, seg_hint, num_sms, st, info);
     case 2:
       if (kind == 1) {
-        static const int variant = getenv("CLAW_VARIANT") ? atoi(getenv("CLAW_VARIANT")) : 0;   // tuning experiments
-        if (variant == 53 && split_method<2>(P, 4))            // BASELINE config 1: MC limiter as a template argument
+        static const int variant = getenv("CLAW_VARIANT") ? atoi(getenv("CLAW_VARIANT")) : 0;   // 1: generic kernels only (A/B timing)
+        if (variant != 1 && split_method<2>(P, 4))             // BASELINE config 1: MC limiter as a template argument
           return launch_split_ws<RpAcoustics2D, 1, 16, 1, 1, 4>(P, seg_hint, num_sms, st, info);
         return launch_split_ws<RpAcoustics2D, 1, 16>(P, seg_hint, num_sms, st, info);
       }
       return launch_ws<RpAcoustics2D, 1, 16, 6>(P, seg_hint, num_sms, st, info);          // generic methods + cp.async ring
     case 3: {
-      static const int variant = getenv("CLAW_VARIANT") ? atoi(getenv("CLAW_VARIANT")) : 0;   // tuning experiments
+      static const int variant = getenv("CLAW_VARIANT") ? atoi(getenv("CLAW_VARIANT")) : 0;   // 1: generic kernels only (A/B timing)
       if (kind == 0 && headline_method<4>(P, 4)) {
         constexpr int MC = 4 << 4;
-        switch (variant) {
-          case 0: return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);   // fastest measured (profiles/r01_h)
-          case 21: return launch_ws<RpEuler4Wave2D, 1, 12, MC | 1>(P, seg_hint, num_sms, st, info);    // the r01_g default
-          case 3: return launch_ws<RpEuler4Wave2D, 1, 12, MC | 1 | 6>(P, seg_hint, num_sms, st, info);   // cp.async ring
-          case 7: return launch_ws<RpEuler4Wave2D, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
-          case 14: return launch_ws<RpEuler4Wave2D, 1, 8, MC | 1 | 6 | 8>(P, seg_hint, num_sms, st, info);   // branch-free limiter
-          case 16: return launch_ws<RpEuler4Wave2DT<0, 1>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);  // branch-free efix
-          case 40: return launch_wsp<RpEuler4Wave2DT<3>, 6, 4>(P, seg_hint, num_sms, st, info);   // warp pair per strip, 168 registers: 5.21 ms (profiles/r01_j)
-          case 50: return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6, 2>(P, seg_hint, num_sms, st, info);   // march loop unrolled x2 (round-2 experiment)
-          case 15: return launch_spec<RpEuler4Wave2D, 64, 6, MC | 1>(P, seg_hint, num_sms, st, info);
-          default: break;     // 9: the generic kernel
-        }
+        // fastest measured: spill-free 8 warps/SM, per-cell Roe data, cp.async row ring (profiles/r01_h, r01_i).
+        // Measured and dropped: 12/16 warps with spills, L1/L2 prefetch hints, branch-free limiter / entropy fix, a warp
+        // pair per strip (5.21 ms, profiles/r01_j), the march loop unrolled x2 (5.15 ms, profiles/r02_a_variants.jsonl).
+        if (variant != 1) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
       }
-      if (kind == 0 && variant == 31) return launch_one<RpEuler4Wave2D, 64, 6>(kind, P, seg_hint, num_sms, st, info);
       if (kind == 0) return launch_ws<RpEuler4Wave2D, 1, 8, 6>(P, seg_hint, num_sms, st, info);
-      if (variant == 30) return launch_one<RpEuler4Wave2D, 128>(kind, P, seg_hint, num_sms, st, info);
-      if (variant == 53 && split_method<4>(P, 4))             // MC limiter as a template argument
+      if (variant != 1 && split_method<4>(P, 4))              // MC limiter as a template argument
         return launch_split_ws<RpEuler4Wave2D, 1, 8, 1, 1, 4>(P, seg_hint, num_sms, st, info);
       return launch_split_ws<RpEuler4Wave2D, 1, 8>(P, seg_hint, num_sms, st, info);
     }
     case 4: {
-      static const int variant = getenv("CLAW_VARIANT") ? atoi(getenv("CLAW_VARIANT")) : 0;   // tuning experiments
-      if (variant == 2) return launch_one<RpShallowRoeEfix2D, 128, 2>(kind, P, seg_hint, num_sms, st, info);
-      if (variant == 3) return launch_one<RpShallowRoeEfix2D, 128, 3>(kind, P, seg_hint, num_sms, st, info);
-      if (variant == 4) return launch_one<RpShallowRoeEfix2D, 128, 4>(kind, P, seg_hint, num_sms, st, info);
-      if (variant == 5) return launch_one<RpShallowRoeEfix2D, 64, 6>(kind, P, seg_hint, num_sms, st, info);
-      if (variant == 6) return launch_one<RpShallowRoeEfix2D, 64, 8>(kind, P, seg_hint, num_sms, st, info);
+      static const int variant = getenv("CLAW_VARIANT") ? atoi(getenv("CLAW_VARIANT")) : 0;   // 1: generic kernels only (A/B timing)
       if (kind == 1) {
-        switch (variant) {
-          case 0: return launch_split_ws<RpShallowRoeEfix2D, 1, 16>(P, seg_hint, num_sms, st, info);   // 9.5 ms at 16384^2
-          case 7: return launch_split_ws<RpShallowRoeEfix2D, 1, 12>(P, seg_hint, num_sms, st, info);   // 10.3
-          case 8: return launch_split_ws<RpShallowRoeEfix2D, 1, 8>(P, seg_hint, num_sms, st, info);
-          case 9: return launch_split_ws<RpShallowRoeEfix2D, 1, 12, 0>(P, seg_hint, num_sms, st, info);
-          case 10: return launch_split_ws<RpShallowRoeEfix2D, 2, 6>(P, seg_hint, num_sms, st, info);
-          case 51: return launch_split_ws<RpShallowRoeEfix2D, 1, 16, 1, 2>(P, seg_hint, num_sms, st, info);   // march loop unrolled x2 (round-2 experiment)
-          case 52: return launch_split_ws<RpShallowRoeEfix2D, 1, 12, 1, 2>(P, seg_hint, num_sms, st, info);   // the same with 168 registers
-          case 53: case 54:                                  // limiter known at compile time (MC on all waves, order 2)
-            if (split_method<3>(P, 4)) {
-              if (variant == 53) return launch_split_ws<RpShallowRoeEfix2D, 1, 16, 1, 1, 4>(P, seg_hint, num_sms, st, info);
-              return launch_split_ws<RpShallowRoeEfix2D, 1, 12, 1, 2, 4>(P, seg_hint, num_sms, st, info);
-            }
-            break;
-          default: break;       // 1: the block kernel
-        }
+        // Limiter known at compile time (MC on all waves, order 2: BASELINE config 3).  Measured on B200 at 16384^2
+        // (profiles/r02_a_c3_variants.jsonl): generic 9.48 ms, specialised 8.97 ms; the march loop unrolled x2 was
+        // slower in every combination (11.4 / 11.3 / 9.65 ms) and is gone.
+        if (variant != 1 && split_method<3>(P, 4))
+          return launch_split_ws<RpShallowRoeEfix2D, 1, 16, 1, 1, 4>(P, seg_hint, num_sms, st, info);
+        return launch_split_ws<RpShallowRoeEfix2D, 1, 16>(P, seg_hint, num_sms, st, info);
       }
-      if (kind == 0 && variant == 0) return launch_ws<RpShallowRoeEfix2D, 1, 12, 6>(P, seg_hint, num_sms, st, info);
-      return launch_one<RpShallowRoeEfix2D, 128>(kind, P, seg_hint, num_sms, st, info);
+      return launch_ws<RpShallowRoeEfix2D, 1, 12, 6>(P, seg_hint, num_sms, st, info);
     }
     case 9:
       if (kind == 1) return launch_split_ws<RpEuler5Wave2D, 1, 8>(P, seg_hint, num_sms, st, info);

@@ -7,6 +7,8 @@
 #define FMA(d, a, b, c) asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(d) : "d"(a), "d"(b), "d"(c))
 #define MUL(d, a, b) asm volatile("mul.rn.f64 %0, %1, %2;" : "=d"(d) : "d"(a), "d"(b))
 #define ADD(d, a, b) asm volatile("add.rn.f64 %0, %1, %2;" : "=d"(d) : "d"(a), "d"(b))
+#define MULF(d, a, b) asm volatile("fma.rn.f64 %0, %1, %2, 0d8000000000000000;" : "=d"(d) : "d"(a), "d"(b))
+#define ADDF(d, a, b) asm volatile("fma.rn.f64 %0, %1, 0d3FF0000000000000, %2;" : "=d"(d) : "d"(a), "d"(b))
 
 template <int MODE>
 __global__ void probe(double* out, int iters, double seed) {
@@ -30,6 +32,20 @@ __global__ void probe(double* out, int iters, double seed) {
                        asm volatile("xor.b32 %0, %0, %1;" : "+r"(n[k]) : "r"(i)); }
       if (MODE == 10) FMA(a[0], a[0], x[k], y[k]);              // ONE dependent chain: latency
       if (MODE == 11) { if (k < 4) FMA(a[k], a[k], x[k], y[k]); else MUL(a[k], a[k], x[k]); }   // 4 DFMA then 4 DMUL
+      // round 2: is the mixing penalty a property of the OPCODE?  DMUL as DFMA(a, x, -RZ), DADD as DFMA(a, 1.0, y):
+      // bit-identical results (x*y + -0.0 == x*y, a*1 + y == a + y in round-to-nearest), one opcode on the pipe.
+      if (MODE == 12) { if (k & 1) MULF(a[k], a[k], x[k]); else FMA(a[k], a[k], x[k], y[k]); }
+      if (MODE == 13) { if (k % 3 == 0) FMA(a[k], a[k], x[k], y[k]); else if (k % 3 == 1) MULF(a[k], a[k], x[k]); else ADDF(a[k], a[k], y[k]); }
+      // the headline kernel's own mix (456 DFMA : 275 DMUL : 139 DADD per 870): 4 : 3 : 1 of every 8
+      if (MODE == 14) { if (k < 4) FMA(a[k], a[k], x[k], y[k]); else if (k < 7) MUL(a[k], a[k], x[k]); else ADD(a[k], a[k], y[k]); }
+      if (MODE == 15) { if (k < 4) FMA(a[k], a[k], x[k], y[k]); else if (k < 7) MULF(a[k], a[k], x[k]); else ADDF(a[k], a[k], y[k]); }
+      if (MODE == 16) { if (k & 1) ADD(a[k], a[k], y[k]); else FMA(a[k], a[k], x[k], y[k]); }   // DFMA / DADD alternating
+      if (MODE == 17) { if (k & 1) ADD(a[k], a[k], y[k]); else MUL(a[k], a[k], x[k]); }         // DMUL / DADD alternating
+      if (MODE == 18) { FMA(a[k], a[k], x[k], y[k]);                                              // 1 DSETP per 4 DFMA
+                        if ((k & 3) == 3) asm volatile("{.reg .pred p; setp.gt.f64 p, %1, %2; selp.b32 %0, %0, %3, p;}" : "+r"(n[k]) : "d"(a[k]), "d"(x[k]), "r"(i)); }
+      if (MODE == 19) { FMA(a[k], a[k], x[k], y[k]); if (k & 1) asm volatile("xor.b32 %0, %0, %1;" : "+r"(n[k]) : "r"(i)); }  // 1 ALU per 2 DFMA
+      if (MODE == 20) { FMA(a[k], a[k], x[k], y[k]);                                              // 1 SHFL per 4 DFMA
+                        if ((k & 3) == 3) asm volatile("shfl.sync.up.b32 %0, %0, 1, 0, 0xffffffff;" : "+r"(n[k])); }
     }
   }
   double s = 0;
@@ -69,7 +85,24 @@ void run(const char* name, int threads, int blocks_per_sm) {
   cudaFree(d);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 1) {                       // round-2 probes only
+    for (int bps : {2, 4}) {
+      run<1>("DFMA (distinct regs)", 128, bps);
+      run<5>("DFMA/DMUL alternating", 128, bps);
+      run<12>("DFMA/DMUL-as-DFMA alternating", 128, bps);
+      run<7>("DFMA/DMUL/DADD round-robin", 128, bps);
+      run<13>("the same, all as DFMA", 128, bps);
+      run<14>("kernel mix 4 DFMA:3 DMUL:1 DADD", 128, bps);
+      run<15>("kernel mix, all as DFMA", 128, bps);
+      run<16>("DFMA/DADD alternating", 128, bps);
+      run<17>("DMUL/DADD alternating", 128, bps);
+      run<18>("4 DFMA + 1 DSETP+SEL", 128, bps);
+      run<19>("2 DFMA + 1 ALU", 128, bps);
+      run<20>("4 DFMA + 1 SHFL", 128, bps);
+    }
+    return 0;
+  }
   for (int bps : {1, 2, 3}) {
     run<7>("DFMA/DMUL/DADD round-robin", 128, bps);
     run<8>("DFMA + 1 ALU op each", 128, bps);

@@ -176,7 +176,7 @@ CASES_2D = {
     'shallow_split_generic': (lambda: S.radial_dam_break(mx=50, my=50), 0, 0),
     'acoustics_split': (lambda: S.acoustics_2d(mx=40, my=36), 0, 16),
     'vc_acoustics_aux_unsplit': (lambda: S.acoustics_2d_variable(mx=30, my=30), 0, 0),
-    # not yet run on a GPU
+    # limiter as a template argument (the default for MC since round 2; selected here by the emulation's variant 53)
     'shallow_split_limiter_template_variant53': (lambda: dict(S.radial_dam_break(mx=50, my=50), limiters=S.MC), 53, 0),
     'shallow_split_variant53_segments': (lambda: dict(S.radial_dam_break(mx=61, my=33), limiters=S.MC), 53, 9),
     'shallow_split_variant53_falls_back': (lambda: S.radial_dam_break(mx=30, my=30), 53, 0),     # not MC: generic kernel
@@ -265,7 +265,8 @@ CASES_3D = {
     'euler_unsplit': (lambda: dict(S.euler_3d_shocktube(mx=6, my=7, mz=20), dimensional_split=False), 0, 0),
     'burgers_unsplit_11': (lambda: S.burgers_3d(mx=10, my=9, mz=8, transverse_waves=11), 0, 0),
     'vc_advection_unsplit_22': (lambda: S.advection_3d_variable(mx=9, my=8, mz=10), 0, 0),
-    # not yet run on a GPU: method set (22, order 2, MC) as template arguments (CLAW_VARIANT3=5)
+    # method set (22, order 2, MC) as template arguments: the default for BASELINE config 4 since round 2 (selected here
+    # by the emulation's variants 5 / 6)
     'acoustics_unsplit_22_spec_variant5': (lambda: dict(S.acoustics_3d_general(mx=12, my=10, mz=9), limiters=S.MC), 0, 5),
     'acoustics_unsplit_22_spec_variant5_segments': (lambda: dict(S.acoustics_3d_general(mx=9, my=14, mz=11), limiters=S.MC), 4, 5),
     'acoustics_reference_example_spec_variant5': (lambda: S.acoustics_3d(mx=10, my=10, mz=10), 0, 5),

@@ -43,7 +43,7 @@ def test_headline_euler_kernel_shape(fast_kernels):
 def test_no_fast_sweep_kernel_of_the_baseline_configs_spills(fast_kernels):
     """Default kernels of BASELINE configs 2/5 (Euler unsplit), 3 (shallow split) and 1 (acoustics split)."""
     for pat in ('sweep2_unsplit_wsINS0_15RpEuler4Wave2DTILi3ELi0EEELi1ELi8ELi71ELi1E',
-                'sweep2_split_wsINS0_18RpShallowRoeEfix2DELi1ELi16ELi1ELi1ELi0E',
+                'sweep2_split_wsINS0_18RpShallowRoeEfix2DELi1ELi16ELi1ELi1ELi4E',
                 'sweep2_split_wsINS0_13RpAcoustics2D'):
         names = [k for k in fast_kernels if pat in k]
         assert names, pat
@@ -53,7 +53,7 @@ def test_no_fast_sweep_kernel_of_the_baseline_configs_spills(fast_kernels):
 
 
 def test_specialised_split_kernel_is_smaller_than_the_generic_one(fast_kernels):
-    """Opt-in variant 53 (limiter as a template argument) against the generic shallow-water split kernel."""
+    """The default kernel of BASELINE config 3 (limiter as a template argument) against the generic shallow-water split kernel."""
     gen = [k for k in fast_kernels if 'sweep2_split_wsINS0_18RpShallowRoeEfix2DELi1ELi16ELi1ELi1ELi0E' in k]
     spec = [k for k in fast_kernels if 'sweep2_split_wsINS0_18RpShallowRoeEfix2DELi1ELi16ELi1ELi1ELi4E' in k]
     assert len(gen) == 1 and len(spec) == 1
@@ -61,7 +61,7 @@ def test_specialised_split_kernel_is_smaller_than_the_generic_one(fast_kernels):
 
 
 def test_specialised_3d_kernels_are_smaller_and_spill_free():
-    """Opt-in CLAW_VARIANT3=5 (method set as template arguments) against the generic vc_acoustics_3D kernels."""
+    """The default kernels of BASELINE config 4 (method set as template arguments) against the generic vc_acoustics_3D kernels."""
     obj = os.path.join(ROOT, 'clawpack_b200', 'csrc', 'build', 'sweep3_inst_fast.o')
     if not os.path.exists(obj):
         pytest.skip('sweep3_inst_fast.o not built')
