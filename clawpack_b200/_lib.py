@@ -49,6 +49,12 @@ def _declare(L):
         'claw_accept': (i, [H]),
         'claw_reject': (i, [H]),
         'claw_sync': (i, [H]),
+        'claw_ctl_begin': (i, [H, vp, d, i, ctypes.c_longlong]),
+        'claw_ctl_attempts': (i, [H, c_double_p, i, i]),
+        'claw_ctl_sweep': (i, [H, c_double_p, i]),
+        'claw_ctl_end': (i, [H]),
+        'claw_ctl_read': (i, [H, vp, ctypes.c_longlong, vp, i, c_int_p]),
+        'claw_ctl_use_graph': (i, [H, i]),
         'claw_halo_elems': (i, [H, ctypes.POINTER(sz)]),
         'claw_halo_pack': (i, [H, i, vp]),
         'claw_halo_unpack': (i, [H, i, vp]),

@@ -66,6 +66,18 @@ struct claw_solver {
   uint64_t launches = 0;
   LaunchInfo last_launch{};
   std::string err;
+  // device-resident step control (claw_ctl_*): attempts queued since the last claw_ctl_read; the device's `cur` is
+  // authoritative while ctl_mode is set and h->cur mirrors it at every read
+  bool ctl_mode = false;
+  bool ctl_pending = false;
+  double* h_ctl = nullptr;   // pinned mirror of the control block + log ring
+  // one step attempt captured as a CUDA graph (single-rank runs): ghost fill + sweep(s) + control kernel
+  cudaGraphExec_t graph = nullptr;
+  cudaStream_t s_cap = nullptr;
+  uint64_t cfg_epoch = 0, graph_epoch = 0;
+  double graph_delta[3] = {0, 0, 0};
+  int graph_fill = -1;
+  int use_graph = 1;
 };
 
 namespace {
@@ -89,7 +101,11 @@ int fail(claw_solver* h, int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                       \
   } while (0)
 
-constexpr int WORK_HDR = 8;  // doubles reserved at the start of `work` (CFL slot)
+// Header of the `work` buffer: the step-control block (StepCtl, 32 words; word 0 = the CFL slot) followed by the
+// log ring of the attempted steps, three doubles (dt, cfl, accepted) per attempt.
+constexpr int CTL_WORDS = 32;
+constexpr int LOG_CAP = 4096;
+constexpr int WORK_HDR = CTL_WORDS + 3 * LOG_CAP;
 
 // ---------------------------------------------------------------------------------------
 // layout conversion: host/staging AoS (m fastest, Fortran order) <-> device SoA planes
@@ -154,16 +170,29 @@ __device__ __forceinline__ void bc_fill_pair(double* base, long long stride, int
   }
 }
 
-__global__ void bc_x2(double* q, int ncomp, int mx, int ny, int pitch, long long plane, int lo_type, int up_type,
+// Which array a ghost-fill / halo kernel works on: a fixed pointer, or -- under a StepCtl -- the buffer that is current
+// (role 0) or alternate (role 1) when the kernel RUNS; null once the step loop has ended (the kernel is a no-op).
+struct ArrSel { double* q[3]; const StepCtl* ctl; int role; };
+__device__ __forceinline__ double* sel_array(const ArrSel& a) {
+  if (a.ctl == nullptr) return a.q[0];
+  if (a.ctl->done) return nullptr;
+  return ctl_buffer(a.ctl, a.q, a.role);
+}
+
+__global__ void bc_x2(ArrSel sel, int ncomp, int mx, int ny, int pitch, long long plane, int lo_type, int up_type,
                       int lo_on, int up_on, int reflect) {
+  double* q = sel_array(sel);
+  if (q == nullptr) return;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= ny * ncomp) return;
   const int j = idx % ny, m = idx / ny;
   bc_fill_pair(q + m * plane + (long long)j * pitch, 1, mx, lo_type, up_type, lo_on != 0, up_on != 0, m == reflect);
 }
 
-__global__ void bc_y2(double* q, int ncomp, int nx, int my, int pitch, long long plane, int lo_type, int up_type,
+__global__ void bc_y2(ArrSel sel, int ncomp, int nx, int my, int pitch, long long plane, int lo_type, int up_type,
                       int lo_on, int up_on, int reflect) {
+  double* q = sel_array(sel);
+  if (q == nullptr) return;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nx * ncomp) return;
   const int i = idx % nx, m = idx / nx;
@@ -171,7 +200,9 @@ __global__ void bc_y2(double* q, int ncomp, int nx, int my, int pitch, long long
 }
 
 // halo rows [j0, j0+2) x all columns x all components <-> contiguous buffer
-__global__ void halo_pack2(const double* q, double* buf, int ncomp, int nx, int j0, int pitch, long long plane) {
+__global__ void halo_pack2(ArrSel sel, double* buf, int ncomp, int nx, int j0, int pitch, long long plane) {
+  const double* q = sel_array(sel);
+  if (q == nullptr) return;
   const long long n = (long long)ncomp * 2 * nx;
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(k % nx);
@@ -180,7 +211,9 @@ __global__ void halo_pack2(const double* q, double* buf, int ncomp, int nx, int 
     buf[k] = q[m * plane + (long long)(j0 + r) * pitch + i];
   }
 }
-__global__ void halo_unpack2(double* q, const double* buf, int ncomp, int nx, int j0, int pitch, long long plane) {
+__global__ void halo_unpack2(ArrSel sel, const double* buf, int ncomp, int nx, int j0, int pitch, long long plane) {
+  double* q = sel_array(sel);
+  if (q == nullptr) return;
   const long long n = (long long)ncomp * 2 * nx;
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(k % nx);
@@ -193,9 +226,11 @@ __global__ void halo_unpack2(double* q, const double* buf, int ncomp, int nx, in
 // 3-D ghost fill of one dimension: one thread per (component, a, b) where a, b run over the FULL
 // extent (ghosts included) of the other two dimensions, so edges/corners are the composition
 // x-then-y-then-z of the numpy slicing (solver.py:377-437).
-__global__ void bc_dim3(double* q, int ncomp, int n_d, long long stride_d, int ext_a, long long stride_a, int ext_b,
+__global__ void bc_dim3(ArrSel sel, int ncomp, int n_d, long long stride_d, int ext_a, long long stride_a, int ext_b,
                         long long stride_b, long long plane, int lo_type, int up_type, int lo_on, int up_on,
                         int reflect) {
+  double* q = sel_array(sel);
+  if (q == nullptr) return;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long per = (long long)ext_a * ext_b;
   if (idx >= per * ncomp) return;
@@ -205,12 +240,18 @@ __global__ void bc_dim3(double* q, int ncomp, int n_d, long long stride_d, int e
 }
 
 // ncomp runs of `len` contiguous doubles <-> one contiguous buffer (3-D halo planes)
-__global__ void gather_runs(const double* src, long long src_stride, double* dst, long long len, int ncomp) {
+__global__ void gather_runs(ArrSel sel, long long off, long long src_stride, double* dst, long long len, int ncomp) {
+  const double* src = sel_array(sel);
+  if (src == nullptr) return;
+  src += off;
   const long long n = len * ncomp;
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
     dst[k] = src[(k / len) * src_stride + (k % len)];
 }
-__global__ void scatter_runs(double* dst, long long dst_stride, const double* src, long long len, int ncomp) {
+__global__ void scatter_runs(ArrSel sel, long long off, long long dst_stride, const double* src, long long len, int ncomp) {
+  double* dst = sel_array(sel);
+  if (dst == nullptr) return;
+  dst += off;
   const long long n = len * ncomp;
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
     dst[(k / len) * dst_stride + (k % len)] = src[k];
@@ -236,6 +277,95 @@ __global__ void dfma_probe(double* out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Device-resident step control: Solver.evolve_to_time / get_dt / accept_reject_step
+// (pyclaw/src/pyclaw/solver.py:524-666) as two single-thread kernels around the sweeps of an attempt.  The
+// arithmetic is the reference's, operation by operation, in round-to-nearest fp64 without contraction, so that dt, t
+// and the accept/reject decisions carry the same bits as the host loop's.
+// ---------------------------------------------------------------------------------------
+__device__ void ctl_pre_step(StepCtl& c) {
+  // get_dt (solver.py:531-552) with the CFL number of the previous attempt ...
+  const double cfl = c.cfl_cached;
+  if (c.dt_variable && c.have_dt_old) {
+    if (cfl > 0.0) {
+      const double x = __ddiv_rn(__dmul_rn(c.dt, c.cfl_desired), cfl);     // get_dt_new (:526-529)
+      c.dt = (x < c.dt_max) ? x : c.dt_max;
+      if (!(c.dtmin < c.dt)) c.dtmin = c.dt;
+      if (!(c.dtmax > c.dt)) c.dtmax = c.dt;
+    } else {
+      c.dt = c.dt_max;
+    }
+  } else {
+    c.have_dt_old = 1;                                                     // self.dt_old = self.dt
+  }
+  if (!c.take_one) {
+    if (__dadd_rn(c.t, c.dt) > c.tend && c.tstart < c.tend) c.dt = __dsub_rn(c.tend, c.t);
+    if (__dsub_rn(__dsub_rn(c.tend, c.t), c.dt) < __dmul_rn(1.e-14, c.t)) c.dt = __dsub_rn(c.tend, c.t);
+  }
+  c.told = c.t;
+  c.cfl_bits = 0ull;                                                       // ... then cfl.set_global_max(0.)
+}
+
+struct CtlBeginArgs {
+  double tend;
+  long long take_one, max_steps, use_host, cur;
+  StepCtl host;              // the host's values of t, dt, dt_max, cfl_*, status, flags (when use_host)
+};
+
+__global__ void ctl_begin_kernel(StepCtl* ctl, CtlBeginArgs a) {
+  StepCtl c = *ctl;
+  if (a.use_host) {
+    const long long attempts = c.attempts;
+    c = a.host;
+    c.cur = a.cur;
+    c.attempts = attempts;   // the log ring keeps running
+  }
+  c.tstart = c.t;
+  c.tend = a.tend;
+  c.take_one = a.take_one;
+  c.max_steps = a.max_steps;
+  c.n = 0;
+  c.num_steps = 0;
+  c.error = 0;
+  c.done = (a.max_steps <= 0 || (!a.take_one && a.tend <= c.tstart)) ? 1 : 0;
+  if (!c.done) ctl_pre_step(c);
+  *ctl = c;
+}
+
+__global__ void ctl_end_kernel(StepCtl* ctl, double* log) {
+  StepCtl c = *ctl;
+  if (c.done) return;
+  const double cfl = __longlong_as_double((long long)c.cfl_bits);
+  c.cfl_cached = cfl;
+  const bool accept = !(cfl > c.cfl_max);                                  // accept_reject_step (:524-526)
+  double* e = log + 3 * (c.attempts % LOG_CAP);
+  e[0] = c.dt; e[1] = cfl; e[2] = accept ? 1.0 : 0.0;
+  c.attempts += 1;
+  if (accept) {
+    c.cur ^= 1;                                                            // the buffer the sweep wrote becomes current
+    if (!(c.cflmax > cfl)) c.cflmax = cfl;
+    if (c.dt_variable) c.t = __dadd_rn(c.t, c.dt);                         // :630-633
+    else c.t = __dadd_rn(c.tstart, __dmul_rn((double)(c.n + 1), c.dt));
+    c.num_steps += 1;
+    c.numsteps += 1;
+  } else if (!c.dt_variable) {                                             // :647-651 'CFL too large, giving up!'
+    if (!(c.cflmax > cfl)) c.cflmax = cfl;
+    c.error = 1;
+    c.done = 1;
+    *ctl = c;
+    return;
+  }                                                                        // else: t = told, q = q_backup (cur unchanged)
+  c.n += 1;
+  if (c.take_one || c.t >= c.tend || c.n >= c.max_steps) {                 // :654-655 and the end of the loop
+    c.done = 1;
+    if (!c.take_one && c.dt_variable && c.t < c.tend && c.num_steps == c.max_steps) c.error = 2;   // :660-664
+  } else {
+    ctl_pre_step(c);
+  }
+  *ctl = c;
+}
+
 int check_handle(const claw_solver* h) {
   if (!h) { g_last_error = "null solver handle"; return 1; }
   return 0;
@@ -251,6 +381,23 @@ int ensure_buffers(claw_solver* h) {
   CK(h, cudaMemsetAsync(h->q[0], 0, h->q_elems * sizeof(double), h->stream));
   CK(h, cudaMemsetAsync(h->q[1], 0, h->q_elems * sizeof(double), h->stream));
   h->owns_buffers = true;
+  return 0;
+}
+
+// Attempts queued under device-side step control: wait for them and bring the host's `cur` up to date.
+int ctl_settle(claw_solver* h) {
+  if (!h->ctl_pending) return 0;
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaMemcpyAsync(h->h_ctl, h->work, CTL_WORDS * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->cur = (int)reinterpret_cast<const StepCtl*>(h->h_ctl)->cur;
+  h->ctl_pending = false;
+  return 0;
+}
+// host-driven entry points (claw_step_launch, claw_accept, ...) take the handle out of device-side step control
+int ctl_leave(claw_solver* h) {
+  if (int rc = ctl_settle(h)) return rc;
+  h->ctl_mode = false;
   return 0;
 }
 
@@ -329,7 +476,18 @@ int get_all(claw_solver* h, const double* dsoa, int ncomp, double* host) {
   return get_region(h, dsoa, ncomp, host, lo, hi, lo, hn);
 }
 
-int fill_ghosts_array(claw_solver* h, double* arr, int ncomp, const int* lo, const int* up, bool is_q) {
+ArrSel sel_fixed(double* p) { ArrSel a{}; a.q[0] = p; a.ctl = nullptr; a.role = 0; return a; }
+// the q buffer that is current (role 0) / alternate (role 1): by the host's `cur`, or by the device's under ctl_mode
+ArrSel sel_q(claw_solver* h, int role) {
+  ArrSel a{};
+  if (!h->ctl_mode) { a.q[0] = h->q[role == 0 ? h->cur : (h->cur ^ 1)]; return a; }
+  a.q[0] = h->q[0]; a.q[1] = h->q[1]; a.q[2] = nullptr;
+  a.ctl = reinterpret_cast<const StepCtl*>(h->work);
+  a.role = role;
+  return a;
+}
+
+int fill_ghosts_array(claw_solver* h, ArrSel arr, int ncomp, const int* lo, const int* up, bool is_q) {
   const Dev2& g = h->g;
   for (int d = 0; d < g.ndim; ++d) {
     // BC.custom (0) on an AUX face is allowed: the host filled those ghost cells once (claw_put_auxbc) and the
@@ -373,8 +531,14 @@ int fill_ghosts_array(claw_solver* h, double* arr, int ncomp, const int* lo, con
 }
 
 int launch_step2(claw_solver* h, double dx, double dy, double dt, int kind, int do_x, int do_y,
-                 const double* src, double* dst, int j0 = 0, int j1 = 0, cudaStream_t stream_override = nullptr) {
+                 const double* src, double* dst, int j0 = 0, int j1 = 0, cudaStream_t stream_override = nullptr,
+                 bool under_ctl = false) {
   Sweep2Params P{};
+  if (under_ctl) {                                     // src / dst / dt are decided on the device (StepCtl)
+    P.ctl = reinterpret_cast<const StepCtl*>(h->work);
+    P.qbuf[0] = h->q[0]; P.qbuf[1] = h->q[1]; P.qbuf[2] = nullptr;
+    P.delta[0] = dx; P.delta[1] = dy;
+  }
   P.j0 = j0; P.j1 = j1;                                // 0,0 = whole grid
   cudaStream_t st = stream_override ? stream_override : h->stream;
   P.qin = src;
@@ -401,8 +565,14 @@ int launch_step2(claw_solver* h, double dx, double dy, double dt, int kind, int 
 
 // one directional pass of the 3-D step (dir 0/1/2 = x/y/z)
 int launch_pass3(claw_solver* h, const double* delta, double dt, int dir, int first_pass, const double* src,
-                 double* dst) {
+                 double* dst, int src_role = -1, int dst_role = -1) {
   Sweep3Params P{};
+  if (src_role >= 0) {                                 // buffers and dt are decided on the device (StepCtl)
+    P.ctl = reinterpret_cast<const StepCtl*>(h->work);
+    P.qbuf[0] = h->q[0]; P.qbuf[1] = h->q[1]; P.qbuf[2] = h->work + WORK_HDR;
+    P.src_role = src_role; P.dst_role = dst_role;
+    for (int d = 0; d < 3; ++d) P.delta[d] = delta[d];
+  }
   P.qin = src;
   P.qout = dst;
   P.aux = h->aux;
@@ -431,7 +601,17 @@ int launch_pass3(claw_solver* h, const double* delta, double dt, int dir, int fi
 
 // whole 3-D step: src (ghosts filled) -> dst.  Unsplit (step3.f90): x-sweep writes dst = src + terms, the y- and
 // z-sweeps add into dst.  Split (3 x step3ds.f90, classic/solver.py:680-690): src -> dst -> tmp -> dst.
-int launch_step3(claw_solver* h, const double* delta, double dt, const double* src, double* dst) {
+int launch_step3(claw_solver* h, const double* delta, double dt, const double* src, double* dst, bool under_ctl) {
+  if (under_ctl) {                                     // roles: 0 = current, 1 = alternate, 2 = third buffer
+    if (h->method[2] < 0) {
+      if (int rc = launch_pass3(h, delta, dt, 0, 1, nullptr, nullptr, 0, 1)) return rc;
+      if (int rc = launch_pass3(h, delta, dt, 1, 1, nullptr, nullptr, 1, 2)) return rc;
+      return launch_pass3(h, delta, dt, 2, 1, nullptr, nullptr, 2, 1);
+    }
+    if (int rc = launch_pass3(h, delta, dt, 0, 1, nullptr, nullptr, 0, 1)) return rc;
+    if (int rc = launch_pass3(h, delta, dt, 1, 0, nullptr, nullptr, 0, 1)) return rc;
+    return launch_pass3(h, delta, dt, 2, 0, nullptr, nullptr, 0, 1);
+  }
   if (h->method[2] < 0) {
     double* tmp = h->work + WORK_HDR;
     if (int rc = launch_pass3(h, delta, dt, 0, 1, src, dst)) return rc;
@@ -443,10 +623,10 @@ int launch_step3(claw_solver* h, const double* delta, double dt, const double* s
   return launch_pass3(h, delta, dt, 2, 0, src, dst);
 }
 
-int launch_step(claw_solver* h, const double* delta, double dt, const double* src, double* dst) {
-  if (h->g.ndim == 3) return launch_step3(h, delta, dt, src, dst);
+int launch_step(claw_solver* h, const double* delta, double dt, const double* src, double* dst, bool under_ctl = false) {
+  if (h->g.ndim == 3) return launch_step3(h, delta, dt, src, dst, under_ctl);
   const int kind = (h->method[2] < 0) ? 1 : 0;         // method(3) = -1: dimensional splitting (classic/solver.py:186)
-  return launch_step2(h, delta[0], delta[1], dt, kind, 1, 1, src, dst);
+  return launch_step2(h, delta[0], delta[1], dt, kind, 1, 1, src, dst, 0, 0, nullptr, under_ctl);
 }
 
 // aux planes read by the 2-D Riemann solvers (rp2.cuh: none; rp2_aux.cuh: RP::MAUX); -1 = unknown id
@@ -567,6 +747,7 @@ int claw_create(claw_solver** out, int ndim, int rp_id, int meqn, int mwaves, in
   if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
   if (e == cudaSuccess) h->num_sms = prop.multiProcessorCount;
   if (e == cudaSuccess) e = cudaHostAlloc(&h->h_cfl, 64, cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaHostAlloc(&h->h_ctl, WORK_HDR * sizeof(double), cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_cfl, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     int rc = fail(nullptr, 100 + (int)e, "claw_create: %s", cudaGetErrorString(e));
@@ -584,6 +765,9 @@ int claw_destroy(claw_solver* h) {
     cudaFree(h->q[0]); cudaFree(h->q[1]); cudaFree(h->aux); cudaFree(h->work);
   }
   if (h->h_cfl) cudaFreeHost(h->h_cfl);
+  if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->graph) cudaGraphExecDestroy(h->graph);
+  if (h->s_cap) cudaStreamDestroy(h->s_cap);
   if (h->ev_cfl) cudaEventDestroy(h->ev_cfl);
   if (h->s_in) {
     cudaStreamDestroy(h->s_in); cudaStreamDestroy(h->s_cmp); cudaStreamDestroy(h->s_out);
@@ -607,11 +791,13 @@ int claw_bind(claw_solver* h, double* d_q0, double* d_q1, double* d_aux, double*
   if (!d_q0 || !d_q1 || !d_work || (h->maux > 0 && !d_aux)) return fail(h, 11, "claw_bind: NULL buffer");
   h->q[0] = d_q0; h->q[1] = d_q1; h->aux = d_aux; h->work = d_work;
   h->cur = 0;
+  ++h->cfg_epoch;
   return 0;
 }
 
 int claw_set_cparam(claw_solver* h, const double* cparam, int n) {
   if (check_handle(h)) return 1;
+  ++h->cfg_epoch;
   if (n < 0 || n > 4) return fail(h, 12, "claw_set_cparam: n=%d (max 4)", n);
   for (int k = 0; k < n; ++k) h->cparam[k] = cparam[k];
   return 0;
@@ -619,6 +805,7 @@ int claw_set_cparam(claw_solver* h, const double* cparam, int n) {
 
 int claw_set_method(claw_solver* h, const int* method7, const int* mthlim, int use_fwave) {
   if (check_handle(h)) return 1;
+  ++h->cfg_epoch;
   for (int k = 0; k < 7; ++k) h->method[k] = method7[k];
   for (int k = 0; k < h->mwaves; ++k) h->mthlim[k] = mthlim[k];
   h->use_fwave = use_fwave;
@@ -628,6 +815,7 @@ int claw_set_method(claw_solver* h, const int* method7, const int* mthlim, int u
 int claw_set_bc(claw_solver* h, const int* lower, const int* upper, const int* aux_lower, const int* aux_upper,
                 const int* reflect_index) {
   if (check_handle(h)) return 1;
+  ++h->cfg_epoch;
   for (int d = 0; d < h->g.ndim; ++d) {
     h->bc_lower[d] = lower[d]; h->bc_upper[d] = upper[d];
     if (aux_lower) h->aux_bc_lower[d] = aux_lower[d];
@@ -639,12 +827,14 @@ int claw_set_bc(claw_solver* h, const int* lower, const int* upper, const int* a
 
 int claw_set_boundary_ownership(claw_solver* h, const int* on_lower, const int* on_upper) {
   if (check_handle(h)) return 1;
+  ++h->cfg_epoch;
   for (int d = 0; d < h->g.ndim; ++d) { h->on_lower[d] = on_lower[d]; h->on_upper[d] = on_upper[d]; }
   return 0;
 }
 
 int claw_set_mode(claw_solver* h, int mode) {
   if (check_handle(h)) return 1;
+  ++h->cfg_epoch;
   if (mode != CLAW_MODE_STRICT && mode != CLAW_MODE_FAST) return fail(h, 13, "claw_set_mode: unknown mode %d", mode);
   h->mode = mode;
   return 0;
@@ -652,6 +842,7 @@ int claw_set_mode(claw_solver* h, int mode) {
 
 int claw_set_tuning(claw_solver* h, int seg_rows) {
   if (check_handle(h)) return 1;
+  ++h->cfg_epoch;
   h->seg_rows = seg_rows < 0 ? 0 : seg_rows;
   return 0;
 }
@@ -659,6 +850,7 @@ int claw_set_tuning(claw_solver* h, int seg_rows) {
 int claw_put_q(claw_solver* h, const double* host_q) {
   if (check_handle(h)) return 1;
   if (int rc = ensure_buffers(h)) return rc;
+  if (int rc = ctl_settle(h)) return rc;
   CK(h, cudaSetDevice(h->device));
   if (int rc = put_region(h, h->q[h->cur], h->meqn, host_q, false)) return rc;
   CK(h, cudaStreamSynchronize(h->stream));
@@ -668,6 +860,7 @@ int claw_put_q(claw_solver* h, const double* host_q) {
 int claw_get_q(claw_solver* h, double* host_q) {
   if (check_handle(h)) return 1;
   if (int rc = ensure_buffers(h)) return rc;
+  if (int rc = ctl_settle(h)) return rc;
   CK(h, cudaSetDevice(h->device));
   return get_interior(h, h->q[h->cur], h->meqn, host_q, false);
 }
@@ -678,6 +871,7 @@ int claw_get_cells(claw_solver* h, int ncells, const int* idx, double* host_out)
   if (check_handle(h)) return 1;
   if (ncells < 0 || (ncells > 0 && (!idx || !host_out))) return fail(h, 12, "claw_get_cells: bad arguments");
   if (int rc = ensure_buffers(h)) return rc;
+  if (int rc = ctl_settle(h)) return rc;
   CK(h, cudaSetDevice(h->device));
   const Dev2& g = h->g;
   double* stage = h->work + WORK_HDR;
@@ -712,6 +906,7 @@ int claw_put_aux(claw_solver* h, const double* host_aux) {
 int claw_put_qbc(claw_solver* h, const double* host_qbc) {
   if (check_handle(h)) return 1;
   if (int rc = ensure_buffers(h)) return rc;
+  if (int rc = ctl_settle(h)) return rc;
   CK(h, cudaSetDevice(h->device));
   if (int rc = put_region(h, h->q[h->cur], h->meqn, host_qbc, true)) return rc;
   CK(h, cudaStreamSynchronize(h->stream));
@@ -721,6 +916,7 @@ int claw_put_qbc(claw_solver* h, const double* host_qbc) {
 int claw_get_qbc(claw_solver* h, double* host_qbc) {
   if (check_handle(h)) return 1;
   if (int rc = ensure_buffers(h)) return rc;
+  if (int rc = ctl_settle(h)) return rc;
   CK(h, cudaSetDevice(h->device));
   return get_all(h, h->q[h->cur], h->meqn, host_qbc);
 }
@@ -740,14 +936,15 @@ int claw_apply_bcs(claw_solver* h) {
   if (int rc = ensure_buffers(h)) return rc;
   CK(h, cudaSetDevice(h->device));
   if (h->maux > 0)
-    if (int rc = fill_ghosts_array(h, h->aux, h->maux, h->aux_bc_lower, h->aux_bc_upper, false)) return rc;
-  return fill_ghosts_array(h, h->q[h->cur], h->meqn, h->bc_lower, h->bc_upper, true);
+    if (int rc = fill_ghosts_array(h, sel_fixed(h->aux), h->maux, h->aux_bc_lower, h->aux_bc_upper, false)) return rc;
+  return fill_ghosts_array(h, sel_q(h, 0), h->meqn, h->bc_lower, h->bc_upper, true);
 }
 
 int claw_step_launch(claw_solver* h, const double* delta, double dt, int fill_ghosts) {
   if (check_handle(h)) return 1;
   if (int rc = validate_config(h)) return rc;
   if (int rc = ensure_buffers(h)) return rc;
+  if (int rc = ctl_leave(h)) return rc;
   CK(h, cudaSetDevice(h->device));
   if (fill_ghosts)
     if (int rc = claw_apply_bcs(h)) return rc;
@@ -779,6 +976,7 @@ int claw_step(claw_solver* h, const double* delta, double dt, int fill_ghosts, d
 
 int claw_accept(claw_solver* h) {
   if (check_handle(h)) return 1;
+  if (int rc = ctl_leave(h)) return rc;
   h->cur ^= 1;
   return 0;
 }
@@ -794,12 +992,165 @@ int claw_sync(claw_solver* h) {
   return 0;
 }
 
+
+// ---- device-resident step control ----------------------------------------------------------
+namespace {
+// one attempt under the control block: [ghost fill] + sweep(s); the control kernel follows (claw_ctl_end)
+int ctl_enqueue_sweep(claw_solver* h, const double* delta, int fill_ghosts) {
+  if (fill_ghosts)
+    if (int rc = claw_apply_bcs(h)) return rc;
+  return launch_step(h, delta, 0.0, nullptr, nullptr, true);
+}
+int ctl_enqueue_end(claw_solver* h) {
+  ctl_end_kernel<<<1, 1, 0, h->stream>>>(reinterpret_cast<StepCtl*>(h->work), h->work + CTL_WORDS);
+  ++h->launches;
+  CK(h, cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+int claw_ctl_begin(claw_solver* h, const double* host_words, double tend, int take_one_step, long long max_steps) {
+  if (check_handle(h)) return 1;
+  if (int rc = validate_config(h)) return rc;
+  if (int rc = ensure_buffers(h)) return rc;
+  CK(h, cudaSetDevice(h->device));
+  CtlBeginArgs a{};
+  a.tend = tend; a.take_one = take_one_step ? 1 : 0; a.max_steps = max_steps;
+  if (host_words) {
+    if (int rc = ctl_settle(h)) return rc;
+    if (!h->ctl_mode) CK(h, cudaMemsetAsync(h->work, 0, CTL_WORDS * sizeof(double), h->stream));   // attempts = 0
+    memcpy(&a.host, host_words, sizeof(StepCtl));
+    a.use_host = 1;
+    a.cur = h->cur;
+    h->ctl_mode = true;
+  } else if (!h->ctl_mode) {
+    return fail(h, 50, "claw_ctl_begin: the first call on a handle must pass the host's control values");
+  }
+  ctl_begin_kernel<<<1, 1, 0, h->stream>>>(reinterpret_cast<StepCtl*>(h->work), a);
+  ++h->launches;
+  CK(h, cudaGetLastError());
+  h->ctl_pending = true;
+  return 0;
+}
+
+int claw_ctl_sweep(claw_solver* h, const double* delta, int fill_ghosts) {
+  if (check_handle(h)) return 1;
+  if (!h->ctl_mode) return fail(h, 51, "claw_ctl_sweep: call claw_ctl_begin first");
+  CK(h, cudaSetDevice(h->device));
+  h->ctl_pending = true;
+  return ctl_enqueue_sweep(h, delta, fill_ghosts);
+}
+
+int claw_ctl_end(claw_solver* h) {
+  if (check_handle(h)) return 1;
+  if (!h->ctl_mode) return fail(h, 51, "claw_ctl_end: call claw_ctl_begin first");
+  CK(h, cudaSetDevice(h->device));
+  h->ctl_pending = true;
+  return ctl_enqueue_end(h);
+}
+
+int claw_ctl_attempts(claw_solver* h, const double* delta, int n, int fill_ghosts) {
+  if (check_handle(h)) return 1;
+  if (!h->ctl_mode) return fail(h, 51, "claw_ctl_attempts: call claw_ctl_begin first");
+  if (n < 0 || n > LOG_CAP) return fail(h, 52, "claw_ctl_attempts: n = %d (0..%d)", n, LOG_CAP);
+  CK(h, cudaSetDevice(h->device));
+  h->ctl_pending = true;
+  const int ndim = h->g.ndim;
+  bool graph_ok = h->use_graph && n >= 2;
+  if (graph_ok) {
+    bool stale = (h->graph == nullptr) || h->graph_epoch != h->cfg_epoch || h->graph_fill != (fill_ghosts ? 1 : 0);
+    for (int d = 0; d < ndim; ++d) stale = stale || (h->graph_delta[d] != delta[d]);
+    if (stale) {
+      // capture ONE attempt; every buffer and dt is picked up from the control block when the node runs
+      if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+      const uint64_t launches0 = h->launches;
+      cudaGraph_t g = nullptr;
+      // captured on a private stream (the handle's stream may be the legacy default stream, which cannot capture);
+      // the instantiated graph is launched into the handle's stream
+      if (!h->s_cap && cudaStreamCreateWithFlags(&h->s_cap, cudaStreamNonBlocking) != cudaSuccess) h->s_cap = nullptr;
+      int rc = 1;
+      cudaError_t e = cudaErrorUnknown;
+      if (h->s_cap && cudaStreamBeginCapture(h->s_cap, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+        cudaStream_t user = h->stream;
+        h->stream = h->s_cap;
+        rc = ctl_enqueue_sweep(h, delta, fill_ghosts);
+        if (!rc) rc = ctl_enqueue_end(h);
+        h->stream = user;
+        e = cudaStreamEndCapture(h->s_cap, &g);
+      }
+      h->launches = launches0;                       // nothing ran
+      if (rc || e != cudaSuccess || g == nullptr) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        h->use_graph = 0;                            // fall back to plain launches for good
+        graph_ok = false;
+      } else {
+        e = cudaGraphInstantiate(&h->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { cudaGetLastError(); h->graph = nullptr; h->use_graph = 0; graph_ok = false; }
+        else {
+          h->graph_epoch = h->cfg_epoch; h->graph_fill = fill_ghosts ? 1 : 0;
+          for (int d = 0; d < ndim; ++d) h->graph_delta[d] = delta[d];
+        }
+      }
+    }
+  }
+  if (graph_ok) {
+    const uint64_t per = (uint64_t)(fill_ghosts ? (ndim == 3 ? 3 : 2) + (h->maux > 0 ? (ndim == 3 ? 3 : 2) : 0) : 0) +
+                         (ndim == 3 ? 3 : 1) + 1;
+    for (int k = 0; k < n; ++k) CK(h, cudaGraphLaunch(h->graph, h->stream));
+    h->launches += per * (uint64_t)n;
+    return 0;
+  }
+  for (int k = 0; k < n; ++k) {
+    if (int rc = ctl_enqueue_sweep(h, delta, fill_ghosts)) return rc;
+    if (int rc = ctl_enqueue_end(h)) return rc;
+  }
+  return 0;
+}
+
+int claw_ctl_read(claw_solver* h, double* words, long long from_attempt, double* log3, int max_entries, int* n_entries) {
+  if (check_handle(h)) return 1;
+  if (!h->ctl_mode) return fail(h, 51, "claw_ctl_read: call claw_ctl_begin first");
+  h->ctl_pending = true;                             // force the read-back
+  if (int rc = ctl_settle(h)) return rc;
+  const StepCtl* c = reinterpret_cast<const StepCtl*>(h->h_ctl);
+  if (words) memcpy(words, h->h_ctl, CTL_WORDS * sizeof(double));
+  int n = 0;
+  if (log3 && max_entries > 0) {
+    long long first = from_attempt;
+    if (c->attempts - first > LOG_CAP) first = c->attempts - LOG_CAP;     // older entries were overwritten
+    if (c->attempts - first > max_entries) first = c->attempts - max_entries;
+    n = (int)(c->attempts - first);
+    if (n > 0) {
+      const long long i0 = first % LOG_CAP, i1 = (first + n - 1) % LOG_CAP;
+      double* dlog = h->work + CTL_WORDS;
+      if (i1 >= i0) {
+        CK(h, cudaMemcpyAsync(log3, dlog + 3 * i0, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
+      } else {
+        const long long n0 = LOG_CAP - i0;
+        CK(h, cudaMemcpyAsync(log3, dlog + 3 * i0, sizeof(double) * 3 * n0, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(log3 + 3 * n0, dlog, sizeof(double) * 3 * (n - n0), cudaMemcpyDeviceToHost, h->stream));
+      }
+      CK(h, cudaStreamSynchronize(h->stream));
+    }
+  }
+  if (n_entries) *n_entries = n;
+  return 0;
+}
+
+int claw_ctl_use_graph(claw_solver* h, int on) {
+  if (check_handle(h)) return 1;
+  h->use_graph = on ? 1 : 0;
+  return 0;
+}
+
 namespace {
 size_t halo_elems_of(const claw_solver* h, int ncomp) {
   return (h->g.ndim == 2) ? (size_t)ncomp * 2 * h->g.nt[0] : (size_t)ncomp * 2 * h->g.kstride;
 }
 // pack (interior rows/planes next to `side`) or unpack (ghost rows/planes of `side`) of one array
-int halo_move(claw_solver* h, double* arr, int ncomp, int side, double* d_buf, bool pack) {
+int halo_move(claw_solver* h, ArrSel arr, int ncomp, int side, double* d_buf, bool pack) {
   if (int rc = ensure_buffers(h)) return rc;
   CK(h, cudaSetDevice(h->device));
   const Dev2& g = h->g;
@@ -812,9 +1163,9 @@ int halo_move(claw_solver* h, double* arr, int ncomp, int side, double* d_buf, b
     else halo_unpack2<<<grid_for(n, 256), 256, 0, h->stream>>>(arr, d_buf, ncomp, g.nt[0], s0, g.pitch, g.plane);
   } else {
     const long long len = 2 * g.kstride;
-    double* base = arr + (long long)s0 * g.kstride;
-    if (pack) gather_runs<<<grid_for(len * ncomp, 256), 256, 0, h->stream>>>(base, g.plane, d_buf, len, ncomp);
-    else scatter_runs<<<grid_for(len * ncomp, 256), 256, 0, h->stream>>>(base, g.plane, d_buf, len, ncomp);
+    const long long off = (long long)s0 * g.kstride;
+    if (pack) gather_runs<<<grid_for(len * ncomp, 256), 256, 0, h->stream>>>(arr, off, g.plane, d_buf, len, ncomp);
+    else scatter_runs<<<grid_for(len * ncomp, 256), 256, 0, h->stream>>>(arr, off, g.plane, d_buf, len, ncomp);
   }
   ++h->launches;
   CK(h, cudaGetLastError());
@@ -829,21 +1180,21 @@ int claw_halo_elems(const claw_solver* h, size_t* elems) {
 }
 int claw_halo_pack(claw_solver* h, int side, double* d_buf) {
   if (check_handle(h)) return 1;
-  return halo_move(h, h->q[h->cur], h->meqn, side, d_buf, true);
+  return halo_move(h, sel_q(h, 0), h->meqn, side, d_buf, true);
 }
 int claw_halo_unpack(claw_solver* h, int side, const double* d_buf) {
   if (check_handle(h)) return 1;
-  return halo_move(h, h->q[h->cur], h->meqn, side, const_cast<double*>(d_buf), false);
+  return halo_move(h, sel_q(h, 0), h->meqn, side, const_cast<double*>(d_buf), false);
 }
 // the same on the buffer the last claw_step_launch WROTE (the state that becomes current on claw_accept): lets the
 // host queue the next step's exchange right behind the sweep, before it has read the CFL number back
 int claw_halo_pack_next(claw_solver* h, int side, double* d_buf) {
   if (check_handle(h)) return 1;
-  return halo_move(h, h->q[h->cur ^ 1], h->meqn, side, d_buf, true);
+  return halo_move(h, sel_q(h, 1), h->meqn, side, d_buf, true);
 }
 int claw_halo_unpack_next(claw_solver* h, int side, const double* d_buf) {
   if (check_handle(h)) return 1;
-  return halo_move(h, h->q[h->cur ^ 1], h->meqn, side, const_cast<double*>(d_buf), false);
+  return halo_move(h, sel_q(h, 1), h->meqn, side, const_cast<double*>(d_buf), false);
 }
 int claw_halo_elems_aux(const claw_solver* h, size_t* elems) {
   if (check_handle(h)) return 1;
@@ -853,12 +1204,12 @@ int claw_halo_elems_aux(const claw_solver* h, size_t* elems) {
 int claw_halo_pack_aux(claw_solver* h, int side, double* d_buf) {
   if (check_handle(h)) return 1;
   if (h->maux == 0) return 0;
-  return halo_move(h, h->aux, h->maux, side, d_buf, true);
+  return halo_move(h, sel_fixed(h->aux), h->maux, side, d_buf, true);
 }
 int claw_halo_unpack_aux(claw_solver* h, int side, const double* d_buf) {
   if (check_handle(h)) return 1;
   if (h->maux == 0) return 0;
-  return halo_move(h, h->aux, h->maux, side, const_cast<double*>(d_buf), false);
+  return halo_move(h, sel_fixed(h->aux), h->maux, side, const_cast<double*>(d_buf), false);
 }
 
 int claw_time_sweep(claw_solver* h, const double* delta, double dt, int reps, double* avg_ms) {
@@ -866,6 +1217,7 @@ int claw_time_sweep(claw_solver* h, const double* delta, double dt, int reps, do
   if (int rc = validate_config(h)) return rc;
   if (int rc = ensure_buffers(h)) return rc;
   if (reps < 1) return fail(h, 14, "claw_time_sweep: reps must be >= 1");
+  if (int rc = ctl_settle(h)) return rc;
   CK(h, cudaSetDevice(h->device));
   cudaEvent_t a, b;
   CK(h, cudaEventCreate(&a));

@@ -30,6 +30,35 @@ namespace clawcuda {
 
 #ifndef CLAWCUDA_SWEEP2_PARAMS
 #define CLAWCUDA_SWEEP2_PARAMS
+// Device-resident step control (clawcuda.cu: ctl_begin_kernel / ctl_end_kernel): the state of Solver.evolve_to_time
+// (pyclaw/src/pyclaw/solver.py:524-666) -- t, dt, the CFL number of the running attempt, which of the two q buffers is
+// current, whether the loop has ended -- lives at the start of the work buffer, so that the host can queue step
+// attempts without reading the CFL number back: the kernels of attempt n+1 pick up dt and the current buffer that the
+// control kernel of attempt n decided on, and turn into no-ops once `done` is set.  Every field is 8 bytes (the host
+// mirrors the block as an array of 64-bit words).
+struct StepCtl {
+  unsigned long long cfl_bits;     // [0]  CFL slot of the running attempt (atomicMax target; all-reduced across ranks)
+  double t, dt, dt_max, cfl_desired, cfl_max, cfl_cached;      // [1..6]
+  double tstart, tend, told;                                   // [7..9]
+  double dtmin, dtmax, cflmax;                                 // [10..12] solver.status
+  long long numsteps;              // [13] status['numsteps']
+  long long cur;                   // [14] index of the current q buffer
+  long long done;                  // [15] 1: the attempts still queued are no-ops
+  long long error;                 // [16] 1: CFL too large with a fixed dt, 2: max_steps reached before tend
+  long long take_one, dt_variable, have_dt_old;                // [17..19]
+  long long n, num_steps, max_steps;                           // [20..22] loop counter, accepted steps of this call
+  long long attempts;              // [23] attempts logged so far (log ring index)
+  long long src_done;              // [24] 1: the attempt's trailing source step must be skipped (cfl >= cfl_max)
+  long long pad[7];
+};
+static_assert(sizeof(StepCtl) == 32 * 8, "StepCtl is mirrored by the host as 32 words");
+
+// buffer roles of a launch that runs under a StepCtl: 0 = current q, 1 = alternate q, 2 = third buffer (3-D split)
+__device__ __forceinline__ double* ctl_buffer(const StepCtl* ctl, double* const* qbuf, int role) {
+  const int c = (int)ctl->cur;
+  return role == 2 ? qbuf[2] : qbuf[role == 0 ? c : (c ^ 1)];
+}
+
 struct Sweep2Params {
   const double* qin;        // SoA: plane m at qin + m*plane, row J at + J*pitch
   double* qout;
@@ -52,8 +81,27 @@ struct Sweep2Params {
   int maux;                 // planes present
   int capa;                 // method(6) = index_capa + 1 (1-based aux plane of the capacity function), 0 = none
   int fwave;                // use_fwave
+  // device-resident step control (null: qin / qout / dtdx / dtdy above are final)
+  const StepCtl* ctl;
+  double* qbuf[3];          // the two ping-pong q buffers (+ unused third): qin = qbuf[cur], qout = qbuf[cur ^ 1]
+  double delta[2];          // dx, dy: dtdx = ctl->dt / dx as step2.f90:77-78 computes it
 };
 #endif
+
+// Prologue of every 2-D sweep kernel: the launch parameters, or -- under a StepCtl -- what the control kernel of the
+// previous attempt left behind.  Returns false when the kernel has nothing to do (the step loop has ended).
+#define CLAW_RESOLVE_STEP2(P, qin_, qout_, dtdx_, dtdy_)                                  \
+  const double* qin_ = (P).qin;                                                           \
+  double* qout_ = (P).qout;                                                               \
+  double dtdx_ = (P).dtdx, dtdy_ = (P).dtdy;                                              \
+  if ((P).ctl != nullptr) {                                                               \
+    if ((P).ctl->done) return;                                                            \
+    qin_ = ctl_buffer((P).ctl, (P).qbuf, 0);                                              \
+    qout_ = ctl_buffer((P).ctl, (P).qbuf, 1);                                             \
+    const double dt_ = (P).ctl->dt;                                                       \
+    dtdx_ = dt_ / (P).delta[0];                                                           \
+    dtdy_ = dt_ / (P).delta[1];                                                           \
+  }
 
 namespace CLAW_NS {
 
@@ -247,7 +295,7 @@ template <class RP, int NT> struct Smem2 {
 // On return: wave limited, s, amdq/apdq ORIGINAL fluctuations, cqxx, fadd (= 0.5 cqxx or 0).
 // Contains __syncthreads(): must be called by all threads of the CTA.
 template <class RP, int NT, int LIM = 0>
-__device__ __forceinline__ void x_face(const Sweep2Params& P, const double* q, const double* c, int t, int tl, int tr,
+__device__ __forceinline__ void x_face(const Sweep2Params& P, double dtdx, const double* q, const double* c, int t, int tl, int tr,
                                        bool second, bool limit, double* sq, double* sxw, double* sdot,
                                        double (*wave)[RP::MEQN], double* s, double* amdq, double* apdq,
                                        double* roe, double* cqxx, double* fadd) {
@@ -288,7 +336,7 @@ __device__ __forceinline__ void x_face(const Sweep2Params& P, const double* q, c
       for (int mw = 0; mw < W; ++mw) dotl[mw] = sdot[mw * NT + tl];
       limit_waves<RP, LIM>(P, wave, s, wnorm2, dotl, dotr);
     }
-    second_order<RP>(P.dtdx, wave, s, cqxx);                              // flux2.f90:134-146
+    second_order<RP>(dtdx, wave, s, cqxx);                                // flux2.f90:134-146
 #pragma unroll
     for (int m = 0; m < M; ++m) fadd[m] = 0.0 + 0.5 * cqxx[m];
   }
@@ -328,13 +376,13 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
   const int tl = t > 0 ? -1 : 0;                           // neighbour offsets (clamped at the strip edge)
   const int tr = t < NT - 1 ? 1 : 0;
 
-  const double dtdx = P.dtdx, dtdy = P.dtdy;
+  CLAW_RESOLVE_STEP2(P, qin, qout, dtdx, dtdy);
   const double hdx = 0.5 * dtdx, hdy = 0.5 * dtdy;
   const bool second = SP ? true : (P.order != 1);
   const bool limit = SP ? true : (second && (P.limit != 0));
   const int mt = SP ? 2 : P.mtrans;
 
-  const double* qcol = P.qin + Ic;
+  const double* qcol = qin + Ic;
   double q1[M], qn0[M], qn1[M], c1[NC1];
   double yI_apdq[M], yI_fadd[M], yI_bm[M], yI_bp[M];      // finished y-interface J (rotated frame)
 #pragma unroll
@@ -469,7 +517,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
     for (int m = 0; m < M; ++m) qn2[m] = qN[m];
     if (SP || J >= Jb - 2) {
       double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
-      x_face<RP, NT, LIM>(P, q1, c1, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
+      x_face<RP, NT, LIM>(P, dtdx, q1, c1, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
       if (x_cfl_col && (J + 1 >= 1) && (J + 1 <= P.my + 2)) {             // flux2.f90:111-119
         cfl = cfl_update<RP>(cfl, dtdx, s);
       }
@@ -516,7 +564,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_unsplit(const __grid_constant
         double r = qn0[m] + dtdx * sgy[(M + m) * NT + tl];
         r = r + ycomb[m];
         r = r - dtdx * sgy[m * NT + tr];
-        if (store_col) P.qout[m * P.plane + (long long)J * P.pitch + I] = r;
+        if (store_col) qout[m * P.plane + (long long)J * P.pitch + I] = r;
       }
     }
 #pragma unroll
@@ -554,12 +602,12 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__
   const int Ic = I < nx ? I : nx - 1;
   const int tl = t > 0 ? -1 : 0;
   const int tr = t < NT - 1 ? 1 : 0;
-  const double dtdx = P.dtdx, dtdy = P.dtdy;
+  CLAW_RESOLVE_STEP2(P, qin, qout, dtdx, dtdy);
   const bool second = (P.order != 1);
   const bool limit = second && (P.limit != 0);
   const bool do_x = P.do_x != 0, do_y = P.do_y != 0;
   constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
-  const double* qcol = P.qin + Ic;
+  const double* qcol = qin + Ic;
   double cfl = 0.0;
   const bool x_cfl_col = (t >= 1) && (I >= 2) && (I <= P.mx + 2);
   const bool interior_col = (I >= 2) && (I <= P.mx + 1);
@@ -578,7 +626,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__
       double cq[NC1];
       if constexpr (NC > 0) RP::cell(P.rp, q, cq);
       double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
-      x_face<RP, NT>(P, q, cq, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
+      x_face<RP, NT>(P, dtdx, q, cq, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
       if (x_cfl_col) {
         cfl = cfl_update<RP>(cfl, dtdx, s);
       }
@@ -589,7 +637,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__
       for (int m = 0; m < M; ++m) {
         const double qadd = (0.0 - dtdx * apdq[m]) - dtdx * sxw[m * NT + tr];
         const double r = (q[m] + qadd) - dtdx * (sxw[(M + m) * NT + tr] - fadd[m]);   // step2ds.f90:149-152
-        if (interior_col && x_ok) P.qout[m * P.plane + (long long)J * P.pitch + I] = r;
+        if (interior_col && x_ok) qout[m * P.plane + (long long)J * P.pitch + I] = r;
       }
     }
     block_max_cfl<NT>(cfl, P.cfl_bits, sred);
@@ -614,7 +662,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__
       double cq[NC1];
       if constexpr (NC > 0) RP::cell(P.rp, qx2, cq);
       double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
-      x_face<RP, NT>(P, qx2, cq, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
+      x_face<RP, NT>(P, dtdx, qx2, cq, t, tl, tr, second, limit, sq, sxw, sdot, wave, s, amdq, apdq, roe, cqxx, fadd);
       if (x_cfl_col) {
         cfl = cfl_update<RP>(cfl, dtdx, s);
       }
@@ -679,7 +727,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep2_split(const __grid_constant__
             // step2ds.f90:237-240
             const double r = (qx0[rot<M>(m)] + qadd) - dtdy * (fadd[m] - yI_fadd[m]);
             if (J >= Jb && col_ok && (do_x ? interior_col : true))
-              P.qout[rot<M>(m) * P.plane + (long long)J * P.pitch + I] = r;
+              qout[rot<M>(m) * P.plane + (long long)J * P.pitch + I] = r;
             yI_apdq[m] = apdqC[m]; yI_fadd[m] = fadd[m];
           }
         }

@@ -75,14 +75,14 @@ __global__ void __launch_bounds__(NW * 32) sweep2_unsplit_aux(const __grid_const
   const int Je = min(Jb + P.seg_rows, P.j1);
   const int Jtop = P.my + 3;                               // last row of the array
 
-  const double dtdx = P.dtdx, dtdy = P.dtdy;
+  CLAW_RESOLVE_STEP2(P, qin, qout, dtdx, dtdy);
   const bool second = (P.order != 1);
   const bool limit = second && (P.limit != 0);
   const int mt = P.mtrans;
   const bool fw = P.fwave != 0;
   const bool cp = P.capa > 0;
 
-  const double* qcol = P.qin + Ic;
+  const double* qcol = qin + Ic;
   const double* acol = P.aux + Ic;
   const double* kcol = cp ? P.aux + (long long)(P.capa - 1) * P.plane + Ic : nullptr;
   auto row = [&](int J) { return (long long)(J < 0 ? 0 : (J > Jtop ? Jtop : J)) * P.pitch; };
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(NW * 32) sweep2_unsplit_aux(const __grid_const
         r = (r + yq[m]) - yb[m];
         r = r - ddiv(dtdx * g1R, k0);
       }
-      if (store_col && J >= Jb) P.qout[m * P.plane + (long long)J * P.pitch + I] = r;
+      if (store_col && J >= Jb) qout[m * P.plane + (long long)J * P.pitch + I] = r;
     }
 #pragma unroll
     for (int m = 0; m < M; ++m) { qn0[m] = qn1[m]; qn1[m] = qn2[m]; q1[m] = qN[m]; }
@@ -337,13 +337,13 @@ __global__ void __launch_bounds__(NW * 32) sweep2_split_aux(const __grid_constan
   const int I = (blockIdx.x * NW + (t >> 5)) * TX + lane;
   const int Ic = I < nx ? I : nx - 1;
   const int Jtop = P.my + 3;
-  const double dtdx = P.dtdx, dtdy = P.dtdy;
+  CLAW_RESOLVE_STEP2(P, qin, qout, dtdx, dtdy);
   const bool second = (P.order != 1);
   const bool limit = second && (P.limit != 0);
   const bool fw = P.fwave != 0;
   const bool cp = P.capa > 0;
   const bool do_x = P.do_x != 0, do_y = P.do_y != 0;
-  const double* qcol = P.qin + Ic;
+  const double* qcol = qin + Ic;
   const double* acol = P.aux + Ic;
   const double* kcol = cp ? P.aux + (long long)(P.capa - 1) * P.plane + Ic : nullptr;
   auto row = [&](int J) { return (long long)(J < 0 ? 0 : (J > Jtop ? Jtop : J)) * P.pitch; };
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(NW * 32) sweep2_split_aux(const __grid_constan
       x_sweep(q, a, kap, r);
       if (interior_col && x_ok) {
 #pragma unroll
-        for (int m = 0; m < M; ++m) P.qout[m * P.plane + (long long)J * P.pitch + I] = r[m];
+        for (int m = 0; m < M; ++m) qout[m * P.plane + (long long)J * P.pitch + I] = r[m];
       }
     }
     block_max_cfl<NT>(cfl, P.cfl_bits, sred);
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(NW * 32) sweep2_split_aux(const __grid_constan
             const double r = cp ? (qx0[rot<M>(m)] + qadd) - ddiv(dtdy * (fadd[m] - yI_fadd[m]), k0)
                                 : (qx0[rot<M>(m)] + qadd) - dtdy * (fadd[m] - yI_fadd[m]);
             if (J >= Jb && col_ok && (do_x ? interior_col : true))
-              P.qout[rot<M>(m) * P.plane + (long long)J * P.pitch + I] = r;
+              qout[rot<M>(m) * P.plane + (long long)J * P.pitch + I] = r;
             yI_apdq[m] = apdqC[m]; yI_fadd[m] = fadd[m];
           }
         }

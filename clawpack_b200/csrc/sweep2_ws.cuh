@@ -74,13 +74,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
   const int Jb = P.j0 + blockIdx.y * P.seg_rows;           // first output row
   const int Je = min(Jb + P.seg_rows, P.j1);               // one past the last output row
 
-  const double dtdx = P.dtdx, dtdy = P.dtdy;
+  CLAW_RESOLVE_STEP2(P, qin, qout, dtdx, dtdy);
   const double hdx = 0.5 * dtdx, hdy = 0.5 * dtdy;
   const bool second = SP ? true : (P.order != 1);
   const bool limit = SP ? true : (second && (P.limit != 0));
   const int mt = SP ? 2 : P.mtrans;
 
-  const double* qcol = P.qin + Ic;
+  const double* qcol = qin + Ic;
   double q1[M], qn0[M], qn1[M], c1[NC1];
   double yI_apdq[M], yI_fadd[M], yI_bm[M], yI_bp[M];      // finished y-interface J (rotated frame)
 #pragma unroll
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
       double r = qn0[m] + dtdx * shfl_left(gy2[m]);
       r = r + ycomb[m];
       r = r - dtdx * shfl_right(gy1[m]);
-      if (store_col && J >= Jb) P.qout[m * P.plane + (long long)J * P.pitch + I] = r;
+      if (store_col && J >= Jb) qout[m * P.plane + (long long)J * P.pitch + I] = r;
     }
 #pragma unroll
     for (int m = 0; m < M; ++m) { qn0[m] = qn1[m]; qn1[m] = qn2[m]; q1[m] = qN[m]; }
@@ -344,11 +344,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
   const int nx = P.mx + 4;
   const int I = (blockIdx.x * NW + (t >> 5)) * TX + lane;
   const int Ic = I < nx ? I : nx - 1;
-  const double dtdx = P.dtdx, dtdy = P.dtdy;
+  CLAW_RESOLVE_STEP2(P, qin, qout, dtdx, dtdy);
   const bool second = LIM ? true : (P.order != 1);
   const bool limit = LIM ? true : (second && (P.limit != 0));
   const bool do_x = P.do_x != 0, do_y = P.do_y != 0;
-  const double* qcol = P.qin + Ic;
+  const double* qcol = qin + Ic;
   double cfl = 0.0;
   const bool x_cfl_col = (lane >= 1) && (I >= 2) && (I <= P.mx + 2);
   const bool interior_col = (I >= 2) && (I <= P.mx + 1);
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
       x_sweep(q, r);
       if (interior_col && x_ok) {
 #pragma unroll
-        for (int m = 0; m < M; ++m) P.qout[m * P.plane + (long long)J * P.pitch + I] = r[m];
+        for (int m = 0; m < M; ++m) qout[m * P.plane + (long long)J * P.pitch + I] = r[m];
       }
     }
     block_max_cfl<NT>(cfl, P.cfl_bits, sred);
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
             const double qadd = (0.0 - dtdy * yI_apdq[m]) - dtdy * amdqC[m];
             const double r = (qx0[rot<M>(m)] + qadd) - dtdy * (fadd[m] - yI_fadd[m]);     // step2ds.f90:237-240
             if (J >= Jb && col_ok && (do_x ? interior_col : true))
-              P.qout[rot<M>(m) * P.plane + (long long)J * P.pitch + I] = r;
+              qout[rot<M>(m) * P.plane + (long long)J * P.pitch + I] = r;
             yI_apdq[m] = apdqC[m]; yI_fadd[m] = fadd[m];
           }
         }

@@ -55,8 +55,25 @@ struct Sweep3Params {
   int zlo, zhi;             // pencil planes K swept by the x- and y-sweeps: [1, mz+2], widened by one at
                             // rank-to-rank faces of a slab decomposition when dimension-split
   RpParams rp;
+  // device-resident step control (null: qin / qout / dtd above are final); see StepCtl in sweep2.cuh
+  const StepCtl* ctl;
+  double* qbuf[3];          // ping-pong q buffers + the third buffer of the dimension-split step
+  int src_role, dst_role;   // 0 = current, 1 = alternate, 2 = third buffer
+  double delta[3];          // dx, dy, dz: dtd = ctl->dt / delta as step3.f90:106-108 computes it
 };
 #endif
+
+#define CLAW_RESOLVE_STEP3(P, qin_, qout_, d0_, d1_, d2_)                                  \
+  const double* qin_ = (P).qin;                                                           \
+  double* qout_ = (P).qout;                                                               \
+  double d0_ = (P).dtd[0], d1_ = (P).dtd[1], d2_ = (P).dtd[2];                            \
+  if ((P).ctl != nullptr) {                                                               \
+    if ((P).ctl->done) return;                                                            \
+    qin_ = ctl_buffer((P).ctl, (P).qbuf, (P).src_role);                                   \
+    qout_ = ctl_buffer((P).ctl, (P).qbuf, (P).dst_role);                                  \
+    const double dt_ = (P).ctl->dt;                                                       \
+    d0_ = dt_ / (P).delta[0]; d1_ = dt_ / (P).delta[1]; d2_ = dt_ / (P).delta[2];         \
+  }
 
 namespace CLAW_NS {
 
@@ -417,7 +434,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
   const int ke = min(kb + P.seg, k_hi);
   const int k0 = split ? kb : kb - 1, k1 = split ? ke - 1 : ke;     // pencil planes k0..k1
 
-  const double dtdx = P.dtd[0], dtdy = P.dtd[1], dtdz = P.dtd[2];
+  CLAW_RESOLVE_STEP3(P, qin, qout, dtdx, dtdy, dtdz);
   const bool second = SP ? true : (P.order != 1);
   const bool limit = SP ? true : (second && (P.limit != 0));
   const bool transverse = SP ? true : (P.m3 > 0);
@@ -428,7 +445,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
   const bool row_out = split ? (J < ny) : (ty >= 1 && ty <= BY - 2 && J >= 2 && J <= P.n[1] + 1);
   const bool cfl_lane = (t >= 1) && (I >= 2) && (I <= P.n[0] + 2) && row_pencil;
 
-  const double* qbase = P.qin + (long long)Jc * P.pitch + Ic;
+  const double* qbase = qin + (long long)Jc * P.pitch + Ic;
   const double* abase = P.aux + Ic;
   double q[M], qnext[M];
   double acc0[M], acc1[M], acc2[M];
@@ -531,7 +548,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
 #pragma unroll
         for (int m = 0; m < M; ++m) {
           const double r = (q[m] + qadd[m]) - dtdx * fdiff[m];
-          P.qout[m * P.plane + (long long)k * P.kstride + (long long)J * P.pitch + I] = upd ? r : q[m];
+          qout[m * P.plane + (long long)k * P.kstride + (long long)J * P.pitch + I] = upd ? r : q[m];
         }
       }
       continue;
@@ -557,7 +574,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
       if (owner_lane && interior_i && k - 1 >= kb && k - 1 < ke) {
 #pragma unroll
         for (int m = 0; m < M; ++m)
-          P.qout[m * P.plane + (long long)(k - 1) * P.kstride + (long long)J * P.pitch + I] = acc0[m];
+          qout[m * P.plane + (long long)(k - 1) * P.kstride + (long long)J * P.pitch + I] = acc0[m];
       }
     }
 #pragma unroll
@@ -597,9 +614,10 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
   const long long strideT = (IXYZ == 1) ? P.kstride : (long long)P.pitch;     // thread-y stride
   const long long strideN = (IXYZ == 1) ? (long long)P.pitch : P.kstride;     // march stride
   // y-sweep: y-like = z (thread-y), z-like = x (thread-x).  z-sweep: y-like = x, z-like = y.
-  const double dtdn = P.dtd[IXYZ];
-  const double dty = (IXYZ == 1) ? P.dtd[2] : P.dtd[0];
-  const double dtz = (IXYZ == 1) ? P.dtd[0] : P.dtd[1];
+  CLAW_RESOLVE_STEP3(P, qin, qout, dtd0, dtd1, dtd2);
+  const double dtdn = (IXYZ == 1) ? dtd1 : dtd2;
+  const double dty = (IXYZ == 1) ? dtd2 : dtd0;
+  const double dtz = (IXYZ == 1) ? dtd0 : dtd1;
 
   const int c_lo = split ? 0 : 2, c_hi = split ? nlen : mlen + 2;
   const int cb = c_lo + blockIdx.z * P.seg;
@@ -615,8 +633,8 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
                                    T >= 2 && T <= P.n[TD] + 1);
 
   const long long col = (long long)Tc * strideT + Ic;
-  const double* qcol = P.qin + col;
-  double* ocol = P.qout + (long long)T * strideT + I;
+  const double* qcol = qin + col;
+  double* ocol = qout + (long long)T * strideT + I;
   double q1[M], q2[M];                                       // q(n-1), q(n-2)
   double auxP[MA];                                           // aux(n-1)
   double waveP[W][M], sP[W], amdqP[M], apdqP[M], ctxP[NC], dotlP[W];   // interface n-1 (pending, unlimited)

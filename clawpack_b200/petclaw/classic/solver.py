@@ -22,12 +22,12 @@ class _DistributedMixin(object):
             from ..device_halo import DeviceHalo
             halo = DeviceHalo(self._dev, state.patch, periodic)
             if state.num_aux > 0:
-                DeviceHalo(self._dev, state.patch, periodic_aux).exchange_aux(self._dev)
-            self._dev.pre_step_hook = halo.exchange
-            self._dev.post_step_hook = halo.reduce_cfl
+                self._dev.halo_aux = DeviceHalo(self._dev, state.patch, periodic_aux)
+                self._dev.halo_aux.exchange_aux(self._dev)
+            self._dev.halo = halo
 
     def step_hyperbolic(self, solution):
-        if self._dev is not None and self._dev.post_step_hook is not None:
+        if self._dev is not None and self._dev.halo is not None:
             cfl = self._dev.step(solution.states[0], self.dt)      # already the global max
             self.cfl.update_global_max(cfl, already_global=True)
             return

@@ -1,16 +1,12 @@
 """Device-side ghost exchange and CFL reduction for the slab decomposition (NCCL over NVLink).
 
-Per step and rank: two pack kernels (libclawcuda, claw_halo_pack) -> one batched NCCL send/recv with
-each slab neighbour -> two unpack kernels; after the sweep one 8-byte ncclAllReduce(max) on the
-kernel's CFL slot, then the host reads the value it needs for accept/reject.
-
-The exchange of step n+1 is queued SPECULATIVELY right behind the sweep of step n, on the buffer that sweep wrote
-(claw_halo_pack_next / claw_halo_unpack_next), before the host blocks on the CFL read-back: the host-side cost of
-queueing pack + NCCL + unpack and the NCCL latency then hide behind the running sweep instead of leaving the GPU idle
-between steps.  If the step is rejected the exchanged ghost rows belong to a buffer that is discarded, and the
-current buffer still carries the ghost rows of the exchange before -- nothing has to be redone either way.
-Measured on 8 B200 (profiles/r01_k_speculative_halo.jsonl): shallow water 16384^2 strong-scaled 1.57 -> 1.46 ms per
-step; Euler 8192^2 per GPU unchanged (5.21 ms).  CLAW_SPECULATIVE_HALO=0 switches it off."""
+Per step attempt and rank, all queued on the solver's stream without a host round trip (the step loop itself runs on
+the device, cuda_classic.DeviceStepper.evolve): two pack kernels (libclawcuda, claw_halo_pack) -> one batched NCCL
+send/recv with each slab neighbour -> two unpack kernels -> ghost fill + sweep -> one 8-byte ncclAllReduce(max) on the
+CFL slot of the control block -> the control kernel, which decides accept/reject identically on every rank.  The pack /
+unpack kernels find the current q buffer through the control block, so the exchange of attempt n+1 is queued before the
+outcome of attempt n is known; after a rejected attempt the same rows are simply exchanged again.  Every rank queues
+the same sequence of collectives for every attempt (no rank-local shortcut decides whether to exchange)."""
 import ctypes
 
 from .. import _lib
@@ -30,8 +26,6 @@ class DeviceHalo(object):
         _lib.check(dev.L.claw_halo_elems(dev.handle, ctypes.byref(n)), dev.handle)
         mk = lambda: torch.empty(n.value, dtype=torch.float64, device=dev.device)   # noqa: E731
         self.send_lo, self.send_up, self.recv_lo, self.recv_up = mk(), mk(), mk(), mk()
-        import os
-        self.speculative = os.environ.get('CLAW_SPECULATIVE_HALO', '1') != '0'
 
     def _vp(self, t):
         return ctypes.c_void_p(t.data_ptr())
@@ -47,12 +41,9 @@ class DeviceHalo(object):
         self._exchange(dev, dev.L.claw_halo_pack_aux, dev.L.claw_halo_unpack_aux, *bufs)
 
     def exchange(self, dev):
-        """Pre-step hook: ghost rows of the current buffer, unless the speculative exchange already delivered them."""
-        if dev.ghosts_current:
-            return
+        """Ghost rows / planes of the current q buffer from the slab neighbours (queued, not waited for)."""
         self._exchange(dev, dev.L.claw_halo_pack, dev.L.claw_halo_unpack, self.send_lo, self.send_up,
                        self.recv_lo, self.recv_up)
-        dev.ghosts_current = True
 
     def _exchange(self, dev, pack, unpack, send_lo, send_up, recv_lo, recv_up):
         L, h, d, nb = dev.L, dev.handle, self.dist, self.nb
@@ -77,11 +68,6 @@ class DeviceHalo(object):
         if nb['recv_up_from'] is not None:
             _lib.check(unpack(h, 1, self._vp(recv_up)), h)
 
-    def reduce_cfl(self, dev):
-        """max over ranks of the CFL slot written by the sweep kernel, on the device, then one read."""
+    def all_reduce_cfl(self, dev):
+        """max over ranks of the CFL slot written by the sweep kernels, in place on the device (petclaw/cfl.py:36)."""
         self.dist.all_reduce(dev.cfl_tensor, op=self.dist.ReduceOp.MAX)
-        if self.speculative:
-            self._exchange(dev, dev.L.claw_halo_pack_next, dev.L.claw_halo_unpack_next, self.send_lo, self.send_up,
-                           self.recv_lo, self.recv_up)
-            dev.ghosts_current = True      # true for the new buffer if accepted, and still true for the old one if not
-        return float(dev.cfl_tensor.item())

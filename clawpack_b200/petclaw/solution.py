@@ -3,6 +3,8 @@
 Frame output replaces PetClaw's parallel petsc/hdf5 writers (petclaw/fileio/) by a gather: every rank contributes
 its slab (``get_q_global`` -- the replacement of ``petclaw/state.py:267-287``), rank 0 writes ONE set of files in
 the serial ascii layout for the global grid, so a file written by an N-GPU run is byte-identical to the serial one."""
+import numpy as np
+
 from ..pyclaw import geometry as _geom
 from ..pyclaw import state as _state
 from ..pyclaw.solution import Solution as _Solution
@@ -21,6 +23,9 @@ class Solution(_Solution):
         st = self.state
         q = st.get_q_global()                                  # collective: every rank takes part
         aux = st.get_aux_global() if (st.num_aux > 0 and write_aux) else None
+        if write_p and st.p is None:
+            raise Exception('write_p is set but state.p has not been computed (set state.mp and a compute_p function)')
+        pglob = st._gather(np.asarray(st.p)) if write_p else None      # collective as well
         if util.rank() == 0:
             gdims = [_geom.Dimension(d.lower, d.upper, d.num_cells, name=d.name, units=d.units)
                      for d in st.patch.dimensions]             # the patch keeps the GLOBAL dimensions
@@ -29,6 +34,8 @@ class Solution(_Solution):
             gst.q = q
             if aux is not None:
                 gst.aux = aux
+            if pglob is not None:
+                gst.p = pglob
             gst.t = st.t
             gst.problem_data = st.problem_data
             gst.grid.mapc2p = st.grid._mapc2p

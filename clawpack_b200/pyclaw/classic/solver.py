@@ -23,6 +23,19 @@ from ..solver import Solver
 
 class ClawSolver(Solver):
     """Generic classic solver; see ClawSolver2D / ClawSolver3D."""
+    # On the device-resident path these live in the device's control block while step attempts are queued
+    # (cuda_classic.DeviceStepper.evolve): reading one waits for the queue, writing one hands authority back to the host.
+    from ..cuda_classic import DeviceMirrored as _M
+    dt = _M('dt')
+    dt_max = _M('dt_max')
+    dt_variable = _M('dt_variable')
+    dt_old = _M('dt_old')
+    cfl_max = _M('cfl_max')
+    cfl_desired = _M('cfl_desired')
+    cfl = _M('cfl')
+    status = _M('status')
+    step_log = _M('step_log')
+    del _M
 
     def __init__(self, riemann_solver=None, claw_package=None):
         self.num_ghost = 2
@@ -96,9 +109,9 @@ class ClawSolver(Solver):
         m[6] = state.num_aux
         self._method = m
 
-    def _device_path_eligible(self):
+    def _device_path_eligible(self, dev_is_mine=False):
         from ..solver import BC
-        if self.fmod is not None or self.before_step is not None or self.step_source is not None:
+        if (self.fmod is not None and not dev_is_mine) or self.before_step is not None or self.step_source is not None:
             return False
         # BC.custom on q needs the host every step; BC.custom on aux alone does not: aux is static on the device
         # path, so the user's aux ghost fill is evaluated once at setup (cuda_classic.DeviceStepper)
@@ -143,8 +156,28 @@ class ClawSolver(Solver):
 
     def teardown(self):
         if self._dev is not None:
-            self._dev.close()
+            self._dev.close()            # downloads the final state first, then detaches from the State
             self._dev = None
+
+    def evolve_to_time(self, solution, tend=None):
+        """solver.py:554-666.  On the device-resident path the loop (get_dt, the step, accept/reject, the retry with a
+        smaller dt) runs on the device: attempts are queued without reading the CFL number back, and ``solver.dt``,
+        ``solver.cfl``, ``solver.status``, ``solver.step_log`` and ``solution.t`` catch up when they are read."""
+        if not self._is_set_up:
+            self.setup(solution)
+        if self._dev is not None and not self._device_path_eligible(dev_is_mine=True):
+            self._leave_device_path(solution)        # a host callback was set after setup(): plug-in mode from now on
+        if self._dev is not None:
+            return self._dev.evolve(self, solution, tend)
+        return super(ClawSolver, self).evolve_to_time(solution, tend)
+
+    def _leave_device_path(self, solution):
+        from .. import cuda_classic
+        self._dev.close()
+        self._dev = None
+        self.fmod = cuda_classic.fmod(self.num_dim, precision=self.cuda_precision)
+        self._allocate_workspace(solution)
+        self._allocate_bc_arrays(solution.states[0])
 
     # ---- retry hooks: buffer swap instead of q_backup when device-resident -------------------
     def _save_for_retry(self, state):

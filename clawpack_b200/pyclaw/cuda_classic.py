@@ -8,12 +8,50 @@ libclawcuda.so (include/clawcuda.h), via ctypes.  PyTorch only provides the devi
   use its Fortran module.
 """
 import ctypes
+import math
+import weakref
 
 import numpy as np
 
 from .. import _lib
 
 _MODES = {'strict': 0, 'fast': 1}
+LOG_CAP = 4096        # attempts the device log ring holds (csrc/clawcuda.cu)
+BATCH = 64            # attempts queued between two reads of the control block (evolve_to_time with an end time)
+# control block words (include/clawcuda.h)
+W_T, W_DT, W_DTMAX, W_CFLDES, W_CFLMAX, W_CFL = 1, 2, 3, 4, 5, 6
+W_DTMIN, W_DTMAXS, W_CFLMAXS, W_NUMSTEPS, W_DONE, W_ERROR = 10, 11, 12, 13, 15, 16
+W_DTVAR, W_HAVEOLD, W_ATTEMPTS = 18, 19, 23
+
+
+class DeviceMirrored(object):
+    """Solver attribute whose authoritative value may live in the device's control block while step attempts are
+    queued: reading it waits for the queue and refreshes the host copy; writing it makes the host copy authoritative
+    again (it is uploaded with the next claw_ctl_begin)."""
+
+    def __init__(self, name):
+        self.slot = '_m_' + name
+
+    def __get__(self, obj, cls):
+        if obj is None:
+            return self
+        d = obj.__dict__
+        dev = d.get('_dev')
+        if dev is not None and dev.pending:
+            dev.drain()
+        try:
+            return d[self.slot]
+        except KeyError:
+            raise AttributeError(self.slot[3:])
+
+    def __set__(self, obj, value):
+        d = obj.__dict__
+        dev = d.get('_dev')
+        if dev is not None:
+            if dev.pending:
+                dev.drain()
+            dev.host_ctl_dirty = True
+        d[self.slot] = value
 
 
 def _iarr(values, n=None):
@@ -82,9 +120,20 @@ class DeviceStepper(object):
         # host <-> device coherence of state.q
         self.host_valid = True      # state._q equals the device's current buffer
         self.host_dirty = True      # state._q may have been changed on the host since the last upload
-        self.pre_step_hook = None   # e.g. the multi-GPU ghost exchange (petclaw)
-        self.post_step_hook = None  # e.g. the CFL all-reduce
-        self.ghosts_current = False # multi-GPU: the slab-face ghost rows of the CURRENT buffer hold the neighbours' data
+        self.aux_dirty = False      # state.aux was replaced on the host since the upload at setup
+        self.halo = None            # multi-rank runs: petclaw.device_halo.DeviceHalo (ghost exchange + CFL all-reduce)
+        self.halo_aux = None        # the same for the aux ghost planes (exchanged when aux is uploaded)
+        # device-resident step control (claw_ctl_*)
+        self.pending = False        # attempts are queued whose outcome the host has not read yet
+        self.host_ctl_dirty = True  # the host's t / dt / cfl limits / status are newer than the device's
+        self.ctl_started = False
+        self.read_attempts = 0      # attempts whose log entries the host has read
+        self.queued = 0             # attempts queued since the last read
+        self._done = False
+        self._words = np.zeros(32, dtype=np.float64)
+        self._log = np.zeros(3 * LOG_CAP, dtype=np.float64)
+        self.solver_ref = weakref.ref(solver)
+        self.state_ref = weakref.ref(state)
         if state.num_aux > 0:
             if any(b == 0 for b in list(solver.aux_bc_lower) + list(solver.aux_bc_upper)):
                 # BC.custom aux faces (e.g. edge velocities on the extended grid, examples/advection_2d_annulus):
@@ -100,6 +149,8 @@ class DeviceStepper(object):
 
     # ---- coherence protocol used by State.q --------------------------------------------------
     def sync_host(self, state):
+        if self.pending:
+            self.drain()
         if not self.host_valid:
             q = state._q
             if not (q.flags['F_CONTIGUOUS'] and q.flags['WRITEABLE'] and q.flags['OWNDATA']):
@@ -110,33 +161,178 @@ class DeviceStepper(object):
         self.host_dirty = True          # the caller may write through the returned array
 
     def host_modified(self):
+        if self.pending:
+            self.drain()
         self.host_valid = True
         self.host_dirty = True
 
     def _upload_if_needed(self, state):
         if self.host_dirty:
+            if self.pending:
+                self.drain()
             q = np.asfortranarray(state._q, dtype=np.float64)
             _lib.check(self.L.claw_put_q(self.handle, q.ctypes.data_as(ctypes.c_void_p)), self.handle)
             self.host_dirty = False
-            self.ghosts_current = False
+        if self.aux_dirty:                                   # state.aux = new_array after setup
+            if state.num_aux > 0:
+                aux = np.asfortranarray(state.aux, dtype=np.float64)
+                _lib.check(self.L.claw_put_aux(self.handle, aux.ctypes.data_as(ctypes.c_void_p)), self.handle)
+                if self.halo_aux is not None:
+                    self.halo_aux.exchange_aux(self)
+            self.aux_dirty = False
+
+    # ---- device-resident evolve_to_time (solver.py:554-666 without a host round trip per step) -------------------
+    def _pack_host_words(self, solver, state):
+        d = solver.__dict__
+        w = np.zeros(32, dtype=np.float64)
+        iw = w.view(np.int64)
+        w[W_T] = state._t
+        w[W_DT] = d['_m_dt']
+        w[W_DTMAX] = d['_m_dt_max']
+        w[W_CFLDES] = d['_m_cfl_desired']
+        w[W_CFLMAX] = d['_m_cfl_max']
+        w[W_CFL] = d['_m_cfl'].get_cached_max()
+        st = d['_m_status']
+        w[W_DTMIN], w[W_DTMAXS], w[W_CFLMAXS] = st['dtmin'], st['dtmax'], st['cflmax']
+        iw[W_NUMSTEPS] = int(st['numsteps'])
+        iw[W_DTVAR] = 1 if d['_m_dt_variable'] else 0
+        iw[W_HAVEOLD] = 0 if d['_m_dt_old'] is None else 1
+        return w
+
+    def _attempt(self, n):
+        """Queue n step attempts: [ghost exchange] + ghost fill + sweep + [CFL all-reduce] + control kernel."""
+        L, h = self.L, self.handle
+        if self.halo is None:
+            _lib.check(L.claw_ctl_attempts(h, _lib.dp(self.delta), int(n), 1), h)
+        else:
+            for _ in range(n):
+                self.halo.exchange(self)
+                _lib.check(L.claw_ctl_sweep(h, _lib.dp(self.delta), 1), h)
+                self.halo.all_reduce_cfl(self)
+                _lib.check(L.claw_ctl_end(h), h)
+        self.queued += n
+        self.pending = True
+
+    def evolve(self, solver, solution, tend):
+        state = solution.state
+        take_one = tend is None
+        self._upload_if_needed(state)
+        d = solver.__dict__
+        if not d['_m_dt_variable']:
+            if self.pending:
+                self.drain()
+            if take_one:
+                max_steps = 1
+            else:
+                tstart, dt = state._t, d['_m_dt']
+                max_steps = int((tend - tstart + 1e-10) / dt)
+                if abs(max_steps * dt - (tend - tstart)) > 1e-5 * (tend - tstart):
+                    raise Exception('dt does not divide (tend-tstart) and dt is fixed!')
+        else:
+            max_steps = int(solver.max_steps)
+            if d['_m_dt_variable'] == 1 and d['_m_cfl_desired'] > d['_m_cfl_max']:
+                raise Exception('Variable time-stepping and desired CFL > maximum CFL')
+        words = None
+        if self.host_ctl_dirty or not self.ctl_started:
+            if self.pending:
+                self.drain()
+            words = self._pack_host_words(solver, state)
+        _lib.check(self.L.claw_ctl_begin(self.handle, None if words is None else words.ctypes.data_as(ctypes.c_void_p),
+                                         float('inf') if take_one else float(tend), 1 if take_one else 0,
+                                         max_steps), self.handle)
+        self.host_ctl_dirty = False
+        self.ctl_started = True
+        self.pending = True
+        gauges = len(state.grid.gauges) > 0
+        if take_one:
+            self._attempt(1)
+            if gauges or self.queued >= LOG_CAP - BATCH:
+                self._drain_with_gauges(solver, solution)
+            return solver.__dict__['_m_status']
+        while True:
+            self.drain()
+            if self._done:
+                break
+            if gauges:
+                n = 1
+            else:
+                t, dt = state._t, d['_m_dt']
+                left = (tend - t) / dt if dt > 0 else 1.0
+                n = int(min(BATCH, max(1.0, math.ceil(left)))) if math.isfinite(left) else 1
+            self._attempt(n)
+            if gauges:
+                self._drain_with_gauges(solver, solution)
+        return solver.__dict__['_m_status']
+
+    def _drain_with_gauges(self, solver, solution):
+        n0 = solver.__dict__['_m_status']['numsteps']
+        self.drain()
+        if solver.__dict__['_m_status']['numsteps'] > n0:
+            solver.write_gauge_values(solution)
+
+    def drain(self):
+        """Wait for the queued attempts and refresh the host's copies of t, dt, the CFL number, solver.status and the
+        step log from the device's control block."""
+        solver, state = self.solver_ref(), self.state_ref()
+        n = ctypes.c_int(0)
+        _lib.check(self.L.claw_ctl_read(self.handle, self._words.ctypes.data_as(ctypes.c_void_p), self.read_attempts,
+                                        self._log.ctypes.data_as(ctypes.c_void_p), LOG_CAP, ctypes.byref(n)),
+                   self.handle)
+        self.pending = False
+        self.queued = 0
+        w, iw = self._words, self._words.view(np.int64)
+        self.read_attempts = int(iw[W_ATTEMPTS])
+        self._done = bool(iw[W_DONE])
+        entries = [(float(self._log[3 * k]), float(self._log[3 * k + 1]), bool(self._log[3 * k + 2] != 0.0))
+                   for k in range(n.value)]
+        if any(e[2] for e in entries):
+            self.host_valid = False
+        if state is not None:
+            state._t = float(w[W_T])
+        if solver is not None:
+            d = solver.__dict__
+            d['_m_dt'] = float(w[W_DT])
+            d['_m_cfl'].set_global_max(float(w[W_CFL]))
+            st = d['_m_status']
+            st['dtmin'], st['dtmax'], st['cflmax'] = float(w[W_DTMIN]), float(w[W_DTMAXS]), float(w[W_CFLMAXS])
+            st['numsteps'] = int(iw[W_NUMSTEPS])
+            if iw[W_HAVEOLD] and d['_m_dt_old'] is None:
+                d['_m_dt_old'] = entries[0][0] if entries else float(w[W_DT])
+            d['_m_step_log'].extend(entries)
+            if entries:
+                d['accept_step'] = entries[-1][2]
+        err = int(iw[W_ERROR])
+        if err:
+            iw[W_ERROR] = 0
+            self.host_ctl_dirty = True          # the next begin starts from the host's (consistent) values
+            if err == 1:
+                raise Exception('CFL too large, giving up!')
+            raise Exception('Maximum number of timesteps have been taken')
 
     # ---- stepping ------------------------------------------------------------------------------
     def step(self, state, dt):
-        """ghost fill + fused sweep on the device; returns the (local) CFL number."""
+        """HOST-driven attempt (``solver.step`` / ``step_hyperbolic`` called directly): ghost fill + fused sweep, then
+        the CFL number is read back; returns the global CFL number.  ``evolve_to_time`` does not come through here."""
         self._upload_if_needed(state)
-        if self.pre_step_hook is not None:
-            self.pre_step_hook(self)
-        cfl = ctypes.c_double(0.0)
-        if self.post_step_hook is None:
-            _lib.check(self.L.claw_step(self.handle, _lib.dp(self.delta), float(dt), 1, ctypes.byref(cfl)),
-                       self.handle)
-            return cfl.value
+        if self.pending:
+            self.drain()
+        self.host_ctl_dirty = True
+        self.ctl_started = False
+        if self.halo is not None:
+            self.halo.exchange(self)
         _lib.check(self.L.claw_step_launch(self.handle, _lib.dp(self.delta), float(dt), 1), self.handle)
-        return self.post_step_hook(self)
+        if self.halo is not None:
+            self.halo.all_reduce_cfl(self)
+            return float(self.cfl_tensor.item())
+        cfl = ctypes.c_double(0.0)
+        _lib.check(self.L.claw_cfl_wait(self.handle, ctypes.byref(cfl)), self.handle)
+        return cfl.value
 
     def get_cells(self, state, cells):
         """q[:, cell] for a list of interior cell index tuples (gauges) without downloading the array."""
         self._upload_if_needed(state)
+        if self.pending:
+            self.drain()
         idx = np.ascontiguousarray(cells, dtype=np.intc).reshape(len(cells), self.num_dim)
         out = np.empty((len(cells), state.num_eqn), dtype=np.float64)
         _lib.check(self.L.claw_get_cells(self.handle, len(cells), _lib.ip(idx), _lib.dp(out)), self.handle)
@@ -145,6 +341,7 @@ class DeviceStepper(object):
     def accept(self):
         _lib.check(self.L.claw_accept(self.handle), self.handle)
         self.host_valid = False
+        self.host_ctl_dirty = True
 
     def reject(self):
         _lib.check(self.L.claw_reject(self.handle), self.handle)
@@ -157,14 +354,23 @@ class DeviceStepper(object):
     def synchronize(self):
         _lib.check(self.L.claw_sync(self.handle), self.handle)
 
-    def close(self):
+    def close(self, sync=True):
+        """Bring the final state back to the host, detach from the State, destroy the handle."""
         if self.handle:
+            state = self.state_ref()
+            if state is not None and state.__dict__.get('_device') is self:
+                try:
+                    if sync:
+                        self.sync_host(state)
+                finally:
+                    state._device = None
             self.L.claw_destroy(self.handle)
             self.handle = ctypes.c_void_p()
+            self.pending = False
 
     def __del__(self):
         try:
-            self.close()
+            self.close(sync=False)
         except Exception:
             pass
 

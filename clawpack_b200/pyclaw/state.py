@@ -24,18 +24,47 @@ class State(object):
         self.p = None
         self.F = None
         self.problem_data = {}
-        self.t = 0.
+        self._device = None          # set by a CUDA solver (cuda_classic.DeviceStepper): owner of the device copy
+        self._t = 0.
         self.index_capa = -1
         self.keep_gauges = False
         self.gauge_data = []
-        self._device = None          # set by a CUDA solver: object with download_q(array) / mark_host_dirty()
         self._q = self.new_array(num_eqn)
-        self.aux = self.new_array(num_aux)
+        self._aux = self.new_array(num_aux)
 
     def __getattr__(self, key):
         if key in State._grid_attrs:
             return getattr(self.grid, key)
         raise AttributeError("'State' object has no attribute '" + key + "'")
+
+    # ---- t: advanced on the device while step attempts are queued (cuda_classic.DeviceStepper.evolve) ----------
+    @property
+    def t(self):
+        dev = self.__dict__.get('_device')
+        if dev is not None and dev.pending:
+            dev.drain()
+        return self._t
+
+    @t.setter
+    def t(self, value):
+        dev = self.__dict__.get('_device')
+        if dev is not None:
+            if dev.pending:
+                dev.drain()
+            dev.host_ctl_dirty = True
+        self._t = value
+
+    # ---- aux: static on the device path; assigning a new array re-uploads it before the next step ------------
+    @property
+    def aux(self):
+        return self._aux
+
+    @aux.setter
+    def aux(self, value):
+        self._aux = value
+        dev = self.__dict__.get('_device')
+        if dev is not None:
+            dev.aux_dirty = True
 
     # ---- q with lazy device synchronisation ------------------------------------------------
     @property

@@ -152,6 +152,40 @@ int claw_accept(claw_solver* h);
 int claw_reject(claw_solver* h);
 int claw_sync(claw_solver* h);
 
+/* ---- device-resident step control -----------------------------------------------------------------------------------
+   Solver.evolve_to_time / get_dt / accept_reject_step (pyclaw/src/pyclaw/solver.py:524-666) driven from the device: the
+   loop state -- t, dt, the CFL number of the running attempt, which q buffer is current, solver.status, whether the loop
+   has ended -- lives in a 32-word control block at the start of the work buffer (word 0 is the CFL slot, see
+   claw_cfl_device_ptr).  The host queues step attempts WITHOUT reading the CFL number back: the kernels of attempt n+1
+   take dt and the current buffer from what the control kernel of attempt n decided, a rejected attempt is simply
+   retried with the new dt from the unchanged buffer (no q_backup copy), and attempts queued past the end of the loop are
+   no-ops.  The arithmetic of dt, t and accept/reject is the reference's operation by operation (same bits).
+
+   Control block as 64-bit words (doubles unless noted):
+     0 CFL slot   1 t   2 dt   3 dt_max   4 cfl_desired   5 cfl_max   6 cfl of the last attempt   7 tstart   8 tend
+     9 told   10 status dtmin   11 status dtmax   12 status cflmax   13 status numsteps (int64)   14 current buffer (int64)
+     15 done (int64)   16 error (int64: 1 = CFL too large with fixed dt, 2 = max_steps reached)   17 take_one_step
+     18 dt_variable   19 dt_old is set   20 loop counter n   21 accepted steps of this call   22 max_steps
+     23 attempts logged so far   24..31 reserved                                  (17..23 int64)
+
+   claw_ctl_begin   start of one evolve_to_time call: tstart = t, done = 0, then the get_dt of the first attempt.
+                    host_words != NULL uploads the host's values of words 1..6, 10..13, 18, 19 first (required on the
+                    first call; later calls pass NULL to carry on from the device's state without a read-back).
+   claw_ctl_attempts  queue n attempts: each = [ghost fill] + sweep(s) + control kernel (single-rank runs; n >= 2 goes
+                    through a CUDA graph of one attempt, captured once per configuration).
+   claw_ctl_sweep / claw_ctl_end  the two halves of ONE attempt for multi-rank runs: the caller all-reduces (max) the
+                    CFL slot across ranks in between (ncclAllReduce on the same stream; petclaw/cfl.py:36).
+   claw_ctl_read    wait for everything queued; returns the control block and the log entries (dt, cfl, accepted) of
+                    attempts [from_attempt, word 23) -- at most max_entries, the newest ones if more are pending. */
+int claw_ctl_begin(claw_solver* h, const double* host_words, double tend, int take_one_step, long long max_steps);
+int claw_ctl_attempts(claw_solver* h, const double* delta, int n, int fill_ghosts);
+int claw_ctl_sweep(claw_solver* h, const double* delta, int fill_ghosts);
+int claw_ctl_end(claw_solver* h);
+int claw_ctl_read(claw_solver* h, double* words32, long long from_attempt, double* log3, int max_entries,
+                  int* n_entries);
+/* CUDA graph for claw_ctl_attempts on (default) / off */
+int claw_ctl_use_graph(claw_solver* h, int on);
+
 /* slab-decomposition ghost exchange along the slowest dimension (replaces DMDA.globalToLocal,
    petclaw/state.py:223-231): pack the 2 interior rows/planes next to face `side` (0 lower, 1 upper)
    of the current q into a contiguous device buffer / unpack a received buffer into that face's ghosts */
