@@ -80,9 +80,16 @@ def make_claw_distributed(sc, kernel_language='CUDA', **solver_kw):
     num_aux = 0 if sc['aux'] is None else sc['aux'].shape[0]
     state = pyclaw.State(domain, sc['q'].shape[0], num_aux)
     s0, s1 = state.patch.slab
-    state.q[...] = np.asarray(sc['q'])[..., s0:s1]
-    if num_aux:
-        state.aux[...] = np.asarray(sc['aux'])[..., s0:s1]
+    if sc.get('slab') is not None:               # the scenario was built for this rank's slab only (global centres)
+        if tuple(sc['slab']) != (s0, s1):
+            raise Exception('scenario slab %r does not match the decomposition %r' % (tuple(sc['slab']), (s0, s1)))
+        state.q[...] = np.asarray(sc['q'])
+        if num_aux:
+            state.aux[...] = np.asarray(sc['aux'])
+    else:
+        state.q[...] = np.asarray(sc['q'])[..., s0:s1]
+        if num_aux:
+            state.aux[...] = np.asarray(sc['aux'])[..., s0:s1]
     state.problem_data.update(sc['problem_data'])
     claw = pyclaw.Controller()
     claw.tfinal = sc['tfinal']

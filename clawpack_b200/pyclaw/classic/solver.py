@@ -131,7 +131,8 @@ class ClawSolver(Solver):
             if self.num_dim > 1 and self._device_path_eligible():
                 self._dev = cuda_classic.DeviceStepper(self, solution.state)
             else:
-                self.fmod = cuda_classic.fmod(self.num_dim, precision=self.cuda_precision)
+                if self.fmod is None:        # a user-supplied plug-in (solver.fmod = ...) is kept, as in the reference
+                    self.fmod = cuda_classic.fmod(self.num_dim, precision=self.cuda_precision)
                 self._allocate_workspace(solution)
                 self._allocate_bc_arrays(solution.states[0])
         elif self.kernel_language == 'Fortran':

@@ -25,8 +25,12 @@ def centers(lower, upper, n):
     return lower + (np.arange(n) + 0.5) * delta
 
 
-def _grid(lower, upper, n):
+def _grid(lower, upper, n, slab=None):
+    """Cell-centre meshgrid; ``slab = (s0, s1)`` keeps only cells [s0, s1) of the LAST dimension (one rank's share of a
+    slab-decomposed run: the centres are still those of the global grid, bit for bit)."""
     cs = [centers(lo, up, k) for lo, up, k in zip(lower, upper, n)]
+    if slab is not None:
+        cs[-1] = cs[-1][slab[0]:slab[1]]
     return np.meshgrid(*cs, indexing='ij')
 
 
@@ -36,7 +40,7 @@ def _base(rp, lower, upper, n, q, **kw):
              dimensional_split=True, transverse_waves=None, cfl_max=1.0, cfl_desired=0.9,
              dt_initial=0.1, bc_lower=None, bc_upper=None, aux_bc_lower=None, aux_bc_upper=None,
              tfinal=1.0, num_output_times=10, index_capa=-1, custom_aux_bc_lower=None, custom_aux_bc_upper=None,
-             mapc2p=None, step_source=None, source_split=1, before_step=None, fwave=False, gauges=None, custom_bc_lower_full=None,
+             slab=None, mapc2p=None, step_source=None, source_split=1, before_step=None, fwave=False, gauges=None, custom_bc_lower_full=None,
              compute_gauge_values=None)
     d.update(kw)
     return d
@@ -408,19 +412,19 @@ def quadrants(mx=100, my=100, tfinal=0.8, riemann_solver='roe'):
                  bc_lower=[EXTRAP, EXTRAP], bc_upper=[EXTRAP, EXTRAP], tfinal=tfinal)
 
 
-def radial_dam_break(mx=150, my=150, tfinal=2.5, riemann_solver='roe'):
-    X, Y = _grid((-2.5, -2.5), (2.5, 2.5), (mx, my))
+def radial_dam_break(mx=150, my=150, tfinal=2.5, riemann_solver='roe', slab=None):
+    X, Y = _grid((-2.5, -2.5), (2.5, 2.5), (mx, my), slab)
     r = np.sqrt((X - 0.) ** 2 + (Y - 0.) ** 2)
-    q = np.zeros((3, mx, my), order='F')
+    q = np.zeros((3,) + X.shape, order='F')
     q[0] = 2. * (r <= 0.5) + 1. * (r > 0.5)
     rp = 'shallow_hlle_2D' if riemann_solver == 'hlle' else 'shallow_roe_with_efix_2D'     # radial_dam_break.py:41-44
     return _base(rp, (-2.5, -2.5), (2.5, 2.5), (mx, my), q,
                  problem_data={'grav': 1.0}, limiters=MC, dimensional_split=True,
-                 bc_lower=[EXTRAP, EXTRAP], bc_upper=[WALL, WALL], tfinal=tfinal)
+                 bc_lower=[EXTRAP, EXTRAP], bc_upper=[WALL, WALL], tfinal=tfinal, slab=slab)
 
 
 def shock_bubble(mx=8192, my=8192, ly=1.0, y_offset=0.0, ly_total=None, dimensional_split=False,
-                 transverse_waves=2, tfinal=0.02):
+                 transverse_waves=2, tfinal=0.02, slab=None):
     """BASELINE configs 2/5: 4-equation Euler, planar Mach shock at x=0.2 hitting a low-density
     bubble; unsplit with transverse corrections, MC limiter, extrapolation BCs, dt_initial=0.1 so
     the first step is a deliberate reject.  ``ly``/``y_offset``/``ly_total`` describe a y-slab of a
@@ -431,6 +435,8 @@ def shock_bubble(mx=8192, my=8192, ly=1.0, y_offset=0.0, ly_total=None, dimensio
         ly_total = ly
     x = centers(0., 1., mx)
     y = centers(y_offset, y_offset + ly, my)
+    if slab is not None:                       # one rank's rows of the global grid (same centres, bit for bit)
+        y = y[slab[0]:slab[1]]
     X, Y = np.meshgrid(x, y, indexing='ij')
     pinf = 5.
     rinf = (gamma1 + pinf * (gamma + 1.)) / ((gamma + 1.) + gamma1 * pinf)
@@ -440,7 +446,7 @@ def shock_bubble(mx=8192, my=8192, ly=1.0, y_offset=0.0, ly_total=None, dimensio
     shocked = X < 0.2
     bubble = rr <= 0.2
     rho = np.where(shocked, rinf, np.where(bubble, 0.1, 1.0))
-    q = np.empty((4, mx, my), order='F')
+    q = np.empty((4,) + X.shape, order='F')
     q[0] = rho
     q[1] = np.where(shocked, rinf * vinf, 0.0)
     q[2] = 0.0
@@ -448,24 +454,24 @@ def shock_bubble(mx=8192, my=8192, ly=1.0, y_offset=0.0, ly_total=None, dimensio
     return _base('euler_4wave_2D', (0., y_offset), (1., y_offset + ly), (mx, my), q,
                  problem_data={'gamma': gamma}, limiters=MC, dimensional_split=bool(dimensional_split),
                  transverse_waves=int(transverse_waves), cfl_max=1.0, cfl_desired=0.9, dt_initial=0.1,
-                 bc_lower=[EXTRAP, EXTRAP], bc_upper=[EXTRAP, EXTRAP], tfinal=tfinal)
+                 bc_lower=[EXTRAP, EXTRAP], bc_upper=[EXTRAP, EXTRAP], tfinal=tfinal, slab=slab)
 
 
 def acoustics_3d(mx=30, my=30, mz=30, heterogeneous=True, dimensional_split=None, transverse_waves=22,
-                 periodic=False, tfinal=2.0, num_output_times=10):
+                 periodic=False, tfinal=2.0, num_output_times=10, slab=None):
     """pyclaw/examples/acoustics_3d_variable/acoustics_3d_interface.py:25-135: problem='heterogeneous'
     (impedance/sound speed 1 for x<0, 2 for x>=0; unsplit, lower wall / upper periodic) or
     'homogeneous' (dimension-split, all periodic).  ``periodic=True`` makes every face periodic
     (sharded runs).  mx=my=mz=15 with the defaults reproduces the stored vector
     verify_classic_heterogeneous.txt."""
-    X, Y, Z = _grid((-1., -1., -1.), (1., 1., 1.), (mx, my, mz))
+    X, Y, Z = _grid((-1., -1., -1.), (1., 1., 1.), (mx, my, mz), slab)
     zl, cl = 1.0, 1.0
     zr, cr = (2.0, 2.0) if heterogeneous else (1.0, 1.0)
-    aux = np.empty((2, mx, my, mz), order='F')
+    aux = np.empty((2,) + X.shape, order='F')
     aux[0] = zl * (X < 0.) + zr * (X >= 0.)
     aux[1] = cl * (X < 0.) + cr * (X >= 0.)
     x0, y0, z0 = -0.5, 0., 0.
-    q = np.zeros((4, mx, my, mz), order='F')
+    q = np.zeros((4,) + X.shape, order='F')
     if heterogeneous:
         r = np.sqrt((X - x0) ** 2 + (Y - y0) ** 2 + (Z - z0) ** 2)
         width = 0.1
@@ -482,7 +488,7 @@ def acoustics_3d(mx=30, my=30, mz=30, heterogeneous=True, dimensional_split=None
                  limiters=MC, dimensional_split=bool(dimensional_split), transverse_waves=int(transverse_waves),
                  cfl_max=1.0, cfl_desired=0.9, dt_initial=0.1,
                  bc_lower=lo, bc_upper=up, aux_bc_lower=lo, aux_bc_upper=up,
-                 tfinal=tfinal, num_output_times=num_output_times)
+                 tfinal=tfinal, num_output_times=num_output_times, slab=slab)
 
 
 def acoustics_3d_general(mx=18, my=15, mz=13, **kw):
