@@ -51,6 +51,9 @@ template <class RP, int NW> struct Smem2ws {
 // UNR > 1 unrolls the march loop so that the row-to-row hand-over of the carried state (q1 <- qN, qn0 <- qn1 <- qn2,
 // c1 <- cN) becomes register renaming instead of moves: statically (scripts/sass_mix.py) 1476 -> 1430 instructions per
 // march step for the headline Euler kernel at UNR = 2 with no spills (UNR = 3 spills); unmeasured on the GPU so far.
+// (Measured and dropped in round 2, profiles/r02_f_variants.jsonl: 2 / 4 / 8 warps per CTA are no faster than 1 -- 4.77,
+// 4.82, 5.29 ms against 4.78 -- and a __syncthreads per march step, tried to keep the warps of a CTA at the same place of
+// the 23 KB loop body for the instruction cache, costs more than it gains: 4.80 / 4.97 / 5.70 ms.)
 template <class RP, int NW, int MINB = 1, int SPEC = 0, int UNR = 1>
 __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_constant__ Sweep2Params P) {
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE, NT = NW * 32;
@@ -61,6 +64,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
   constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
   using S = Smem2ws<RP, NW>;
   constexpr int TX = 28;                                   // owned columns per warp
+  // Fast mode, specialised kernel: the transverse corrections are carried as the unscaled sums G1 = bm(i+1) + bm'(i),
+  // G2 = bp(i+1) + bp'(i) and scaled once by kxy = (dt/dx)(dt/dy)/2 where they enter q (gadd = -(dt/2dx) G, then
+  // -dt/dy gadd, flux2.f90:185-203 / step2.f90:139-147): two FP64 instructions less per component and sweep.
+#ifdef CLAW_STRICT
+  constexpr bool FG = false;
+#else
+  constexpr bool FG = SP;
+#endif
   CLAW_DYN_SMEM(smem);
   const int t = threadIdx.x, lane = t & 31;
   double* const syw = smem + S::OFF_YW * NT + t;
@@ -76,6 +87,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
 
   CLAW_RESOLVE_STEP2(P, qin, qout, dtdx, dtdy);
   const double hdx = 0.5 * dtdx, hdy = 0.5 * dtdy;
+  [[maybe_unused]] const double kxy = hdx * dtdy;
   const bool second = SP ? true : (P.order != 1);
   const bool limit = SP ? true : (second && (P.limit != 0));
   const int mt = SP ? 2 : P.mtrans;
@@ -205,12 +217,19 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
           // cell J of this y-pencil: interface J (carried) and interface J+1 (just finished)
 #pragma unroll
           for (int m = 0; m < M; ++m) {
-            const double g1 = (0.0 - hdy * bmA[m]) - hdy * yI_bm[m];      // flux2.f90:185-203
-            const double g2 = (0.0 - hdy * bpA[m]) - hdy * yI_bp[m];
-            // step2.f90:223-225: qadd - dtdy*(fadd(j+1)-fadd(j)) - dtdx*(gadd(2)-gadd(1))
-            ycomb[rot<M>(m)] = (qadd[m] - dtdy * (fadd[m] - yI_fadd[m])) - dtdx * (g2 - g1);
-            gy1[rot<M>(m)] = g1;
-            gy2[rot<M>(m)] = g2;
+            if constexpr (FG) {
+              const double G1 = bmA[m] + yI_bm[m], G2 = bpA[m] + yI_bp[m];
+              ycomb[rot<M>(m)] = fma(kxy, G2 - G1, qadd[m] - dtdy * (fadd[m] - yI_fadd[m]));
+              gy1[rot<M>(m)] = G1;
+              gy2[rot<M>(m)] = G2;
+            } else {
+              const double g1 = (0.0 - hdy * bmA[m]) - hdy * yI_bm[m];      // flux2.f90:185-203
+              const double g2 = (0.0 - hdy * bpA[m]) - hdy * yI_bp[m];
+              // step2.f90:223-225: qadd - dtdy*(fadd(j+1)-fadd(j)) - dtdx*(gadd(2)-gadd(1))
+              ycomb[rot<M>(m)] = (qadd[m] - dtdy * (fadd[m] - yI_fadd[m])) - dtdx * (g2 - g1);
+              gy1[rot<M>(m)] = g1;
+              gy2[rot<M>(m)] = g2;
+            }
             yI_fadd[m] = fadd[m]; yI_bm[m] = bmP[m]; yI_bp[m] = bpP[m];
           }
         }
@@ -293,12 +312,19 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
         const double amdqR = shfl_right(amdq[m]), faddR = shfl_right(fadd[m]);
         const double bmAR = shfl_right(bmA[m]), bpAR = shfl_right(bpA[m]);
         const double qadd = (0.0 - dtdx * apdq[m]) - dtdx * amdqR;         // flux2.f90:105-108
-        const double g1 = (0.0 - hdx * bmAR) - hdx * bmP[m];              // flux2.f90:185-203
-        const double g2 = (0.0 - hdx * bpAR) - hdx * bpP[m];
-        // step2.f90:139-147, pencil J+1: rows J, J+1, J+2
-        qn0[m] = qn0[m] - dtdy * g1;
-        qn1[m] = ((qn1[m] + qadd) - dtdx * (faddR - fadd[m])) - dtdy * (g2 - g1);
-        qn2[m] = qN[m] + dtdy * g2;
+        if constexpr (FG) {
+          const double G1 = bmAR + bmP[m], G2 = bpAR + bpP[m];
+          qn0[m] = fma(kxy, G1, qn0[m]);
+          qn1[m] = fma(kxy, G2 - G1, (qn1[m] + qadd) - dtdx * (faddR - fadd[m]));
+          qn2[m] = fma(-kxy, G2, qN[m]);
+        } else {
+          const double g1 = (0.0 - hdx * bmAR) - hdx * bmP[m];              // flux2.f90:185-203
+          const double g2 = (0.0 - hdx * bpAR) - hdx * bpP[m];
+          // step2.f90:139-147, pencil J+1: rows J, J+1, J+2
+          qn0[m] = qn0[m] - dtdy * g1;
+          qn1[m] = ((qn1[m] + qadd) - dtdx * (faddR - fadd[m])) - dtdy * (g2 - g1);
+          qn2[m] = qN[m] + dtdy * g2;
+        }
       }
     }
 
@@ -307,9 +333,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
 #pragma unroll
     for (int m = 0; m < M; ++m) {
       // step2.f90:221-229, columns I-1, I, I+1
-      double r = qn0[m] + dtdx * shfl_left(gy2[m]);
-      r = r + ycomb[m];
-      r = r - dtdx * shfl_right(gy1[m]);
+      double r;
+      if constexpr (FG) {
+        r = fma(-kxy, shfl_left(gy2[m]), qn0[m]);
+        r = r + ycomb[m];
+        r = fma(kxy, shfl_right(gy1[m]), r);
+      } else {
+        r = qn0[m] + dtdx * shfl_left(gy2[m]);
+        r = r + ycomb[m];
+        r = r - dtdx * shfl_right(gy1[m]);
+      }
       if (store_col && J >= Jb) qout[m * P.plane + (long long)J * P.pitch + I] = r;
     }
 #pragma unroll
