@@ -39,14 +39,31 @@ template <int LEVEL> __device__ __forceinline__ void prefetch_row(const double* 
 }
 #endif
 
-template <class RP, int NW> struct Smem2ws {
+template <class RP, int NW, int RD = 2> struct Smem2ws {
   static constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE;
   static constexpr int OFF_YW = 0;                  // [W*M]   waves of the pending y-interface
   static constexpr int OFF_YA = OFF_YW + W * M;     // [2M+NR+W] amdq, apdq, roe, dotl
-  static constexpr int OFF_PF = OFF_YA + 2 * M + NR + W;   // [2*M] two-stage ring of prefetched q rows (cp.async)
-  static constexpr int PER_THREAD = OFF_PF + 2 * M;
+  static constexpr int OFF_PF = OFF_YA + 2 * M + NR + W;   // [RD*M] ring of prefetched q rows (cp.async), RD stages
+  static constexpr int PER_THREAD = OFF_PF + RD * M;
   static constexpr size_t BYTES = (size_t)PER_THREAD * NW * 32 * sizeof(double) + 64 * sizeof(double);
 };
+
+template <int N> __device__ __forceinline__ void cp_async_wait_keep() {   // wait until at most N groups are pending
+#ifdef CLAW_HOST_CHECK
+#else
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+__device__ __forceinline__ bool same_bits(double a, double b) {
+  return __double_as_longlong(a) == __double_as_longlong(b);
+}
+__device__ __forceinline__ bool warp_all(bool pred) {
+#ifdef CLAW_HOST_CHECK
+  return emul::vote_all(pred);
+#else
+  return __all_sync(0xffffffffu, pred) != 0;
+#endif
+}
 
 // UNR > 1 unrolls the march loop so that the row-to-row hand-over of the carried state (q1 <- qN, qn0 <- qn1 <- qn2,
 // c1 <- cN) becomes register renaming instead of moves: statically (scripts/sass_mix.py) 1476 -> 1430 instructions per
@@ -54,7 +71,19 @@ template <class RP, int NW> struct Smem2ws {
 // (Measured and dropped in round 2, profiles/r02_f_variants.jsonl: 2 / 4 / 8 warps per CTA are no faster than 1 -- 4.77,
 // 4.82, 5.29 ms against 4.78 -- and a __syncthreads per march step, tried to keep the warps of a CTA at the same place of
 // the 23 KB loop body for the instruction cache, costs more than it gains: 4.80 / 4.97 / 5.70 ms.)
-template <class RP, int NW, int MINB = 1, int SPEC = 0, int UNR = 1>
+//
+// QD > 0 (fast mode, specialised kernel, cp.async ring): UNIFORM-REGION FAST PATH with a QD-stage row ring.  Where the
+// state is exactly uniform -- ahead of a front, behind a planar shock, inside an undisturbed bubble: most cells of the
+// BASELINE shock-bubble data -- every jump is +-0, so every wave, fluctuation, correction and transverse term of the
+// step is exactly zero and the update leaves q as it is; the reference spends its full operation count there all the
+// same.  Per march step the warp votes on "the x-interfaces of row J+1 and the y-interface J+2 of all 32 columns join
+// bit-identical states"; when that holds for the new interface and held for the two before it (the pending one that is
+// finished in this step and the one whose results the cell still carries), the step reduces to: CFL speed |u_n| + c of
+// the two interfaces from the per-cell data, store, rotate the carried rows.  The result is the same as the full path's
+// (which would add exact zeros); the CFL speeds come from the cell data instead of the Roe average of two identical
+// states (equal to rounding).  The kernel is then bound by HBM in such regions and by the FP64 pipe only near fronts;
+// the deeper ring keeps enough rows in flight for the former.
+template <class RP, int NW, int MINB = 1, int SPEC = 0, int UNR = 1, int QD = 0>
 __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_constant__ Sweep2Params P) {
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE, NT = NW * 32;
   constexpr bool SP = (SPEC & 1) != 0;
@@ -62,7 +91,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
   constexpr bool BFL = (SPEC & 8) != 0;                    // branch-free limiter (fast mode)
   constexpr int PF = (SPEC >> 1) & 3;                      // q-row prefetch: 0 none, 1 L1 hint, 2 L2 hint, 3 cp.async ring
   constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
-  using S = Smem2ws<RP, NW>;
+  constexpr int RD = QD > 0 ? QD : 2;                      // stages of the row ring
+#ifdef CLAW_STRICT
+  constexpr bool QUIET = false;
+#else
+  constexpr bool QUIET = (QD > 0) && SP && (PF == 3) && (NC > 0);
+#endif
+  static_assert((RD & (RD - 1)) == 0, "ring depth must be a power of two");
+  using S = Smem2ws<RP, NW, RD>;
   constexpr int TX = 28;                                   // owned columns per warp
   // Fast mode, specialised kernel: the transverse corrections are carried as the unscaled sums G1 = bm(i+1) + bm'(i),
   // G2 = bp(i+1) + bp'(i) and scaled once by kxy = (dt/dx)(dt/dy)/2 where they enter q (gadd = -(dt/2dx) G, then
@@ -109,27 +145,46 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
   // The first consumer of a freshly loaded row is the Roe average of the y-interface: without a prefetch the warp
   // sits on the DRAM latency once per march step (ncu: 13 % of all stall samples on that one instruction).  PF=3
   // keeps row J+3 in flight (cp.async into a thread-private two-stage ring) while row J+2 is being worked on.
+  // ring slot of array row r: r & (RD - 1); rows Jb-1 .. Jb+RD-3 are in flight when the loop starts
   if constexpr (PF == 3) {
 #pragma unroll
-    for (int m = 0; m < M; ++m)
-      cp_async8(spf + (((Jb - 3) & 1) * M + m) * NT, qcol + m * P.plane + (long long)(Jb - 1) * P.pitch);
-    cp_async_commit();
+    for (int k = 0; k < RD - 1; ++k) {
+      const int r = Jb - 1 + k;
+      if (r <= Je + 1) {
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+          cp_async8(spf + ((r & (RD - 1)) * M + m) * NT, qcol + m * P.plane + (long long)r * P.pitch);
+      }
+      cp_async_commit();
+    }
   }
+  // running ring positions (in doubles, per-thread stride NT): the slot written at the first step (row Jb+RD-2) and the
+  // slot read at the first step (row Jb-1); running global pointers of the row to fetch and of the row to store
+  [[maybe_unused]] int wslot = ((Jb + RD - 2) & (RD - 1)) * M * NT, rslot = ((Jb - 1) & (RD - 1)) * M * NT;
+  [[maybe_unused]] const double* gfetch = qcol + (long long)(Jb + RD - 2) * P.pitch;
+  // uniform-region fast path: were the y-interfaces J+1 and J zero on all lanes?  was the last step a quiet one?  has the
+  // CFL speed of the current run of identical rows been taken for the x- / the y-interface?
+  [[maybe_unused]] bool yq1 = false, yq2 = false, prev_quiet = false, qcfl_x = false, qcfl_y = false;
 
   // warm-up rows: see sweep2_unsplit (the specialised kernel runs the full body from the first step)
 #pragma unroll UNR
   for (int J = Jb - 3; J < Je; ++J) {
     double qN[M];
     if constexpr (PF == 3) {
-      cp_async_wait_all();
+      {                                                    // row J+RD+1 goes into the slot row J+1 was read from
+        if (J + RD + 1 <= Je + 1) {
+          const double* g = gfetch;
 #pragma unroll
-      for (int m = 0; m < M; ++m) qN[m] = spf[((J & 1) * M + m) * NT];
-      if (J + 1 < Je) {
-#pragma unroll
-        for (int m = 0; m < M; ++m)
-          cp_async8(spf + (((J + 1) & 1) * M + m) * NT, qcol + m * P.plane + (long long)(J + 3) * P.pitch);
+          for (int m = 0; m < M; ++m) { cp_async8(spf + wslot + m * NT, g); g += P.plane; }
+        }
+        cp_async_commit();
+        gfetch += P.pitch;
+        wslot = (wslot == (RD - 1) * M * NT) ? 0 : wslot + M * NT;
       }
-      cp_async_commit();
+      cp_async_wait_keep<RD - 1>();                        // row J+2 has landed
+#pragma unroll
+      for (int m = 0; m < M; ++m) qN[m] = spf[rslot + m * NT];
+      rslot = (rslot == (RD - 1) * M * NT) ? 0 : rslot + M * NT;
     } else {
 #pragma unroll
       for (int m = 0; m < M; ++m) qN[m] = qcol[m * P.plane + (long long)(J + 2) * P.pitch];
@@ -141,6 +196,55 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
       }
     }
     double cN[NC1];
+    [[maybe_unused]] double qlx[M];                        // row J+1 of the column on my left (x-interface of this step)
+    if constexpr (QUIET) {
+      bool yz = true, xz = true;
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        qlx[m] = shfl_left(q1[m]);
+        yz = yz && same_bits(q1[m], qN[m]);
+        xz = xz && same_bits(qlx[m], q1[m]);
+      }
+      const bool yq0 = warp_all(yz);                       // y-interface J+2 joins identical states in all 32 columns
+      const bool xq0 = warp_all(xz);
+      const bool quiet = yq0 && xq0 && yq1 && yq2;
+      yq2 = yq1; yq1 = yq0;
+      if (quiet) {
+        // Rows J+1 and J+2 carry the same bits in every column, so q1 and the cell data c1 stay as they are, and the CFL
+        // speed of the two zero-jump interfaces is the same for every row of this run of quiet steps: it is taken once
+        // per run and interface direction, at the first step whose row is inside the range the reference visits
+        // (flux2.f90:111-119 over the pencils of step2.f90:92,172).
+        const bool ry = (J + 2 >= 2) && (J + 2 <= P.my + 2), rx = (J + 1 >= 1) && (J + 1 <= P.my + 2);
+        if (ry && !qcfl_y) { if (y_cfl_col) cfl = fmax2(cfl, dtdy * RP::quiet_smax(P.rp, 1, q1, c1)); qcfl_y = true; }
+        if (rx && !qcfl_x) { if (x_cfl_col) cfl = fmax2(cfl, dtdx * RP::quiet_smax(P.rp, 0, q1, c1)); qcfl_x = true; }
+        if (store_col && J >= Jb) {
+          double* o = qout + (long long)J * P.pitch + I;
+#pragma unroll
+          for (int m = 0; m < M; ++m) { *o = qn0[m]; o += P.plane; }
+        }
+#pragma unroll
+        for (int m = 0; m < M; ++m) { qn0[m] = qn1[m]; qn1[m] = q1[m]; }
+        prev_quiet = true;
+        continue;
+      }
+      qcfl_x = false; qcfl_y = false;
+      if (prev_quiet) {
+        // the pending y-interface (J+1) was skipped: it is a zero interface -- zero waves, fluctuations and limiter dot
+        // products, finite stand-in Roe data (they only ever multiply those zeros); the carried results of interface J
+        // (yI_*) are zero already, which is what made the skipped steps quiet
+        double roeQ[NR];
+        RP::quiet_roe(roeQ);
+#pragma unroll
+        for (int k = 0; k < W * M; ++k) syw[k * NT] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 2 * M; ++k) sya[k * NT] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) sya[(2 * M + k) * NT] = roeQ[k];
+#pragma unroll
+        for (int mw = 0; mw < W; ++mw) sya[(2 * M + NR + mw) * NT] = 0.0;
+        prev_quiet = false;
+      }
+    }
     if constexpr (NC > 0) RP::cell(P.rp, qN, cN);
 
     // =========================== y-pipeline ==========================================
@@ -256,7 +360,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
       {
         double ql[M], cl[NC1];
 #pragma unroll
-        for (int m = 0; m < M; ++m) ql[m] = shfl_left(q1[m]);
+        for (int m = 0; m < M; ++m) {
+          if constexpr (QUIET) ql[m] = qlx[m];
+          else ql[m] = shfl_left(q1[m]);
+        }
 #pragma unroll
         for (int k = 0; k < NC; ++k) cl[k] = shfl_left(c1[k]);
         RP::normal(P.rp, 0, ql, q1, cl, c1, wave, s, amdq, apdq, roe);    // flux2.f90:101

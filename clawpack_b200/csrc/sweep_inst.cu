@@ -12,7 +12,7 @@ namespace CLAW_NS {
 
 template <class KERN>
 static cudaError_t launch_kernel(KERN kern, int NT, int smem, bool x_only, Sweep2Params& P, int seg_hint, int num_sms,
-                                 cudaStream_t st, LaunchInfo* info, int cols_per_cta = 0) {
+                                 cudaStream_t st, LaunchInfo* info, int cols_per_cta = 0, int max_seg = 256) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int occ = 1;
@@ -37,7 +37,7 @@ static cudaError_t launch_kernel(KERN kern, int NT, int smem, bool x_only, Sweep
     seg = (int)((rows + nseg - 1) / nseg);
     const int min_seg = ((long long)strips * ((rows + 31) / 32) >= (long long)num_sms * occ) ? 32 : 8;
     if (seg < min_seg) seg = min_seg;
-    if (seg > 256) seg = 256;
+    if (seg > max_seg) seg = max_seg;
   }
   if (seg > rows) seg = rows;
   P.seg_rows = seg;
@@ -56,11 +56,14 @@ static cudaError_t launch_one(int kind, Sweep2Params& P, int seg_hint, int num_s
 }
 
 // warp-synchronous unsplit kernel (sweep2_ws.cuh): NW independent 28-column strips per CTA
-template <class RP, int NW, int MINB, int SPEC, int UNR = 1>
+template <class RP, int NW, int MINB, int SPEC, int UNR = 1, int QD = 0>
 static cudaError_t launch_ws(Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
-  using S = Smem2ws<RP, NW>;
-  return launch_kernel(sweep2_unsplit_ws<RP, NW, MINB, SPEC, UNR>, NW * 32, (int)S::BYTES, false, P, seg_hint, num_sms, st,
-                       info, NW * 28);
+  using S = Smem2ws<RP, NW, (QD > 0 ? QD : 2)>;
+  // with the uniform-region fast path the cost of a CTA depends on how much of a front it holds: 64-row segments keep
+  // the slowest CTAs short enough for the tail of the launch (measured at 8192^2, profiles/r02_i_segrows.jsonl: 1.38 ms
+  // with 256-row segments, 1.20 / 1.16 / 1.29 ms with 128 / 64 / 32)
+  return launch_kernel(sweep2_unsplit_ws<RP, NW, MINB, SPEC, UNR, QD>, NW * 32, (int)S::BYTES, false, P, seg_hint, num_sms,
+                       st, info, NW * 28, QD > 0 ? 64 : 256);
 }
 
 // warp-synchronous dimension-split kernel (sweep2_ws.cuh)
@@ -113,7 +116,13 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
         // fastest measured: spill-free 8 warps/SM, per-cell Roe data, cp.async row ring (profiles/r01_h, r01_i).
         // Measured and dropped: 12/16 warps with spills, L1/L2 prefetch hints, branch-free limiter / entropy fix, a warp
         // pair per strip (5.21 ms, profiles/r01_j), the march loop unrolled x2 (5.15 ms, profiles/r02_a_variants.jsonl).
-        if (variant != 1) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
+        // uniform-region fast path (fast mode only; see sweep2_ws.cuh) with a 2 / 4 / 8-stage row ring
+        // default: with the uniform-region fast path (a no-op in strict mode) and an 8-stage row ring; measured at
+        // 8192^2 on the shock-bubble data (profiles/r02_g_variants.jsonl): 4.62 ms without it, 1.75 / 1.49 / 1.44 ms
+        // with a 2 / 4 / 8-stage ring.  CLAW_VARIANT=2: the same kernel without the fast path (dense-data timing, A/B).
+        if (variant == 2) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
+        if (variant == 71) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6, 1, 4>(P, seg_hint, num_sms, st, info);
+        if (variant != 1) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6, 1, 8>(P, seg_hint, num_sms, st, info);
       }
       if (kind == 0) return launch_ws<RpEuler4Wave2D, 1, 8, 6>(P, seg_hint, num_sms, st, info);
       if (variant != 1 && split_method<4>(P, 4))              // MC limiter as a template argument

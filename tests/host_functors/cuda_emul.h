@@ -62,6 +62,16 @@ inline double shfl(double v, int src_of_lane(int lane, int arg), int arg) {
   yield_sync();
   return g_xbuf[ph][base + src_of_lane(lane, arg)];
 }
+// warp vote: true iff the predicate holds on all 32 lanes of the calling fiber's warp (all of them reach the call)
+inline bool vote_all(bool pred) {
+  const int me = g_cur, base = me & ~31;
+  const unsigned ph = g_phase[me]++ & 1u;
+  g_xbuf[ph][me] = pred ? 1.0 : 0.0;
+  yield_sync();
+  bool all = true;
+  for (int l = 0; l < 32 && base + l < g_n; ++l) all = all && (g_xbuf[ph][base + l] != 0.0);
+  return all;
+}
 }  // namespace emul
 
 #define __global__

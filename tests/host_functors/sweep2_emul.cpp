@@ -61,7 +61,11 @@ int run(int rp_id, int kind, int variant, Sweep2Params& P, int seg) {
       kind ? split_ws<RpAcoustics2D>(P, seg) : unsplit_ws<RpAcoustics2D>(P, seg); return 0;
     case 3:
       if (kind == 0 && P.mtrans == 2 && all_limiters<4>(P, 4) && variant != 9) {      // the headline kernel of bench.py
-        launch(sweep2_unsplit_ws<RpEuler4Wave2DT<3>, 1, 1, (4 << 4) | 1 | 6, 1>, 32, false, P, seg);
+        // variants 72 / 71: with the uniform-region fast path and an 8- / 4-stage row ring (fast mode; in strict mode the
+        // template argument only changes the ring depth)
+        if (variant == 72) launch(sweep2_unsplit_ws<RpEuler4Wave2DT<3>, 1, 1, (4 << 4) | 1 | 6, 1, 8>, 32, false, P, seg);
+        else if (variant == 71) launch(sweep2_unsplit_ws<RpEuler4Wave2DT<3>, 1, 1, (4 << 4) | 1 | 6, 1, 4>, 32, false, P, seg);
+        else launch(sweep2_unsplit_ws<RpEuler4Wave2DT<3>, 1, 1, (4 << 4) | 1 | 6, 1>, 32, false, P, seg);
         return 0;
       }
       if (kind == 1 && variant == 53 && all_limiters<4>(P, 4)) {

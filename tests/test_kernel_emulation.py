@@ -170,6 +170,13 @@ CASES_2D = {
     # kernels already proven on the GPU: they validate the emulation
     'euler_headline_kernel_spec': (lambda: S.shock_bubble(mx=60, my=40), 0, 0),
     'euler_headline_kernel_segments': (lambda: S.shock_bubble(mx=57, my=45), 0, 8),
+    # uniform-region fast path (sweep2_ws.cuh, QD > 0): the shock-bubble data are uniform away from the fronts, so quiet
+    # and full march steps alternate within every strip; 8- and 4-stage row ring, with and without march segments
+    'euler_headline_quiet_ring8': (lambda: S.shock_bubble(mx=120, my=90), 72, 0),
+    'euler_headline_quiet_ring8_segments': (lambda: S.shock_bubble(mx=57, my=45), 72, 8),
+    'euler_headline_quiet_ring4_short_segments': (lambda: S.shock_bubble(mx=70, my=64), 71, 5),
+    'euler_quadrants_quiet_ring8': (lambda: dict(S.quadrants(mx=64, my=64), dimensional_split=False, transverse_waves=2,
+                                                 limiters=S.MC), 72, 16),
     'euler_unsplit_generic_inc_mixed_limiters': (lambda: dict(S.quadrants(mx=40, my=30), dimensional_split=False,
                                                               transverse_waves=1,
                                                               limiters=[S.SUPERBEE, S.MINMOD, S.VANLEER, S.MC]), 0, 0),
