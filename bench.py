@@ -62,6 +62,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-other-configs', action='store_true')
     ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--no-dense', action='store_true')
     ap.add_argument('--cpu-n', type=int, default=1024, help='grid side of the bounded CPU-baseline sample (cuda arm)')
     args = ap.parse_args()
     if args.config == 'c5':
@@ -326,7 +327,7 @@ def sass_identity(kernel_pattern, obj):
         return None, None
 
 
-NCU_KEYS = {'c2': ('sweep2_unsplit_wsINS0_15RpEuler4Wave2DTILi3ELi0EEELi1ELi8ELi71ELi1E', 'sweep_inst_%s.o'),
+NCU_KEYS = {'c2': ('sweep2_unsplit_wsINS0_15RpEuler4Wave2DTILi3ELi0EEELi1ELi8ELi71ELi1ELi8E', 'sweep_inst_%s.o'),
             'c3': ('sweep2_split_wsINS0_18RpShallowRoeEfix2DELi1ELi16ELi1ELi1ELi4E', 'sweep_inst_%s.o'),
             'c1': ('sweep2_split_wsINS0_13RpAcoustics2DELi1ELi16ELi1ELi1ELi4E', 'sweep_inst_%s.o'),
             'c4': ('sweep3_marchINS0_15RpVcAcoustics3DELi2ELi32ELi8ELi1ELi41E', 'sweep3_inst_%s.o')}
@@ -433,6 +434,26 @@ def run_config(ctx, args, config, n, steps, warmup, primary):
                                      ctypes.byref(avg_ms)), dev.handle)
     linfo = (ctypes.c_int * 5)()
     _lib.check(dev.L.claw_last_launch_info(dev.handle, linfo), dev.handle)
+    # The same kernel on DENSE data: the BASELINE initial data are piecewise constant, and the kernels of c1-c3 skip the
+    # arithmetic of exactly uniform regions (results unchanged), which makes them HBM-bound there.  For the FP64-bound
+    # regime every cell of the current state gets a smooth 1e-3 perturbation (no two neighbours carry the same bits) and
+    # the sweep kernel is timed again on it.
+    dense_ms = None
+    if config in ('c2', 'c3') and ctx.world == 1 and not args.no_dense:
+        state = solution.state
+        q = state.q
+        idx = np.indices(q.shape[1:], sparse=True)
+        pert = 1.0 + 1e-3 * np.sin(0.37 * idx[0] + 0.11 * idx[1] + 0.5)
+        q[0] *= pert
+        if config == 'c2':
+            q[3] *= pert
+        state.q = q
+        dev._upload_if_needed(state)
+        dm = ctypes.c_double()
+        _lib.check(dev.L.claw_time_sweep(dev.handle, _lib.dp(dev.delta), float(solver.dt) * 0.5, 5, ctypes.byref(dm)),
+                   dev.handle)
+        dense_ms = dm.value
+        del q, pert
     out = None
     if ctx.rank == 0:
         ops = algorithmic_ops(config)
@@ -442,6 +463,10 @@ def run_config(ctx, args, config, n, steps, warmup, primary):
         t_f = ops['flops'] / (2.0 * ctx.peak_gdfma * 1e9)                     # s per cell if FP64-bound
         t_h = BYTES_PER_CELL[config] / (ctx.hbm_peak * 1e9)                   # s per cell if HBM-bound
         bound = 'fp64' if t_f > t_h else 'hbm'
+        # c1-c3 on the BASELINE data: uniform regions cost no arithmetic (see above), the measured kernel time is far
+        # below the FP64 time of the algorithmic operation count -- the binding roofline of THIS workload is HBM
+        if flops_per_s / 1e9 / (2.0 * ctx.peak_gdfma) > 1.0 or (dense_ms is not None and dense_ms > 1.5 * avg_ms.value):
+            bound = 'hbm'
         ev = ncu_evidence(config, args.precision)
         kernels = {'c2': 'sweep2_unsplit_ws<RpEuler4Wave2DT<3>, 1 warp/CTA, MC|spec|cp.async row ring>',
                    'c1': 'sweep2_split_ws<RpAcoustics2D, 1 warp/CTA, LIM=MC> (x- and y-sweep fused in one march)',
@@ -466,7 +491,18 @@ def run_config(ctx, args, config, n, steps, warmup, primary):
             'fp64_pipe': ev['fp64_pipe'], 'ncu': ev['ncu'], 'ncu_stale': ev.get('stale'),
             'hbm': {'achieved': hbm_gbs, 'peak': ctx.hbm_peak, 'unit': 'GB/s', 'frac': hbm_gbs / ctx.hbm_peak,
                     'peak_source': ctx.hbm_src},
+            'fp64': {'achieved': flops_per_s / 1e12, 'peak': 2.0 * ctx.peak_gdfma / 1e3, 'unit': 'TFLOP/s',
+                     'frac': flops_per_s / 1e9 / (2.0 * ctx.peak_gdfma),
+                     'note': 'algorithmic flops of the reference on this data / kernel time; > 1 means the kernel skipped '
+                             'the arithmetic of uniform regions (exact zeros) and is not FP64-bound on this data'},
         }
+        if dense_ms is not None:
+            dflops = ops['flops'] * cells_local / (dense_ms * 1e-3)
+            roofline['dense'] = {'data': 'the same state with a smooth 1e-3 perturbation in every cell (no uniform regions)',
+                                 'bound': 'fp64', 'kernel_ms': dense_ms, 'achieved': dflops / 1e12,
+                                 'peak': 2.0 * ctx.peak_gdfma / 1e3, 'unit': 'TFLOP/s',
+                                 'frac': dflops / 1e9 / (2.0 * ctx.peak_gdfma),
+                                 'cell_updates_per_s': cells_local / (dense_ms * 1e-3)}
         out = {'metric': METRICS[config], 'value': value, 'unit': UNIT, 'n_gpus': ctx.world, 'steps': attempts,
                'warmup': max(warmup, 3), 'ms_per_step': ms / attempts, 'higher_is_better': True,
                'scaling': 'weak' if config == 'c2' else 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
@@ -643,7 +679,12 @@ def main():
                                'roofline': {k: r['roofline'][k] for k in ('bound', 'achieved', 'peak', 'unit', 'frac',
                                                                          'kernel', 'kernel_ms', 'traffic',
                                                                          'algorithmic_flops_per_cell',
-                                                                         'algorithmic_bytes_per_cell', 'ncu_stale')}})
+                                                                         'algorithmic_bytes_per_cell', 'ncu_stale')
+                                            if k in r['roofline']}})
+                if 'dense' in r['roofline']:
+                    others[-1]['roofline']['dense'] = r['roofline']['dense']
+                others[-1]['roofline']['fp64_frac'] = r['roofline']['fp64']['frac']
+                others[-1]['roofline']['hbm_frac'] = r['roofline']['hbm']['frac']
         if ctx.rank == 0:
             out['other_configs'] = others
     if ctx.world > 1:

@@ -57,6 +57,9 @@ template <int N> __device__ __forceinline__ void cp_async_wait_keep() {   // wai
 __device__ __forceinline__ bool same_bits(double a, double b) {
   return __double_as_longlong(a) == __double_as_longlong(b);
 }
+__device__ __forceinline__ unsigned long long diff_bits(double a, double b) {
+  return (unsigned long long)(__double_as_longlong(a) ^ __double_as_longlong(b));
+}
 __device__ __forceinline__ bool warp_all(bool pred) {
 #ifdef CLAW_HOST_CHECK
   return emul::vote_all(pred);
@@ -167,24 +170,29 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
   [[maybe_unused]] bool yq1 = false, yq2 = false, prev_quiet = false, qcfl_x = false, qcfl_y = false;
 
   // warm-up rows: see sweep2_unsplit (the specialised kernel runs the full body from the first step)
+  // step Js of the ring: queue row Js+RD+1 into the slot row Js+1 was read from, wait for row Js+2, read it
+  auto ring_fetch = [&](int Js, double* q) {
+    if (Js + RD + 1 <= Je + 1) {
+      const double* g = gfetch;
+#pragma unroll
+      for (int m = 0; m < M; ++m) { cp_async8(spf + wslot + m * NT, g); g += P.plane; }
+    }
+    cp_async_commit();
+    gfetch += P.pitch;
+    wslot = (wslot == (RD - 1) * M * NT) ? 0 : wslot + M * NT;
+    cp_async_wait_keep<RD - 1>();
+#pragma unroll
+    for (int m = 0; m < M; ++m) q[m] = spf[rslot + m * NT];
+    rslot = (rslot == (RD - 1) * M * NT) ? 0 : rslot + M * NT;
+  };
+  double qN[M];
+  [[maybe_unused]] bool have_row = false;                  // qN already holds row J+2 (handed over by the tight quiet loop)
+  [[maybe_unused]] int nquiet = 0;                         // consecutive quiet steps
 #pragma unroll UNR
   for (int J = Jb - 3; J < Je; ++J) {
-    double qN[M];
     if constexpr (PF == 3) {
-      {                                                    // row J+RD+1 goes into the slot row J+1 was read from
-        if (J + RD + 1 <= Je + 1) {
-          const double* g = gfetch;
-#pragma unroll
-          for (int m = 0; m < M; ++m) { cp_async8(spf + wslot + m * NT, g); g += P.plane; }
-        }
-        cp_async_commit();
-        gfetch += P.pitch;
-        wslot = (wslot == (RD - 1) * M * NT) ? 0 : wslot + M * NT;
-      }
-      cp_async_wait_keep<RD - 1>();                        // row J+2 has landed
-#pragma unroll
-      for (int m = 0; m < M; ++m) qN[m] = spf[rslot + m * NT];
-      rslot = (rslot == (RD - 1) * M * NT) ? 0 : rslot + M * NT;
+      if (!QUIET || !have_row) ring_fetch(J, qN);
+      have_row = false;
     } else {
 #pragma unroll
       for (int m = 0; m < M; ++m) qN[m] = qcol[m * P.plane + (long long)(J + 2) * P.pitch];
@@ -225,9 +233,38 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
 #pragma unroll
         for (int m = 0; m < M; ++m) { qn0[m] = qn1[m]; qn1[m] = q1[m]; }
         prev_quiet = true;
+        ++nquiet;
+        // From the third quiet step of a run on, the carried rows qn0, qn1 hold the bits of q1 too, and a further row
+        // with those bits also passes the x-test (it is the same 32 values again): while rows keep coming in unchanged
+        // the step is "fetch, compare with q1, vote, store q1" -- a tight loop of its own, without the rotation of the
+        // carried state and without the bookkeeping of the general step.
+        if (nquiet >= 2 && qcfl_x && qcfl_y && J >= Jb) {
+          double* orow = qout + (long long)(J + 1) * P.pitch + I;
+          while (J + 1 < Je) {
+            double qT[M];
+            ring_fetch(J + 1, qT);
+            unsigned long long d = 0ull;
+#pragma unroll
+            for (int m = 0; m < M; ++m) d |= diff_bits(q1[m], qT[m]);
+            if (!warp_all(d == 0ull)) {                    // step J+1 goes through the general classification
+#pragma unroll
+              for (int m = 0; m < M; ++m) qN[m] = qT[m];
+              have_row = true;
+              break;
+            }
+            ++J;
+            if (store_col) {
+              double* o = orow;
+#pragma unroll
+              for (int m = 0; m < M; ++m) { *o = q1[m]; o += P.plane; }
+            }
+            orow += P.pitch;
+          }
+        }
         continue;
       }
       qcfl_x = false; qcfl_y = false;
+      nquiet = 0;
       if (prev_quiet) {
         // the pending y-interface (J+1) was skipped: it is a zero interface -- zero waves, fluctuations and limiter dot
         // products, finite stand-in Roe data (they only ever multiply those zeros); the carried results of interface J
@@ -468,11 +505,22 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
 // =====================================================================================
 // LIM > 0: order 2 with limiter id LIM on every wave family, known at compile time (the generic kernel selects the
 // limiter per wave at run time: a five-way switch per wave and interface in both sweeps).  UNR: see sweep2_unsplit_ws.
-template <class RP, int NW, int MINB = 1, int PF = 1, int UNR = 1, int LIM = 0>
+// QD > 0 (fast mode, LIM > 0, fused x+y step): uniform-region fast path with a QD-stage row ring, as in
+// sweep2_unsplit_ws: when the x-interfaces of row J+2 and the y-interfaces J+2, J+1, J of all 32 columns join
+// bit-identical states, the x-sweep leaves the row as it is and the y-update adds exact zeros; the step then only takes
+// the CFL speed of the uniform state (once per run of such steps), stores row J and rotates the carried rows.
+template <class RP, int NW, int MINB = 1, int PF = 1, int UNR = 1, int LIM = 0, int QD = 0>
 __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_constant__ Sweep2Params P) {
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE, NT = NW * 32;
   constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
-  using S = Smem2ws<RP, NW>;
+  constexpr int RD = QD > 0 ? QD : 2;
+#ifdef CLAW_STRICT
+  constexpr bool QUIET = false;
+#else
+  constexpr bool QUIET = (QD > 0) && (LIM > 0) && (PF != 0) && (NC == 0);
+#endif
+  static_assert((RD & (RD - 1)) == 0, "ring depth must be a power of two");
+  using S = Smem2ws<RP, NW, RD>;
   constexpr int TX = 28;
   CLAW_DYN_SMEM(smem);
   const int t = threadIdx.x, lane = t & 31;
@@ -498,11 +546,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
   const int Je = min(Jb + P.seg_rows, P.j1);
 
   // x-sweep of one row (step2ds.f90:96-160 with ids = 1): q -> x-updated value of my cell
-  auto x_sweep = [&](const double* q, double* out) {
+  auto x_sweep = [&](const double* q, double* out, const double* ql_in) {
     double cq[NC1], cl[NC1], ql[M];
     if constexpr (NC > 0) RP::cell(P.rp, q, cq);
 #pragma unroll
-    for (int m = 0; m < M; ++m) ql[m] = shfl_left(q[m]);
+    for (int m = 0; m < M; ++m) ql[m] = (ql_in != nullptr) ? ql_in[m] : shfl_left(q[m]);
 #pragma unroll
     for (int k = 0; k < NC; ++k) cl[k] = shfl_left(cq[k]);
     double wave[W][M], s[W], amdq[M], apdq[M], roe[NR], cqxx[M], fadd[M];
@@ -566,7 +614,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
     for (int J = Jb; J < Je; ++J) {
       double q[M], r[M];
       fetch(J, J, J + 1, J + 1 < Je, q);
-      x_sweep(q, r);
+      x_sweep(q, r, nullptr);
       if (interior_col && x_ok) {
 #pragma unroll
         for (int m = 0; m < M; ++m) qout[m * P.plane + (long long)J * P.pitch + I] = r[m];
@@ -582,16 +630,124 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
   for (int m = 0; m < M; ++m) { qx0[m] = 0.0; qx1[m] = 0.0; yI_apdq[m] = 0.0; yI_fadd[m] = 0.0; }
 #pragma unroll
   for (int k = 0; k < NC1; ++k) cx1[k] = 0.0;
-  if constexpr (PF != 0) { prefetch(Jb, Jb - 2); cp_async_commit(); }
+  // QD-stage ring (QUIET builds): rows Jb-2 .. Jb+RD-4 are in flight when the loop starts; running slot offsets
+  [[maybe_unused]] int wslot = ((Jb + RD - 3) & (RD - 1)) * M * NT, rslot = ((Jb - 2) & (RD - 1)) * M * NT;
+  [[maybe_unused]] const double* gfetch = qcol + (long long)(Jb + RD - 3) * P.pitch;
+  [[maybe_unused]] bool yq1 = false, yq2 = false, prev_quiet = false, qcfl_x = false, qcfl_y = false;
+  if constexpr (QD > 0) {
+#pragma unroll
+    for (int k = 0; k < RD - 1; ++k) {
+      const int r = Jb - 2 + k;
+      if (r <= Je + 1) {
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+          cp_async8(spf + ((r & (RD - 1)) * M + m) * NT, qcol + m * P.plane + (long long)r * P.pitch);
+      }
+      cp_async_commit();
+    }
+  } else if constexpr (PF != 0) { prefetch(Jb, Jb - 2); cp_async_commit(); }
 
+  // step Js of the QD-stage ring: queue row Js+RD+1 into the slot row Js+1 was read from, wait for row Js+2, read it
+  auto ring_fetch = [&](int Js, double* q) {
+    if (Js + RD + 1 <= Je + 1) {
+      const double* g = gfetch;
+#pragma unroll
+      for (int m = 0; m < M; ++m) { cp_async8(spf + wslot + m * NT, g); g += P.plane; }
+    }
+    cp_async_commit();
+    gfetch += P.pitch;
+    wslot = (wslot == (RD - 1) * M * NT) ? 0 : wslot + M * NT;
+    cp_async_wait_keep<RD - 1>();
+#pragma unroll
+    for (int m = 0; m < M; ++m) q[m] = spf[rslot + m * NT];
+    rslot = (rslot == (RD - 1) * M * NT) ? 0 : rslot + M * NT;
+  };
+  double qx2[M];
+  [[maybe_unused]] bool have_row = false;                  // qx2 already holds row J+2 (handed over by the tight quiet loop)
+  [[maybe_unused]] int nquiet = 0;
 #pragma unroll UNR
   for (int J = Jb - 4; J < Je; ++J) {
     // ---- x-sweep of row J+2 ----------------------------------------------------------
-    double qx2[M];
-    fetch(J - (Jb - 4) + Jb, J + 2, J + 3, J + 1 < Je, qx2);
+    if constexpr (QD > 0) {
+      if (!QUIET || !have_row) ring_fetch(J, qx2);
+      have_row = false;
+    } else {
+      fetch(J - (Jb - 4) + Jb, J + 2, J + 3, J + 1 < Je, qx2);
+    }
+    [[maybe_unused]] double qlx[M];
+    if constexpr (QUIET) {
+      bool xz = true, yz = true;
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        qlx[m] = shfl_left(qx2[m]);
+        xz = xz && same_bits(qlx[m], qx2[m]);
+        yz = yz && same_bits(qx1[m], qx2[m]);
+      }
+      const bool xq0 = warp_all(xz);                       // the x-sweep leaves row J+2 as it is in all 32 columns
+      const bool yq0 = warp_all(yz) && xq0 && (J >= Jb - 3);   // the x-updated rows J+1 and J+2 carry the same bits
+      const bool quiet = do_x && yq0 && yq1 && yq2 && (J >= Jb - 1);
+      yq2 = yq1; yq1 = yq0;
+      if (quiet) {
+        const bool ry = (J + 2 >= 2) && (J + 2 <= P.my + 2);
+        if (!qcfl_x) { if (x_cfl_col) cfl = fmax2(cfl, dtdx * RP::quiet_smax(P.rp, 0, qx2)); qcfl_x = true; }
+        if (ry && !qcfl_y) { if (col_ok) cfl = fmax2(cfl, dtdy * RP::quiet_smax(P.rp, 1, qx2)); qcfl_y = true; }
+        if (J >= Jb && col_ok && interior_col) {
+          double* o = qout + (long long)J * P.pitch + I;
+#pragma unroll
+          for (int m = 0; m < M; ++m) { *o = qx0[m]; o += P.plane; }
+        }
+#pragma unroll
+        for (int m = 0; m < M; ++m) qx0[m] = qx1[m];       // qx1 = qx2: the same bits already
+        prev_quiet = true;
+        ++nquiet;
+        // from the second quiet step of a run on, qx0 carries the bits of qx1 too: while rows keep coming in with those
+        // bits (which also means they pass the x-test again) the step is "fetch, compare, vote, store"
+        if (nquiet >= 2 && qcfl_x && qcfl_y && J >= Jb) {
+          double* orow = qout + (long long)(J + 1) * P.pitch + I;
+          const bool st = col_ok && interior_col;
+          while (J + 1 < Je) {
+            double qT[M];
+            ring_fetch(J + 1, qT);
+            unsigned long long d = 0ull;
+#pragma unroll
+            for (int m = 0; m < M; ++m) d |= diff_bits(qx1[m], qT[m]);
+            if (!warp_all(d == 0ull)) {
+#pragma unroll
+              for (int m = 0; m < M; ++m) qx2[m] = qT[m];
+              have_row = true;
+              break;
+            }
+            ++J;
+            if (st) {
+              double* o = orow;
+#pragma unroll
+              for (int m = 0; m < M; ++m) { *o = qx1[m]; o += P.plane; }
+            }
+            orow += P.pitch;
+          }
+        }
+        continue;
+      }
+      qcfl_x = false; qcfl_y = false;
+      nquiet = 0;
+      if (prev_quiet) {                                    // the pending y-interface was skipped: a zero interface
+        double roeQ[NR];
+        RP::quiet_roe(roeQ);
+#pragma unroll
+        for (int k = 0; k < W * M; ++k) syw[k * NT] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 2 * M; ++k) sya[k * NT] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) sya[(2 * M + k) * NT] = roeQ[k];
+#pragma unroll
+        for (int mw = 0; mw < W; ++mw) sya[(2 * M + NR + mw) * NT] = 0.0;
+        prev_quiet = false;
+      }
+    }
     if (do_x) {
       double r[M];
-      x_sweep(qx2, r);
+      if constexpr (QUIET) x_sweep(qx2, r, qlx);
+      else x_sweep(qx2, r, nullptr);
       if (interior_col) {                                  // ghost columns are not updated by the x-sweep
 #pragma unroll
         for (int m = 0; m < M; ++m) qx2[m] = r[m];

@@ -67,11 +67,11 @@ static cudaError_t launch_ws(Sweep2Params& P, int seg_hint, int num_sms, cudaStr
 }
 
 // warp-synchronous dimension-split kernel (sweep2_ws.cuh)
-template <class RP, int NW, int MINB, int PF = 1, int UNR = 1, int LIM = 0>
+template <class RP, int NW, int MINB, int PF = 1, int UNR = 1, int LIM = 0, int QD = 0>
 static cudaError_t launch_split_ws(Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
-  using S = Smem2ws<RP, NW>;
-  return launch_kernel(sweep2_split_ws<RP, NW, MINB, PF, UNR, LIM>, NW * 32, (int)S::BYTES, !P.do_y, P, seg_hint, num_sms, st, info,
-                       NW * 28);
+  using S = Smem2ws<RP, NW, (QD > 0 ? QD : 2)>;
+  return launch_kernel(sweep2_split_ws<RP, NW, MINB, PF, UNR, LIM, QD>, NW * 32, (int)S::BYTES, !P.do_y, P, seg_hint, num_sms,
+                       st, info, NW * 28, QD > 0 ? 64 : 256);
 }
 
 // aux-reading solvers (sweep2_aux.cuh): warp-synchronous, NW strips per CTA
@@ -104,7 +104,11 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
     case 2:
       if (kind == 1) {
         static const int variant = getenv("CLAW_VARIANT") ? atoi(getenv("CLAW_VARIANT")) : 0;   // 1: generic kernels only (A/B timing)
-        if (variant != 1 && split_method<2>(P, 4))             // BASELINE config 1: MC limiter as a template argument
+        if (variant == 2 && split_method<2>(P, 4))             // without the uniform-region fast path (A/B)
+          return launch_split_ws<RpAcoustics2D, 1, 16, 1, 1, 4>(P, seg_hint, num_sms, st, info);
+        if (variant != 1 && split_method<2>(P, 4) && P.do_x && P.do_y)   // BASELINE config 1: MC limiter as a template argument
+          return launch_split_ws<RpAcoustics2D, 1, 16, 1, 1, 4, 8>(P, seg_hint, num_sms, st, info);
+        if (variant != 1 && split_method<2>(P, 4))
           return launch_split_ws<RpAcoustics2D, 1, 16, 1, 1, 4>(P, seg_hint, num_sms, st, info);
         return launch_split_ws<RpAcoustics2D, 1, 16>(P, seg_hint, num_sms, st, info);
       }
@@ -135,6 +139,10 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
         // Limiter known at compile time (MC on all waves, order 2: BASELINE config 3).  Measured on B200 at 16384^2
         // (profiles/r02_a_c3_variants.jsonl): generic 9.48 ms, specialised 8.97 ms; the march loop unrolled x2 was
         // slower in every combination (11.4 / 11.3 / 9.65 ms) and is gone.
+        if (variant == 2 && split_method<3>(P, 4))             // without the uniform-region fast path (A/B)
+          return launch_split_ws<RpShallowRoeEfix2D, 1, 16, 1, 1, 4>(P, seg_hint, num_sms, st, info);
+        if (variant != 1 && split_method<3>(P, 4) && P.do_x && P.do_y)   // fused step: with the uniform-region fast path
+          return launch_split_ws<RpShallowRoeEfix2D, 1, 16, 1, 1, 4, 8>(P, seg_hint, num_sms, st, info);
         if (variant != 1 && split_method<3>(P, 4))
           return launch_split_ws<RpShallowRoeEfix2D, 1, 16, 1, 1, 4>(P, seg_hint, num_sms, st, info);
         return launch_split_ws<RpShallowRoeEfix2D, 1, 16>(P, seg_hint, num_sms, st, info);

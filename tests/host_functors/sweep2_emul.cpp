@@ -58,6 +58,10 @@ int run(int rp_id, int kind, int variant, Sweep2Params& P, int seg) {
         launch(sweep2_split_ws<RpAcoustics2D, 1, 1, 1, 1, 4>, 32, !P.do_y, P, seg);
         return 0;
       }
+      if (kind == 1 && variant == 73 && all_limiters<2>(P, 4) && P.do_x && P.do_y) {   // + uniform-region fast path, 8-stage ring
+        launch(sweep2_split_ws<RpAcoustics2D, 1, 1, 1, 1, 4, 8>, 32, false, P, seg);
+        return 0;
+      }
       kind ? split_ws<RpAcoustics2D>(P, seg) : unsplit_ws<RpAcoustics2D>(P, seg); return 0;
     case 3:
       if (kind == 0 && P.mtrans == 2 && all_limiters<4>(P, 4) && variant != 9) {      // the headline kernel of bench.py
@@ -76,6 +80,14 @@ int run(int rp_id, int kind, int variant, Sweep2Params& P, int seg) {
     case 4:
       if (kind == 1 && (variant == 53 || variant == 54) && all_limiters<3>(P, 4)) {     // limiter as a template argument
         launch(sweep2_split_ws<RpShallowRoeEfix2D, 1, 1, 1, 1, 4>, 32, !P.do_y, P, seg);
+        return 0;
+      }
+      if (kind == 1 && variant == 73 && all_limiters<3>(P, 4) && P.do_x && P.do_y) {   // + uniform-region fast path, 8-stage ring
+        launch(sweep2_split_ws<RpShallowRoeEfix2D, 1, 1, 1, 1, 4, 8>, 32, false, P, seg);
+        return 0;
+      }
+      if (kind == 1 && variant == 74 && all_limiters<3>(P, 4) && P.do_x && P.do_y) {   // the same with a 4-stage ring
+        launch(sweep2_split_ws<RpShallowRoeEfix2D, 1, 1, 1, 1, 4, 4>, 32, false, P, seg);
         return 0;
       }
       kind ? split_ws<RpShallowRoeEfix2D>(P, seg) : unsplit_ws<RpShallowRoeEfix2D>(P, seg); return 0;
@@ -99,7 +111,7 @@ struct Soa {
   std::vector<double> in, out, aux;
 };
 
-// ids: 0 = unsplit step2, 1 / 2 = step2ds sweep
+// ids: 0 = unsplit step2, 1 / 2 = step2ds sweep, 3 = fused dimension-split step (x-sweep of all rows, then y-sweep)
 int step(int ids, int meqn, int mwaves, int maux, int mx, int my, const double* qold, double* qnew, const double* auxbc,
          double dx, double dy, double dt, const int* method7, const int* mthlim, int use_fwave, int rp_id,
          const double* cparam, int ncparam, int variant, int seg, double* cfl) {

@@ -155,6 +155,13 @@ class EmulatedFmod2D(object):
 
     def step2ds(self, maxm, num_ghost, mx, my, qold, qnew, aux, dx, dy, dt, method, mthlim, aux1, aux2, aux3, work,
                 ids, use_fwave, rpn2, rpt2):
+        if self.variant in (73, 74):
+            # the FUSED dimension-split step of the device-resident path (x-sweep of every row + y-sweep in one march,
+            # clawcuda.cu launch_step: kind 1, do_x = do_y = 1) behind the two step2ds calls of the host loop: the first
+            # call does the whole step (emulation id 3), the second is a no-op
+            if ids == 2:
+                return qnew, 0.0
+            return self._call(3, mx, my, qold, qnew, aux, dx, dy, dt, method, mthlim, use_fwave, rpn2)
         return self._call(ids, mx, my, qold, qnew, aux, dx, dy, dt, method, mthlim, use_fwave, rpn2)
 
 
@@ -190,6 +197,12 @@ CASES_2D = {
     'acoustics_split_limiter_template_variant53': (lambda: S.acoustics_2d(mx=40, my=36), 53, 8),     # BASELINE config 1
     'euler_split_limiter_template_variant53': (lambda: dict(S.quadrants(mx=40, my=30), limiters=S.MC), 53, 7),
     'euler_split_generic': (lambda: S.quadrants(mx=40, my=30), 0, 7),
+    # uniform-region fast path of the fused split step (sweep2_split_ws, QD > 0): dam break (uniform away from the ring),
+    # acoustics pulse (zero outside the annulus); 8- and 4-stage ring, long and short march segments
+    'shallow_split_quiet_ring8': (lambda: dict(S.radial_dam_break(mx=120, my=100), limiters=S.MC), 73, 0),
+    'shallow_split_quiet_ring8_segments': (lambda: dict(S.radial_dam_break(mx=61, my=70), limiters=S.MC), 73, 9),
+    'shallow_split_quiet_ring4_short_segments': (lambda: dict(S.radial_dam_break(mx=90, my=64), limiters=S.MC), 74, 5),
+    'acoustics_split_quiet_ring8': (lambda: S.acoustics_2d(mx=100, my=90), 73, 16),
     'kpp_split': (lambda: S.kpp_2d(mx=40, my=40), 0, 0),
     'kpp_unsplit_notrans': (lambda: dict(S.kpp_2d(mx=33, my=29), dimensional_split=False, transverse_waves=0,
                                          cfl_max=0.5, cfl_desired=0.45), 0, 8),
