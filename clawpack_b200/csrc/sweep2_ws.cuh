@@ -60,6 +60,13 @@ __device__ __forceinline__ bool same_bits(double a, double b) {
 __device__ __forceinline__ unsigned long long diff_bits(double a, double b) {
   return (unsigned long long)(__double_as_longlong(a) ^ __double_as_longlong(b));
 }
+// the value is needed in a register HERE: keeps the compiler from sinking the assignment that produced it into the
+// exits of a loop that follows (where it would be repeated on every iteration)
+__device__ __forceinline__ void pin(double& v) {
+#ifndef CLAW_HOST_CHECK
+  asm volatile("" : "+d"(v));
+#endif
+}
 __device__ __forceinline__ bool warp_all(bool pred) {
 #ifdef CLAW_HOST_CHECK
   return emul::vote_all(pred);
@@ -240,12 +247,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
         // carried state and without the bookkeeping of the general step.
         if (nquiet >= 2 && qcfl_x && qcfl_y && J >= Jb) {
           double* orow = qout + (long long)(J + 1) * P.pitch + I;
+#pragma unroll
+          for (int m = 0; m < M; ++m) { pin(qn0[m]); pin(qn1[m]); pin(q1[m]); }
           while (J + 1 < Je) {
             double qT[M];
             ring_fetch(J + 1, qT);
+            // (qn1 and qn0 carry the bits of q1 here; comparing with the one and storing the other keeps both alive in
+            // this loop, so that the compiler does not sink their last assignments into every exit of it)
             unsigned long long d = 0ull;
 #pragma unroll
-            for (int m = 0; m < M; ++m) d |= diff_bits(q1[m], qT[m]);
+            for (int m = 0; m < M; ++m) d |= diff_bits(qn1[m], qT[m]);
             if (!warp_all(d == 0ull)) {                    // step J+1 goes through the general classification
 #pragma unroll
               for (int m = 0; m < M; ++m) qN[m] = qT[m];
@@ -256,7 +267,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
             if (store_col) {
               double* o = orow;
 #pragma unroll
-              for (int m = 0; m < M; ++m) { *o = q1[m]; o += P.plane; }
+              for (int m = 0; m < M; ++m) { *o = qn0[m]; o += P.plane; }
             }
             orow += P.pitch;
           }
@@ -705,6 +716,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
         if (nquiet >= 2 && qcfl_x && qcfl_y && J >= Jb) {
           double* orow = qout + (long long)(J + 1) * P.pitch + I;
           const bool st = col_ok && interior_col;
+#pragma unroll
+          for (int m = 0; m < M; ++m) { pin(qx0[m]); pin(qx1[m]); }
           while (J + 1 < Je) {
             double qT[M];
             ring_fetch(J + 1, qT);
@@ -721,7 +734,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
             if (st) {
               double* o = orow;
 #pragma unroll
-              for (int m = 0; m < M; ++m) { *o = qx1[m]; o += P.plane; }
+              for (int m = 0; m < M; ++m) { *o = qx0[m]; o += P.plane; }   // qx0 carries the bits of qx1 here
             }
             orow += P.pitch;
           }

@@ -126,6 +126,7 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
         // with a 2 / 4 / 8-stage ring.  CLAW_VARIANT=2: the same kernel without the fast path (dense-data timing, A/B).
         if (variant == 2) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
         if (variant == 71) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6, 1, 4>(P, seg_hint, num_sms, st, info);
+        if (variant == 73) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6, 1, 16>(P, seg_hint, num_sms, st, info);
         if (variant != 1) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6, 1, 8>(P, seg_hint, num_sms, st, info);
       }
       if (kind == 0) return launch_ws<RpEuler4Wave2D, 1, 8, 6>(P, seg_hint, num_sms, st, info);
