@@ -33,6 +33,8 @@ def _declare(L):
         'claw_set_bc': (i, [H, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
         'claw_set_boundary_ownership': (i, [H, c_int_p, c_int_p]),
         'claw_set_mode': (i, [H, i]),
+        'claw_set_source': (i, [H, i, c_double_p, i]),
+        'claw_set_bc_state': (i, [H, i, i, c_double_p]),
         'claw_set_tuning': (i, [H, i]),
         'claw_put_q': (i, [H, vp]),
         'claw_get_q': (i, [H, vp]),

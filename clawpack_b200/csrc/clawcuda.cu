@@ -58,6 +58,12 @@ struct claw_solver {
   int on_lower[3] = {1, 1, 1}, on_upper[3] = {1, 1, 1};
   int mode = CLAW_MODE_STRICT;
   int seg_rows = 0;
+  // device-side callbacks (claw_set_source / claw_set_bc_state): id of the source-term functor run after the sweeps of
+  // an attempt (Godunov splitting, classic/solver.py:137-144) and its parameters; ghost-cell states of BC type
+  // CLAW_BC_FIXED_STATE per dimension and side
+  int src_id = 0;
+  double src_params[4] = {0, 0, 0, 0};
+  double bc_state[3][2][8] = {};
   double* h_cfl = nullptr;   // pinned
   cudaEvent_t ev_cfl = nullptr;
   // transfer/compute pipeline of the f2py-shaped host entry points
@@ -74,6 +80,7 @@ struct claw_solver {
   // one step attempt captured as a CUDA graph (single-rank runs): ghost fill + sweep(s) + control kernel
   cudaGraphExec_t graph = nullptr;
   cudaStream_t s_cap = nullptr;
+  uint64_t graph_nodes = 0;
   uint64_t cfg_epoch = 0, graph_epoch = 0;
   double graph_delta[3] = {0, 0, 0};
   int graph_fill = -1;
@@ -143,8 +150,11 @@ __global__ void soa_to_aos(const double* __restrict__ soa, double* __restrict__ 
 // included), so corners are the composition x-then-y exactly as the numpy slicing does.
 // reflect < 0: no negation (aux arrays / non-wall).
 // ---------------------------------------------------------------------------------------
+struct BcState { double lo[8], up[8]; };    // ghost-cell state per component of a CLAW_BC_FIXED_STATE face
+
 __device__ __forceinline__ void bc_fill_pair(double* base, long long stride, int n, int lo_type, int up_type,
-                                             bool lo_on, bool up_on, bool negate) {
+                                             bool lo_on, bool up_on, bool negate, double lo_val = 0.0,
+                                             double up_val = 0.0) {
   // base[k*stride], k in [0, n+4): cells along the BC dimension
   if (lo_on) {
     if (lo_type == CLAW_BC_EXTRAP) {
@@ -155,6 +165,8 @@ __device__ __forceinline__ void bc_fill_pair(double* base, long long stride, int
     } else if (lo_type == CLAW_BC_WALL) {
       const double v3 = base[3 * stride], v2 = base[2 * stride];
       base[0] = negate ? -v3 : v3; base[stride] = negate ? -v2 : v2;
+    } else if (lo_type == CLAW_BC_FIXED_STATE) {
+      base[0] = lo_val; base[stride] = lo_val;
     }
   }
   if (up_on) {
@@ -166,6 +178,8 @@ __device__ __forceinline__ void bc_fill_pair(double* base, long long stride, int
     } else if (up_type == CLAW_BC_WALL) {
       const double vn1 = base[(long long)(n + 1) * stride], vn = base[(long long)n * stride];
       base[(long long)(n + 2) * stride] = negate ? -vn1 : vn1; base[(long long)(n + 3) * stride] = negate ? -vn : vn;
+    } else if (up_type == CLAW_BC_FIXED_STATE) {
+      base[(long long)(n + 2) * stride] = up_val; base[(long long)(n + 3) * stride] = up_val;
     }
   }
 }
@@ -180,23 +194,45 @@ __device__ __forceinline__ double* sel_array(const ArrSel& a) {
 }
 
 __global__ void bc_x2(ArrSel sel, int ncomp, int mx, int ny, int pitch, long long plane, int lo_type, int up_type,
-                      int lo_on, int up_on, int reflect) {
+                      int lo_on, int up_on, int reflect, BcState bs) {
   double* q = sel_array(sel);
   if (q == nullptr) return;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= ny * ncomp) return;
   const int j = idx % ny, m = idx / ny;
-  bc_fill_pair(q + m * plane + (long long)j * pitch, 1, mx, lo_type, up_type, lo_on != 0, up_on != 0, m == reflect);
+  bc_fill_pair(q + m * plane + (long long)j * pitch, 1, mx, lo_type, up_type, lo_on != 0, up_on != 0, m == reflect,
+               bs.lo[m & 7], bs.up[m & 7]);
 }
 
 __global__ void bc_y2(ArrSel sel, int ncomp, int nx, int my, int pitch, long long plane, int lo_type, int up_type,
-                      int lo_on, int up_on, int reflect) {
+                      int lo_on, int up_on, int reflect, BcState bs) {
   double* q = sel_array(sel);
   if (q == nullptr) return;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nx * ncomp) return;
   const int i = idx % nx, m = idx / nx;
-  bc_fill_pair(q + m * plane + i, pitch, my, lo_type, up_type, lo_on != 0, up_on != 0, m == reflect);
+  bc_fill_pair(q + m * plane + i, pitch, my, lo_type, up_type, lo_on != 0, up_on != 0, m == reflect, bs.lo[m & 7],
+               bs.up[m & 7]);
+}
+
+// small grids: x strips, then y strips, in ONE launch of one CTA (the y strips read the corners the x strips wrote, so
+// the two phases are separated by a CTA barrier); saves a launch per step where launches are what a step costs
+__global__ void bc_xy2_small(ArrSel sel, int ncomp, int mx, int my, int pitch, long long plane, int lo0, int up0,
+                             int lo1, int up1, int lon0, int upn0, int lon1, int upn1, int refl0, int refl1, BcState b0,
+                             BcState b1) {
+  double* q = sel_array(sel);
+  if (q == nullptr) return;
+  const int nx = mx + 4, ny = my + 4;
+  for (int idx = threadIdx.x; idx < ny * ncomp; idx += blockDim.x) {
+    const int j = idx % ny, m = idx / ny;
+    bc_fill_pair(q + m * plane + (long long)j * pitch, 1, mx, lo0, up0, lon0 != 0, upn0 != 0, m == refl0, b0.lo[m & 7],
+                 b0.up[m & 7]);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < nx * ncomp; idx += blockDim.x) {
+    const int i = idx % nx, m = idx / nx;
+    bc_fill_pair(q + m * plane + i, pitch, my, lo1, up1, lon1 != 0, upn1 != 0, m == refl1, b1.lo[m & 7], b1.up[m & 7]);
+  }
 }
 
 // halo rows [j0, j0+2) x all columns x all components <-> contiguous buffer
@@ -228,7 +264,7 @@ __global__ void halo_unpack2(ArrSel sel, const double* buf, int ncomp, int nx, i
 // x-then-y-then-z of the numpy slicing (solver.py:377-437).
 __global__ void bc_dim3(ArrSel sel, int ncomp, int n_d, long long stride_d, int ext_a, long long stride_a, int ext_b,
                         long long stride_b, long long plane, int lo_type, int up_type, int lo_on, int up_on,
-                        int reflect) {
+                        int reflect, BcState bs) {
   double* q = sel_array(sel);
   if (q == nullptr) return;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -236,7 +272,7 @@ __global__ void bc_dim3(ArrSel sel, int ncomp, int n_d, long long stride_d, int 
   if (idx >= per * ncomp) return;
   const int a = (int)(idx % ext_a), b = (int)((idx / ext_a) % ext_b), m = (int)(idx / per);
   bc_fill_pair(q + m * plane + a * stride_a + b * stride_b, stride_d, n_d, lo_type, up_type, lo_on != 0, up_on != 0,
-               m == reflect);
+               m == reflect, bs.lo[m & 7], bs.up[m & 7]);
 }
 
 // ncomp runs of `len` contiguous doubles <-> one contiguous buffer (3-D halo planes)
@@ -366,6 +402,56 @@ __global__ void ctl_end_kernel(StepCtl* ctl, double* log) {
   *ctl = c;
 }
 
+// ---------------------------------------------------------------------------------------
+// Device-side source terms (the `step_source` callback of classic/solver.py:126-144 for users who hand over a device
+// functor instead of a Python function).  Godunov splitting: the source step follows the sweeps of an attempt, on the
+// buffer they wrote, and -- as in ClawSolver.step, :134 -- only when that attempt's CFL number is below cfl_max.
+//
+// id 1: geometric source of the 2-D Euler equations with cylindrical symmetry, two-stage Runge-Kutta
+//       (pyclaw/examples/euler_2d/shock_bubble_interaction.py:112-143, step_Euler_radial): components 0..3 =
+//       (rho, rho u, rho v, E), aux plane 0 = radial coordinate of the cell centre, params = (gamma).  The arithmetic is
+//       numpy's elementwise sequence operation by operation (round-to-nearest, no contraction), so the result carries
+//       the same bits as the host callback's.
+// ---------------------------------------------------------------------------------------
+__global__ void src_euler_radial2(ArrSel sel, const double* __restrict__ aux, int mx, int my, int pitch, long long plane,
+                                  double gamma, double dt_host) {
+  double* q = sel_array(sel);
+  if (q == nullptr) return;
+  double dt = dt_host;
+  if (sel.ctl != nullptr) {
+    const double cfl = __longlong_as_double((long long)sel.ctl->cfl_bits);
+    if (cfl >= sel.ctl->cfl_max) return;                                   // classic/solver.py:134
+    dt = sel.ctl->dt;
+  }
+  const long long n = (long long)mx * my;
+  const double g1 = __dsub_rn(gamma, 1.0);
+  const double dt2 = __ddiv_rn(dt, 2.0);
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(c % mx) + 2, j = (int)(c / mx) + 2;
+    double* p = q + (long long)j * pitch + i;
+    const double rad = aux[(long long)j * pitch + i];
+    const double q0 = p[0], q1 = p[plane], q2 = p[2 * plane], q3 = p[3 * plane];
+    // first stage
+    double rho = q0;
+    double u = __ddiv_rn(q1, rho), v = __ddiv_rn(q2, rho);
+    double press = __dmul_rn(g1, __dsub_rn(q3, __dmul_rn(__dmul_rn(0.5, rho), __dadd_rn(__dmul_rn(u, u), __dmul_rn(v, v)))));
+    const double a2 = __ddiv_rn(dt2, rad);
+    const double s0 = __dsub_rn(q0, __dmul_rn(a2, q2));
+    const double s1 = __dsub_rn(q1, __dmul_rn(__dmul_rn(__dmul_rn(a2, rho), u), v));
+    const double s2 = __dsub_rn(q2, __dmul_rn(__dmul_rn(__dmul_rn(a2, rho), v), v));
+    const double s3 = __dsub_rn(q3, __dmul_rn(__dmul_rn(a2, v), __dadd_rn(q3, press)));
+    // second stage
+    rho = s0;
+    u = __ddiv_rn(s1, rho); v = __ddiv_rn(s2, rho);
+    press = __dmul_rn(g1, __dsub_rn(s3, __dmul_rn(__dmul_rn(0.5, rho), __dadd_rn(__dmul_rn(u, u), __dmul_rn(v, v)))));
+    const double a = __ddiv_rn(dt, rad);
+    p[0] = __dsub_rn(q0, __dmul_rn(a, s2));
+    p[plane] = __dsub_rn(q1, __dmul_rn(__dmul_rn(__dmul_rn(a, rho), u), v));
+    p[2 * plane] = __dsub_rn(q2, __dmul_rn(__dmul_rn(__dmul_rn(a, rho), v), v));
+    p[3 * plane] = __dsub_rn(q3, __dmul_rn(__dmul_rn(a, v), __dadd_rn(s3, press)));
+  }
+}
+
 int check_handle(const claw_solver* h) {
   if (!h) { g_last_error = "null solver handle"; return 1; }
   return 0;
@@ -487,13 +573,19 @@ ArrSel sel_q(claw_solver* h, int role) {
   return a;
 }
 
+BcState bc_state_of(const claw_solver* h, int d) {
+  BcState b{};
+  for (int m = 0; m < 8; ++m) { b.lo[m] = h->bc_state[d][0][m]; b.up[m] = h->bc_state[d][1][m]; }
+  return b;
+}
+
 int fill_ghosts_array(claw_solver* h, ArrSel arr, int ncomp, const int* lo, const int* up, bool is_q) {
   const Dev2& g = h->g;
   for (int d = 0; d < g.ndim; ++d) {
     // BC.custom (0) on an AUX face is allowed: the host filled those ghost cells once (claw_put_auxbc) and the
     // kernels below leave type 0 untouched; on q it needs a host round trip every step
-    const int tmin = is_q ? 1 : 0;
-    if ((h->on_lower[d] && (lo[d] < tmin || lo[d] > 3)) || (h->on_upper[d] && (up[d] < tmin || up[d] > 3)))
+    const int tmin = is_q ? 1 : 0, tmax = is_q ? CLAW_BC_FIXED_STATE : 3;
+    if ((h->on_lower[d] && (lo[d] < tmin || lo[d] > tmax)) || (h->on_upper[d] && (up[d] < tmin || up[d] > tmax)))
       return fail(h, 21, "boundary condition %d/%d in dimension %d cannot run on the device "
                          "(BC.custom needs a host round trip)", lo[d], up[d], d);
   }
@@ -505,9 +597,18 @@ int fill_ghosts_array(claw_solver* h, ArrSel arr, int ncomp, const int* lo, cons
       const long long n = (long long)g.nt[a] * g.nt[b] * ncomp;
       bc_dim3<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(arr, ncomp, g.n[d], st[d], g.nt[a], st[a], g.nt[b],
                                                                   st[b], g.plane, lo[d], up[d], h->on_lower[d],
-                                                                  h->on_upper[d], refl);
+                                                                  h->on_upper[d], refl, bc_state_of(h, d));
       ++h->launches;
     }
+    CK(h, cudaGetLastError());
+    return 0;
+  }
+  if ((long long)g.nt[0] * ncomp <= 4096 && (long long)g.nt[1] * ncomp <= 4096) {
+    bc_xy2_small<<<1, 1024, 0, h->stream>>>(arr, ncomp, g.n[0], g.n[1], g.pitch, g.plane, lo[0], up[0], lo[1], up[1],
+                                            h->on_lower[0], h->on_upper[0], h->on_lower[1], h->on_upper[1],
+                                            is_q ? h->reflect_index[0] : -1, is_q ? h->reflect_index[1] : -1,
+                                            bc_state_of(h, 0), bc_state_of(h, 1));
+    ++h->launches;
     CK(h, cudaGetLastError());
     return 0;
   }
@@ -516,14 +617,14 @@ int fill_ghosts_array(claw_solver* h, ArrSel arr, int ncomp, const int* lo, cons
     const int refl = is_q ? h->reflect_index[0] : -1;
     const int n = g.nt[1] * ncomp;
     bc_x2<<<(n + 127) / 128, 128, 0, h->stream>>>(arr, ncomp, g.n[0], g.nt[1], g.pitch, g.plane, lo[0], up[0],
-                                                  h->on_lower[0], h->on_upper[0], refl);
+                                                  h->on_lower[0], h->on_upper[0], refl, bc_state_of(h, 0));
     ++h->launches;
   }
   {
     const int refl = is_q ? h->reflect_index[1] : -1;
     const int n = g.nt[0] * ncomp;
     bc_y2<<<(n + 127) / 128, 128, 0, h->stream>>>(arr, ncomp, g.nt[0], g.n[1], g.pitch, g.plane, lo[1], up[1],
-                                                  h->on_lower[1], h->on_upper[1], refl);
+                                                  h->on_lower[1], h->on_upper[1], refl, bc_state_of(h, 1));
     ++h->launches;
   }
   CK(h, cudaGetLastError());
@@ -832,6 +933,28 @@ int claw_set_boundary_ownership(claw_solver* h, const int* on_lower, const int* 
   return 0;
 }
 
+int claw_set_source(claw_solver* h, int src_id, const double* params, int nparams) {
+  if (check_handle(h)) return 1;
+  ++h->cfg_epoch;
+  if (src_id == 0) { h->src_id = 0; return 0; }
+  if (src_id != CLAW_SRC_EULER_RADIAL_2D) return fail(h, 60, "claw_set_source: unknown source functor %d", src_id);
+  if (h->g.ndim != 2 || h->meqn < 4 || h->maux < 1)
+    return fail(h, 61, "claw_set_source: the radial Euler source needs a 2-D state with >= 4 components and aux(1) = radius "
+                       "(ndim=%d meqn=%d maux=%d)", h->g.ndim, h->meqn, h->maux);
+  if (nparams < 1 || !params) return fail(h, 62, "claw_set_source: the radial Euler source takes one parameter (gamma)");
+  h->src_id = src_id;
+  for (int k = 0; k < 4; ++k) h->src_params[k] = (k < nparams) ? params[k] : 0.0;
+  return 0;
+}
+
+int claw_set_bc_state(claw_solver* h, int dim, int side, const double* values) {
+  if (check_handle(h)) return 1;
+  if (dim < 0 || dim >= h->g.ndim || side < 0 || side > 1 || !values) return fail(h, 63, "claw_set_bc_state: bad arguments");
+  ++h->cfg_epoch;
+  for (int m = 0; m < 8; ++m) h->bc_state[dim][side][m] = (m < h->meqn) ? values[m] : 0.0;
+  return 0;
+}
+
 int claw_set_mode(claw_solver* h, int mode) {
   if (check_handle(h)) return 1;
   ++h->cfg_epoch;
@@ -1002,6 +1125,13 @@ int ctl_enqueue_sweep(claw_solver* h, const double* delta, int fill_ghosts) {
   return launch_step(h, delta, 0.0, nullptr, nullptr, true);
 }
 int ctl_enqueue_end(claw_solver* h) {
+  if (h->src_id == 1) {                                // source step on the buffer the sweeps wrote, before accept/reject
+    const Dev2& g = h->g;
+    const long long n = (long long)g.n[0] * g.n[1];
+    src_euler_radial2<<<grid_for(n, 256), 256, 0, h->stream>>>(sel_q(h, 1), h->aux, g.n[0], g.n[1], g.pitch, g.plane,
+                                                               h->src_params[0], 0.0);
+    ++h->launches;
+  }
   ctl_end_kernel<<<1, 1, 0, h->stream>>>(reinterpret_cast<StepCtl*>(h->work), h->work + CTL_WORDS);
   ++h->launches;
   CK(h, cudaGetLastError());
@@ -1078,6 +1208,7 @@ int claw_ctl_attempts(claw_solver* h, const double* delta, int n, int fill_ghost
         h->stream = user;
         e = cudaStreamEndCapture(h->s_cap, &g);
       }
+      h->graph_nodes = h->launches - launches0;      // kernels per attempt
       h->launches = launches0;                       // nothing ran
       if (rc || e != cudaSuccess || g == nullptr) {
         if (g) cudaGraphDestroy(g);
@@ -1096,10 +1227,8 @@ int claw_ctl_attempts(claw_solver* h, const double* delta, int n, int fill_ghost
     }
   }
   if (graph_ok) {
-    const uint64_t per = (uint64_t)(fill_ghosts ? (ndim == 3 ? 3 : 2) + (h->maux > 0 ? (ndim == 3 ? 3 : 2) : 0) : 0) +
-                         (ndim == 3 ? 3 : 1) + 1;
     for (int k = 0; k < n; ++k) CK(h, cudaGraphLaunch(h->graph, h->stream));
-    h->launches += per * (uint64_t)n;
+    h->launches += h->graph_nodes * (uint64_t)n;
     return 0;
   }
   for (int k = 0; k < n; ++k) {

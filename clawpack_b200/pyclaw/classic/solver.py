@@ -111,12 +111,17 @@ class ClawSolver(Solver):
 
     def _device_path_eligible(self, dev_is_mine=False):
         from ..solver import BC
-        if (self.fmod is not None and not dev_is_mine) or self.before_step is not None or self.step_source is not None:
+        if (self.fmod is not None and not dev_is_mine) or self.before_step is not None:
             return False
-        # BC.custom on q needs the host every step; BC.custom on aux alone does not: aux is static on the device
-        # path, so the user's aux ghost fill is evaluated once at setup (cuda_classic.DeviceStepper)
-        for lst in (self.bc_lower, self.bc_upper):
-            if any(b == BC.custom for b in lst):
+        # a source term keeps the run on the device only as a device functor (pyclaw.device_callbacks) with Godunov
+        # splitting: the half step of Strang splitting before the sweep would modify the buffer a rejected step keeps
+        if self.step_source is not None and not (hasattr(self.step_source, 'device_source') and self.source_split == 1):
+            return False
+        # BC.custom on q needs the host every step unless the fill is a device functor; BC.custom on aux alone does
+        # not: aux is static on the device path, so the user's aux ghost fill is evaluated once at setup
+        # (cuda_classic.DeviceStepper)
+        for lst, fun in ((self.bc_lower, self.user_bc_lower), (self.bc_upper, self.user_bc_upper)):
+            if any(b == BC.custom for b in lst) and not hasattr(fun, 'device_bc'):
                 return False
         return True
 

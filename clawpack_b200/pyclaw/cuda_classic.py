@@ -105,7 +105,21 @@ class DeviceStepper(object):
         _lib.check(L.claw_set_method(h, _lib.ip(np.ascontiguousarray(solver._method, dtype=np.intc)), _lib.ip(mth),
                                      int(bool(solver.fwave))), h)
         nd = solver.num_dim
-        _lib.check(L.claw_set_bc(h, _lib.ip(_iarr(solver.bc_lower, 3)), _lib.ip(_iarr(solver.bc_upper, 3)),
+        # BC.custom faces whose fill is a device functor (device_callbacks.FixedStateBC) become device BC types
+        bc_lo, bc_up = list(solver.bc_lower), list(solver.bc_upper)
+        for side, (types, fun) in enumerate(((bc_lo, solver.user_bc_lower), (bc_up, solver.user_bc_upper))):
+            for d in range(nd):
+                if types[d] == 0 and hasattr(fun, 'device_bc'):
+                    bc_type, values = fun.device_bc
+                    types[d] = bc_type
+                    vals = np.zeros(8, dtype=np.float64)
+                    vals[:len(values)] = values
+                    _lib.check(L.claw_set_bc_state(h, d, side, _lib.dp(vals)), h)
+        if solver.step_source is not None:
+            src_id, params = solver.step_source.device_source
+            pa = np.array(list(params) + [0.0], dtype=np.float64)
+            _lib.check(L.claw_set_source(h, int(src_id), _lib.dp(pa), len(params)), h)
+        _lib.check(L.claw_set_bc(h, _lib.ip(_iarr(bc_lo, 3)), _lib.ip(_iarr(bc_up, 3)),
                                  _lib.ip(_iarr(solver.aux_bc_lower, 3)), _lib.ip(_iarr(solver.aux_bc_upper, 3)),
                                  _lib.ip(_iarr(solver.reflect_index, 3))), h)
         grid = state.grid

@@ -40,7 +40,7 @@ def _base(rp, lower, upper, n, q, **kw):
              dimensional_split=True, transverse_waves=None, cfl_max=1.0, cfl_desired=0.9,
              dt_initial=0.1, bc_lower=None, bc_upper=None, aux_bc_lower=None, aux_bc_upper=None,
              tfinal=1.0, num_output_times=10, index_capa=-1, custom_aux_bc_lower=None, custom_aux_bc_upper=None,
-             slab=None, mapc2p=None, step_source=None, source_split=1, before_step=None, fwave=False, gauges=None, custom_bc_lower_full=None,
+             slab=None, device_callbacks=None, mapc2p=None, step_source=None, source_split=1, before_step=None, fwave=False, gauges=None, custom_bc_lower_full=None,
              compute_gauge_values=None)
     d.update(kw)
     return d
@@ -167,7 +167,8 @@ def quadrants_tracer(mx=60, my=50, **kw):
     return sc
 
 
-def shock_bubble_interaction(q0, tfinal=0.2, num_output_times=1, dimensional_split=True, transverse_waves=None):
+def shock_bubble_interaction(q0, tfinal=0.2, num_output_times=1, dimensional_split=True, transverse_waves=None,
+                             device_callbacks=False):
     """pyclaw/examples/euler_2d/shock_bubble_interaction.py:93-215 (classic branch): axisymmetric Euler + tracer
     (euler_5wave_2D), Mach-2.95 shock hitting a light bubble; aux(1) = radial coordinate of the cell centre;
     Godunov-split geometric source term advanced on the HOST by a 2-stage Runge-Kutta step; inflow (BC.custom) at
@@ -214,7 +215,12 @@ def shock_bubble_interaction(q0, tfinal=0.2, num_output_times=1, dimensional_spl
         q[2, :, :] = q[2, :, :] - dt / rad * rho * v * v
         q[3, :, :] = q[3, :, :] - dt / rad * v * (qs[3, :, :] + press)
 
+    dc = None
+    if device_callbacks:                                 # source term and inflow BC as device functors: no host round trip
+        from .pyclaw import device_callbacks as D
+        dc = {'step_source': D.EulerRadialSource(gamma), 'user_bc_lower': D.FixedStateBC([rinf, rinf * vinf, 0., einf, 0.])}
     return _base('euler_5wave_2D', lower, upper, (mx, my), q0, aux=aux, problem_data={'gamma': gamma},
+                 device_callbacks=dc,
                  limiters=[MC, MC, MC, MC, SUPERBEE], dimensional_split=bool(dimensional_split),
                  transverse_waves=transverse_waves, cfl_max=0.5, cfl_desired=0.45,
                  bc_lower=[0, WALL], bc_upper=[EXTRAP, EXTRAP], aux_bc_lower=[EXTRAP, EXTRAP],
@@ -889,6 +895,12 @@ def make_claw(sc, kernel_language='CUDA', pyclaw=None, **solver_kw):
         fs = sc['step_source']
         solver.step_source = lambda solver_, state, dt: fs(state.q, state.aux, dt)
         solver.source_split = sc.get('source_split', 1)
+    if sc.get('device_callbacks') is not None:          # the same hooks as device functors (pyclaw.device_callbacks)
+        dc = sc['device_callbacks']
+        if 'step_source' in dc:
+            solver.step_source = dc['step_source']
+        if 'user_bc_lower' in dc:
+            solver.user_bc_lower = dc['user_bc_lower']
     if sc.get('before_step') is not None:
         fb = sc['before_step']
         solver.before_step = lambda solver_, state: fb(state.q, state.aux)

@@ -81,7 +81,16 @@ enum {
 };
 
 /* Boundary-condition ids = pyclaw.BC (pyclaw/src/pyclaw/solver.py:13-19) */
-enum { CLAW_BC_CUSTOM = 0, CLAW_BC_EXTRAP = 1, CLAW_BC_PERIODIC = 2, CLAW_BC_WALL = 3 };
+enum { CLAW_BC_CUSTOM = 0, CLAW_BC_EXTRAP = 1, CLAW_BC_PERIODIC = 2, CLAW_BC_WALL = 3,
+       /* device-side stand-in for a BC.custom callback that writes one fixed state into the ghost cells of a face
+          (e.g. incoming_shock, pyclaw/examples/euler_2d/shock_bubble_interaction.py:93-109); state via claw_set_bc_state */
+       CLAW_BC_FIXED_STATE = 4 };
+
+/* device-side source-term functors (claw_set_source): the `step_source` callbacks of reference examples, restated as
+   kernels so that a run with a source term stays device-resident (Godunov splitting, classic/solver.py:126-144) */
+enum { CLAW_SRC_NONE = 0,
+       CLAW_SRC_EULER_RADIAL_2D = 1   /* step_Euler_radial, examples/euler_2d/shock_bubble_interaction.py:112-143;
+                                         aux(1) = radius, params = (gamma) */ };
 
 /* arithmetic mode: STRICT = no FMA contraction, op-for-op the reference (bit-exact vs the oracle);
    FAST = FMA contraction allowed (within the 1e-12/step tolerance) */
@@ -117,6 +126,11 @@ int claw_set_bc(claw_solver* h, const int* lower, const int* upper, const int* a
 /* which faces of this patch are physical boundaries (petclaw/geometry.py:21-41); default all */
 int claw_set_boundary_ownership(claw_solver* h, const int* on_lower, const int* on_upper);
 int claw_set_mode(claw_solver* h, int mode);
+/* source functor run after the sweeps of every attempt under claw_ctl_* (skipped when that attempt's CFL >= cfl_max, as
+   ClawSolver.step does, classic/solver.py:134); src_id 0 switches it off */
+int claw_set_source(claw_solver* h, int src_id, const double* params, int nparams);
+/* ghost-cell state (meqn values) of a CLAW_BC_FIXED_STATE face; side 0 = lower, 1 = upper */
+int claw_set_bc_state(claw_solver* h, int dim, int side, const double* values);
 /* tuning knobs: rows per march segment (0 = auto) */
 int claw_set_tuning(claw_solver* h, int seg_rows);
 

@@ -232,3 +232,44 @@ def test_missing_transverse_solver_is_refused():
         claw = S.make_claw(sc, kernel_language='CUDA')
         with pytest.raises(ClawCudaError):
             claw.run()
+
+
+# ---- device-side source term and BC.custom (pyclaw.device_callbacks) --------------------------------------------------
+def test_shock_bubble_interaction_device_resident_bit_exact():
+    """The reference's shock-bubble example (euler_5wave_2D + step_Euler_radial + incoming_shock) with the source term and
+    the inflow fill as DEVICE functors: the solver stays on the device-resident path (no plug-in object, no host round
+    trip per step) and reproduces the oracle run with the host callbacks bit for bit in strict arithmetic, step log
+    included; and the reference's stored vector to its tolerance (test_euler2d.py:35-37: L1 < 1e-6)."""
+    q0 = goldens2()['euler_2d__shock_bubble_interaction_q0']
+    sc = S.shock_bubble_interaction(q0, device_callbacks=True)
+    claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision='strict')
+    claw.run()
+    assert claw.solver._dev is not None and claw.solver.fmod is None          # device-resident, not plug-in mode
+    q = claw.frames[claw.num_output_times].state.get_q_global()
+    r = ref_solver(S.shock_bubble_interaction(q0))
+    r.run(sc['tfinal'], sc['num_output_times'])
+    assert claw.solver.step_log == r.step_log
+    assert np.array_equal(q, r.q), np.max(np.abs(q - r.q))
+    e = goldens2()['euler_2d__shock_bubble_interaction']
+    dx, dy = claw.solution.domain.grid.delta
+    assert dx * dy * np.sum(np.abs(q[0].reshape(-1) - e)) < 1e-6
+
+
+def test_shock_bubble_interaction_device_resident_fast_and_host_call():
+    """Fast arithmetic within tolerance; and the device functor objects are ordinary host callbacks as well (plug-in
+    mode when kernel_language='CUDA' is given a before_step hook that forces the host path)."""
+    q0 = goldens2()['euler_2d__shock_bubble_interaction_q0']
+    sc = S.shock_bubble_interaction(q0, tfinal=0.05, device_callbacks=True)
+    r = ref_solver(S.shock_bubble_interaction(q0, tfinal=0.05))
+    r.run(sc['tfinal'], sc['num_output_times'])
+    claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision='fast')
+    claw.run()
+    assert claw.solver._dev is not None
+    q = claw.frames[claw.num_output_times].state.get_q_global()
+    assert [s[2] for s in claw.solver.step_log] == [s[2] for s in r.step_log]
+    assert np.max(np.abs(q - r.q)) / np.max(np.abs(r.q)) < 1e-10
+    claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision='strict')
+    claw.solver.before_step = lambda solver, state: None                      # host hook: plug-in mode
+    claw.run()
+    assert claw.solver._dev is None and claw.solver.fmod is not None
+    assert np.array_equal(claw.frames[claw.num_output_times].state.get_q_global(), r.q)

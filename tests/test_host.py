@@ -425,3 +425,30 @@ def test_reads_the_reference_amrclaw_binary_frame(tmp_path):
                 assert np.array_equal(a.q, b.q)
             else:
                 assert np.max(np.abs(a.q - b.q)) <= 5e-9 * max(1.0, np.max(np.abs(b.q)))
+
+
+def test_device_callback_objects_are_reference_shaped_host_callbacks(oracle_lib):
+    """pyclaw.device_callbacks: EulerRadialSource / FixedStateBC called as ordinary host callbacks (step_source(solver,
+    state, dt); user_bc_lower(state, dim, t, qbc, auxbc, num_ghost)) give the bits of the example's own Python functions
+    (shock_bubble_interaction.py:93-143) in the host loop -- and are recognised as device functors by the eligibility
+    test of the device-resident path."""
+    g2 = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_goldens2.npz'))
+    q0 = g2['euler_2d__shock_bubble_interaction_q0'][:, :64, :]
+    sc = S.shock_bubble_interaction(q0, tfinal=0.02, device_callbacks=True)
+    claw = S.make_claw(sc, kernel_language='Fortran', fmod=OracleFmod())
+    assert hasattr(claw.solver.step_source, 'device_source') and hasattr(claw.solver.user_bc_lower, 'device_bc')
+    claw.solver.kernel_language = 'CUDA'
+    try:
+        claw.solver.fmod = None
+        assert claw.solver._device_path_eligible()
+        claw.solver.source_split = 2                      # Strang splitting: host path
+        assert not claw.solver._device_path_eligible()
+        claw.solver.source_split = 1
+    finally:
+        claw.solver.kernel_language = 'Fortran'
+        claw.solver.fmod = OracleFmod()
+    claw.run()
+    r = ref_solver(S.shock_bubble_interaction(q0, tfinal=0.02))
+    r.run(sc['tfinal'], sc['num_output_times'])
+    assert claw.solver.step_log == r.step_log
+    assert np.array_equal(claw.frames[-1].q, r.q)

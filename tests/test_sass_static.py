@@ -36,9 +36,10 @@ def test_headline_euler_kernel_shape(fast_kernels):
     assert _count(c, lambda k: k.startswith('LDGSTS')) >= 4                      # cp.async row prefetch ring
     assert _count(c, lambda k: k.startswith('SHFL')) >= 90                       # neighbour exchange by shuffle
     assert _count(c, lambda k: k.startswith('BAR')) <= 2                         # no barrier in the march loop
-    # measured build (round 2, with the uniform-region fast path and the 8-stage ring): ~2240 instructions, ~860 of them
-    # FP64 arithmetic; the full march step is ~1420 instructions with ~800 FP64, the quiet step ~160 with 10
-    assert n <= 2400 and fp64 / n >= 0.36, (n, fp64)
+    # measured build (round 2, with the uniform-region fast path, its tight inner loop for runs of quiet rows and the
+    # 8-stage ring): ~3290 instructions, ~940 of them FP64 arithmetic; the full march step is ~1420 instructions with
+    # ~800 FP64, the quiet step ~160 with 10
+    assert n <= 3500 and 800 <= fp64 <= 1000, (n, fp64)
     assert _count(c, lambda k: k.startswith('VOTE')) >= 2                        # the warp votes of the fast path
     assert _count(c, lambda k: k.startswith('MUFU.RCP64H') or k.startswith('MUFU.RSQ64H')) <= 32   # shared reciprocals
 
@@ -57,8 +58,9 @@ def test_no_fast_sweep_kernel_of_the_baseline_configs_spills(fast_kernels):
 
 def test_specialised_split_kernel_is_smaller_than_the_generic_one(fast_kernels):
     """The default kernel of BASELINE config 3 (limiter as a template argument) against the generic shallow-water split kernel."""
-    gen = [k for k in fast_kernels if 'sweep2_split_wsINS0_18RpShallowRoeEfix2DELi1ELi16ELi1ELi1ELi0E' in k]
-    spec = [k for k in fast_kernels if 'sweep2_split_wsINS0_18RpShallowRoeEfix2DELi1ELi16ELi1ELi1ELi4E' in k]
+    # (both without the uniform-region fast path, QD = 0: the default adds ~900 instructions of quiet-row handling)
+    gen = [k for k in fast_kernels if 'sweep2_split_wsINS0_18RpShallowRoeEfix2DELi1ELi16ELi1ELi1ELi0ELi0E' in k]
+    spec = [k for k in fast_kernels if 'sweep2_split_wsINS0_18RpShallowRoeEfix2DELi1ELi16ELi1ELi1ELi4ELi0E' in k]
     assert len(gen) == 1 and len(spec) == 1
     assert len(fast_kernels[spec[0]]) < 0.75 * len(fast_kernels[gen[0]])
 
