@@ -63,6 +63,11 @@ struct claw_solver {
   // CLAW_BC_FIXED_STATE per dimension and side
   int src_id = 0;
   double src_params[4] = {0, 0, 0, 0};
+  // tile ordering of the 2-D kernels with the uniform-region fast path (sweep2_ws.cuh, HotTiles): small device buffer
+  // owned by the handle; capacity of one tile list / one flag array in words
+  unsigned* hot = nullptr;
+  int hot_cap = 0, hot_tiles = 0;
+  unsigned hot_epoch = 0;
   double bc_state[3][2][8] = {};
   double* h_cfl = nullptr;   // pinned
   cudaEvent_t ev_cfl = nullptr;
@@ -656,6 +661,12 @@ int launch_step2(claw_solver* h, double dx, double dy, double dt, int kind, int 
   P.do_x = do_x; P.do_y = do_y;
   P.aux = h->aux; P.maux = h->maux; P.capa = h->method[5]; P.fwave = h->use_fwave;
   for (int k = 0; k < 4; ++k) P.rp.p[k] = h->cparam[k];
+  // tile ordering: full-grid launches of the device-resident path only (the chunks of the pipelined host entry points
+  // are different grids on other streams)
+  if (h->hot && j0 == 0 && j1 == 0 && stream_override == nullptr) {
+    P.hot = h->hot; P.hot_cap = h->hot_cap; P.hot_tiles = h->hot_tiles;
+    P.hot_epoch = h->hot_epoch++;
+  }
   cudaError_t e = (h->mode == CLAW_MODE_FAST)
                       ? fast::launch_sweep2(h->rp_id, kind, P, h->seg_rows, h->num_sms, st, &h->last_launch)
                       : strict::launch_sweep2(h->rp_id, kind, P, h->seg_rows, h->num_sms, st, &h->last_launch);
@@ -850,6 +861,17 @@ int claw_create(claw_solver** out, int ndim, int rp_id, int meqn, int mwaves, in
   if (e == cudaSuccess) e = cudaHostAlloc(&h->h_cfl, 64, cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaHostAlloc(&h->h_ctl, WORK_HDR * sizeof(double), cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_cfl, cudaEventDisableTiming);
+  if (e == cudaSuccess && ndim == 2) {
+    // tiles of the finest march segmentation the launch code uses (8 rows) on 28-column strips
+    const long long strips = (n[0] + 27) / 28, segs = (n[1] + 4 + 7) / 8 + 1;
+    if (strips * segs < (1LL << 26)) {
+      h->hot_tiles = (int)(strips * segs);
+      h->hot_cap = (int)(strips * (segs / 16 + 1));
+      const size_t bytes = (8 + 3 * (size_t)h->hot_cap + 3 * (size_t)h->hot_tiles) * sizeof(unsigned);
+      e = cudaMalloc(&h->hot, bytes);
+      if (e == cudaSuccess) e = cudaMemset(h->hot, 0, bytes);
+    }
+  }
   if (e != cudaSuccess) {
     int rc = fail(nullptr, 100 + (int)e, "claw_create: %s", cudaGetErrorString(e));
     delete h;
@@ -867,6 +889,7 @@ int claw_destroy(claw_solver* h) {
   }
   if (h->h_cfl) cudaFreeHost(h->h_cfl);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->hot) cudaFree(h->hot);
   if (h->graph) cudaGraphExecDestroy(h->graph);
   if (h->s_cap) cudaStreamDestroy(h->s_cap);
   if (h->ev_cfl) cudaEventDestroy(h->ev_cfl);

@@ -75,6 +75,190 @@ __device__ __forceinline__ bool warp_all(bool pred) {
 #endif
 }
 
+// Row ring in shared memory, thread-private: component m of ring slot s lives at spf[(m * RD + s) * NT] (component-major,
+// so that the slot offset wraps with one AND for any number of components).  The tight loop below addresses it through
+// the 32-bit shared window (one conversion per kernel, constant byte offsets folded into the instructions) instead of
+// generic pointers (a window conversion per access).
+#ifdef CLAW_HOST_CHECK
+using ring_t = double*;
+inline ring_t ring_of(double* p) { return p; }
+template <int OFF> inline void ring_cp8(ring_t r, int off, const double* g) { r[off + OFF] = *g; }
+template <int OFF> inline double ring_ld(ring_t r, int off) { return r[off + OFF]; }
+#else
+using ring_t = unsigned;
+__device__ __forceinline__ ring_t ring_of(double* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int OFF> __device__ __forceinline__ void ring_cp8(ring_t r, int off, const double* g) {
+  asm volatile("cp.async.ca.shared.global [%0+%2], [%1], 8;" ::"r"(r + 8u * (unsigned)off), "l"(g), "n"(8 * OFF) : "memory");
+}
+template <int OFF> __device__ __forceinline__ double ring_ld(ring_t r, int off) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(r + 8u * (unsigned)off), "n"(8 * OFF) : "memory");
+  return v;
+}
+#endif
+template <int M, int RD, int NT, int m = 0> __device__ __forceinline__ void ring_cp_row(ring_t r, int off, const double* (&g)[M]) {
+  if constexpr (m < M) { ring_cp8<m * RD * NT>(r, off, g[m]); ring_cp_row<M, RD, NT, m + 1>(r, off, g); }
+}
+template <int M, int RD, int NT, int m = 0> __device__ __forceinline__ void ring_ld_row(ring_t r, int off, double (&q)[M]) {
+  if constexpr (m < M) { q[m] = ring_ld<m * RD * NT>(r, off); ring_ld_row<M, RD, NT, m + 1>(r, off, q); }
+}
+
+// Tight loop of the uniform-region fast path: a run of rows that carry the bits of `ref` in all 32 columns of the warp.
+// Per row: queue the row RD steps ahead, wait for the next row of the ring, compare it with `ref`, vote, store `sto`
+// (which carries the bits of `ref`) as the output row.  J is the march step whose row has been stored last; the loop
+// ends at the segment end or at the first row that differs, which is handed over in qT (return value true) for the
+// general classification of step J + 1.  Ring bookkeeping (wslot, rslot: slot offsets in doubles; gfetch: row to queue
+// next) is the caller's and is left as ring_fetch would have left it.
+template <int M, int RD, int NT>
+__device__ __forceinline__ bool quiet_run(int& J, const int Je, const double (&ref)[M], const double (&sto)[M], double (&qT)[M],
+                                          double* spf, int& wslot, int& rslot, const double*& gfetch, const long long plane,
+                                          const int pitch, double* orow, const bool st) {
+  constexpr int WRAP = RD * NT - 1;
+  const ring_t ring = ring_of(spf);
+  // running pointers per component (an invariant base + 32-bit row offset was measured to compile to more instructions:
+  // at 255 registers the compiler rematerialises the plane pointers on every row)
+  const double* gf[M];
+  double* os[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) { gf[m] = gfetch + m * plane; os[m] = orow + m * plane; }
+  int nf = Je - J - RD;                                    // rows still to be queued (step Js queues row Js+RD+1 <= Je+1)
+  int wo = wslot, ro = rslot;
+  bool differs = false;
+  const int J0 = J;
+  while (J + 1 < Je) {
+    if (nf > 0) ring_cp_row<M, RD, NT>(ring, wo, gf);
+    cp_async_commit();
+    --nf;
+#pragma unroll
+    for (int m = 0; m < M; ++m) gf[m] += pitch;
+    wo = (wo + NT) & WRAP;
+    cp_async_wait_keep<RD - 1>();
+    ring_ld_row<M, RD, NT>(ring, ro, qT);
+    ro = (ro + NT) & WRAP;
+    unsigned long long d = 0ull;
+#pragma unroll
+    for (int m = 0; m < M; ++m) d |= diff_bits(ref[m], qT[m]);
+    if (!warp_all(d == 0ull)) { differs = true; break; }
+    ++J;
+    if (st) {
+#pragma unroll
+      for (int m = 0; m < M; ++m) *os[m] = sto[m];
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) os[m] += pitch;
+  }
+  gfetch += (long long)(J - J0 + (differs ? 1 : 0)) * pitch;
+  wslot = wo; rslot = ro;
+  return differs;
+}
+
+// Measured and dropped (profiles/r02_q, r02_s): a WIDE form of this loop -- 16-byte loads straight into registers (two
+// LDG.128 per row for up to four components, U rows in flight, no shared memory), 16-byte stores of the 28 owned columns,
+// the loop proper as a __noinline__ function with its own register allocation (39 instead of 65-75 instructions per row).
+// It was slower on both kernels (8192^2 Euler 0.79 against 0.75 ms, 16384^2 shallow water 2.38 against 2.19 ms).  What
+// the ncu capture of the shallow-water kernel (mio_throttle 5.5, short_scoreboard 4.1 warps per issue cycle at 4.3 TB/s)
+// really showed was too many cp.async rows in flight per SM: 16 warps x 7 rows ran at 4.3 TB/s, 16 x 3 at 5.9 TB/s,
+// 8 x 7 at 6.0 TB/s, 8 x 3 at 5.4 TB/s -- about 50 rows per SM is the optimum, which fixes the ring depth per kernel
+// (sweep_inst.cu).
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tile ordering for the kernels with the uniform-region fast path.  There the cost of a tile (one strip x one march
+// segment) depends on the data: a tile inside a uniform region streams at HBM speed, a tile full of a front costs the
+// full arithmetic of every row -- 50 to 100 times more -- and the heavy tiles that happen to be dispatched last are the
+// tail of the launch (measured at 8192^2, profiles/r02_n: planar shock alone +0.10 to +0.15 ms on 0.75 ms).  Fronts move
+// by at most one cell per step, so last step's heavy tiles are this step's: every CTA reports whether its tile was heavy,
+// and the next launch runs the reported tiles FIRST, from `hot_rows` extra grid rows in front of the regular grid (CTAs
+// are dispatched in linear order); the regular CTA of such a tile exits at once.  Purely a scheduling hint: each tile is
+// still processed exactly once per launch, by the same code.
+//
+// Device buffer (unsigned words): three tile lists used in rotation -- launch number e (the attempt counter of the
+// StepCtl, or a host counter) READS list e % 3, WRITES list (e+1) % 3 and CLEARS list (e+2) % 3, so that no word is read
+// and written in the same launch and no CTA has to wait for another.  [0..2] entries in list 0 / 1 / 2, [3..5] stamp of
+// the grid each list was written for, [8 .. 8+3*cap) the lists, then three flag arrays (hot_tiles words each):
+// flag[tile] = 1 + position in the list, 0 = not listed.  List and flag are checked against each other on both sides, so
+// stale or foreign contents (a skipped launch number, another segmentation) can only cost the ordering, never a tile.
+// ---------------------------------------------------------------------------------------------------------------------
+// which instantiations carry the uniform-region fast path (and with it the tile ordering): shared by the kernels and the
+// launch code, which adds the hot grid rows only for these
+template <class RP, int SPEC, int QD> struct UnsplitQuiet {
+#ifdef CLAW_STRICT
+  static constexpr bool value = false;
+#else
+  static constexpr bool value = (QD > 0) && ((SPEC & 1) != 0) && (((SPEC >> 1) & 3) == 3) && (RP::NCELL > 0);
+#endif
+};
+template <class RP, int PF, int LIM, int QD> struct SplitQuiet {
+#ifdef CLAW_STRICT
+  static constexpr bool value = false;
+#else
+  static constexpr bool value = (QD > 0) && (LIM > 0) && (PF != 0) && (RP::NCELL == 0);
+#endif
+};
+
+struct HotTile {
+  int bx, by;               // the tile this CTA works on (strip, segment)
+  unsigned tile, epoch;
+  bool run;                 // false: nothing to do for this CTA (empty hot slot, or the tile is run by a hot CTA)
+};
+
+__device__ __forceinline__ unsigned hot_stamp(const Sweep2Params& P, unsigned strips, unsigned nseg) {
+  return ((strips << 16) ^ nseg ^ ((unsigned)P.seg_rows << 8)) | 0x80000000u;
+}
+
+__device__ __forceinline__ HotTile hot_begin(const Sweep2Params& P) {
+  HotTile h;
+  h.bx = (int)blockIdx.x; h.by = (int)blockIdx.y; h.tile = 0; h.epoch = 0; h.run = true;
+  if (P.hot_rows <= 0) return h;
+  const unsigned strips = gridDim.x, nseg = gridDim.y - (unsigned)P.hot_rows, ntiles = strips * nseg;
+  const unsigned cap = (unsigned)P.hot_rows * strips;
+  const unsigned* hot = P.hot;
+  h.epoch = (P.ctl != nullptr) ? (unsigned)P.ctl->attempts : (unsigned)P.hot_epoch;
+  const unsigned p = h.epoch % 3u;
+  const unsigned* list = hot + 8 + p * (unsigned)P.hot_cap;
+  const unsigned* flag = hot + 8 + 3u * (unsigned)P.hot_cap + p * (unsigned)P.hot_tiles;
+  unsigned cnt = hot[p];
+  const unsigned stamp = hot[3 + p];
+  if (blockIdx.y < (unsigned)P.hot_rows) {
+    const unsigned idx = blockIdx.y * strips + blockIdx.x;
+    h.run = false;
+    if (stamp != hot_stamp(P, strips, nseg)) cnt = 0u;
+    if (cnt > cap) cnt = cap;
+    if (idx < cnt) {
+      const unsigned tl = list[idx];
+      if (tl < ntiles && flag[tl] == idx + 1u) { h.run = true; h.tile = tl; h.bx = (int)(tl % strips); h.by = (int)(tl / strips); }
+    }
+  } else {
+    h.by = (int)blockIdx.y - P.hot_rows;
+    h.tile = (unsigned)h.by * strips + (unsigned)h.bx;
+    const unsigned f = flag[h.tile];                        // (independent of the two header loads above)
+    if (stamp != hot_stamp(P, strips, nseg)) cnt = 0u;
+    if (cnt > cap) cnt = cap;
+    if (f != 0u && f - 1u < cnt && list[f - 1u] == h.tile) h.run = false;       // a hot CTA runs this tile
+  }
+  return h;
+}
+
+// called by every thread of every CTA of the launch at its end; `heavy`: this CTA's tile goes first next time
+__device__ __forceinline__ void hot_end(const Sweep2Params& P, const HotTile& h, bool heavy) {
+  if (P.hot_rows <= 0 || threadIdx.x != 0) return;
+  unsigned* hot = P.hot;
+  const unsigned strips = gridDim.x, nseg = gridDim.y - (unsigned)P.hot_rows;
+  const unsigned cap = (unsigned)P.hot_rows * strips;
+  const unsigned pn = (h.epoch + 1u) % 3u, pz = (h.epoch + 2u) % 3u;
+  if (h.run) {
+    unsigned f = 0u;
+    if (heavy) {
+      const unsigned idx = atomicAdd(hot + pn, 1u);
+      if (idx < cap) { hot[8 + pn * (unsigned)P.hot_cap + idx] = h.tile; f = idx + 1u; }
+    }
+    hot[8 + 3u * (unsigned)P.hot_cap + pn * (unsigned)P.hot_tiles + h.tile] = f;
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0) {                // one CTA per launch: stamp the list being written, clear the
+    hot[3 + pn] = hot_stamp(P, strips, nseg);              // one the NEXT launch will write
+    hot[pz] = 0u;
+  }
+}
+
 // UNR > 1 unrolls the march loop so that the row-to-row hand-over of the carried state (q1 <- qN, qn0 <- qn1 <- qn2,
 // c1 <- cN) becomes register renaming instead of moves: statically (scripts/sass_mix.py) 1476 -> 1430 instructions per
 // march step for the headline Euler kernel at UNR = 2 with no spills (UNR = 3 spills); unmeasured on the GPU so far.
@@ -102,11 +286,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
   constexpr int PF = (SPEC >> 1) & 3;                      // q-row prefetch: 0 none, 1 L1 hint, 2 L2 hint, 3 cp.async ring
   constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
   constexpr int RD = QD > 0 ? QD : 2;                      // stages of the row ring
-#ifdef CLAW_STRICT
-  constexpr bool QUIET = false;
-#else
-  constexpr bool QUIET = (QD > 0) && SP && (PF == 3) && (NC > 0);
-#endif
+  constexpr bool QUIET = UnsplitQuiet<RP, SPEC, QD>::value;
   static_assert((RD & (RD - 1)) == 0, "ring depth must be a power of two");
   using S = Smem2ws<RP, NW, RD>;
   constexpr int TX = 28;                                   // owned columns per warp
@@ -125,13 +305,21 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
   double* const spf = smem + S::OFF_PF * NT + t;
   double* const sred = smem + S::PER_THREAD * NT;
 
+  CLAW_RESOLVE_STEP2(P, qin, qout, dtdx, dtdy);
+  [[maybe_unused]] HotTile hot;
+  int bx = (int)blockIdx.x, by = (int)blockIdx.y;
+  [[maybe_unused]] int nfull = 0;                          // march steps of this tile that took the full path
+  if constexpr (QUIET && NW == 1) {
+    hot = hot_begin(P);
+    if (!hot.run) { hot_end(P, hot, false); return; }
+    bx = hot.bx; by = hot.by;
+  }
   const int nx = P.mx + 4;
-  const int I = (blockIdx.x * NW + (t >> 5)) * TX + lane;  // my column (array coords)
+  const int I = (bx * NW + (t >> 5)) * TX + lane;          // my column (array coords)
   const int Ic = I < nx ? I : nx - 1;                      // clamped for loads
-  const int Jb = P.j0 + blockIdx.y * P.seg_rows;           // first output row
+  const int Jb = P.j0 + by * P.seg_rows;                   // first output row
   const int Je = min(Jb + P.seg_rows, P.j1);               // one past the last output row
 
-  CLAW_RESOLVE_STEP2(P, qin, qout, dtdx, dtdy);
   const double hdx = 0.5 * dtdx, hdy = 0.5 * dtdy;
   [[maybe_unused]] const double kxy = hdx * dtdy;
   const bool second = SP ? true : (P.order != 1);
@@ -163,18 +351,23 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
       if (r <= Je + 1) {
 #pragma unroll
         for (int m = 0; m < M; ++m)
-          cp_async8(spf + ((r & (RD - 1)) * M + m) * NT, qcol + m * P.plane + (long long)r * P.pitch);
+          cp_async8(spf + (m * RD + (r & (RD - 1))) * NT, qcol + m * P.plane + (long long)r * P.pitch);
       }
       cp_async_commit();
     }
   }
-  // running ring positions (in doubles, per-thread stride NT): the slot written at the first step (row Jb+RD-2) and the
-  // slot read at the first step (row Jb-1); running global pointers of the row to fetch and of the row to store
-  [[maybe_unused]] int wslot = ((Jb + RD - 2) & (RD - 1)) * M * NT, rslot = ((Jb - 1) & (RD - 1)) * M * NT;
+  // running ring positions (slot offsets in doubles, component-major ring: see ring_t above): the slot written at the
+  // first step (row Jb+RD-2) and the slot read at the first step (row Jb-1); running global pointer of the row to fetch
+  [[maybe_unused]] int wslot = ((Jb + RD - 2) & (RD - 1)) * NT, rslot = ((Jb - 1) & (RD - 1)) * NT;
   [[maybe_unused]] const double* gfetch = qcol + (long long)(Jb + RD - 2) * P.pitch;
   // uniform-region fast path: were the y-interfaces J+1 and J zero on all lanes?  was the last step a quiet one?  has the
   // CFL speed of the current run of identical rows been taken for the x- / the y-interface?
-  [[maybe_unused]] bool yq1 = false, yq2 = false, prev_quiet = false, qcfl_x = false, qcfl_y = false;
+  // A march segment starts three rows below its first output row.  The y-interfaces Jb-2 and Jb-3 that the vote of the
+  // first two steps would have to know about only reach cells below Jb, which this segment does not store: they count as
+  // quiet, so that a segment inside a uniform region does not pay two full march steps before it may go quiet (the
+  // interfaces from Jb-1 on, which do reach stored cells, are classified from the data as everywhere else).
+  [[maybe_unused]] const bool wq = (P.tune & 1) == 0;
+  [[maybe_unused]] bool yq1 = wq, yq2 = wq, prev_quiet = false, qcfl_x = false, qcfl_y = false;
 
   // warm-up rows: see sweep2_unsplit (the specialised kernel runs the full body from the first step)
   // step Js of the ring: queue row Js+RD+1 into the slot row Js+1 was read from, wait for row Js+2, read it
@@ -182,15 +375,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
     if (Js + RD + 1 <= Je + 1) {
       const double* g = gfetch;
 #pragma unroll
-      for (int m = 0; m < M; ++m) { cp_async8(spf + wslot + m * NT, g); g += P.plane; }
+      for (int m = 0; m < M; ++m) { cp_async8(spf + wslot + m * RD * NT, g); g += P.plane; }
     }
     cp_async_commit();
     gfetch += P.pitch;
-    wslot = (wslot == (RD - 1) * M * NT) ? 0 : wslot + M * NT;
+    wslot = (wslot + NT) & (RD * NT - 1);
     cp_async_wait_keep<RD - 1>();
 #pragma unroll
-    for (int m = 0; m < M; ++m) q[m] = spf[rslot + m * NT];
-    rslot = (rslot == (RD - 1) * M * NT) ? 0 : rslot + M * NT;
+    for (int m = 0; m < M; ++m) q[m] = spf[rslot + m * RD * NT];
+    rslot = (rslot + NT) & (RD * NT - 1);
   };
   double qN[M];
   [[maybe_unused]] bool have_row = false;                  // qN already holds row J+2 (handed over by the tight quiet loop)
@@ -246,36 +439,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
         // the step is "fetch, compare with q1, vote, store q1" -- a tight loop of its own, without the rotation of the
         // carried state and without the bookkeeping of the general step.
         if (nquiet >= 2 && qcfl_x && qcfl_y && J >= Jb) {
-          double* orow = qout + (long long)(J + 1) * P.pitch + I;
 #pragma unroll
           for (int m = 0; m < M; ++m) { pin(qn0[m]); pin(qn1[m]); pin(q1[m]); }
-          while (J + 1 < Je) {
-            double qT[M];
-            ring_fetch(J + 1, qT);
-            // (qn1 and qn0 carry the bits of q1 here; comparing with the one and storing the other keeps both alive in
-            // this loop, so that the compiler does not sink their last assignments into every exit of it)
-            unsigned long long d = 0ull;
-#pragma unroll
-            for (int m = 0; m < M; ++m) d |= diff_bits(qn1[m], qT[m]);
-            if (!warp_all(d == 0ull)) {                    // step J+1 goes through the general classification
-#pragma unroll
-              for (int m = 0; m < M; ++m) qN[m] = qT[m];
-              have_row = true;
-              break;
-            }
-            ++J;
-            if (store_col) {
-              double* o = orow;
-#pragma unroll
-              for (int m = 0; m < M; ++m) { *o = qn0[m]; o += P.plane; }
-            }
-            orow += P.pitch;
-          }
+          // (qn1 and qn0 carry the bits of q1 here; comparing with the one and storing the other keeps both alive in
+          // the loop, so that the compiler does not sink their last assignments into every exit of it)
+          have_row = quiet_run<M, RD, NT>(J, Je, qn1, qn0, qN, spf, wslot, rslot, gfetch, P.plane, P.pitch,
+                                          qout + (long long)(J + 1) * P.pitch + I, store_col);
         }
         continue;
       }
       qcfl_x = false; qcfl_y = false;
       nquiet = 0;
+      ++nfull;
       if (prev_quiet) {
         // the pending y-interface (J+1) was skipped: it is a zero interface -- zero waves, fluctuations and limiter dot
         // products, finite stand-in Roe data (they only ever multiply those zeros); the carried results of interface J
@@ -506,6 +681,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
     for (int k = 0; k < NC; ++k) c1[k] = cN[k];
   }
   block_max_cfl<NT>(cfl, P.cfl_bits, sred);
+  if constexpr (QUIET && NW == 1) hot_end(P, hot, 4 * nfull >= P.seg_rows);
 }
 
 // =====================================================================================
@@ -525,11 +701,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE, NT = NW * 32;
   constexpr int NC = RP::NCELL, NC1 = NC > 0 ? NC : 1;
   constexpr int RD = QD > 0 ? QD : 2;
-#ifdef CLAW_STRICT
-  constexpr bool QUIET = false;
-#else
-  constexpr bool QUIET = (QD > 0) && (LIM > 0) && (PF != 0) && (NC == 0);
-#endif
+  constexpr bool QUIET = SplitQuiet<RP, PF, LIM, QD>::value;
   static_assert((RD & (RD - 1)) == 0, "ring depth must be a power of two");
   using S = Smem2ws<RP, NW, RD>;
   constexpr int TX = 28;
@@ -540,10 +712,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
   double* const spf = smem + S::OFF_PF * NT + t;
   double* const sred = smem + S::PER_THREAD * NT;
 
-  const int nx = P.mx + 4;
-  const int I = (blockIdx.x * NW + (t >> 5)) * TX + lane;
-  const int Ic = I < nx ? I : nx - 1;
   CLAW_RESOLVE_STEP2(P, qin, qout, dtdx, dtdy);
+  [[maybe_unused]] HotTile hot;
+  int bx = (int)blockIdx.x, by = (int)blockIdx.y;
+  [[maybe_unused]] int nfull = 0;
+  if constexpr (QUIET && NW == 1) {
+    hot = hot_begin(P);
+    if (!hot.run) { hot_end(P, hot, false); return; }
+    bx = hot.bx; by = hot.by;
+  }
+  const int nx = P.mx + 4;
+  const int I = (bx * NW + (t >> 5)) * TX + lane;
+  const int Ic = I < nx ? I : nx - 1;
   const bool second = LIM ? true : (P.order != 1);
   const bool limit = LIM ? true : (second && (P.limit != 0));
   const bool do_x = P.do_x != 0, do_y = P.do_y != 0;
@@ -553,7 +733,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
   const bool interior_col = (I >= 2) && (I <= P.mx + 1);
   const bool x_ok = (lane >= 2) && (lane <= 29);            // my x-updated value is complete
   const bool col_ok = (I <= P.mx + 3) && (!do_x || !interior_col || x_ok);
-  const int Jb = P.j0 + blockIdx.y * P.seg_rows;
+  const int Jb = P.j0 + by * P.seg_rows;
   const int Je = min(Jb + P.seg_rows, P.j1);
 
   // x-sweep of one row (step2ds.f90:96-160 with ids = 1): q -> x-updated value of my cell
@@ -642,9 +822,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
 #pragma unroll
   for (int k = 0; k < NC1; ++k) cx1[k] = 0.0;
   // QD-stage ring (QUIET builds): rows Jb-2 .. Jb+RD-4 are in flight when the loop starts; running slot offsets
-  [[maybe_unused]] int wslot = ((Jb + RD - 3) & (RD - 1)) * M * NT, rslot = ((Jb - 2) & (RD - 1)) * M * NT;
+  [[maybe_unused]] int wslot = ((Jb + RD - 3) & (RD - 1)) * NT, rslot = ((Jb - 2) & (RD - 1)) * NT;
   [[maybe_unused]] const double* gfetch = qcol + (long long)(Jb + RD - 3) * P.pitch;
-  [[maybe_unused]] bool yq1 = false, yq2 = false, prev_quiet = false, qcfl_x = false, qcfl_y = false;
+  // warm-up steps of a segment (J < Jb): interfaces that only reach cells below Jb count as quiet (see sweep2_unsplit_ws)
+  [[maybe_unused]] const bool wq = (P.tune & 1) == 0;
+  [[maybe_unused]] bool yq1 = wq, yq2 = wq, prev_quiet = false, qcfl_x = false, qcfl_y = false;
   if constexpr (QD > 0) {
 #pragma unroll
     for (int k = 0; k < RD - 1; ++k) {
@@ -652,7 +834,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
       if (r <= Je + 1) {
 #pragma unroll
         for (int m = 0; m < M; ++m)
-          cp_async8(spf + ((r & (RD - 1)) * M + m) * NT, qcol + m * P.plane + (long long)r * P.pitch);
+          cp_async8(spf + (m * RD + (r & (RD - 1))) * NT, qcol + m * P.plane + (long long)r * P.pitch);
       }
       cp_async_commit();
     }
@@ -663,15 +845,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
     if (Js + RD + 1 <= Je + 1) {
       const double* g = gfetch;
 #pragma unroll
-      for (int m = 0; m < M; ++m) { cp_async8(spf + wslot + m * NT, g); g += P.plane; }
+      for (int m = 0; m < M; ++m) { cp_async8(spf + wslot + m * RD * NT, g); g += P.plane; }
     }
     cp_async_commit();
     gfetch += P.pitch;
-    wslot = (wslot == (RD - 1) * M * NT) ? 0 : wslot + M * NT;
+    wslot = (wslot + NT) & (RD * NT - 1);
     cp_async_wait_keep<RD - 1>();
 #pragma unroll
-    for (int m = 0; m < M; ++m) q[m] = spf[rslot + m * NT];
-    rslot = (rslot == (RD - 1) * M * NT) ? 0 : rslot + M * NT;
+    for (int m = 0; m < M; ++m) q[m] = spf[rslot + m * RD * NT];
+    rslot = (rslot + NT) & (RD * NT - 1);
   };
   double qx2[M];
   [[maybe_unused]] bool have_row = false;                  // qx2 already holds row J+2 (handed over by the tight quiet loop)
@@ -695,9 +877,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
         yz = yz && same_bits(qx1[m], qx2[m]);
       }
       const bool xq0 = warp_all(xz);                       // the x-sweep leaves row J+2 as it is in all 32 columns
+      if (wq && J == Jb - 4) {
+        // first warm-up step: row Jb-2 is only x-swept (no y-interface yet); a uniform row stays as it is
+        if (do_x && xq0) {
+          if (!qcfl_x) { if (x_cfl_col) cfl = fmax2(cfl, dtdx * RP::quiet_smax(P.rp, 0, qx2)); qcfl_x = true; }
+#pragma unroll
+          for (int m = 0; m < M; ++m) { qx0[m] = qx1[m]; qx1[m] = qx2[m]; }
+          continue;
+        }
+      }
       const bool yq0 = warp_all(yz) && xq0 && (J >= Jb - 3);   // the x-updated rows J+1 and J+2 carry the same bits
-      const bool quiet = do_x && yq0 && yq1 && yq2 && (J >= Jb - 1);
-      yq2 = yq1; yq1 = yq0;
+      const bool quiet = do_x && yq0 && yq1 && yq2 && (J >= (wq ? Jb - 3 : Jb - 1));
+      if (!wq || J >= Jb - 3) { yq2 = yq1; yq1 = yq0; }
       if (quiet) {
         const bool ry = (J + 2 >= 2) && (J + 2 <= P.my + 2);
         if (!qcfl_x) { if (x_cfl_col) cfl = fmax2(cfl, dtdx * RP::quiet_smax(P.rp, 0, qx2)); qcfl_x = true; }
@@ -714,35 +905,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
         // from the second quiet step of a run on, qx0 carries the bits of qx1 too: while rows keep coming in with those
         // bits (which also means they pass the x-test again) the step is "fetch, compare, vote, store"
         if (nquiet >= 2 && qcfl_x && qcfl_y && J >= Jb) {
-          double* orow = qout + (long long)(J + 1) * P.pitch + I;
-          const bool st = col_ok && interior_col;
 #pragma unroll
           for (int m = 0; m < M; ++m) { pin(qx0[m]); pin(qx1[m]); }
-          while (J + 1 < Je) {
-            double qT[M];
-            ring_fetch(J + 1, qT);
-            unsigned long long d = 0ull;
-#pragma unroll
-            for (int m = 0; m < M; ++m) d |= diff_bits(qx1[m], qT[m]);
-            if (!warp_all(d == 0ull)) {
-#pragma unroll
-              for (int m = 0; m < M; ++m) qx2[m] = qT[m];
-              have_row = true;
-              break;
-            }
-            ++J;
-            if (st) {
-              double* o = orow;
-#pragma unroll
-              for (int m = 0; m < M; ++m) { *o = qx0[m]; o += P.plane; }   // qx0 carries the bits of qx1 here
-            }
-            orow += P.pitch;
-          }
+          have_row = quiet_run<M, RD, NT>(J, Je, qx1, qx0, qx2, spf, wslot, rslot, gfetch, P.plane, P.pitch,
+                                          qout + (long long)(J + 1) * P.pitch + I, col_ok && interior_col);
         }
         continue;
       }
       qcfl_x = false; qcfl_y = false;
       nquiet = 0;
+      ++nfull;
       if (prev_quiet) {                                    // the pending y-interface was skipped: a zero interface
         double roeQ[NR];
         RP::quiet_roe(roeQ);
@@ -841,6 +1013,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_split_ws(const __grid_co
     for (int k = 0; k < NC; ++k) cx1[k] = cx2[k];
   }
   block_max_cfl<NT>(cfl, P.cfl_bits, sred);
+  if constexpr (QUIET && NW == 1) hot_end(P, hot, 4 * nfull >= P.seg_rows);
 }
 
 }  // namespace CLAW_NS

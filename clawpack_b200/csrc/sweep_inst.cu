@@ -12,7 +12,8 @@ namespace CLAW_NS {
 
 template <class KERN>
 static cudaError_t launch_kernel(KERN kern, int NT, int smem, bool x_only, Sweep2Params& P, int seg_hint, int num_sms,
-                                 cudaStream_t st, LaunchInfo* info, int cols_per_cta = 0, int max_seg = 256) {
+                                 cudaStream_t st, LaunchInfo* info, int cols_per_cta = 0, int max_seg = 256,
+                                 bool hot_ok = false) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int occ = 1;
@@ -41,7 +42,22 @@ static cudaError_t launch_kernel(KERN kern, int NT, int smem, bool x_only, Sweep
   }
   if (seg > rows) seg = rows;
   P.seg_rows = seg;
+  static const int tune = getenv("CLAW_TUNE") ? atoi(getenv("CLAW_TUNE")) : 0;    // A/B switches (Sweep2Params::tune)
+  P.tune = tune;
   dim3 grid(strips, (rows + seg - 1) / seg);
+  // tile ordering (sweep2_ws.cuh, HotTiles): extra grid rows in front of the regular grid run last step's heavy tiles
+  // first; worth it only when the launch is several waves of CTAs long
+  P.hot_rows = 0;
+  if (hot_ok && P.hot != nullptr && !(tune & 2) && !x_only) {
+    const long long ntiles = (long long)grid.x * grid.y;
+    int hy = (int)grid.y / 16;
+    if (hy < 1) hy = 1;
+    while (hy > 0 && (long long)hy * grid.x > P.hot_cap) --hy;
+    if (hy > 0 && ntiles <= P.hot_tiles && ntiles >= 4LL * num_sms * occ && grid.x < 65536 && grid.y + hy < 65536) {
+      P.hot_rows = hy;
+      grid.y += hy;
+    }
+  }
   kern<<<grid, NT, smem, st>>>(P);
   if (info) { info->grid_x = grid.x; info->grid_y = grid.y; info->block = NT; info->smem_bytes = smem; info->ctas_per_sm = occ; }
   return cudaGetLastError();
@@ -63,7 +79,7 @@ static cudaError_t launch_ws(Sweep2Params& P, int seg_hint, int num_sms, cudaStr
   // the slowest CTAs short enough for the tail of the launch (measured at 8192^2, profiles/r02_i_segrows.jsonl: 1.38 ms
   // with 256-row segments, 1.20 / 1.16 / 1.29 ms with 128 / 64 / 32)
   return launch_kernel(sweep2_unsplit_ws<RP, NW, MINB, SPEC, UNR, QD>, NW * 32, (int)S::BYTES, false, P, seg_hint, num_sms,
-                       st, info, NW * 28, QD > 0 ? 64 : 256);
+                       st, info, NW * 28, QD > 0 ? 64 : 256, UnsplitQuiet<RP, SPEC, QD>::value && NW == 1);
 }
 
 // warp-synchronous dimension-split kernel (sweep2_ws.cuh)
@@ -71,7 +87,7 @@ template <class RP, int NW, int MINB, int PF = 1, int UNR = 1, int LIM = 0, int 
 static cudaError_t launch_split_ws(Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
   using S = Smem2ws<RP, NW, (QD > 0 ? QD : 2)>;
   return launch_kernel(sweep2_split_ws<RP, NW, MINB, PF, UNR, LIM, QD>, NW * 32, (int)S::BYTES, !P.do_y, P, seg_hint, num_sms,
-                       st, info, NW * 28, QD > 0 ? 64 : 256);
+                       st, info, NW * 28, QD > 0 ? 32 : 256, SplitQuiet<RP, PF, LIM, QD>::value && NW == 1 && P.do_x && P.do_y);
 }
 
 // aux-reading solvers (sweep2_aux.cuh): warp-synchronous, NW strips per CTA
@@ -107,7 +123,7 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
         if (variant == 2 && split_method<2>(P, 4))             // without the uniform-region fast path (A/B)
           return launch_split_ws<RpAcoustics2D, 1, 16, 1, 1, 4>(P, seg_hint, num_sms, st, info);
         if (variant != 1 && split_method<2>(P, 4) && P.do_x && P.do_y)   // BASELINE config 1: MC limiter as a template argument
-          return launch_split_ws<RpAcoustics2D, 1, 16, 1, 1, 4, 8>(P, seg_hint, num_sms, st, info);
+          return launch_split_ws<RpAcoustics2D, 1, 16, 1, 1, 4, 4>(P, seg_hint, num_sms, st, info);
         if (variant != 1 && split_method<2>(P, 4))
           return launch_split_ws<RpAcoustics2D, 1, 16, 1, 1, 4>(P, seg_hint, num_sms, st, info);
         return launch_split_ws<RpAcoustics2D, 1, 16>(P, seg_hint, num_sms, st, info);
@@ -142,8 +158,13 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
         // slower in every combination (11.4 / 11.3 / 9.65 ms) and is gone.
         if (variant == 2 && split_method<3>(P, 4))             // without the uniform-region fast path (A/B)
           return launch_split_ws<RpShallowRoeEfix2D, 1, 16, 1, 1, 4>(P, seg_hint, num_sms, st, info);
+        // Ring depth: about 50 rows in flight per SM is the optimum of the uniform-region path (16384^2, uniform data,
+        // profiles/r02_s: 16 warps x 8 stages 3.01 ms, 16 x 4 2.19 ms, 16 x 2 2.72 ms, 12 x 4 2.37 ms, 8 x 8 2.14 ms,
+        // 8 x 4 2.37 ms); 16 warps per SM keep the FP64-bound dense path fastest (12.2 ms against 14.1 at 8, 13.6 at 12).
+        if (variant == 82 && split_method<3>(P, 4) && P.do_x && P.do_y)  // A/B: 8 warps per SM, 8-stage ring
+          return launch_split_ws<RpShallowRoeEfix2D, 1, 8, 1, 1, 4, 8>(P, seg_hint, num_sms, st, info);
         if (variant != 1 && split_method<3>(P, 4) && P.do_x && P.do_y)   // fused step: with the uniform-region fast path
-          return launch_split_ws<RpShallowRoeEfix2D, 1, 16, 1, 1, 4, 8>(P, seg_hint, num_sms, st, info);
+          return launch_split_ws<RpShallowRoeEfix2D, 1, 16, 1, 1, 4, 4>(P, seg_hint, num_sms, st, info);
         if (variant != 1 && split_method<3>(P, 4))
           return launch_split_ws<RpShallowRoeEfix2D, 1, 16, 1, 1, 4>(P, seg_hint, num_sms, st, info);
         return launch_split_ws<RpShallowRoeEfix2D, 1, 16>(P, seg_hint, num_sms, st, info);

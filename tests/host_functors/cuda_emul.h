@@ -99,3 +99,5 @@ inline long long __double_as_longlong(double v) { long long r; std::memcpy(&r, &
 inline unsigned long long atomicMax(unsigned long long* a, unsigned long long v) {
   const unsigned long long old = *a; if (v > old) *a = v; return old;
 }
+inline unsigned atomicAdd(unsigned* a, unsigned v) { const unsigned old = *a; *a = old + v; return old; }
+inline void __threadfence() {}

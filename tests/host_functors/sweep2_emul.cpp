@@ -34,6 +34,13 @@ template <class F> void launch(F kern, int nthreads, bool x_only, Sweep2Params& 
   P.seg_rows = seg;
   emul::Dim3 grid, block;
   grid.x = strips; grid.y = (rows + seg - 1) / seg; block.x = nthreads;
+  P.hot_rows = 0;
+  if (P.hot != nullptr && !x_only) {                    // tile ordering as in launch_kernel(): hot grid rows in front
+    int hy = (int)grid.y / 16;
+    if (hy < 1) hy = 1;
+    while (hy > 0 && (long long)hy * grid.x > P.hot_cap) --hy;
+    if (hy > 0 && (long long)grid.x * grid.y <= P.hot_tiles) { P.hot_rows = hy; grid.y += hy; }
+  }
   const Sweep2Params Pc = P;
   emul::launch(grid, block, [&]() { kern(Pc); });
 }
@@ -106,6 +113,9 @@ int run(int rp_id, int kind, int variant, Sweep2Params& P, int seg) {
   return 5;
 }
 
+std::vector<unsigned> g_hot(8 + 3 * 4096 + 3 * 65536, 0u);
+unsigned g_hot_epoch = 0;      // HotTiles buffer of the 1xx variants
+
 struct Soa {
   int nx, ny, pitch; long long plane;
   std::vector<double> in, out, aux;
@@ -117,6 +127,7 @@ int step(int ids, int meqn, int mwaves, int maux, int mx, int my, const double* 
          const double* cparam, int ncparam, int variant, int seg, double* cfl) {
   Soa s;
   s.nx = mx + 4; s.ny = my + 4; s.pitch = s.nx + 3;                 // an odd pitch: rows are not aligned
+  if (variant >= 100) s.pitch = (s.nx + 15) / 16 * 16;              // the product's pitch
   s.plane = (long long)s.pitch * s.ny;
   s.in.assign((size_t)s.plane * meqn, 0.0);
   s.out.assign((size_t)s.plane * meqn, -7.0e300);                  // stale buffer: only the region read back may be used
@@ -137,6 +148,13 @@ int step(int ids, int meqn, int mwaves, int maux, int mx, int my, const double* 
   P.do_x = (ids != 2); P.do_y = (ids != 1);
   P.aux = maux > 0 ? s.aux.data() : nullptr; P.maux = maux; P.capa = method7[5]; P.fwave = use_fwave;
   for (int k = 0; k < 4; ++k) P.rp.p[k] = (cparam && k < ncparam) ? cparam[k] : 0.0;
+  if (variant >= 100) {
+    // variants 1xx: variant xx with the tile ordering of the uniform-region kernels (HotTiles, sweep2_ws.cuh).  The
+    // buffer lives across calls like the handle's does across steps -- and across test cases with other grids, which
+    // exercises the stale-list checks.
+    P.hot = g_hot.data(); P.hot_cap = 4096; P.hot_tiles = 65536; P.hot_epoch = g_hot_epoch++;
+    variant -= 100;
+  }
   if (int rc = run(rp_id, ids == 0 ? 0 : 1, variant, P, seg)) return rc;
   int i0 = 2, i1 = 2 + mx, j0 = 2, j1 = 2 + my;                    // get_interior / get_region of the plug-in calls
   if (ids == 1) { j0 = 0; j1 = s.ny; }
@@ -155,3 +173,7 @@ extern "C" int emul_step2_host(int meqn, int mwaves, int maux, int mx, int my, c
   return step(ids, meqn, mwaves, maux, mx, my, qold, qnew, aux, dx, dy, dt, method7, mthlim, use_fwave, rp_id, cparam,
               ncparam, variant, seg, cfl);
 }
+
+// header words of the HotTiles buffer (entries of the three lists, their grid stamps) and the launch counter -- the tests
+// check that the tile ordering was really exercised
+extern "C" void emul_hot_header(unsigned* out7) { for (int k = 0; k < 6; ++k) out7[k] = g_hot[k]; out7[6] = g_hot_epoch; }

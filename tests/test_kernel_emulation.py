@@ -155,7 +155,7 @@ class EmulatedFmod2D(object):
 
     def step2ds(self, maxm, num_ghost, mx, my, qold, qnew, aux, dx, dy, dt, method, mthlim, aux1, aux2, aux3, work,
                 ids, use_fwave, rpn2, rpt2):
-        if self.variant in (73, 74):
+        if self.variant in (73, 74, 173, 174):
             # the FUSED dimension-split step of the device-resident path (x-sweep of every row + y-sweep in one march,
             # clawcuda.cu launch_step: kind 1, do_x = do_y = 1) behind the two step2ds calls of the host loop: the first
             # call does the whole step (emulation id 3), the second is a no-op
@@ -182,6 +182,12 @@ CASES_2D = {
     'euler_headline_quiet_ring8': (lambda: S.shock_bubble(mx=120, my=90), 72, 0),
     'euler_headline_quiet_ring8_segments': (lambda: S.shock_bubble(mx=57, my=45), 72, 8),
     'euler_headline_quiet_ring4_short_segments': (lambda: S.shock_bubble(mx=70, my=64), 71, 5),
+    # the same with the tile ordering (variant + 100): heavy tiles reported by one step run first in the next
+    'euler_headline_quiet_ring8_tile_order': (lambda: S.shock_bubble(mx=120, my=90), 172, 8),
+    'euler_headline_quiet_ring4_tile_order_short_segments': (lambda: S.shock_bubble(mx=70, my=64), 171, 5),
+    'shallow_split_quiet_ring8_tile_order': (lambda: dict(S.radial_dam_break(mx=120, my=100), limiters=S.MC), 173, 9),
+    'shallow_split_quiet_ring8_tile_order_long_segments': (lambda: dict(S.radial_dam_break(mx=150, my=140), limiters=S.MC), 173, 0),
+    'acoustics_split_quiet_ring8_tile_order': (lambda: S.acoustics_2d(mx=100, my=90), 173, 24),
     'euler_quadrants_quiet_ring8': (lambda: dict(S.quadrants(mx=64, my=64), dimensional_split=False, transverse_waves=2,
                                                  limiters=S.MC), 72, 16),
     'euler_unsplit_generic_inc_mixed_limiters': (lambda: dict(S.quadrants(mx=40, my=30), dimensional_split=False,
@@ -229,6 +235,13 @@ def test_emulated_sweep2_kernels_bit_exact_vs_oracle(emul2lib, name):
         r.evolve_to_time()
     # (kpp_2D: sin / cos come from the same libm on both sides here, so the bits agree as well in strict mode)
     _check(solver, sol, r, emul2lib.mode)
+    if variant >= 100 and emul2lib.mode == 'fast':
+        # the tile ordering ran: the fronts of these data made some tiles heavy in the last launch, and the list the next
+        # launch will write has been cleared
+        hdr = (ctypes.c_uint * 7)()
+        emul2lib.emul_hot_header(hdr)
+        written = hdr[6] % 3                                 # the last launch (number hdr[6] - 1) wrote this list
+        assert hdr[6] >= 5 and hdr[written] > 0 and hdr[(written + 1) % 3] == 0, list(hdr)
 
 
 # ---- 3-D: sweep3_x and the march kernels (csrc/sweep3.cuh) ---------------------------------------------------------

@@ -37,9 +37,9 @@ def test_headline_euler_kernel_shape(fast_kernels):
     assert _count(c, lambda k: k.startswith('SHFL')) >= 90                       # neighbour exchange by shuffle
     assert _count(c, lambda k: k.startswith('BAR')) <= 2                         # no barrier in the march loop
     # measured build (round 2, with the uniform-region fast path, its tight inner loop for runs of quiet rows and the
-    # 8-stage ring): ~3290 instructions, ~940 of them FP64 arithmetic; the full march step is ~1420 instructions with
-    # ~800 FP64, the quiet step ~160 with 10
-    assert n <= 3500 and 800 <= fp64 <= 1000, (n, fp64)
+    # 8-stage ring, tile ordering, wide tight loop as a local function): ~4500 instructions, ~940 of them FP64 arithmetic; the full march step is ~1420
+    # instructions with ~800 FP64, the quiet step ~160 with 10, a row of the tight loop 75
+    assert n <= 4800 and 800 <= fp64 <= 1000, (n, fp64)
     assert _count(c, lambda k: k.startswith('VOTE')) >= 2                        # the warp votes of the fast path
     assert _count(c, lambda k: k.startswith('MUFU.RCP64H') or k.startswith('MUFU.RSQ64H')) <= 32   # shared reciprocals
 
