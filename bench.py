@@ -321,7 +321,7 @@ def sass_identity(kernel_pattern, obj):
         names = [k for k in ks if kernel_pattern in k]
         if len(names) != 1:
             return None, None
-        text = '\n'.join(ks[names[0]])
+        text = '\n'.join('%x %s' % (a, t) for a, t in ks[names[0]])
         return names[0], hashlib.sha1(text.encode()).hexdigest()
     except Exception:
         return None, None

@@ -65,6 +65,11 @@ def _declare(L):
         'claw_halo_elems_aux': (i, [H, ctypes.POINTER(sz)]),
         'claw_halo_pack_aux': (i, [H, i, vp]),
         'claw_halo_unpack_aux': (i, [H, i, vp]),
+        'claw_halo_exchange': (i, [H, vp, i, i, i, i, i]),
+        'claw_allreduce_cfl': (i, [H, vp]),
+        'claw_nccl_unique_id': (i, [vp]),
+        'claw_nccl_comm_init': (i, [ctypes.POINTER(ctypes.c_void_p), i, i, vp, i]),
+        'claw_nccl_comm_destroy': (i, [vp]),
         'claw_time_sweep': (i, [H, c_double_p, d, i, c_double_p]),
         'claw_launch_count': (i, [H, ctypes.POINTER(ctypes.c_uint64)]),
         'claw_last_launch_info': (i, [H, c_int_p]),

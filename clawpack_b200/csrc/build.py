@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
     for j in jobs:
         if j.wait() != 0:
             raise RuntimeError('nvcc failed')
-    subprocess.check_call(['nvcc', '-ccbin', HOSTCXX] + ARCH + ['-shared', '-o', OUT] + objs + ['-lcudart'], cwd=HERE)
+    subprocess.check_call(['nvcc', '-ccbin', HOSTCXX] + ARCH + ['-shared', '-o', OUT] + objs + ['-lcudart', '-ldl'], cwd=HERE)
     return OUT
 
 

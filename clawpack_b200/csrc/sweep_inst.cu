@@ -31,12 +31,17 @@ static cudaError_t launch_kernel(KERN kern, int NT, int smem, bool x_only, Sweep
   if (seg <= 0) {
     // enough CTAs for >= 6 waves of resident CTAs, but segments not shorter than 32 rows
     // (each segment pays 3-4 warm-up rows) nor longer than 256.  Small grids that cannot even fill the GPU once with
-    // 32-row segments are latency-bound on the march length instead: there the floor is 8 rows.
+    // 32-row segments are latency-bound on the march length instead: there the segments are as short as one wave of CTAs
+    // allows (the redundant warm-up rows cost nothing on an otherwise idle GPU), down to 2 rows.
     const long long want = 6LL * num_sms * occ;
     long long nseg = (want + strips - 1) / strips;
     if (nseg < 1) nseg = 1;
     seg = (int)((rows + nseg - 1) / nseg);
-    const int min_seg = ((long long)strips * ((rows + 31) / 32) >= (long long)num_sms * occ) ? 32 : 8;
+    int min_seg = 32;
+    if ((long long)strips * ((rows + 31) / 32) < (long long)num_sms * occ) {
+      const long long one_wave = ((long long)rows * strips + (long long)num_sms * occ - 1) / ((long long)num_sms * occ);
+      min_seg = one_wave < 2 ? 2 : (int)one_wave;
+    }
     if (seg < min_seg) seg = min_seg;
     if (seg > max_seg) seg = max_seg;
   }

@@ -6,15 +6,47 @@ send/recv with each slab neighbour -> two unpack kernels -> ghost fill + sweep -
 CFL slot of the control block -> the control kernel, which decides accept/reject identically on every rank.  The pack /
 unpack kernels find the current q buffer through the control block, so the exchange of attempt n+1 is queued before the
 outcome of attempt n is known; after a rejected attempt the same rows are simply exchanged again.  Every rank queues
-the same sequence of collectives for every attempt (no rank-local shortcut decides whether to exchange)."""
+the same sequence of collectives for every attempt (no rank-local shortcut decides whether to exchange).
+
+Two transports.  Default: the process group of ``torch.distributed`` (pack / unpack kernels of libclawcuda around
+``batch_isend_irecv``; ``all_reduce`` on the CFL slot).  ``CLAW_HALO=cabi`` (or ``DeviceHalo(..., transport='cabi')``): the
+whole exchange behind the C ABI -- ``claw_halo_exchange`` / ``claw_allreduce_cfl`` (include/clawcuda.h) on a communicator
+of the library's own (``claw_nccl_comm_init``; the 128-byte id travels through the torch process group once) -- which is
+what a non-Python host (an MPI / C driver) would call; one ctypes call per exchange instead of a dozen Python-level ops."""
 import ctypes
+import os
 
 from .. import _lib
 from . import util
 
 
+_cabi_comm = {}          # (device index) -> ncclComm_t of libclawcuda, shared by all DeviceHalo objects of the process
+
+
+def _cabi_communicator(dev, nranks, rank):
+    """The library-side NCCL communicator of this process (created once: rank 0 draws the id, the torch process group
+    broadcasts it)."""
+    key = dev.device.index
+    if key in _cabi_comm:
+        return _cabi_comm[key]
+    import torch
+    dist = util._dist()
+    L = dev.L
+    ident = (ctypes.c_ubyte * 128)()
+    if rank == 0:
+        _lib.check(L.claw_nccl_unique_id(ctypes.cast(ident, ctypes.c_void_p)))
+    t = torch.tensor(list(ident), dtype=torch.uint8, device=dev.device if dist.get_backend() == 'nccl' else 'cpu')
+    dist.broadcast(t, src=0)
+    ident = (ctypes.c_ubyte * 128)(*[int(v) for v in t.cpu().tolist()])
+    comm = ctypes.c_void_p()
+    _lib.check(L.claw_nccl_comm_init(ctypes.byref(comm), int(nranks), int(rank), ctypes.cast(ident, ctypes.c_void_p),
+                                     int(dev.device.index)))
+    _cabi_comm[key] = comm
+    return comm
+
+
 class DeviceHalo(object):
-    def __init__(self, dev, patch, periodic):
+    def __init__(self, dev, patch, periodic, transport=None):
         import torch
         self.torch = torch
         self.dev = dev
@@ -22,6 +54,14 @@ class DeviceHalo(object):
         nranks, r = patch.num_ranks, patch.rank
         per_lo, per_up = periodic if isinstance(periodic, tuple) else (periodic, periodic)
         self.nb = util.slab_neighbours(nranks, r, per_lo, per_up)
+        self.transport = transport or os.environ.get('CLAW_HALO', 'torch')
+        if self.transport not in ('torch', 'cabi'):
+            raise ValueError("halo transport must be 'torch' or 'cabi'")
+        self.comm = _cabi_communicator(dev, nranks, r) if self.transport == 'cabi' else None
+        self.nbi = [-1 if self.nb[k] is None else int(self.nb[k])
+                    for k in ('send_up_to', 'recv_lo_from', 'send_lo_to', 'recv_up_from')]
+        if self.comm is not None:
+            return
         n = ctypes.c_size_t()
         _lib.check(dev.L.claw_halo_elems(dev.handle, ctypes.byref(n)), dev.handle)
         mk = lambda: torch.empty(n.value, dtype=torch.float64, device=dev.device)   # noqa: E731
@@ -36,12 +76,18 @@ class DeviceHalo(object):
         _lib.check(dev.L.claw_halo_elems_aux(dev.handle, ctypes.byref(n)), dev.handle)
         if n.value == 0:
             return
+        if self.comm is not None:
+            _lib.check(dev.L.claw_halo_exchange(dev.handle, self.comm, *self.nbi, 1), dev.handle)
+            return
         torch = self.torch
         bufs = [torch.empty(n.value, dtype=torch.float64, device=dev.device) for _ in range(4)]
         self._exchange(dev, dev.L.claw_halo_pack_aux, dev.L.claw_halo_unpack_aux, *bufs)
 
     def exchange(self, dev):
         """Ghost rows / planes of the current q buffer from the slab neighbours (queued, not waited for)."""
+        if self.comm is not None:
+            _lib.check(dev.L.claw_halo_exchange(dev.handle, self.comm, *self.nbi, 0), dev.handle)
+            return
         self._exchange(dev, dev.L.claw_halo_pack, dev.L.claw_halo_unpack, self.send_lo, self.send_up,
                        self.recv_lo, self.recv_up)
 
@@ -70,4 +116,7 @@ class DeviceHalo(object):
 
     def all_reduce_cfl(self, dev):
         """max over ranks of the CFL slot written by the sweep kernels, in place on the device (petclaw/cfl.py:36)."""
+        if self.comm is not None:
+            _lib.check(dev.L.claw_allreduce_cfl(dev.handle, self.comm), dev.handle)
+            return
         self.dist.all_reduce(dev.cfl_tensor, op=self.dist.ReduceOp.MAX)

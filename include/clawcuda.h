@@ -215,6 +215,24 @@ int claw_halo_elems_aux(const claw_solver* h, size_t* elems);
 int claw_halo_pack_aux(claw_solver* h, int side, double* d_buf);
 int claw_halo_unpack_aux(claw_solver* h, int side, const double* d_buf);
 
+/* ---- ghost exchange and CFL reduction over NCCL, for hosts that are not Python (an MPI / C driver) ----------------
+   What PetClaw does with DMDA globalToLocal (petclaw/state.py:223-231) and an MPI max-reduce (petclaw/cfl.py:22,36),
+   queued on the handle's stream: pack kernels -> one grouped ncclSend/ncclRecv with each slab neighbour -> unpack
+   kernels; ncclAllReduce(max) in place on the 8-byte CFL slot.  `nccl_comm` is the caller's ncclComm_t (one rank per
+   GPU).  NCCL is resolved at run time (dlopen of libnccl.so.2: the library itself has no link dependency on it).
+   Neighbours as ranks of that communicator, -1 = none: channel A carries my upper interior rows / planes to the upper
+   neighbour's lower ghosts, channel B my lower interior rows / planes to the lower neighbour's upper ghosts (a periodic
+   slab dimension wraps by naming the rank at the other end; petclaw/util.py: slab_neighbours).  `aux` != 0 exchanges the
+   static aux array instead of q (once, after claw_put_aux). */
+int claw_halo_exchange(claw_solver* h, void* nccl_comm, int send_up_to, int recv_lo_from, int send_lo_to,
+                       int recv_up_from, int aux);
+int claw_allreduce_cfl(claw_solver* h, void* nccl_comm);
+/* building a communicator without an MPI launcher: rank 0 creates the 128-byte id, the host broadcasts it by its own
+   means, every rank calls claw_nccl_comm_init (ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy) */
+int claw_nccl_unique_id(void* id128);
+int claw_nccl_comm_init(void** nccl_comm, int nranks, int rank, const void* id128, int device);
+int claw_nccl_comm_destroy(void* nccl_comm);
+
 /* time `reps` back-to-back launches of the sweep kernel alone (no ghost fill, no swap) with CUDA
    events on the handle's stream; returns the average duration in milliseconds (bench.py roofline) */
 int claw_time_sweep(claw_solver* h, const double* delta, double dt, int reps, double* avg_ms);

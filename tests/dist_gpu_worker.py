@@ -35,7 +35,10 @@ def main():
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     rank, world = dist.get_rank(), dist.get_world_size()
     ok = True
-    for case in sorted(CASES):
+    # second pass: the same cases with the exchange behind the C ABI (claw_halo_exchange / claw_allreduce_cfl on the
+    # library's own NCCL communicator) -- the path a non-Python host would use
+    for transport, case in [('torch', c) for c in sorted(CASES)] + [('cabi', c) for c in sorted(CASES)]:
+        os.environ['CLAW_HALO'] = transport
         sc = CASES[case]()
         claw = petclaw.make_claw_distributed(sc, kernel_language='CUDA', cuda_precision='strict')
         claw.run()
@@ -45,8 +48,8 @@ def main():
             r = ref_solver(sc)
             r.run(sc['tfinal'], sc['num_output_times'])
             same_q, same_log = np.array_equal(q, r.q), (log == r.step_log)
-            print('case %s world %d: q bit-identical to serial oracle: %s, step log identical: %s (%d steps)'
-                  % (case, world, same_q, same_log, len(log)), flush=True)
+            print('case %s (%s) world %d: q bit-identical to serial oracle: %s, step log identical: %s (%d steps)'
+                  % (case, transport, world, same_q, same_log, len(log)), flush=True)
             ok = ok and same_q and same_log
         claw.solver.teardown()
         dist.barrier()
