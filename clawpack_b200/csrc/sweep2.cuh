@@ -86,7 +86,8 @@ struct Sweep2Params {
   double* qbuf[3];          // the two ping-pong q buffers (+ unused third): qin = qbuf[cur], qout = qbuf[cur ^ 1]
   double delta[2];          // dx, dy: dtdx = ctl->dt / dx as step2.f90:77-78 computes it
   int tune;                 // A/B switches of the launch code (env CLAW_TUNE; 0 = defaults): bit 0 = warm-up rows of a
-                            // march segment never take the uniform-region fast path; bit 1 = no tile ordering
+                            // march segment never take the uniform-region fast path; bit 1 = no tile ordering;
+                            // bit 5 = tile ordering on launches of any length
   // tile ordering of the kernels with the uniform-region fast path (sweep2_ws.cuh, HotTiles): device buffer, capacity of
   // one tile list, capacity of one flag array, grid rows of "hot" CTAs in front of the regular ones (0: off)
   unsigned* hot;

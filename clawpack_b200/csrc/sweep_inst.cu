@@ -58,7 +58,10 @@ static cudaError_t launch_kernel(KERN kern, int NT, int smem, bool x_only, Sweep
     int hy = (int)grid.y / 16;
     if (hy < 1) hy = 1;
     while (hy > 0 && (long long)hy * grid.x > P.hot_cap) --hy;
-    if (hy > 0 && ntiles <= P.hot_tiles && ntiles >= 4LL * num_sms * occ && grid.x < 65536 && grid.y + hy < 65536) {
+    // (CLAW_TUNE bit 5: also on launches shorter than four waves -- lets the parity tests exercise the ordering on grids
+    // the oracle finishes quickly)
+    if (hy > 0 && ntiles <= P.hot_tiles && (ntiles >= 4LL * num_sms * occ || (tune & 32)) && grid.x < 65536 &&
+        grid.y + hy < 65536) {
       P.hot_rows = hy;
       grid.y += hy;
     }

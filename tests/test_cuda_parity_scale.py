@@ -112,3 +112,22 @@ def test_c1_acoustics_200_through_graph_batches():
     assert claw.solution.t == r.t
     assert np.array_equal(claw.solution.state.q, r.q)
     assert claw.solver.status['numsteps'] == sum(1 for s in r.step_log if s[2])
+
+
+def test_tile_ordering_forced_on_mid_size_grids():
+    """The tile ordering of the uniform-region kernels (sweep2_ws.cuh, HotTiles) only switches on for launches of four
+    waves of CTAs or more (8192^2-class grids).  CLAW_TUNE=32 forces it on any launch, so that 100-step runs against the
+    oracle exercise it with the lists of every step feeding the next: Euler 1024 x 768 (unsplit) and shallow water 768^2
+    (dimension-split), fast mode, the tolerance of the north star.  The switch is read once per process: subprocess."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from test_cuda_parity_scale import _check, S\n"
+            "_check(S.shock_bubble(mx=1024, my=768), 101, 1e-10, strict_too=False)\n"
+            "_check(S.radial_dam_break(mx=768, my=768), 101, 1e-10, strict_too=False)\n"
+            "print('tile ordering parity ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                     os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CLAW_TUNE='32')
+    p = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=900)
+    assert p.returncode == 0 and 'tile ordering parity ok' in p.stdout, p.stdout[-3000:]
