@@ -512,6 +512,12 @@ def run_config(ctx, args, config, n, steps, warmup, primary):
                        'stepping': 'evolve_to_time(solution, tend): attempts queued in CUDA-graph batches'
                        if config == 'c1' else 'evolve_to_time(solution) per step, queued without a CFL read-back'},
                'roofline': roofline, 'clocks': clocks, 'gpu_launches': launches, 'setup_s': round(time.time() - t_setup, 1)}
+        if ctx.world > 1 and dev.halo is not None:
+            out['run']['halo_transport'] = {
+                'peer': 'peer memory over NVLink (CUDA IPC): ghost rows written into the neighbour\'s buffers after the '
+                        'sweep, CFL max through mailboxes inside the control kernel; no collective per step',
+                'torch': 'NCCL send/recv + all-reduce through torch.distributed',
+                'cabi': 'NCCL send/recv + all-reduce behind the C ABI (claw_halo_exchange / claw_allreduce_cfl)'}[dev.halo.transport]
     solver.teardown()
     del claw, solver, solution, dev
     torch.cuda.empty_cache()

@@ -70,6 +70,12 @@ def _declare(L):
         'claw_nccl_unique_id': (i, [vp]),
         'claw_nccl_comm_init': (i, [ctypes.POINTER(ctypes.c_void_p), i, i, vp, i]),
         'claw_nccl_comm_destroy': (i, [vp]),
+        'claw_cfl_read': (i, [H, c_double_p]),
+        'claw_own_buffers': (i, [H]),
+        'claw_peer_export': (i, [H, vp]),
+        'claw_peer_connect': (i, [H, i, i, vp, i, i]),
+        'claw_peer_sync': (i, [H, i]),
+        'claw_peer_allreduce_cfl': (i, [H, c_double_p]),
         'claw_time_sweep': (i, [H, c_double_p, d, i, c_double_p]),
         'claw_launch_count': (i, [H, ctypes.POINTER(ctypes.c_uint64)]),
         'claw_last_launch_info': (i, [H, c_int_p]),

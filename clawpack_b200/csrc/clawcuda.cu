@@ -73,6 +73,22 @@ struct claw_solver {
   // send / receive buffers of claw_halo_exchange (send up, receive lower, send lower, receive upper), q and aux
   double* hx[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t hx_elems = 0;
+  // peer-memory transport (claw_peer_*): the slab neighbours' q / aux buffers and every rank's mailbox, mapped into
+  // this process through CUDA IPC; rows / planes next to a rank face are written straight into the neighbour's ghost
+  // cells over NVLink, the CFL numbers are exchanged through the mailboxes
+  struct Peer {
+    bool active = false;
+    int nranks = 1, rank = 0;
+    int up = -1, lo = -1;                      // ranks whose LOWER / UPPER ghost cells I fill (channels A / B)
+    double* up_q[2] = {nullptr, nullptr};      // the upper neighbour's two q buffers
+    double* lo_q[2] = {nullptr, nullptr};
+    double* up_aux = nullptr; double* lo_aux = nullptr;
+    long long up_plane = 0, lo_plane = 0;      // their plane strides (slabs may differ in height)
+    int lo_nlast = 0;                          // interior cells of the lower neighbour along the slab dimension
+    unsigned long long* mail = nullptr;        // my mailbox (device memory owned by the handle)
+    unsigned long long* peer_mail[64] = {};    // every rank's mailbox ([rank] = mine)
+    void* opened[64][4] = {};                  // base pointers returned by cudaIpcOpenMemHandle (q0, q1, aux, mailbox)
+  } peer;
   double bc_state[3][2][8] = {};
   double* h_cfl = nullptr;   // pinned
   cudaEvent_t ev_cfl = nullptr;
@@ -359,7 +375,7 @@ __global__ void ctl_begin_kernel(StepCtl* ctl, CtlBeginArgs a) {
   *ctl = c;
 }
 
-__global__ void ctl_end_kernel(StepCtl* ctl, double* log) {
+__device__ void ctl_end_body(StepCtl* ctl, double* log) {
   StepCtl c = *ctl;
   if (c.done) return;
   const double cfl = __longlong_as_double((long long)c.cfl_bits);
@@ -390,6 +406,98 @@ __global__ void ctl_end_kernel(StepCtl* ctl, double* log) {
     ctl_pre_step(c);
   }
   *ctl = c;
+}
+
+__global__ void ctl_end_kernel(StepCtl* ctl, double* log) { ctl_end_body(ctl, log); }
+
+// ---------------------------------------------------------------------------------------
+// Peer-memory transport.  Mailbox of a rank (unsigned 64-bit words, device memory, mapped by every other rank):
+//   [0 .. 256)    CFL slots  [parity][writer rank] = (bits of the writer's CFL number, tag)
+//   [256 .. 320)  barrier slots [writer rank] = tag
+//   [320], [321]  the owner's own running tags (CFL exchanges / barriers done so far; never reset)
+// A writer stores the value, fences at system scope, then stores the tag; the owner polls its own memory.  Tags only grow;
+// the parity double-buffers the CFL slots (a rank can be at most one exchange ahead of another: it cannot finish exchange
+// n+1 without everybody's value of n+1).
+// ---------------------------------------------------------------------------------------
+constexpr int MAIL_CFL = 0, MAIL_BAR = 256, MAIL_TAGS = 320, MAIL_WORDS = 512, MAIL_MAXR = 64;
+struct PeerMail { unsigned long long* local; unsigned long long* remote[MAIL_MAXR]; int nranks, rank; };
+constexpr long long PEER_SPIN_LIMIT = 1LL << 26;       // ~ tens of seconds of polling: a dead peer must not hang the GPU
+
+// max over ranks of `mine` (bit pattern of a non-negative double); called by 64 threads of one CTA; false on timeout
+__device__ bool peer_max_bits(const PeerMail& pm, unsigned long long mine, unsigned long long* out) {
+  __shared__ unsigned long long s_max;
+  __shared__ int s_ok;
+  const int r = threadIdx.x;
+  const unsigned long long tag = pm.local[MAIL_TAGS] + 1ull;
+  const unsigned par = (unsigned)(tag & 1ull);
+  if (r == 0) { s_max = 0ull; s_ok = 1; }
+  __syncthreads();
+  if (r < pm.nranks) {
+    volatile unsigned long long* dst = pm.remote[r] + MAIL_CFL + (par * MAIL_MAXR + pm.rank) * 2;
+    dst[0] = mine;
+    __threadfence_system();
+    dst[1] = tag;
+    volatile unsigned long long* src = pm.local + MAIL_CFL + (par * MAIL_MAXR + r) * 2;
+    long long spins = 0;
+    while (src[1] < tag) { if (++spins > PEER_SPIN_LIMIT) { s_ok = 0; break; } }
+    __threadfence_system();
+    atomicMax(&s_max, src[0]);
+  }
+  __syncthreads();
+  if (r == 0) { pm.local[MAIL_TAGS] = tag; *out = s_max; }
+  return s_ok != 0;
+}
+
+// control kernel of a multi-rank attempt: all-reduce (max) of the CFL slot through the mailboxes, then the same decision
+// on every rank
+__global__ void ctl_end_peer_kernel(StepCtl* ctl, double* log, PeerMail pm) {
+  if (ctl->done) return;                                   // identical on every rank: nobody exchanges
+  unsigned long long mx = 0ull;
+  const bool ok = peer_max_bits(pm, ctl->cfl_bits, &mx);
+  if (threadIdx.x == 0) {
+    if (!ok) { ctl->error = 3; ctl->done = 1; return; }    // a peer never answered
+    ctl->cfl_bits = mx;
+    ctl_end_body(ctl, log);
+  }
+}
+// the same reduction on the bare CFL slot (host-driven attempts: claw_step_launch)
+__global__ void peer_allreduce_kernel(unsigned long long* cfl_bits, PeerMail pm, int* status) {
+  unsigned long long mx = 0ull;
+  const bool ok = peer_max_bits(pm, *cfl_bits, &mx);
+  if (threadIdx.x == 0) { if (ok) *cfl_bits = mx; else *status = 1; }
+}
+// barrier across ranks (after a rank has refreshed its neighbours' ghost cells by hand: initial data, host uploads)
+__global__ void peer_barrier_kernel(PeerMail pm, int* status) {
+  const int r = threadIdx.x;
+  const unsigned long long tag = pm.local[MAIL_TAGS + 1] + 1ull;
+  __shared__ int s_ok;
+  if (r == 0) s_ok = 1;
+  __syncthreads();
+  if (r < pm.nranks) {
+    __threadfence_system();
+    volatile unsigned long long* dst = pm.remote[r] + MAIL_BAR + pm.rank;
+    *dst = tag;
+    volatile unsigned long long* src = pm.local + MAIL_BAR + r;
+    long long spins = 0;
+    while (*src < tag) { if (++spins > PEER_SPIN_LIMIT) { s_ok = 0; break; } }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (r == 0) { pm.local[MAIL_TAGS + 1] = tag; if (!s_ok) *status = 1; }
+}
+// ncomp runs of `len` doubles from my array into a neighbour's (both selected by the same role under the same StepCtl:
+// the current-buffer index is identical on every rank)
+__global__ void peer_copy_runs(ArrSel src_sel, long long src_off, long long src_stride, ArrSel dst_sel, long long dst_off,
+                               long long dst_stride, long long len, int ncomp) {
+  const double* src = sel_array(src_sel);
+  double* dst = sel_array(dst_sel);
+  if (src == nullptr || dst == nullptr) return;
+  src += src_off; dst += dst_off;
+  const long long n = len * ncomp;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    const long long m = k / len, i = k % len;
+    dst[m * dst_stride + i] = src[m * src_stride + i];
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -869,6 +977,9 @@ int claw_destroy(claw_solver* h) {
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->hot) cudaFree(h->hot);
   for (int k = 0; k < 4; ++k) if (h->hx[k]) cudaFree(h->hx[k]);
+  for (int r = 0; r < 64; ++r)
+    for (int k = 0; k < 4; ++k) if (h->peer.opened[r][k]) cudaIpcCloseMemHandle(h->peer.opened[r][k]);
+  if (h->peer.mail) cudaFree(h->peer.mail);
   if (h->graph) cudaGraphExecDestroy(h->graph);
   if (h->s_cap) cudaStreamDestroy(h->s_cap);
   if (h->ev_cfl) cudaEventDestroy(h->ev_cfl);
@@ -1094,6 +1205,17 @@ int claw_cfl_wait(claw_solver* h, double* cfl) {
   return 0;
 }
 
+// the CFL slot as it is NOW on the device (after a reduction across ranks queued behind claw_step_launch); waits
+int claw_cfl_read(claw_solver* h, double* cfl) {
+  if (check_handle(h)) return 1;
+  if (!h->work || !cfl) return fail(h, 15, "claw_cfl_read: no buffers / NULL argument");
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaMemcpyAsync(h->h_cfl, h->work, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  *cfl = *h->h_cfl;
+  return 0;
+}
+
 int claw_step(claw_solver* h, const double* delta, double dt, int fill_ghosts, double* cfl) {
   if (int rc = claw_step_launch(h, delta, dt, fill_ghosts)) return rc;
   return claw_cfl_wait(h, cfl);
@@ -1121,6 +1243,49 @@ int claw_sync(claw_solver* h) {
 // ---- device-resident step control ----------------------------------------------------------
 namespace {
 // one attempt under the control block: [ghost fill] + sweep(s); the control kernel follows (claw_ctl_end)
+PeerMail peer_mail_of(const claw_solver* h) {
+  PeerMail pm{};
+  pm.local = h->peer.mail;
+  for (int r = 0; r < MAIL_MAXR; ++r) pm.remote[r] = h->peer.peer_mail[r];
+  pm.nranks = h->peer.nranks; pm.rank = h->peer.rank;
+  return pm;
+}
+// my interior rows / planes next to the rank faces -> the neighbours' ghost rows / planes.  role 0 / 1 = the current /
+// the alternate q buffer (picked on the device under a StepCtl); aux = the static aux array instead
+int peer_push(claw_solver* h, int role, bool aux) {
+  const Dev2& g = h->g;
+  const int last = g.ndim - 1, ng = g.ng;
+  const int ncomp = aux ? h->maux : h->meqn;
+  if (ncomp == 0) return 0;
+  // one "layer" of the slab dimension: a row (2-D, pitch doubles) or a plane (3-D, kstride doubles)
+  const long long layer = (g.ndim == 2) ? (long long)g.pitch : g.kstride;
+  const long long len = ng * layer;
+  auto sel_remote = [&](double* const* q2, double* a) {
+    ArrSel d{};
+    if (aux) { d.q[0] = a; return d; }
+    if (!h->ctl_mode) { d.q[0] = q2[role == 0 ? h->cur : (h->cur ^ 1)]; return d; }
+    d.q[0] = q2[0]; d.q[1] = q2[1]; d.q[2] = nullptr;
+    d.ctl = reinterpret_cast<const StepCtl*>(h->work);
+    d.role = role;
+    return d;
+  };
+  const ArrSel src = aux ? sel_fixed(h->aux) : sel_q(h, role);
+  const int blocks = grid_for(len * ncomp, 256);
+  if (h->peer.up >= 0) {        // channel A: my upper interior layers [n, n+ng) -> the upper neighbour's lower ghosts [0, ng)
+    peer_copy_runs<<<blocks, 256, 0, h->stream>>>(src, (long long)g.n[last] * layer, g.plane,
+                                                  sel_remote(h->peer.up_q, h->peer.up_aux), 0, h->peer.up_plane, len, ncomp);
+    ++h->launches;
+  }
+  if (h->peer.lo >= 0) {        // channel B: my lower interior layers [ng, 2ng) -> the lower neighbour's upper ghosts
+    peer_copy_runs<<<blocks, 256, 0, h->stream>>>(src, (long long)ng * layer, g.plane,
+                                                  sel_remote(h->peer.lo_q, h->peer.lo_aux),
+                                                  (long long)(h->peer.lo_nlast + ng) * layer, h->peer.lo_plane, len, ncomp);
+    ++h->launches;
+  }
+  CK(h, cudaGetLastError());
+  return 0;
+}
+
 int ctl_enqueue_sweep(claw_solver* h, const double* delta, int fill_ghosts) {
   if (fill_ghosts)
     if (int rc = claw_apply_bcs(h)) return rc;
@@ -1134,7 +1299,15 @@ int ctl_enqueue_end(claw_solver* h) {
                                                                h->src_params[0], 0.0);
     ++h->launches;
   }
-  ctl_end_kernel<<<1, 1, 0, h->stream>>>(reinterpret_cast<StepCtl*>(h->work), h->work + CTL_WORDS);
+  if (h->peer.active) {
+    // the rows / planes next to the rank faces of the buffer this attempt wrote go straight into the neighbours' ghost
+    // cells of THEIR alternate buffer (it becomes current on every rank together, or is discarded on every rank)
+    if (int rc = peer_push(h, 1, false)) return rc;
+    ctl_end_peer_kernel<<<1, MAIL_MAXR, 0, h->stream>>>(reinterpret_cast<StepCtl*>(h->work), h->work + CTL_WORDS,
+                                                       peer_mail_of(h));
+  } else {
+    ctl_end_kernel<<<1, 1, 0, h->stream>>>(reinterpret_cast<StepCtl*>(h->work), h->work + CTL_WORDS);
+  }
   ++h->launches;
   CK(h, cudaGetLastError());
   return 0;
@@ -1341,6 +1514,140 @@ int claw_halo_unpack_aux(claw_solver* h, int side, const double* d_buf) {
   if (check_handle(h)) return 1;
   if (h->maux == 0) return 0;
   return halo_move(h, sel_fixed(h->aux), h->maux, side, const_cast<double*>(d_buf), false);
+}
+
+// ---- peer-memory transport (CUDA IPC over NVLink) ------------------------------------------------------------------
+namespace {
+struct PeerInfo {                                   // what a rank tells the others (CLAW_PEER_INFO_BYTES = 320)
+  cudaIpcMemHandle_t q0, q1, aux, mail;             // 4 x 64 bytes
+  long long plane;
+  int nlast, has_aux, ndim, pitch;
+  char pad[320 - 4 * 64 - 8 - 16];
+};
+static_assert(sizeof(PeerInfo) == 320, "PeerInfo is exchanged as 320 bytes");
+}  // namespace
+
+int claw_own_buffers(claw_solver* h) {
+  if (check_handle(h)) return 1;
+  return ensure_buffers(h);
+}
+
+int claw_peer_export(claw_solver* h, void* info320) {
+  if (check_handle(h)) return 1;
+  if (!info320) return fail(h, 70, "claw_peer_export: NULL buffer");
+  if (int rc = ensure_buffers(h)) return rc;
+  if (!h->owns_buffers)
+    return fail(h, 71, "claw_peer_export: the buffers must be the library's own allocations (claw_own_buffers instead of "
+                       "claw_bind): an IPC handle names a whole allocation");
+  CK(h, cudaSetDevice(h->device));
+  if (!h->peer.mail) {
+    CK(h, cudaMalloc(&h->peer.mail, MAIL_WORDS * sizeof(unsigned long long)));
+    CK(h, cudaMemset(h->peer.mail, 0, MAIL_WORDS * sizeof(unsigned long long)));
+  }
+  PeerInfo inf{};
+  CK(h, cudaIpcGetMemHandle(&inf.q0, h->q[0]));
+  CK(h, cudaIpcGetMemHandle(&inf.q1, h->q[1]));
+  if (h->aux) CK(h, cudaIpcGetMemHandle(&inf.aux, h->aux));
+  CK(h, cudaIpcGetMemHandle(&inf.mail, h->peer.mail));
+  inf.plane = h->g.plane; inf.nlast = h->g.n[h->g.ndim - 1]; inf.has_aux = h->aux ? 1 : 0;
+  inf.ndim = h->g.ndim; inf.pitch = h->g.pitch;
+  std::memcpy(info320, &inf, sizeof inf);
+  return 0;
+}
+
+int claw_peer_connect(claw_solver* h, int nranks, int rank, const void* infos, int send_up_to, int send_lo_to) {
+  if (check_handle(h)) return 1;
+  if (!infos || nranks < 1 || nranks > MAIL_MAXR || rank < 0 || rank >= nranks)
+    return fail(h, 72, "claw_peer_connect: bad arguments (nranks = %d, at most %d)", nranks, MAIL_MAXR);
+  if (!h->peer.mail) return fail(h, 73, "claw_peer_connect: call claw_peer_export first");
+  if (send_up_to >= nranks || send_lo_to >= nranks) return fail(h, 72, "claw_peer_connect: neighbour out of range");
+  CK(h, cudaSetDevice(h->device));
+  const PeerInfo* all = static_cast<const PeerInfo*>(infos);
+  auto& P = h->peer;
+  P.nranks = nranks; P.rank = rank; P.up = send_up_to; P.lo = send_lo_to;
+  auto open = [&](int r, int which, const cudaIpcMemHandle_t& hd, void** out) -> int {
+    if (!P.opened[r][which]) {
+      cudaError_t e = cudaIpcOpenMemHandle(&P.opened[r][which], hd, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        P.opened[r][which] = nullptr;
+        cudaGetLastError();
+        return fail(h, 74, "claw_peer_connect: cudaIpcOpenMemHandle of rank %d failed: %s", r, cudaGetErrorString(e));
+      }
+    }
+    *out = P.opened[r][which];
+    return 0;
+  };
+  for (int r = 0; r < nranks; ++r) {
+    if (all[r].ndim != h->g.ndim || all[r].pitch != h->g.pitch)
+      return fail(h, 75, "claw_peer_connect: rank %d has another grid layout", r);
+    if (r == rank) { P.peer_mail[r] = P.mail; continue; }
+    void* p = nullptr;
+    if (int rc = open(r, 3, all[r].mail, &p)) return rc;
+    P.peer_mail[r] = static_cast<unsigned long long*>(p);
+  }
+  auto neighbour = [&](int r, double** q2, double** a, long long* plane) -> int {
+    if (r < 0) return 0;
+    if (r == rank) {                                 // a periodic slab dimension on one rank never gets here
+      return fail(h, 76, "claw_peer_connect: a rank cannot be its own neighbour");
+    }
+    void* p = nullptr;
+    if (int rc = open(r, 0, all[r].q0, &p)) return rc;
+    q2[0] = static_cast<double*>(p);
+    if (int rc = open(r, 1, all[r].q1, &p)) return rc;
+    q2[1] = static_cast<double*>(p);
+    if (all[r].has_aux) {
+      if (int rc = open(r, 2, all[r].aux, &p)) return rc;
+      *a = static_cast<double*>(p);
+    }
+    *plane = all[r].plane;
+    return 0;
+  };
+  if (int rc = neighbour(send_up_to, P.up_q, &P.up_aux, &P.up_plane)) return rc;
+  if (int rc = neighbour(send_lo_to, P.lo_q, &P.lo_aux, &P.lo_plane)) return rc;
+  if (send_lo_to >= 0) P.lo_nlast = all[send_lo_to].nlast;
+  P.active = true;
+  ++h->cfg_epoch;
+  return 0;
+}
+
+namespace {
+int peer_status_check(claw_solver* h, int* d_status, const char* what) {
+  int st = 0;
+  CK(h, cudaMemcpyAsync(&st, d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (st) return fail(h, 77, "%s: a peer rank did not answer (timeout)", what);
+  return 0;
+}
+int* peer_status_word(claw_solver* h) {               // a word of the mailbox nobody else writes
+  return reinterpret_cast<int*>(h->peer.mail + MAIL_TAGS + 8);
+}
+}  // namespace
+
+int claw_peer_sync(claw_solver* h, int aux) {
+  if (check_handle(h)) return 1;
+  if (!h->peer.active) return fail(h, 73, "claw_peer_sync: no peers connected");
+  CK(h, cudaSetDevice(h->device));
+  if (int rc = peer_push(h, 0, aux != 0)) return rc;
+  CK(h, cudaMemsetAsync(peer_status_word(h), 0, sizeof(int), h->stream));
+  peer_barrier_kernel<<<1, MAIL_MAXR, 0, h->stream>>>(peer_mail_of(h), peer_status_word(h));
+  ++h->launches;
+  CK(h, cudaGetLastError());
+  return peer_status_check(h, peer_status_word(h), "claw_peer_sync");
+}
+
+int claw_peer_allreduce_cfl(claw_solver* h, double* cfl) {
+  if (check_handle(h)) return 1;
+  if (!h->peer.active) return fail(h, 73, "claw_peer_allreduce_cfl: no peers connected");
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaMemsetAsync(peer_status_word(h), 0, sizeof(int), h->stream));
+  peer_allreduce_kernel<<<1, MAIL_MAXR, 0, h->stream>>>(reinterpret_cast<unsigned long long*>(h->work), peer_mail_of(h),
+                                                       peer_status_word(h));
+  ++h->launches;
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(h->h_cfl, h->work, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (int rc = peer_status_check(h, peer_status_word(h), "claw_peer_allreduce_cfl")) return rc;
+  if (cfl) *cfl = *h->h_cfl;
+  return 0;
 }
 
 // ---- NCCL through the C ABI -------------------------------------------------------------------------------------

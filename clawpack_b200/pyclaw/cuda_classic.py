@@ -9,6 +9,7 @@ libclawcuda.so (include/clawcuda.h), via ctypes.  PyTorch only provides the devi
 """
 import ctypes
 import math
+import os
 import weakref
 
 import numpy as np
@@ -91,14 +92,22 @@ class DeviceStepper(object):
         nq, na, nw = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
         _lib.check(L.claw_buffer_sizes(h, ctypes.byref(nq), ctypes.byref(na), ctypes.byref(nw)), h)
         f64 = torch.float64
-        self.q0 = torch.zeros(nq.value, dtype=f64, device=self.device)
-        self.q1 = torch.zeros(nq.value, dtype=f64, device=self.device)
-        self.aux = torch.zeros(max(na.value, 1), dtype=f64, device=self.device)
-        self.work = torch.zeros(nw.value, dtype=f64, device=self.device)
-        _lib.check(L.claw_bind(h, ctypes.c_void_p(self.q0.data_ptr()), ctypes.c_void_p(self.q1.data_ptr()),
-                               ctypes.c_void_p(self.aux.data_ptr() if na.value else 0),
-                               ctypes.c_void_p(self.work.data_ptr())), h)
-        self.cfl_tensor = self.work[0:1]          # the 8-byte CFL slot (for the multi-GPU max all-reduce)
+        # The peer-memory transport of multi-rank runs (petclaw.device_halo; the default, CLAW_HALO=peer) maps the neighbours' buffers
+        # through CUDA IPC, which names whole allocations: the buffers then are the library's own (cudaMalloc each)
+        # instead of tensors cut from PyTorch's caching allocator.
+        self.own_buffers = (os.environ.get('CLAW_HALO', 'peer') == 'peer' and getattr(state.patch, 'num_ranks', 1) > 1)
+        if self.own_buffers:
+            _lib.check(L.claw_own_buffers(h), h)
+            self.q0 = self.q1 = self.aux = self.work = self.cfl_tensor = None
+        else:
+            self.q0 = torch.zeros(nq.value, dtype=f64, device=self.device)
+            self.q1 = torch.zeros(nq.value, dtype=f64, device=self.device)
+            self.aux = torch.zeros(max(na.value, 1), dtype=f64, device=self.device)
+            self.work = torch.zeros(nw.value, dtype=f64, device=self.device)
+            _lib.check(L.claw_bind(h, ctypes.c_void_p(self.q0.data_ptr()), ctypes.c_void_p(self.q1.data_ptr()),
+                                   ctypes.c_void_p(self.aux.data_ptr() if na.value else 0),
+                                   ctypes.c_void_p(self.work.data_ptr())), h)
+            self.cfl_tensor = self.work[0:1]      # the 8-byte CFL slot (for the multi-GPU max all-reduce)
         cp, ncp = _cparam_of(solver.rp)
         _lib.check(L.claw_set_cparam(h, _lib.dp(cp), ncp), h)
         mth = _iarr(solver._mthlim)
@@ -135,6 +144,7 @@ class DeviceStepper(object):
         self.host_valid = True      # state._q equals the device's current buffer
         self.host_dirty = True      # state._q may have been changed on the host since the last upload
         self.aux_dirty = False      # state.aux was replaced on the host since the upload at setup
+        self.peer_dirty = True      # (peer transport) the neighbours' ghost cells of the current buffer need a refresh
         self.halo = None            # multi-rank runs: petclaw.device_halo.DeviceHalo (ghost exchange + CFL all-reduce)
         self.halo_aux = None        # the same for the aux ghost planes (exchanged when aux is uploaded)
         # device-resident step control (claw_ctl_*)
@@ -187,6 +197,7 @@ class DeviceStepper(object):
             q = np.asfortranarray(state._q, dtype=np.float64)
             _lib.check(self.L.claw_put_q(self.handle, q.ctypes.data_as(ctypes.c_void_p)), self.handle)
             self.host_dirty = False
+            self.peer_dirty = True          # peer transport: the neighbours' copies of my boundary rows are stale
         if self.aux_dirty:                                   # state.aux = new_array after setup
             if state.num_aux > 0:
                 aux = np.asfortranarray(state.aux, dtype=np.float64)
@@ -217,6 +228,14 @@ class DeviceStepper(object):
         """Queue n step attempts: [ghost exchange] + ghost fill + sweep + [CFL all-reduce] + control kernel."""
         L, h = self.L, self.handle
         if self.halo is None:
+            _lib.check(L.claw_ctl_attempts(h, _lib.dp(self.delta), int(n), 1), h)
+        elif self.halo.transport == 'peer':
+            # ghost cells travel inside the attempt (peer-memory writes after the sweep, CFL through the mailboxes): the
+            # N-rank attempt is queued like the 1-rank one.  Only after a host upload -- which every rank must do alike
+            # -- are the neighbours' ghost cells refreshed by hand.
+            if self.peer_dirty:
+                self.halo.exchange(self)
+                self.peer_dirty = False
             _lib.check(L.claw_ctl_attempts(h, _lib.dp(self.delta), int(n), 1), h)
         else:
             for _ in range(n):
@@ -321,6 +340,8 @@ class DeviceStepper(object):
             self.host_ctl_dirty = True          # the next begin starts from the host's (consistent) values
             if err == 1:
                 raise Exception('CFL too large, giving up!')
+            if err == 3:
+                raise _lib.ClawCudaError('a peer rank did not deliver its CFL number (peer-memory transport timed out)')
             raise Exception('Maximum number of timesteps have been taken')
 
     # ---- stepping ------------------------------------------------------------------------------
@@ -336,8 +357,13 @@ class DeviceStepper(object):
             self.halo.exchange(self)
         _lib.check(self.L.claw_step_launch(self.handle, _lib.dp(self.delta), float(dt), 1), self.handle)
         if self.halo is not None:
+            if self.halo.transport == 'peer':
+                self.peer_dirty = True       # the next attempt starts from ghost cells refreshed by hand
+                return self.halo.all_reduce_cfl(self)
             self.halo.all_reduce_cfl(self)
-            return float(self.cfl_tensor.item())
+            cfl = ctypes.c_double(0.0)
+            _lib.check(self.L.claw_cfl_read(self.handle, ctypes.byref(cfl)), self.handle)
+            return cfl.value
         cfl = ctypes.c_double(0.0)
         _lib.check(self.L.claw_cfl_wait(self.handle, ctypes.byref(cfl)), self.handle)
         return cfl.value

@@ -160,6 +160,9 @@ int claw_step_launch(claw_solver* h, const double* delta, double dt, int fill_gh
 int claw_cfl_device_ptr(claw_solver* h, void** d_cfl);
 /* wait for the launch and return its CFL number */
 int claw_cfl_wait(claw_solver* h, double* cfl);
+/* the CFL slot as it is on the device after everything queued so far (e.g. a reduction across ranks behind
+   claw_step_launch); waits for the stream */
+int claw_cfl_read(claw_solver* h, double* cfl);
 /* claw_step_launch + claw_cfl_wait */
 int claw_step(claw_solver* h, const double* delta, double dt, int fill_ghosts, double* cfl);
 int claw_accept(claw_solver* h);
@@ -232,6 +235,24 @@ int claw_allreduce_cfl(claw_solver* h, void* nccl_comm);
 int claw_nccl_unique_id(void* id128);
 int claw_nccl_comm_init(void** nccl_comm, int nranks, int rank, const void* id128, int device);
 int claw_nccl_comm_destroy(void* nccl_comm);
+
+/* ---- peer-memory transport: ghost cells and CFL numbers over NVLink without a collective library -----------------
+   One process per GPU on ONE node.  Every rank exports IPC handles of its (library-owned) q / aux buffers and of a small
+   mailbox (claw_peer_export -> CLAW_PEER_INFO_BYTES bytes), the host gathers the blocks of all ranks by its own means,
+   and claw_peer_connect maps the slab neighbours' buffers and everybody's mailbox (cudaIpcOpenMemHandle).  From then on
+   an attempt under claw_ctl_* needs no exchange call at all: after the sweep(s) the rows / planes next to a rank face are
+   written straight into the neighbour's ghost cells of the buffer that becomes current on accept, and the control kernel
+   all-reduces (max) the CFL number through the mailboxes before it decides -- identically on every rank.  So
+   claw_ctl_attempts (and its CUDA graph) serve N ranks like one.  claw_peer_sync refreshes the neighbours' ghost cells of
+   the CURRENT buffer (aux != 0: of the aux array) and ends with a barrier across ranks: call it on EVERY rank after the
+   initial data (or any later host upload) are in place.  claw_peer_allreduce_cfl is the reduction alone, for host-driven
+   attempts (claw_step_launch).  Replaces DMDA globalToLocal / Vec.max of PetClaw (petclaw/state.py:223-231, cfl.py:36). */
+#define CLAW_PEER_INFO_BYTES 320
+int claw_own_buffers(claw_solver* h);          /* allocate q0 / q1 / aux / work inside the library (instead of claw_bind) */
+int claw_peer_export(claw_solver* h, void* info);
+int claw_peer_connect(claw_solver* h, int nranks, int rank, const void* infos_of_all_ranks, int send_up_to, int send_lo_to);
+int claw_peer_sync(claw_solver* h, int aux);
+int claw_peer_allreduce_cfl(claw_solver* h, double* cfl);
 
 /* time `reps` back-to-back launches of the sweep kernel alone (no ghost fill, no swap) with CUDA
    events on the handle's stream; returns the average duration in milliseconds (bench.py roofline) */

@@ -37,19 +37,23 @@ def main():
     ok = True
     # second pass: the same cases with the exchange behind the C ABI (claw_halo_exchange / claw_allreduce_cfl on the
     # library's own NCCL communicator) -- the path a non-Python host would use
-    for transport, case in [('torch', c) for c in sorted(CASES)] + [('cabi', c) for c in sorted(CASES)]:
+    # third pass: the peer-memory transport (ghost cells written into the neighbour's buffers over NVLink inside the
+    # attempt, CFL through mailboxes; claw_peer_*)
+    transports = os.environ.get('CLAW_TEST_TRANSPORTS', 'torch,cabi,peer').split(',')
+    for transport, case in [(t, c) for t in transports for c in sorted(CASES)]:
         os.environ['CLAW_HALO'] = transport
         sc = CASES[case]()
         claw = petclaw.make_claw_distributed(sc, kernel_language='CUDA', cuda_precision='strict')
         claw.run()
+        used = claw.solver._dev.halo.transport if claw.solver._dev is not None and claw.solver._dev.halo is not None else '-'
         q = claw.solution.state.get_q_global()
         log = claw.solver.step_log
         if rank == 0:
             r = ref_solver(sc)
             r.run(sc['tfinal'], sc['num_output_times'])
             same_q, same_log = np.array_equal(q, r.q), (log == r.step_log)
-            print('case %s (%s) world %d: q bit-identical to serial oracle: %s, step log identical: %s (%d steps)'
-                  % (case, transport, world, same_q, same_log, len(log)), flush=True)
+            print('case %s (%s -> %s) world %d: q bit-identical to serial oracle: %s, step log identical: %s (%d steps)'
+                  % (case, transport, used, world, same_q, same_log, len(log)), flush=True)
             ok = ok and same_q and same_log
         claw.solver.teardown()
         dist.barrier()

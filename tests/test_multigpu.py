@@ -26,4 +26,4 @@ def test_slab_nccl_matches_serial_oracle(world):
            '--master-addr', '127.0.0.1', '--master-port', str(29700 + world), os.path.join(HERE, 'dist_gpu_worker.py')]
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-4000:]
-    assert p.stdout.count('q bit-identical to serial oracle: True, step log identical: True') == 12, p.stdout[-4000:]      # six cases x two transports (torch process group, C ABI)
+    assert p.stdout.count('q bit-identical to serial oracle: True, step log identical: True') == 18, p.stdout[-6000:]      # six cases x three transports (torch process group, C ABI, peer memory)
