@@ -1361,7 +1361,7 @@ int claw_ctl_attempts(claw_solver* h, const double* delta, int n, int fill_ghost
   CK(h, cudaSetDevice(h->device));
   h->ctl_pending = true;
   const int ndim = h->g.ndim;
-  bool graph_ok = h->use_graph && n >= 2;
+  bool graph_ok = h->use_graph && n >= 1;          // (a single attempt too: the graph is captured once per configuration)
   if (graph_ok) {
     bool stale = (h->graph == nullptr) || h->graph_epoch != h->cfg_epoch || h->graph_fill != (fill_ghosts ? 1 : 0);
     for (int d = 0; d < ndim; ++d) stale = stale || (h->graph_delta[d] != delta[d]);

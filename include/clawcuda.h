@@ -188,8 +188,9 @@ int claw_sync(claw_solver* h);
    claw_ctl_begin   start of one evolve_to_time call: tstart = t, done = 0, then the get_dt of the first attempt.
                     host_words != NULL uploads the host's values of words 1..6, 10..13, 18, 19 first (required on the
                     first call; later calls pass NULL to carry on from the device's state without a read-back).
-   claw_ctl_attempts  queue n attempts: each = [ghost fill] + sweep(s) + control kernel (single-rank runs; n >= 2 goes
-                    through a CUDA graph of one attempt, captured once per configuration).
+   claw_ctl_attempts  queue n attempts: each = [ghost fill] + sweep(s) [+ source functor] [+ peer-memory copies] + control
+                    kernel, through a CUDA graph of one attempt captured once per configuration (single-rank runs, and
+                    multi-rank runs under the peer-memory transport, claw_peer_*).
    claw_ctl_sweep / claw_ctl_end  the two halves of ONE attempt for multi-rank runs: the caller all-reduces (max) the
                     CFL slot across ranks in between (ncclAllReduce on the same stream; petclaw/cfl.py:36).
    claw_ctl_read    wait for everything queued; returns the control block and the log entries (dt, cfl, accepted) of
