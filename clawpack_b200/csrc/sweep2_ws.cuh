@@ -103,18 +103,58 @@ template <int M, int RD, int NT, int m = 0> __device__ __forceinline__ void ring
   if constexpr (m < M) { q[m] = ring_ld<m * RD * NT>(r, off); ring_ld_row<M, RD, NT, m + 1>(r, off, q); }
 }
 
+// TMA form of the row ring (template flag TMA of sweep2_unsplit_ws): one bulk copy per component and row --
+// cp.async.bulk global -> shared, 256 bytes = the 32 columns of the strip, issued by lane 0, completion counted in bytes
+// on an mbarrier per ring slot -- instead of 32 lanes x 8-byte cp.async.  `mbar` = shared-window address of the slot's
+// mbarrier; the k-th use of a slot completes phase parity k & 1.
+#ifdef CLAW_HOST_CHECK
+inline void tma_mbar_init(ring_t, int) {}
+inline void tma_row_issue(ring_t dst, int off, const double* src, int bytes, ring_t, bool first, int total) {
+  (void)first; (void)total;
+  std::memcpy(dst + off, src, (size_t)bytes);
+}
+inline void tma_wait(ring_t, unsigned) {}
+inline void warp_sync() { emul::yield_sync(); }
+#else
+__device__ __forceinline__ void tma_mbar_init(ring_t mbar, int n) {
+  for (int k = 0; k < n; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar + 8u * k) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// one component of a row; `first` arms the slot's mbarrier with the byte count of the whole row (`total`)
+__device__ __forceinline__ void tma_row_issue(ring_t dst, int off, const double* src, int bytes, ring_t mbar, bool first,
+                                              int total) {
+  if (first) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(total) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst + 8u * (unsigned)off),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_wait(ring_t mbar, unsigned parity) {
+  unsigned ok = 0;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void warp_sync() { __syncwarp(); }
+#endif
+
 // Tight loop of the uniform-region fast path: a run of rows that carry the bits of `ref` in all 32 columns of the warp.
 // Per row: queue the row RD steps ahead, wait for the next row of the ring, compare it with `ref`, vote, store `sto`
 // (which carries the bits of `ref`) as the output row.  J is the march step whose row has been stored last; the loop
 // ends at the segment end or at the first row that differs, which is handed over in qT (return value true) for the
 // general classification of step J + 1.  Ring bookkeeping (wslot, rslot: slot offsets in doubles; gfetch: row to queue
 // next) is the caller's and is left as ring_fetch would have left it.
-template <int M, int RD, int NT>
+template <int M, int RD, int NT, bool TMA = false>
 __device__ __forceinline__ bool quiet_run(int& J, const int Je, const double (&ref)[M], const double (&sto)[M], double (&qT)[M],
                                           double* spf, int& wslot, int& rslot, const double*& gfetch, const long long plane,
-                                          const int pitch, double* orow, const bool st) {
+                                          const int pitch, double* orow, const bool st, [[maybe_unused]] ring_t mbar = ring_t(),
+                                          [[maybe_unused]] unsigned* rphase = nullptr, [[maybe_unused]] bool live = true) {
   constexpr int WRAP = RD * NT - 1;
   const ring_t ring = ring_of(spf);
+  [[maybe_unused]] const bool lane0 = (threadIdx.x & 31) == 0;
+  [[maybe_unused]] const ring_t ring0 = ring_of(spf - (threadIdx.x & 31));     // lane 0's slot: start of the 32-lane row
   // running pointers per component (an invariant base + 32-bit row offset was measured to compile to more instructions:
   // at 255 registers the compiler rematerialises the plane pointers on every row)
   const double* gf[M];
@@ -126,19 +166,34 @@ __device__ __forceinline__ bool quiet_run(int& J, const int Je, const double (&r
   bool differs = false;
   const int J0 = J;
   while (J + 1 < Je) {
-    if (nf > 0) ring_cp_row<M, RD, NT>(ring, wo, gf);
-    cp_async_commit();
+    if constexpr (TMA) {
+      warp_sync();                                         // every lane has read the slot that is queued again
+      if (nf > 0 && lane0) {
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+          tma_row_issue(ring0, wo + m * RD * NT, gf[m], NT * 8, mbar + 8u * (unsigned)(wo / NT), m == 0, M * NT * 8);
+      }
+    } else {
+      if (nf > 0) ring_cp_row<M, RD, NT>(ring, wo, gf);
+      cp_async_commit();
+    }
     --nf;
 #pragma unroll
     for (int m = 0; m < M; ++m) gf[m] += pitch;
     wo = (wo + NT) & WRAP;
-    cp_async_wait_keep<RD - 1>();
+    if constexpr (TMA) {
+      const unsigned sl = (unsigned)(ro / NT);
+      tma_wait(mbar + 8u * sl, (*rphase >> sl) & 1u);
+      *rphase ^= 1u << sl;
+    } else {
+      cp_async_wait_keep<RD - 1>();
+    }
     ring_ld_row<M, RD, NT>(ring, ro, qT);
     ro = (ro + NT) & WRAP;
     unsigned long long d = 0ull;
 #pragma unroll
     for (int m = 0; m < M; ++m) d |= diff_bits(ref[m], qT[m]);
-    if (!warp_all(d == 0ull)) { differs = true; break; }
+    if (!warp_all(d == 0ull || !live)) { differs = true; break; }
     ++J;
     if (st) {
 #pragma unroll
@@ -277,7 +332,7 @@ __device__ __forceinline__ void hot_end(const Sweep2Params& P, const HotTile& h,
 // (which would add exact zeros); the CFL speeds come from the cell data instead of the Roe average of two identical
 // states (equal to rounding).  The kernel is then bound by HBM in such regions and by the FP64 pipe only near fronts;
 // the deeper ring keeps enough rows in flight for the former.
-template <class RP, int NW, int MINB = 1, int SPEC = 0, int UNR = 1, int QD = 0>
+template <class RP, int NW, int MINB = 1, int SPEC = 0, int UNR = 1, int QD = 0, int TMA = 0>
 __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_constant__ Sweep2Params P) {
   constexpr int M = RP::MEQN, W = RP::MWAVES, NR = RP::NROE, NT = NW * 32;
   constexpr bool SP = (SPEC & 1) != 0;
@@ -343,15 +398,36 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
   // The first consumer of a freshly loaded row is the Roe average of the y-interface: without a prefetch the warp
   // sits on the DRAM latency once per march step (ncu: 13 % of all stall samples on that one instruction).  PF=3
   // keeps row J+3 in flight (cp.async into a thread-private two-stage ring) while row J+2 is being worked on.
+  // TMA ring (one warp per CTA): lanes beyond the end of the row read the row's padding instead of a clamped copy of the
+  // last column -- they never reach a stored cell or the CFL number, and the votes of the fast path leave them out; a
+  // strip that would run over the padded row keeps the per-lane cp.async ring
+  constexpr bool TM = (TMA != 0) && (PF == 3) && (NW == 1);
+  [[maybe_unused]] const bool use_tma = TM && (bx * TX + 32 <= P.pitch);
+  [[maybe_unused]] const bool live = !use_tma || (I < nx);
+  [[maybe_unused]] const ring_t ring_s = ring_of(spf - lane), mbar_s = ring_of(sred + 32);
+  [[maybe_unused]] unsigned rphase = 0u;
+  if constexpr (TM) {
+    if (use_tma && lane == 0) tma_mbar_init(mbar_s, RD);
+    warp_sync();
+  }
   // ring slot of array row r: r & (RD - 1); rows Jb-1 .. Jb+RD-3 are in flight when the loop starts
   if constexpr (PF == 3) {
 #pragma unroll
     for (int k = 0; k < RD - 1; ++k) {
       const int r = Jb - 1 + k;
       if (r <= Je + 1) {
+        if (TM && use_tma) {
+          if (lane == 0) {
 #pragma unroll
-        for (int m = 0; m < M; ++m)
-          cp_async8(spf + (m * RD + (r & (RD - 1))) * NT, qcol + m * P.plane + (long long)r * P.pitch);
+            for (int m = 0; m < M; ++m)
+              tma_row_issue(ring_s, (m * RD + (r & (RD - 1))) * NT, qcol + m * P.plane + (long long)r * P.pitch, NT * 8,
+                            mbar_s + 8u * (unsigned)(r & (RD - 1)), m == 0, M * NT * 8);
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < M; ++m)
+            cp_async8(spf + (m * RD + (r & (RD - 1))) * NT, qcol + m * P.plane + (long long)r * P.pitch);
+        }
       }
       cp_async_commit();
     }
@@ -372,15 +448,32 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
   // warm-up rows: see sweep2_unsplit (the specialised kernel runs the full body from the first step)
   // step Js of the ring: queue row Js+RD+1 into the slot row Js+1 was read from, wait for row Js+2, read it
   auto ring_fetch = [&](int Js, double* q) {
-    if (Js + RD + 1 <= Je + 1) {
-      const double* g = gfetch;
+    if (TM && use_tma) {
+      warp_sync();                                         // every lane has read the slot that is queued again
+      if (Js + RD + 1 <= Je + 1 && lane == 0) {
+        const double* g = gfetch;
 #pragma unroll
-      for (int m = 0; m < M; ++m) { cp_async8(spf + wslot + m * RD * NT, g); g += P.plane; }
+        for (int m = 0; m < M; ++m) {
+          tma_row_issue(ring_s, wslot + m * RD * NT, g, NT * 8, mbar_s + 8u * (unsigned)(wslot / NT), m == 0, M * NT * 8);
+          g += P.plane;
+        }
+      }
+      gfetch += P.pitch;
+      wslot = (wslot + NT) & (RD * NT - 1);
+      const unsigned sl = (unsigned)(rslot / NT);
+      tma_wait(mbar_s + 8u * sl, (rphase >> sl) & 1u);
+      rphase ^= 1u << sl;
+    } else {
+      if (Js + RD + 1 <= Je + 1) {
+        const double* g = gfetch;
+#pragma unroll
+        for (int m = 0; m < M; ++m) { cp_async8(spf + wslot + m * RD * NT, g); g += P.plane; }
+      }
+      cp_async_commit();
+      gfetch += P.pitch;
+      wslot = (wslot + NT) & (RD * NT - 1);
+      cp_async_wait_keep<RD - 1>();
     }
-    cp_async_commit();
-    gfetch += P.pitch;
-    wslot = (wslot + NT) & (RD * NT - 1);
-    cp_async_wait_keep<RD - 1>();
 #pragma unroll
     for (int m = 0; m < M; ++m) q[m] = spf[rslot + m * RD * NT];
     rslot = (rslot + NT) & (RD * NT - 1);
@@ -413,8 +506,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
         yz = yz && same_bits(q1[m], qN[m]);
         xz = xz && same_bits(qlx[m], q1[m]);
       }
-      const bool yq0 = warp_all(yz);                       // y-interface J+2 joins identical states in all 32 columns
-      const bool xq0 = warp_all(xz);
+      const bool yq0 = warp_all(yz || !live);              // y-interface J+2 joins identical states in all 32 columns
+      const bool xq0 = warp_all(xz || !live);
       const bool quiet = yq0 && xq0 && yq1 && yq2;
       yq2 = yq1; yq1 = yq0;
       if (quiet) {
@@ -443,8 +536,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep2_unsplit_ws(const __grid_
           for (int m = 0; m < M; ++m) { pin(qn0[m]); pin(qn1[m]); pin(q1[m]); }
           // (qn1 and qn0 carry the bits of q1 here; comparing with the one and storing the other keeps both alive in
           // the loop, so that the compiler does not sink their last assignments into every exit of it)
-          have_row = quiet_run<M, RD, NT>(J, Je, qn1, qn0, qN, spf, wslot, rslot, gfetch, P.plane, P.pitch,
-                                          qout + (long long)(J + 1) * P.pitch + I, store_col);
+          if (TM && use_tma)
+            have_row = quiet_run<M, RD, NT, TM>(J, Je, qn1, qn0, qN, spf, wslot, rslot, gfetch, P.plane, P.pitch,
+                                                qout + (long long)(J + 1) * P.pitch + I, store_col, mbar_s, &rphase, live);
+          else
+            have_row = quiet_run<M, RD, NT>(J, Je, qn1, qn0, qN, spf, wslot, rslot, gfetch, P.plane, P.pitch,
+                                            qout + (long long)(J + 1) * P.pitch + I, store_col);
         }
         continue;
       }

@@ -32,7 +32,7 @@ static cudaError_t launch_kernel(KERN kern, int NT, int smem, bool x_only, Sweep
     // enough CTAs for >= 6 waves of resident CTAs, but segments not shorter than 32 rows
     // (each segment pays 3-4 warm-up rows) nor longer than 256.  Small grids that cannot even fill the GPU once with
     // 32-row segments are latency-bound on the march length instead: there the segments are as short as one wave of CTAs
-    // allows (the redundant warm-up rows cost nothing on an otherwise idle GPU), down to 2 rows.
+    // allows (the redundant warm-up rows cost nothing on an otherwise idle GPU), down to a single row.
     const long long want = 6LL * num_sms * occ;
     long long nseg = (want + strips - 1) / strips;
     if (nseg < 1) nseg = 1;
@@ -40,7 +40,7 @@ static cudaError_t launch_kernel(KERN kern, int NT, int smem, bool x_only, Sweep
     int min_seg = 32;
     if ((long long)strips * ((rows + 31) / 32) < (long long)num_sms * occ) {
       const long long one_wave = ((long long)rows * strips + (long long)num_sms * occ - 1) / ((long long)num_sms * occ);
-      min_seg = one_wave < 2 ? 2 : (int)one_wave;
+      min_seg = one_wave < 1 ? 1 : (int)one_wave;
     }
     if (seg < min_seg) seg = min_seg;
     if (seg > max_seg) seg = max_seg;
@@ -80,13 +80,13 @@ static cudaError_t launch_one(int kind, Sweep2Params& P, int seg_hint, int num_s
 }
 
 // warp-synchronous unsplit kernel (sweep2_ws.cuh): NW independent 28-column strips per CTA
-template <class RP, int NW, int MINB, int SPEC, int UNR = 1, int QD = 0>
+template <class RP, int NW, int MINB, int SPEC, int UNR = 1, int QD = 0, int TMA = 0>
 static cudaError_t launch_ws(Sweep2Params& P, int seg_hint, int num_sms, cudaStream_t st, LaunchInfo* info) {
   using S = Smem2ws<RP, NW, (QD > 0 ? QD : 2)>;
   // with the uniform-region fast path the cost of a CTA depends on how much of a front it holds: 64-row segments keep
   // the slowest CTAs short enough for the tail of the launch (measured at 8192^2, profiles/r02_i_segrows.jsonl: 1.38 ms
   // with 256-row segments, 1.20 / 1.16 / 1.29 ms with 128 / 64 / 32)
-  return launch_kernel(sweep2_unsplit_ws<RP, NW, MINB, SPEC, UNR, QD>, NW * 32, (int)S::BYTES, false, P, seg_hint, num_sms,
+  return launch_kernel(sweep2_unsplit_ws<RP, NW, MINB, SPEC, UNR, QD, TMA>, NW * 32, (int)S::BYTES, false, P, seg_hint, num_sms,
                        st, info, NW * 28, QD > 0 ? 64 : 256, UnsplitQuiet<RP, SPEC, QD>::value && NW == 1);
 }
 
@@ -150,6 +150,10 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
         // with a 2 / 4 / 8-stage ring.  CLAW_VARIANT=2: the same kernel without the fast path (dense-data timing, A/B).
         if (variant == 2) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
         if (variant == 71) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6, 1, 4>(P, seg_hint, num_sms, st, info);
+        // the row ring fed by TMA bulk copies (cp.async.bulk + mbarrier, one 256-byte copy per component and row issued
+        // by lane 0) instead of 32 lanes x 8-byte cp.async: A/B
+        if (variant == 91) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6, 1, 8, 1>(P, seg_hint, num_sms, st, info);
+        if (variant == 92) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6, 1, 16, 1>(P, seg_hint, num_sms, st, info);
         if (variant == 73) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6, 1, 16>(P, seg_hint, num_sms, st, info);
         if (variant != 1) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6, 1, 8>(P, seg_hint, num_sms, st, info);
       }

@@ -74,7 +74,8 @@ int run(int rp_id, int kind, int variant, Sweep2Params& P, int seg) {
       if (kind == 0 && P.mtrans == 2 && all_limiters<4>(P, 4) && variant != 9) {      // the headline kernel of bench.py
         // variants 72 / 71: with the uniform-region fast path and an 8- / 4-stage row ring (fast mode; in strict mode the
         // template argument only changes the ring depth)
-        if (variant == 72) launch(sweep2_unsplit_ws<RpEuler4Wave2DT<3>, 1, 1, (4 << 4) | 1 | 6, 1, 8>, 32, false, P, seg);
+        if (variant == 91) launch(sweep2_unsplit_ws<RpEuler4Wave2DT<3>, 1, 1, (4 << 4) | 1 | 6, 1, 8, 1>, 32, false, P, seg);   // TMA ring
+        else if (variant == 72) launch(sweep2_unsplit_ws<RpEuler4Wave2DT<3>, 1, 1, (4 << 4) | 1 | 6, 1, 8>, 32, false, P, seg);
         else if (variant == 71) launch(sweep2_unsplit_ws<RpEuler4Wave2DT<3>, 1, 1, (4 << 4) | 1 | 6, 1, 4>, 32, false, P, seg);
         else launch(sweep2_unsplit_ws<RpEuler4Wave2DT<3>, 1, 1, (4 << 4) | 1 | 6, 1>, 32, false, P, seg);
         return 0;

@@ -188,6 +188,13 @@ CASES_2D = {
     'shallow_split_quiet_ring8_tile_order': (lambda: dict(S.radial_dam_break(mx=120, my=100), limiters=S.MC), 173, 9),
     'shallow_split_quiet_ring8_tile_order_long_segments': (lambda: dict(S.radial_dam_break(mx=150, my=140), limiters=S.MC), 173, 0),
     'acoustics_split_quiet_ring8_tile_order': (lambda: S.acoustics_2d(mx=100, my=90), 173, 24),
+    # one-row march segments (what the launch code picks for grids far too small to fill the GPU: BASELINE config 1)
+    'acoustics_split_quiet_one_row_segments': (lambda: S.acoustics_2d(mx=60, my=40), 73, 1),
+    'euler_headline_quiet_one_row_segments': (lambda: S.shock_bubble(mx=60, my=33), 72, 1),
+    'shallow_split_generic_one_row_segments': (lambda: S.radial_dam_break(mx=40, my=31), 0, 1),
+    # the row ring fed by TMA bulk copies (emulated as a 32-lane memcpy by lane 0); 191: with the product's pitch
+    'euler_headline_quiet_tma_ring': (lambda: S.shock_bubble(mx=120, my=90), 191, 8),
+    'euler_headline_quiet_tma_ring_ragged': (lambda: S.shock_bubble(mx=57, my=45), 91, 0),
     'euler_quadrants_quiet_ring8': (lambda: dict(S.quadrants(mx=64, my=64), dimensional_split=False, transverse_waves=2,
                                                  limiters=S.MC), 72, 16),
     'euler_unsplit_generic_inc_mixed_limiters': (lambda: dict(S.quadrants(mx=40, my=30), dimensional_split=False,
