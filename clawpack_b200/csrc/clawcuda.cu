@@ -18,6 +18,7 @@
 #include <string>
 
 #include "launch.h"
+#include "bc_map.h"
 #include "sweep3.cuh"
 
 using namespace clawcuda;
@@ -410,6 +411,28 @@ __device__ void ctl_end_body(StepCtl* ctl, double* log) {
 
 __global__ void ctl_end_kernel(StepCtl* ctl, double* log) { ctl_end_body(ctl, log); }
 
+// Both passes in ONE launch (bc_map.h: the x-then-y fill as an index map; one thread per ghost-frame cell and component;
+// no thread reads a cell that another one writes).  Config 1 (200^2 acoustics), per step attempt: 18.8 us with the two
+// launches of bc_x2 / bc_y2, 16.3 us with this one (profiles/r02_zb).  Folding the attempt's control step into this
+// launch as well (every CTA evaluates the decision of the previous attempt on a private copy, the last CTA to finish
+// publishes it: two launches per attempt) was measured SLOWER, 18.0 us -- the chain "read the control block -> fill ->
+// fence -> ticket -> publish" is four dependent round trips to L2 inside one small kernel -- and was dropped.
+struct BcXY { int lo[2], up[2], lo_on[2], up_on[2], reflect[2]; BcState bx, by; };
+__global__ void bc_xy2(ArrSel sel, int ncomp, int mx, int my, int pitch, long long plane, BcXY b) {
+  double* q = sel_array(sel);
+  if (q == nullptr) return;
+  const long long ncell = 4LL * (my + 4) + 4LL * mx;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int i, j;
+  if (idx >= ncell * ncomp || !bc_frame_cell(idx % ncell, mx, my, i, j)) return;
+  const int m = (int)(idx / ncell);
+  double* qm = q + m * plane;
+  bool wrote;
+  const double v = bc_xy_value(qm, pitch, i, j, mx, my, b.lo, b.up, b.lo_on, b.up_on, m == b.reflect[0], m == b.reflect[1],
+                               b.bx.lo[m & 7], b.bx.up[m & 7], b.by.lo[m & 7], b.by.up[m & 7], wrote);
+  if (wrote) qm[(long long)j * pitch + i] = v;
+}
+
 // ---------------------------------------------------------------------------------------
 // Peer-memory transport.  Mailbox of a rank (unsigned 64-bit words, device memory, mapped by every other rank):
 //   [0 .. 256)    CFL slots  [parity][writer rank] = (bits of the writer's CFL number, tag)
@@ -701,8 +724,23 @@ int fill_ghosts_array(claw_solver* h, ArrSel arr, int ncomp, const int* lo, cons
     CK(h, cudaGetLastError());
     return 0;
   }
-  // (one launch of a single CTA doing the x strips, a barrier, then the y strips was measured on the 200^2 acoustics
-  // problem: 27.6 us per step against 23.4 us with the two launches below, profiles/r02_t)
+  // CLAW_BC_TWO_PASS=1: the ghost fill as two launches, x strips then y strips (A/B and a second implementation for
+  // the parity tests); default: one launch through the composed index map
+  static const bool two_pass = getenv("CLAW_BC_TWO_PASS") && atoi(getenv("CLAW_BC_TWO_PASS")) != 0;
+  // (a face reads interior cells only when the grid has at least two cells across: below that, keep the two passes)
+  if (!two_pass && g.n[0] >= 2 && g.n[1] >= 2) {
+    BcXY b{};
+    for (int d = 0; d < 2; ++d) {
+      b.lo[d] = lo[d]; b.up[d] = up[d]; b.lo_on[d] = h->on_lower[d]; b.up_on[d] = h->on_upper[d];
+      b.reflect[d] = is_q ? h->reflect_index[d] : -1;     // only consulted by the BC.wall branches (solver.py:464-473)
+    }
+    b.bx = bc_state_of(h, 0); b.by = bc_state_of(h, 1);
+    const long long n = (4LL * g.nt[1] + 4LL * g.n[0]) * ncomp;
+    bc_xy2<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(arr, ncomp, g.n[0], g.n[1], g.pitch, g.plane, b);
+    ++h->launches;
+    CK(h, cudaGetLastError());
+    return 0;
+  }
   {
     // the negation flag is only consulted by the BC.wall branches (solver.py:464-473)
     const int refl = is_q ? h->reflect_index[0] : -1;

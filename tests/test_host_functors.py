@@ -392,3 +392,70 @@ def test_device_functor_source_matches_oracle_rp3(hostlib3, name, ixyz, icoor):
     for a, b, what in pairs:
         assert np.isfinite(b).all(), (name, what)
         assert _same(a, b, L.mode), (name, L.mode, ixyz, icoor, what, float(np.max(np.abs(a - b))))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# One-launch ghost fill (clawpack_b200/csrc/bc_map.h, kernel bc_xy2): the index map against the reference's slicing order
+# ---------------------------------------------------------------------------------------------------------------
+def _bc_two_pass(q, lo, up, lo_on, up_on, reflect, fixed):
+    """Solver._bc_lower / _bc_upper (pyclaw/src/pyclaw/solver.py:439-519) dimension by dimension, x first; q is
+    (ncomp, my+4, mx+4) [row-major image of the SoA planes]; type 4 = fixed state (the device form of BC.custom)."""
+    q = q.copy()
+    for d in (0, 1):
+        a = np.moveaxis(q, 2 - d, 0)            # a[k, ...]: k along dimension d
+        n = a.shape[0] - 4
+        for side in (0, 1):
+            t = (lo, up)[side][d]
+            on = (lo_on, up_on)[side][d]
+            other_on = (up_on, lo_on)[side][d]
+            if not on:
+                continue
+            for g in range(2):
+                k = g if side == 0 else n + 2 + g
+                if t == 1:
+                    a[k] = a[2] if side == 0 else a[n + 1]
+                elif t == 2:
+                    if other_on:
+                        a[k] = a[n + k] if side == 0 else a[k - n]
+                elif t == 3:
+                    src = 3 - k if side == 0 else 2 * n + 3 - k
+                    a[k] = a[src]
+                    if reflect[d] >= 0:
+                        a[k, reflect[d]] = -a[src, reflect[d]]          # a[k, m, ...]: the component axis stays second
+                elif t == 4:
+                    for m in range(q.shape[0]):
+                        a[k, m] = fixed[d][side][m]
+    return q
+
+
+def test_one_launch_ghost_fill_map_matches_two_passes(tmp_path_factory):
+    src = os.path.join(HERE, 'host_functors', 'bc_map_host.cpp')
+    L = _build(tmp_path_factory, src, 'bcmap', 'strict')
+    ip = ctypes.POINTER(ctypes.c_int)
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.hostfun_bc_xy2.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [ip] * 5 + [dp] * 4
+    L.hostfun_bc_xy2.restype = ctypes.c_int
+    rng = np.random.default_rng(5)
+    ncase = 0
+    for mx, my in ((7, 5), (4, 9), (2, 2), (13, 2)):       # (a face reads interior cells only from 2 cells on)
+        for _ in range(60):
+            lo = rng.integers(0, 5, 2).astype(np.int32)
+            up = rng.integers(0, 5, 2).astype(np.int32)
+            lo_on = (rng.random(2) < 0.8).astype(np.int32)
+            up_on = (rng.random(2) < 0.8).astype(np.int32)
+            ncomp = int(rng.integers(1, 5))
+            reflect = np.array([rng.integers(-1, ncomp), rng.integers(-1, ncomp)], dtype=np.int32)
+            fixed = rng.standard_normal((2, 2, 8))
+            q0 = rng.standard_normal((ncomp, my + 4, mx + 4))
+            want = _bc_two_pass(q0, lo, up, lo_on, up_on, reflect, fixed)
+            got = np.ascontiguousarray(q0.copy())
+            ia = lambda a: a.ctypes.data_as(ip)
+            da = lambda a: np.ascontiguousarray(a).ctypes.data_as(dp)
+            xlo, xup, ylo, yup = (np.ascontiguousarray(fixed[0, 0]), np.ascontiguousarray(fixed[0, 1]),
+                                  np.ascontiguousarray(fixed[1, 0]), np.ascontiguousarray(fixed[1, 1]))
+            rc = L.hostfun_bc_xy2(got.ctypes.data_as(dp), ncomp, mx, my, ia(lo), ia(up), ia(lo_on), ia(up_on), ia(reflect),
+                                  da(xlo), da(xup), da(ylo), da(yup))
+            assert rc == 0
+            assert np.array_equal(got, want), (mx, my, lo, up, lo_on, up_on, reflect)
+            ncase += 1
+    assert ncase == 240
