@@ -338,7 +338,7 @@ def sass_identity(kernel_pattern, obj):
         return None, None
 
 
-NCU_KEYS = {'c2': ('sweep2_unsplit_wsINS0_15RpEuler4Wave2DTILi3ELi0EEELi1ELi8ELi71ELi1ELi8E', 'sweep_inst_%s.o'),
+NCU_KEYS = {'c2': ('sweep2_unsplit_wsINS0_15RpEuler4Wave2DTILi3ELi0EEELi1ELi8ELi71ELi1ELi8ELi0E', 'sweep_inst_%s.o'),
             'c3': ('sweep2_split_wsINS0_18RpShallowRoeEfix2DELi1ELi16ELi1ELi1ELi4ELi4E', 'sweep_inst_%s.o'),
             'c1': ('sweep2_split_wsINS0_13RpAcoustics2DELi1ELi16ELi1ELi1ELi4ELi4E', 'sweep_inst_%s.o'),
             'c4': ('sweep3_marchINS0_15RpVcAcoustics3DELi2ELi32ELi8ELi1ELi41E', 'sweep3_inst_%s.o')}

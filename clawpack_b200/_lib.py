@@ -91,6 +91,8 @@ def _declare(L):
         'claw_host_alloc': (i, [ctypes.POINTER(vp), sz]),
         'claw_host_free': (i, [vp]),
         'claw_measure_fp64_peak': (i, [i, c_double_p]),
+        'claw_rp_plugin_load': (i, [ctypes.c_char_p, c_int_p]),
+        'claw_rp_plugin_info': (i, [i, c_int_p]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

@@ -16,6 +16,7 @@
 #include <dlfcn.h>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "launch.h"
 #include "bc_map.h"
@@ -760,6 +761,21 @@ int fill_ghosts_array(claw_solver* h, ArrSel arr, int ncomp, const int* lo, cons
   return 0;
 }
 
+// Riemann-solver plug-ins (rp_plugin.cu): shared objects registered by claw_rp_plugin_load
+struct RpPlugin {
+  std::string path;
+  void* dl = nullptr;
+  int (*launch2)(int, int, void*, int, int, void*, void*) = nullptr;
+  int meqn = 0, mwaves = 0, maux = 0, no_transverse = 0;
+};
+std::mutex g_plugin_mutex;
+std::vector<RpPlugin> g_plugins;               // rp_id = CLAW_RP_PLUGIN_BASE + index; entries are never removed
+const RpPlugin* plugin_of(int rp_id) {
+  std::lock_guard<std::mutex> lock(g_plugin_mutex);
+  const int k = rp_id - CLAW_RP_PLUGIN_BASE;
+  return (k >= 0 && k < (int)g_plugins.size()) ? &g_plugins[(size_t)k] : nullptr;
+}
+
 int launch_step2(claw_solver* h, double dx, double dy, double dt, int kind, int do_x, int do_y,
                  const double* src, double* dst, int j0 = 0, int j1 = 0, cudaStream_t stream_override = nullptr,
                  bool under_ctl = false) {
@@ -791,9 +807,17 @@ int launch_step2(claw_solver* h, double dx, double dy, double dt, int kind, int 
     P.hot = h->hot; P.hot_cap = h->hot_cap; P.hot_tiles = h->hot_tiles;
     P.hot_epoch = h->hot_epoch++;
   }
-  cudaError_t e = (h->mode == CLAW_MODE_FAST)
-                      ? fast::launch_sweep2(h->rp_id, kind, P, h->seg_rows, h->num_sms, st, &h->last_launch)
-                      : strict::launch_sweep2(h->rp_id, kind, P, h->seg_rows, h->num_sms, st, &h->last_launch);
+  cudaError_t e;
+  if (h->rp_id >= CLAW_RP_PLUGIN_BASE) {               // user-supplied Riemann solver: its own instantiation of the kernels
+    const RpPlugin* p = plugin_of(h->rp_id);
+    if (!p) return fail(h, 30, "rp_id %d is not a registered Riemann-solver plug-in", h->rp_id);
+    e = (cudaError_t)p->launch2(h->mode == CLAW_MODE_FAST ? 1 : 0, kind, &P, h->seg_rows, h->num_sms, (void*)st,
+                                &h->last_launch);
+  } else {
+    e = (h->mode == CLAW_MODE_FAST)
+            ? fast::launch_sweep2(h->rp_id, kind, P, h->seg_rows, h->num_sms, st, &h->last_launch)
+            : strict::launch_sweep2(h->rp_id, kind, P, h->seg_rows, h->num_sms, st, &h->last_launch);
+  }
   ++h->launches;
   if (e != cudaSuccess) return fail(h, 100 + (int)e, "sweep kernel launch failed: %s", cudaGetErrorString(e));
   return 0;
@@ -867,6 +891,7 @@ int launch_step(claw_solver* h, const double* delta, double dt, const double* sr
 
 // aux planes read by the 2-D Riemann solvers (rp2.cuh: none; rp2_aux.cuh: RP::MAUX); -1 = unknown id
 int rp2_aux_planes(int rp_id) {
+  if (rp_id >= CLAW_RP_PLUGIN_BASE) { const RpPlugin* p = plugin_of(rp_id); return p ? p->maux : -1; }
   switch (rp_id) {
     case 1: case 2: case 3: case 4: case 9: case 11: case 12: case 16: case 18: return 0;
     case 7: return 2;      // vc_acoustics_2D: density, sound speed
@@ -892,6 +917,15 @@ int validate_config(claw_solver* h) {
       return fail(h, 31, "capacity functions are only implemented for the aux-reading 2-D solvers (rp_id %d reads none)", h->rp_id);
     if (need_aux == 0 && h->use_fwave)
       return fail(h, 32, "rp_id %d is not an f-wave solver", h->rp_id);
+    if (h->rp_id >= CLAW_RP_PLUGIN_BASE) {
+      const RpPlugin* p = plugin_of(h->rp_id);
+      if (p->meqn != h->meqn || p->mwaves != h->mwaves)
+        return fail(h, 37, "Riemann-solver plug-in %s solves %d equations with %d waves, the solver was created with "
+                           "num_eqn=%d, num_waves=%d", p->path.c_str(), p->meqn, p->mwaves, h->meqn, h->mwaves);
+      if (p->no_transverse && h->method[2] > 0)
+        return fail(h, 36, "Riemann-solver plug-in %s has no transverse solver: transverse_waves must be 0 or the step "
+                           "dimensionally split", p->path.c_str());
+    }
     if ((h->rp_id == 11 || h->rp_id == 12 || h->rp_id == 14 || h->rp_id == 18 || h->rp_id == 20) && h->method[2] > 0)
       return fail(h, 36, "rp_id %d has no usable transverse Riemann solver (rpt2_dummy.f90; rpt2_shallow_bathymetry_fwave "
                          "reads an unassigned value): transverse_waves must be 0 or the step dimensionally split", h->rp_id);
@@ -939,6 +973,51 @@ int claw_device_count(void) {
   return n;
 }
 
+int claw_rp_plugin_load(const char* path, int* rp_id) {
+  if (!path || !rp_id) return fail(nullptr, 1, "claw_rp_plugin_load: NULL argument");
+  std::lock_guard<std::mutex> lock(g_plugin_mutex);
+  for (size_t k = 0; k < g_plugins.size(); ++k)
+    if (g_plugins[k].path == path) { *rp_id = CLAW_RP_PLUGIN_BASE + (int)k; return 0; }
+  void* dl = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!dl) return fail(nullptr, 60, "claw_rp_plugin_load: %s", dlerror());
+  auto abi = reinterpret_cast<int (*)(void)>(dlsym(dl, "claw_rp_plugin_abi"));
+  auto info = reinterpret_cast<void (*)(int*)>(dlsym(dl, "claw_rp_plugin_info"));
+  auto launch2 = reinterpret_cast<int (*)(int, int, void*, int, int, void*, void*)>(dlsym(dl, "claw_rp_plugin_launch2"));
+  if (!abi || !info || !launch2) {
+    dlclose(dl);
+    return fail(nullptr, 61, "claw_rp_plugin_load: %s does not export claw_rp_plugin_abi / _info / _launch2 "
+                             "(compile clawpack_b200/csrc/rp_plugin.cu against your functor)", path);
+  }
+  int v[6] = {0, 0, 0, 0, 0, 0};
+  info(v);
+  if (abi() != CLAW_PLUGIN_ABI || v[5] != (int)sizeof(Sweep2Params)) {
+    const int got = abi();
+    dlclose(dl);
+    return fail(nullptr, 62, "claw_rp_plugin_load: %s was compiled against layout version %d (Sweep2Params %d bytes), this "
+                             "library has version %d (%d bytes): recompile the plug-in", path, got, v[5], CLAW_PLUGIN_ABI,
+                (int)sizeof(Sweep2Params));
+  }
+  if (v[0] != 2 || v[1] < 1 || v[1] > 8 || v[2] < 1 || v[2] > 8 || v[3] < 0) {
+    dlclose(dl);
+    return fail(nullptr, 63, "claw_rp_plugin_load: %s reports num_dim=%d, meqn=%d, mwaves=%d, maux=%d (2-D solvers with "
+                             "1..8 equations and waves are supported)", path, v[0], v[1], v[2], v[3]);
+  }
+  RpPlugin p;
+  p.path = path; p.dl = dl; p.launch2 = launch2;
+  p.meqn = v[1]; p.mwaves = v[2]; p.maux = v[3]; p.no_transverse = v[4];
+  g_plugins.push_back(p);
+  *rp_id = CLAW_RP_PLUGIN_BASE + (int)g_plugins.size() - 1;
+  return 0;
+}
+
+int claw_rp_plugin_info(int rp_id, int* info5) {
+  if (!info5) return fail(nullptr, 1, "claw_rp_plugin_info: NULL argument");
+  const RpPlugin* p = plugin_of(rp_id);
+  if (!p) return fail(nullptr, 30, "rp_id %d is not a registered Riemann-solver plug-in", rp_id);
+  info5[0] = 2; info5[1] = p->meqn; info5[2] = p->mwaves; info5[3] = p->maux; info5[4] = p->no_transverse;
+  return 0;
+}
+
 int claw_create(claw_solver** out, int ndim, int rp_id, int meqn, int mwaves, int maux, const int* n, int num_ghost,
                 int device, void* stream) {
   if (!out) return fail(nullptr, 1, "claw_create: out is NULL");
@@ -950,10 +1029,18 @@ int claw_create(claw_solver** out, int ndim, int rp_id, int meqn, int mwaves, in
   static const int k_meqn[] = {0, 1, 3, 4, 3, 4, 5, 3, 1, 5, 3, 4, 3, 3, 3, 1, 1, 1, 1, 5, 2},
                    k_mwaves[] = {0, 1, 2, 4, 3, 2, 3, 2, 1, 5, 2, 2, 2, 2, 3, 1, 1, 1, 1, 4, 1},
                    k_ndim[] = {0, 2, 2, 2, 2, 3, 3, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 3, 2, 2, 2};
+  if (rp_id >= CLAW_RP_PLUGIN_BASE) {                    // user-supplied solver (claw_rp_plugin_load)
+    const RpPlugin* p = plugin_of(rp_id);
+    if (!p) return fail(nullptr, 5, "claw_create: rp_id %d is not a registered Riemann-solver plug-in", rp_id);
+    if (p->meqn != meqn || p->mwaves != mwaves || ndim != 2)
+      return fail(nullptr, 6, "claw_create: plug-in %s expects ndim=2 meqn=%d mwaves=%d (got %d, %d, %d)", p->path.c_str(),
+                  p->meqn, p->mwaves, ndim, meqn, mwaves);
+  } else {
   if (rp_id < 1 || rp_id > 20) return fail(nullptr, 5, "claw_create: unknown rp_id %d", rp_id);
   if (k_meqn[rp_id] != meqn || k_mwaves[rp_id] != mwaves || k_ndim[rp_id] != ndim)
     return fail(nullptr, 6, "claw_create: rp_id %d expects ndim=%d meqn=%d mwaves=%d (got %d, %d, %d)", rp_id,
                 k_ndim[rp_id], k_meqn[rp_id], k_mwaves[rp_id], ndim, meqn, mwaves);
+  }
   for (int d = 0; d < ndim; ++d)
     if (n[d] < 1) return fail(nullptr, 7, "claw_create: n[%d] = %d", d, n[d]);
   int ndev = claw_device_count();

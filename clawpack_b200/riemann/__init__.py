@@ -55,3 +55,4 @@ from . import acoustics_2D_constants, advection_2D_constants, euler_4wave_2D_con
 from . import shallow_roe_with_efix_2D_constants, vc_acoustics_3D_constants             # noqa: E402,F401
 from . import euler_3D_constants, vc_acoustics_2D_constants, vc_advection_2D_constants   # noqa: E402,F401
 from . import euler_5wave_2D_constants                                                   # noqa: E402,F401
+from .plugin import build_cuda_solver, compile_cuda_solver, load_cuda_solver      # noqa: E402,F401

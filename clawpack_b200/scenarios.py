@@ -862,7 +862,8 @@ def make_claw(sc, kernel_language='CUDA', pyclaw=None, **solver_kw):
     from clawpack_b200 import riemann
     ndim = len(sc['num_cells'])
     Solver = {1: pyclaw.ClawSolver1D, 2: pyclaw.ClawSolver2D, 3: pyclaw.ClawSolver3D}[ndim]
-    solver = Solver(getattr(riemann, sc['rp']))
+    # 'rp_object': a solver object that is not one of clawpack_b200.riemann's (a user-compiled CUDA plug-in)
+    solver = Solver(sc['rp_object'] if sc.get('rp_object') is not None else getattr(riemann, sc['rp']))
     solver.kernel_language = kernel_language
     solver.limiters = sc['limiters']
     solver.order = sc['order']

@@ -27,7 +27,7 @@ def _count(c, pred):
 
 def test_headline_euler_kernel_shape(fast_kernels):
     """sweep2_unsplit_ws<RpEuler4Wave2DT<3>,1,8,MC|spec|cp.async ring,QD=8> (fast): the kernel bench.py times."""
-    names = [k for k in fast_kernels if 'sweep2_unsplit_wsINS0_15RpEuler4Wave2DTILi3ELi0EEELi1ELi8ELi71ELi1ELi8E' in k]
+    names = [k for k in fast_kernels if 'sweep2_unsplit_wsINS0_15RpEuler4Wave2DTILi3ELi0EEELi1ELi8ELi71ELi1ELi8ELi0E' in k]
     assert len(names) == 1, names
     c = sass_mix.mix(fast_kernels[names[0]])
     n = sum(c.values())
@@ -46,7 +46,7 @@ def test_headline_euler_kernel_shape(fast_kernels):
 
 def test_no_fast_sweep_kernel_of_the_baseline_configs_spills(fast_kernels):
     """Default kernels of BASELINE configs 2/5 (Euler unsplit), 3 (shallow split) and 1 (acoustics split)."""
-    for pat in ('sweep2_unsplit_wsINS0_15RpEuler4Wave2DTILi3ELi0EEELi1ELi8ELi71ELi1ELi8E',
+    for pat in ('sweep2_unsplit_wsINS0_15RpEuler4Wave2DTILi3ELi0EEELi1ELi8ELi71ELi1ELi8ELi0E',
                 'sweep2_split_wsINS0_18RpShallowRoeEfix2DELi1ELi16ELi1ELi1ELi4E',
                 'sweep2_split_wsINS0_13RpAcoustics2D'):
         names = [k for k in fast_kernels if pat in k]
@@ -82,3 +82,15 @@ def test_specialised_3d_kernels_are_smaller_and_spill_free():
         assert len(k[s[0]]) < 0.82 * len(k[g[0]]), (gen, len(k[g[0]]), len(k[s[0]]))
         c = sass_mix.mix(k[s[0]])
         assert _count(c, lambda x: x.split('.')[0] in ('LDL', 'STL')) == 0, spec
+
+
+def test_tma_ring_variant_uses_bulk_copies_and_mbarriers(fast_kernels):
+    """CLAW_VARIANT=91 (sweep2_unsplit_ws<..., TMA=1>): the row ring is fed by cp.async.bulk (UBLKCP) with mbarrier
+    completion (SYNCS); the default kernel has neither (measured slower on B200)."""
+    tma = [k for k in fast_kernels if 'RpEuler4Wave2DTILi3ELi0EEELi1ELi8ELi71ELi1ELi8ELi1E' in k]
+    dflt = [k for k in fast_kernels if 'RpEuler4Wave2DTILi3ELi0EEELi1ELi8ELi71ELi1ELi8ELi0E' in k]
+    assert len(tma) == 1 and len(dflt) == 1
+    c = sass_mix.mix(fast_kernels[tma[0]])
+    assert _count(c, lambda k: k.startswith('UBLKCP')) >= 4 and _count(c, lambda k: k.startswith('SYNCS')) >= 2
+    c = sass_mix.mix(fast_kernels[dflt[0]])
+    assert _count(c, lambda k: k.startswith('UBLKCP')) == 0 and _count(c, lambda k: k.startswith('LDGSTS')) >= 4
