@@ -7,14 +7,27 @@
 namespace clawcuda {
 namespace CLAW_NS {
 
-static int pick_seg(int len, long long tiles, int num_sms) {
-  // enough CTAs for ~2 waves, segments not shorter than 16 cells (each pays 2-4 warm-up steps)
-  long long nseg = (2LL * num_sms + tiles - 1) / tiles;
-  if (nseg < 1) nseg = 1;
-  int seg = (int)((len + nseg - 1) / nseg);
-  if (seg < 16) seg = 16;
-  if (seg > len) seg = len;
-  return seg < 1 ? 1 : seg;
+// Cells per march segment.  A launch runs tiles * nseg CTAs on `slots` resident ones: tiles * nseg / slots rounds of
+// (len / nseg + warm) march steps each, plus on average half a round at the ragged end (warm = the cost of a segment's
+// redundant warm-up steps in full steps: 2 planes for the x-sweep, ~1 for the marches, whose warm-up steps skip the
+// transverse solves).  The nseg in 1..32 with the fewest steps wins; segments are not shorter than 16 cells.  Measured
+// at 512^3 (profiles/r02_ze): one segment per tile 33.1 ms per step, 256-cell segments 31.3, 128 (this model's choice)
+// 30.5, 64 30.7.
+static int pick_seg(int len, long long tiles, int slots, int warm) {
+  static const int forced = getenv("CLAW_SEG3") ? atoi(getenv("CLAW_SEG3")) : 0;      // A/B: cells per segment
+  if (forced > 0) return forced < len ? forced : len;
+  if (slots < 1) slots = 1;
+  double best_cost = -1.0;
+  int best_seg = len;
+  for (int nseg = 1; nseg <= 32; ++nseg) {
+    const int seg = (len + nseg - 1) / nseg;
+    if (nseg > 1 && seg < 16) break;
+    const long long ns = (len + seg - 1) / seg;
+    const double rounds = (double)(tiles * ns) / slots;
+    const double cost = ((rounds < 1.0 ? 1.0 : rounds) + 0.5) * (seg + warm);
+    if (best_cost < 0.0 || cost < best_cost) { best_cost = cost; best_seg = seg; }
+  }
+  return best_seg < 1 ? 1 : best_seg;
 }
 
 template <class RP, int BY, int MINB, int SPEC = 0>
@@ -32,7 +45,7 @@ static cudaError_t launch_x(Sweep3Params& P, int num_sms, cudaStream_t st, Launc
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
   if (occ < 1) occ = 1;
-  P.seg = pick_seg(len, (long long)gx * gy, num_sms * occ);
+  P.seg = pick_seg(len, (long long)gx * gy, num_sms * occ, 2);
   dim3 grid(gx, gy, (len + P.seg - 1) / P.seg), block(32, BY);
   kern<<<grid, block, smem, st>>>(P);
   if (info) { info->grid_x = grid.x; info->grid_y = grid.y * grid.z; info->block = NT; info->smem_bytes = smem; info->ctas_per_sm = occ; }
@@ -55,7 +68,7 @@ static cudaError_t launch_march(Sweep3Params& P, int num_sms, cudaStream_t st, L
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
   if (occ < 1) occ = 1;
-  P.seg = pick_seg(len, (long long)gx * gy, num_sms * occ);
+  P.seg = pick_seg(len, (long long)gx * gy, num_sms * occ, 1);
   dim3 grid(gx, gy, (len + P.seg - 1) / P.seg), block(BX, BY);
   kern<<<grid, block, smem, st>>>(P);
   if (info) { info->grid_x = grid.x; info->grid_y = grid.y * grid.z; info->block = NT; info->smem_bytes = smem; info->ctas_per_sm = occ; }
@@ -88,6 +101,9 @@ cudaError_t launch_sweep3(int rp_id, int dir, Sweep3Params& P, int num_sms, cuda
       // every wave), x-sweep as two 32x6 CTAs per SM (168 registers, no spills).  Measured on B200 at 512^3
       // (profiles/r02_b_c4_variants.jsonl): 49.6 ms generic -> 35.4 ms specialised -> 32.4 ms with the 32x6 x-sweep.
       if (variant != 1 && headline_method3<2>(P, 4)) {
+        // (two copies of the gadd / hadd exchange area alternating by step parity, so that one of the two barriers per
+        // march step goes away, were measured at 512^3: marches 12.3 against 11.8 ms -- the 213 KB of shared memory leave
+        // the 3x3 aux neighbourhood fetches hardly any L1 --, x-sweep within 1 %: dropped, profiles/r02_zd, r02_ze)
         if (dir == 0) return launch_x<RpVcAcoustics3D, 6, 2, 41>(P, num_sms, st, info);
         return launch_dir<RpVcAcoustics3D, 8, 1, 41>(dir, P, num_sms, st, info);
       }
