@@ -112,6 +112,7 @@ struct claw_solver {
   uint64_t cfg_epoch = 0, graph_epoch = 0;
   double graph_delta[3] = {0, 0, 0};
   int graph_fill = -1;
+  bool aux_ghosts_valid = false;     // the ghost cells of the (static) aux array have been filled since it last changed
   int use_graph = 1;
 };
 
@@ -275,10 +276,9 @@ __global__ void bc_dim3(ArrSel sel, int ncomp, int n_d, long long stride_d, int 
                         int reflect, BcState bs) {
   double* q = sel_array(sel);
   if (q == nullptr) return;
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long per = (long long)ext_a * ext_b;
-  if (idx >= per * ncomp) return;
-  const int a = (int)(idx % ext_a), b = (int)((idx / ext_a) % ext_b), m = (int)(idx / per);
+  // grid: x over the faster transverse dimension a (adjacent threads = adjacent a), y = b, z = component
+  const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y, m = blockIdx.z;
+  if (a >= ext_a) return;
   bc_fill_pair(q + m * plane + a * stride_a + b * stride_b, stride_d, n_d, lo_type, up_type, lo_on != 0, up_on != 0,
                m == reflect, bs.lo[m & 7], bs.up[m & 7]);
 }
@@ -509,6 +509,29 @@ __global__ void peer_barrier_kernel(PeerMail pm, int* status) {
   __syncthreads();
   if (r == 0) { pm.local[MAIL_TAGS + 1] = tag; if (!s_ok) *status = 1; }
 }
+// The same barrier inside a step attempt (3-D dimension-split steps under the peer-memory transport, see ctl_enqueue_end)
+__global__ void peer_barrier_ctl_kernel(StepCtl* ctl, PeerMail pm) {
+  if (ctl->done) return;                                   // identical on every rank: nobody waits
+  const int r = threadIdx.x;
+  const unsigned long long tag = pm.local[MAIL_TAGS + 1] + 1ull;
+  __shared__ int s_ok;
+  if (r == 0) s_ok = 1;
+  __syncthreads();
+  if (r < pm.nranks) {
+    __threadfence_system();
+    volatile unsigned long long* dst = pm.remote[r] + MAIL_BAR + pm.rank;
+    *dst = tag;
+    volatile unsigned long long* src = pm.local + MAIL_BAR + r;
+    long long spins = 0;
+    while (*src < tag) { if (++spins > PEER_SPIN_LIMIT) { s_ok = 0; break; } }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (r == 0) {
+    pm.local[MAIL_TAGS + 1] = tag;
+    if (!s_ok) { ctl->error = 3; ctl->done = 1; }          // a peer never answered
+  }
+}
 // ncomp runs of `len` doubles from my array into a neighbour's (both selected by the same role under the same StepCtl:
 // the current-buffer index is identical on every rank)
 __global__ void peer_copy_runs(ArrSel src_sel, long long src_off, long long src_stride, ArrSel dst_sel, long long dst_off,
@@ -517,10 +540,18 @@ __global__ void peer_copy_runs(ArrSel src_sel, long long src_off, long long src_
   double* dst = sel_array(dst_sel);
   if (src == nullptr || dst == nullptr) return;
   src += src_off; dst += dst_off;
-  const long long n = len * ncomp;
-  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
-    const long long m = k / len, i = k % len;
-    dst[m * dst_stride + i] = src[m * src_stride + i];
+  // blockIdx.y = component; 16-byte accesses when the runs allow it (row pitches are multiples of 16 doubles, so they
+  // do for every array this library allocates): the stores cross NVLink
+  const int m = blockIdx.y;
+  const double* s = src + m * src_stride;
+  double* d = dst + m * dst_stride;
+  const long long stride = (long long)gridDim.x * blockDim.x, k0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if ((len & 1) == 0 && ((reinterpret_cast<unsigned long long>(s) | reinterpret_cast<unsigned long long>(d)) & 15ull) == 0) {
+    const double2* s2 = reinterpret_cast<const double2*>(s);
+    double2* d2 = reinterpret_cast<double2*>(d);
+    for (long long k = k0; k < len / 2; k += stride) d2[k] = s2[k];
+  } else {
+    for (long long k = k0; k < len; k += stride) d[k] = s[k];
   }
 }
 
@@ -714,10 +745,13 @@ int fill_ghosts_array(claw_solver* h, ArrSel arr, int ncomp, const int* lo, cons
   if (g.ndim == 3) {
     const long long st[3] = {1, (long long)g.pitch, g.kstride};
     for (int d = 0; d < 3; ++d) {
-      const int a = (d + 1) % 3, b = (d + 2) % 3;
+      // a = the transverse dimension with the smaller stride (adjacent threads touch adjacent cells where the face
+      // allows it: y- and z-faces are contiguous in x; an x-face thread owns the 2 x 2 ghost cells of its pencil)
+      const int a = (d == 0) ? 1 : 0, b = (d == 2) ? 1 : 2;
       const int refl = is_q ? h->reflect_index[d] : -1;
-      const long long n = (long long)g.nt[a] * g.nt[b] * ncomp;
-      bc_dim3<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(arr, ncomp, g.n[d], st[d], g.nt[a], st[a], g.nt[b],
+      const dim3 grid((unsigned)((g.nt[a] + 127) / 128), (unsigned)g.nt[b], (unsigned)ncomp);
+      if (g.nt[b] > 65535) return fail(h, 23, "3-D ghost fill: more than 65535 cells across");
+      bc_dim3<<<grid, 128, 0, h->stream>>>(arr, ncomp, g.n[d], st[d], g.nt[a], st[a], g.nt[b],
                                                                   st[b], g.plane, lo[d], up[d], h->on_lower[d],
                                                                   h->on_upper[d], refl, bc_state_of(h, d));
       ++h->launches;
@@ -765,8 +799,9 @@ int fill_ghosts_array(claw_solver* h, ArrSel arr, int ncomp, const int* lo, cons
 struct RpPlugin {
   std::string path;
   void* dl = nullptr;
-  int (*launch2)(int, int, void*, int, int, void*, void*) = nullptr;
-  int meqn = 0, mwaves = 0, maux = 0, no_transverse = 0;
+  int (*launch2)(int, int, void*, int, int, void*, void*) = nullptr;      // 2-D solvers
+  int (*launch3)(int, int, void*, int, void*, void*) = nullptr;           // 3-D solvers
+  int ndim = 2, meqn = 0, mwaves = 0, maux = 0, no_transverse = 0;
 };
 std::mutex g_plugin_mutex;
 std::vector<RpPlugin> g_plugins;               // rp_id = CLAW_RP_PLUGIN_BASE + index; entries are never removed
@@ -810,7 +845,7 @@ int launch_step2(claw_solver* h, double dx, double dy, double dt, int kind, int 
   cudaError_t e;
   if (h->rp_id >= CLAW_RP_PLUGIN_BASE) {               // user-supplied Riemann solver: its own instantiation of the kernels
     const RpPlugin* p = plugin_of(h->rp_id);
-    if (!p) return fail(h, 30, "rp_id %d is not a registered Riemann-solver plug-in", h->rp_id);
+    if (!p || !p->launch2) return fail(h, 30, "rp_id %d is not a registered 2-D Riemann-solver plug-in", h->rp_id);
     e = (cudaError_t)p->launch2(h->mode == CLAW_MODE_FAST ? 1 : 0, kind, &P, h->seg_rows, h->num_sms, (void*)st,
                                 &h->last_launch);
   } else {
@@ -851,9 +886,16 @@ int launch_pass3(claw_solver* h, const double* delta, double dt, int dir, int fi
   P.zlo = (h->method[2] < 0 && !h->on_lower[2]) ? 0 : 1;
   P.zhi = h->g.n[2] + ((h->method[2] < 0 && !h->on_upper[2]) ? 3 : 2);
   for (int k = 0; k < 4; ++k) P.rp.p[k] = h->cparam[k];
-  cudaError_t e = (h->mode == CLAW_MODE_FAST)
-                      ? fast::launch_sweep3(h->rp_id, dir, P, h->num_sms, h->stream, &h->last_launch)
-                      : strict::launch_sweep3(h->rp_id, dir, P, h->num_sms, h->stream, &h->last_launch);
+  cudaError_t e;
+  if (h->rp_id >= CLAW_RP_PLUGIN_BASE) {               // user-supplied Riemann solver
+    const RpPlugin* p = plugin_of(h->rp_id);
+    if (!p || !p->launch3) return fail(h, 30, "rp_id %d is not a registered 3-D Riemann-solver plug-in", h->rp_id);
+    e = (cudaError_t)p->launch3(h->mode == CLAW_MODE_FAST ? 1 : 0, dir, &P, h->num_sms, (void*)h->stream, &h->last_launch);
+  } else {
+    e = (h->mode == CLAW_MODE_FAST)
+            ? fast::launch_sweep3(h->rp_id, dir, P, h->num_sms, h->stream, &h->last_launch)
+            : strict::launch_sweep3(h->rp_id, dir, P, h->num_sms, h->stream, &h->last_launch);
+  }
   ++h->launches;
   if (e != cudaSuccess) return fail(h, 100 + (int)e, "3-D sweep kernel launch failed: %s", cudaGetErrorString(e));
   return 0;
@@ -891,7 +933,7 @@ int launch_step(claw_solver* h, const double* delta, double dt, const double* sr
 
 // aux planes read by the 2-D Riemann solvers (rp2.cuh: none; rp2_aux.cuh: RP::MAUX); -1 = unknown id
 int rp2_aux_planes(int rp_id) {
-  if (rp_id >= CLAW_RP_PLUGIN_BASE) { const RpPlugin* p = plugin_of(rp_id); return p ? p->maux : -1; }
+  if (rp_id >= CLAW_RP_PLUGIN_BASE) { const RpPlugin* p = plugin_of(rp_id); return (p && p->ndim == 2) ? p->maux : -1; }
   switch (rp_id) {
     case 1: case 2: case 3: case 4: case 9: case 11: case 12: case 16: case 18: return 0;
     case 7: return 2;      // vc_acoustics_2D: density, sound speed
@@ -936,10 +978,15 @@ int validate_config(claw_solver* h) {
         return fail(h, 35, "limiter id %d of wave family %d is not defined by philim.f90 (0..5)", h->mthlim[mw], mw);
     return 0;
   }
-  if (h->rp_id != 5 && h->rp_id != 6 && h->rp_id != 15 && h->rp_id != 17)
+  const RpPlugin* plug3 = (h->rp_id >= CLAW_RP_PLUGIN_BASE) ? plugin_of(h->rp_id) : nullptr;
+  if (plug3 && plug3->ndim != 3) plug3 = nullptr;
+  if (!plug3 && h->rp_id != 5 && h->rp_id != 6 && h->rp_id != 15 && h->rp_id != 17)
     return fail(h, 30, "rp_id %d is not a 3-D Riemann solver of this build", h->rp_id);
+  if (plug3 && (plug3->meqn != h->meqn || plug3->mwaves != h->mwaves))
+    return fail(h, 37, "Riemann-solver plug-in %s solves %d equations with %d waves, the solver was created with num_eqn=%d, "
+                       "num_waves=%d", plug3->path.c_str(), plug3->meqn, plug3->mwaves, h->meqn, h->mwaves);
   {
-    const int need_aux = (h->rp_id == 5) ? 2 : (h->rp_id == 17 ? 3 : 0);      // RP::MAUX of rp3.cuh
+    const int need_aux = plug3 ? plug3->maux : (h->rp_id == 5) ? 2 : (h->rp_id == 17 ? 3 : 0);      // RP::MAUX of rp3.cuh
     if (h->maux < need_aux)
       return fail(h, 31, "Riemann solver %d reads %d aux components, the state has num_aux=%d", h->rp_id, need_aux, h->maux);
   }
@@ -983,28 +1030,31 @@ int claw_rp_plugin_load(const char* path, int* rp_id) {
   auto abi = reinterpret_cast<int (*)(void)>(dlsym(dl, "claw_rp_plugin_abi"));
   auto info = reinterpret_cast<void (*)(int*)>(dlsym(dl, "claw_rp_plugin_info"));
   auto launch2 = reinterpret_cast<int (*)(int, int, void*, int, int, void*, void*)>(dlsym(dl, "claw_rp_plugin_launch2"));
-  if (!abi || !info || !launch2) {
+  auto launch3 = reinterpret_cast<int (*)(int, int, void*, int, void*, void*)>(dlsym(dl, "claw_rp_plugin_launch3"));
+  if (!abi || !info || (!launch2 && !launch3)) {
     dlclose(dl);
-    return fail(nullptr, 61, "claw_rp_plugin_load: %s does not export claw_rp_plugin_abi / _info / _launch2 "
+    return fail(nullptr, 61, "claw_rp_plugin_load: %s does not export claw_rp_plugin_abi / _info / _launch2 (or _launch3) "
                              "(compile clawpack_b200/csrc/rp_plugin.cu against your functor)", path);
   }
   int v[6] = {0, 0, 0, 0, 0, 0};
   info(v);
-  if (abi() != CLAW_PLUGIN_ABI || v[5] != (int)sizeof(Sweep2Params)) {
+  const int want_bytes = (v[0] == 3) ? (int)sizeof(Sweep3Params) : (int)sizeof(Sweep2Params);
+  if (abi() != CLAW_PLUGIN_ABI || v[5] != want_bytes) {
     const int got = abi();
     dlclose(dl);
-    return fail(nullptr, 62, "claw_rp_plugin_load: %s was compiled against layout version %d (Sweep2Params %d bytes), this "
-                             "library has version %d (%d bytes): recompile the plug-in", path, got, v[5], CLAW_PLUGIN_ABI,
-                (int)sizeof(Sweep2Params));
+    return fail(nullptr, 62, "claw_rp_plugin_load: %s was compiled against layout version %d (launch parameters %d bytes), "
+                             "this library has version %d (%d bytes): recompile the plug-in", path, got, v[5], CLAW_PLUGIN_ABI,
+                want_bytes);
   }
-  if (v[0] != 2 || v[1] < 1 || v[1] > 8 || v[2] < 1 || v[2] > 8 || v[3] < 0) {
+  if ((v[0] != 2 && v[0] != 3) || (v[0] == 2 && !launch2) || (v[0] == 3 && !launch3) || v[1] < 1 || v[1] > 8 || v[2] < 1 ||
+      v[2] > 8 || v[3] < 0) {
     dlclose(dl);
-    return fail(nullptr, 63, "claw_rp_plugin_load: %s reports num_dim=%d, meqn=%d, mwaves=%d, maux=%d (2-D solvers with "
-                             "1..8 equations and waves are supported)", path, v[0], v[1], v[2], v[3]);
+    return fail(nullptr, 63, "claw_rp_plugin_load: %s reports num_dim=%d, meqn=%d, mwaves=%d, maux=%d (2-D and 3-D solvers "
+                             "with 1..8 equations and waves are supported)", path, v[0], v[1], v[2], v[3]);
   }
   RpPlugin p;
-  p.path = path; p.dl = dl; p.launch2 = launch2;
-  p.meqn = v[1]; p.mwaves = v[2]; p.maux = v[3]; p.no_transverse = v[4];
+  p.path = path; p.dl = dl; p.launch2 = launch2; p.launch3 = launch3;
+  p.ndim = v[0]; p.meqn = v[1]; p.mwaves = v[2]; p.maux = v[3]; p.no_transverse = v[4];
   g_plugins.push_back(p);
   *rp_id = CLAW_RP_PLUGIN_BASE + (int)g_plugins.size() - 1;
   return 0;
@@ -1014,7 +1064,7 @@ int claw_rp_plugin_info(int rp_id, int* info5) {
   if (!info5) return fail(nullptr, 1, "claw_rp_plugin_info: NULL argument");
   const RpPlugin* p = plugin_of(rp_id);
   if (!p) return fail(nullptr, 30, "rp_id %d is not a registered Riemann-solver plug-in", rp_id);
-  info5[0] = 2; info5[1] = p->meqn; info5[2] = p->mwaves; info5[3] = p->maux; info5[4] = p->no_transverse;
+  info5[0] = p->ndim; info5[1] = p->meqn; info5[2] = p->mwaves; info5[3] = p->maux; info5[4] = p->no_transverse;
   return 0;
 }
 
@@ -1032,9 +1082,9 @@ int claw_create(claw_solver** out, int ndim, int rp_id, int meqn, int mwaves, in
   if (rp_id >= CLAW_RP_PLUGIN_BASE) {                    // user-supplied solver (claw_rp_plugin_load)
     const RpPlugin* p = plugin_of(rp_id);
     if (!p) return fail(nullptr, 5, "claw_create: rp_id %d is not a registered Riemann-solver plug-in", rp_id);
-    if (p->meqn != meqn || p->mwaves != mwaves || ndim != 2)
-      return fail(nullptr, 6, "claw_create: plug-in %s expects ndim=2 meqn=%d mwaves=%d (got %d, %d, %d)", p->path.c_str(),
-                  p->meqn, p->mwaves, ndim, meqn, mwaves);
+    if (p->meqn != meqn || p->mwaves != mwaves || ndim != p->ndim)
+      return fail(nullptr, 6, "claw_create: plug-in %s expects ndim=%d meqn=%d mwaves=%d (got %d, %d, %d)", p->path.c_str(),
+                  p->ndim, p->meqn, p->mwaves, ndim, meqn, mwaves);
   } else {
   if (rp_id < 1 || rp_id > 20) return fail(nullptr, 5, "claw_create: unknown rp_id %d", rp_id);
   if (k_meqn[rp_id] != meqn || k_mwaves[rp_id] != mwaves || k_ndim[rp_id] != ndim)
@@ -1126,6 +1176,7 @@ int claw_buffer_sizes(const claw_solver* h, size_t* q_elems, size_t* aux_elems, 
 
 int claw_bind(claw_solver* h, double* d_q0, double* d_q1, double* d_aux, double* d_work) {
   if (check_handle(h)) return 1;
+  h->aux_ghosts_valid = false;
   if (h->owns_buffers) return fail(h, 10, "claw_bind: buffers were already allocated internally");
   if (!d_q0 || !d_q1 || !d_work || (h->maux > 0 && !d_aux)) return fail(h, 11, "claw_bind: NULL buffer");
   h->q[0] = d_q0; h->q[1] = d_q1; h->aux = d_aux; h->work = d_work;
@@ -1154,6 +1205,7 @@ int claw_set_method(claw_solver* h, const int* method7, const int* mthlim, int u
 int claw_set_bc(claw_solver* h, const int* lower, const int* upper, const int* aux_lower, const int* aux_upper,
                 const int* reflect_index) {
   if (check_handle(h)) return 1;
+  h->aux_ghosts_valid = false;
   ++h->cfg_epoch;
   for (int d = 0; d < h->g.ndim; ++d) {
     h->bc_lower[d] = lower[d]; h->bc_upper[d] = upper[d];
@@ -1166,6 +1218,7 @@ int claw_set_bc(claw_solver* h, const int* lower, const int* upper, const int* a
 
 int claw_set_boundary_ownership(claw_solver* h, const int* on_lower, const int* on_upper) {
   if (check_handle(h)) return 1;
+  h->aux_ghosts_valid = false;
   ++h->cfg_epoch;
   for (int d = 0; d < h->g.ndim; ++d) { h->on_lower[d] = on_lower[d]; h->on_upper[d] = on_upper[d]; }
   return 0;
@@ -1256,6 +1309,7 @@ int claw_get_cells(claw_solver* h, int ncells, const int* idx, double* host_out)
 
 int claw_put_aux(claw_solver* h, const double* host_aux) {
   if (check_handle(h)) return 1;
+  h->aux_ghosts_valid = false;
   if (h->maux == 0) return 0;
   if (int rc = ensure_buffers(h)) return rc;
   CK(h, cudaSetDevice(h->device));
@@ -1284,6 +1338,7 @@ int claw_get_qbc(claw_solver* h, double* host_qbc) {
 
 int claw_put_auxbc(claw_solver* h, const double* host_auxbc) {
   if (check_handle(h)) return 1;
+  h->aux_ghosts_valid = false;
   if (h->maux == 0) return 0;
   if (int rc = ensure_buffers(h)) return rc;
   CK(h, cudaSetDevice(h->device));
@@ -1296,8 +1351,12 @@ int claw_apply_bcs(claw_solver* h) {
   if (check_handle(h)) return 1;
   if (int rc = ensure_buffers(h)) return rc;
   CK(h, cudaSetDevice(h->device));
-  if (h->maux > 0)
+  // aux is static between uploads: its ghost cells are filled once after every change (upload, halo exchange, BC change),
+  // not once per step attempt (3 of the 6 ghost-fill launches of a 3-D attempt)
+  if (h->maux > 0 && !h->aux_ghosts_valid) {
     if (int rc = fill_ghosts_array(h, sel_fixed(h->aux), h->maux, h->aux_bc_lower, h->aux_bc_upper, false)) return rc;
+    if (!(h->s_cap != nullptr && h->stream == h->s_cap)) h->aux_ghosts_valid = true;    // (not while a graph is captured)
+  }
   return fill_ghosts_array(h, sel_q(h, 0), h->meqn, h->bc_lower, h->bc_upper, true);
 }
 
@@ -1395,7 +1454,7 @@ int peer_push(claw_solver* h, int role, bool aux) {
     return d;
   };
   const ArrSel src = aux ? sel_fixed(h->aux) : sel_q(h, role);
-  const int blocks = grid_for(len * ncomp, 256);
+  const dim3 blocks(grid_for((len + 1) / 2, 256), ncomp);
   if (h->peer.up >= 0) {        // channel A: my upper interior layers [n, n+ng) -> the upper neighbour's lower ghosts [0, ng)
     peer_copy_runs<<<blocks, 256, 0, h->stream>>>(src, (long long)g.n[last] * layer, g.plane,
                                                   sel_remote(h->peer.up_q, h->peer.up_aux), 0, h->peer.up_plane, len, ncomp);
@@ -1427,6 +1486,14 @@ int ctl_enqueue_end(claw_solver* h) {
   if (h->peer.active) {
     // the rows / planes next to the rank faces of the buffer this attempt wrote go straight into the neighbours' ghost
     // cells of THEIR alternate buffer (it becomes current on every rank together, or is discarded on every rank)
+    // A dimension-split 3-D step (step3ds x 3) passes the WHOLE array through its three buffers, ghost planes included: a
+    // neighbour that is one pass ahead must not write my ghost planes of the alternate buffer before my last pass has
+    // gone over them, nor while my y-sweep still reads them.  All ranks finish their sweeps, then everybody pushes.
+    // (The unsplit kernels and the 2-D ones only ever write interior cells: no barrier there.)
+    if (h->g.ndim == 3 && h->method[2] < 0) {
+      peer_barrier_ctl_kernel<<<1, MAIL_MAXR, 0, h->stream>>>(reinterpret_cast<StepCtl*>(h->work), peer_mail_of(h));
+      ++h->launches;
+    }
     if (int rc = peer_push(h, 1, false)) return rc;
     ctl_end_peer_kernel<<<1, MAIL_MAXR, 0, h->stream>>>(reinterpret_cast<StepCtl*>(h->work), h->work + CTL_WORDS,
                                                        peer_mail_of(h));
@@ -1486,6 +1553,10 @@ int claw_ctl_attempts(claw_solver* h, const double* delta, int n, int fill_ghost
   CK(h, cudaSetDevice(h->device));
   h->ctl_pending = true;
   const int ndim = h->g.ndim;
+  if (fill_ghosts && h->maux > 0 && !h->aux_ghosts_valid) {      // before a graph is captured: it then holds no aux fill
+    if (int rc = fill_ghosts_array(h, sel_fixed(h->aux), h->maux, h->aux_bc_lower, h->aux_bc_upper, false)) return rc;
+    h->aux_ghosts_valid = true;
+  }
   bool graph_ok = h->use_graph && n >= 1;          // (a single attempt too: the graph is captured once per configuration)
   if (graph_ok) {
     bool stale = (h->graph == nullptr) || h->graph_epoch != h->cfg_epoch || h->graph_fill != (fill_ghosts ? 1 : 0);
@@ -1637,6 +1708,7 @@ int claw_halo_pack_aux(claw_solver* h, int side, double* d_buf) {
 }
 int claw_halo_unpack_aux(claw_solver* h, int side, const double* d_buf) {
   if (check_handle(h)) return 1;
+  h->aux_ghosts_valid = false;
   if (h->maux == 0) return 0;
   return halo_move(h, sel_fixed(h->aux), h->maux, side, const_cast<double*>(d_buf), false);
 }
@@ -1654,6 +1726,7 @@ static_assert(sizeof(PeerInfo) == 320, "PeerInfo is exchanged as 320 bytes");
 
 int claw_own_buffers(claw_solver* h) {
   if (check_handle(h)) return 1;
+  h->aux_ghosts_valid = false;
   return ensure_buffers(h);
 }
 
@@ -1750,6 +1823,7 @@ int* peer_status_word(claw_solver* h) {               // a word of the mailbox n
 
 int claw_peer_sync(claw_solver* h, int aux) {
   if (check_handle(h)) return 1;
+  if (aux) h->aux_ghosts_valid = false;
   if (!h->peer.active) return fail(h, 73, "claw_peer_sync: no peers connected");
   CK(h, cudaSetDevice(h->device));
   if (int rc = peer_push(h, 0, aux != 0)) return rc;
@@ -1856,6 +1930,7 @@ int claw_nccl_comm_destroy(void* comm) {
 int claw_halo_exchange(claw_solver* h, void* comm, int send_up_to, int recv_lo_from, int send_lo_to, int recv_up_from,
                        int aux) {
   if (check_handle(h)) return 1;
+  if (aux) h->aux_ghosts_valid = false;
   if (int rc = nccl_need(h)) return rc;
   if (!comm) return fail(h, 298, "claw_halo_exchange: NULL communicator");
   const int ncomp = aux ? h->maux : h->meqn;

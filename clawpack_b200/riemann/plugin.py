@@ -32,9 +32,10 @@ def _stale(out, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_cuda_solver(header, functor, out_dir=None, name=None, force=False):
+def build_cuda_solver(header, functor, out_dir=None, name=None, force=False, num_dim=2):
     """Compile clawpack_b200/csrc/rp_plugin.cu against the functor `functor` defined in `header`; returns the path of
-    the shared object (lib<name>.so in `out_dir`, default: next to the header).  Works without a GPU."""
+    the shared object (lib<name>.so in `out_dir`, default: next to the header).  Works without a GPU.  num_dim=3: a 3-D
+    solver (functor interface of clawpack_b200/csrc/rp3.cuh)."""
     header = os.path.abspath(header)
     out_dir = os.path.abspath(out_dir or os.path.join(os.path.dirname(header), '_build'))
     os.makedirs(out_dir, exist_ok=True)
@@ -44,7 +45,8 @@ def build_cuda_solver(header, functor, out_dir=None, name=None, force=False):
     if not force and not _stale(out, deps):
         return out
     common = ['nvcc', '-ccbin', HOSTCXX] + ARCH + ['-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '-I', CSRC,
-                                                    '-DCLAW_PLUGIN_HEADER="%s"' % header, '-DCLAW_PLUGIN_FUNCTOR=%s' % functor]
+                                                    '-DCLAW_PLUGIN_HEADER="%s"' % header, '-DCLAW_PLUGIN_FUNCTOR=%s' % functor,
+                                                    '-DCLAW_PLUGIN_NDIM=%d' % num_dim]
     tag = hashlib.sha1((header + functor).encode()).hexdigest()[:10]
     objs, jobs = [], []
     for ns, flags in (('strict', ['-DCLAW_NS=strict', '-DCLAW_STRICT=1', '-fmad=false']),
@@ -85,7 +87,7 @@ def load_cuda_solver(so_path, name=None, cparam=()):
     return mod
 
 
-def compile_cuda_solver(header, functor, cparam=(), out_dir=None, name=None, force=False):
+def compile_cuda_solver(header, functor, cparam=(), out_dir=None, name=None, force=False, num_dim=2):
     """build_cuda_solver + load_cuda_solver."""
-    so = build_cuda_solver(header, functor, out_dir=out_dir, name=name, force=force)
+    so = build_cuda_solver(header, functor, out_dir=out_dir, name=name, force=force, num_dim=num_dim)
     return load_cuda_solver(so, name=name or functor, cparam=cparam)

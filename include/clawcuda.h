@@ -80,12 +80,13 @@ enum {
   CLAW_RP_TRAFFIC_VC_TRACER_1D = 36    /* rp1_traffic_vc_tracer.f90 (2 equations; aux: speed limit) */
 };
 
-/* User-supplied 2-D Riemann solvers.  The reference takes them as two C pointers from a module the user compiled
+/* User-supplied Riemann solvers (2-D and 3-D).  The reference takes them as two C pointers from a module the user compiled
  * (`self.rp.rpn2._cpointer`, `self.rp.rpt2._cpointer`: pyclaw/src/pyclaw/classic/solver.py:516-521, after
  * `solver.rp = my_module`).  Here the user compiles a device functor against clawpack_b200/csrc/rp_plugin.cu into a
  * shared object (see that file for the recipe and the functor interface) and registers it:
  *   claw_rp_plugin_load(path, &rp_id)   dlopen + layout check; rp_id >= CLAW_RP_PLUGIN_BASE is then accepted wherever
- *                                       a built-in 2-D rp_id is (claw_create, claw_step2_host, claw_step2ds_host)
+ *                                       a built-in rp_id is (claw_create, claw_step2_host / claw_step2ds_host, or
+ *                                       claw_step3_host / claw_step3ds_host for a plug-in compiled with -DCLAW_PLUGIN_NDIM=3)
  *   claw_rp_plugin_info(rp_id, info)    info[0..4] = num_dim, meqn, mwaves, aux planes read, 1 if no transverse solver
  * Loading the same path twice returns the same id. */
 #define CLAW_RP_PLUGIN_BASE 1000

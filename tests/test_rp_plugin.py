@@ -25,6 +25,26 @@ def _vc_acoustics():
                                        name='user_vc_acoustics_2D')
 
 
+def _acoustics3d():
+    return riemann.compile_cuda_solver(os.path.join(PLUG, 'user_acoustics3d.cuh'), 'UserAcoustics3D',
+                                       name='user_acoustics_3D', num_dim=3)
+
+
+def test_3d_plugin_builds_without_a_gpu_and_registers():
+    rp = _acoustics3d()
+    assert rp.rp_id >= 1000 and (rp.num_dim, rp.num_eqn, rp.num_waves, rp.num_aux_read) == (3, 4, 2, 2)
+    P = ctypes.CDLL(rp.plugin_path)
+    assert hasattr(P, 'claw_rp_plugin_launch3') and not hasattr(P, 'claw_rp_plugin_launch2')
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    n = (ctypes.c_int * 3)(8, 8, 8)
+    rc = L.claw_create(ctypes.byref(h), 2, rp.rp_id, 4, 2, 2, n, 2, 0, None)        # a 3-D solver on a 2-D grid
+    assert rc != 0 and b'expects ndim=3' in L.claw_last_error(None)
+    from clawpack_b200 import pyclaw
+    solver = pyclaw.ClawSolver3D(rp)
+    assert solver.num_eqn == 4 and solver.num_waves == 2
+
+
 def test_plugins_build_without_a_gpu_and_register():
     rp = _acoustics()
     assert rp.rp_id >= 1000 and (rp.num_eqn, rp.num_waves, rp.num_aux_read, rp.num_dim) == (3, 2, 0, 2)
@@ -122,6 +142,27 @@ def test_plugin_fast_within_tolerance_and_equal_to_builtin_strict(name):
     qs, _ = _run(sc, 8, 'strict', plug())
     qb, _ = _run(sc, 8, 'strict')
     assert np.array_equal(qs, qb)
+
+
+PLUGIN_CASES_3D = {
+    'unsplit_22': lambda: S.acoustics_3d_general(mx=20, my=17, mz=15),
+    'unsplit_11_superbee': lambda: dict(S.acoustics_3d_general(mx=14, my=30, mz=12), transverse_waves=11, limiters=S.SUPERBEE),
+    'split': lambda: S.acoustics_3d_general(mx=13, my=12, mz=33, dimensional_split=True),
+    'reference_example': lambda: S.acoustics_3d(mx=24, my=24, mz=24),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', sorted(PLUGIN_CASES_3D))
+def test_3d_plugin_vs_oracle(name):
+    sc = PLUGIN_CASES_3D[name]()
+    q, log = _run(sc, 5, 'strict', _acoustics3d())
+    qr, logr = _ref(sc, 5)
+    assert log == logr
+    assert np.array_equal(q, qr), float(np.max(np.abs(q - qr)))
+    qf, logf = _run(sc, 5, 'fast', _acoustics3d())
+    assert [a for _, _, a in logf] == [a for _, _, a in logr]
+    assert np.max(np.abs(qf - qr)) <= 1e-12 * max(np.max(np.abs(qr)), 1e-300)
 
 
 @pytest.mark.gpu
