@@ -804,11 +804,15 @@ struct RpPlugin {
   int ndim = 2, meqn = 0, mwaves = 0, maux = 0, no_transverse = 0;
 };
 std::mutex g_plugin_mutex;
-std::vector<RpPlugin> g_plugins;               // rp_id = CLAW_RP_PLUGIN_BASE + index; entries are never removed
+// rp_id = CLAW_RP_PLUGIN_BASE + index; entries are never removed and never move (pointers handed out by plugin_of stay
+// valid while other threads register more plug-ins)
+constexpr int MAX_PLUGINS = 256;
+RpPlugin g_plugins[MAX_PLUGINS];
+int g_num_plugins = 0;
 const RpPlugin* plugin_of(int rp_id) {
   std::lock_guard<std::mutex> lock(g_plugin_mutex);
   const int k = rp_id - CLAW_RP_PLUGIN_BASE;
-  return (k >= 0 && k < (int)g_plugins.size()) ? &g_plugins[(size_t)k] : nullptr;
+  return (k >= 0 && k < g_num_plugins) ? &g_plugins[k] : nullptr;
 }
 
 int launch_step2(claw_solver* h, double dx, double dy, double dt, int kind, int do_x, int do_y,
@@ -1023,8 +1027,9 @@ int claw_device_count(void) {
 int claw_rp_plugin_load(const char* path, int* rp_id) {
   if (!path || !rp_id) return fail(nullptr, 1, "claw_rp_plugin_load: NULL argument");
   std::lock_guard<std::mutex> lock(g_plugin_mutex);
-  for (size_t k = 0; k < g_plugins.size(); ++k)
-    if (g_plugins[k].path == path) { *rp_id = CLAW_RP_PLUGIN_BASE + (int)k; return 0; }
+  for (int k = 0; k < g_num_plugins; ++k)
+    if (g_plugins[k].path == path) { *rp_id = CLAW_RP_PLUGIN_BASE + k; return 0; }
+  if (g_num_plugins == MAX_PLUGINS) return fail(nullptr, 64, "claw_rp_plugin_load: %d plug-ins are registered already", MAX_PLUGINS);
   void* dl = dlopen(path, RTLD_NOW | RTLD_LOCAL);
   if (!dl) return fail(nullptr, 60, "claw_rp_plugin_load: %s", dlerror());
   auto abi = reinterpret_cast<int (*)(void)>(dlsym(dl, "claw_rp_plugin_abi"));
@@ -1055,8 +1060,9 @@ int claw_rp_plugin_load(const char* path, int* rp_id) {
   RpPlugin p;
   p.path = path; p.dl = dl; p.launch2 = launch2; p.launch3 = launch3;
   p.ndim = v[0]; p.meqn = v[1]; p.mwaves = v[2]; p.maux = v[3]; p.no_transverse = v[4];
-  g_plugins.push_back(p);
-  *rp_id = CLAW_RP_PLUGIN_BASE + (int)g_plugins.size() - 1;
+  g_plugins[g_num_plugins] = p;
+  *rp_id = CLAW_RP_PLUGIN_BASE + g_num_plugins;
+  ++g_num_plugins;
   return 0;
 }
 
