@@ -875,6 +875,7 @@ int launch_pass3(claw_solver* h, const double* delta, double dt, int dir, int fi
   P.qin = src;
   P.qout = dst;
   P.aux = h->aux;
+  P.capa = h->method[5];                                                             // step3.f90:103
   P.cfl_bits = reinterpret_cast<unsigned long long*>(h->work);
   for (int d = 0; d < 3; ++d) { P.n[d] = h->g.n[d]; P.dtd[d] = dt / delta[d]; }      // step3.f90:106-108
   P.pitch = h->g.pitch; P.kstride = h->g.kstride; P.plane = h->g.plane;
@@ -994,7 +995,9 @@ int validate_config(claw_solver* h) {
     if (h->maux < need_aux)
       return fail(h, 31, "Riemann solver %d reads %d aux components, the state has num_aux=%d", h->rp_id, need_aux, h->maux);
   }
-  if (h->method[5] != 0) return fail(h, 31, "capacity functions are not supported by the 3-D CUDA kernels yet (index_capa=%d)", h->method[5] - 1);
+  if (h->method[5] < 0 || h->method[5] > h->maux)
+    return fail(h, 31, "index_capa=%d is outside the aux array (num_aux=%d)", h->method[5] - 1, h->maux);
+
   if (h->use_fwave) return fail(h, 32, "f-wave solvers are not supported by the CUDA kernels yet");
   if (h->method[1] != 1 && h->method[1] != 2) return fail(h, 33, "order must be 1 or 2 (got %d)", h->method[1]);
   {

@@ -53,7 +53,7 @@ struct StepCtl {
 };
 // layout version of StepCtl / Sweep2Params / LaunchInfo: a Riemann-solver plug-in (rp_plugin.cu) compiled against another
 // version is refused by claw_rp_plugin_load
-#define CLAW_PLUGIN_ABI 3
+#define CLAW_PLUGIN_ABI 4
 static_assert(sizeof(StepCtl) == 32 * 8, "StepCtl is mirrored by the host as 32 words");
 
 // buffer roles of a launch that runs under a StepCtl: 0 = current q, 1 = alternate q, 2 = third buffer (3-D split)

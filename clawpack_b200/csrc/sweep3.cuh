@@ -60,6 +60,8 @@ struct Sweep3Params {
   double* qbuf[3];          // ping-pong q buffers + the third buffer of the dimension-split step
   int src_role, dst_role;   // 0 = current, 1 = alternate, 2 = third buffer
   double delta[3];          // dx, dy, dz: dtd = ctl->dt / delta as step3.f90:106-108 computes it
+  int capa;                 // method(6) = index_capa + 1: 1-based aux plane of the capacity function, 0 = none
+                            // (last member: the offsets of the others are those of the profiled builds)
 };
 #endif
 
@@ -109,9 +111,11 @@ __device__ __forceinline__ void limit_waves3(const int* mthlim, double (*wave)[M
 }
 
 // flux3.f90:231-259 (use_fwave = .false.): cqxx (= the fadd increment) of one interface
+// dtd_l / dtd_r = dtdx1d of the cells left / right of the interface (equal without a capacity function)
 template <int M, int W>
-__device__ __forceinline__ void second_order3(double dtd, const double (*wave)[M], const double* s, double* cqxx) {
-  const double dtdxave = 0.5 * (dtd + dtd);
+__device__ __forceinline__ void second_order3(double dtd_l, double dtd_r, const double (*wave)[M], const double* s,
+                                              double* cqxx) {
+  const double dtdxave = 0.5 * (dtd_l + dtd_r);                                         // flux3.f90:236
 #pragma unroll
   for (int m = 0; m < M; ++m) {
     double c = 0.0;
@@ -351,6 +355,78 @@ __device__ __forceinline__ void apply_center(double* acc, const double* sm, cons
     }
   }
 }
+// ---- capacity function (step3.f90:229-273 / 384-431 / 546-593) -------------------------------------------------------
+// Every bracketed flux sum is divided by the capacity of the cell it goes into: one addend per source pencil,
+//   acc = acc + sgn * (dty * Gterm + s2 * dtz * Hterm) / capa      (the reference's nine expressions in the (a, b) frame)
+// instead of the two sequential addends of the plain form.  Components a transverse solve leaves structurally zero
+// (fast mode stores only TV::N of them) enter as exact zeros, which is what the reference adds.
+template <class RP, int IXYZ, int A, int B, int NT>
+__device__ __forceinline__ void apply_target_capa(double* acc, const double* sm, double dty, double dtz, double capa) {
+  using TY = typename RP::template TV<IXYZ, 2>;
+  using TZ = typename RP::template TV<IXYZ, 3>;
+  constexpr int NG = TY::N, NH = TZ::N, M = RP::MEQN;
+  double gt[M], ht[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) { gt[m] = 0.0; ht[m] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < NG; ++k) {
+    const int m = TY::comp(k);
+    if (A == -1 && B == 0) gt[m] = G_(1, 0);
+    if (A == -1 && B == -1) gt[m] = G_(1, -1);
+    if (A == 0 && B == -1) gt[m] = G_(2, -1) - G_(1, -1);
+    if (A == 1 && B == -1) gt[m] = G_(2, -1);
+    if (A == 1 && B == 0) gt[m] = G_(2, 0);
+    if (A == 1 && B == 1) gt[m] = G_(2, 1);
+    if (A == 0 && B == 1) gt[m] = G_(2, 1) - G_(1, 1);
+    if (A == -1 && B == 1) gt[m] = G_(1, 1);
+  }
+#pragma unroll
+  for (int k = 0; k < NH; ++k) {
+    const int m = TZ::comp(k);
+    if (A == -1 && B == 0) ht[m] = H_(2, -1) - H_(1, -1);
+    if (A == -1 && B == -1) ht[m] = H_(1, -1);
+    if (A == 0 && B == -1) ht[m] = H_(1, 0);
+    if (A == 1 && B == -1) ht[m] = H_(1, 1);
+    if (A == 1 && B == 0) ht[m] = H_(2, 1) - H_(1, 1);
+    if (A == 1 && B == 1) ht[m] = H_(2, 1);
+    if (A == 0 && B == 1) ht[m] = H_(2, 0);
+    if (A == -1 && B == 1) ht[m] = H_(2, -1);
+  }
+  constexpr bool plus_outer = (A == 1);                                        // targets (1, b): "+ (...)", else "- (...)"
+  constexpr bool minus_inner = (A == 1 && B <= 0) || (A <= 0 && B == 1);       // "g - h" inside the bracket, else "g + h"
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    const double g = dty * gt[m], h = dtz * ht[m];
+    const double t = ddiv(minus_inner ? g - h : g + h, capa);
+    acc[m] = plus_outer ? acc[m] + t : acc[m] - t;
+  }
+}
+// the pencil's own cell (step3.f90:231-235): dtdn is the SCALAR dt/dx of the sweep direction
+template <class RP, int IXYZ, int NT>
+__device__ __forceinline__ void apply_center_capa(double* acc, const double* sm, const double* qadd, const double* fdiff,
+                                                  double dtdn, double dty, double dtz, bool transverse, double capa) {
+  using TY = typename RP::template TV<IXYZ, 2>;
+  using TZ = typename RP::template TV<IXYZ, 3>;
+  constexpr int NG = TY::N, NH = TZ::N, M = RP::MEQN;
+  double gt[M], ht[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) { gt[m] = 0.0; ht[m] = 0.0; }
+  if (transverse) {
+#pragma unroll
+    for (int k = 0; k < NG; ++k) gt[TY::comp(k)] = G_(2, 0) - G_(1, 0);
+#pragma unroll
+    for (int k = 0; k < NH; ++k) ht[TZ::comp(k)] = H_(2, 0) - H_(1, 0);
+  }
+#pragma unroll
+  for (int m = 0; m < M; ++m) acc[m] = (acc[m] + qadd[m]) - ddiv((dtdn * fdiff[m] + dty * gt[m]) + dtz * ht[m], capa);
+}
+// flux3.f90:211-218 with dtdx1d of the two cells of the interface
+template <int W>
+__device__ __forceinline__ double cfl_update_capa(double cfl, double dtd_l, double dtd_r, const double* s) {
+#pragma unroll
+  for (int mw = 0; mw < W; ++mw) cfl = fmax2(fmax2(cfl, dtd_r * s[mw]), -dtd_l * s[mw]);
+  return cfl;
+}
 #undef G_
 #undef H_
 
@@ -438,6 +514,10 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
   const bool second = SP ? true : (P.order != 1);
   const bool limit = SP ? true : (second && (P.limit != 0));
   const bool transverse = SP ? true : (P.m3 > 0);
+  // capacity function (method(6)): generic kernels of aux-carrying solvers only -- the specialised BASELINE kernels
+  // compile the branch out
+  const bool capa = !SP && P.capa > 0;
+  const int icapa = capa ? P.capa - 1 : 0;
 
   const bool owner_lane = (t >= 2 && t <= 29 && I < nx) || (blockIdx.x == 0 && t < 2);
   const bool interior_i = (I >= 2 && I <= P.n[0] + 1);
@@ -507,8 +587,20 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
     for (int ma = 0; ma < MA; ++ma) auxl[ma] = (RP::MAUX > 0) ? shfl_up1(A[1][1][ma]) : 0.0;
     double wave[W][M], s[W], amdq[M], apdq[M], ctx[NC], cqxx[M];
     RP::template normal<0>(P.rp, ql, q, auxl, A[1][1], wave, s, amdq, apdq, ctx);      // flux3.f90:201
+    // capacity of my cell in the planes k-1, k, k+1 (the capacity plane need not be one the Riemann solver reads, so it
+    // is fetched on its own; this path is not a throughput target)
+    double c0 = 1.0, c1 = 1.0, c2 = 1.0;
+    if (!SP && capa) {
+      const double* cp = P.aux + (long long)icapa * P.plane + (long long)Jc * P.pitch + Ic;
+      c0 = cp[(long long)(k > 0 ? k - 1 : 0) * P.kstride];
+      c1 = cp[(long long)k * P.kstride];
+      c2 = cp[(long long)kn * P.kstride];
+    }
+    // dtdx1d of my cell and of the cell on my left (step3.f90:132-136); without a capacity function both are dt/dx
+    const double dI = (!SP && capa) ? ddiv(dtdx, c1) : dtdx;
+    const double dIm1 = (!SP && capa) ? shfl_up1(dI) : dtdx;
     if (cfl_lane && plane_pencil) {                                                     // flux3.f90:211-218
-        cfl = cfl_update<W>(cfl, dtdx, s);
+        cfl = (!SP && capa) ? cfl_update_capa<W>(cfl, dIm1, dI, s) : cfl_update<W>(cfl, dtdx, s);
     }
 #pragma unroll
     for (int m = 0; m < M; ++m) cqxx[m] = 0.0;
@@ -527,7 +619,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
         for (int mw = 0; mw < W; ++mw) dotl[mw] = shfl_up1(dotr[mw]);
         limit_waves3<M, W, LIM>(P.mthlim, wave, s, wnorm2, dotl, dotr);
       }
-      second_order3<M, W>(dtdx, wave, s, cqxx);                                         // flux3.f90:231-259
+      second_order3<M, W>(dIm1, dI, wave, s, cqxx);                                     // flux3.f90:231-259
     }
     // ---- the next interface's left-going pieces (cell I owns the m-side of interface I+1) --
     double amdqR[M], cqxxR[M], ctxR[NC];
@@ -538,7 +630,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
     double qadd[M], fdiff[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-      qadd[m] = (0.0 - dtdx * apdq[m]) - dtdx * amdqR[m];                              // flux3.f90:205-208
+      qadd[m] = (0.0 - dI * apdq[m]) - dI * amdqR[m];                                  // flux3.f90:205-208
       fdiff[m] = (0.0 + cqxxR[m]) - (0.0 + cqxx[m]);                                    // fadd(i+1) - fadd(i)
     }
     if (split) {
@@ -547,15 +639,35 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_x(const __grid_constant_
       if (owner_lane && row_out && k >= kb && k < ke) {
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-          const double r = (q[m] + qadd[m]) - dtdx * fdiff[m];
+          const double r = (!SP && capa) ? (q[m] + qadd[m]) - ddiv(dtdx * fdiff[m], c1)         // step3ds.f90:200-205
+                                : (q[m] + qadd[m]) - dtdx * fdiff[m];
           qout[m * P.plane + (long long)k * P.kstride + (long long)J * P.pitch + I] = upd ? r : q[m];
         }
       }
       continue;
     }
-    if (transverse) flux3_cell<RP, 0, NT, M3C, M4C>(P, dtdx, dtdy, dtdz, apdq, cqxx, ctx, amdqR, cqxxR, ctxR, A, sm);
+    if (transverse) flux3_cell<RP, 0, NT, M3C, M4C>(P, dI, dtdy, dtdz, apdq, cqxx, ctx, amdqR, cqxxR, ctxR, A, sm);
     __syncthreads();
-    if (row_out) {
+    if (!SP && row_out && capa) {
+      if (transverse) {
+        apply_target_capa<RP, 0, 1, -1, NT>(acc0, sm - 32, dtdy, dtdz, c0);
+        apply_target_capa<RP, 0, 0, -1, NT>(acc0, sm, dtdy, dtdz, c0);
+        apply_target_capa<RP, 0, -1, -1, NT>(acc0, sm + 32, dtdy, dtdz, c0);
+        apply_target_capa<RP, 0, 1, 0, NT>(acc1, sm - 32, dtdy, dtdz, c1);
+        apply_center_capa<RP, 0, NT>(acc1, sm, qadd, fdiff, dtdx, dtdy, dtdz, true, c1);
+        apply_target_capa<RP, 0, -1, 0, NT>(acc1, sm + 32, dtdy, dtdz, c1);
+        apply_target_capa<RP, 0, 1, 1, NT>(acc2, sm - 32, dtdy, dtdz, c2);
+        apply_target_capa<RP, 0, 0, 1, NT>(acc2, sm, dtdy, dtdz, c2);
+        apply_target_capa<RP, 0, -1, 1, NT>(acc2, sm + 32, dtdy, dtdz, c2);
+      } else {
+        apply_center_capa<RP, 0, NT>(acc1, sm, qadd, fdiff, dtdx, dtdy, dtdz, false, c1);
+      }
+      if (owner_lane && interior_i && k - 1 >= kb && k - 1 < ke) {
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+          qout[m * P.plane + (long long)(k - 1) * P.kstride + (long long)J * P.pitch + I] = acc0[m];
+      }
+    } else if (row_out) {
       if (transverse) {
         // pencils (J-1, k), (J, k), (J+1, k) in this order (step3.f90:124-125: k outer, j inner);
         // a = J_target - J_source, b = plane_target - k
@@ -626,6 +738,8 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
   const bool second = SP ? true : (P.order != 1);
   const bool limit = SP ? true : (second && (P.limit != 0));
   const bool transverse = SP ? true : (P.m3 > 0);
+  const bool capa = !SP && P.capa > 0;                      // capacity function: see sweep3_x
+  const int icapa = capa ? P.capa - 1 : 0;
   const bool pencil = (I >= 1 && I <= P.n[0] + 2) &&
                       (IXYZ == 1 ? (T >= P.zlo && T <= P.zhi) : (T >= 1 && T <= P.n[TD] + 2));
   const bool out_thread = split ? (I < nx && T < nT)
@@ -652,6 +766,8 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
 #pragma unroll
   for (int ma = 0; ma < MA; ++ma) auxP[ma] = 1.0;
   double cfl = 0.0;
+  // dtdx1d (step3.f90:291-295 / 447-451) and the capacity of the cells n-1 (P) and n-2 (C) of my column
+  double dP = dtdn, dC = dtdn, capaP = 1.0, capaC = 1.0;
 
   // operands of march step n, fetched asynchronously one step ahead into stage (n & 1):
   //   slots [0, M): q(n);  [M, M+MA): aux(n);  [M+MA, M+10MA): aux 3x3 of cell n-2;  [M+10MA, 2M+10MA): old qout(n-2)
@@ -704,8 +820,16 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
     // ---- interface n (raw) ---------------------------------------------------------------
     double waveN[W][M], sN[W], amdqN[M], apdqN[M], ctxN[NC];
     RP::template normal<IXYZ>(P.rp, q1, qN, auxP, auxN, waveN, sN, amdqN, apdqN, ctxN);
+    double capaN = 1.0;                                      // (fetched on its own: see sweep3_x)
+    if (!SP && capa) {
+      const int nc = n < 0 ? 0 : (n < nlen ? n : nlen - 1);
+      capaN = P.aux[(long long)icapa * P.plane + col + (long long)nc * strideN];
+    }
+    const double dN = (!SP && capa) ? ddiv(dtdn, capaN) : dtdn;
+    // (the specialised kernels see the constant: no carried copies in their loop)
+    const double dPe = SP ? dtdn : dP, dCe = SP ? dtdn : dC;
     if (pencil && n >= 2 && n <= mlen + 2 && n > cb - 2) {                              // flux3.f90:211-218
-        cfl = cfl_update<W>(cfl, dtdn, sN);
+        cfl = (!SP && capa) ? cfl_update_capa<W>(cfl, dPe, dN, sN) : cfl_update<W>(cfl, dtdn, sN);
     }
     // ---- finish interface n-1: limiter (needs waves n-2 via dotl, n-1, n) + cqxx -----------
     double cqxxP[M];
@@ -720,7 +844,7 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
         wave_dots3<M, W>(waveP, waveN, wnorm2, dotn);
         limit_waves3<M, W, LIM>(P.mthlim, waveP, sP, wnorm2, dotlP, dotn);
       }
-      second_order3<M, W>(dtdn, waveP, sP, cqxxP);
+      second_order3<M, W>(dCe, dPe, waveP, sP, cqxxP);           // interface n-1: cells n-2 | n-1
     }
     // ---- cell c = n-2: p-side = interface n-2 (carried), m-side = interface n-1 ---------------
     const int c = n - 2;
@@ -728,7 +852,7 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
     double qadd[M], fdiff[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-      qadd[m] = (0.0 - dtdn * apdqC[m]) - dtdn * amdqP[m];
+      qadd[m] = (0.0 - dCe * apdqC[m]) - dCe * amdqP[m];
       fdiff[m] = (0.0 + cqxxP[m]) - (0.0 + cqxxC[m]);
     }
     if (split) {
@@ -736,7 +860,8 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
       if (out_thread && c_out) {
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-          const double r = (q2[m] + qadd[m]) - dtdn * fdiff[m];
+          const double r = (!SP && capa) ? (q2[m] + qadd[m]) - ddiv(dtdn * fdiff[m], capaC)    // step3ds.f90:282-287, 365-370
+                                : (q2[m] + qadd[m]) - dtdn * fdiff[m];
           ocol[m * P.plane + (long long)c * strideN] = upd ? r : q2[m];
         }
       }
@@ -751,13 +876,40 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
 #pragma unroll
               for (int ma = 0; ma < MA; ++ma) A[dy][dz][ma] = st[(PFN + (dy * 3 + dz) * SM3::MA + ma) * NT];
         }
-        flux3_cell<RP, IXYZ, NT, M3C, M4C>(P, dtdn, dty, dtz, apdqC, cqxxC, ctxC, amdqP, cqxxP, ctxP, A, sm);
+        flux3_cell<RP, IXYZ, NT, M3C, M4C>(P, dCe, dty, dtz, apdqC, cqxxC, ctxC, amdqP, cqxxP, ctxP, A, sm);
       }
       __syncthreads();
       if (out_thread) {
         double acc[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) acc[m] = P.first_pass ? q2[m] : st[(PFO + m) * NT];
+        if (!SP && capa) {                                   // every addend divided by my cell's capacity
+          if (transverse) {
+            if (IXYZ == 1) {
+              apply_target_capa<RP, IXYZ, 1, 1, NT>(acc, sm - BX - 1, dty, dtz, capaC);
+              apply_target_capa<RP, IXYZ, 1, 0, NT>(acc, sm - BX, dty, dtz, capaC);
+              apply_target_capa<RP, IXYZ, 1, -1, NT>(acc, sm - BX + 1, dty, dtz, capaC);
+              apply_target_capa<RP, IXYZ, 0, 1, NT>(acc, sm - 1, dty, dtz, capaC);
+              apply_center_capa<RP, IXYZ, NT>(acc, sm, qadd, fdiff, dtdn, dty, dtz, true, capaC);
+              apply_target_capa<RP, IXYZ, 0, -1, NT>(acc, sm + 1, dty, dtz, capaC);
+              apply_target_capa<RP, IXYZ, -1, 1, NT>(acc, sm + BX - 1, dty, dtz, capaC);
+              apply_target_capa<RP, IXYZ, -1, 0, NT>(acc, sm + BX, dty, dtz, capaC);
+              apply_target_capa<RP, IXYZ, -1, -1, NT>(acc, sm + BX + 1, dty, dtz, capaC);
+            } else {
+              apply_target_capa<RP, IXYZ, 1, 1, NT>(acc, sm - BX - 1, dty, dtz, capaC);
+              apply_target_capa<RP, IXYZ, 0, 1, NT>(acc, sm - BX, dty, dtz, capaC);
+              apply_target_capa<RP, IXYZ, -1, 1, NT>(acc, sm - BX + 1, dty, dtz, capaC);
+              apply_target_capa<RP, IXYZ, 1, 0, NT>(acc, sm - 1, dty, dtz, capaC);
+              apply_center_capa<RP, IXYZ, NT>(acc, sm, qadd, fdiff, dtdn, dty, dtz, true, capaC);
+              apply_target_capa<RP, IXYZ, -1, 0, NT>(acc, sm + 1, dty, dtz, capaC);
+              apply_target_capa<RP, IXYZ, 1, -1, NT>(acc, sm + BX - 1, dty, dtz, capaC);
+              apply_target_capa<RP, IXYZ, 0, -1, NT>(acc, sm + BX, dty, dtz, capaC);
+              apply_target_capa<RP, IXYZ, -1, -1, NT>(acc, sm + BX + 1, dty, dtz, capaC);
+            }
+          } else {
+            apply_center_capa<RP, IXYZ, NT>(acc, sm, qadd, fdiff, dtdn, dty, dtz, false, capaC);
+          }
+        } else
         if (transverse) {
           // source pencils in the reference's loop order: thread-y outer, thread-x inner
           // (step3.f90:283-284 "do k / do i", :439-440 "do j / do i")
@@ -801,6 +953,7 @@ __global__ void __launch_bounds__(BX * BY, MINB) sweep3_march(const __grid_const
     for (int cc = 0; cc < NC; ++cc) { ctxC[cc] = ctxP[cc]; ctxP[cc] = ctxN[cc]; }
 #pragma unroll
     for (int ma = 0; ma < MA; ++ma) auxP[ma] = auxN[ma];
+    if (!SP) { dC = dP; dP = dN; capaC = capaP; capaP = capaN; }
 #pragma unroll
     for (int mw = 0; mw < W; ++mw) {
       sP[mw] = sN[mw]; dotlP[mw] = dotn[mw];

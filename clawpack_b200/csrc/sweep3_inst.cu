@@ -20,7 +20,7 @@ cudaError_t launch_sweep3(int rp_id, int dir, Sweep3Params& P, int num_sms, cuda
       // Method set as template arguments when it is the BASELINE config-4 set (unsplit, order 2, method(3) = 22, MC on
       // every wave), x-sweep as two 32x6 CTAs per SM (168 registers, no spills).  Measured on B200 at 512^3
       // (profiles/r02_b_c4_variants.jsonl): 49.6 ms generic -> 35.4 ms specialised -> 32.4 ms with the 32x6 x-sweep.
-      if (variant != 1 && headline_method3<2>(P, 4)) {
+      if (variant != 1 && headline_method3<2>(P, 4) && P.capa == 0) {       // (the specialised kernels have no capacity branch)
         // (two copies of the gadd / hadd exchange area alternating by step parity, so that one of the two barriers per
         // march step goes away, were measured at 512^3: marches 12.3 against 11.8 ms -- the 213 KB of shared memory leave
         // the 3x3 aux neighbourhood fetches hardly any L1 --, x-sweep within 1 %: dropped, profiles/r02_zd, r02_ze)

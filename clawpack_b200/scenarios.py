@@ -516,6 +516,19 @@ def acoustics_3d_general(mx=18, my=15, mz=13, **kw):
     return sc
 
 
+def acoustics_3d_capa(mx=18, my=15, mz=13, **kw):
+    """vc_acoustics_3D on a grid with a capacity function (step3.f90:132-136, 229-273; no reference example uses one in
+    3-D): the stress case above with a third aux plane kappa(x, y, z) in [0.6, 1.5] and ``index_capa = 2``."""
+    sc = acoustics_3d_general(mx=mx, my=my, mz=mz)
+    X, Y, Z = _grid((-1., -1., -1.), (1., 1., 1.), (mx, my, mz))
+    aux = np.empty((3, mx, my, mz), order='F')
+    aux[:2] = sc['aux']
+    aux[2] = 1.05 + 0.3 * np.sin(2 * X - Y) * np.cos(3 * Z + 0.5) + 0.15 * np.cos(4 * X * Y + Z)
+    sc = dict(sc, aux=aux, index_capa=2)
+    sc.update(kw)
+    return sc
+
+
 def burgers_2d(mx=60, my=50, dimensional_split=False, transverse_waves=2, tfinal=0.3, num_output_times=2):
     """2-D Burgers equation (riemann burgers_2D; no reference example): data of both signs, periodic."""
     X, Y = _grid((0., 0.), (1., 1.), (mx, my))

@@ -721,8 +721,41 @@ inline void step3_scatter(Q3<R> qnew, int num_eqn, int mlen, const int* base, co
     }
 }
 
+// The same with a capacity function (step3.f90:229-273 / 384-431 / 546-593): every bracketed flux sum is divided by
+// the capacity of the cell it goes into.  C(p, a, b) = aux(index_capa, .) of the cell at pencil coordinate p, offsets
+// (a, b) in the y-like / z-like directions.  dtdn is the SCALAR dt/dx of the sweep direction (qadd already carries the
+// per-cell dtdx1d).  The three sweeps' statements are the same nine expressions in the rotated (a, b) frame.
+template <class R>
+inline void step3_scatter_capa(Q3<R> qnew, Q3<R> aux, int index_capa, int num_eqn, int mlen, const int* base,
+                               const int* en, const int* ey, const int* ez, R dtdn, R dtdy, R dtdz, Flux3Work<R>& w) {
+  V2<R> qadd = w.qadd, fadd = w.fadd;
+  V4<R> gadd = w.gadd, hadd = w.hadd;
+  auto Q = [&](int m, int p, int a, int b) -> R& {
+    return qnew(m, base[0] + p * en[0] + a * ey[0] + b * ez[0], base[1] + p * en[1] + a * ey[1] + b * ez[1],
+                base[2] + p * en[2] + a * ey[2] + b * ez[2]);
+  };
+  auto C = [&](int p, int a, int b) -> R {
+    return aux(index_capa, base[0] + p * en[0] + a * ey[0] + b * ez[0], base[1] + p * en[1] + a * ey[1] + b * ez[1],
+               base[2] + p * en[2] + a * ey[2] + b * ez[2]);
+  };
+  for (int i = 1; i <= mlen; ++i)
+    for (int m = 1; m <= num_eqn; ++m) {
+      Q(m, i, 0, 0) = Q(m, i, 0, 0) + qadd(m, i)
+                      - (dtdn * (fadd(m, i + 1) - fadd(m, i)) + dtdy * (gadd(m, 2, 0, i) - gadd(m, 1, 0, i))
+                         + dtdz * (hadd(m, 2, 0, i) - hadd(m, 1, 0, i))) / C(i, 0, 0);
+      Q(m, i, -1, 0) = Q(m, i, -1, 0) - (dtdy * gadd(m, 1, 0, i) + dtdz * (hadd(m, 2, -1, i) - hadd(m, 1, -1, i))) / C(i, -1, 0);
+      Q(m, i, -1, -1) = Q(m, i, -1, -1) - (dtdy * gadd(m, 1, -1, i) + dtdz * hadd(m, 1, -1, i)) / C(i, -1, -1);
+      Q(m, i, 0, -1) = Q(m, i, 0, -1) - (dtdy * (gadd(m, 2, -1, i) - gadd(m, 1, -1, i)) + dtdz * hadd(m, 1, 0, i)) / C(i, 0, -1);
+      Q(m, i, 1, -1) = Q(m, i, 1, -1) + (dtdy * gadd(m, 2, -1, i) - dtdz * hadd(m, 1, 1, i)) / C(i, 1, -1);
+      Q(m, i, 1, 0) = Q(m, i, 1, 0) + (dtdy * gadd(m, 2, 0, i) - dtdz * (hadd(m, 2, 1, i) - hadd(m, 1, 1, i))) / C(i, 1, 0);
+      Q(m, i, 1, 1) = Q(m, i, 1, 1) + (dtdy * gadd(m, 2, 1, i) + dtdz * hadd(m, 2, 1, i)) / C(i, 1, 1);
+      Q(m, i, 0, 1) = Q(m, i, 0, 1) - (dtdy * (gadd(m, 2, 1, i) - gadd(m, 1, 1, i)) - dtdz * hadd(m, 2, 0, i)) / C(i, 0, 1);
+      Q(m, i, -1, 1) = Q(m, i, -1, 1) - (dtdy * gadd(m, 1, 1, i) - dtdz * hadd(m, 2, -1, i)) / C(i, -1, 1);
+    }
+}
+
 // =====================================================================
-// step3 -- pyclaw/src/pyclaw/classic/step3.f90:2-597 (index_capa = 0 only)
+// step3 -- pyclaw/src/pyclaw/classic/step3.f90:2-597 (with and without a capacity function)
 // =====================================================================
 template <class R>
 int step3(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int mx, int my, int mz,
@@ -732,7 +765,8 @@ int step3(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int 
   Rpn3<R> rpn3; Rpt3<R> rpt3; Rptt3<R> rptt3;
   if (!select_rp3<R>(rp_id, rpn3, rpt3, rptt3)) return 1;
   if (maxm < mx || maxm < my || maxm < mz) return 2;
-  if (method[5] != 0) return 4;                          // capacity function: not restated
+  const int index_capa = method[5];                      // :103
+  if (index_capa < 0 || index_capa > num_aux) return 4;
   const int nx = mx + 2 * num_ghost, ny = my + 2 * num_ghost;
   Q3<R> qold{qold_, num_eqn, nx, ny, num_ghost}, qnew{qnew_, num_eqn, nx, ny, num_ghost};
   Q3<R> aux{aux_, num_aux > 0 ? num_aux : 1, nx, ny, num_ghost};
@@ -754,11 +788,14 @@ int step3(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int 
               w.aux2(ma, i, 2 + ka) = aux(ma, i, j, k + ka);
               w.aux3(ma, i, 2 + ka) = aux(ma, i, j + 1, k + ka);
             }
+      if (index_capa > 0)                                 // :132-136
+        for (int i = 1 - num_ghost; i <= mx + num_ghost; ++i) w.dtdx1d(i) = dtdx / aux(index_capa, i, j, k);
       flux3(1, maxm, num_eqn, num_waves, num_ghost, mx, w.dtdx1d, dtdy, dtdz, num_aux, method, mthlim, w, cfl1d,
             use_fwave, rpn3, rpt3, rptt3, cparam);         // :163
       cfl = r_max(cfl, cfl1d);
       const int base[3] = {0, j, k}, en[3] = {1, 0, 0}, ey[3] = {0, 1, 0}, ez[3] = {0, 0, 1};
-      step3_scatter(qnew, num_eqn, mx, base, en, ey, ez, dtdx, dtdy, dtdz, w);   // :193-226
+      if (index_capa == 0) step3_scatter(qnew, num_eqn, mx, base, en, ey, ez, dtdx, dtdy, dtdz, w);   // :193-226
+      else step3_scatter_capa(qnew, aux, index_capa, num_eqn, mx, base, en, ey, ez, dtdx, dtdy, dtdz, w);   // :229-273
     }
   // ---- y sweeps (:283-431): y-like = z, z-like = x ---------------------------------------------
   for (int k = 0; k <= mz + 1; ++k)
@@ -773,11 +810,14 @@ int step3(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int 
               w.aux2(ma, j, 2 + ia) = aux(ma, i + ia, j, k);
               w.aux3(ma, j, 2 + ia) = aux(ma, i + ia, j, k + 1);
             }
+      if (index_capa > 0)                                 // :291-295
+        for (int j = 1 - num_ghost; j <= my + num_ghost; ++j) w.dtdy1d(j) = dtdy / aux(index_capa, i, j, k);
       flux3(2, maxm, num_eqn, num_waves, num_ghost, my, w.dtdy1d, dtdz, dtdx, num_aux, method, mthlim, w, cfl1d,
             use_fwave, rpn3, rpt3, rptt3, cparam);         // :317
       cfl = r_max(cfl, cfl1d);
       const int base[3] = {i, 0, k}, en[3] = {0, 1, 0}, ey[3] = {0, 0, 1}, ez[3] = {1, 0, 0};
-      step3_scatter(qnew, num_eqn, my, base, en, ey, ez, dtdy, dtdz, dtdx, w);   // :348-381
+      if (index_capa == 0) step3_scatter(qnew, num_eqn, my, base, en, ey, ez, dtdy, dtdz, dtdx, w);   // :348-381
+      else step3_scatter_capa(qnew, aux, index_capa, num_eqn, my, base, en, ey, ez, dtdy, dtdz, dtdx, w);   // :384-431
     }
   // ---- z sweeps (:439-593): y-like = x, z-like = y ---------------------------------------------
   for (int j = 0; j <= my + 1; ++j)
@@ -792,18 +832,21 @@ int step3(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, int 
               w.aux2(ma, k, 2 + ja) = aux(ma, i, j + ja, k);
               w.aux3(ma, k, 2 + ja) = aux(ma, i + 1, j + ja, k);
             }
+      if (index_capa > 0)                                 // :447-451
+        for (int k = 1 - num_ghost; k <= mz + num_ghost; ++k) w.dtdz1d(k) = dtdz / aux(index_capa, i, j, k);
       flux3(3, maxm, num_eqn, num_waves, num_ghost, mz, w.dtdz1d, dtdx, dtdy, num_aux, method, mthlim, w, cfl1d,
             use_fwave, rpn3, rpt3, rptt3, cparam);         // :477
       cfl = r_max(cfl, cfl1d);
       const int base[3] = {i, j, 0}, en[3] = {0, 0, 1}, ey[3] = {1, 0, 0}, ez[3] = {0, 1, 0};
-      step3_scatter(qnew, num_eqn, mz, base, en, ey, ez, dtdz, dtdx, dtdy, w);   // :510-543
+      if (index_capa == 0) step3_scatter(qnew, num_eqn, mz, base, en, ey, ez, dtdz, dtdx, dtdy, w);   // :510-543
+      else step3_scatter_capa(qnew, aux, index_capa, num_eqn, mz, base, en, ey, ez, dtdz, dtdx, dtdy, w);   // :546-593
     }
   *cfl_out = cfl;
   return 0;
 }
 
 // =====================================================================
-// step3ds -- pyclaw/src/pyclaw/classic/step3ds.f90 (one split sweep, idir = 1|2|3; index_capa = 0 only)
+// step3ds -- pyclaw/src/pyclaw/classic/step3ds.f90 (one split sweep, idir = 1|2|3; with and without a capacity function)
 // Only ONE ghost layer is swept (:134-135, 215-216, 298-299).  qold may alias qnew.
 // =====================================================================
 template <class R>
@@ -814,7 +857,8 @@ int step3ds(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, in
   if (!select_rp3<R>(rp_id, rpn3, rpt3, rptt3)) return 1;
   if (maxm < mx || maxm < my || maxm < mz) return 2;
   if (idir < 1 || idir > 3) return 3;
-  if (method[5] != 0) return 4;
+  const int index_capa = method[5];                      // :112
+  if (index_capa < 0 || index_capa > num_aux) return 4;
   const int nx = mx + 2 * num_ghost, ny = my + 2 * num_ghost;
   Q3<R> qold{qold_, num_eqn, nx, ny, num_ghost}, qnew{qnew_, num_eqn, nx, ny, num_ghost};
   Q3<R> aux{aux_, num_aux > 0 ? num_aux : 1, nx, ny, num_ghost};
@@ -859,12 +903,21 @@ int step3ds(int maxm, int num_eqn, int num_waves, int num_aux, int num_ghost, in
           for (int a = -1; a <= 1; ++a)
             for (int t = 1 - num_ghost; t <= mlen + num_ghost; ++t)
               for (int ma = 1; ma <= num_aux; ++ma) w.aux2(ma, t, 2 + a) = at(aux, ma, t, a);
+        if (index_capa > 0)                               // :142-146, 223-227, 306-310
+          for (int t = 1 - num_ghost; t <= mlen + num_ghost; ++t) dt1d(t) = dtdn / at(aux, index_capa, t, 0);
         flux3(idir, maxm, num_eqn, num_waves, num_ghost, mlen, dt1d, dty, dtz, num_aux, method, mthlim, w, cfl1d,
               use_fwave, rpn3, rpt3, rptt3, cparam);
         cfl = r_max(cfl, cfl1d);
-        for (int t = 1; t <= mlen; ++t)                    // :195-198, 278-281, 361-364
-          for (int m = 1; m <= num_eqn; ++m)
-            at(qnew, m, t, 0) = at(qnew, m, t, 0) + w.qadd(m, t) - dtdn * (w.fadd(m, t + 1) - w.fadd(m, t));
+        if (index_capa == 0) {
+          for (int t = 1; t <= mlen; ++t)                  // :195-198, 278-281, 361-364
+            for (int m = 1; m <= num_eqn; ++m)
+              at(qnew, m, t, 0) = at(qnew, m, t, 0) + w.qadd(m, t) - dtdn * (w.fadd(m, t + 1) - w.fadd(m, t));
+        } else {
+          for (int t = 1; t <= mlen; ++t)                  // :200-205, 282-287, 365-370: dtdx * (df) / capa, left to right
+            for (int m = 1; m <= num_eqn; ++m)
+              at(qnew, m, t, 0) = at(qnew, m, t, 0) + w.qadd(m, t)
+                                  - dtdn * (w.fadd(m, t + 1) - w.fadd(m, t)) / at(aux, index_capa, t, 0);
+        }
       }
     cfls[tid] = r_max(cfls[tid], cfl);
   }

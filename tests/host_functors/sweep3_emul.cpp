@@ -105,6 +105,7 @@ extern "C" int emul_step3_host(int meqn, int mwaves, int maux, int mx, int my, i
     P.limit = 0;
     for (int mw = 0; mw < mwaves; ++mw) { P.mthlim[mw] = mthlim[mw]; if (mthlim[mw] > 0) P.limit = 1; }
     P.first_pass = first_pass;
+    P.capa = method7[5];
     P.zlo = 1; P.zhi = mz + 2;
     for (int k = 0; k < 4; ++k) P.rp.p[k] = (cparam && k < ncparam) ? cparam[k] : 0.0;
     return P;

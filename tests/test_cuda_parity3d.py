@@ -40,6 +40,14 @@ def _euler_blob(mx=20, my=14, mz=12, **kw):
     return sc
 
 
+def _euler_capa(**kw):
+    sc = _euler_blob(mx=12, my=10, mz=14, **kw)
+    X, Y, Z = np.meshgrid(*[S.centers(-1., 1., k) for k in (12, 10, 14)], indexing='ij')
+    aux = np.empty((1, 12, 10, 14), order='F')
+    aux[0] = 1.0 + 0.25 * np.sin(2 * X + Y) * np.cos(Z)
+    return dict(sc, aux=aux, index_capa=0, aux_bc_lower=sc['bc_lower'], aux_bc_upper=sc['bc_upper'])
+
+
 CASES3 = {
     'ac_unsplit_22': lambda: _ac(),
     'ac_unsplit_11': lambda: _ac(transverse_waves=11, mx=17, my=9, mz=11),
@@ -66,6 +74,13 @@ CASES3 = {
     'vcadv3_unsplit_21': lambda: S.advection_3d_variable(mx=13, my=30, mz=9, transverse_waves=21),
     'vcadv3_unsplit_11_superbee': lambda: dict(S.advection_3d_variable(mx=11, my=10, mz=31, transverse_waves=11), limiters=S.SUPERBEE),
     'vcadv3_split': lambda: S.advection_3d_variable(mx=16, my=12, mz=14, dimensional_split=True),
+    # capacity function in 3-D (step3.f90:229-273, step3ds.f90:200-205; pinned by the oracle's identities only, no
+    # reference run uses one): a third aux plane the Riemann solver does not read; an Euler run whose ONLY aux plane is it
+    'ac_capa_unsplit_22': lambda: S.acoustics_3d_capa(),
+    'ac_capa_unsplit_21_superbee': lambda: S.acoustics_3d_capa(mx=11, my=17, mz=9, transverse_waves=21, limiters=S.SUPERBEE),
+    'ac_capa_unsplit_10_o1': lambda: S.acoustics_3d_capa(mx=31, my=9, mz=12, transverse_waves=10, order=1),
+    'ac_capa_split': lambda: S.acoustics_3d_capa(mx=13, my=8, mz=11, dimensional_split=True),
+    'euler_capa_unsplit_22': lambda: _euler_capa(),
     'ac_tiny': lambda: _ac(mx=3, my=2, mz=4),
     'ac_tile_edges': lambda: _ac(mx=57, my=7, mz=13),          # 28-lane strips, 6-row tiles: ragged edges
     'ac_tile_edges2': lambda: _ac(mx=31, my=13, mz=6),

@@ -302,6 +302,13 @@ CASES_3D = {
     'acoustics_unsplit_22_aux': (lambda: S.acoustics_3d_general(mx=12, my=10, mz=9), 0, 0),
     'acoustics_unsplit_22_segments': (lambda: S.acoustics_3d_general(mx=9, my=14, mz=11), 4, 0),
     'acoustics_split': (lambda: S.acoustics_3d_general(mx=10, my=9, mz=8, dimensional_split=True), 0, 0),
+    # capacity function in 3-D (step3.f90:229-273 / 384-431 / 546-593, step3ds.f90:200-205): generic kernels only
+    'acoustics_capa_unsplit_22': (lambda: S.acoustics_3d_capa(mx=12, my=10, mz=9), 0, 0),
+    'acoustics_capa_unsplit_22_segments': (lambda: S.acoustics_3d_capa(mx=9, my=14, mz=11), 4, 0),
+    'acoustics_capa_unsplit_11_mc': (lambda: S.acoustics_3d_capa(mx=31, my=8, mz=9, transverse_waves=11, limiters=S.MC), 0, 0),
+    'acoustics_capa_unsplit_no_transverse_first_order': (lambda: S.acoustics_3d_capa(mx=10, my=9, mz=8, transverse_waves=0, order=1), 0, 0),
+    'acoustics_capa_split': (lambda: S.acoustics_3d_capa(mx=10, my=9, mz=8, dimensional_split=True), 0, 0),
+    'euler_capa_unsplit_aux_is_only_the_capacity': (lambda: _euler3_capa(), 0, 0),
     'euler_unsplit': (lambda: dict(S.euler_3d_shocktube(mx=6, my=7, mz=20), dimensional_split=False), 0, 0),
     'burgers_unsplit_11': (lambda: S.burgers_3d(mx=10, my=9, mz=8, transverse_waves=11), 0, 0),
     'vc_advection_unsplit_22': (lambda: S.advection_3d_variable(mx=9, my=8, mz=10), 0, 0),
@@ -312,6 +319,14 @@ CASES_3D = {
     'acoustics_reference_example_spec_variant5': (lambda: S.acoustics_3d(mx=10, my=10, mz=10), 0, 5),
     'acoustics_unsplit_22_spec_variant6_x_tiles_32x6': (lambda: dict(S.acoustics_3d_general(mx=30, my=11, mz=7), limiters=S.MC), 3, 6),
 }
+
+
+def _euler3_capa():
+    sc = dict(S.euler_3d_shocktube(mx=6, my=7, mz=20), dimensional_split=False)
+    X, Y, Z = np.meshgrid(*[S.centers(lo, up, k) for lo, up, k in zip(sc['lower'], sc['upper'], (6, 7, 20))], indexing='ij')
+    aux = np.empty((1, 6, 7, 20), order='F')
+    aux[0] = 1.0 + 0.2 * np.sin(3 * X + Y) * np.cos(2 * Z)
+    return dict(sc, aux=aux, index_capa=0, aux_bc_lower=sc['bc_lower'], aux_bc_upper=sc['bc_upper'])
 
 
 @pytest.mark.parametrize('name', sorted(CASES_3D))

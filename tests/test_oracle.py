@@ -437,3 +437,48 @@ def test_sill_golden(oracle_lib):
     dx, dy = s.delta
     assert dx * dy * np.sum(np.abs(s.q[0].reshape(-1) - g)) < 1e-6
     assert np.max(np.abs(s.q[0].reshape(-1) - g)) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 3-D capacity function (step3.f90:132-136, 229-273, 384-431, 546-593; step3ds.f90:142-146, 200-205): no reference test
+# or example runs it, so this branch of the oracle is PARITY-UNPINNED by reference vectors.  What pins it here are the two
+# identities the Fortran text implies: kappa == 1 is the plain scheme (up to the re-association of the update into one
+# bracket), and a constant kappa == c is the plain scheme with dt / c.
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('split', [False, True])
+def test_capacity_function_3d_identities(split):
+    base = S.acoustics_3d_general(mx=11, my=9, mz=10, dimensional_split=split)
+
+    def with_capa(kappa):
+        sc = S.acoustics_3d_capa(mx=11, my=9, mz=10, dimensional_split=split)
+        sc['aux'][2] = kappa
+        return sc
+
+    def run(sc, dt, nsteps):
+        r = ref_solver(sc)
+        r.dt_variable = False
+        r.dt = dt
+        for _ in range(nsteps):
+            r.evolve_to_time()
+        assert all(acc for _, _, acc in r.step_log)
+        return np.array(r.q, copy=True), [c for _, c, _ in r.step_log]
+
+    dt = 0.02
+    q0, cfl0 = run(base, dt, 4)
+    q1, cfl1 = run(with_capa(1.0), dt, 4)
+    assert np.max(np.abs(q1 - q0)) <= 1e-14 * np.max(np.abs(q0)) and np.allclose(cfl1, cfl0, rtol=1e-15, atol=0)
+    assert not np.array_equal(q1, q0) or split                # (the unsplit update is re-associated: not the same bits)
+    # kappa == 2 against dt / 2: exact up to rounding as long as no double-transverse term is formed (method(3) = 20:
+    # m4 = 0); the (1/6) dtdx1d dtdz terms of flux3.f90:412-450 carry ONE capacity-scaled factor and one plain dt/dz, so
+    # with method(3) = 22 the two runs differ at third order in dt -- as they do in the reference
+    tw = dict(transverse_waves=20) if not split else {}
+    qh, cflh = run(dict(base, **tw), dt / 2.0, 4)
+    q2, cfl2 = run(dict(with_capa(2.0), **tw), dt, 4)
+    assert np.max(np.abs(q2 - qh)) <= 1e-14 * np.max(np.abs(qh)) and np.allclose(cfl2, cflh, rtol=1e-15, atol=0)
+    if not split:
+        qh22, _ = run(base, dt / 2.0, 4)
+        q222, _ = run(with_capa(2.0), dt, 4)
+        assert 1e-7 < np.max(np.abs(q222 - qh22)) < 1e-3
+    # and a variable capacity changes the answer (the plane is really read)
+    qv, _ = run(S.acoustics_3d_capa(mx=11, my=9, mz=10, dimensional_split=split), dt, 4)
+    assert np.max(np.abs(qv - q0)) > 1e-3
