@@ -450,6 +450,7 @@ def run_config(ctx, args, config, n, steps, warmup, primary):
     # regime every cell of the current state gets a smooth 1e-3 perturbation (no two neighbours carry the same bits) and
     # the sweep kernel is timed again on it.
     dense_ms = None
+    dense_plain = False
     if config in ('c2', 'c3') and ctx.world == 1 and not args.no_dense:
         state = solution.state
         q = state.q
@@ -464,6 +465,9 @@ def run_config(ctx, args, config, n, steps, warmup, primary):
         _lib.check(dev.L.claw_time_sweep(dev.handle, _lib.dp(dev.delta), float(solver.dt) * 0.5, 5, ctypes.byref(dm)),
                    dev.handle)
         dense_ms = dm.value
+        dstate = (ctypes.c_int * 3)()
+        _lib.check(dev.L.claw_dense_state(dev.handle, dstate), dev.handle)
+        dense_plain = bool(dstate[1])
         del q, pert
     out = None
     if ctx.rank == 0:
@@ -514,7 +518,10 @@ def run_config(ctx, args, config, n, steps, warmup, primary):
                                  'algorithmic_flops_per_cell': round(ops.get('dense_flops', ops['flops']), 2),
                                  'peak': 2.0 * ctx.peak_gdfma / 1e3, 'unit': 'TFLOP/s',
                                  'frac': dflops / 1e9 / (2.0 * ctx.peak_gdfma),
-                                 'cell_updates_per_s': cells_local / (dense_ms * 1e-3)}
+                                 'cell_updates_per_s': cells_local / (dense_ms * 1e-3),
+                                 'kernel': ('the same kernel WITHOUT the uniform-region fast path: the dense-data switch takes it '
+                                            'when most tiles report the full path (DESIGN.md 3.1a)') if dense_plain else
+                                           'the kernel with the uniform-region fast path'}
         out = {'metric': METRICS[config], 'value': value, 'unit': UNIT, 'n_gpus': ctx.world, 'steps': attempts,
                'warmup': max(warmup, 3), 'ms_per_step': ms / attempts, 'higher_is_better': True,
                'scaling': 'weak' if config == 'c2' else 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',

@@ -79,6 +79,7 @@ def _declare(L):
         'claw_time_sweep': (i, [H, c_double_p, d, i, c_double_p]),
         'claw_launch_count': (i, [H, ctypes.POINTER(ctypes.c_uint64)]),
         'claw_last_launch_info': (i, [H, c_int_p]),
+        'claw_dense_state': (i, [H, c_int_p]),
         'claw_step2_host': (i, [i] * 7 + [vp, vp, vp, d, d, d, c_int_p, c_int_p, i, i, c_double_p, i, i, c_double_p]),
         'claw_step2ds_host': (i, [i] * 7 + [vp, vp, vp, d, d, d, c_int_p, c_int_p, i, i, i, c_double_p, i, i,
                                             c_double_p]),

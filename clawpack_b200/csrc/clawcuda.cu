@@ -72,6 +72,15 @@ struct claw_solver {
   unsigned* hot = nullptr;
   int hot_cap = 0, hot_tiles = 0;
   unsigned hot_epoch = 0;
+  // Dense-data switch (dense_update): the fast-path kernels report how many tiles took the full path; when that is most
+  // of the grid the launch code takes the kernels without the fast path (14-20 % faster there), and probes again later
+  unsigned* h_hot = nullptr;         // pinned copy of the 8 header words of `hot`
+  cudaEvent_t ev_hot = nullptr;
+  bool hot_copy_pending = false, hot_copy_from_quiet = false, dense_probe = false;
+  int dense_pref = 0;
+  long long last_ntiles = 0, dense_batches = 0;
+  int last_hot_rows = 0;
+  int time_sweep_dense = 0;          // which kernel the last claw_time_sweep timed (reported by claw_last_launch_info)
   // send / receive buffers of claw_halo_exchange (send up, receive lower, send lower, receive upper), q and aux
   double* hx[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t hx_elems = 0;
@@ -842,9 +851,11 @@ int launch_step2(claw_solver* h, double dx, double dy, double dt, int kind, int 
   for (int k = 0; k < 4; ++k) P.rp.p[k] = h->cparam[k];
   // tile ordering: full-grid launches of the device-resident path only (the chunks of the pipelined host entry points
   // are different grids on other streams)
-  if (h->hot && j0 == 0 && j1 == 0 && stream_override == nullptr) {
+  const bool full_grid = h->hot && j0 == 0 && j1 == 0 && stream_override == nullptr;
+  if (full_grid) {
     P.hot = h->hot; P.hot_cap = h->hot_cap; P.hot_tiles = h->hot_tiles;
     P.hot_epoch = h->hot_epoch++;
+    P.dense_pref = h->dense_pref;
   }
   cudaError_t e;
   if (h->rp_id >= CLAW_RP_PLUGIN_BASE) {               // user-supplied Riemann solver: its own instantiation of the kernels
@@ -859,6 +870,73 @@ int launch_step2(claw_solver* h, double dx, double dy, double dt, int kind, int 
   }
   ++h->launches;
   if (e != cudaSuccess) return fail(h, 100 + (int)e, "sweep kernel launch failed: %s", cudaGetErrorString(e));
+  if (full_grid) {                                     // what dense_update needs to read the heavy-tile counts
+    h->last_hot_rows = P.hot_rows;
+    h->last_ntiles = (long long)h->last_launch.grid_x * (h->last_launch.grid_y - P.hot_rows);
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Dense-data switch.  On data without uniform regions the kernels with the uniform-region fast path are 14-20 % slower
+// than the same kernels without it (shorter march segments, the per-step classification, the deeper
+// ring).  The fast-path kernels count their heavy tiles for the tile ordering anyway (HotTiles, sweep2_ws.cuh), so the
+// host copies the three counters after a batch of attempts -- asynchronously, consumed at the next batch without a
+// wait -- and
+//   * switches to the plain kernels when more than 60 % of the tiles were heavy,
+//   * probes with the fast-path kernels every 64th batch while in that state, and switches back below 40 %.
+// Only launches long enough for the tile ordering (several waves of CTAs) report counts; smaller grids never switch.
+// CLAW_DENSE_SWITCH=0 turns it off.  A switch re-captures the attempt graph (cfg_epoch).
+// ---------------------------------------------------------------------------------------
+bool dense_switch_enabled() {
+  static const bool on = !(getenv("CLAW_DENSE_SWITCH") && atoi(getenv("CLAW_DENSE_SWITCH")) == 0);
+  return on;
+}
+// fraction of heavy tiles in the counters copied last, or -1 when they say nothing
+double dense_fraction(const claw_solver* h) {
+  if (!h->h_hot || h->last_ntiles <= 0 || h->last_hot_rows <= 0) return -1.0;
+  unsigned mx = h->h_hot[0];
+  if (h->h_hot[1] > mx) mx = h->h_hot[1];
+  if (h->h_hot[2] > mx) mx = h->h_hot[2];
+  return (double)mx / (double)h->last_ntiles;
+}
+void dense_decide(claw_solver* h, double frac) {
+  if (frac < 0.0) return;
+  const int before = h->dense_pref;
+  if (h->dense_probe) {                                // the batch that just ran was a probe out of the dense state
+    h->dense_probe = false;
+    h->dense_pref = frac > 0.4 ? 1 : 0;
+    h->dense_batches = 0;
+    if (h->dense_pref != 0) ++h->cfg_epoch;            // (the probe ran the fast-path kernels: back to the plain ones)
+    return;
+  }
+  if (!h->dense_pref && frac > 0.6) h->dense_pref = 1;
+  if (h->dense_pref != before) { ++h->cfg_epoch; h->dense_batches = 0; }
+}
+// called before a batch of attempts is queued
+void dense_update(claw_solver* h) {
+  if (!dense_switch_enabled() || !h->hot || h->g.ndim != 2) return;
+  if (h->hot_copy_pending && cudaEventQuery(h->ev_hot) == cudaSuccess) {
+    h->hot_copy_pending = false;
+    if (h->hot_copy_from_quiet) dense_decide(h, dense_fraction(h));
+  }
+  if (h->dense_pref && !h->dense_probe && ++h->dense_batches >= 64) {       // look again: has the data become sparse?
+    h->dense_probe = true;
+    h->dense_pref = 0;
+    ++h->cfg_epoch;
+  }
+}
+// called after a batch of attempts has been queued
+int dense_collect(claw_solver* h) {
+  if (!dense_switch_enabled() || !h->hot || h->g.ndim != 2 || h->hot_copy_pending) return 0;
+  if (!h->h_hot) {
+    CK(h, cudaHostAlloc(&h->h_hot, 8 * sizeof(unsigned), cudaHostAllocDefault));
+    CK(h, cudaEventCreateWithFlags(&h->ev_hot, cudaEventDisableTiming));
+  }
+  CK(h, cudaMemcpyAsync(h->h_hot, h->hot, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaEventRecord(h->ev_hot, h->stream));
+  h->hot_copy_pending = true;
+  h->hot_copy_from_quiet = (h->dense_pref == 0);
   return 0;
 }
 
@@ -1160,6 +1238,8 @@ int claw_destroy(claw_solver* h) {
   if (h->h_cfl) cudaFreeHost(h->h_cfl);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->hot) cudaFree(h->hot);
+  if (h->h_hot) cudaFreeHost(h->h_hot);
+  if (h->ev_hot) cudaEventDestroy(h->ev_hot);
   for (int k = 0; k < 4; ++k) if (h->hx[k]) cudaFree(h->hx[k]);
   for (int r = 0; r < 64; ++r)
     for (int k = 0; k < 4; ++k) if (h->peer.opened[r][k]) cudaIpcCloseMemHandle(h->peer.opened[r][k]);
@@ -1566,6 +1646,7 @@ int claw_ctl_attempts(claw_solver* h, const double* delta, int n, int fill_ghost
     if (int rc = fill_ghosts_array(h, sel_fixed(h->aux), h->maux, h->aux_bc_lower, h->aux_bc_upper, false)) return rc;
     h->aux_ghosts_valid = true;
   }
+  dense_update(h);                                   // may switch kernels (and with it re-capture the graph below)
   bool graph_ok = h->use_graph && n >= 1;          // (a single attempt too: the graph is captured once per configuration)
   if (graph_ok) {
     bool stale = (h->graph == nullptr) || h->graph_epoch != h->cfg_epoch || h->graph_fill != (fill_ghosts ? 1 : 0);
@@ -1609,13 +1690,13 @@ int claw_ctl_attempts(claw_solver* h, const double* delta, int n, int fill_ghost
   if (graph_ok) {
     for (int k = 0; k < n; ++k) CK(h, cudaGraphLaunch(h->graph, h->stream));
     h->launches += h->graph_nodes * (uint64_t)n;
-    return 0;
+    return n > 0 ? dense_collect(h) : 0;
   }
   for (int k = 0; k < n; ++k) {
     if (int rc = ctl_enqueue_sweep(h, delta, fill_ghosts)) return rc;
     if (int rc = ctl_enqueue_end(h)) return rc;
   }
-  return 0;
+  return n > 0 ? dense_collect(h) : 0;
 }
 
 int claw_ctl_read(claw_solver* h, double* words, long long from_attempt, double* log3, int max_entries, int* n_entries) {
@@ -1995,12 +2076,28 @@ int claw_time_sweep(claw_solver* h, const double* delta, double dt, int reps, do
   cudaEvent_t a, b;
   CK(h, cudaEventCreate(&a));
   CK(h, cudaEventCreate(&b));
+  // the kernel a run on this state would settle on: one untimed launch of the fast-path kernels reports the heavy tiles,
+  // the same rule as dense_decide picks (restored afterwards: the attempt graph was captured for the saved choice)
+  const int saved_pref = h->dense_pref;
+  if (dense_switch_enabled() && h->hot && h->g.ndim == 2) {
+    h->dense_pref = 0;
+    if (int rc = launch_step(h, delta, dt, h->q[h->cur], h->q[h->cur ^ 1])) return rc;
+    if (!h->hot_copy_pending) {
+      if (int rc = dense_collect(h)) return rc;
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->hot_copy_pending = false;
+    const double frac = dense_fraction(h);
+    h->dense_pref = (frac > 0.6) ? 1 : 0;
+  }
   CK(h, cudaMemsetAsync(h->work, 0, sizeof(double), h->stream));
   CK(h, cudaEventRecord(a, h->stream));
   for (int r = 0; r < reps; ++r)
-    if (int rc = launch_step(h, delta, dt, h->q[h->cur], h->q[h->cur ^ 1])) return rc;
+    if (int rc = launch_step(h, delta, dt, h->q[h->cur], h->q[h->cur ^ 1])) { h->dense_pref = saved_pref; return rc; }
   CK(h, cudaEventRecord(b, h->stream));
   CK(h, cudaEventSynchronize(b));
+  h->time_sweep_dense = h->dense_pref;
+  h->dense_pref = saved_pref;
   float ms = 0.f;
   CK(h, cudaEventElapsedTime(&ms, a, b));
   cudaEventDestroy(a);
@@ -2013,6 +2110,12 @@ int claw_last_launch_info(const claw_solver* h, int* info5) {
   if (check_handle(h)) return 1;
   info5[0] = h->last_launch.grid_x; info5[1] = h->last_launch.grid_y; info5[2] = h->last_launch.block;
   info5[3] = h->last_launch.smem_bytes; info5[4] = h->last_launch.ctas_per_sm;
+  return 0;
+}
+
+int claw_dense_state(const claw_solver* h, int* state3) {
+  if (check_handle(h)) return 1;
+  state3[0] = h->dense_pref; state3[1] = h->time_sweep_dense; state3[2] = dense_switch_enabled() ? 1 : 0;
   return 0;
 }
 

@@ -53,7 +53,7 @@ struct StepCtl {
 };
 // layout version of StepCtl / Sweep2Params / LaunchInfo: a Riemann-solver plug-in (rp_plugin.cu) compiled against another
 // version is refused by claw_rp_plugin_load
-#define CLAW_PLUGIN_ABI 4
+#define CLAW_PLUGIN_ABI 5
 static_assert(sizeof(StepCtl) == 32 * 8, "StepCtl is mirrored by the host as 32 words");
 
 // buffer roles of a launch that runs under a StepCtl: 0 = current q, 1 = alternate q, 2 = third buffer (3-D split)
@@ -96,6 +96,9 @@ struct Sweep2Params {
   unsigned* hot;
   int hot_cap, hot_tiles, hot_rows;
   unsigned hot_epoch;       // launch number when the launch does not run under a StepCtl
+  int dense_pref;           // 1: the launch code takes the kernel WITHOUT the uniform-region fast path (the previous launches
+                            // reported most tiles heavy; clawcuda.cu: dense_update).  Last member: the offsets of the others
+                            // are those of the profiled builds.
 };
 #endif
 

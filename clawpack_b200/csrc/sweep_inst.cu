@@ -28,7 +28,7 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
     case 2:
       if (kind == 1) {
         static const int variant = getenv("CLAW_VARIANT") ? atoi(getenv("CLAW_VARIANT")) : 0;   // 1: generic kernels only (A/B timing)
-        if (variant == 2 && split_method<2>(P, 4))             // without the uniform-region fast path (A/B)
+        if ((variant == 2 || P.dense_pref) && split_method<2>(P, 4))   // without the uniform-region fast path (A/B; dense data)
           return launch_split_ws<RpAcoustics2D, 1, 16, 1, 1, 4>(P, seg_hint, num_sms, st, info);
         if (variant != 1 && split_method<2>(P, 4) && P.do_x && P.do_y)   // BASELINE config 1: MC limiter as a template argument
           return launch_split_ws<RpAcoustics2D, 1, 16, 1, 1, 4, 4>(P, seg_hint, num_sms, st, info);
@@ -48,7 +48,7 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
         // default: with the uniform-region fast path (a no-op in strict mode) and an 8-stage row ring; measured at
         // 8192^2 on the shock-bubble data (profiles/r02_g_variants.jsonl): 4.62 ms without it, 1.75 / 1.49 / 1.44 ms
         // with a 2 / 4 / 8-stage ring.  CLAW_VARIANT=2: the same kernel without the fast path (dense-data timing, A/B).
-        if (variant == 2) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
+        if (variant == 2 || P.dense_pref) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6>(P, seg_hint, num_sms, st, info);
         if (variant == 71) return launch_ws<RpEuler4Wave2DT<3>, 1, 8, MC | 1 | 6, 1, 4>(P, seg_hint, num_sms, st, info);
         // the row ring fed by TMA bulk copies (cp.async.bulk + mbarrier, one 256-byte copy per component and row issued
         // by lane 0) instead of 32 lanes x 8-byte cp.async: A/B
@@ -68,7 +68,7 @@ cudaError_t launch_sweep2(int rp_id, int kind, Sweep2Params& P, int seg_hint, in
         // Limiter known at compile time (MC on all waves, order 2: BASELINE config 3).  Measured on B200 at 16384^2
         // (profiles/r02_a_c3_variants.jsonl): generic 9.48 ms, specialised 8.97 ms; the march loop unrolled x2 was
         // slower in every combination (11.4 / 11.3 / 9.65 ms) and is gone.
-        if (variant == 2 && split_method<3>(P, 4))             // without the uniform-region fast path (A/B)
+        if ((variant == 2 || P.dense_pref) && split_method<3>(P, 4))   // without the uniform-region fast path (A/B; dense data)
           return launch_split_ws<RpShallowRoeEfix2D, 1, 16, 1, 1, 4>(P, seg_hint, num_sms, st, info);
         // Ring depth: about 50 rows in flight per SM is the optimum of the uniform-region path (16384^2, uniform data,
         // profiles/r02_s: 16 warps x 8 stages 3.01 ms, 16 x 4 2.19 ms, 16 x 2 2.72 ms, 12 x 4 2.37 ms, 8 x 8 2.14 ms,

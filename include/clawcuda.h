@@ -275,6 +275,10 @@ int claw_time_sweep(claw_solver* h, const double* delta, double dt, int reps, do
 /* geometry of the last sweep launch: grid.x, grid.y(*z), threads per CTA, dynamic shared memory bytes, resident CTAs
    per SM (occupancy calculator) -- diagnostics for bench.py / profiles */
 int claw_last_launch_info(const claw_solver* h, int* info5);
+/* Dense-data switch of the 2-D kernels with the uniform-region fast path: state3 = { 1 if the stepping
+ * currently uses the kernels WITHOUT the fast path (most tiles were heavy), 1 if the last claw_time_sweep timed those,
+ * 1 if the switch is enabled (CLAW_DENSE_SWITCH != 0) }. */
+int claw_dense_state(const claw_solver* h, int* state3);
 /* kernels launched by this handle so far (bench.py `gpu_launches`) */
 int claw_launch_count(const claw_solver* h, uint64_t* count);
 

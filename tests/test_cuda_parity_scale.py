@@ -131,3 +131,62 @@ def test_tile_ordering_forced_on_mid_size_grids():
     p = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
                        timeout=900)
     assert p.returncode == 0 and 'tile ordering parity ok' in p.stdout, p.stdout[-3000:]
+
+
+def test_dense_data_switch_on_mid_size_grids():
+    """The dense-data switch (clawcuda.cu: dense_update): on data without uniform regions the fast-path kernels report
+    (almost) every tile heavy and the stepping moves to the kernels without the fast path; on the BASELINE data it stays
+    where it is.  Both ways the run stays within the north-star tolerance of the oracle, through the switch and the graph
+    re-capture.  CLAW_TUNE=32 lets launches of mid-size grids report their tiles (read once per process: subprocess)."""
+    import subprocess
+    import sys
+    code = '''
+import sys, ctypes
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+from test_cuda_parity_scale import _ref, _rel, S
+from clawpack_b200 import _lib
+
+def run(sc, nsteps):
+    claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision='fast')
+    sol, solver = claw.solution, claw.solver
+    solver.setup(sol)
+    solver.dt = solver.dt_initial
+    states = []
+    st = (ctypes.c_int * 3)()
+    for _ in range(nsteps):
+        solver.evolve_to_time(sol)
+        _lib.check(solver._dev.L.claw_dense_state(solver._dev.handle, st), solver._dev.handle)
+        states.append(st[0])
+    q = np.array(sol.state.q, copy=True)
+    log = list(solver.step_log)
+    solver.teardown()
+    return q, log, states, st[2]
+
+def dense(sc):
+    q = sc['q']
+    idx = np.indices(q.shape[1:], sparse=True)
+    pert = 1.0 + 1e-3 * np.sin(0.37 * idx[0] + 0.11 * idx[1] + 0.5)
+    q[0] *= pert
+    q[-1] *= pert if q.shape[0] == 4 else 1.0
+    return sc
+
+for make, n in ((lambda: S.shock_bubble(mx=1024, my=768), 40), (lambda: S.radial_dam_break(mx=768, my=768), 40)):
+    for is_dense in (False, True):
+        sc = dense(make()) if is_dense else make()
+        q, log, states, enabled = run(sc, n)
+        assert enabled == 1
+        qr, logr = _ref(sc, n)
+        assert [s[2] for s in log] == [s[2] for s in logr]
+        assert np.allclose([s[0] for s in log], [s[0] for s in logr], rtol=1e-11, atol=0)
+        assert _rel(q, qr) <= 1e-10, _rel(q, qr)
+        if is_dense:
+            assert states[0] == 0 and states[-1] == 1 and 1 in states[:12], states      # switched within a few batches
+        else:
+            assert not any(states), states
+print('dense switch ok')
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CLAW_TUNE='32')
+    p = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=900)
+    assert p.returncode == 0 and 'dense switch ok' in p.stdout, p.stdout[-3000:]
