@@ -916,14 +916,21 @@ void dense_decide(claw_solver* h, double frac) {
 // called before a batch of attempts is queued
 void dense_update(claw_solver* h) {
   if (!dense_switch_enabled() || !h->hot || h->g.ndim != 2) return;
-  if (h->hot_copy_pending && cudaEventQuery(h->ev_hot) == cudaSuccess) {
+  // (the verdict of a probe is waited for -- once per probe -- so that a host that queues far ahead of the GPU does not
+  // keep running the probe's kernels on dense data for as many batches as it is ahead)
+  const bool wait = h->hot_copy_pending && h->dense_probe && h->hot_copy_from_quiet;
+  if (h->hot_copy_pending && (wait ? cudaEventSynchronize(h->ev_hot) : cudaEventQuery(h->ev_hot)) == cudaSuccess) {
     h->hot_copy_pending = false;
     if (h->hot_copy_from_quiet) dense_decide(h, dense_fraction(h));
   }
-  if (h->dense_pref && !h->dense_probe && ++h->dense_batches >= 64) {       // look again: has the data become sparse?
+  static const long long probe_every = (getenv("CLAW_DENSE_PROBE") && atoi(getenv("CLAW_DENSE_PROBE")) > 0)
+                                           ? atoi(getenv("CLAW_DENSE_PROBE")) : 64;      // (tests shorten it)
+  if (h->dense_pref && !h->dense_probe && ++h->dense_batches >= probe_every) {       // look again: has the data become sparse?
     h->dense_probe = true;
     h->dense_pref = 0;
     ++h->cfg_epoch;
+    // the plain kernels never cleared the counters: the probe must not add to what an earlier launch left behind
+    cudaMemsetAsync(h->hot, 0, 3 * sizeof(unsigned), h->stream);
   }
 }
 // called after a batch of attempts has been queued
@@ -2081,6 +2088,7 @@ int claw_time_sweep(claw_solver* h, const double* delta, double dt, int reps, do
   const int saved_pref = h->dense_pref;
   if (dense_switch_enabled() && h->hot && h->g.ndim == 2) {
     h->dense_pref = 0;
+    if (saved_pref) CK(h, cudaMemsetAsync(h->hot, 0, 3 * sizeof(unsigned), h->stream));   // (see dense_update)
     if (int rc = launch_step(h, delta, dt, h->q[h->cur], h->q[h->cur ^ 1])) return rc;
     if (!h->hot_copy_pending) {
       if (int rc = dense_collect(h)) return rc;
@@ -2116,6 +2124,12 @@ int claw_last_launch_info(const claw_solver* h, int* info5) {
 int claw_dense_state(const claw_solver* h, int* state3) {
   if (check_handle(h)) return 1;
   state3[0] = h->dense_pref; state3[1] = h->time_sweep_dense; state3[2] = dense_switch_enabled() ? 1 : 0;
+  if (getenv("CLAW_DENSE_DEBUG")) {                    // development aid: the caller passes room for 12 ints
+    state3[3] = h->dense_probe; state3[4] = h->hot_copy_pending; state3[5] = h->hot_copy_from_quiet;
+    state3[6] = h->last_hot_rows; state3[7] = (int)h->last_ntiles; state3[8] = (int)h->dense_batches;
+    state3[9] = h->h_hot ? (int)h->h_hot[0] : -1; state3[10] = h->h_hot ? (int)h->h_hot[1] : -1;
+    state3[11] = h->h_hot ? (int)h->h_hot[2] : -1;
+  }
   return 0;
 }
 

@@ -156,6 +156,7 @@ def run(sc, nsteps):
     st = (ctypes.c_int * 3)()
     for _ in range(nsteps):
         solver.evolve_to_time(sol)
+        _ = sol.t                                  # (read-back: the host does not run ahead of the GPU in this test)
         _lib.check(solver._dev.L.claw_dense_state(solver._dev.handle, st), solver._dev.handle)
         states.append(st[0])
     q = np.array(sol.state.q, copy=True)
@@ -181,12 +182,38 @@ for make, n in ((lambda: S.shock_bubble(mx=1024, my=768), 40), (lambda: S.radial
         assert np.allclose([s[0] for s in log], [s[0] for s in logr], rtol=1e-11, atol=0)
         assert _rel(q, qr) <= 1e-10, _rel(q, qr)
         if is_dense:
-            assert states[0] == 0 and states[-1] == 1 and 1 in states[:12], states      # switched within a few batches
+            assert states[0] == 0 and 1 in states[:12] and sum(states[12:]) >= len(states[12:]) // 2, states   # switched within a few
+            # batches and stays there but for the probes (every 4th batch in this test)
         else:
             assert not any(states), states
+# the way back: dense data first, then the state is replaced by the sparse BASELINE data (a host upload); the next probe
+# (every 4th batch here, CLAW_DENSE_PROBE) finds few heavy tiles and the stepping returns to the fast-path kernels
+sc = dense(S.shock_bubble(mx=1024, my=768))
+claw = S.make_claw(sc, kernel_language='CUDA', cuda_precision='fast')
+sol, solver = claw.solution, claw.solver
+solver.setup(sol)
+solver.dt = solver.dt_initial
+st = (ctypes.c_int * 3)()
+seen = []
+for _ in range(14):
+    solver.evolve_to_time(sol)
+    _ = sol.t
+    _lib.check(solver._dev.L.claw_dense_state(solver._dev.handle, st), solver._dev.handle)
+    seen.append(st[0])
+assert seen[-1] == 1 or seen[-2] == 1, seen              # dense (a probe batch may be the last one)
+sol.state.q = S.shock_bubble(mx=1024, my=768)['q']
+after = []
+for _ in range(16):
+    solver.evolve_to_time(sol)
+    _ = sol.t
+    _lib.check(solver._dev.L.claw_dense_state(solver._dev.handle, st), solver._dev.handle)
+    after.append(st[0])
+assert after[-1] == 0 and after[-2] == 0 and after[-3] == 0, (seen, after)
+assert np.isfinite(sol.state.q).all()
+solver.teardown()
 print('dense switch ok')
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, CLAW_TUNE='32')
+    env = dict(os.environ, CLAW_TUNE='32', CLAW_DENSE_PROBE='4')
     p = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
                        timeout=900)
     assert p.returncode == 0 and 'dense switch ok' in p.stdout, p.stdout[-3000:]
