@@ -428,10 +428,10 @@ __global__ void ctl_end_kernel(StepCtl* ctl, double* log) { ctl_end_body(ctl, lo
 // publishes it: two launches per attempt) was measured SLOWER, 18.0 us -- the chain "read the control block -> fill ->
 // fence -> ticket -> publish" is four dependent round trips to L2 inside one small kernel -- and was dropped.
 struct BcXY { int lo[2], up[2], lo_on[2], up_on[2], reflect[2]; BcState bx, by; };
-__global__ void bc_xy2(ArrSel sel, int ncomp, int mx, int my, int pitch, long long plane, BcXY b) {
+__global__ void bc_xy2(ArrSel sel, int ncomp, int mx, int my, int pitch, long long plane, BcXY b, long long ncell) {
   double* q = sel_array(sel);
   if (q == nullptr) return;
-  const long long ncell = 4LL * (my + 4) + 4LL * mx;
+  // ncell: 4 ghost columns x all rows [+ 4 ghost rows x the interior columns when this rank fills a y face]
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int i, j;
   if (idx >= ncell * ncomp || !bc_frame_cell(idx % ncell, mx, my, i, j)) return;
@@ -543,17 +543,19 @@ __global__ void peer_barrier_ctl_kernel(StepCtl* ctl, PeerMail pm) {
 }
 // ncomp runs of `len` doubles from my array into a neighbour's (both selected by the same role under the same StepCtl:
 // the current-buffer index is identical on every rank)
-__global__ void peer_copy_runs(ArrSel src_sel, long long src_off, long long src_stride, ArrSel dst_sel, long long dst_off,
-                               long long dst_stride, long long len, int ncomp) {
+struct PeerChannel { long long src_off; ArrSel dst; long long dst_off, dst_stride; };
+__global__ void peer_copy_runs(ArrSel src_sel, long long src_stride, PeerChannel ch0, PeerChannel ch1, long long len, int ncomp) {
+  // blockIdx.z = channel (up / down neighbour): both directions in ONE launch; blockIdx.y = component
+  const PeerChannel& ch = blockIdx.z == 0 ? ch0 : ch1;
   const double* src = sel_array(src_sel);
-  double* dst = sel_array(dst_sel);
+  double* dst = sel_array(ch.dst);
   if (src == nullptr || dst == nullptr) return;
-  src += src_off; dst += dst_off;
-  // blockIdx.y = component; 16-byte accesses when the runs allow it (row pitches are multiples of 16 doubles, so they
-  // do for every array this library allocates): the stores cross NVLink
+  src += ch.src_off; dst += ch.dst_off;
+  // 16-byte accesses when the runs allow it (row pitches are multiples of 16 doubles, so they do for every array this
+  // library allocates): the stores cross NVLink
   const int m = blockIdx.y;
   const double* s = src + m * src_stride;
-  double* d = dst + m * dst_stride;
+  double* d = dst + m * ch.dst_stride;
   const long long stride = (long long)gridDim.x * blockDim.x, k0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if ((len & 1) == 0 && ((reinterpret_cast<unsigned long long>(s) | reinterpret_cast<unsigned long long>(d)) & 15ull) == 0) {
     const double2* s2 = reinterpret_cast<const double2*>(s);
@@ -779,8 +781,12 @@ int fill_ghosts_array(claw_solver* h, ArrSel arr, int ncomp, const int* lo, cons
       b.reflect[d] = is_q ? h->reflect_index[d] : -1;     // only consulted by the BC.wall branches (solver.py:464-473)
     }
     b.bx = bc_state_of(h, 0); b.by = bc_state_of(h, 1);
-    const long long n = (4LL * g.nt[1] + 4LL * g.n[0]) * ncomp;
-    bc_xy2<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(arr, ncomp, g.n[0], g.n[1], g.pitch, g.plane, b);
+    // an inner rank of a slab decomposition fills no y face: its launch covers the ghost columns only (the x-fill of the
+    // received ghost rows included)
+    const bool y_active = (b.lo_on[1] && b.lo[1] != CLAW_BC_CUSTOM) || (b.up_on[1] && b.up[1] != CLAW_BC_CUSTOM);
+    const long long ncell = 4LL * g.nt[1] + (y_active ? 4LL * g.n[0] : 0LL);
+    const long long n = ncell * ncomp;
+    bc_xy2<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(arr, ncomp, g.n[0], g.n[1], g.pitch, g.plane, b, ncell);
     ++h->launches;
     CK(h, cudaGetLastError());
     return 0;
@@ -1550,16 +1556,19 @@ int peer_push(claw_solver* h, int role, bool aux) {
     return d;
   };
   const ArrSel src = aux ? sel_fixed(h->aux) : sel_q(h, role);
-  const dim3 blocks(grid_for((len + 1) / 2, 256), ncomp);
-  if (h->peer.up >= 0) {        // channel A: my upper interior layers [n, n+ng) -> the upper neighbour's lower ghosts [0, ng)
-    peer_copy_runs<<<blocks, 256, 0, h->stream>>>(src, (long long)g.n[last] * layer, g.plane,
-                                                  sel_remote(h->peer.up_q, h->peer.up_aux), 0, h->peer.up_plane, len, ncomp);
-    ++h->launches;
-  }
-  if (h->peer.lo >= 0) {        // channel B: my lower interior layers [ng, 2ng) -> the lower neighbour's upper ghosts
-    peer_copy_runs<<<blocks, 256, 0, h->stream>>>(src, (long long)ng * layer, g.plane,
-                                                  sel_remote(h->peer.lo_q, h->peer.lo_aux),
-                                                  (long long)(h->peer.lo_nlast + ng) * layer, h->peer.lo_plane, len, ncomp);
+  // channel A: my upper interior layers [n, n+ng) -> the upper neighbour's lower ghosts [0, ng);
+  // channel B: my lower interior layers [ng, 2ng) -> the lower neighbour's upper ghosts.  One launch for both.
+  PeerChannel ch[2];
+  int nch = 0;
+  if (h->peer.up >= 0)
+    ch[nch++] = PeerChannel{(long long)g.n[last] * layer, sel_remote(h->peer.up_q, h->peer.up_aux), 0, h->peer.up_plane};
+  if (h->peer.lo >= 0)
+    ch[nch++] = PeerChannel{(long long)ng * layer, sel_remote(h->peer.lo_q, h->peer.lo_aux),
+                            (long long)(h->peer.lo_nlast + ng) * layer, h->peer.lo_plane};
+  if (nch > 0) {
+    if (nch == 1) ch[1] = ch[0];
+    const dim3 blocks(grid_for((len + 1) / 2, 256), ncomp, nch);
+    peer_copy_runs<<<blocks, 256, 0, h->stream>>>(src, g.plane, ch[0], ch[1], len, ncomp);
     ++h->launches;
   }
   CK(h, cudaGetLastError());
